@@ -1,0 +1,204 @@
+// ORACLE — test infrastructure only (see oracle/README.md).
+// Synchronous replanning step for a whole swarm, restating the loop glue of the reference
+// (citations relative to /root/reference):
+//   src/multi_sync_simulator.cpp:190-337   update() snapshot + sequential plan() over agents
+//   src/traj_planner.cpp:99-145,344-425    plan / planImpl / planLSC
+//   src/traj_planner.cpp:829-864,699-712   obstaclePredictionWithPrevSol / ...WithCurrVel
+//   src/traj_planner.cpp:997-1016,1030-1037 initialTrajPlanningPrevSol / ...CurrVel
+//   src/traj_planner.cpp:866-878,1047-1061 prediction / initial-trajectory checks (detect only)
+//   src/traj_planner.cpp:1225-1252         generateCollisionConstraints
+//   src/traj_planner.cpp:1442-1491         generateFeasibleSFC (window shift + one new box)
+//   src/traj_planner.cpp:1548-1585         trajOptimization (failure keeps the optimizer's last
+//                                          successful trajectory and still reports SUCCESS)
+//   include/polynomial.hpp:63-121          getStateFromControlPoints at t = dt
+// Goal planning (src/traj_planner.cpp:477-608) is NOT on the path: current_goal_position is an input.
+#pragma once
+#include <thread>
+#include <vector>
+
+#include "edt.hpp"
+#include "geom.hpp"
+#include "qp.hpp"
+
+namespace orc {
+
+struct SwarmParams {
+    double dt = 0.2, w = 0.01, wT = 1.0, res = 0.1, reset_threshold = 0.15;
+    int use_octomap = 0;
+    float world_min[3] = {-5, -5, 0}, world_max[3] = {5, 5, 2.5f};
+};
+
+struct AgentConst { double radius, downwash, vmax[3], amax[3], v_nom; };
+
+enum StepFlags { FLAG_SLACK_NEEDED = 1, FLAG_SFC_SEED_BLOCKED = 2 };
+
+struct Swarm {
+    SwarmParams prm;
+    int N = 0;
+    std::vector<AgentConst> ac;
+    QpTables T;
+    const DistMap* dm = nullptr;
+    int seq = 0;                                 // planner_seq (lock-step for all agents)
+    std::vector<F3> traj;                        // [N][30] traj_curr
+    std::vector<F3> pos, vel, acc;               // current state (input of the step)
+    std::vector<F3> goal;                        // current_goal_position (input of the step)
+    std::vector<F3> box_min, box_max;            // [N][5] persistent SFC
+    std::vector<int> init_sfc;                   // flag_initialize_sfc
+    // step outputs
+    std::vector<double> qp_cost; std::vector<int> qp_status, qp_iters, qp_active, flags;
+    std::vector<double> qp_maxviol, qp_kkt;
+    std::vector<F3> pred;                        // [N][30] initial_traj == prediction seen by others
+    // optional capture of all constraints of the step (tests): [N][N][5]
+    bool capture = false;
+    std::vector<F3> cap_normal; std::vector<double> cap_d; std::vector<int> cap_gjk;
+    long long counters[4] = {0, 0, 0, 0};        // gjk iterations, qp iterations, edt lookups, qp rows
+
+    void init(const SwarmParams& p, int n_agents, const AgentConst* consts) {
+        prm = p; N = n_agents; ac.assign(consts, consts + N);
+        build_tables(p.dt, p.w, p.wT, T);
+        traj.assign((size_t)N * 30, f3(0, 0, 0));                   // traj_planner.cpp:36-39
+        pos.assign(N, f3(0, 0, 0)); vel = pos; acc = pos; goal = pos;
+        box_min.assign((size_t)N * 5, f3(0, 0, 0)); box_max = box_min;
+        init_sfc.assign(N, 1);                                      // traj_planner.cpp:49
+        qp_cost.assign(N, 0); qp_status.assign(N, 0); qp_iters.assign(N, 0); qp_active.assign(N, 0);
+        qp_maxviol.assign(N, 0); qp_kkt.assign(N, 0); flags.assign(N, 0);
+        pred.assign((size_t)N * 30, f3(0, 0, 0));
+        seq = 0;
+    }
+
+    void predict_all() {
+        for (int a = 0; a < N; a++) {
+            F3* o = &pred[(size_t)a * 30];
+            if (seq < 2) {                                          // :830, :998 (seq already incremented)
+                for (int m = 0; m < 5; m++)
+                    for (int i = 0; i < 6; i++) {
+                        double m_intp = m + (double)i / 5;
+                        o[m * 6 + i] = pos[a] + (vel[a] * (float)m_intp) * (float)prm.dt;   // :707-708
+                    }
+            } else {
+                const F3* t = &traj[(size_t)a * 30];
+                for (int m = 0; m < 4; m++) for (int i = 0; i < 6; i++) o[m * 6 + i] = t[(m + 1) * 6 + i];
+                for (int i = 0; i < 6; i++) o[24 + i] = t[29];                               // :851-855
+            }
+            if (normf(o[0] - pos[a]) > prm.reset_threshold) flags[a] |= FLAG_SLACK_NEEDED;    // :869, :1048
+        }
+    }
+
+    void plan_agent(int a, std::vector<F3>& new_traj, std::vector<LscRows>& rows_buf) {
+        const F3* own = &pred[(size_t)a * 30];
+        rows_buf.clear();
+        long long gjk_it = 0;
+        for (int j = 0; j < N; j++) {
+            if (j == a) continue;
+            LscPair lp;
+            const F3* obs = &pred[(size_t)j * 30];
+            lsc_pair(own, obs, 5, ac[a].radius, ac[a].downwash, ac[j].radius, ac[j].downwash, lp);
+            for (int m = 0; m < 5; m++) {
+                LscRows r; r.m = m;
+                r.a[0] = (double)lp.normal[m].x; r.a[1] = (double)lp.normal[m].y; r.a[2] = (double)lp.normal[m].z;
+                for (int i = 0; i < 6; i++) {
+                    const F3 o = obs[m * 6 + i];
+                    r.rhs[i] = lp.d[m][i] + ((r.a[0] * (double)o.x + r.a[1] * (double)o.y) + r.a[2] * (double)o.z);
+                }
+                rows_buf.push_back(r);
+                gjk_it += lp.gjk_iters[m];
+                if (capture) {
+                    size_t c = ((size_t)a * N + j) * 5 + m;
+                    cap_normal[c] = lp.normal[m]; cap_gjk[c] = lp.gjk_iters[m];
+                    for (int i = 0; i < 6; i++) cap_d[c * 6 + i] = lp.d[m][i];
+                }
+            }
+        }
+        // SFC (traj_planner.cpp:1451-1491)
+        const long long lk0 = tl_edt_lookups;
+        if (prm.use_octomap) {
+            Corridor cc{dm, f3(prm.world_min[0], prm.world_min[1], prm.world_min[2]),
+                        f3(prm.world_max[0], prm.world_max[1], prm.world_max[2]), prm.res};
+            F3 bmin, bmax;
+            if (init_sfc[a]) {
+                if (cc.expand_from_point(pos[a], goal[a], ac[a].radius, bmin, bmax)) {
+                    for (int m = 0; m < 5; m++) { box_min[a * 5 + m] = bmin; box_max[a * 5 + m] = bmax; }
+                } else flags[a] |= FLAG_SFC_SEED_BLOCKED;
+                init_sfc[a] = 0;
+            } else {
+                for (int m = 1; m < 5; m++) { box_min[a * 5 + m - 1] = box_min[a * 5 + m]; box_max[a * 5 + m - 1] = box_max[a * 5 + m]; }
+                if (cc.expand_from_point(traj[(size_t)a * 30 + 29], goal[a], ac[a].radius, bmin, bmax)) {
+                    box_min[a * 5 + 4] = bmin; box_max[a * 5 + 4] = bmax;
+                } else flags[a] |= FLAG_SFC_SEED_BLOCKED;
+            }
+        }
+        // QP
+        QpProblem qp;
+        for (int k = 0; k < 3; k++) { qp.s[0][k] = (double)pos[a](k); qp.s[1][k] = (double)vel[a](k); qp.s[2][k] = (double)acc[a](k); qp.goal[k] = (double)goal[a](k); }
+        qp.ts = terminal_segments(pos[a], goal[a], ac[a].v_nom, prm.dt);
+        if (qp.ts > 5) qp.ts = 5;   // reference throws (traj_optimizer.cpp:356-358); cannot occur for ideal >= 0
+        for (int k = 0; k < 3; k++)
+            for (int m = 0; m < 5; m++)
+                for (int i = 0; i < 6; i++) {
+                    int v = k * 30 + m * 6 + i;
+                    if (m == 0 && i < 3) { qp.lb[v] = -INFINITY; qp.ub[v] = INFINITY; continue; }
+                    double lo = (double)prm.world_min[k], hi = (double)prm.world_max[k];
+                    if (prm.use_octomap) {
+                        lo = std::max(lo, (double)box_min[a * 5 + m](k));
+                        hi = std::min(hi, (double)box_max[a * 5 + m](k));
+                    }
+                    qp.lb[v] = lo; qp.ub[v] = hi;
+                }
+        for (int k = 0; k < 3; k++) { qp.vmax[k] = ac[a].vmax[k]; qp.amax[k] = ac[a].amax[k]; }
+        qp.rows = rows_buf.data(); qp.n_rows = (int)rows_buf.size();
+        QpResult res;
+        qp_solve(T, qp, res);
+        qp_status[a] = res.status; qp_iters[a] = res.iters; qp_active[a] = res.n_active;
+        qp_maxviol[a] = res.max_violation; qp_kkt[a] = res.kkt_stationarity;
+        if (res.status == QP_OK) {
+            qp_cost[a] = res.cost;
+            for (int m = 0; m < 5; m++)
+                for (int i = 0; i < 6; i++)
+                    new_traj[(size_t)a * 30 + m * 6 + i] =
+                        f3((float)res.x[m * 6 + i], (float)res.x[30 + m * 6 + i], (float)res.x[60 + m * 6 + i]);
+        }
+        __atomic_fetch_add(&counters[0], gjk_it, __ATOMIC_RELAXED);
+        __atomic_fetch_add(&counters[1], (long long)res.iters, __ATOMIC_RELAXED);
+        __atomic_fetch_add(&counters[2], tl_edt_lookups - lk0, __ATOMIC_RELAXED);
+        __atomic_fetch_add(&counters[3], (long long)(450 + 6 * rows_buf.size()), __ATOMIC_RELAXED);
+    }
+
+    // one synchronous replanning step for agents [a0, a1)
+    void step(int a0, int a1, int threads) {
+        seq++;                                                         // traj_planner.cpp:127
+        std::fill(flags.begin(), flags.end(), 0);
+        if (capture) {
+            cap_normal.assign((size_t)N * N * 5, f3(0, 0, 0)); cap_d.assign((size_t)N * N * 30, 0.0); cap_gjk.assign((size_t)N * N * 5, 0);
+        }
+        predict_all();
+        std::vector<F3> new_traj = traj;
+        if (threads <= 1) {
+            std::vector<LscRows> rows;
+            for (int a = a0; a < a1; a++) plan_agent(a, new_traj, rows);
+        } else {
+            std::vector<std::thread> th;
+            for (int t = 0; t < threads; t++)
+                th.emplace_back([&, t]() {
+                    std::vector<LscRows> rows;
+                    for (int a = a0 + t; a < a1; a += threads) plan_agent(a, new_traj, rows);
+                });
+            for (auto& t : th) t.join();
+        }
+        traj.swap(new_traj);
+    }
+
+    // include/polynomial.hpp:63-121 evaluated at current_time = dt: segment 1, t = 0
+    void future_state(int a, F3& p, F3& v, F3& ac_) const {
+        const F3* c = &traj[(size_t)a * 30 + 6];
+        p = c[0];
+        F3 v0 = ((c[1] - c[0]) * 5.0f) * (float)std::pow(prm.dt, -1);
+        F3 v1 = ((c[2] - c[1]) * 5.0f) * (float)std::pow(prm.dt, -1);
+        v = v0;
+        ac_ = ((v1 - v0) * 4.0f) * (float)std::pow(prm.dt, -1);
+    }
+    void advance_states() {
+        for (int a = 0; a < N; a++) future_state(a, pos[a], vel[a], acc[a]);
+    }
+};
+
+}  // namespace orc
