@@ -1,0 +1,212 @@
+/*
+ * lscgpu.h — C ABI of the B200 replanning engine (liblscgpu.so).
+ *
+ * One engine handle plans ALL agents of one synchronous replanning step on one GPU: linear safe
+ * corridor (LSC) construction against every neighbour's predicted Bezier hull, safe flight corridor
+ * (SFC) box expansion against the octomap distance field, and the Bernstein trajectory QP.
+ * Plain pointers and sizes only; no exceptions cross this boundary; every entry point returns
+ * LSCGPU_OK (0) or a negative error code and lscgpu_last_error() describes the failure.
+ * There is no CPU fallback: every compute entry point fails with LSCGPU_ERR_CUDA when no sm_100
+ * device is usable.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the reference
+ * tree qwerty35/lsc_planner @ f4d4caf).
+ *
+ * Data conventions (same as the reference):
+ *   trajectory  float[M=5][n+1=6][3]      traj_t, include/sp_const.hpp:17 (segment, control point, xyz)
+ *   QP variable order  k*30 + m*6 + i     src/traj_optimizer.cpp:72-95,277 (axis-major)
+ *   status      PlanningReport values      include/sp_const.hpp:80-87 (SUCCESS = 5, QPFAILED = 3)
+ */
+#ifndef LSCGPU_H
+#define LSCGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LSCGPU_M 5          /* segments (horizon / dt), launch/simulation.launch:60-64 */
+#define LSCGPU_NCP 6        /* control points per segment (n = 5) */
+#define LSCGPU_TRAJ_FLOATS 90
+
+enum {
+    LSCGPU_OK = 0,
+    LSCGPU_ERR_ARG = -1,      /* bad argument / unsupported parameter (reference: std::invalid_argument) */
+    LSCGPU_ERR_CUDA = -2,     /* CUDA runtime failure or no usable device */
+    LSCGPU_ERR_IO = -3,       /* octomap file unreadable / malformed */
+    LSCGPU_ERR_NCCL = -4,
+    LSCGPU_ERR_STATE = -5     /* call order violated (e.g. octomap required but not uploaded) */
+};
+
+/* PlanningReport, include/sp_const.hpp:80-87 */
+enum {
+    LSCGPU_REPORT_INITIALIZED = 0,
+    LSCGPU_REPORT_INITTRAJGENERATIONFAILED = 1,
+    LSCGPU_REPORT_CONSTRAINTGENERATIONFAILED = 2,
+    LSCGPU_REPORT_QPFAILED = 3,
+    LSCGPU_REPORT_WAITFORROSMSG = 4,
+    LSCGPU_REPORT_SUCCESS = 5
+};
+
+/* QP solver verdict (finer than the reference, which only knows "IloException") */
+enum { LSCGPU_QP_OK = 0, LSCGPU_QP_INFEASIBLE = 1, LSCGPU_QP_MAXITER = 2 };
+
+/* per-agent flag bits of one step */
+enum {
+    LSCGPU_FLAG_SLACK_NEEDED = 1,      /* |initial_traj start - state| > reset_threshold: the reference would enter the
+                                          slack branch (src/traj_planner.cpp:866-878,1047-1061); reported, not handled */
+    LSCGPU_FLAG_SFC_SEED_BLOCKED = 2   /* expandBoxFromPoint would throw (include/corridor_constructor.hpp:35-38) */
+};
+
+/* The subset of Param (include/param.hpp, defaults src/param.cpp:4-107) that the hot path reads. */
+typedef struct lscgpu_params {
+    double dt;                     /* traj/dt              (0.2)  == multisim/time_step */
+    double control_input_weight;   /* opt/control_input_weight (0.01) */
+    double terminal_weight;        /* opt/terminal_weight  (1.0) */
+    double world_resolution;       /* world/resolution     (0.1) */
+    double reset_threshold;        /* multisim/reset_threshold (0.15) */
+    int world_use_octomap;         /* world/use_octomap: adds the SFC rows (src/traj_optimizer.cpp:409-434) */
+    float world_min[3];            /* Mission::world_min / world_max (src/mission.cpp:60-75) */
+    float world_max[3];
+    int M, n, phi, dim;            /* must be 5, 5, 3, 3 (traj/horizon 1.0, traj/n, traj/phi, world/dimension) */
+} lscgpu_params;
+
+/* Constant part of Agent (include/sp_const.hpp:153-165). */
+typedef struct lscgpu_agent_const {
+    double radius, downwash, nominal_velocity;
+    double max_vel[3], max_acc[3];
+} lscgpu_agent_const;
+
+/* What MultiSyncSimulator::update() pushes into a TrajPlanner before plan()
+ * (src/multi_sync_simulator.cpp:190-318: setCurrentState + the goal chosen by goal planning). */
+typedef struct lscgpu_agent_in {
+    float position[3], velocity[3], acceleration[3];   /* Agent::current_state */
+    float goal[3];                                      /* Agent::current_goal_position */
+} lscgpu_agent_in;
+
+/* What the simulator pulls out after plan(): getTraj(), getQPCost(), getPlanningReport(),
+ * getFutureStateMsg(dt) (include/traj_planner.hpp:76-101). */
+typedef struct lscgpu_agent_out {
+    float traj[LSCGPU_M][LSCGPU_NCP][3];
+    float next_position[3], next_velocity[3], next_acceleration[3];   /* trajectory evaluated at t = dt */
+    double qp_cost;             /* getObjValue incl. the constant of the terminal cost */
+    int32_t report;             /* PlanningReport; the reference reports SUCCESS even when the QP failed and keeps the
+                                   previous trajectory (src/traj_planner.cpp:1553-1584) — so does this field */
+    int32_t qp_status;          /* LSCGPU_QP_* */
+    int32_t qp_iterations;      /* active-set iterations */
+    int32_t qp_active;          /* active inequality rows at the solution */
+    int32_t flags;              /* LSCGPU_FLAG_* */
+    int32_t terminal_segments;  /* getTerminalSegments (src/traj_optimizer.cpp:541-548) */
+} lscgpu_agent_out;
+
+typedef struct lscgpu_engine lscgpu_engine;
+
+const char* lscgpu_last_error(void);
+int lscgpu_version(void);
+
+/* ---- lifetime ---------------------------------------------------------------------------------
+ * Replaces: N x TrajPlanner ctor + TrajOptimizer ctor (src/traj_planner.cpp:4-72, src/traj_optimizer.cpp:4-25:
+ * Q_base / Aeq_base built once) inside MultiSyncSimulator's ctor (src/multi_sync_simulator.cpp:4-81). */
+int lscgpu_create(const lscgpu_params* params, int n_agents, const lscgpu_agent_const* agents, int device,
+                  lscgpu_engine** out);
+void lscgpu_destroy(lscgpu_engine* e);
+
+/* Replaces MultiSyncSimulator::setOctomap (src/multi_sync_simulator.cpp:153-167): octomap::OcTree::readBinary +
+ * DynamicEDTOctomap(1.0, tree, world_min, world_max, false) + update(). The distance field is built on the GPU. */
+int lscgpu_set_octomap_file(lscgpu_engine* e, const char* bt_path);
+/* Same, from finest-level occupied voxel keys (signed, key - 32768), int32[n][3]. n == 0: empty map. */
+int lscgpu_set_octomap_voxels(lscgpu_engine* e, const int32_t* keys, int n);
+/* Distance-map geometry and content (DynamicEDTOctomap::getDistance = sqrt(sqdist) * res; -1 outside). */
+int lscgpu_get_distmap_info(lscgpu_engine* e, int32_t size[3], int32_t offset[3], int64_t* n_occupied);
+int lscgpu_get_distmap_sqdist(lscgpu_engine* e, uint8_t* out /* size[0]*size[1]*size[2], x-major */);
+
+/* ---- multi-GPU ---------------------------------------------------------------------------------
+ * Agents [a0, a1) are planned by this engine; all engines of the job hold a replica of every agent's previous
+ * trajectory. No counterpart in the reference (single process; agents planned sequentially,
+ * src/multi_sync_simulator.cpp:320-337). */
+int lscgpu_set_shard(lscgpu_engine* e, int a0, int a1);
+int lscgpu_nccl_unique_id(uint8_t id_out[128]);
+int lscgpu_nccl_init(lscgpu_engine* e, const uint8_t id[128], int rank, int n_ranks);
+
+/* ---- the replanning step ------------------------------------------------------------------------
+ * Replaces the loop `for qi: agents[qi]->plan(sim_current_time)` of MultiSyncSimulator::plan()
+ * (src/multi_sync_simulator.cpp:320-337), i.e. per agent TrajPlanner::planLSC (src/traj_planner.cpp:389-425):
+ * obstaclePrediction/initialTrajPlanning (prev-solution variants), generateLSC, generateFeasibleSFC,
+ * TrajOptimizer::solve. `in` and `out` are host arrays of n_agents elements (all agents, also on a sharded engine:
+ * the step ends with the all-gather, so every rank returns every agent). planner_seq is advanced by one. */
+int lscgpu_replan_batch(lscgpu_engine* e, const lscgpu_agent_in* in, lscgpu_agent_out* out);
+
+/* Device-resident variant used for kernel-level timing: the inputs are the engine's own advanced states
+ * (previous trajectories evaluated at t = dt) and the goals of the last lscgpu_replan_batch / lscgpu_set_goals.
+ * Nothing crosses PCIe. lscgpu_fetch copies the results of the last step to the host. */
+int lscgpu_set_goals(lscgpu_engine* e, const float* goals /* [n_agents][3] */);
+int lscgpu_set_states(lscgpu_engine* e, const float* pos, const float* vel, const float* acc /* [n_agents][3] each */);
+int lscgpu_replan_resident(lscgpu_engine* e);   /* enqueue only: returns without waiting for the GPU */
+int lscgpu_synchronize(lscgpu_engine* e);       /* wait for all enqueued steps; refreshes lscgpu_get_step_stats */
+int lscgpu_fetch(lscgpu_engine* e, lscgpu_agent_out* out);
+
+/* TrajPlanner::reset / fresh planners: planner_seq = 0, trajectories zero, flag_initialize_sfc = true. */
+int lscgpu_reset(lscgpu_engine* e);
+/* Restore persistent planner state (teacher-forced parity runs, checkpoint restore):
+ * traj_curr of every agent + planner_seq; SFC windows float[n_agents][5][6] (min xyz, max xyz) + flag_initialize_sfc. */
+int lscgpu_set_prev_traj(lscgpu_engine* e, const float* traj /* [n_agents][90] */, int planner_seq);
+int lscgpu_set_sfc(lscgpu_engine* e, const float* boxes, const int32_t* flag_initialize_sfc);
+int lscgpu_get_sfc(lscgpu_engine* e, float* boxes, int32_t* flag_initialize_sfc);
+int lscgpu_get_planner_seq(lscgpu_engine* e);
+
+/* Constraints of the last step, as CollisionConstraints::getLSC would return them
+ * (src/collision_constraints.cpp:362-364): for local agent `agent` and every other agent in id order,
+ * normals float[n_agents-1][5][3], margins d double[n_agents-1][5][6]. */
+int lscgpu_get_lsc(lscgpu_engine* e, int agent, float* normals, double* d);
+/* initial_traj of every agent of the last step (= the prediction its neighbours used), float[n_agents][90]. */
+int lscgpu_get_initial_traj(lscgpu_engine* e, float* out);
+
+/* ---- operator-level entry points (unit parity with the reference's classes) -------------------- */
+
+/* TrajOptimizer::solve (src/traj_optimizer.cpp:31-154) for a batch of independent problems. Inputs per problem b:
+ *   state[b][9]   pos xyz, vel xyz, acc xyz  (Agent::current_state)           goal[b][3]  current_goal_position
+ *   sfc[b][5][6]  SFC boxes (box_min xyz, box_max xyz) or NULL when !world_use_octomap
+ *   obs_offset[b], obs_offset[b+1]  range of this problem's obstacles in the LSC arrays; for obstacle o:
+ *   lsc_normal[o][5][3] (LSC::normal_vector), lsc_point[o][5][6][3] (LSC::obs_control_point), lsc_d[o][5][6] (LSC::d)
+ *   agent_index[b] selects max_vel/max_acc/nominal_velocity of a created agent.
+ * Outputs: x[b][90] in the reference's variable order, cost[b], status[b] (LSCGPU_QP_*), iterations[b]. */
+int lscgpu_qp_solve_batch(lscgpu_engine* e, int n_problems, const int32_t* agent_index, const double* state,
+                          const double* goal, const float* sfc, const int32_t* obs_offset, const float* lsc_normal,
+                          const float* lsc_point, const double* lsc_d, double* x, double* cost, int32_t* status,
+                          int32_t* iterations);
+
+/* closestPointsBetweenPointAndConvexHull(origin, hull) (include/geometry.hpp:364-394) -> gjk()
+ * (src/openGJK/openGJK.cpp:674-780) for n_hulls hulls of 6 points: hulls double[n][6][3] -> v double[n][3]
+ * (closest point of the hull to the origin), iterations int32[n]. */
+int lscgpu_gjk_batch(lscgpu_engine* e, int n_hulls, const double* hulls, double* v, int32_t* iterations);
+
+/* CorridorConstructor::expandBoxFromPoint (include/corridor_constructor.hpp:18-44) for n seeds:
+ * point/goal float[n][3], radius[n] -> box float[n][6], ok int32[n] (0: seed blocked, reference throws). */
+int lscgpu_sfc_expand_batch(lscgpu_engine* e, int n, const float* point, const float* goal, const double* radius,
+                            float* box, int32_t* ok);
+
+/* ---- instrumentation -------------------------------------------------------------------------- */
+typedef struct lscgpu_step_stats {
+    /* Totals over the steps enqueued since the previous lscgpu_synchronize / lscgpu_replan_batch return. */
+    int32_t steps;
+    float ms_total;        /* device time, first kernel of the first step to last kernel of the last (CUDA events on
+                              the engine stream) */
+    float ms_predict, ms_lsc, ms_sfc, ms_qp, ms_exchange, ms_commit;   /* per-kernel sums; 0 unless profiling is on */
+    int32_t kernel_launches;        /* kernels of this library launched */
+    int64_t lsc_pairs;              /* (agent, neighbour, segment) hull tests */
+    int64_t gjk_iterations;         /* GJK outer iterations */
+    int64_t qp_rows_priced;         /* inequality rows evaluated by the QP kernel (all local agents) */
+    int64_t qp_iterations;          /* active-set iterations (all local agents) */
+    int64_t qp_full_passes;         /* verification sweeps over the complete LSC row set (all local agents) */
+} lscgpu_step_stats;
+int lscgpu_get_step_stats(lscgpu_engine* e, lscgpu_step_stats* out);
+/* enable per-kernel event timing (event records between the kernels of every step; off by default) */
+int lscgpu_set_profiling(lscgpu_engine* e, int on);
+/* the CUDA stream all work of this engine is enqueued on (cudaStream_t as void*) */
+void* lscgpu_stream(lscgpu_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSCGPU_H */

@@ -1,0 +1,80 @@
+// Shared device-side declarations of the replanning engine (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/lscgpu.h"
+#include "qp_tables.hpp"
+
+namespace lscgpu {
+
+// ---- swarm geometry of one step ----------------------------------------------------------------
+constexpr int kTrajFloats = 90;       // [m][i][xyz]
+constexpr int kPairsPerObs = 5;       // one LSC normal per (obstacle, segment)
+
+// Per-agent constants, device copy of lscgpu_agent_const.
+struct AgentConstDev {
+    double radius, downwash, v_nom;
+    double vmax[3], amax[3];
+    int sat_index;        // which blocked-voxel table (one per distinct radius) the SFC kernel uses
+    int pad;
+};
+
+// LSC row storage of ONE agent, structure of arrays over P = 5 * (N-1) (obstacle, segment) pairs,
+// pair index p = m * n_obs + obstacle  (segment-major: neighbouring threads of the LSC kernel own
+// neighbouring obstacles, so every store below is coalesced):
+//   nrm[p]   = (a_x, a_y, a_z, 1/|a|)   float4, a = LSC normal with z un-scaled (widened to double on use)
+//   rhs[i][p] = d_i + a . o_{m,i}       double, i = 0..5   -> row:  a . c_{m,i} >= rhs[i][p]
+struct RowStore {
+    float4* nrm;          // [L][P_pad]
+    double* rhs;          // [L][6][P_pad]
+    float* dmargin;       // optional capture of d_i (float would lose bits) -> stored as double in `dcap`
+    double* dcap;         // [L][6][P_pad] safety margins d (only when capture is on), else nullptr
+    int P_pad;            // pairs per agent, padded to a multiple of 32
+};
+
+// canonical inequality row ids inside the QP kernel:
+//   [0,180)    variable bounds  ((k*5+m)*6+i)*2 + side          side 0: x >= lb, side 1: x <= ub
+//   [180,450)  dynamic limits   180 + ((k*5+m)*9+j)*2 + side    j<5 velocity, j>=5 acceleration
+//   [450, ..)  LSC              450 + p*6 + i
+constexpr int kFixedRows = 450;
+
+struct StepCounters {
+    unsigned long long rows_priced;
+    unsigned long long qp_iterations;
+    unsigned long long full_passes;
+    unsigned long long gjk_iterations;
+};
+
+// ---- small float3/double3 helpers with explicit IEEE roundings ----------------------------------
+// The reference's geometry is octomap::point3d = float32 with float arithmetic.
+// Where the rounding sequence matters for parity (predictions, normals, margins, terminal-segment count)
+// we use the _rn intrinsics so that nvcc cannot contract a*b+c into an FMA.
+struct F3 { float x, y, z; };
+struct D3 { double x, y, z; };
+
+__device__ __forceinline__ F3 f3_sub(F3 a, F3 b) { return F3{__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z)}; }
+__device__ __forceinline__ F3 f3_add(F3 a, F3 b) { return F3{__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z)}; }
+__device__ __forceinline__ F3 f3_scale(F3 a, float s) { return F3{__fmul_rn(a.x, s), __fmul_rn(a.y, s), __fmul_rn(a.z, s)}; }
+// octomath::Vector3::dot: float products and sums, returned as double
+__device__ __forceinline__ double f3_dot(F3 a, F3 b) {
+    return (double)__fadd_rn(__fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z));
+}
+__device__ __forceinline__ double d3_dot(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ D3 d3_sub(D3 a, D3 b) { return D3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ D3 d3_cross(D3 a, D3 b) {
+    return D3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_sum_int(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace lscgpu

@@ -1,0 +1,122 @@
+// Host-visible launch wrappers of the engine's kernels (definitions in the .cu files of this directory).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "device_common.cuh"
+
+namespace lscgpu {
+
+// ---- k_predict: initial trajectories / obstacle predictions, terminal segments, widened state -----------------
+struct PredictLaunch {
+    int n_agents, n_pad;           // n_pad: row length of the transposed prediction table
+    int planner_seq;               // already incremented (src/traj_planner.cpp:127)
+    double dt, reset_threshold;
+    const lscgpu_agent_in* in;     // [N]
+    const float* prev_traj;        // [N][90]
+    const AgentConstDev* consts;   // [N]
+    float* pred;                   // [N][90]    initial_traj, AoS
+    float* predT;                  // [90][n_pad] same, element-major (coalesced reads by the LSC kernel)
+    double* state9;                // [N][9]
+    double* goal3;                 // [N][3]
+    int* ts;                       // [N]
+    int* flags;                    // [N]
+};
+void launch_predict(const PredictLaunch& L, cudaStream_t s);
+
+// ---- k_lsc_build ------------------------------------------------------------------------------------------
+struct LscLaunch {
+    int n_agents, n_pad, a0, n_local;
+    const float* pred;             // [N][90]
+    const float* predT;            // [90][n_pad]
+    const AgentConstDev* consts;
+    const QpTablesDev* T;
+    const double* state9;          // [N][9]
+    const double* goal3;
+    const int* ts;
+    float4* nrm;                   // [n_local][P_pad]
+    double* rhs;                   // [n_local][6][P_pad]
+    int P_pad;
+    int* cand;                     // [n_local][cand_cap]
+    int* cand_count;               // [n_local]  (zeroed by the launcher)
+    int cand_cap;
+    double cand_threshold;         // whitened slack below which a pair enters the initial working set
+    StepCounters* counters;
+};
+void launch_lsc_build(const LscLaunch& L, cudaStream_t s);
+
+// one agent's LSCs recomputed into CollisionConstraints layout (debug / parity)
+void launch_lsc_capture(int n_agents, int agent, const float* pred, const AgentConstDev* consts, float* normals,
+                        double* d, cudaStream_t s);
+void launch_gjk_batch(int n, const double* hulls, double* v, int* iters, cudaStream_t s);
+// LSC arrays of the reference container -> row store (operator-level QP entry)
+void launch_rows_from_lsc(int n_problems, const int* obs_offset, int total_obs, const float* lsc_normal,
+                          const float* lsc_point, const double* lsc_d, float4* nrm, double* rhs, cudaStream_t s);
+
+void launch_terminal_segments(int n, const double* state9, const double* goal3, const int* agent_index,
+                              const AgentConstDev* consts, double dt, int* ts_out, cudaStream_t s);
+
+// ---- k_qp_solve -------------------------------------------------------------------------------------------
+struct QpLaunch {
+    int n_problems;
+    const QpTablesDev* T;
+    const AgentConstDev* consts;
+    const int* agent_index;        // null: agent = agent_base + b
+    int agent_base;
+    const double* state9;          // indexed by agent when agent_index == null, else by problem
+    const double* goal3;
+    const int* ts;
+    const float* boxes;            // [..][5][6] or null (no SFC rows); indexed like state9
+    float wmin[3], wmax[3];
+    const float4* nrm;
+    const double* rhs;
+    const int* obs_offset;         // batch mode: obstacles of problem b = [obs_offset[b], obs_offset[b+1]); null: swarm mode
+    int n_obs;                     // swarm mode: N-1
+    int P_pad;                     // swarm mode row pitch; batch mode: total pairs (rhs pitch)
+    int* cand; int* cand_count; int cand_cap;
+    int max_iter;
+    // outputs
+    double* x_out;                 // [n_problems][90] or null
+    double* cost_out; int* status_out; int* iters_out;   // batch mode
+    lscgpu_agent_out* out;         // swarm mode: indexed by agent
+    const float* prev_traj;        // [N][90]  (kept when the QP fails)
+    double* last_cost;             // [N]
+    const int* flags;              // [N]
+    StepCounters* counters;
+};
+void launch_qp_solve(const QpLaunch& L, cudaStream_t s);
+
+// commit: every agent's new trajectory becomes traj_curr, advanced state becomes the next resident input
+void launch_commit(int n_agents, const lscgpu_agent_out* out, float* prev_traj, lscgpu_agent_in* in, cudaStream_t s);
+
+// ---- distance field / SFC ---------------------------------------------------------------------------------
+struct DistMapDev {
+    int size[3];                   // cells per axis
+    int off[3];                    // signed key of cell 0
+    uint8_t* sqdist;               // [x][y][z] squared cell distance clamped at max_sq
+    int max_sq;
+    int* sat;                      // [n_tables][(sx+1)][(sy+1)][(sz+1)] inclusive-exclusive prefix sums of "blocked"
+    int n_tables;
+};
+void launch_edt_build(const int32_t* keys_dev, int n_keys, DistMapDev dm, const int* thresholds_dev, int n_tables,
+                      uint8_t* scratch_a, uint8_t* scratch_b, cudaStream_t s);
+
+struct SfcLaunch {
+    int n;                         // seeds
+    DistMapDev dm;
+    double res;
+    float wmin[3], wmax[3];
+    // swarm mode (mode 0): seeds from agent inputs / previous trajectories, persistent windows updated in place
+    int mode, agent_base, planner_window;
+    const lscgpu_agent_in* in;
+    const float* prev_traj;
+    const AgentConstDev* consts;
+    float* boxes;                  // [N][5][6]
+    int* init_sfc;                 // [N]
+    int* flags;                    // [N]
+    // batch mode (mode 1)
+    const float* point; const float* goal; const int* sat_index; float* box_out; int* ok_out;
+};
+void launch_sfc_expand(const SfcLaunch& L, cudaStream_t s);
+
+}  // namespace lscgpu

@@ -1,0 +1,266 @@
+// k_predict, k_lsc_build and the small glue kernels around them (sm_100a).
+#include "gjk.cuh"
+#include "kernels.hpp"
+
+namespace lscgpu {
+
+// ------------------------------------------------------------------------------------------------------------
+// k_predict — one block of 96 threads per agent; thread e < 90 owns trajectory element e = (m*6+i)*3 + axis.
+// Replaces obstaclePredictionWithPrevSol / ...WithCurrVel (src/traj_planner.cpp:829-864,699-712),
+// initialTrajPlanningPrevSol / ...CurrVel (:997-1016,1030-1037), the checks (:866-878,1047-1061, detection only)
+// and getTerminalSegments (src/traj_optimizer.cpp:541-548). Because every agent runs the same planner on the same
+// snapshot, agent j's initial trajectory IS the prediction every neighbour makes of j, so it is computed once.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(96) k_predict(PredictLaunch L) {
+    const int a = blockIdx.x;
+    const int e = threadIdx.x;
+    const lscgpu_agent_in& in = L.in[a];
+    if (e < kTrajFloats) {
+        const int axis = e % 3, cp = e / 3, m = cp / 6, i = cp % 6;
+        float val;
+        if (L.planner_seq < 2) {
+            // pos + (vel * m_intp) * dt with float3 arithmetic (octomath), m_intp = m + i/n in double
+            const double m_intp = (double)m + (double)i / (double)kN;
+            const float vel = in.velocity[axis];
+            val = __fadd_rn(in.position[axis], __fmul_rn(__fmul_rn(vel, (float)m_intp), (float)L.dt));
+        } else {
+            const float* t = L.prev_traj + (size_t)a * kTrajFloats;
+            val = (m < kM - 1) ? t[((m + 1) * 6 + i) * 3 + axis] : t[(kM * 6 - 1) * 3 + axis];
+        }
+        L.pred[(size_t)a * kTrajFloats + e] = val;
+        L.predT[(size_t)e * L.n_pad + a] = val;
+        if (e < 9) {
+            const float s = e < 3 ? in.position[e] : (e < 6 ? in.velocity[e - 3] : in.acceleration[e - 6]);
+            L.state9[(size_t)a * 9 + e] = (double)s;
+        } else if (e < 12) {
+            L.goal3[(size_t)a * 3 + (e - 9)] = (double)in.goal[e - 9];
+        }
+    }
+    __syncthreads();
+    if (e == 0) {
+        const float* o = L.pred + (size_t)a * kTrajFloats;
+        const F3 p0{o[0], o[1], o[2]}, pos{in.position[0], in.position[1], in.position[2]};
+        const F3 dlt = f3_sub(p0, pos);
+        int fl = 0;
+        if (sqrt(f3_dot(dlt, dlt)) > L.reset_threshold) fl |= LSCGPU_FLAG_SLACK_NEEDED;
+        L.flags[a] = fl;
+        const F3 g{in.goal[0], in.goal[1], in.goal[2]};
+        const F3 gd = f3_sub(g, pos);
+        const double ideal = __ddiv_rn(sqrt(f3_dot(gd, gd)), L.consts[a].v_nom);
+        const double horizon = __dmul_rn((double)kM, L.dt);
+        const double q = __ddiv_rn(__dadd_rn(__dsub_rn(horizon, ideal), 1e-9), L.dt);
+        int ts = (int)q;
+        if (ts < 1) ts = 1;
+        if (ts > kM) ts = kM;     // the reference throws here (src/traj_optimizer.cpp:356-358); unreachable for ideal >= 0
+        L.ts[a] = ts;
+    }
+}
+
+void launch_predict(const PredictLaunch& L, cudaStream_t s) { k_predict<<<L.n_agents, 96, 0, s>>>(L); }
+
+// ------------------------------------------------------------------------------------------------------------
+// k_lsc_build — grid (ceil((N-1)/128), n_local), block 128: thread = one (agent, obstacle) pair, 5 hull tests.
+// Own control points, the unconstrained QP minimiser x0 and the whitened bound lengths sit in shared memory; the
+// obstacle's control points are read from the element-major table (one coalesced 128 B line per warp per load).
+// Output: the agent's LSC rows (RowStore layout) + the initial working set of pairs whose rows are close to, or
+// violated at, x0.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_lsc_build(LscLaunch L) {
+    __shared__ float own[kTrajFloats];
+    __shared__ double x0[kNv];
+    __shared__ double inv_gn[kAx];
+    const int al = blockIdx.y;
+    const int a = L.a0 + al;
+    const int n_obs = L.n_agents - 1;
+    const int ts = L.ts[a];
+    for (int e = threadIdx.x; e < kTrajFloats; e += blockDim.x) own[e] = L.pred[(size_t)a * kTrajFloats + e];
+    for (int e = threadIdx.x; e < kNv; e += blockDim.x) {
+        const int k = e / kAx, i = e % kAx;
+        const double* s = L.state9 + (size_t)a * 9;
+        const double* Xs = L.T->Xs[ts - 1][i];
+        x0[e] = Xs[0] * s[k] + Xs[1] * s[3 + k] + Xs[2] * s[6 + k] + L.T->xg[ts - 1][i] * L.goal3[(size_t)a * 3 + k];
+    }
+    for (int e = threadIdx.x; e < kAx; e += blockDim.x) inv_gn[e] = 1.0 / L.T->gnorm[ts - 1][e];
+    __syncthreads();
+
+    const int jj = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = jj < n_obs;
+    const int j = live ? (jj < a ? jj : jj + 1) : a;
+    const AgentConstDev ca = L.consts[a], cj = L.consts[j];
+    const double downwash = (ca.downwash * ca.radius + cj.downwash * cj.radius) / (ca.radius + cj.radius);
+    const double collision_dist = cj.radius + ca.radius;
+    float4* nrm_out = L.nrm + (size_t)al * L.P_pad;
+    double* rhs_out = L.rhs + (size_t)al * 6 * L.P_pad;
+    int gjk_it = 0;
+#pragma unroll 1
+    for (int m = 0; m < kM && live; m++) {
+        F3 ow[6], ob[6];
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            const int e = (m * 6 + i) * 3;
+            ow[i] = F3{own[e], own[e + 1], own[e + 2]};
+            ob[i] = F3{L.predT[(size_t)e * L.n_pad + j], L.predT[(size_t)(e + 1) * L.n_pad + j],
+                       L.predT[(size_t)(e + 2) * L.n_pad + j]};
+        }
+        LscSegment seg;
+        lsc_segment(ow, ob, downwash, collision_dist, seg);
+        gjk_it += seg.iterations;
+        const double ax = (double)seg.normal.x, ay = (double)seg.normal.y, az = (double)seg.normal.z;
+        const double an = sqrt(ax * ax + ay * ay + az * az);
+        const float inv_an = an > 0.0 ? (float)(1.0 / an) : INFINITY;
+        const int p = m * n_obs + jj;
+        nrm_out[p] = make_float4(seg.normal.x, seg.normal.y, seg.normal.z, inv_an);
+        double mu_min = INFINITY;
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            // row  a . c_{m,i} >= d_i + a . o_{m,i}      (src/traj_optimizer.cpp:437-466)
+            const double rhs = seg.d[i] + (__dmul_rn(ax, (double)ob[i].x) + __dmul_rn(ay, (double)ob[i].y) +
+                                           __dmul_rn(az, (double)ob[i].z));
+            rhs_out[(size_t)i * L.P_pad + p] = rhs;
+            if (m == 0 && i < kPhi) continue;
+            const int vi = m * 6 + i;
+            const double slack = ax * x0[vi] + ay * x0[kAx + vi] + az * x0[2 * kAx + vi] - rhs;
+            const double mu = slack * (double)inv_an * inv_gn[vi];
+            mu_min = fmin(mu_min, mu);
+        }
+        if (!(mu_min >= L.cand_threshold)) {
+            const int slot = atomicAdd(L.cand_count + al, 1);
+            if (slot < L.cand_cap) L.cand[(size_t)al * L.cand_cap + slot] = p;
+        }
+    }
+    if (L.counters) {
+        // one atomic per warp
+        const int tot = warp_sum_int(gjk_it);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&L.counters->gjk_iterations, (unsigned long long)tot);
+    }
+}
+
+void launch_lsc_build(const LscLaunch& L, cudaStream_t s) {
+    const int n_obs = L.n_agents - 1;
+    if (n_obs <= 0 || L.n_local <= 0) return;
+    dim3 grid((n_obs + 127) / 128, L.n_local);
+    k_lsc_build<<<grid, 128, 0, s>>>(L);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Debug / parity: CollisionConstraints::getLSC layout for one agent.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_lsc_capture(int n_agents, int a, const float* pred, const AgentConstDev* consts, float* normals,
+                              double* d) {
+    const int jj = blockIdx.x * blockDim.x + threadIdx.x;
+    if (jj >= n_agents - 1) return;
+    const int j = jj < a ? jj : jj + 1;
+    const AgentConstDev ca = consts[a], cj = consts[j];
+    const double downwash = (ca.downwash * ca.radius + cj.downwash * cj.radius) / (ca.radius + cj.radius);
+    for (int m = 0; m < kM; m++) {
+        F3 ow[6], ob[6];
+        for (int i = 0; i < 6; i++) {
+            const float* po = pred + (size_t)a * kTrajFloats + (m * 6 + i) * 3;
+            const float* pj = pred + (size_t)j * kTrajFloats + (m * 6 + i) * 3;
+            ow[i] = F3{po[0], po[1], po[2]};
+            ob[i] = F3{pj[0], pj[1], pj[2]};
+        }
+        LscSegment seg;
+        lsc_segment(ow, ob, downwash, cj.radius + ca.radius, seg);
+        float* no = normals + ((size_t)jj * kM + m) * 3;
+        no[0] = seg.normal.x; no[1] = seg.normal.y; no[2] = seg.normal.z;
+        for (int i = 0; i < 6; i++) d[((size_t)jj * kM + m) * 6 + i] = seg.d[i];
+    }
+}
+void launch_lsc_capture(int n_agents, int agent, const float* pred, const AgentConstDev* consts, float* normals,
+                        double* d, cudaStream_t s) {
+    if (n_agents < 2) return;
+    k_lsc_capture<<<(n_agents - 1 + 63) / 64, 64, 0, s>>>(n_agents, agent, pred, consts, normals, d);
+}
+
+__global__ void k_gjk_batch(int n, const double* hulls, double* v_out, int* iters) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    D3 P[6];
+    for (int i = 0; i < 6; i++) P[i] = D3{hulls[(size_t)t * 18 + 3 * i], hulls[(size_t)t * 18 + 3 * i + 1], hulls[(size_t)t * 18 + 3 * i + 2]};
+    D3 v;
+    const int it = gjk_origin_hull6(P, v);
+    v_out[(size_t)t * 3] = v.x; v_out[(size_t)t * 3 + 1] = v.y; v_out[(size_t)t * 3 + 2] = v.z;
+    iters[t] = it;
+}
+void launch_gjk_batch(int n, const double* hulls, double* v, int* iters, cudaStream_t s) {
+    if (n <= 0) return;
+    k_gjk_batch<<<(n + 127) / 128, 128, 0, s>>>(n, hulls, v, iters);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Row store from the reference's LSC container (operator-level QP entry, lscgpu_qp_solve_batch).
+// Pair layout inside problem b with n_b obstacles: p = m * n_b + o, stored at pair offset 5 * obs_offset[b].
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_rows_from_lsc(int n_problems, const int* obs_offset, int total_obs, const float* lsc_normal,
+                                const float* lsc_point, const double* lsc_d, float4* nrm, double* rhs) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;     // global (obstacle, segment)
+    if (t >= total_obs * kM) return;
+    const int o = t / kM, m = t % kM;
+    // find the problem of obstacle o (few problems: linear scan is fine for an operator-level entry)
+    int b = 0;
+    while (b + 1 < n_problems && obs_offset[b + 1] <= o) b++;
+    const int n_b = obs_offset[b + 1] - obs_offset[b];
+    const int p = kM * obs_offset[b] + m * n_b + (o - obs_offset[b]);
+    const size_t pitch = (size_t)total_obs * kM;
+    const float* nv = lsc_normal + ((size_t)o * kM + m) * 3;
+    const double ax = (double)nv[0], ay = (double)nv[1], az = (double)nv[2];
+    const double an = sqrt(ax * ax + ay * ay + az * az);
+    nrm[p] = make_float4(nv[0], nv[1], nv[2], an > 0.0 ? (float)(1.0 / an) : INFINITY);
+    for (int i = 0; i < 6; i++) {
+        const float* pt = lsc_point + (((size_t)o * kM + m) * 6 + i) * 3;
+        rhs[(size_t)i * pitch + p] = lsc_d[((size_t)o * kM + m) * 6 + i] +
+            (__dmul_rn(ax, (double)pt[0]) + __dmul_rn(ay, (double)pt[1]) + __dmul_rn(az, (double)pt[2]));
+    }
+}
+void launch_rows_from_lsc(int n_problems, const int* obs_offset, int total_obs, const float* lsc_normal,
+                          const float* lsc_point, const double* lsc_d, float4* nrm, double* rhs, cudaStream_t s) {
+    if (total_obs <= 0) return;
+    const int n = total_obs * kM;
+    k_rows_from_lsc<<<(n + 127) / 128, 128, 0, s>>>(n_problems, obs_offset, total_obs, lsc_normal, lsc_point, lsc_d, nrm, rhs);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// k_commit — after the (all-gathered) results are complete: traj_curr <- new trajectory, and the advanced state
+// becomes the input of a device-resident next step (MultiSyncSimulator::update(), src/multi_sync_simulator.cpp:203).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_commit(int n_agents, const lscgpu_agent_out* out, float* prev_traj, lscgpu_agent_in* in) {
+    const int a = blockIdx.x;
+    const int e = threadIdx.x;
+    const lscgpu_agent_out& o = out[a];
+    if (e < kTrajFloats) prev_traj[(size_t)a * kTrajFloats + e] = (&o.traj[0][0][0])[e];
+    if (e < 3) {
+        in[a].position[e] = o.next_position[e];
+        in[a].velocity[e] = o.next_velocity[e];
+        in[a].acceleration[e] = o.next_acceleration[e];
+    }
+}
+void launch_commit(int n_agents, const lscgpu_agent_out* out, float* prev_traj, lscgpu_agent_in* in, cudaStream_t s) {
+    k_commit<<<n_agents, 96, 0, s>>>(n_agents, out, prev_traj, in);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// getTerminalSegments (src/traj_optimizer.cpp:541-548) for the operator-level QP entry: float3 norm of
+// goal - position, double division by the nominal velocity.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_terminal_segments(int n, const double* state9, const double* goal3, const int* agent_index,
+                                    const AgentConstDev* consts, double dt, int* ts_out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    const F3 pos{(float)state9[(size_t)b * 9], (float)state9[(size_t)b * 9 + 1], (float)state9[(size_t)b * 9 + 2]};
+    const F3 g{(float)goal3[(size_t)b * 3], (float)goal3[(size_t)b * 3 + 1], (float)goal3[(size_t)b * 3 + 2]};
+    const F3 gd = f3_sub(g, pos);
+    const double ideal = __ddiv_rn(sqrt(f3_dot(gd, gd)), consts[agent_index[b]].v_nom);
+    const double q = __ddiv_rn(__dadd_rn(__dsub_rn(__dmul_rn((double)kM, dt), ideal), 1e-9), dt);
+    int ts = (int)q;
+    if (ts < 1) ts = 1;
+    if (ts > kM) ts = kM;
+    ts_out[b] = ts;
+}
+void launch_terminal_segments(int n, const double* state9, const double* goal3, const int* agent_index,
+                              const AgentConstDev* consts, double dt, int* ts_out, cudaStream_t s) {
+    if (n <= 0) return;
+    k_terminal_segments<<<(n + 127) / 128, 128, 0, s>>>(n, state9, goal3, agent_index, consts, dt, ts_out);
+}
+
+}  // namespace lscgpu

@@ -1,0 +1,238 @@
+"""Thin Python binding of the C-ABI engine (used by tests/, bench.py and __graft_entry__).
+
+The product's host side is C++ (lsc_planner_b200/host/, mirroring the reference's TrajPlanner / TrajOptimizer /
+MultiSyncSimulator); this module only marshals numpy arrays into include/lscgpu.h calls.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _capi as A
+
+
+@dataclass
+class Param:
+    """The hot-path subset of the reference's Param (include/param.hpp; defaults launch/simulation.launch)."""
+    dt: float = 0.2
+    control_input_weight: float = 0.01
+    terminal_weight: float = 1.0
+    world_resolution: float = 0.1
+    reset_threshold: float = 0.15
+    world_use_octomap: bool = False
+    world_min: Sequence[float] = (-5.0, -5.0, 0.0)
+    world_max: Sequence[float] = (5.0, 5.0, 2.5)
+    M: int = 5
+    n: int = 5
+    phi: int = 3
+    dim: int = 3
+
+    def to_c(self) -> A.Params:
+        p = A.Params()
+        p.dt, p.control_input_weight, p.terminal_weight = self.dt, self.control_input_weight, self.terminal_weight
+        p.world_resolution, p.reset_threshold = self.world_resolution, self.reset_threshold
+        p.world_use_octomap = int(self.world_use_octomap)
+        for k in range(3):
+            p.world_min[k] = float(np.float32(self.world_min[k])); p.world_max[k] = float(np.float32(self.world_max[k]))
+        p.M, p.n, p.phi, p.dim = self.M, self.n, self.phi, self.dim
+        return p
+
+
+@dataclass
+class AgentType:
+    """Constant part of the reference's Agent (include/sp_const.hpp:153-165); defaults = `crazyflie` quadrotor."""
+    radius: float = 0.15
+    downwash: float = 2.0
+    nominal_velocity: float = 1.0
+    max_vel: Sequence[float] = (1.0, 1.0, 1.0)
+    max_acc: Sequence[float] = (2.0, 2.0, 2.0)
+
+
+class ReplanEngine:
+    """One GPU's replanning engine for a swarm of `n_agents` (include/lscgpu.h)."""
+
+    def __init__(self, n_agents: int, param: Optional[Param] = None, agents: Optional[Sequence[AgentType]] = None,
+                 device: int = 0):
+        self.lib = A.lib()
+        self.n = int(n_agents)
+        self.param = param or Param()
+        agents = list(agents) if agents is not None else [AgentType()] * self.n
+        if len(agents) != self.n:
+            raise ValueError("one AgentType per agent")
+        arr = (A.AgentConst * self.n)()
+        for i, a in enumerate(agents):
+            arr[i].radius, arr[i].downwash, arr[i].nominal_velocity = a.radius, a.downwash, a.nominal_velocity
+            for k in range(3):
+                arr[i].max_vel[k] = a.max_vel[k]; arr[i].max_acc[k] = a.max_acc[k]
+        self.agents = agents
+        h = A.ptr()
+        cp = self.param.to_c()
+        A.check(self.lib.lscgpu_create(C.byref(cp), self.n, arr, device, C.byref(h)))
+        self.h = h
+        self.a0, self.a1 = 0, self.n
+        self._in = np.zeros(self.n, A.AGENT_IN)
+        self._out = np.zeros(self.n, A.AGENT_OUT)
+
+    # ---- lifetime ------------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.lscgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- map -----------------------------------------------------------------------------------------------
+    def set_octomap_file(self, path: str):
+        A.check(self.lib.lscgpu_set_octomap_file(self.h, path.encode()))
+
+    def set_octomap_voxels(self, keys):
+        keys = np.ascontiguousarray(keys, np.int32).reshape(-1, 3)
+        A.check(self.lib.lscgpu_set_octomap_voxels(self.h, A.p(keys), len(keys)))
+
+    def distmap(self):
+        size = np.zeros(3, np.int32); off = np.zeros(3, np.int32); nocc = np.zeros(1, np.int64)
+        A.check(self.lib.lscgpu_get_distmap_info(self.h, A.p(size), A.p(off), A.p(nocc)))
+        sq = np.zeros(tuple(size), np.uint8)
+        A.check(self.lib.lscgpu_get_distmap_sqdist(self.h, A.p(sq)))
+        return dict(size=size, off=off, n_occupied=int(nocc[0]), sqdist=sq)
+
+    # ---- sharding ------------------------------------------------------------------------------------------
+    def set_shard(self, a0: int, a1: int):
+        A.check(self.lib.lscgpu_set_shard(self.h, a0, a1)); self.a0, self.a1 = a0, a1
+
+    def nccl_unique_id(self) -> bytes:
+        buf = np.zeros(128, np.uint8)
+        A.check(self.lib.lscgpu_nccl_unique_id(A.p(buf)))
+        return buf.tobytes()
+
+    def nccl_init(self, unique_id: bytes, rank: int, n_ranks: int):
+        buf = np.frombuffer(unique_id, np.uint8).copy()
+        A.check(self.lib.lscgpu_nccl_init(self.h, A.p(buf), rank, n_ranks))
+        block = (self.n + n_ranks - 1) // n_ranks
+        self.a0 = min(self.n, rank * block); self.a1 = min(self.n, self.a0 + block)
+
+    # ---- stepping ------------------------------------------------------------------------------------------
+    def replan(self, pos, vel, acc, goal, out: Optional[np.ndarray] = None, inp: Optional[np.ndarray] = None):
+        """One synchronous replanning step with host inputs (H2D + kernels + D2H). Returns the AGENT_OUT array."""
+        inp = self._in if inp is None else inp
+        inp["position"] = pos; inp["velocity"] = vel; inp["acceleration"] = acc; inp["goal"] = goal
+        return self.replan_raw(inp, out)
+
+    def replan_raw(self, inp: np.ndarray, out: Optional[np.ndarray] = None):
+        out = self._out if out is None else out
+        A.check(self.lib.lscgpu_replan_batch(self.h, A.p(inp), A.p(out)))
+        return out
+
+    def replan_ptr(self, in_ptr: int, out_ptr: int):
+        """Same, on raw host addresses (e.g. pinned torch tensors)."""
+        A.check(self.lib.lscgpu_replan_batch(self.h, A.ptr(in_ptr), A.ptr(out_ptr)))
+
+    def set_goals(self, goal):
+        g = np.ascontiguousarray(goal, np.float32).reshape(self.n, 3)
+        A.check(self.lib.lscgpu_set_goals(self.h, A.p(g)))
+
+    def set_states(self, pos, vel=None, acc=None):
+        pos = np.ascontiguousarray(pos, np.float32).reshape(self.n, 3)
+        vel = np.zeros_like(pos) if vel is None else np.ascontiguousarray(vel, np.float32).reshape(self.n, 3)
+        acc = np.zeros_like(pos) if acc is None else np.ascontiguousarray(acc, np.float32).reshape(self.n, 3)
+        A.check(self.lib.lscgpu_set_states(self.h, A.p(pos), A.p(vel), A.p(acc)))
+
+    def replan_resident(self, steps: int = 1, sync: bool = True):
+        """Enqueue `steps` device-resident closed-loop steps (inputs = the engine's own advanced states)."""
+        for _ in range(steps):
+            A.check(self.lib.lscgpu_replan_resident(self.h))
+        if sync:
+            self.synchronize()
+
+    def synchronize(self):
+        A.check(self.lib.lscgpu_synchronize(self.h))
+
+    def fetch(self, out: Optional[np.ndarray] = None):
+        out = self._out if out is None else out
+        A.check(self.lib.lscgpu_fetch(self.h, A.p(out)))
+        return out
+
+    def reset(self):
+        A.check(self.lib.lscgpu_reset(self.h))
+
+    def set_prev_traj(self, traj, planner_seq: int):
+        t = np.ascontiguousarray(traj, np.float32).reshape(self.n, 90)
+        A.check(self.lib.lscgpu_set_prev_traj(self.h, A.p(t), planner_seq))
+
+    def set_sfc(self, boxes, init_flags):
+        b = np.ascontiguousarray(boxes, np.float32).reshape(self.n, 30)
+        f = np.ascontiguousarray(init_flags, np.int32).reshape(self.n)
+        A.check(self.lib.lscgpu_set_sfc(self.h, A.p(b), A.p(f)))
+
+    def get_sfc(self):
+        b = np.zeros((self.n, 5, 6), np.float32); f = np.zeros(self.n, np.int32)
+        A.check(self.lib.lscgpu_get_sfc(self.h, A.p(b), A.p(f)))
+        return b, f
+
+    @property
+    def planner_seq(self) -> int:
+        return self.lib.lscgpu_get_planner_seq(self.h)
+
+    def get_lsc(self, agent: int):
+        """(normals [N-1][5][3] float32, d [N-1][5][6] float64) of the last step, CollisionConstraints layout."""
+        nr = np.zeros((max(self.n - 1, 0), 5, 3), np.float32); d = np.zeros((max(self.n - 1, 0), 5, 6), np.float64)
+        A.check(self.lib.lscgpu_get_lsc(self.h, agent, A.p(nr), A.p(d)))
+        return nr, d
+
+    def initial_traj(self):
+        out = np.zeros((self.n, 5, 6, 3), np.float32)
+        A.check(self.lib.lscgpu_get_initial_traj(self.h, A.p(out)))
+        return out
+
+    # ---- operator-level entries ----------------------------------------------------------------------------
+    def qp_solve_batch(self, agent_index, state, goal, obs_offset, lsc_normal, lsc_point, lsc_d, sfc=None):
+        """TrajOptimizer::solve for a batch. Returns dict(x [B][90], cost, status, iterations)."""
+        ai = np.ascontiguousarray(agent_index, np.int32); nb = len(ai)
+        st = np.ascontiguousarray(state, np.float64).reshape(nb, 9)
+        gl = np.ascontiguousarray(goal, np.float64).reshape(nb, 3)
+        off = np.ascontiguousarray(obs_offset, np.int32)
+        assert len(off) == nb + 1
+        tot = int(off[-1])
+        nr = np.ascontiguousarray(lsc_normal, np.float32).reshape(tot, 5, 3)
+        pt = np.ascontiguousarray(lsc_point, np.float32).reshape(tot, 5, 6, 3)
+        dd = np.ascontiguousarray(lsc_d, np.float64).reshape(tot, 5, 6)
+        bx = None if sfc is None else np.ascontiguousarray(sfc, np.float32).reshape(nb, 30)
+        x = np.zeros((nb, 90)); cost = np.zeros(nb); status = np.zeros(nb, np.int32); iters = np.zeros(nb, np.int32)
+        A.check(self.lib.lscgpu_qp_solve_batch(self.h, nb, A.p(ai), A.p(st), A.p(gl), None if bx is None else A.p(bx),
+                                               A.p(off), A.p(nr), A.p(pt), A.p(dd), A.p(x), A.p(cost), A.p(status),
+                                               A.p(iters)))
+        return dict(x=x, cost=cost, status=status, iterations=iters)
+
+    def gjk_batch(self, hulls):
+        h = np.ascontiguousarray(hulls, np.float64).reshape(-1, 6, 3); n = len(h)
+        v = np.zeros((n, 3)); it = np.zeros(n, np.int32)
+        A.check(self.lib.lscgpu_gjk_batch(self.h, n, A.p(h), A.p(v), A.p(it)))
+        return v, it
+
+    def sfc_expand_batch(self, point, goal, radius=None):
+        pt = np.ascontiguousarray(point, np.float32).reshape(-1, 3); n = len(pt)
+        gl = np.ascontiguousarray(goal, np.float32).reshape(n, 3)
+        r = np.full(n, self.agents[0].radius) if radius is None else np.ascontiguousarray(radius, np.float64).reshape(n)
+        box = np.zeros((n, 6), np.float32); ok = np.zeros(n, np.int32)
+        A.check(self.lib.lscgpu_sfc_expand_batch(self.h, n, A.p(pt), A.p(gl), A.p(r), A.p(box), A.p(ok)))
+        return box, ok
+
+    # ---- instrumentation -----------------------------------------------------------------------------------
+    def set_profiling(self, on: bool):
+        A.check(self.lib.lscgpu_set_profiling(self.h, int(on)))
+
+    def step_stats(self) -> dict:
+        s = A.StepStats()
+        A.check(self.lib.lscgpu_get_step_stats(self.h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in A.StepStats._fields_}
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.lscgpu_stream(self.h) or 0)

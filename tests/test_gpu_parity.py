@@ -1,0 +1,272 @@
+"""GPU parity: the CUDA path (through the C-ABI) against the CPU oracle and the committed golden fixtures.
+
+Tolerances:
+  GJK closest point      <= 1e-9 m vs the reference's own openGJK outputs (golden/gjk_ref_vectors.npz)
+  distance field, SFC    bit-exact (integer squared distances; boxes compared as float32 bit patterns)
+  LSC normals / margins  <= 1e-6 (float32 normals; in practice bit-identical)
+  QP                     trajectory <= 1e-6 m, relative objective gap <= 1e-6, status identical
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+WMIN, WMAX = [-5, -5, 0], [5, 5, 2.5]
+
+
+def _engine(n, **kw):
+    import lsc_planner_b200 as L
+    agents = kw.pop("agents", None)
+    return L.ReplanEngine(n, L.Param(**kw), agents)
+
+
+@pytest.fixture(scope="module")
+def forest_path(golden_dir):
+    return os.path.join(golden_dir, "worlds", "simple_forest.bt")
+
+
+# ---------------------------------------------------------------------------------------------------------
+def test_gjk_matches_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "gjk_ref_vectors.npz"))
+    e = _engine(2)
+    v, it = e.gjk_batch(g["hulls"])
+    assert ((it >= 1) & (it <= 25)).all()
+    assert np.abs(v - g["v"]).max() <= 1e-9
+    assert np.abs(np.linalg.norm(v, axis=1) - g["dist"]).max() <= 1e-9
+    # and against the oracle on fresh random hulls (float32-representable, as the planner feeds them)
+    rng = np.random.default_rng(11)
+    H = (rng.normal(size=(2000, 6, 3)) * rng.choice([0.05, 1.0, 4.0], size=(2000, 1, 1)) +
+         rng.normal(size=(2000, 1, 3)) * rng.choice([0.0, 2.0, 8.0], size=(2000, 1, 1))).astype(np.float32).astype(np.float64)
+    v, _ = e.gjk_batch(H)
+    vo = np.array([O.gjk(h)[0] for h in H])
+    assert np.abs(v - vo).max() <= 1e-9
+
+
+def test_distance_field_bit_exact(forest_path):
+    e = _engine(2, world_use_octomap=True, world_min=WMIN, world_max=WMAX)
+    e.set_octomap_file(forest_path)
+    dm = e.distmap()
+    om = O.Map.from_bt(forest_path, WMIN, WMAX)
+    assert list(dm["size"]) == list(om.size) == [101, 101, 26] and list(dm["off"]) == list(om.off)
+    assert dm["n_occupied"] == om.n_occ == 4384
+    assert np.array_equal(dm["sqdist"].astype(np.int32), om.sqdist())
+    # voxel-list upload gives the same field
+    e2 = _engine(2, world_use_octomap=True, world_min=WMIN, world_max=WMAX)
+    e2.set_octomap_voxels(om.occupied())
+    assert np.array_equal(e2.distmap()["sqdist"], dm["sqdist"])
+
+
+def test_sfc_expand_bit_exact(forest_path):
+    e = _engine(2, world_use_octomap=True, world_min=WMIN, world_max=WMAX)
+    e.set_octomap_file(forest_path)
+    om = O.Map.from_bt(forest_path, WMIN, WMAX)
+    rng = np.random.default_rng(3)
+    n = 300
+    pts = rng.uniform([-4.9, -4.9, 0.05], [4.9, 4.9, 2.45], size=(n, 3)).astype(np.float32)
+    pts[:60] = np.round(pts[:60] * 10) / 10            # lattice seeds (degenerate initial boxes)
+    pts[60:90, 2] = np.round(pts[60:90, 2] * 10) / 10
+    gls = rng.uniform([-4.9, -4.9, 0.05], [4.9, 4.9, 2.45], size=(n, 3)).astype(np.float32)
+    box, ok = e.sfc_expand_batch(pts, gls)
+    n_ok = 0
+    for i in range(n):
+        oko, bo, _ = om.sfc_expand(pts[i], gls[i])
+        assert bool(ok[i]) == oko, i
+        if oko:
+            n_ok += 1
+            assert np.array_equal(box[i].view(np.uint32), bo.view(np.uint32)), (i, box[i], bo)
+    assert n_ok > 150
+    # empty map: the box fills the world
+    e3 = _engine(2, world_use_octomap=True, world_min=WMIN, world_max=WMAX)
+    e3.set_octomap_voxels(np.zeros((0, 3), np.int32))
+    box, ok = e3.sfc_expand_batch([[1.03, -2.0, 1.0]], [[3, 3, 1]])
+    assert ok[0] == 1 and np.allclose(box[0], [-5, -5, 0, 5, 5, 2.5], atol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def _lp_problem(g, skip=None):
+    keep = [r for r in range(len(g["rows_m"])) if skip is None or r // 5 != skip]
+    n_obs = len(keep) // 5
+    normal = np.zeros((n_obs, 5, 3), np.float32); point = np.zeros((n_obs, 5, 6, 3), np.float32); d = np.zeros((n_obs, 5, 6))
+    rows = []
+    for t, r in enumerate(keep):
+        o, m = t // 5, int(g["rows_m"][r])
+        assert m == t % 5
+        normal[o, m] = g["rows_a"][r]                   # float32-representable (widened floats in the LP dump)
+        d[o, m] = g["rows_rhs"][r]                      # obstacle point = origin -> rhs = d
+        rows.append((m, g["rows_a"][r], g["rows_rhs"][r]))
+    return normal, point, d, rows
+
+
+def test_qp_on_reference_lp_dump(golden_dir):
+    """log/QPmodel.lp (the reference's only recorded QP): INFEASIBLE like CPLEX said; solvable without the
+    conflicting neighbour, where the engine must match the oracle and the independent NNLS solve."""
+    import lsc_planner_b200 as L
+    import qp_pyref as R
+    g = np.load(os.path.join(golden_dir, "qpmodel_lp.npz"))
+    agents = [L.AgentType(max_vel=tuple(g["vmax"]), max_acc=tuple(g["amax"]))]
+    lb, ub = g["lb"], g["ub"]
+    wmin = [lb[3], lb[33], lb[63]]; wmax = [ub[3], ub[33], ub[63]]
+    e = _engine(1, agents=agents, world_min=wmin, world_max=wmax)
+    T = O.Tables()
+    for skip, expect in ((None, 1), (3, 0)):
+        normal, point, d, rows = _lp_problem(g, skip)
+        # the engine derives ts from |goal - pos| / v_nom: the dump's ts must be reproduced
+        st = np.zeros(9); st[:3] = g["state"][0]
+        r = e.qp_solve_batch([0], st, g["goal"], [0, len(normal)], normal, point, d)
+        assert r["status"][0] == expect
+        ro = T.solve(g["state"], g["goal"], int(g["ts"]), lb, ub, g["vmax"], g["amax"], rows)
+        assert ro["status"] == expect
+        if expect == 0:
+            assert np.abs(r["x"][0] - ro["x"]).max() <= 1e-7
+            assert abs(r["cost"][0] - ro["cost"]) <= 1e-9 * max(1.0, abs(ro["cost"]))
+            D = T.dense(g["state"], g["goal"], int(g["ts"]), lb, ub, g["vmax"], g["amax"], rows)
+            x, obj, stt = R.solve_ldp(D)
+            assert stt == "ok" and np.abs(r["x"][0] - x).max() <= 1e-7 and abs(r["cost"][0] - obj) <= 1e-8 * max(1, abs(obj))
+            v_eq, v_in = R.kkt_violation(D, r["x"][0])
+            assert v_eq <= 1e-7 and v_in <= 1e-7
+
+
+# ---------------------------------------------------------------------------------------------------------
+def _teacher_forced(scn, steps, omap=None, bt=None, check_lsc_agents=(0,), traj_tol=1e-6):
+    """Oracle runs closed loop; before every step the engine is loaded with the oracle's planner state, so both
+    plan from identical inputs. Returns per-step max |traj diff|."""
+    import lsc_planner_b200 as L
+    n = scn.n
+    sw = O.Swarm(n, scn.world_min, scn.world_max, use_octomap=omap is not None, omap=omap,
+                 radius=[a.radius for a in scn.agents], downwash=[a.downwash for a in scn.agents],
+                 vmax=[a.max_vel for a in scn.agents], amax=[a.max_acc for a in scn.agents],
+                 v_nom=[a.nominal_velocity for a in scn.agents])
+    sw.set_state(scn.start); sw.set_goals(scn.goal); sw.set_capture(True)
+    e = L.ReplanEngine(n, L.Param(world_min=scn.world_min, world_max=scn.world_max, world_use_octomap=omap is not None),
+                       scn.agents)
+    if bt:
+        e.set_octomap_file(bt)
+    worst = []
+    for step in range(steps):
+        pos, vel, acc = sw.state()
+        traj_prev = sw.traj(); seq = sw.seq
+        if omap is not None:
+            e.set_sfc(sw.boxes(), _init_flags(sw, step))
+        e.set_prev_traj(traj_prev, seq)
+        sw.step()
+        out = e.replan(pos, vel, acc, scn.goal)
+        q = sw.qp()
+        assert e.planner_seq == sw.seq
+        # initial trajectories / predictions: same float arithmetic -> bit-identical
+        assert np.array_equal(e.initial_traj().view(np.uint32), sw.pred().view(np.uint32))
+        nr_o, d_o, _ = sw.capture()
+        for a in check_lsc_agents:
+            nr, d = e.get_lsc(a)
+            others = [j for j in range(n) if j != a]
+            assert np.abs(nr - nr_o[a, others]).max() <= 1e-6
+            assert np.abs(d - d_o[a, others]).max() <= 1e-6
+        if omap is not None:
+            bx, _ = e.get_sfc()
+            assert np.array_equal(bx.view(np.uint32), sw.boxes().view(np.uint32)), step
+        assert np.array_equal(out["qp_status"], q["status"]), (step, out["qp_status"], q["status"])
+        assert (out["report"] == 5).all()
+        t_o = sw.traj()
+        diff = np.abs(out["traj"] - t_o).max()
+        worst.append(diff)
+        assert diff <= traj_tol, (step, diff)
+        ok = q["status"] == 0
+        assert np.abs(out["qp_cost"][ok] - q["cost"][ok]).max() <= 1e-6 * max(1.0, np.abs(q["cost"]).max())
+        assert np.array_equal(out["flags"], q["flags"])
+        sw.advance()
+        p2, v2, a2 = sw.state()
+        assert np.abs(out["next_position"] - p2).max() <= traj_tol
+        assert np.abs(out["next_velocity"] - v2).max() <= 1e-4 and np.abs(out["next_acceleration"] - a2).max() <= 2e-3
+    return worst
+
+
+def _init_flags(sw, step):
+    # oracle: flag_initialize_sfc is true only before the first step
+    return np.full(sw.n, 1 if step == 0 else 0, np.int32)
+
+
+def test_swarm_circle20_teacher_forced(golden_dir):
+    import lsc_planner_b200 as L
+    scn = L.scenarios.load_mission(os.path.join(golden_dir, "missions", "multi_circle20.json"))
+    _teacher_forced(scn, 40, check_lsc_agents=(0, 7, 19))
+
+
+def test_swarm_simple3_teacher_forced(golden_dir):
+    import lsc_planner_b200 as L
+    scn = L.scenarios.load_mission(os.path.join(golden_dir, "missions", "multi_simple3.json"))
+    _teacher_forced(scn, 30, check_lsc_agents=(0, 1, 2))
+
+
+def test_swarm_forest_teacher_forced(forest_path):
+    import lsc_planner_b200 as L
+    om = O.Map.from_bt(forest_path, WMIN, WMAX)
+    e = _engine(2, world_use_octomap=True, world_min=WMIN, world_max=WMAX)
+    e.set_octomap_file(forest_path)
+    dm = e.distmap()
+    scn = L.scenarios.random_forest(24, dm["sqdist"], dm["off"], seed=0)
+    _teacher_forced(scn, 25, omap=om, bt=forest_path, check_lsc_agents=(0, 5))
+
+
+def test_swarm_closed_loop_circle20(golden_dir):
+    """Engine alone, closed loop on its own outputs (device-resident stepping), vs the oracle closed loop."""
+    import lsc_planner_b200 as L
+    scn = L.scenarios.load_mission(os.path.join(golden_dir, "missions", "multi_circle20.json"))
+    n = scn.n
+    sw = O.Swarm(n, scn.world_min, scn.world_max)
+    sw.set_state(scn.start); sw.set_goals(scn.goal)
+    e = L.ReplanEngine(n, L.Param(world_min=scn.world_min, world_max=scn.world_max), scn.agents)
+    e.set_states(scn.start); e.set_goals(scn.goal)
+    min_dist = np.inf
+    for step in range(60):
+        sw.step(); sw.advance()
+        e.replan_resident()
+        out = e.fetch()
+        assert (out["qp_status"] == 0).all()
+        p = out["next_position"].astype(np.float64)
+        d = (p[:, None] - p[None]) * [1, 1, 0.5]
+        dist = np.sqrt((d ** 2).sum(-1)) + np.eye(n) * 99
+        min_dist = min(min_dist, dist.min())
+        # same trajectories up to accumulated float noise
+        assert np.abs(out["traj"] - sw.traj()).max() <= 1e-3, step
+    assert min_dist >= 0.3 - 1e-3            # no collision: downwash-scaled distance >= r_i + r_j
+
+
+def test_swarm_property_n256():
+    """Config 3 size: every agent's solution satisfies every row of ITS OWN QP (checked in numpy from the engine's
+    captured constraints), the dynamic limits and the equality constraints; spot agents are re-solved by the oracle."""
+    import lsc_planner_b200 as L
+    scn = L.scenarios.circle_swap(256)
+    n = scn.n
+    e = L.ReplanEngine(n, L.Param(world_min=scn.world_min, world_max=scn.world_max), scn.agents)
+    e.set_states(scn.start); e.set_goals(scn.goal)
+    sw = O.Swarm(n, scn.world_min, scn.world_max)
+    for step in range(12):
+        e.replan_resident()
+        out = e.fetch().copy()
+        assert (out["qp_status"] == 0).all()
+        pred = e.initial_traj()
+        x = out["traj"].astype(np.float64)                       # [n][5][6][3]
+        # continuity + dynamic limits
+        vel = (x[:, :, 1:] - x[:, :, :-1]) * 25.0
+        acc = (x[:, :, 2:] - 2 * x[:, :, 1:-1] + x[:, :, :-2]) * 500.0
+        assert np.abs(vel[:, 1:]).max() <= 1.0 + 1e-4 and np.abs(acc[:, 1:]).max() <= 2.0 + 2e-2
+        assert np.abs(x[:, 1:, 0] - x[:, :-1, 5]).max() <= 1e-6
+        assert np.abs(x[:, 4, 5] - x[:, 4, 4]).max() <= 1e-6 and np.abs(x[:, 4, 5] - x[:, 4, 3]).max() <= 1e-6
+        for a in (0, 100, 255):
+            nr, d = e.get_lsc(a)
+            others = [j for j in range(n) if j != a]
+            rel = x[a][None] - pred[others].astype(np.float64)    # [n-1][5][6][3]
+            lhs = np.einsum("omik,omk->omi", rel, nr.astype(np.float64)) - d
+            lhs[:, 0, :3] = 0                                     # rows skipped for the initial state
+            assert lhs.min() >= -2e-6, (step, a, lhs.min())
+    # teacher-forced oracle check at this size: one more step, agent 3 re-planned by the oracle from the same inputs
+    sw.set_state(out["next_position"], out["next_velocity"], out["next_acceleration"]); sw.set_goals(scn.goal)
+    sw.set_traj(out["traj"], e.planner_seq)
+    sw.step(3, 4)
+    o2 = e.replan(out["next_position"], out["next_velocity"], out["next_acceleration"], scn.goal)
+    assert e.planner_seq == sw.seq
+    assert sw.qp()["status"][3] == 0
+    assert np.abs(o2["traj"][3] - sw.traj()[3]).max() <= 1e-6
