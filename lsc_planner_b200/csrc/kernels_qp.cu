@@ -23,7 +23,11 @@ namespace lscgpu {
 
 constexpr int NR = kRed;        // 39
 constexpr int LD = 39;          // row pitch of J and R (odd pitch: row-per-lane accesses are bank-conflict free)
-constexpr double kPriceTol = 1e-10;
+// Primal feasibility tolerance = CPLEX's default EpRHS (the reference sets no tolerance, src/traj_optimizer.cpp:42-54):
+// like a dual simplex, a row enters the working set only when violated by more than this; entered rows are then met
+// exactly. Trajectories travel as float32, so agents in contact see hulls ~1e-7 closer than r_i + r_j; an exact
+// solver would call that infeasible where CPLEX answers "optimal".
+constexpr double kFeasTol = 1e-6;
 constexpr double kZeroTol = 1e-13;
 
 struct SelectedRow {
@@ -57,7 +61,10 @@ __device__ __forceinline__ bool row_is_active(const QpShared& S, int q, int id) 
         if (S.act[k] == id) return true;
     return false;
 }
-__device__ __forceinline__ void consider(Best& b, const QpShared& S, int q, double mu, int id) {
+// slack: a.x - b of the row; scale: 1 / (whitened length of its normal)
+__device__ __forceinline__ void consider(Best& b, const QpShared& S, int q, double slack, double scale, int id) {
+    if (!(slack < -kFeasTol)) return;
+    const double mu = scale < INFINITY ? slack * scale : -INFINITY;   // zero normal with positive rhs: infeasible row
     if (mu < b.mu && !row_is_active(S, q, id)) { b.mu = mu; b.id = id; }
 }
 __device__ __forceinline__ Best warp_argmin(Best b) {
@@ -77,8 +84,8 @@ __device__ __forceinline__ void price_fixed(Best& best, const QpShared& S, int q
         const int k = var / kAx, mi = var % kAx, m = mi / 6, i = mi % 6;
         if (m == 0 && i < kPhi) continue;
         const double xv = S.x[var], ig = S.inv_gn[mi];
-        consider(best, S, q, (xv - S.lb[m * 3 + k]) * ig, var * 2);
-        consider(best, S, q, (S.ub[m * 3 + k] - xv) * ig, var * 2 + 1);
+        consider(best, S, q, xv - S.lb[m * 3 + k], ig, var * 2);
+        consider(best, S, q, S.ub[m * 3 + k] - xv, ig, var * 2 + 1);
     }
     for (int idx = lane; idx < 135; idx += 32) {
         const int k = idx / 45, rem = idx % 45, m = rem / 9, j = rem % 9;
@@ -95,27 +102,25 @@ __device__ __forceinline__ void price_fixed(Best& best, const QpShared& S, int q
             lim = S.amax[k];
         }
         const double inv = S.inv_dyn[m * 9 + j];
-        consider(best, S, q, (lim - expr) * inv, kFixedRows - 270 + idx * 2);
-        consider(best, S, q, (lim + expr) * inv, kFixedRows - 270 + idx * 2 + 1);
+        consider(best, S, q, lim - expr, inv, kFixedRows - 270 + idx * 2);
+        consider(best, S, q, lim + expr, inv, kFixedRows - 270 + idx * 2 + 1);
     }
 }
 
-// one (obstacle, segment) pair: up to 6 rows. Returns the smallest whitened slack of the pair.
-__device__ __forceinline__ double price_pair(Best& best, const QpShared& S, int q, int p, int n_obs, const float4* nrm,
+// one (obstacle, segment) pair: up to 6 rows. Returns true when a row of the pair is violated beyond the tolerance.
+__device__ __forceinline__ bool price_pair(Best& best, const QpShared& S, int q, int p, int n_obs, const float4* nrm,
                                              const double* rhs, size_t pitch) {
     const int m = p / n_obs;
     const float4 nr = nrm[p];
     const double ax = (double)nr.x, ay = (double)nr.y, az = (double)nr.z, inv = (double)nr.w;
-    double mu_min = INFINITY;
+    bool violated = false;
     for (int i = (m == 0 ? kPhi : 0); i < 6; i++) {
         const int vi = m * 6 + i;
         const double slack = ax * S.x[vi] + ay * S.x[kAx + vi] + az * S.x[2 * kAx + vi] - rhs[(size_t)i * pitch + p];
-        double mu = slack * inv * S.inv_gn[vi];
-        if (!(inv < INFINITY)) mu = slack < 0.0 ? -INFINITY : INFINITY;   // zero normal: infeasible iff rhs > 0
-        mu_min = fmin(mu_min, mu);
-        consider(best, S, q, mu, kFixedRows + p * 6 + i);
+        violated |= slack < -kFeasTol;
+        consider(best, S, q, slack, inv * S.inv_gn[vi], kFixedRows + p * 6 + i);
     }
-    return mu_min;
+    return violated;
 }
 
 __device__ __forceinline__ void decode_row(QpShared& S, int id, int n_obs, const float4* nrm, const double* rhs,
@@ -234,13 +239,11 @@ __global__ void __launch_bounds__(32) k_qp_solve(QpLaunch L) {
 
     int q = 0, iters = 0, status = LSCGPU_QP_OK;
     int n_work = min(L.cand_count[b], L.cand_cap);
-    const bool work_overflow = L.cand_count[b] > L.cand_cap;
-    (void)work_overflow;
     unsigned long long rows_priced = 0, full_passes = 0;
 
     while (true) {
         // ---- pricing --------------------------------------------------------------------------------------------
-        Best best{-kPriceTol, -1};
+        Best best{0.0, -1};
         price_fixed(best, S, q, lane, vel_coef, acc_coef);
         for (int w = lane; w < n_work; w += 32) price_pair(best, S, q, cand[w], n_obs, nrm, rhs, pitch);
         rows_priced += 414 + 6ull * n_work;
@@ -252,7 +255,7 @@ __global__ void __launch_bounds__(32) k_qp_solve(QpLaunch L) {
             for (int p0 = 0; p0 < P; p0 += 32) {
                 const int p = p0 + lane;
                 bool viol = false;
-                if (p < P) viol = price_pair(best, S, q, p, n_obs, nrm, rhs, pitch) < -kPriceTol;
+                if (p < P) viol = price_pair(best, S, q, p, n_obs, nrm, rhs, pitch);
                 const unsigned mask = __ballot_sync(0xffffffffu, viol);
                 if (viol) {
                     const int slot = n_work + __popc(mask & ((1u << lane) - 1u));

@@ -68,7 +68,21 @@ def circle_swap(n: int, z: float = 1.0, spacing: float = 0.8, r0: float = 4.0, r
 def random_forest(n: int, sqdist: np.ndarray, off, res: float = 0.1, seed: int = 0, world_min=(-5, -5, 0),
                   world_max=(5, 5, 2.5), clearance_m: float = 0.4, pair_dist: float = 0.6, downwash: float = 2.0) -> Scenario:
     """rejection-sampled starts and goals in the world shrunk by 0.5 m with EDT >= 0.4 m
-    and pairwise downwash-scaled distance >= 0.6 m inside each set. `sqdist` is the engine's squared cell distance grid."""
+    and pairwise downwash-scaled distance >= 0.6 m inside each set. `sqdist` is the engine's squared cell distance grid.
+    0.6 m spacing saturates the 10 x 10 x 2.5 m world near 200 agents (random sequential packing), so for larger swarms
+    the spacing is reduced stepwise (0.5, 0.4, 0.35 m; the collision distance is 0.3 m) until all agents fit."""
+    vol = float(np.prod((np.asarray(world_max, float) - np.asarray(world_min, float) - 1.0) * [1, 1, 1.0 / downwash]))
+    for pd in [d for d in (pair_dist, 0.5, 0.4, 0.35) if d <= pair_dist]:
+        if n > 0.3 * vol / (math.pi / 6 * pd ** 3) and pd > 0.35:
+            continue                       # beyond the random-sequential-packing capacity at this spacing
+        try:
+            return _random_forest(n, sqdist, off, res, seed, world_min, world_max, clearance_m, pd, downwash)
+        except RuntimeError:
+            continue
+    raise RuntimeError("cannot place agents")
+
+
+def _random_forest(n, sqdist, off, res, seed, world_min, world_max, clearance_m, pair_dist, downwash) -> Scenario:
     rng = np.random.default_rng(seed)
     lo = np.asarray(world_min, float) + 0.5; hi = np.asarray(world_max, float) - 0.5
     need_sq = (clearance_m / res) ** 2
@@ -78,7 +92,7 @@ def random_forest(n: int, sqdist: np.ndarray, off, res: float = 0.1, seed: int =
         tries = 0
         while len(pts) < n:
             tries += 1
-            if tries > 2000000:
+            if tries > 400 * n + 20000:
                 raise RuntimeError("cannot place agents")
             p = rng.uniform(lo, hi)
             c = np.floor(p / res).astype(int) - np.asarray(off)

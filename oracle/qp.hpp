@@ -34,6 +34,13 @@ constexpr int QRED = QDIM * QFREE;   // 39
 
 enum QpStatus { QP_OK = 0, QP_INFEASIBLE = 1, QP_MAXITER = 2 };
 
+// Primal feasibility tolerance: CPLEX's default EpRHS = 1e-6 (the reference changes no tolerance,
+// src/traj_optimizer.cpp:42-54). As in a dual simplex, an inequality row enters the working set only when it is
+// violated by MORE than the tolerance; rows that do enter are then satisfied exactly. Without it the closed loop
+// breaks down: trajectories are handed on as float32 (traj_t), so two agents in contact see each other's hulls
+// 1e-7 closer than r_i + r_j and an exact solver reports INFEASIBLE where CPLEX returns "optimal".
+constexpr double QP_FEAS_TOL = 1e-6;
+
 inline int n_choose_k(int n, int k) {
     if (k > n) return 0;
     if (k * 2 > n) k = n - k;
@@ -357,6 +364,7 @@ inline void qp_solve(const QpTables& T, const QpProblem& p, QpResult& out, int m
             else if (id >= 450) nn = std::sqrt(r.a[0] * r.a[0] + r.a[1] * r.a[1] + r.a[2] * r.a[2]) * T.gnorm[ts - 1][r.idx[0] % QAX];
             else nn = row_normal(r, nv);
             double sl = row_slack(r);
+            if (!(sl < -QP_FEAS_TOL)) continue;
             double mu = sl / std::max(nn, 1e-300);
             if (mu < mu_best) { mu_best = mu; pbest = id; rb = r; nb = nn; }
         }
