@@ -194,7 +194,8 @@ typedef struct lscgpu_step_stats {
                               the engine stream) */
     float ms_predict, ms_lsc, ms_sfc, ms_qp, ms_exchange, ms_commit;   /* per-kernel sums; 0 unless profiling is on */
     int32_t kernel_launches;        /* kernels of this library launched */
-    int64_t lsc_pairs;              /* (agent, neighbour, segment) hull tests */
+    int64_t lsc_pairs;              /* (agent, neighbour, segment) pairs of the swarm: (N-1) * 5 per local agent */
+    int64_t lsc_pairs_kept;         /* pairs that survived the exact culling test, i.e. GJK hull tests actually run */
     int64_t gjk_iterations;         /* GJK outer iterations */
     int64_t qp_rows_priced;         /* inequality rows evaluated by the QP kernel (all local agents) */
     int64_t qp_iterations;          /* active-set iterations (all local agents) */

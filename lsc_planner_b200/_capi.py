@@ -32,7 +32,7 @@ class AgentConst(C.Structure):
 class StepStats(C.Structure):
     _fields_ = [("steps", C.c_int32), ("ms_total", C.c_float), ("ms_predict", C.c_float), ("ms_lsc", C.c_float),
                 ("ms_sfc", C.c_float), ("ms_qp", C.c_float), ("ms_exchange", C.c_float), ("ms_commit", C.c_float),
-                ("kernel_launches", C.c_int32), ("lsc_pairs", C.c_int64), ("gjk_iterations", C.c_int64),
+                ("kernel_launches", C.c_int32), ("lsc_pairs", C.c_int64), ("lsc_pairs_kept", C.c_int64), ("gjk_iterations", C.c_int64),
                 ("qp_rows_priced", C.c_int64), ("qp_iterations", C.c_int64), ("qp_full_passes", C.c_int64)]
 
 

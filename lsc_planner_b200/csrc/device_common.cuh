@@ -44,6 +44,7 @@ struct StepCounters {
     unsigned long long qp_iterations;
     unsigned long long full_passes;
     unsigned long long gjk_iterations;
+    unsigned long long kept_pairs;
 };
 
 // ---- small float3/double3 helpers with explicit IEEE roundings ----------------------------------

@@ -64,7 +64,7 @@ struct lscgpu_engine {
     cudaStream_t stream = nullptr;
     int planner_seq = 0;
     bool profiling = false;
-    double cand_threshold = 2.0;
+    double cand_threshold = 0.0;
     int max_iter = 2000;
 
     std::vector<lscgpu_agent_const> consts_host;
@@ -83,8 +83,10 @@ struct lscgpu_engine {
     float4* d_nrm = nullptr;
     double* d_rhs = nullptr;
     int P_pad = 0, n_rows_alloc = 0;
-    int *d_cand = nullptr, *d_cand_count = nullptr;
+    int *d_cand = nullptr, *d_cand_count = nullptr, *d_kept = nullptr, *d_kept_count = nullptr;
     int cand_cap = 0;
+    float4* d_sphere = nullptr;      // [5][n_pad]
+    float* d_reach = nullptr;        // [N][5]
     StepCounters* d_counters = nullptr;
     // map
     bool have_map = false;
@@ -103,7 +105,9 @@ struct lscgpu_engine {
 
 static void free_rows(lscgpu_engine* e) {
     cudaFree(e->d_nrm); cudaFree(e->d_rhs); cudaFree(e->d_cand); cudaFree(e->d_cand_count);
+    cudaFree(e->d_kept); cudaFree(e->d_kept_count);
     e->d_nrm = nullptr; e->d_rhs = nullptr; e->d_cand = nullptr; e->d_cand_count = nullptr;
+    e->d_kept = nullptr; e->d_kept_count = nullptr;
     e->n_rows_alloc = 0;
 }
 
@@ -118,6 +122,8 @@ static int alloc_rows(lscgpu_engine* e) {
     CU(cudaMalloc(&e->d_rhs, sizeof(double) * (size_t)n_local * 6 * e->P_pad));
     CU(cudaMalloc(&e->d_cand, sizeof(int) * (size_t)n_local * e->cand_cap));
     CU(cudaMalloc(&e->d_cand_count, sizeof(int) * (size_t)n_local));
+    CU(cudaMalloc(&e->d_kept, sizeof(int) * (size_t)n_local * e->P_pad));
+    CU(cudaMalloc(&e->d_kept_count, sizeof(int) * (size_t)n_local));
     e->n_rows_alloc = n_local;
     return LSCGPU_OK;
 }
@@ -133,7 +139,7 @@ extern "C" void lscgpu_destroy(lscgpu_engine* e) {
     cudaFree(e->d_tables); cudaFree(e->d_consts); cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_traj);
     cudaFree(e->d_pred); cudaFree(e->d_predT); cudaFree(e->d_boxes); cudaFree(e->d_state9); cudaFree(e->d_goal3);
     cudaFree(e->d_last_cost); cudaFree(e->d_ts); cudaFree(e->d_flags); cudaFree(e->d_init_sfc); cudaFree(e->d_counters);
-    cudaFree(e->dm.sqdist); cudaFree(e->dm.sat);
+    cudaFree(e->dm.sqdist); cudaFree(e->dm.sat); cudaFree(e->d_sphere); cudaFree(e->d_reach);
     for (auto& se : e->ev_pool) for (auto& ev : se.ev) if (ev) cudaEventDestroy(ev);
     if (e->ev_begin) cudaEventDestroy(e->ev_begin);
     if (e->ev_end) cudaEventDestroy(e->ev_end);
@@ -226,6 +232,9 @@ extern "C" int lscgpu_create(const lscgpu_params* p, int n_agents, const lscgpu_
     CUB(cudaMalloc(&e->d_pred, sizeof(float) * N * kTrajFloats));
     CUB(cudaMalloc(&e->d_predT, sizeof(float) * (size_t)kTrajFloats * e->n_pad));
     CUB(cudaMemset(e->d_predT, 0, sizeof(float) * (size_t)kTrajFloats * e->n_pad));
+    CUB(cudaMalloc(&e->d_sphere, sizeof(float4) * (size_t)kM * e->n_pad));
+    CUB(cudaMemset(e->d_sphere, 0, sizeof(float4) * (size_t)kM * e->n_pad));
+    CUB(cudaMalloc(&e->d_reach, sizeof(float) * N * kM));
     CUB(cudaMalloc(&e->d_boxes, sizeof(float) * N * 30));
     CUB(cudaMalloc(&e->d_state9, sizeof(double) * N * 9));
     CUB(cudaMalloc(&e->d_goal3, sizeof(double) * N * 3));
@@ -264,6 +273,9 @@ static int build_map(lscgpu_engine* e, const int32_t* keys, int n) {
         total *= (size_t)e->dm.size[k]; tab *= (size_t)(e->dm.size[k] + 1);
     }
     if (tab > (size_t)1 << 31) return fail(LSCGPU_ERR_ARG, "world too large for the 32-bit blocked-voxel tables");
+    for (int k = 0; k < 3; k++)
+        if (std::fabs(e->prm.world_min[k]) > 60.f || std::fabs(e->prm.world_max[k]) > 60.f)
+            return fail(LSCGPU_ERR_ARG, "SFC kernel supports worlds within +-60 m (float32 sample rounding must stay below the 1e-5 nudge)");
     // blocked predicate of isObstacleInBox (include/corridor_constructor.hpp:113-114), per distinct radius:
     // getDistance = (float)((float)sqrt(sq) * res) < radius + 0.5 res - 1e-5  -> largest blocked squared distance
     std::vector<int> thr(e->radii.size());
@@ -389,7 +401,10 @@ static int step_device(lscgpu_engine* e) {
         }
         ev = e->ev_pool[e->pending].ev;
     }
-    if (n_local > 0) CU(cudaMemsetAsync(e->d_cand_count, 0, sizeof(int) * n_local, s));
+    if (n_local > 0) {
+        CU(cudaMemsetAsync(e->d_cand_count, 0, sizeof(int) * n_local, s));
+        CU(cudaMemsetAsync(e->d_kept_count, 0, sizeof(int) * n_local, s));
+    }
     if (e->pending == 0) CU(cudaEventRecord(e->ev_begin, s));
     if (prof) CU(cudaEventRecord(ev[0], s));
 
@@ -398,7 +413,7 @@ static int step_device(lscgpu_engine* e) {
     pl.dt = e->prm.dt; pl.reset_threshold = e->prm.reset_threshold;
     pl.in = e->d_in; pl.prev_traj = e->d_traj; pl.consts = e->d_consts;
     pl.pred = e->d_pred; pl.predT = e->d_predT; pl.state9 = e->d_state9; pl.goal3 = e->d_goal3;
-    pl.ts = e->d_ts; pl.flags = e->d_flags;
+    pl.ts = e->d_ts; pl.flags = e->d_flags; pl.sphere = e->d_sphere; pl.reach = e->d_reach;
     launch_predict(pl, s); launches++;
     if (prof) CU(cudaEventRecord(ev[1], s));
 
@@ -418,7 +433,9 @@ static int step_device(lscgpu_engine* e) {
         ll.n_agents = e->N; ll.n_pad = e->n_pad; ll.a0 = e->a0; ll.n_local = n_local;
         ll.pred = e->d_pred; ll.predT = e->d_predT; ll.consts = e->d_consts; ll.T = e->d_tables;
         ll.state9 = e->d_state9; ll.goal3 = e->d_goal3; ll.ts = e->d_ts;
+        ll.sphere = e->d_sphere; ll.reach = e->d_reach;
         ll.nrm = e->d_nrm; ll.rhs = e->d_rhs; ll.P_pad = e->P_pad;
+        ll.kept = e->d_kept; ll.kept_count = e->d_kept_count;
         ll.cand = e->d_cand; ll.cand_count = e->d_cand_count; ll.cand_cap = e->cand_cap;
         ll.cand_threshold = e->cand_threshold; ll.counters = e->d_counters;
         launch_lsc_build(ll, s); launches++;
@@ -433,6 +450,7 @@ static int step_device(lscgpu_engine* e) {
         ql.boxes = e->prm.world_use_octomap ? e->d_boxes : nullptr;
         for (int k = 0; k < 3; k++) { ql.wmin[k] = e->prm.world_min[k]; ql.wmax[k] = e->prm.world_max[k]; }
         ql.nrm = e->d_nrm; ql.rhs = e->d_rhs; ql.obs_offset = nullptr; ql.n_obs = e->N - 1; ql.P_pad = e->P_pad;
+        ql.kept = e->d_kept; ql.kept_count = e->d_kept_count;
         ql.cand = e->d_cand; ql.cand_count = e->d_cand_count; ql.cand_cap = e->cand_cap; ql.max_iter = e->max_iter;
         ql.out = e->d_out; ql.prev_traj = e->d_traj; ql.last_cost = e->d_last_cost; ql.flags = e->d_flags;
         ql.counters = e->d_counters;
@@ -478,6 +496,7 @@ static int finish_steps(lscgpu_engine* e) {
     }
     st.kernel_launches = e->pending_launches;
     st.lsc_pairs = (int64_t)e->pending * (e->a1 - e->a0) * (e->N - 1) * kPairsPerObs;
+    st.lsc_pairs_kept = (int64_t)c.kept_pairs;
     st.gjk_iterations = (int64_t)c.gjk_iterations;
     st.qp_rows_priced = (int64_t)c.rows_priced;
     st.qp_iterations = (int64_t)c.qp_iterations;
@@ -651,7 +670,7 @@ extern "C" int lscgpu_qp_solve_batch(lscgpu_engine* e, int nb, const int32_t* ag
     CU(cudaSetDevice(e->device));
     cudaStream_t s = e->stream;
     DevBuf B;
-    int *d_ai, *d_off, *d_ts, *d_cand, *d_cc, *d_status, *d_iters;
+    int *d_ai, *d_off, *d_ts, *d_cand, *d_cc, *d_status, *d_iters, *d_kept, *d_kc;
     double *d_state, *d_goal, *d_d, *d_rhs, *d_x, *d_cost;
     float *d_sfc = nullptr, *d_n, *d_p;
     float4* d_nrm;
@@ -659,6 +678,8 @@ extern "C" int lscgpu_qp_solve_batch(lscgpu_engine* e, int nb, const int32_t* ag
     const int cap = (int)std::min<size_t>(std::max<size_t>(pairs, 32), 4096);
     CU(B.get(&d_ai, nb)); CU(B.get(&d_off, nb + 1)); CU(B.get(&d_ts, nb)); CU(B.get(&d_cand, (size_t)nb * cap));
     CU(B.get(&d_cc, nb)); CU(B.get(&d_status, nb)); CU(B.get(&d_iters, nb));
+    CU(B.get(&d_kept, pairs)); CU(B.get(&d_kc, nb));
+    CU(cudaMemsetAsync(d_kc, 0, sizeof(int) * nb, s));
     CU(B.get(&d_state, (size_t)nb * 9)); CU(B.get(&d_goal, (size_t)nb * 3)); CU(B.get(&d_d, pairs * 6));
     CU(B.get(&d_rhs, pairs * 6)); CU(B.get(&d_x, (size_t)nb * kNv)); CU(B.get(&d_cost, nb));
     CU(B.get(&d_n, pairs * 3)); CU(B.get(&d_p, pairs * 18)); CU(B.get(&d_nrm, pairs));
@@ -676,13 +697,14 @@ extern "C" int lscgpu_qp_solve_batch(lscgpu_engine* e, int nb, const int32_t* ag
         CU(cudaMemcpyAsync(d_d, lsc_d, sizeof(double) * pairs * 6, cudaMemcpyHostToDevice, s));
     }
     CU(cudaMemsetAsync(d_cc, 0, sizeof(int) * nb, s));
-    launch_rows_from_lsc(nb, d_off, total_obs, d_n, d_p, d_d, d_nrm, d_rhs, s);
+    launch_rows_from_lsc(nb, d_off, total_obs, d_n, d_p, d_d, d_nrm, d_rhs, d_kept, d_kc, s);
     launch_terminal_segments(nb, d_state, d_goal, d_ai, e->d_consts, e->prm.dt, d_ts, s);
     QpLaunch ql{};
     ql.n_problems = nb; ql.T = e->d_tables; ql.consts = e->d_consts; ql.agent_index = d_ai; ql.agent_base = 0;
     ql.state9 = d_state; ql.goal3 = d_goal; ql.ts = d_ts; ql.boxes = d_sfc;
     for (int k = 0; k < 3; k++) { ql.wmin[k] = e->prm.world_min[k]; ql.wmax[k] = e->prm.world_max[k]; }
     ql.nrm = d_nrm; ql.rhs = d_rhs; ql.obs_offset = d_off; ql.n_obs = 0; ql.P_pad = (int)pairs;
+    ql.kept = d_kept; ql.kept_count = d_kc;
     ql.cand = d_cand; ql.cand_count = d_cc; ql.cand_cap = cap; ql.max_iter = e->max_iter;
     ql.x_out = d_x; ql.cost_out = d_cost; ql.status_out = d_status; ql.iters_out = d_iters;
     ql.out = nullptr; ql.counters = nullptr;

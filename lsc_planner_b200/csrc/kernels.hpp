@@ -21,6 +21,8 @@ struct PredictLaunch {
     double* goal3;                 // [N][3]
     int* ts;                       // [N]
     int* flags;                    // [N]
+    float4* sphere;                // [5][n_pad] bounding sphere (centre xyz, radius) of every segment's control points
+    float* reach;                  // [N][5] how far ANY feasible control point of segment m can be from initial_traj's
 };
 void launch_predict(const PredictLaunch& L, cudaStream_t s);
 
@@ -34,9 +36,13 @@ struct LscLaunch {
     const double* state9;          // [N][9]
     const double* goal3;
     const int* ts;
-    float4* nrm;                   // [n_local][P_pad]
+    const float4* sphere;          // [5][n_pad]
+    const float* reach;            // [N][5]
+    float4* nrm;                   // [n_local][P_pad]   written only for kept pairs
     double* rhs;                   // [n_local][6][P_pad]
     int P_pad;
+    int* kept;                     // [n_local][P_pad] pair indices that survive the exact culling test
+    int* kept_count;               // [n_local]  (zeroed by the launcher)
     int* cand;                     // [n_local][cand_cap]
     int* cand_count;               // [n_local]  (zeroed by the launcher)
     int cand_cap;
@@ -51,7 +57,8 @@ void launch_lsc_capture(int n_agents, int agent, const float* pred, const AgentC
 void launch_gjk_batch(int n, const double* hulls, double* v, int* iters, cudaStream_t s);
 // LSC arrays of the reference container -> row store (operator-level QP entry)
 void launch_rows_from_lsc(int n_problems, const int* obs_offset, int total_obs, const float* lsc_normal,
-                          const float* lsc_point, const double* lsc_d, float4* nrm, double* rhs, cudaStream_t s);
+                          const float* lsc_point, const double* lsc_d, float4* nrm, double* rhs, int* kept,
+                          int* kept_count, cudaStream_t s);
 
 void launch_terminal_segments(int n, const double* state9, const double* goal3, const int* agent_index,
                               const AgentConstDev* consts, double dt, int* ts_out, cudaStream_t s);
@@ -73,6 +80,7 @@ struct QpLaunch {
     const int* obs_offset;         // batch mode: obstacles of problem b = [obs_offset[b], obs_offset[b+1]); null: swarm mode
     int n_obs;                     // swarm mode: N-1
     int P_pad;                     // swarm mode row pitch; batch mode: total pairs (rhs pitch)
+    const int* kept; const int* kept_count;   // pairs to sweep: swarm mode [b][P_pad]; batch mode at 5*obs_offset[b]
     int* cand; int* cand_count; int cand_cap;
     int max_iter;
     // outputs

@@ -37,8 +37,8 @@ __global__ void __launch_bounds__(96) k_predict(PredictLaunch L) {
         }
     }
     __syncthreads();
+    const float* o = L.pred + (size_t)a * kTrajFloats;
     if (e == 0) {
-        const float* o = L.pred + (size_t)a * kTrajFloats;
         const F3 p0{o[0], o[1], o[2]}, pos{in.position[0], in.position[1], in.position[2]};
         const F3 dlt = f3_sub(p0, pos);
         int fl = 0;
@@ -54,92 +54,173 @@ __global__ void __launch_bounds__(96) k_predict(PredictLaunch L) {
         if (ts > kM) ts = kM;     // the reference throws here (src/traj_optimizer.cpp:356-358); unreachable for ideal >= 0
         L.ts[a] = ts;
     }
+    if (e >= 32 && e < 32 + kM) {
+        // Culling data of segment m. Bounding sphere of the 6 control points, and `reach`: an upper
+        // bound of |x - c| for ANY point x the QP may give control point (m,i) and its initial_traj point c. The
+        // first three control points are fixed by the state (p, p + v dt/5, ...); every later increment is limited
+        // by the velocity rows to vmax dt / n per axis, so |x_{m,i} - p| <= sqrt(3) vmax dt (m+1) + max_k |x_{0,k} - p|.
+        const int m = e - 32;
+        float cx = 0.f, cy = 0.f, cz = 0.f;
+        for (int i = 0; i < 6; i++) { cx += o[(m * 6 + i) * 3]; cy += o[(m * 6 + i) * 3 + 1]; cz += o[(m * 6 + i) * 3 + 2]; }
+        cx *= (1.f / 6.f); cy *= (1.f / 6.f); cz *= (1.f / 6.f);
+        float rad2 = 0.f, far2 = 0.f;
+        for (int i = 0; i < 6; i++) {
+            const float x = o[(m * 6 + i) * 3], y = o[(m * 6 + i) * 3 + 1], z = o[(m * 6 + i) * 3 + 2];
+            rad2 = fmaxf(rad2, (x - cx) * (x - cx) + (y - cy) * (y - cy) + (z - cz) * (z - cz));
+            const float dx = x - in.position[0], dy = y - in.position[1], dz = z - in.position[2];
+            far2 = fmaxf(far2, dx * dx + dy * dy + dz * dz);
+        }
+        L.sphere[(size_t)m * L.n_pad + a] = make_float4(cx, cy, cz, sqrtf(rad2) * 1.0001f + 1e-5f);
+        const AgentConstDev& c = L.consts[a];
+        const float vmax = (float)fmax(c.vmax[0], fmax(c.vmax[1], c.vmax[2]));
+        const float dtf = (float)L.dt;
+        float fix2 = 0.f;       // the state-determined points x_{0,1}, x_{0,2} relative to p
+        {
+            float d1 = 0.f, d2 = 0.f;
+            for (int k = 0; k < 3; k++) {
+                const float s1 = in.velocity[k] * dtf / (float)kN;
+                const float s2 = 2.f * s1 + in.acceleration[k] * dtf * dtf / (float)(kN * (kN - 1));
+                d1 += s1 * s1; d2 += s2 * s2;
+            }
+            fix2 = fmaxf(d1, d2);
+        }
+        const float r = 1.7320509f * vmax * dtf * (float)(m + 1) + sqrtf(fix2) + sqrtf(far2);
+        L.reach[(size_t)a * kM + m] = r * 1.0001f + 1e-3f;
+    }
 }
 
 void launch_predict(const PredictLaunch& L, cudaStream_t s) { k_predict<<<L.n_agents, 96, 0, s>>>(L); }
 
 // ------------------------------------------------------------------------------------------------------------
-// k_lsc_build — grid (ceil((N-1)/128), n_local), block 128: thread = one (agent, obstacle) pair, 5 hull tests.
-// Own control points, the unconstrained QP minimiser x0 and the whitened bound lengths sit in shared memory; the
-// obstacle's control points are read from the element-major table (one coalesced 128 B line per warp per load).
-// Output: the agent's LSC rows (RowStore layout) + the initial working set of pairs whose rows are close to, or
-// violated at, x0.
+// k_lsc_build — one block of 128 threads per local agent.
+//   Phase A (all threads, one neighbour each per chunk of 128): exact culling test per (neighbour, segment) from the
+//     bounding spheres — 80 B per neighbour, coalesced float4 reads. A pair is dropped only when its LSC rows cannot
+//     be violated by any trajectory that respects the velocity limits, so dropping is
+//     solution-preserving; survivors go to a shared-memory queue.
+//   Phase B (whenever the queue holds a full batch, and at the end): one queued (neighbour, segment) hull per thread —
+//     GJK in FP64 registers, LSC rows written to the agent's row store at the pair's dense index p = m*(N-1) + jj,
+//     p appended to the agent's kept list, and to the initial QP working set when a row is violated at x0.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_lsc_build(LscLaunch L) {
+constexpr int kLscThreads = 128;
+
+__global__ void __launch_bounds__(kLscThreads) k_lsc_build(LscLaunch L) {
     __shared__ float own[kTrajFloats];
     __shared__ double x0[kNv];
     __shared__ double inv_gn[kAx];
-    const int al = blockIdx.y;
+    __shared__ float4 own_sphere[kM];
+    __shared__ float own_reach[kM];
+    __shared__ int queue[kLscThreads * (kM + 1)];
+    __shared__ int q_count, kept_base;
+    const int al = blockIdx.x;
     const int a = L.a0 + al;
     const int n_obs = L.n_agents - 1;
     const int ts = L.ts[a];
-    for (int e = threadIdx.x; e < kTrajFloats; e += blockDim.x) own[e] = L.pred[(size_t)a * kTrajFloats + e];
-    for (int e = threadIdx.x; e < kNv; e += blockDim.x) {
+    const int tid = threadIdx.x;
+    for (int e = tid; e < kTrajFloats; e += kLscThreads) own[e] = L.pred[(size_t)a * kTrajFloats + e];
+    for (int e = tid; e < kNv; e += kLscThreads) {
         const int k = e / kAx, i = e % kAx;
         const double* s = L.state9 + (size_t)a * 9;
         const double* Xs = L.T->Xs[ts - 1][i];
         x0[e] = Xs[0] * s[k] + Xs[1] * s[3 + k] + Xs[2] * s[6 + k] + L.T->xg[ts - 1][i] * L.goal3[(size_t)a * 3 + k];
     }
-    for (int e = threadIdx.x; e < kAx; e += blockDim.x) inv_gn[e] = 1.0 / L.T->gnorm[ts - 1][e];
+    for (int e = tid; e < kAx; e += kLscThreads) inv_gn[e] = 1.0 / L.T->gnorm[ts - 1][e];
+    if (tid < kM) { own_sphere[tid] = L.sphere[(size_t)tid * L.n_pad + a]; own_reach[tid] = L.reach[(size_t)a * kM + tid]; }
+    if (tid == 0) { q_count = 0; kept_base = 0; }
     __syncthreads();
 
-    const int jj = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = jj < n_obs;
-    const int j = live ? (jj < a ? jj : jj + 1) : a;
-    const AgentConstDev ca = L.consts[a], cj = L.consts[j];
-    const double downwash = (ca.downwash * ca.radius + cj.downwash * cj.radius) / (ca.radius + cj.radius);
-    const double collision_dist = cj.radius + ca.radius;
+    const AgentConstDev ca = L.consts[a];
     float4* nrm_out = L.nrm + (size_t)al * L.P_pad;
     double* rhs_out = L.rhs + (size_t)al * 6 * L.P_pad;
+    int* kept_out = L.kept + (size_t)al * L.P_pad;
     int gjk_it = 0;
-#pragma unroll 1
-    for (int m = 0; m < kM && live; m++) {
-        F3 ow[6], ob[6];
+
+
+    for (int j0 = 0; j0 < n_obs; j0 += kLscThreads) {
+        const int jj = j0 + tid;
+        if (jj < n_obs) {
+            const int j = jj < a ? jj : jj + 1;
+            const AgentConstDev cj = L.consts[j];
+            const float dw = (float)((ca.downwash * ca.radius + cj.downwash * cj.radius) / (ca.radius + cj.radius));
+            const float inv_dw = 1.0f / dw;
+            const float smax = fmaxf(1.0f, inv_dw);
+            const float rho = (float)(ca.radius + cj.radius);
 #pragma unroll
-        for (int i = 0; i < 6; i++) {
-            const int e = (m * 6 + i) * 3;
-            ow[i] = F3{own[e], own[e + 1], own[e + 2]};
-            ob[i] = F3{L.predT[(size_t)e * L.n_pad + j], L.predT[(size_t)(e + 1) * L.n_pad + j],
-                       L.predT[(size_t)(e + 2) * L.n_pad + j]};
+            for (int m = 0; m < kM; m++) {
+                const float4 so = own_sphere[m];
+                const float4 sj = L.sphere[(size_t)m * L.n_pad + j];
+                const float dx = so.x - sj.x, dy = so.y - sj.y, dz = (so.z - sj.z) * inv_dw;
+                const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
+                const float d_lb = dist * 0.9999f - smax * (so.w + sj.w);        // lower bound of the hull distance
+                const bool cull = d_lb - rho > 2.0f * smax * own_reach[m];
+                if (!cull) queue[atomicAdd(&q_count, 1)] = m * n_obs + jj;
+            }
         }
-        LscSegment seg;
-        lsc_segment(ow, ob, downwash, collision_dist, seg);
-        gjk_it += seg.iterations;
-        const double ax = (double)seg.normal.x, ay = (double)seg.normal.y, az = (double)seg.normal.z;
-        const double an = sqrt(ax * ax + ay * ay + az * az);
-        const float inv_an = an > 0.0 ? (float)(1.0 / an) : INFINITY;
-        const int p = m * n_obs + jj;
-        nrm_out[p] = make_float4(seg.normal.x, seg.normal.y, seg.normal.z, inv_an);
-        double mu_min = INFINITY;
+        __syncthreads();
+        // drain full batches (and everything after the last chunk)
+        const bool last = j0 + kLscThreads >= n_obs;
+        while (q_count >= kLscThreads || (last && q_count > 0)) {
+            const int n_items = min(q_count, kLscThreads);
+            const int total = q_count;
+            int p = -1;
+            if (tid < n_items) p = queue[total - n_items + tid];      // take the batch from the END of the queue
+            __syncthreads();
+            if (tid == 0) q_count = total - n_items;
+            if (p >= 0) {
+                const int m = p / n_obs, jj2 = p % n_obs;
+                const int j = jj2 < a ? jj2 : jj2 + 1;
+                const AgentConstDev cj = L.consts[j];
+                const double downwash = (ca.downwash * ca.radius + cj.downwash * cj.radius) / (ca.radius + cj.radius);
+                F3 ow[6], ob[6];
 #pragma unroll
-        for (int i = 0; i < 6; i++) {
-            // row  a . c_{m,i} >= d_i + a . o_{m,i}      (src/traj_optimizer.cpp:437-466)
-            const double rhs = seg.d[i] + (__dmul_rn(ax, (double)ob[i].x) + __dmul_rn(ay, (double)ob[i].y) +
-                                           __dmul_rn(az, (double)ob[i].z));
-            rhs_out[(size_t)i * L.P_pad + p] = rhs;
-            if (m == 0 && i < kPhi) continue;
-            const int vi = m * 6 + i;
-            const double slack = ax * x0[vi] + ay * x0[kAx + vi] + az * x0[2 * kAx + vi] - rhs;
-            const double mu = slack * (double)inv_an * inv_gn[vi];
-            mu_min = fmin(mu_min, mu);
-        }
-        if (!(mu_min >= L.cand_threshold)) {
-            const int slot = atomicAdd(L.cand_count + al, 1);
-            if (slot < L.cand_cap) L.cand[(size_t)al * L.cand_cap + slot] = p;
+                for (int i = 0; i < 6; i++) {
+                    const int e = (m * 6 + i) * 3;
+                    ow[i] = F3{own[e], own[e + 1], own[e + 2]};
+                    ob[i] = F3{L.predT[(size_t)e * L.n_pad + j], L.predT[(size_t)(e + 1) * L.n_pad + j],
+                               L.predT[(size_t)(e + 2) * L.n_pad + j]};
+                }
+                LscSegment seg;
+                lsc_segment(ow, ob, downwash, cj.radius + ca.radius, seg);
+                gjk_it += seg.iterations;
+                const double ax = (double)seg.normal.x, ay = (double)seg.normal.y, az = (double)seg.normal.z;
+                const double an = sqrt(ax * ax + ay * ay + az * az);
+                const float inv_an = an > 0.0 ? (float)(1.0 / an) : INFINITY;
+                nrm_out[p] = make_float4(seg.normal.x, seg.normal.y, seg.normal.z, inv_an);
+                bool near = false;
+#pragma unroll
+                for (int i = 0; i < 6; i++) {
+                    // row  a . c_{m,i} >= d_i + a . o_{m,i}      (src/traj_optimizer.cpp:437-466)
+                    const double rhs = seg.d[i] + (__dmul_rn(ax, (double)ob[i].x) + __dmul_rn(ay, (double)ob[i].y) +
+                                                   __dmul_rn(az, (double)ob[i].z));
+                    rhs_out[(size_t)i * L.P_pad + p] = rhs;
+                    if (m == 0 && i < kPhi) continue;
+                    const int vi = m * 6 + i;
+                    const double slack = ax * x0[vi] + ay * x0[kAx + vi] + az * x0[2 * kAx + vi] - rhs;
+                    const double mu = slack * (double)inv_an * inv_gn[vi];
+                    if (!(mu >= L.cand_threshold)) near = true;
+                }
+                kept_out[kept_base + tid] = p;
+                if (near) {
+                    const int slot = atomicAdd(L.cand_count + al, 1);
+                    if (slot < L.cand_cap) L.cand[(size_t)al * L.cand_cap + slot] = p;
+                }
+            }
+            __syncthreads();
+            if (tid == 0) kept_base += n_items;
+            __syncthreads();
         }
     }
+    if (tid == 0) L.kept_count[al] = kept_base;
     if (L.counters) {
-        // one atomic per warp
         const int tot = warp_sum_int(gjk_it);
-        if ((threadIdx.x & 31) == 0) atomicAdd(&L.counters->gjk_iterations, (unsigned long long)tot);
+        if ((tid & 31) == 0) atomicAdd(&L.counters->gjk_iterations, (unsigned long long)tot);
+        if (tid == 0) atomicAdd(&L.counters->kept_pairs, (unsigned long long)kept_base);
     }
 }
 
 void launch_lsc_build(const LscLaunch& L, cudaStream_t s) {
     const int n_obs = L.n_agents - 1;
     if (n_obs <= 0 || L.n_local <= 0) return;
-    dim3 grid((n_obs + 127) / 128, L.n_local);
-    k_lsc_build<<<grid, 128, 0, s>>>(L);
+    k_lsc_build<<<L.n_local, kLscThreads, 0, s>>>(L);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -193,7 +274,8 @@ void launch_gjk_batch(int n, const double* hulls, double* v, int* iters, cudaStr
 // Pair layout inside problem b with n_b obstacles: p = m * n_b + o, stored at pair offset 5 * obs_offset[b].
 // ------------------------------------------------------------------------------------------------------------
 __global__ void k_rows_from_lsc(int n_problems, const int* obs_offset, int total_obs, const float* lsc_normal,
-                                const float* lsc_point, const double* lsc_d, float4* nrm, double* rhs) {
+                                const float* lsc_point, const double* lsc_d, float4* nrm, double* rhs, int* kept,
+                                int* kept_count) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;     // global (obstacle, segment)
     if (t >= total_obs * kM) return;
     const int o = t / kM, m = t % kM;
@@ -202,6 +284,8 @@ __global__ void k_rows_from_lsc(int n_problems, const int* obs_offset, int total
     while (b + 1 < n_problems && obs_offset[b + 1] <= o) b++;
     const int n_b = obs_offset[b + 1] - obs_offset[b];
     const int p = kM * obs_offset[b] + m * n_b + (o - obs_offset[b]);
+    kept[p] = p - kM * obs_offset[b];                 // every pair is swept (no culling at the operator level)
+    if (o == obs_offset[b] && m == 0) kept_count[b] = kM * n_b;
     const size_t pitch = (size_t)total_obs * kM;
     const float* nv = lsc_normal + ((size_t)o * kM + m) * 3;
     const double ax = (double)nv[0], ay = (double)nv[1], az = (double)nv[2];
@@ -214,10 +298,12 @@ __global__ void k_rows_from_lsc(int n_problems, const int* obs_offset, int total
     }
 }
 void launch_rows_from_lsc(int n_problems, const int* obs_offset, int total_obs, const float* lsc_normal,
-                          const float* lsc_point, const double* lsc_d, float4* nrm, double* rhs, cudaStream_t s) {
+                          const float* lsc_point, const double* lsc_d, float4* nrm, double* rhs, int* kept,
+                          int* kept_count, cudaStream_t s) {
     if (total_obs <= 0) return;
     const int n = total_obs * kM;
-    k_rows_from_lsc<<<(n + 127) / 128, 128, 0, s>>>(n_problems, obs_offset, total_obs, lsc_normal, lsc_point, lsc_d, nrm, rhs);
+    k_rows_from_lsc<<<(n + 127) / 128, 128, 0, s>>>(n_problems, obs_offset, total_obs, lsc_normal, lsc_point, lsc_d, nrm, rhs,
+                                                    kept, kept_count);
 }
 
 // ------------------------------------------------------------------------------------------------------------

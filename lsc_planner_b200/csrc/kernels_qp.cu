@@ -5,24 +5,29 @@
 //
 // Formulation (qp_tables.hpp): with the whitened null-space basis of the equality rows the QP is the least-distance
 // problem  min |v|^2  s.t.  n_j . v >= -s_j(x0)  in 39 dimensions, x = x0 + (G (+) G (+) G) v. It is solved by a dual
-// active-set method (Goldfarb-Idnani with an identity Hessian): start at the unconstrained minimiser v = 0, pick a
-// violated row, move along the projection of its normal onto the null space of the active normals until the row is
-// satisfied or an active multiplier reaches zero (then that row leaves), repeat. The orthogonal factor J (39x39) and
-// the triangular factor R of the active normals live in shared memory; adding a row is one Householder reflection
-// applied by all 32 lanes (one J row each), dropping a row is a sequence of Givens rotations.
+// active-set method (Goldfarb-Idnani with an identity Hessian): start at the unconstrained minimiser, pick a violated
+// row, move along the projection z of its normal onto the orthogonal complement of the active normals until the row
+// is met or an active multiplier reaches zero (then that row leaves), repeat.
 //
-// Rows are never assembled as a matrix: bounds (SFC boxes + world box), velocity and acceleration limits are priced
-// from x directly; LSC rows are priced from the row store written by k_lsc_build (3 non-zeros each). LSC pricing is
-// two-tier: the working set (pairs selected by k_lsc_build, plus every pair found violated later) is priced at every
-// iteration; only when nothing in it is violated does the warp sweep ALL pairs of the agent (coalesced, pair index
-// fastest across lanes). The solve ends when such a full sweep finds no violated row, so the result satisfies every
-// row of the reference's QP and is its unique minimiser.
+// Factorisation: only a THIN orthonormal basis Q (39 x q) of the q active normals and the q x q triangle R
+// (N_active = Q R) are kept, in shared memory. The projection is two passes of classical Gram-Schmidt against Q
+// (re-orthogonalised, so it is as accurate as a full QR), adding a row appends z/|z| as a new column, dropping a row
+// is a sequence of Givens rotations on R's rows and Q's columns. Work per iteration is O(39 q), q ~ 5, instead of
+// the O(39^2) of a full orthogonal factor.
+//
+// Rows are never assembled as a matrix. Bounds (SFC boxes + world box), velocity and acceleration limits are priced
+// from x with per-lane constants held in registers. LSC rows come from the row store written by k_lsc_build (three
+// non-zeros each) and are priced in two tiers: the working set (pairs selected by k_lsc_build plus every pair found
+// violated later; its first 64 pairs are cached in shared memory) at every iteration, and ALL kept pairs of the agent
+// (the pairs that survived k_lsc_build's exact culling) only when nothing in the working set is violated. The solve ends
+// when such a sweep finds no row violated beyond the feasibility tolerance.
 #include "kernels.hpp"
 
 namespace lscgpu {
 
 constexpr int NR = kRed;        // 39
-constexpr int LD = 39;          // row pitch of J and R (odd pitch: row-per-lane accesses are bank-conflict free)
+constexpr int LD = 39;          // row pitch of Q and R (odd: row-per-lane accesses are bank-conflict free)
+constexpr int WC = 64;          // working-set pairs cached in shared memory
 // Primal feasibility tolerance = CPLEX's default EpRHS (the reference sets no tolerance, src/traj_optimizer.cpp:42-54):
 // like a dual simplex, a row enters the working set only when violated by more than this; entered rows are then met
 // exactly. Trajectories travel as float32, so agents in contact see hulls ~1e-7 closer than r_i + r_j; an exact
@@ -38,15 +43,15 @@ struct SelectedRow {
 };
 
 struct QpShared {
-    double J[NR * LD];
-    double R[NR * LD];
+    double Q[NR * LD];          // columns 0..q-1: orthonormal basis of the active normals
+    double R[NR * LD];          // upper triangle, row-major
     double G[kAx * kFree];
     double x[kNv];
-    double v[NR], nv[NR], d[NR], z[NR], rr[NR], lam[NR], u[NR];
+    double nv[NR], z[NR], d[NR], tmp[NR], rr[NR], lam[NR];
     double inv_gn[kAx];
-    double inv_dyn[45];
-    double lb[15], ub[15];      // [m][axis]
-    double vmax[3], amax[3];
+    double w_rhs[WC * 6];
+    float4 w_nrm[WC];
+    int w_pair[WC];
     int act[NR];
     SelectedRow sel;
 };
@@ -77,61 +82,68 @@ __device__ __forceinline__ Best warp_argmin(Best b) {
     return b;
 }
 
-// bounds + dynamic limits (ids 0..449)
-__device__ __forceinline__ void price_fixed(Best& best, const QpShared& S, int q, int lane, double vel_coef,
+// Per-lane constants of the fixed rows (ids 0..449): 3 variables and 5 dynamic-limit stencils per lane.
+struct FixedRows {
+    int bvar[3];            // variable index or -1
+    double blo[3], bhi[3], big[3];
+    int dbase[5];           // first variable of the stencil or -1
+    int dkind[5];           // 0 velocity, 1 acceleration
+    int did[5];             // row id of side 0
+    double dlim[5], dinv[5];
+};
+
+__device__ __forceinline__ void price_fixed(Best& best, const QpShared& S, int q, const FixedRows& F, double vel_coef,
                                             double acc_coef) {
-    for (int var = lane; var < kNv; var += 32) {
-        const int k = var / kAx, mi = var % kAx, m = mi / 6, i = mi % 6;
-        if (m == 0 && i < kPhi) continue;
-        const double xv = S.x[var], ig = S.inv_gn[mi];
-        consider(best, S, q, xv - S.lb[m * 3 + k], ig, var * 2);
-        consider(best, S, q, S.ub[m * 3 + k] - xv, ig, var * 2 + 1);
+#pragma unroll
+    for (int t = 0; t < 3; t++) {
+        if (F.bvar[t] < 0) continue;
+        const double xv = S.x[F.bvar[t]];
+        consider(best, S, q, xv - F.blo[t], F.big[t], F.bvar[t] * 2);
+        consider(best, S, q, F.bhi[t] - xv, F.big[t], F.bvar[t] * 2 + 1);
     }
-    for (int idx = lane; idx < 135; idx += 32) {
-        const int k = idx / 45, rem = idx % 45, m = rem / 9, j = rem % 9;
-        const int base = k * kAx + m * 6;
-        double expr, lim;
-        if (j < 5) {
-            if (m == 0 && j < 2) continue;
-            expr = vel_coef * (S.x[base + j + 1] - S.x[base + j]);
-            lim = S.vmax[k];
-        } else {
-            const int i = j - 5;
-            if (m == 0 && i == 0) continue;
-            expr = acc_coef * (S.x[base + i + 2] - 2.0 * S.x[base + i + 1] + S.x[base + i]);
-            lim = S.amax[k];
-        }
-        const double inv = S.inv_dyn[m * 9 + j];
-        consider(best, S, q, lim - expr, inv, kFixedRows - 270 + idx * 2);
-        consider(best, S, q, lim + expr, inv, kFixedRows - 270 + idx * 2 + 1);
+#pragma unroll
+    for (int t = 0; t < 5; t++) {
+        if (F.dbase[t] < 0) continue;
+        const double* c = S.x + F.dbase[t];
+        const double expr = F.dkind[t] == 0 ? vel_coef * (c[1] - c[0]) : acc_coef * (c[2] - 2.0 * c[1] + c[0]);
+        consider(best, S, q, F.dlim[t] - expr, F.dinv[t], F.did[t]);
+        consider(best, S, q, F.dlim[t] + expr, F.dinv[t], F.did[t] + 1);
     }
 }
 
 // one (obstacle, segment) pair: up to 6 rows. Returns true when a row of the pair is violated beyond the tolerance.
-__device__ __forceinline__ bool price_pair(Best& best, const QpShared& S, int q, int p, int n_obs, const float4* nrm,
-                                             const double* rhs, size_t pitch) {
-    const int m = p / n_obs;
-    const float4 nr = nrm[p];
+__device__ __forceinline__ bool price_pair_vals(Best& best, const QpShared& S, int q, int p, int m, float4 nr,
+                                                const double* r6) {
     const double ax = (double)nr.x, ay = (double)nr.y, az = (double)nr.z, inv = (double)nr.w;
     bool violated = false;
-    for (int i = (m == 0 ? kPhi : 0); i < 6; i++) {
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        if (m == 0 && i < kPhi) continue;
         const int vi = m * 6 + i;
-        const double slack = ax * S.x[vi] + ay * S.x[kAx + vi] + az * S.x[2 * kAx + vi] - rhs[(size_t)i * pitch + p];
+        const double slack = ax * S.x[vi] + ay * S.x[kAx + vi] + az * S.x[2 * kAx + vi] - r6[i];
         violated |= slack < -kFeasTol;
         consider(best, S, q, slack, inv * S.inv_gn[vi], kFixedRows + p * 6 + i);
     }
     return violated;
 }
 
+__device__ __forceinline__ void load_pair(int p, const float4* nrm, const double* rhs, size_t pitch, float4& nr,
+                                          double* r6) {
+    nr = nrm[p];
+#pragma unroll
+    for (int i = 0; i < 6; i++) r6[i] = rhs[(size_t)i * pitch + p];
+}
+
 __device__ __forceinline__ void decode_row(QpShared& S, int id, int n_obs, const float4* nrm, const double* rhs,
-                                           size_t pitch, double vel_coef, double acc_coef) {
+                                           size_t pitch, double vel_coef, double acc_coef, const double* lb,
+                                           const double* ub, const double* vmax, const double* amax) {
     SelectedRow& r = S.sel;
     if (id < 180) {
         const int var = id >> 1, side = id & 1;
         const int k = var / kAx, mi = var % kAx, m = mi / 6;
         r.nnz = 1; r.idx[0] = var;
-        if (side == 0) { r.a[0] = 1.0; r.b = S.lb[m * 3 + k]; }
-        else { r.a[0] = -1.0; r.b = -S.ub[m * 3 + k]; }
+        if (side == 0) { r.a[0] = 1.0; r.b = lb[m * 3 + k]; }
+        else { r.a[0] = -1.0; r.b = -ub[m * 3 + k]; }
     } else if (id < kFixedRows) {
         const int e = id - 180, side = e & 1, idx = e >> 1;
         const int k = idx / 45, rem = idx % 45, m = rem / 9, j = rem % 9;
@@ -139,11 +151,11 @@ __device__ __forceinline__ void decode_row(QpShared& S, int id, int n_obs, const
         const double sg = side == 0 ? -1.0 : 1.0;
         if (j < 5) {
             r.nnz = 2; r.idx[0] = base + j + 1; r.idx[1] = base + j;
-            r.a[0] = sg * vel_coef; r.a[1] = -sg * vel_coef; r.b = -S.vmax[k];
+            r.a[0] = sg * vel_coef; r.a[1] = -sg * vel_coef; r.b = -vmax[k];
         } else {
             const int i = j - 5;
             r.nnz = 3; r.idx[0] = base + i + 2; r.idx[1] = base + i + 1; r.idx[2] = base + i;
-            r.a[0] = sg * acc_coef; r.a[1] = -2.0 * sg * acc_coef; r.a[2] = sg * acc_coef; r.b = -S.amax[k];
+            r.a[0] = sg * acc_coef; r.a[1] = -2.0 * sg * acc_coef; r.a[2] = sg * acc_coef; r.b = -amax[k];
         }
     } else {
         const int e = id - kFixedRows, p = e / 6, i = e % 6, m = p / n_obs, vi = m * 6 + i;
@@ -162,7 +174,7 @@ __device__ __forceinline__ double selected_slack(const QpShared& S) {
 }
 
 // remove active row l: delete column l of R, restore the triangle with Givens rotations (rows j, j+1 of R,
-// columns j, j+1 of J)
+// columns j, j+1 of Q)
 __device__ __forceinline__ void drop_active(QpShared& S, int& q, int l, int lane) {
     __syncwarp();
     for (int r = lane; r < q; r += 32) {
@@ -183,10 +195,11 @@ __device__ __forceinline__ void drop_active(QpShared& S, int& q, int l, int lane
             S.R[j * LD + k] = c * t1 + s * t2;
             S.R[(j + 1) * LD + k] = -s * t1 + c * t2;
         }
+        if (lane == 0) S.R[(j + 1) * LD + j] = 0.0;
         for (int r = lane; r < NR; r += 32) {
-            const double t1 = S.J[r * LD + j], t2 = S.J[r * LD + j + 1];
-            S.J[r * LD + j] = c * t1 + s * t2;
-            S.J[r * LD + j + 1] = -s * t1 + c * t2;
+            const double t1 = S.Q[r * LD + j], t2 = S.Q[r * LD + j + 1];
+            S.Q[r * LD + j] = c * t1 + s * t2;
+            S.Q[r * LD + j + 1] = -s * t1 + c * t2;
         }
     }
     __syncwarp();
@@ -194,17 +207,19 @@ __device__ __forceinline__ void drop_active(QpShared& S, int& q, int l, int lane
 
 __global__ void __launch_bounds__(32) k_qp_solve(QpLaunch L) {
     __shared__ QpShared S;
+    __shared__ double s_lb[15], s_ub[15], s_vmax[3], s_amax[3];
     const int b = blockIdx.x;
     const int lane = threadIdx.x;
     const bool batch = L.obs_offset != nullptr;
     const int agent = L.agent_index ? L.agent_index[b] : L.agent_base + b;
     const int di = batch ? b : agent;                 // index into state9/goal3/ts/boxes
     const int n_obs = batch ? (L.obs_offset[b + 1] - L.obs_offset[b]) : L.n_obs;
-    const int P = kPairsPerObs * n_obs;
     const size_t pitch = (size_t)L.P_pad;
     const float4* nrm = batch ? L.nrm + (size_t)kPairsPerObs * L.obs_offset[b] : L.nrm + (size_t)b * L.P_pad;
     const double* rhs = batch ? L.rhs + (size_t)kPairsPerObs * L.obs_offset[b] : L.rhs + (size_t)b * 6 * L.P_pad;
     int* cand = L.cand + (size_t)b * L.cand_cap;
+    const int* kept = batch ? L.kept + (size_t)kPairsPerObs * L.obs_offset[b] : L.kept + (size_t)b * L.P_pad;
+    const int n_kept = L.kept_count[b];
     const QpTablesDev& T = *L.T;
     const int ts = L.ts[di];
     const double vel_coef = T.vel_coef, acc_coef = T.acc_coef;
@@ -213,7 +228,6 @@ __global__ void __launch_bounds__(32) k_qp_solve(QpLaunch L) {
     // ---- stage tables and problem data ------------------------------------------------------------------------
     for (int e = lane; e < kAx * kFree; e += 32) S.G[e] = (&T.G[ts - 1][0][0])[e];
     for (int e = lane; e < kAx; e += 32) S.inv_gn[e] = 1.0 / T.gnorm[ts - 1][e];
-    for (int e = lane; e < 45; e += 32) S.inv_dyn[e] = 1.0 / (&T.dyn_norm[ts - 1][0][0])[e];
     if (lane < 15) {
         const int m = lane / 3, k = lane % 3;
         double lo = (double)L.wmin[k], hi = (double)L.wmax[k];
@@ -222,9 +236,9 @@ __global__ void __launch_bounds__(32) k_qp_solve(QpLaunch L) {
             lo = fmax(lo, (double)bx[k]);
             hi = fmin(hi, (double)bx[3 + k]);
         }
-        S.lb[lane] = lo; S.ub[lane] = hi;
+        s_lb[lane] = lo; s_ub[lane] = hi;
     }
-    if (lane < 3) { S.vmax[lane] = ac.vmax[lane]; S.amax[lane] = ac.amax[lane]; }
+    if (lane < 3) { s_vmax[lane] = ac.vmax[lane]; s_amax[lane] = ac.amax[lane]; }
     const double* st = L.state9 + (size_t)di * 9;
     const double* gl = L.goal3 + (size_t)di * 3;
     for (int e = lane; e < kNv; e += 32) {
@@ -232,44 +246,105 @@ __global__ void __launch_bounds__(32) k_qp_solve(QpLaunch L) {
         const double* Xs = T.Xs[ts - 1][i];
         S.x[e] = Xs[0] * st[k] + Xs[1] * st[3 + k] + Xs[2] * st[6 + k] + T.xg[ts - 1][i] * gl[k];
     }
-    for (int e = lane; e < NR * LD; e += 32) { S.J[e] = 0.0; S.R[e] = 0.0; }
     __syncwarp();
-    for (int e = lane; e < NR; e += 32) { S.J[e * LD + e] = 1.0; S.v[e] = 0.0; }
-    __syncwarp();
+    // per-lane constants of the fixed rows
+    FixedRows F;
+#pragma unroll
+    for (int t = 0; t < 3; t++) {
+        const int var = lane + 32 * t;
+        F.bvar[t] = -1; F.blo[t] = F.bhi[t] = F.big[t] = 0.0;
+        if (var < kNv) {
+            const int k = var / kAx, mi = var % kAx, m = mi / 6, i = mi % 6;
+            if (!(m == 0 && i < kPhi)) {
+                F.bvar[t] = var; F.blo[t] = s_lb[m * 3 + k]; F.bhi[t] = s_ub[m * 3 + k]; F.big[t] = S.inv_gn[mi];
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 5; t++) {
+        const int idx = lane + 32 * t;
+        F.dbase[t] = -1; F.dkind[t] = 0; F.did[t] = 0; F.dlim[t] = F.dinv[t] = 0.0;
+        if (idx < 135) {
+            const int k = idx / 45, rem = idx % 45, m = rem / 9, j = rem % 9;
+            const bool vel = j < 5;
+            const int i = vel ? j : j - 5;
+            const bool skip = vel ? (m == 0 && j < 2) : (m == 0 && i == 0);
+            if (!skip) {
+                F.dbase[t] = k * kAx + m * 6 + i;
+                F.dkind[t] = vel ? 0 : 1;
+                F.did[t] = 180 + idx * 2;
+                F.dlim[t] = vel ? s_vmax[k] : s_amax[k];
+                F.dinv[t] = 1.0 / T.dyn_norm[ts - 1][m][j];
+            }
+        }
+    }
 
+    for (int e = lane; e < NR * LD; e += 32) S.R[e] = 0.0;
     int q = 0, iters = 0, status = LSCGPU_QP_OK;
     int n_work = min(L.cand_count[b], L.cand_cap);
+    // cache the head of the working set
+    for (int w = lane; w < min(n_work, WC); w += 32) {
+        const int p = cand[w];
+        float4 nr; double r6[6];
+        load_pair(p, nrm, rhs, pitch, nr, r6);
+        S.w_pair[w] = p; S.w_nrm[w] = nr;
+#pragma unroll
+        for (int i = 0; i < 6; i++) S.w_rhs[w * 6 + i] = r6[i];
+    }
+    __syncwarp();
     unsigned long long rows_priced = 0, full_passes = 0;
 
     while (true) {
         // ---- pricing --------------------------------------------------------------------------------------------
         Best best{0.0, -1};
-        price_fixed(best, S, q, lane, vel_coef, acc_coef);
-        for (int w = lane; w < n_work; w += 32) price_pair(best, S, q, cand[w], n_obs, nrm, rhs, pitch);
+        price_fixed(best, S, q, F, vel_coef, acc_coef);
+        for (int w = lane; w < min(n_work, WC); w += 32) {
+            const int p = S.w_pair[w];
+            price_pair_vals(best, S, q, p, p / n_obs, S.w_nrm[w], S.w_rhs + w * 6);
+        }
+        for (int w = WC + lane; w < n_work; w += 32) {
+            const int p = cand[w];
+            float4 nr; double r6[6];
+            load_pair(p, nrm, rhs, pitch, nr, r6);
+            price_pair_vals(best, S, q, p, p / n_obs, nr, r6);
+        }
         rows_priced += 414 + 6ull * n_work;
         best = warp_argmin(best);
         if (best.id < 0) {
             // nothing violated among bounds, limits and the working set: sweep every LSC pair of the agent
             full_passes++;
-            rows_priced += 6ull * P;
-            for (int p0 = 0; p0 < P; p0 += 32) {
-                const int p = p0 + lane;
-                bool viol = false;
-                if (p < P) viol = price_pair(best, S, q, p, n_obs, nrm, rhs, pitch);
-                const unsigned mask = __ballot_sync(0xffffffffu, viol);
-                if (viol) {
-                    const int slot = n_work + __popc(mask & ((1u << lane) - 1u));
-                    if (slot < L.cand_cap) cand[slot] = p;
+            rows_priced += 6ull * n_kept;
+            for (int s0 = 0; s0 < n_kept; s0 += 64) {
+                // two pairs per lane in flight
+                const int pa = s0 + lane < n_kept ? kept[s0 + lane] : -1;
+                const int pb = s0 + 32 + lane < n_kept ? kept[s0 + 32 + lane] : -1;
+                float4 nra, nrb; double ra[6], rb[6];
+                if (pa >= 0) load_pair(pa, nrm, rhs, pitch, nra, ra);
+                if (pb >= 0) load_pair(pb, nrm, rhs, pitch, nrb, rb);
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int p = h == 0 ? pa : pb;
+                    bool viol = false;
+                    if (p >= 0) viol = price_pair_vals(best, S, q, p, p / n_obs, h == 0 ? nra : nrb, h == 0 ? ra : rb);
+                    const unsigned mask = __ballot_sync(0xffffffffu, viol);
+                    if (viol) {
+                        const int slot = n_work + __popc(mask & ((1u << lane) - 1u));
+                        if (slot < WC) {
+                            S.w_pair[slot] = p; S.w_nrm[slot] = h == 0 ? nra : nrb;
+#pragma unroll
+                            for (int i = 0; i < 6; i++) S.w_rhs[slot * 6 + i] = h == 0 ? ra[i] : rb[i];
+                        } else if (slot < L.cand_cap) cand[slot] = p;
+                    }
+                    n_work = min(n_work + __popc(mask), L.cand_cap);
                 }
-                n_work = min(n_work + __popc(mask), L.cand_cap);
             }
             __syncwarp();
             best = warp_argmin(best);
-            if (best.id < 0) break;             // optimal: no violated row anywhere
+            if (best.id < 0) break;             // no row violated beyond the tolerance anywhere: done
         }
-        if (lane == 0) decode_row(S, best.id, n_obs, nrm, rhs, pitch, vel_coef, acc_coef);
+        if (lane == 0) decode_row(S, best.id, n_obs, nrm, rhs, pitch, vel_coef, acc_coef, s_lb, s_ub, s_vmax, s_amax);
         __syncwarp();
-        // whitened normal  nv = (G (+) G (+) G)^T a
+        // whitened normal  nv = (G (+) G (+) G)^T a, normalised
         double part = 0.0;
         for (int c = lane; c < NR; c += 32) {
             const int k = c / kFree, cc = c % kFree;
@@ -288,22 +363,42 @@ __global__ void __launch_bounds__(32) k_qp_solve(QpLaunch L) {
         bool fail = false;
         while (true) {
             if (++iters > L.max_iter) { status = LSCGPU_QP_MAXITER; fail = true; break; }
-            // d = J^T nv
-            double zz_part = 0.0;
-            for (int c = lane; c < NR; c += 32) {
-                double s = 0.0;
-                for (int r = 0; r < NR; r++) s += S.J[r * LD + c] * S.nv[r];
-                S.d[c] = s;
-                if (c >= q) zz_part += s * s;
-            }
-            const double zz = warp_sum(zz_part);
+            // ---- z = (I - Q Q^T) nv by two Gram-Schmidt passes; d = Q^T nv ---------------------------------------
+            for (int c = lane; c < NR; c += 32) { S.z[c] = S.nv[c]; S.d[c] = 0.0; }
             __syncwarp();
-            // z = J2 d2 (step direction), rr = R^-1 d1 (change of the active multipliers)
-            for (int r = lane; r < NR; r += 32) {
-                double s = 0.0;
-                for (int c = q; c < NR; c++) s += S.J[r * LD + c] * S.d[c];
-                S.z[r] = s;
+            if (q > 0) {
+#pragma unroll 1
+                for (int pass = 0; pass < 2; pass++) {
+                    for (int k = lane; k < q; k += 32) {          // lane k: column k of Q against z
+                        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+                        for (int r = 0; r < NR; r += 3) {
+                            s0 += S.Q[r * LD + k] * S.z[r];
+                            s1 += S.Q[(r + 1) * LD + k] * S.z[r + 1];
+                            s2 += S.Q[(r + 2) * LD + k] * S.z[r + 2];
+                        }
+                        const double s = s0 + s1 + s2;
+                        S.tmp[k] = s;
+                        S.d[k] += s;
+                    }
+                    __syncwarp();
+                    for (int r = lane; r < NR; r += 32) {         // lane r: row r of Q against the coefficients
+                        double s0 = 0.0, s1 = 0.0;
+                        int k = 0;
+                        for (; k + 1 < q; k += 2) {
+                            s0 += S.Q[r * LD + k] * S.tmp[k];
+                            s1 += S.Q[r * LD + k + 1] * S.tmp[k + 1];
+                        }
+                        if (k < q) s0 += S.Q[r * LD + k] * S.tmp[k];
+                        S.z[r] -= s0 + s1;
+                    }
+                    __syncwarp();
+                }
             }
+            double zz_part = 0.0;
+            for (int c = lane; c < NR; c += 32) zz_part += S.z[c] * S.z[c];
+            const double zz = warp_sum(zz_part);
+            // rr = R^-1 d (change of the active multipliers per unit step)
             for (int k = lane; k < q; k += 32) S.rr[k] = S.d[k];
             for (int c = q - 1; c >= 0; c--) {
                 __syncwarp();
@@ -336,7 +431,6 @@ __global__ void __launch_bounds__(32) k_qp_solve(QpLaunch L) {
             for (int k = lane; k < q; k += 32) S.lam[k] -= t * S.rr[k];
             lam_p += t;
             if (!primal) { drop_active(S, q, l, lane); continue; }
-            for (int c = lane; c < NR; c += 32) S.v[c] += t * S.z[c];
             for (int e = lane; e < kNv; e += 32) {
                 const int k = e / kAx, i = e % kAx;
                 double s = 0.0;
@@ -346,24 +440,12 @@ __global__ void __launch_bounds__(32) k_qp_solve(QpLaunch L) {
             }
             __syncwarp();
             if (t2 <= t1) {
-                // add the row: Householder reflection H with (J2 H)^T nv = (alpha, 0, ..., 0)
-                const double dq = S.d[q];
-                const double alpha = dq > 0.0 ? -sqrt(zz) : sqrt(zz);
-                if (q < NR - 1) {
-                    for (int c = q + lane; c < NR; c += 32) S.u[c] = (c == q) ? dq - alpha : S.d[c];
-                    const double uu = zz - dq * dq + (dq - alpha) * (dq - alpha);
-                    const double beta = 2.0 / uu;
-                    __syncwarp();
-                    for (int r = lane; r < NR; r += 32) {
-                        double s = 0.0;
-                        for (int c = q; c < NR; c++) s += S.J[r * LD + c] * S.u[c];
-                        s *= beta;
-                        for (int c = q; c < NR; c++) S.J[r * LD + c] -= s * S.u[c];
-                    }
-                }
+                // the row becomes active: new basis column z / |z|, new column (d, |z|) of R
+                const double zn = sqrt(zz), izn = 1.0 / zn;
+                for (int r = lane; r < NR; r += 32) S.Q[r * LD + q] = S.z[r] * izn;
                 for (int k = lane; k < q; k += 32) S.R[k * LD + q] = S.d[k];
                 if (lane == 0) {
-                    S.R[q * LD + q] = (q < NR - 1) ? alpha : dq;
+                    S.R[q * LD + q] = zn;
                     S.act[q] = best.id;
                     S.lam[q] = lam_p;
                 }

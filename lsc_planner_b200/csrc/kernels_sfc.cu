@@ -110,47 +110,57 @@ void launch_edt_build(const int32_t* keys_dev, int n_keys, DistMapDev dm, const 
 // ------------------------------------------------------------------------------------------------------------
 // SFC expansion, one warp per seed.
 // ------------------------------------------------------------------------------------------------------------
-struct AxisSamples {      // voxel cells (key - offset) the reference's scan visits along one axis
-    int extra;            // the it == 0 sample
-    int lo, hi;           // it = 1 .. size-1 (contiguous)
+// A box is tracked twice: as the reference's doubles (faces moved by repeated +-res, so the float32 output carries
+// exactly the reference's rounding) and as integer lattice planes (plane P <-> coordinate P*res) that drive the voxel
+// tests. For |coordinate| < 64 m the reference's float sample `(float)(box + it*res) +- 1e-5f` always lands in voxel
+// P (+ nudge) or P-1 (- nudge): float32 rounding there is < 4e-6 per operation, below the 1e-5 nudge, so the integer
+// model reproduces OcTree::coordToKey of every sample exactly (the engine rejects larger worlds).
+struct LatticeBox {
+    double d[6];          // min xyz, max xyz
+    int p[6];             // lattice planes of the faces
 };
 
 struct SfcCtx {
     DistMapDev dm;
     const int* sat;       // table of this seed's radius
-    double res, inv_res;
+    double res;
     double wmin[3], wmax[3];
+    double wmin_nudge[3]; // world_min + 1e-5 (include/corridor_constructor.hpp:104)
     int lane;
 };
-
-// OcTree::coordToKey of a float sample nudged by +-1e-5 (include/corridor_constructor.hpp:93-111)
-__device__ __forceinline__ int sample_cell(const SfcCtx& c, double coord, bool minus, int axis) {
-    const float sp = (float)coord;
-    const float p = __fadd_rn(sp, minus ? (float)(-1e-5) : (float)(1e-5));
-    return (int)floor(__dmul_rn(c.inv_res, (double)p)) - c.dm.off[axis];
-}
 
 __device__ __forceinline__ int sat_at(const SfcCtx& c, int x, int y, int z) {
     return c.sat[((size_t)x * (c.dm.size[1] + 1) + y) * (c.dm.size[2] + 1) + z];
 }
 
-// isObstacleInBox(box, margin): true iff any sampled voxel is blocked or outside the map.
-__device__ bool obstacle_in_box(const SfcCtx& c, const double* box) {
-    AxisSamples ax[3];
+// number of blocked voxels in the cell box [lo, hi] (inclusive, inside the map): 8 table reads by lanes 0-7
+__device__ __forceinline__ int blocked_in_cells(const SfcCtx& c, const int* lo, const int* hi) {
+    int v = 0;
+    if (c.lane < 8) {
+        const int cx = (c.lane & 1) ? hi[0] + 1 : lo[0];
+        const int cy = (c.lane & 2) ? hi[1] + 1 : lo[1];
+        const int cz = (c.lane & 4) ? hi[2] + 1 : lo[2];
+        // inclusion-exclusion: + when the number of "lo" picks is even, i.e. an odd number of "hi+1" picks
+        v = (__popc(c.lane) & 1) ? sat_at(c, cx, cy, cz) : -sat_at(c, cx, cy, cz);
+    }
+    return warp_sum_int(v);
+}
+
+// isObstacleInBox(box, margin) (include/corridor_constructor.hpp:81-122): true iff any sampled voxel is blocked or
+// outside the map. Per axis the scan visits the voxel of the it == 0 sample (below the min face unless the face sits
+// on the world boundary) and the voxels lo+1 .. hi of the it >= 1 samples (voxel lo again for a flat box).
+__device__ bool obstacle_in_box(const SfcCtx& c, const LatticeBox& bx) {
+    int extra[3], lo[3], hi[3];
     bool outside = false;
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-        const int bs = (int)round(__ddiv_rn(__dsub_rn(box[i + 3], box[i]), c.res)) + 1;
-        const bool minus = box[i] > __dadd_rn(c.wmin[i], 1e-5);
-        ax[i].extra = sample_cell(c, box[i], minus, i);
-        if (bs <= 1) {
-            ax[i].lo = ax[i].hi = sample_cell(c, box[i], false, i);
-        } else {
-            ax[i].lo = sample_cell(c, __dadd_rn(box[i], __dmul_rn(1.0, c.res)), false, i);
-            ax[i].hi = sample_cell(c, __dadd_rn(box[i], __dmul_rn((double)(bs - 1), c.res)), false, i);
-        }
+        const int pl = bx.p[i], ph = bx.p[i + 3];
+        const bool minus = bx.d[i] > c.wmin_nudge[i];
+        extra[i] = (minus ? pl - 1 : pl) - c.dm.off[i];
+        if (ph - pl + 1 <= 1) { lo[i] = hi[i] = pl - c.dm.off[i]; }
+        else { lo[i] = pl + 1 - c.dm.off[i]; hi[i] = ph - c.dm.off[i]; }
         const int n = c.dm.size[i];
-        if (ax[i].extra < 0 || ax[i].extra >= n || ax[i].lo < 0 || ax[i].hi >= n || ax[i].lo > ax[i].hi) outside = true;
+        if (extra[i] < 0 || extra[i] >= n || lo[i] < 0 || hi[i] >= n) outside = true;
     }
     if (outside) return true;       // getDistance = -1 outside the map: always below the threshold
     int sum = 0;
@@ -163,15 +173,15 @@ __device__ bool obstacle_in_box(const SfcCtx& c, const double* box) {
 #pragma unroll
         for (int i = 0; i < 3; i++) {
             const bool single = (sub >> i) & 1;
-            const int lo = single ? ax[i].extra : ax[i].lo;
-            const int hi = single ? ax[i].extra : ax[i].hi;
-            if ((corner >> i) & 1) coord[i] = hi + 1;
-            else { coord[i] = lo; sign = -sign; }
+            const int l = single ? extra[i] : lo[i];
+            const int u = single ? extra[i] : hi[i];
+            if ((corner >> i) & 1) coord[i] = u + 1;
+            else { coord[i] = l; sign = -sign; }
         }
         sum += sign * sat_at(c, coord[0], coord[1], coord[2]);
     }
     sum = warp_sum_int(sum);
-    return sum > 0;
+    return sum != 0;
 }
 
 __device__ __forceinline__ bool box_in_boundary(const SfcCtx& c, const double* b) {
@@ -204,43 +214,104 @@ __device__ void axis_candidates(const double* box, F3 goal, int* cand) {
     }
 }
 
-// expandBoxFromPoint: returns false when the seed box is blocked
-__device__ bool expand_from_point(const SfcCtx& c, F3 point, F3 goal, double* box) {
+// Largest k (power-of-two search, then refinement) such that the next k full round-robin cycles of expand_box are
+// guaranteed to pass every slab test: the voxel region all those tests can touch — the committed box grown by k on
+// each remaining candidate face, plus the one-voxel rim the +-1e-5 nudges reach — holds no blocked voxel, lies inside
+// the map, and the grown box stays inside the world.
+__device__ int free_cycles(const SfcCtx& c, const LatticeBox& box, unsigned cand_mask, int k_max) {
+    auto passes = [&](int k) -> bool {
+        int lo[3], hi[3];
+        bool ok = true;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const int kl = (cand_mask >> i) & 1 ? k : 0, kh = (cand_mask >> (i + 3)) & 1 ? k : 0;
+            lo[i] = box.p[i] - kl - 1 - c.dm.off[i];
+            hi[i] = box.p[i + 3] + kh - c.dm.off[i];
+            if (lo[i] < 0 || hi[i] >= c.dm.size[i]) ok = false;
+            // in-boundary test of the farthest slabs (1e-9 slack of isBoxInBoundary >> accumulated rounding)
+            if (box.d[i] - kl * c.res <= c.wmin[i] - 1e-9 + 1e-11) ok = false;
+            if (box.d[i + 3] + kh * c.res >= c.wmax[i] + 1e-9 - 1e-11) ok = false;
+        }
+        if (!ok) return false;
+        return blocked_in_cells(c, lo, hi) == 0;
+    };
+    if (k_max < 1 || !passes(1)) return 0;
+    int k = 1;
+    while (2 * k <= k_max && passes(2 * k)) k *= 2;
+    for (int step = k / 2; step >= 1; step /= 2)
+        if (k + step <= k_max && passes(k + step)) k += step;
+    return k;
+}
+
+// expandBoxFromPoint + expandSFCFromBox + expand_box: returns false when the seed box is blocked
+__device__ bool expand_from_point(const SfcCtx& c, F3 point, F3 goal, double* out) {
+    LatticeBox box, bc, bu;
     const float pt[3] = {point.x, point.y, point.z};
     for (int i = 0; i < 3; i++) {
         const double p = (double)pt[i];
         const double ratio = __ddiv_rn(p, c.res);
         const double rp = __dmul_rn(round(ratio), c.res);
-        if (fabs(__dsub_rn(p, rp)) < 0.01) { box[i] = rp; box[i + 3] = rp; }
-        else { box[i] = __dmul_rn(floor(ratio), c.res); box[i + 3] = __dmul_rn(ceil(ratio), c.res); }
+        if (fabs(__dsub_rn(p, rp)) < 0.01) {
+            box.d[i] = rp; box.d[i + 3] = rp;
+            box.p[i] = box.p[i + 3] = (int)round(ratio);
+        } else {
+            box.d[i] = __dmul_rn(floor(ratio), c.res); box.d[i + 3] = __dmul_rn(ceil(ratio), c.res);
+            box.p[i] = (int)floor(ratio); box.p[i + 3] = (int)ceil(ratio);
+        }
     }
     if (obstacle_in_box(c, box)) return false;
     int cand[6], n_cand = 6;
-    axis_candidates(box, goal, cand);
-    double bc[6], bu[6];
+    axis_candidates(box.d, goal, cand);
+    auto propose = [&](int axis) {       // bc = committed box + one slab on `axis`, bu = that slab
+        bu = bc;
+        if (axis < 3) {
+            bu.d[axis + 3] = bc.d[axis]; bu.p[axis + 3] = bc.p[axis];
+            bc.d[axis] = __dsub_rn(bc.d[axis], c.res); bc.p[axis] -= 1;
+            bu.d[axis] = bc.d[axis]; bu.p[axis] = bc.p[axis];
+        } else {
+            bu.d[axis - 3] = bc.d[axis]; bu.p[axis - 3] = bc.p[axis];
+            bc.d[axis] = __dadd_rn(bc.d[axis], c.res); bc.p[axis] += 1;
+            bu.d[axis] = bc.d[axis]; bu.p[axis] = bc.p[axis];
+        }
+    };
     int i = -1;
     while (n_cand > 0) {
-        for (int k = 0; k < 6; k++) { bc[k] = box[k]; bu[k] = box[k]; }
-        while (!obstacle_in_box(c, bu) && box_in_boundary(c, bu)) {
+        bc = box; bu = box;
+        bool pending = false;       // true once bu is a proposed slab (the first test after an erase is the whole box)
+        int cooldown = 0;
+        unsigned mask = 0;
+        for (int k = 0; k < n_cand; k++) mask |= 1u << cand[k];
+        while (true) {
+            if (pending && cooldown == 0) {
+                // State: `box` committed, slab of cand[i] proposed. One round-robin cycle = n_cand passed tests moves
+                // every candidate face one step and proposes cand[i]'s slab again. Skip k cycles that cannot fail.
+                const int k = free_cycles(c, box, mask, 1 << 14);
+                if (k > 0) {
+                    for (int t = 0; t < n_cand; t++) {
+                        const int axis = cand[t];
+                        double f = box.d[axis];
+                        for (int sidx = 0; sidx < k; sidx++) f = axis < 3 ? __dsub_rn(f, c.res) : __dadd_rn(f, c.res);
+                        box.d[axis] = f;
+                        box.p[axis] += axis < 3 ? -k : k;
+                    }
+                    bc = box;
+                    propose(cand[i]);
+                } else cooldown = n_cand;
+            }
+            if (cooldown > 0) cooldown--;
+            if (obstacle_in_box(c, bu) || !box_in_boundary(c, bu.d)) break;
             i++;
             if (i >= n_cand) i = 0;
-            const int axis = cand[i];
-            for (int k = 0; k < 6; k++) { box[k] = bc[k]; bu[k] = bc[k]; }
-            if (axis < 3) {
-                bu[axis + 3] = bc[axis];
-                bc[axis] = __dsub_rn(bc[axis], c.res);
-                bu[axis] = bc[axis];
-            } else {
-                bu[axis - 3] = bc[axis];
-                bc[axis] = __dadd_rn(bc[axis], c.res);
-                bu[axis] = bc[axis];
-            }
+            box = bc;
+            propose(cand[i]);
+            pending = true;
         }
         if (i < 0) i = 0;     // unreachable: the seed box was tested above
         for (int k = i; k < n_cand - 1; k++) cand[k] = cand[k + 1];
         n_cand--;
         if (i > 0) i--; else i = n_cand - 1;
     }
+    for (int k = 0; k < 6; k++) out[k] = box.d[k];
     return true;
 }
 
@@ -250,9 +321,11 @@ __global__ void __launch_bounds__(128) k_sfc_expand(SfcLaunch L) {
     SfcCtx c;
     c.dm = L.dm;
     c.res = L.res;
-    c.inv_res = __ddiv_rn(1.0, L.res);
     c.lane = threadIdx.x & 31;
-    for (int i = 0; i < 3; i++) { c.wmin[i] = (double)L.wmin[i]; c.wmax[i] = (double)L.wmax[i]; }
+    for (int i = 0; i < 3; i++) {
+        c.wmin[i] = (double)L.wmin[i]; c.wmax[i] = (double)L.wmax[i];
+        c.wmin_nudge[i] = __dadd_rn(c.wmin[i], 1e-5);
+    }
     const size_t tab = (size_t)(L.dm.size[0] + 1) * (L.dm.size[1] + 1) * (L.dm.size[2] + 1);
     double box[6];
     if (L.mode == 1) {

@@ -146,6 +146,8 @@ int orc_qp_dense(void* tv, const double* state9, const double* goal3, int ts, co
     return D.n_in;
 }
 
+void orc_set_tier_threshold(double t) { g_tier_threshold = t; }
+
 // ---- swarm ------------------------------------------------------------------------------------
 void* orc_swarm_create(int n_agents, double dt, double w, double wT, double res, double reset_threshold,
                        int use_octomap, const float* wmin, const float* wmax, const double* radius,

@@ -299,6 +299,11 @@ inline bool row_get(const QpTables& T, const QpProblem& p, int id, RowView& r) {
     return true;
 }
 
+// Test hook (debugging the CUDA kernel's two-tier pricing on the CPU): when finite, LSC rows are priced in two tiers
+// exactly like k_qp_solve — a working set of (obstacle, segment) pairs whose whitened slack at x0 is below this
+// threshold, extended by a full sweep whenever nothing in it is violated. Default: every row priced every iteration.
+inline double g_tier_threshold = INFINITY;
+
 // Goldfarb-Idnani dual active set on  min |v|^2  s.t.  n_j . v >= -slack0_j   (x = x0 + G v)
 inline void qp_solve(const QpTables& T, const QpProblem& p, QpResult& out, int max_iter = 2000) {
     const int n = QRED;
@@ -352,21 +357,38 @@ inline void qp_solve(const QpTables& T, const QpProblem& p, QpResult& out, int m
     };
 
     double nv[QRED], d[QRED], z[QRED], rr[QRED];
+    const bool tiered = g_tier_threshold < INFINITY;
+    std::vector<char> in_work(tiered ? p.n_rows : 0, 0);
+    int pbest = -1; double mu_best = -tol; RowView rb; double nb = 0;
+    auto price = [&](int id) -> bool {          // returns true when the row is violated beyond the tolerance
+        if (is_active[id]) return false;
+        RowView r;
+        if (!row_get(T, p, id, r)) return false;
+        double nn;
+        if (r.nnz == 1) nn = T.gnorm[ts - 1][r.idx[0] % QAX];
+        else if (id >= 450) nn = std::sqrt(r.a[0] * r.a[0] + r.a[1] * r.a[1] + r.a[2] * r.a[2]) * T.gnorm[ts - 1][r.idx[0] % QAX];
+        else nn = row_normal(r, nv);
+        double sl = row_slack(r);
+        if (tiered && id >= 450 && pbest == -2) {       // initial working-set selection at x0
+            if (!(sl / std::max(nn, 1e-300) >= g_tier_threshold)) in_work[(id - 450) / 6] = 1;
+            return false;
+        }
+        if (!(sl < -QP_FEAS_TOL)) return false;
+        double mu = sl / std::max(nn, 1e-300);
+        if (mu < mu_best) { mu_best = mu; pbest = id; rb = r; nb = nn; }
+        return true;
+    };
+    if (tiered) { pbest = -2; for (int id = 450; id < n_ids; id++) price(id); }
     while (true) {
         // pricing: most violated row in whitened distance
-        int pbest = -1; double mu_best = -tol; RowView rb; double nb = 0;
-        for (int id = 0; id < n_ids; id++) {
-            if (is_active[id]) continue;
-            RowView r;
-            if (!row_get(T, p, id, r)) continue;
-            double nn;
-            if (r.nnz == 1) nn = T.gnorm[ts - 1][r.idx[0] % QAX];
-            else if (id >= 450) nn = std::sqrt(r.a[0] * r.a[0] + r.a[1] * r.a[1] + r.a[2] * r.a[2]) * T.gnorm[ts - 1][r.idx[0] % QAX];
-            else nn = row_normal(r, nv);
-            double sl = row_slack(r);
-            if (!(sl < -QP_FEAS_TOL)) continue;
-            double mu = sl / std::max(nn, 1e-300);
-            if (mu < mu_best) { mu_best = mu; pbest = id; rb = r; nb = nn; }
+        pbest = -1; mu_best = -tol;
+        if (!tiered) {
+            for (int id = 0; id < n_ids; id++) price(id);
+        } else {
+            for (int id = 0; id < 450; id++) price(id);
+            for (int id = 450; id < n_ids; id++) if (in_work[(id - 450) / 6]) price(id);
+            if (pbest < 0)
+                for (int id = 450; id < n_ids; id++) if (price(id)) in_work[(id - 450) / 6] = 1;
         }
         if (pbest < 0) break;
         double nrm = row_normal(rb, nv);

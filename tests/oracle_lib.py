@@ -52,6 +52,7 @@ def lib():
         L.orc_qp_solve.argtypes = qp_args + [f64p, f64p]; L.orc_qp_solve.restype = C.c_int
         L.orc_qp_dense.argtypes = qp_args + [C.c_void_p, f64p, f64p, f64p, f64p, f64p, f64p, f64p, C.c_int]
         L.orc_qp_dense.restype = C.c_int
+        L.orc_set_tier_threshold.argtypes = [C.c_double]
         L.orc_swarm_create.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int,
                                        f32p, f32p, f64p, f64p, f64p, f64p, f64p]
         L.orc_swarm_create.restype = C.c_void_p
