@@ -18,7 +18,7 @@
 // Rows are never assembled as a matrix. Bounds (SFC boxes + world box), velocity and acceleration limits are priced
 // from x with per-lane constants held in registers. LSC rows come from the row store written by k_lsc_build (three
 // non-zeros each) and are priced in two tiers: the working set (pairs selected by k_lsc_build plus every pair found
-// violated later; its first 64 pairs are cached in shared memory) at every iteration, and ALL kept pairs of the agent
+// violated later; its first 32 pairs are cached in shared memory) at every iteration, and ALL kept pairs of the agent
 // (the pairs that survived k_lsc_build's exact culling) only when nothing in the working set is violated. The solve ends
 // when such a sweep finds no row violated beyond the feasibility tolerance.
 #include "kernels.hpp"
@@ -27,7 +27,7 @@ namespace lscgpu {
 
 constexpr int NR = kRed;        // 39
 constexpr int LD = 39;          // row pitch of Q and R (odd: row-per-lane accesses are bank-conflict free)
-constexpr int WC = 64;          // working-set pairs cached in shared memory
+constexpr int WC = 32;          // working-set pairs cached in shared memory
 // Primal feasibility tolerance = CPLEX's default EpRHS (the reference sets no tolerance, src/traj_optimizer.cpp:42-54):
 // like a dual simplex, a row enters the working set only when violated by more than this; entered rows are then met
 // exactly. Trajectories travel as float32, so agents in contact see hulls ~1e-7 closer than r_i + r_j; an exact
@@ -38,6 +38,7 @@ constexpr double kZeroTol = 1e-13;
 struct SelectedRow {
     int nnz;
     int idx[3];
+    int axis[3], var[3];      // idx = axis * 30 + var
     double a[3];
     double b;
 };
@@ -45,9 +46,8 @@ struct SelectedRow {
 struct QpShared {
     double Q[NR * LD];          // columns 0..q-1: orthonormal basis of the active normals
     double R[NR * LD];          // upper triangle, row-major
-    double G[kAx * kFree];
     double x[kNv];
-    double nv[NR], z[NR], d[NR], tmp[NR], rr[NR], lam[NR];
+    double nv[NR], z[NR], d[NR], tmp[NR], rr[NR], lam[NR], inv_diag[NR];
     double inv_gn[kAx];
     double w_rhs[WC * 6];
     float4 w_nrm[WC];
@@ -61,16 +61,13 @@ struct Best {
     int id;
 };
 
-__device__ __forceinline__ bool row_is_active(const QpShared& S, int q, int id) {
-    for (int k = 0; k < q; k++)
-        if (S.act[k] == id) return true;
-    return false;
-}
-// slack: a.x - b of the row; scale: 1 / (whitened length of its normal)
+// slack: a.x - b of the row; scale: 1 / (whitened length of its normal).
+// Active rows need no special treatment: they are met exactly (|slack| ~ 1e-13), far inside the tolerance, so they
+// can never be selected again while active (checked once per iteration on the winner only).
 __device__ __forceinline__ void consider(Best& b, const QpShared& S, int q, double slack, double scale, int id) {
     if (!(slack < -kFeasTol)) return;
     const double mu = scale < INFINITY ? slack * scale : -INFINITY;   // zero normal with positive rhs: infeasible row
-    if (mu < b.mu && !row_is_active(S, q, id)) { b.mu = mu; b.id = id; }
+    if (mu < b.mu) { b.mu = mu; b.id = id; }
 }
 __device__ __forceinline__ Best warp_argmin(Best b) {
 #pragma unroll
@@ -165,6 +162,7 @@ __device__ __forceinline__ void decode_row(QpShared& S, int id, int n_obs, const
         r.a[0] = (double)nr.x; r.a[1] = (double)nr.y; r.a[2] = (double)nr.z;
         r.b = rhs[(size_t)i * pitch + p];
     }
+    for (int t = 0; t < r.nnz; t++) { r.axis[t] = r.idx[t] / kAx; r.var[t] = r.idx[t] % kAx; }
 }
 
 __device__ __forceinline__ double selected_slack(const QpShared& S) {
@@ -203,6 +201,8 @@ __device__ __forceinline__ void drop_active(QpShared& S, int& q, int l, int lane
         }
     }
     __syncwarp();
+    for (int k = l + lane; k < q; k += 32) S.inv_diag[k] = 1.0 / S.R[k * LD + k];
+    __syncwarp();
 }
 
 __global__ void __launch_bounds__(32) k_qp_solve(QpLaunch L) {
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(32) k_qp_solve(QpLaunch L) {
     const AgentConstDev& ac = L.consts[agent];
 
     // ---- stage tables and problem data ------------------------------------------------------------------------
-    for (int e = lane; e < kAx * kFree; e += 32) S.G[e] = (&T.G[ts - 1][0][0])[e];
+    const double* __restrict__ Gt = &T.G[ts - 1][0][0];      // whitened basis of this ts (read-only, L1-resident)
     for (int e = lane; e < kAx; e += 32) S.inv_gn[e] = 1.0 / T.gnorm[ts - 1][e];
     if (lane < 15) {
         const int m = lane / 3, k = lane % 3;
@@ -280,6 +280,11 @@ __global__ void __launch_bounds__(32) k_qp_solve(QpLaunch L) {
     }
 
     for (int e = lane; e < NR * LD; e += 32) S.R[e] = 0.0;
+    // per-lane index constants (no divisions in the loop)
+    const int c_axis0 = lane / kFree, c_col0 = lane % kFree;      // whitened coordinate c = lane
+    int x_axis[3], x_var[3];
+#pragma unroll
+    for (int h = 0; h < 3; h++) { const int e = min(lane + 32 * h, kNv - 1); x_axis[h] = e / kAx; x_var[h] = e % kAx; }
     int q = 0, iters = 0, status = LSCGPU_QP_OK;
     int n_work = min(L.cand_count[b], L.cand_cap);
     // cache the head of the working set
@@ -342,22 +347,32 @@ __global__ void __launch_bounds__(32) k_qp_solve(QpLaunch L) {
             best = warp_argmin(best);
             if (best.id < 0) break;             // no row violated beyond the tolerance anywhere: done
         }
+        {
+            bool dup = false;
+            for (int k = lane; k < q; k += 32) dup |= S.act[k] == best.id;
+            if (__any_sync(0xffffffffu, dup)) { status = LSCGPU_QP_MAXITER; break; }   // numerical breakdown
+        }
         if (lane == 0) decode_row(S, best.id, n_obs, nrm, rhs, pitch, vel_coef, acc_coef, s_lb, s_ub, s_vmax, s_amax);
         __syncwarp();
         // whitened normal  nv = (G (+) G (+) G)^T a, normalised
         double part = 0.0;
-        for (int c = lane; c < NR; c += 32) {
-            const int k = c / kFree, cc = c % kFree;
-            double s = 0.0;
-            for (int t = 0; t < S.sel.nnz; t++)
-                if (S.sel.idx[t] / kAx == k) s += S.sel.a[t] * S.G[(S.sel.idx[t] % kAx) * kFree + cc];
-            S.nv[c] = s;
-            part += s * s;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int c = lane + 32 * h;
+            if (c < NR) {
+                const int k = h == 0 ? c_axis0 : 2, cc = h == 0 ? c_col0 : c - 2 * kFree;
+                double s = 0.0;
+                for (int t = 0; t < S.sel.nnz; t++)
+                    if (S.sel.axis[t] == k) s += S.sel.a[t] * __ldg(Gt + S.sel.var[t] * kFree + cc);
+                S.nv[c] = s;
+                part += s * s;
+            }
         }
         const double nrm_len = sqrt(warp_sum(part));
         if (!(nrm_len > 0.0)) { status = LSCGPU_QP_INFEASIBLE; break; }
+        const double inv_len = 1.0 / nrm_len;
         __syncwarp();
-        for (int c = lane; c < NR; c += 32) S.nv[c] /= nrm_len;
+        for (int c = lane; c < NR; c += 32) S.nv[c] *= inv_len;
         __syncwarp();
         double lam_p = 0.0;
         bool fail = false;
@@ -366,6 +381,7 @@ __global__ void __launch_bounds__(32) k_qp_solve(QpLaunch L) {
             // ---- z = (I - Q Q^T) nv by two Gram-Schmidt passes; d = Q^T nv ---------------------------------------
             for (int c = lane; c < NR; c += 32) { S.z[c] = S.nv[c]; S.d[c] = 0.0; }
             __syncwarp();
+            double zz = 1.0;                 // |nv| = 1
             if (q > 0) {
 #pragma unroll 1
                 for (int pass = 0; pass < 2; pass++) {
@@ -382,6 +398,7 @@ __global__ void __launch_bounds__(32) k_qp_solve(QpLaunch L) {
                         S.d[k] += s;
                     }
                     __syncwarp();
+                    double zp = 0.0;
                     for (int r = lane; r < NR; r += 32) {         // lane r: row r of Q against the coefficients
                         double s0 = 0.0, s1 = 0.0;
                         int k = 0;
@@ -390,22 +407,37 @@ __global__ void __launch_bounds__(32) k_qp_solve(QpLaunch L) {
                             s1 += S.Q[r * LD + k + 1] * S.tmp[k + 1];
                         }
                         if (k < q) s0 += S.Q[r * LD + k] * S.tmp[k];
-                        S.z[r] -= s0 + s1;
+                        const double zr = S.z[r] - (s0 + s1);
+                        S.z[r] = zr;
+                        zp += zr * zr;
                     }
+                    const double zz_new = warp_sum(zp);
                     __syncwarp();
+                    // "twice is enough": a second pass only when the first one cancelled most of the vector
+                    const bool again = zz_new < 0.25 * zz;
+                    zz = zz_new;
+                    if (!again) break;
                 }
             }
-            double zz_part = 0.0;
-            for (int c = lane; c < NR; c += 32) zz_part += S.z[c] * S.z[c];
-            const double zz = warp_sum(zz_part);
-            // rr = R^-1 d (change of the active multipliers per unit step)
-            for (int k = lane; k < q; k += 32) S.rr[k] = S.d[k];
-            for (int c = q - 1; c >= 0; c--) {
-                __syncwarp();
-                const double piv = S.rr[c] / S.R[c * LD + c];
-                __syncwarp();
-                for (int k = lane; k < c; k += 32) S.rr[k] -= S.R[k * LD + c] * piv;
-                if (lane == 0) S.rr[c] = piv;
+            // rr = R^-1 d (change of the active multipliers per unit step): column-oriented back substitution,
+            // rr[k] lives in lane k's register while q <= 32
+            if (q <= 32) {
+                double rk = lane < q ? S.d[lane] : 0.0;
+                for (int c = q - 1; c >= 0; c--) {
+                    const double piv = __shfl_sync(0xffffffffu, rk, c) * S.inv_diag[c];
+                    if (lane < c) rk -= S.R[lane * LD + c] * piv;
+                    if (lane == c) rk = piv;
+                }
+                if (lane < q) S.rr[lane] = rk;
+            } else {
+                for (int k = lane; k < q; k += 32) S.rr[k] = S.d[k];
+                for (int c = q - 1; c >= 0; c--) {
+                    __syncwarp();
+                    const double piv = S.rr[c] * S.inv_diag[c];
+                    __syncwarp();
+                    for (int k = lane; k < c; k += 32) S.rr[k] -= S.R[k * LD + c] * piv;
+                    if (lane == 0) S.rr[c] = piv;
+                }
             }
             __syncwarp();
             // ratio test over the active multipliers
@@ -423,7 +455,7 @@ __global__ void __launch_bounds__(32) k_qp_solve(QpLaunch L) {
                 if (ol >= 0 && (l < 0 || ot < t1 || (ot == t1 && ol < l))) { t1 = ot; l = ol; }
             }
             const bool primal = zz > kZeroTol;
-            const double slack = selected_slack(S) / nrm_len;
+            const double slack = selected_slack(S) * inv_len;
             double t2 = primal ? -slack / zz : INFINITY;
             if (t2 < 0.0) t2 = 0.0;
             const double t = fmin(t1, t2);
@@ -431,12 +463,18 @@ __global__ void __launch_bounds__(32) k_qp_solve(QpLaunch L) {
             for (int k = lane; k < q; k += 32) S.lam[k] -= t * S.rr[k];
             lam_p += t;
             if (!primal) { drop_active(S, q, l, lane); continue; }
-            for (int e = lane; e < kNv; e += 32) {
-                const int k = e / kAx, i = e % kAx;
-                double s = 0.0;
 #pragma unroll
-                for (int c = 0; c < kFree; c++) s += S.G[i * kFree + c] * S.z[k * kFree + c];
-                S.x[e] += t * s;
+            for (int h = 0; h < 3; h++) {
+                const int e = lane + 32 * h;
+                if (e < kNv) {
+                    const double* g = Gt + x_var[h] * kFree;
+                    const double* zk = S.z + x_axis[h] * kFree;
+                    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                    for (int c = 0; c + 1 < kFree; c += 2) { s0 += __ldg(g + c) * zk[c]; s1 += __ldg(g + c + 1) * zk[c + 1]; }
+                    s0 += __ldg(g + kFree - 1) * zk[kFree - 1];
+                    S.x[e] += t * (s0 + s1);
+                }
             }
             __syncwarp();
             if (t2 <= t1) {
@@ -446,6 +484,7 @@ __global__ void __launch_bounds__(32) k_qp_solve(QpLaunch L) {
                 for (int k = lane; k < q; k += 32) S.R[k * LD + q] = S.d[k];
                 if (lane == 0) {
                     S.R[q * LD + q] = zn;
+                    S.inv_diag[q] = izn;
                     S.act[q] = best.id;
                     S.lam[q] = lam_p;
                 }
