@@ -1,0 +1,199 @@
+// TrajPlanner with the reference's class surface (include/traj_planner.hpp:49-101) on top of the batched C-ABI.
+//
+// The reference plans agents one after the other: MultiSyncSimulator::plan() loops `agents[qi]->plan(t)`
+// (src/multi_sync_simulator.cpp:320-337) and every planner sees the SAME snapshot of the swarm (update() ran before,
+// :190-318). Here the N planners of a simulator share one ReplanBatch: the first plan() of a new planner_seq sends
+// every agent's state to the GPU (lscgpu_replan_batch) and plans the whole swarm; the other N-1 plan() calls of that
+// step just pick up their result. Setters that fed the reference's per-agent copies of the swarm (setObstacles,
+// setObsPrevTrajs, setDistMap) are accepted and ignored: the engine already holds every trajectory and the map.
+#pragma once
+#include <chrono>
+#include <cmath>
+#include <memory>
+#include <vector>
+
+#include "traj_optimizer.hpp"
+
+namespace DynamicPlanning {
+
+inline double nChoosek(int n, int k) {
+    if (k > n) return 0;
+    double r = 1;
+    for (int i = 1; i <= k; i++) r = r * (n - k + i) / i;
+    return r;
+}
+inline double getBernsteinBasis(int n, int i, double t) { return nChoosek(n, i) * std::pow(t, i) * std::pow(1 - t, n - i); }
+inline point3d getPointFromControlPoints(const std::vector<point3d>& cps, double t) {      // include/polynomial.hpp:26-45
+    if (t < 0 - SP_EPSILON || t > 1 + SP_EPSILON) throw std::invalid_argument("[Polynomial] Input of getPointFromControlPoints is out of bound");
+    const int n_ctrl = (int)cps.size() - 1;
+    double x = 0, y = 0, z = 0;
+    for (int i = 0; i < n_ctrl + 1; i++) {
+        const double b = getBernsteinBasis(n_ctrl, i, t);
+        x += cps[i].x() * b; y += cps[i].y() * b; z += cps[i].z() * b;
+    }
+    return point3d((float)x, (float)y, (float)z);
+}
+// include/polynomial.hpp:63-121 (position, velocity, acceleration)
+inline State getStateFromControlPoints(const traj_t& control_points, double current_time, int M, int n, double dt) {
+    int m = static_cast<int>(current_time / dt);
+    if (m == M && current_time < M * dt + SP_EPSILON) m = M - 1;
+    else if (m >= M) throw std::invalid_argument("[Polynomial] Input of getOdom is out of bound");
+    State state;
+    const double tn = current_time / dt - m;
+    state.position = getPointFromControlPoints(control_points[m], tn);
+    std::vector<point3d> vel(n), acc(n - 1);
+    for (int i = 0; i < n; i++) vel[i] = (control_points[m][i + 1] - control_points[m][i]) * (float)n * (float)std::pow(dt, -1);
+    state.velocity = getPointFromControlPoints(vel, tn);
+    for (int i = 0; i < n - 1; i++) acc[i] = (vel[i + 1] - vel[i]) * (float)(n - 1) * (float)std::pow(dt, -1);
+    state.acceleration = getPointFromControlPoints(acc, tn);
+    return state;
+}
+
+// One per simulator: owns the engine and the host-side in/out records of all agents.
+class ReplanBatch {
+public:
+    ReplanBatch(const Param& _param, const Mission& _mission, int device = 0)
+        : param(_param), mission(_mission), engine(createEngine(_param, _mission, device)), in(_mission.qn), out(_mission.qn),
+          fresh(_mission.qn, false) {
+        lscgpu_set_profiling(engine.get(), 1);
+    }
+    EnginePtr getEngine() const { return engine; }
+
+    void setOctomap(const std::string& file) {      // MultiSyncSimulator::setOctomap (src/multi_sync_simulator.cpp:153-167)
+        if (lscgpu_set_octomap_file(engine.get(), file.c_str()) != LSCGPU_OK)
+            throw std::invalid_argument(std::string("[lscgpu] ") + lscgpu_last_error());
+    }
+    void setInput(int qi, const State& s, const point3d& goal) {
+        for (int k = 0; k < 3; k++) {
+            in[qi].position[k] = s.position(k); in[qi].velocity[k] = s.velocity(k);
+            in[qi].acceleration[k] = s.acceleration(k); in[qi].goal[k] = goal(k);
+        }
+        fresh[qi] = true;
+    }
+    bool isFresh(int qi) const { return fresh[qi]; }
+    // plans the whole swarm once per planner_seq
+    void ensurePlanned(int planner_seq) {
+        if (planned_seq >= planner_seq) return;
+        for (bool f : fresh) if (!f) throw PlanningReport::WAITFORROSMSG;
+        const auto t0 = std::chrono::steady_clock::now();
+        if (lscgpu_replan_batch(engine.get(), in.data(), out.data()) != LSCGPU_OK)
+            throw std::invalid_argument(std::string("[lscgpu] ") + lscgpu_last_error());
+        wall_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        lscgpu_get_step_stats(engine.get(), &stats);
+        planned_seq = planner_seq;
+        std::fill(fresh.begin(), fresh.end(), false);
+    }
+    const lscgpu_agent_out& result(int qi) const { return out[qi]; }
+    double wallSecondsPerAgent() const { return wall_seconds / std::max(1, mission.qn); }
+    const lscgpu_step_stats& stepStats() const { return stats; }
+
+private:
+    Param param;
+    Mission mission;
+    EnginePtr engine;
+    std::vector<lscgpu_agent_in> in;
+    std::vector<lscgpu_agent_out> out;
+    std::vector<bool> fresh;
+    int planned_seq = 0;
+    double wall_seconds = 0;
+    lscgpu_step_stats stats{};
+};
+
+class TrajPlanner {
+public:
+    TrajPlanner(int _agent_id, const Param& _param, const Mission& _mission, std::shared_ptr<ReplanBatch> _batch)
+        : param(_param), mission(_mission), batch(std::move(_batch)) {
+        agent = mission.agents[_agent_id];
+        M = param.M; n = param.n; dim = param.world_dimension;
+        traj_curr.assign(M, std::vector<point3d>(n + 1));               // src/traj_planner.cpp:36-39
+        planner_seq = 0;
+        planning_report = PlanningReport::Initialized;
+        if (param.planner_mode != PlannerMode::LSC) throw std::invalid_argument("[TrajPlanner] Invalid planner mode");
+    }
+
+    PlanningReport plan(double /*sim_current_time*/) {
+        if (!flag_current_state_updated) return PlanningReport::WAITFORROSMSG;      // src/traj_planner.cpp:101-110
+        planner_seq++;                                                                // :127
+        goalPlanning();
+        batch->setInput(agent.id, agent.current_state, agent.current_goal_position);
+        flag_planned = false;
+        return planning_report = PlanningReport::SUCCESS;   // provisional; collect() below finalises after the batch ran
+    }
+    // second half of plan(): called for every agent after all of them pushed their inputs
+    PlanningReport collect() {
+        if (flag_planned) return planning_report;
+        batch->ensurePlanned(planner_seq);
+        const lscgpu_agent_out& o = batch->result(agent.id);
+        for (int m = 0; m < M; m++)
+            for (int i = 0; i < n + 1; i++) traj_curr[m][i] = point3d(o.traj[m][i][0], o.traj[m][i][1], o.traj[m][i][2]);
+        current_qp_cost = o.qp_cost;
+        qp_status = o.qp_status;
+        planning_report = (PlanningReport)o.report;
+        const lscgpu_step_stats& st = batch->stepStats();
+        const double per = 1e-3 / std::max(1, mission.qn);
+        PlanningTimeStatistics t;
+        t.obstacle_prediction_time.current = 0.5 * st.ms_predict * per;
+        t.initial_traj_planning_time.current = 0.5 * st.ms_predict * per;
+        t.goal_planning_time.current = 0;
+        t.lsc_generation_time.current = st.ms_lsc * per;
+        t.sfc_generation_time.current = st.ms_sfc * per;
+        t.traj_optimization_time.current = st.ms_qp * per;
+        t.total_planning_time.current = batch->wallSecondsPerAgent();
+        planning_time.update(t);
+        flag_current_state_updated = false;                                           // :132-136
+        flag_planned = true;
+        return planning_report;
+    }
+
+    // Setters
+    void setCurrentState(const State& s) { agent.current_state = s; flag_current_state_updated = true; }
+    template <class T> void setDistMap(const T&) {}
+    template <class T> void setObstacles(const T&) {}
+    void setObsPrevTrajs(const std::vector<traj_t>&) {}
+    void updatePlannerState(const PlannerState& s) { planner_state = s; }
+    void setStart(const point3d& p) { agent.start_position = p; }
+    void setDesiredGoal(const point3d& p) { agent.desired_goal_position = p; }
+
+    // Getters
+    point3d getCurrentPosition() const { return agent.current_state.position; }
+    State getCurrentStateMsg() const { return agent.current_state; }
+    State getFutureStateMsg(double future_time) const { return getStateFromControlPoints(traj_curr, future_time, M, n, param.dt); }
+    PlanningTimeStatistics getPlanningTime() const { return planning_time; }
+    double getQPCost() const { return current_qp_cost; }
+    int getQPStatus() const { return qp_status; }
+    PlanningReport getPlanningReport() const { return planning_report; }
+    traj_t getTraj() const { return traj_curr; }
+    point3d getCurrentGoalPosition() const { return agent.current_goal_position; }
+    point3d getDesiredGoalPosition() const { return agent.desired_goal_position; }
+    int getPlannerSeq() const { return planner_seq; }
+    point3d getNormalVector(int obs_id, int m) const {
+        std::vector<float> nr((size_t)(mission.qn - 1) * M * 3);
+        std::vector<double> d((size_t)(mission.qn - 1) * M * (n + 1));
+        if (lscgpu_get_lsc(batch->getEngine().get(), agent.id, nr.data(), d.data()) != LSCGPU_OK)
+            throw std::invalid_argument(std::string("[lscgpu] ") + lscgpu_last_error());
+        const int oi = obs_id < agent.id ? obs_id : obs_id - 1;
+        return point3d(nr[((size_t)oi * M + m) * 3], nr[((size_t)oi * M + m) * 3 + 1], nr[((size_t)oi * M + m) * 3 + 2]);
+    }
+
+private:
+    // Goal planning (src/traj_planner.cpp:477-608) is the step BEFORE the path; only the static goal is provided here:
+    // current_goal_position = desired goal (GoalMode::STATIC); the grid/A* modes are listed as "next" in DESIGN.md.
+    void goalPlanning() {
+        agent.current_goal_position = planner_state == PlannerState::GOBACK ? agent.start_position : agent.desired_goal_position;
+    }
+
+    Param param;
+    Mission mission;
+    std::shared_ptr<ReplanBatch> batch;
+    Agent agent;
+    traj_t traj_curr;
+    PlannerState planner_state = PlannerState::GOTO;
+    PlanningReport planning_report;
+    PlanningTimeStatistics planning_time;
+    double current_qp_cost = 0;
+    int qp_status = 0;
+    int planner_seq, M, n, dim;
+    bool flag_current_state_updated = false, flag_planned = true;
+};
+
+}  // namespace DynamicPlanning

@@ -1,0 +1,72 @@
+"""Host-side C++ mirror of the reference interface (lsc_planner_b200/host): builds, passes its CPU self-test, and the
+simulator binary refuses to run without a GPU; on the GPU box it must reproduce the oracle's closed loop."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "lsc_planner_b200", "host")
+MISSIONS = os.path.join(ROOT, "tests", "golden", "missions")
+
+
+@pytest.fixture(scope="module")
+def built():
+    from lsc_planner_b200 import build as B
+    B.build()
+    subprocess.run(["make", "-C", HOST], check=True, capture_output=True)
+    return HOST
+
+
+def test_host_selftest(built):
+    r = subprocess.run([os.path.join(built, "host_selftest"), os.path.join(MISSIONS, "multi_circle20.json")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "host selftest ok" in r.stdout
+
+
+def test_simulator_needs_gpu(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    r = subprocess.run([os.path.join(built, "lsc_sim"), "mission=" + os.path.join(MISSIONS, "multi_simple3.json")],
+                       capture_output=True, text=True)
+    assert r.returncode == 1 and "no CUDA device" in r.stderr
+
+
+def _read_result_csv(path, n):
+    rows = np.genfromtxt(path, delimiter=",", skip_header=1)
+    return rows.reshape(len(rows), n, 15)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mission", ["multi_simple3.json", "multi_circle20.json"])
+def test_simulator_matches_oracle_closed_loop(built, tmp_path, mission):
+    """lsc_sim (C++ host loop -> C-ABI -> kernels) against the oracle's closed loop: same recorded positions, no
+    collision, same flight time."""
+    import lsc_planner_b200 as L
+    import oracle_lib as O
+    scn = L.scenarios.load_mission(os.path.join(MISSIONS, mission))
+    res, summ = str(tmp_path / "result.csv"), str(tmp_path / "summary.csv")
+    r = subprocess.run([os.path.join(built, "lsc_sim"), "mission=" + os.path.join(MISSIONS, mission),
+                        "multisim/record_time_step=0.2", "result=" + res, "summary=" + summ],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    rec = _read_result_csv(res, scn.n)                       # one row per step (record_time_step = time_step)
+    sw = O.Swarm(scn.n, scn.world_min, scn.world_max, radius=[a.radius for a in scn.agents],
+                 downwash=[a.downwash for a in scn.agents], vmax=[a.max_vel for a in scn.agents],
+                 amax=[a.max_acc for a in scn.agents], v_nom=[a.nominal_velocity for a in scn.agents])
+    sw.set_state(scn.start); sw.set_goals(scn.goal)
+    steps = len(rec)
+    assert 20 < steps < 400
+    for k in range(steps):
+        pos, vel, acc = sw.state()
+        assert np.abs(rec[k, :, 2:5] - pos).max() <= 2e-3, k          # state at the start of step k
+        assert np.allclose(rec[k, :, 1], 0.2 * k, atol=1e-9) and (rec[k, :, 13] == 5).all()
+        # the simulator stops at the first step whose start state is within goal_threshold (isFinished)
+        done = np.linalg.norm(pos - scn.goal, axis=1).max() <= 0.1
+        assert done == (k == steps - 1) or (done and abs(np.linalg.norm(pos - scn.goal, axis=1).max() - 0.1) < 2e-3), k
+        sw.step(); sw.advance()
+    s = np.genfromtxt(summ, delimiter=",", skip_header=1, dtype=None, encoding=None).tolist()
+    assert abs(s[1] - 0.2 * (steps - 1)) < 1e-6 and s[3] == 0 and s[4] >= 1.0 - 1e-4   # flight time, no collision
