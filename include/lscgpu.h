@@ -98,6 +98,8 @@ typedef struct lscgpu_agent_out {
     int32_t qp_active;          /* active inequality rows at the solution */
     int32_t flags;              /* LSCGPU_FLAG_* */
     int32_t terminal_segments;  /* getTerminalSegments (src/traj_optimizer.cpp:541-548) */
+    int32_t qp_sweeps;          /* verification sweeps over all kept LSC pairs */
+    int32_t qp_kcycles;         /* SM clock cycles / 1024 this agent's QP took (its traj_optimization_time) */
 } lscgpu_agent_out;
 
 typedef struct lscgpu_engine lscgpu_engine;

@@ -43,8 +43,8 @@ AGENT_OUT = np.dtype([("traj", np.float32, (5, 6, 3)), ("next_position", np.floa
                       ("next_velocity", np.float32, 3), ("next_acceleration", np.float32, 3),
                       ("qp_cost", np.float64), ("report", np.int32), ("qp_status", np.int32),
                       ("qp_iterations", np.int32), ("qp_active", np.int32), ("flags", np.int32),
-                      ("terminal_segments", np.int32)], align=True)
-assert AGENT_IN.itemsize == 48 and AGENT_OUT.itemsize == 432, (AGENT_IN.itemsize, AGENT_OUT.itemsize)
+                      ("terminal_segments", np.int32), ("qp_sweeps", np.int32), ("qp_kcycles", np.int32)], align=True)
+assert AGENT_IN.itemsize == 48 and AGENT_OUT.itemsize == 440, (AGENT_IN.itemsize, AGENT_OUT.itemsize)
 
 _lib = None
 ptr = C.c_void_p

@@ -99,7 +99,10 @@ void launch_predict(const PredictLaunch& L, cudaStream_t s) { k_predict<<<L.n_ag
 //     solution-preserving; survivors go to a shared-memory queue.
 //   Phase B (whenever the queue holds a full batch, and at the end): one queued (neighbour, segment) hull per thread —
 //     GJK in FP64 registers, LSC rows written to the agent's row store at the pair's dense index p = m*(N-1) + jj,
-//     p appended to the agent's kept list, and to the initial QP working set when a row is violated at x0.
+//     p appended to the agent's kept list together with the smallest whitened slack of its rows at the unconstrained
+//     QP minimiser x0 (the QP kernel's verification sweeps skip a pair until the iterate has travelled that far), and
+//     to the agent's initial working-set lists: pairs with a row nearly active at initial_traj (the shifted previous
+//     solution, which is where the new solution usually ends up) and pairs with a row violated at x0.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kLscThreads = 128;
 
@@ -132,6 +135,7 @@ __global__ void __launch_bounds__(kLscThreads) k_lsc_build(LscLaunch L) {
     float4* nrm_out = L.nrm + (size_t)al * L.P_pad;
     double* rhs_out = L.rhs + (size_t)al * 6 * L.P_pad;
     int* kept_out = L.kept + (size_t)al * L.P_pad;
+    double* safe_out = L.safe + (size_t)al * L.P_pad;
     int gjk_it = 0;
 
 
@@ -185,7 +189,7 @@ __global__ void __launch_bounds__(kLscThreads) k_lsc_build(LscLaunch L) {
                 const double an = sqrt(ax * ax + ay * ay + az * az);
                 const float inv_an = an > 0.0 ? (float)(1.0 / an) : INFINITY;
                 nrm_out[p] = make_float4(seg.normal.x, seg.normal.y, seg.normal.z, inv_an);
-                bool near = false;
+                double mu_min = INFINITY, mu_near = INFINITY;
 #pragma unroll
                 for (int i = 0; i < 6; i++) {
                     // row  a . c_{m,i} >= d_i + a . o_{m,i}      (src/traj_optimizer.cpp:437-466)
@@ -195,14 +199,22 @@ __global__ void __launch_bounds__(kLscThreads) k_lsc_build(LscLaunch L) {
                     if (m == 0 && i < kPhi) continue;
                     const int vi = m * 6 + i;
                     const double slack = ax * x0[vi] + ay * x0[kAx + vi] + az * x0[2 * kAx + vi] - rhs;
-                    const double mu = slack * (double)inv_an * inv_gn[vi];
-                    if (!(mu >= L.cand_threshold)) near = true;
+                    const double mu = an > 0.0 ? slack * (double)inv_an * inv_gn[vi] : (slack < 0.0 ? -INFINITY : INFINITY);
+                    mu_min = fmin(mu_min, mu);
+                    // the same row at the agent's own initial_traj point (feasible when the previous step was)
+                    const double slack_c = ax * (double)ow[i].x + ay * (double)ow[i].y + az * (double)ow[i].z - rhs;
+                    mu_near = fmin(mu_near, an > 0.0 ? slack_c * (double)inv_an * inv_gn[vi] : -INFINITY);
+                }
+                if (!(mu_near >= L.near_threshold)) {
+                    const int slot = atomicAdd(L.near_count + 2 * al, 1);
+                    if (slot < L.near_cap) L.near[(size_t)(2 * al) * L.near_cap + slot] = p;
+                }
+                if (!(mu_min >= 0.0)) {
+                    const int slot = atomicAdd(L.near_count + 2 * al + 1, 1);
+                    if (slot < L.near_cap) L.near[(size_t)(2 * al + 1) * L.near_cap + slot] = p;
                 }
                 kept_out[kept_base + tid] = p;
-                if (near) {
-                    const int slot = atomicAdd(L.cand_count + al, 1);
-                    if (slot < L.cand_cap) L.cand[(size_t)al * L.cand_cap + slot] = p;
-                }
+                safe_out[kept_base + tid] = mu_min > 0.0 ? mu_min * 0.999999 : mu_min;
             }
             __syncthreads();
             if (tid == 0) kept_base += n_items;
@@ -275,7 +287,7 @@ void launch_gjk_batch(int n, const double* hulls, double* v, int* iters, cudaStr
 // ------------------------------------------------------------------------------------------------------------
 __global__ void k_rows_from_lsc(int n_problems, const int* obs_offset, int total_obs, const float* lsc_normal,
                                 const float* lsc_point, const double* lsc_d, float4* nrm, double* rhs, int* kept,
-                                int* kept_count) {
+                                int* kept_count, double* safe) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;     // global (obstacle, segment)
     if (t >= total_obs * kM) return;
     const int o = t / kM, m = t % kM;
@@ -284,7 +296,8 @@ __global__ void k_rows_from_lsc(int n_problems, const int* obs_offset, int total
     while (b + 1 < n_problems && obs_offset[b + 1] <= o) b++;
     const int n_b = obs_offset[b + 1] - obs_offset[b];
     const int p = kM * obs_offset[b] + m * n_b + (o - obs_offset[b]);
-    kept[p] = p - kM * obs_offset[b];                 // every pair is swept (no culling at the operator level)
+    kept[p] = p - kM * obs_offset[b];                 // every pair is priced (no culling at the operator level)
+    safe[p] = -INFINITY;                              // ... starting with the first iteration
     if (o == obs_offset[b] && m == 0) kept_count[b] = kM * n_b;
     const size_t pitch = (size_t)total_obs * kM;
     const float* nv = lsc_normal + ((size_t)o * kM + m) * 3;
@@ -299,11 +312,11 @@ __global__ void k_rows_from_lsc(int n_problems, const int* obs_offset, int total
 }
 void launch_rows_from_lsc(int n_problems, const int* obs_offset, int total_obs, const float* lsc_normal,
                           const float* lsc_point, const double* lsc_d, float4* nrm, double* rhs, int* kept,
-                          int* kept_count, cudaStream_t s) {
+                          int* kept_count, double* safe, cudaStream_t s) {
     if (total_obs <= 0) return;
     const int n = total_obs * kM;
     k_rows_from_lsc<<<(n + 127) / 128, 128, 0, s>>>(n_problems, obs_offset, total_obs, lsc_normal, lsc_point, lsc_d, nrm, rhs,
-                                                    kept, kept_count);
+                                                    kept, kept_count, safe);
 }
 
 // ------------------------------------------------------------------------------------------------------------

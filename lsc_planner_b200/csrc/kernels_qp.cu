@@ -17,17 +17,23 @@
 //
 // Rows are never assembled as a matrix. Bounds (SFC boxes + world box), velocity and acceleration limits are priced
 // from x with per-lane constants held in registers. LSC rows come from the row store written by k_lsc_build (three
-// non-zeros each) and are priced in two tiers: the working set (pairs selected by k_lsc_build plus every pair found
-// violated later; its first 32 pairs are cached in shared memory) at every iteration, and ALL kept pairs of the agent
-// (the pairs that survived k_lsc_build's exact culling) only when nothing in the working set is violated. The solve ends
-// when such a sweep finds no row violated beyond the feasibility tolerance.
+// non-zeros each) and are priced in two tiers.
+//   Tier 1, every iteration: a working set of at most 48 pairs cached in shared memory — the pairs k_lsc_build found
+//     nearly active at initial_traj, plus pairs found violated by a sweep.
+//   Tier 2, only when tier 1 and the fixed rows show no violation: a distance-gated sweep over the kept pairs (those
+//     that survived k_lsc_build's exact culling). In the whitened space every row normal has unit length, so a row's
+//     slack cannot fall faster than the iterate travels: per pair we keep `safe` = (distance travelled when it was
+//     last evaluated) + (smallest whitened slack of its rows then); the sweep reads that one number per pair (8 B,
+//     coalesced) and loads and evaluates the 64 B row only if the travelled distance has reached it.
+// The solve ends when a sweep finds no row violated beyond the feasibility tolerance; every skipped row is provably
+// satisfied.
 #include "kernels.hpp"
 
 namespace lscgpu {
 
 constexpr int NR = kRed;        // 39
 constexpr int LD = 39;          // row pitch of Q and R (odd: row-per-lane accesses are bank-conflict free)
-constexpr int WC = 32;          // working-set pairs cached in shared memory
+constexpr int WC = 48;          // working-set capacity (pairs cached in shared memory)
 // Primal feasibility tolerance = CPLEX's default EpRHS (the reference sets no tolerance, src/traj_optimizer.cpp:42-54):
 // like a dual simplex, a row enters the working set only when violated by more than this; entered rows are then met
 // exactly. Trajectories travel as float32, so agents in contact see hulls ~1e-7 closer than r_i + r_j; an exact
@@ -108,20 +114,22 @@ __device__ __forceinline__ void price_fixed(Best& best, const QpShared& S, int q
     }
 }
 
-// one (obstacle, segment) pair: up to 6 rows. Returns true when a row of the pair is violated beyond the tolerance.
-__device__ __forceinline__ bool price_pair_vals(Best& best, const QpShared& S, int q, int p, int m, float4 nr,
-                                                const double* r6) {
+// one (obstacle, segment) pair: up to 6 rows. Returns the smallest whitened slack of the pair's rows.
+__device__ __forceinline__ double price_pair_vals(Best& best, const QpShared& S, int q, int p, int m, float4 nr,
+                                                  const double* r6) {
     const double ax = (double)nr.x, ay = (double)nr.y, az = (double)nr.z, inv = (double)nr.w;
-    bool violated = false;
+    double mu_min = INFINITY;
 #pragma unroll
     for (int i = 0; i < 6; i++) {
         if (m == 0 && i < kPhi) continue;
         const int vi = m * 6 + i;
         const double slack = ax * S.x[vi] + ay * S.x[kAx + vi] + az * S.x[2 * kAx + vi] - r6[i];
-        violated |= slack < -kFeasTol;
-        consider(best, S, q, slack, inv * S.inv_gn[vi], kFixedRows + p * 6 + i);
+        const double scale = inv * S.inv_gn[vi];
+        const double mu = scale < INFINITY ? slack * scale : (slack < 0.0 ? -INFINITY : INFINITY);
+        mu_min = fmin(mu_min, mu);
+        consider(best, S, q, slack, scale, kFixedRows + p * 6 + i);
     }
-    return violated;
+    return mu_min;
 }
 
 __device__ __forceinline__ void load_pair(int p, const float4* nrm, const double* rhs, size_t pitch, float4& nr,
@@ -208,6 +216,7 @@ __device__ __forceinline__ void drop_active(QpShared& S, int& q, int l, int lane
 __global__ void __launch_bounds__(32) k_qp_solve(QpLaunch L) {
     __shared__ QpShared S;
     __shared__ double s_lb[15], s_ub[15], s_vmax[3], s_amax[3];
+    const long long t_start = clock64();
     const int b = blockIdx.x;
     const int lane = threadIdx.x;
     const bool batch = L.obs_offset != nullptr;
@@ -217,7 +226,7 @@ __global__ void __launch_bounds__(32) k_qp_solve(QpLaunch L) {
     const size_t pitch = (size_t)L.P_pad;
     const float4* nrm = batch ? L.nrm + (size_t)kPairsPerObs * L.obs_offset[b] : L.nrm + (size_t)b * L.P_pad;
     const double* rhs = batch ? L.rhs + (size_t)kPairsPerObs * L.obs_offset[b] : L.rhs + (size_t)b * 6 * L.P_pad;
-    int* cand = L.cand + (size_t)b * L.cand_cap;
+    double* safe = batch ? L.safe + (size_t)kPairsPerObs * L.obs_offset[b] : L.safe + (size_t)b * L.P_pad;
     const int* kept = batch ? L.kept + (size_t)kPairsPerObs * L.obs_offset[b] : L.kept + (size_t)b * L.P_pad;
     const int n_kept = L.kept_count[b];
     const QpTablesDev& T = *L.T;
@@ -286,63 +295,95 @@ __global__ void __launch_bounds__(32) k_qp_solve(QpLaunch L) {
 #pragma unroll
     for (int h = 0; h < 3; h++) { const int e = min(lane + 32 * h, kNv - 1); x_axis[h] = e / kAx; x_var[h] = e % kAx; }
     int q = 0, iters = 0, status = LSCGPU_QP_OK;
-    int n_work = min(L.cand_count[b], L.cand_cap);
-    // cache the head of the working set
-    for (int w = lane; w < min(n_work, WC); w += 32) {
-        const int p = cand[w];
-        float4 nr; double r6[6];
-        load_pair(p, nrm, rhs, pitch, nr, r6);
-        S.w_pair[w] = p; S.w_nrm[w] = nr;
+    double travelled = 0.0;          // path length of the iterate in the whitened space
+    unsigned long long rows_priced = 0, full_passes = 0;
+    // initial working set
+    int n_work = 0;
+    if (L.near) {
+        // list 0 (nearly active at initial_traj) first, then list 1 (violated at x0) while there is room
+        const int n0 = min(min(L.near_count[2 * b], L.near_cap), WC);
+        const int* near = L.near + (size_t)(2 * b) * L.near_cap;
+        for (int w = lane; w < n0; w += 32) S.w_pair[w] = near[w];
+        n_work = n0;
+        __syncwarp();
+        const int n1 = min(L.near_count[2 * b + 1], L.near_cap);
+        const int* viol = near + L.near_cap;
+        for (int w0 = 0; w0 < n1 && n_work < WC; w0 += 32) {
+            const int p = w0 + lane < n1 ? viol[w0 + lane] : -1;
+            bool fresh = p >= 0;
+            for (int k = 0; k < n0 && fresh; k++) fresh = S.w_pair[k] != p;
+            const unsigned mask = __ballot_sync(0xffffffffu, fresh);
+            const int slot = n_work + __popc(mask & ((1u << lane) - 1u));
+            if (fresh && slot < WC) S.w_pair[slot] = p;
+            n_work = min(n_work + __popc(mask), WC);
+        }
+        __syncwarp();
+        for (int w = lane; w < n_work; w += 32) {
+            float4 nr; double r6[6];
+            load_pair(S.w_pair[w], nrm, rhs, pitch, nr, r6);
+            S.w_nrm[w] = nr;
 #pragma unroll
-        for (int i = 0; i < 6; i++) S.w_rhs[w * 6 + i] = r6[i];
+            for (int i = 0; i < 6; i++) S.w_rhs[w * 6 + i] = r6[i];
+        }
     }
     __syncwarp();
-    unsigned long long rows_priced = 0, full_passes = 0;
 
     while (true) {
-        // ---- pricing --------------------------------------------------------------------------------------------
+        // ---- pricing: tier 1 --------------------------------------------------------------------------------------
         Best best{0.0, -1};
         price_fixed(best, S, q, F, vel_coef, acc_coef);
-        for (int w = lane; w < min(n_work, WC); w += 32) {
+        for (int w = lane; w < n_work; w += 32) {
             const int p = S.w_pair[w];
             price_pair_vals(best, S, q, p, p / n_obs, S.w_nrm[w], S.w_rhs + w * 6);
-        }
-        for (int w = WC + lane; w < n_work; w += 32) {
-            const int p = cand[w];
-            float4 nr; double r6[6];
-            load_pair(p, nrm, rhs, pitch, nr, r6);
-            price_pair_vals(best, S, q, p, p / n_obs, nr, r6);
         }
         rows_priced += 414 + 6ull * n_work;
         best = warp_argmin(best);
         if (best.id < 0) {
-            // nothing violated among bounds, limits and the working set: sweep every LSC pair of the agent
+            // ---- tier 2: distance-gated sweep over the kept pairs -------------------------------------------------
             full_passes++;
-            rows_priced += 6ull * n_kept;
-            for (int s0 = 0; s0 < n_kept; s0 += 64) {
-                // two pairs per lane in flight
-                const int pa = s0 + lane < n_kept ? kept[s0 + lane] : -1;
-                const int pb = s0 + 32 + lane < n_kept ? kept[s0 + 32 + lane] : -1;
-                float4 nra, nrb; double ra[6], rb[6];
-                if (pa >= 0) load_pair(pa, nrm, rhs, pitch, nra, ra);
-                if (pb >= 0) load_pair(pb, nrm, rhs, pitch, nrb, rb);
+            int evaluated = 0;
+            for (int s0 = 0; s0 < n_kept; s0 += 128) {
+                double sv[4];
 #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int p = h == 0 ? pa : pb;
+                for (int h = 0; h < 4; h++) {           // four gate values per lane in flight
+                    const int si = s0 + 32 * h + lane;
+                    sv[h] = si < n_kept ? safe[si] : INFINITY;
+                }
+#pragma unroll
+                for (int h = 0; h < 4; h++) {
+                    const int si = s0 + 32 * h + lane;
                     bool viol = false;
-                    if (p >= 0) viol = price_pair_vals(best, S, q, p, p / n_obs, h == 0 ? nra : nrb, h == 0 ? ra : rb);
+                    int p = -1;
+                    float4 nr; double r6[6];
+                    if (!(sv[h] > travelled)) {
+                        p = kept[si];
+                        load_pair(p, nrm, rhs, pitch, nr, r6);
+                        const double mu_min = price_pair_vals(best, S, q, p, p / n_obs, nr, r6);
+                        // 1e-6 relative margin: the stored 1/|a| is float32, so mu carries ~6e-8 relative error
+                        safe[si] = travelled + (mu_min > 0.0 ? mu_min * 0.999999 : mu_min);
+                        evaluated++;
+                        // does a row of this pair exceed the tolerance? (consider() already took it as a candidate)
+#pragma unroll
+                        for (int i = 0; i < 6; i++) {
+                            const int m = p / n_obs;
+                            if (m == 0 && i < kPhi) continue;
+                            const int vi = m * 6 + i;
+                            viol |= (double)nr.x * S.x[vi] + (double)nr.y * S.x[kAx + vi] + (double)nr.z * S.x[2 * kAx + vi] - r6[i] < -kFeasTol;
+                        }
+                    }
                     const unsigned mask = __ballot_sync(0xffffffffu, viol);
                     if (viol) {
                         const int slot = n_work + __popc(mask & ((1u << lane) - 1u));
                         if (slot < WC) {
-                            S.w_pair[slot] = p; S.w_nrm[slot] = h == 0 ? nra : nrb;
+                            S.w_pair[slot] = p; S.w_nrm[slot] = nr;
 #pragma unroll
-                            for (int i = 0; i < 6; i++) S.w_rhs[slot * 6 + i] = h == 0 ? ra[i] : rb[i];
-                        } else if (slot < L.cand_cap) cand[slot] = p;
+                            for (int i = 0; i < 6; i++) S.w_rhs[slot * 6 + i] = r6[i];
+                        }
                     }
-                    n_work = min(n_work + __popc(mask), L.cand_cap);
+                    n_work = min(n_work + __popc(mask), WC);
                 }
             }
+            rows_priced += 6ull * warp_sum_int(evaluated);
             __syncwarp();
             best = warp_argmin(best);
             if (best.id < 0) break;             // no row violated beyond the tolerance anywhere: done
@@ -463,6 +504,7 @@ __global__ void __launch_bounds__(32) k_qp_solve(QpLaunch L) {
             for (int k = lane; k < q; k += 32) S.lam[k] -= t * S.rr[k];
             lam_p += t;
             if (!primal) { drop_active(S, q, l, lane); continue; }
+            travelled += t * sqrt(zz) * (1.0 + 1e-9) + 1e-13;
 #pragma unroll
             for (int h = 0; h < 3; h++) {
                 const int e = lane + 32 * h;
@@ -548,6 +590,8 @@ __global__ void __launch_bounds__(32) k_qp_solve(QpLaunch L) {
             o.qp_active = q;
             o.flags = L.flags ? L.flags[agent] : 0;
             o.terminal_segments = ts;
+            o.qp_sweeps = (int)full_passes;
+            o.qp_kcycles = (int)((clock64() - t_start) >> 10);
         }
     }
 }

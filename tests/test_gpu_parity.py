@@ -4,7 +4,8 @@ Tolerances:
   GJK closest point      <= 1e-9 m vs the reference's own openGJK outputs (golden/gjk_ref_vectors.npz)
   distance field, SFC    bit-exact (integer squared distances; boxes compared as float32 bit patterns)
   LSC normals / margins  <= 1e-6 (float32 normals; in practice bit-identical)
-  QP                     status identical; trajectory <= 1e-6 m and relative objective gap <= 1e-6 whenever no row of
+  QP                     status identical; trajectory <= 2e-6 m (two float32 ulps at 8 m: the trajectory is handed on as
+                         float32) and relative objective gap <= 1e-6 whenever no row of
                          the agent's QP sits inside the 1e-6 feasibility band (CPLEX EpRHS, oracle/qp.hpp): there
                          the minimiser is unique. Rows violated by less than the band are ignored by both solvers, and
                          which of them end up active can depend on pricing order; those agent-steps (a few %) must
@@ -135,7 +136,7 @@ def test_qp_on_reference_lp_dump(golden_dir):
 
 
 # ---------------------------------------------------------------------------------------------------------
-def _teacher_forced(scn, steps, omap=None, bt=None, check_lsc_agents=(0,), traj_tol=1e-6):
+def _teacher_forced(scn, steps, omap=None, bt=None, check_lsc_agents=(0,), traj_tol=2e-6):
     """Oracle runs closed loop; before every step the engine is loaded with the oracle's planner state, so both
     plan from identical inputs. Returns per-step max |traj diff|."""
     import lsc_planner_b200 as L

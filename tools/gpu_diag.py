@@ -22,7 +22,12 @@ for s in range(a.steps):
     e.replan_resident()
     if s % a.every == 0 or s == a.steps - 1:
         o = e.fetch(); st = e.step_stats()
-        it = o["qp_iterations"]
+        it = o["qp_iterations"]; kc = o["qp_kcycles"].astype(float) * 1024 / 1.965e3   # us
+        slow = np.argsort(-kc)[:3]
+        print("      slowest agents:", [(int(a), f"{kc[a]:.0f}us", int(it[a]), int(o["qp_sweeps"][a]), int(o["qp_status"][a]), int(o["qp_active"][a])) for a in slow],
+              f"| us p50 {np.percentile(kc,50):.0f} p90 {np.percentile(kc,90):.0f} p99 {np.percentile(kc,99):.0f}",
+              "| sweeps p50 %.0f p99 %.0f max %.0f" % tuple(np.percentile(o["qp_sweeps"], [50, 99, 100])),
+              f"| rows priced/iter {st['qp_rows_priced'] / max(st['qp_iterations'] + scn.n, 1):.0f}")
         dist = np.linalg.norm(o["next_position"] - scn.goal, axis=1)
         print(f"step {s:4d} ms tot {st['ms_total']:.3f} lsc {st['ms_lsc']:.3f} sfc {st['ms_sfc']:.3f} qp {st['ms_qp']:.3f} | iters mean {it.mean():.1f} "
               f"p50 {np.percentile(it,50):.0f} p99 {np.percentile(it,99):.0f} max {it.max()} | status {np.bincount(o['qp_status'], minlength=3)} "
