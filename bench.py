@@ -47,6 +47,22 @@ def peaks():
     return {"hbm_gbs": 6650.0}, "fallback"
 
 
+def fma_peaks():
+    """FP32 / FP64 FMA peaks measured on this pool's B200 by tools/fma_peak.cu (profiles/fma_peaks.json)."""
+    p = os.path.join(ROOT, "profiles", "fma_peaks.json")
+    return json.load(open(p)) if os.path.exists(p) else None
+
+
+def alg_flops_per_replan(n_agents: int, octomap: bool, gjk_iters: float, qp_iters: float):
+    """F_lsc = (N-1) M (90 + 46 I_gjk) [FP64 GJK + float margins], F_qp = (K+1)(2 nnz(A) + 1080 + 2*39^2)
+    + 2/3 39^3; I_gjk (per hull) and K come from the ORACLE's counters on the same inputs."""
+    hulls = (n_agents - 1) * 5
+    f_lsc = hulls * 90 + 46.0 * gjk_iters          # gjk_iters = total GJK iterations of the agent's hulls
+    nnz = 81 * (n_agents - 1) + 618 + (162 if octomap else 0) + 174
+    f_qp = (qp_iters + 1) * (2 * nnz + 1080 + 2 * 39 ** 2) + (2.0 / 3.0) * 39 ** 3
+    return f_lsc, f_qp
+
+
 def alg_bytes_per_replan(n_agents: int, l_sfc: float) -> float:
     """neighbours' previous trajectories + radius/downwash, own trajectory, state, goal, SFC window
     in/out, EDT lookups (4 B each, oracle count), output trajectory, status + cost."""
@@ -321,6 +337,16 @@ def run_ours(args):
                 "ms_per_launch": dom_ms, "algorithmic_bytes_per_launch": b_alg,
                 "note": "latency/FP64-issue bound path (SURVEY.md §8d): unique bytes are L2-resident, so the HBM fraction is "
                         "low by construction; see DESIGN.md §5"}
+    fma = None
+    fp = fma_peaks()
+    if cpu is not None and fp is not None:
+        f_lsc, f_qp = alg_flops_per_replan(n, scn.use_octomap, cpu["per_replan"]["gjk_iterations"], cpu["per_replan"]["qp_iterations"])
+        rate = value
+        fma = {"algorithmic_flops_per_replan": {"lsc": f_lsc, "qp": f_qp},
+               "achieved_tflops": (f_lsc + f_qp) * rate * 1e-12,
+               "fp64_peak_tflops": fp["fp64_tflops"], "fp32_peak_tflops": fp["fp32_tflops"],
+               "frac_of_fp64_peak": (f_lsc + f_qp) * rate * 1e-12 / fp["fp64_tflops"],
+               "note": "all hot-path arithmetic runs in FP64 (GJK, QP); counters from the oracle on the same step"}
     if rank == 0:
         line = {
             "metric": "agent-replans/sec", "value": value, "unit": "agent-replans/s", "n_gpus": args.gpus,
@@ -337,6 +363,7 @@ def run_ours(args):
             "gpu_launches": int(launches.item()),
             "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]},
             "roofline": roofline,
+            "fma_roofline": fma,
             "cpu_baseline": cpu,
             "kernel_ms_per_step": {k: v / max(st["steps"], 1) for k, v in per_kernel.items()},
             "qp": {"iterations_per_replan": st["qp_iterations"] / max(n_local * st["steps"], 1),
