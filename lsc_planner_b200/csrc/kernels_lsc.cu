@@ -56,9 +56,8 @@ __global__ void __launch_bounds__(96) k_predict(PredictLaunch L) {
     }
     if (e >= 32 && e < 32 + kM) {
         // Culling data of segment m. Bounding sphere of the 6 control points, and `reach`: an upper
-        // bound of |x - c| for ANY point x the QP may give control point (m,i) and its initial_traj point c. The
-        // first three control points are fixed by the state (p, p + v dt/5, ...); every later increment is limited
-        // by the velocity rows to vmax dt / n per axis, so |x_{m,i} - p| <= sqrt(3) vmax dt (m+1) + max_k |x_{0,k} - p|.
+        // bound of |x - c| for ANY point x the QP may give control point (m,i) and its initial_traj point c:
+        // |x - c| <= |x - p| + |c - p| with p the current position.
         const int m = e - 32;
         float cx = 0.f, cy = 0.f, cz = 0.f;
         for (int i = 0; i < 6; i++) { cx += o[(m * 6 + i) * 3]; cy += o[(m * 6 + i) * 3 + 1]; cz += o[(m * 6 + i) * 3 + 2]; }
@@ -71,20 +70,25 @@ __global__ void __launch_bounds__(96) k_predict(PredictLaunch L) {
             far2 = fmaxf(far2, dx * dx + dy * dy + dz * dz);
         }
         L.sphere[(size_t)m * L.n_pad + a] = make_float4(cx, cy, cz, sqrtf(rad2) * 1.0001f + 1e-5f);
+        // Reachable offset of any control point of segment m from the current position, per axis, from the velocity
+        // AND acceleration rows (src/traj_optimizer.cpp:469-525): the velocity control points v_t satisfy
+        // |v_{t+1} - v_t| <= amax dt/(n-1) and |v_t| <= vmax (the first two are fixed by the state), consecutive
+        // position control points differ by v_t dt/n, and C1/C2 continuity carries both bounds across segments.
         const AgentConstDev& c = L.consts[a];
-        const float vmax = (float)fmax(c.vmax[0], fmax(c.vmax[1], c.vmax[2]));
         const float dtf = (float)L.dt;
-        float fix2 = 0.f;       // the state-determined points x_{0,1}, x_{0,2} relative to p
-        {
-            float d1 = 0.f, d2 = 0.f;
-            for (int k = 0; k < 3; k++) {
-                const float s1 = in.velocity[k] * dtf / (float)kN;
-                const float s2 = 2.f * s1 + in.acceleration[k] * dtf * dtf / (float)(kN * (kN - 1));
-                d1 += s1 * s1; d2 += s2 * s2;
-            }
-            fix2 = fmaxf(d1, d2);
+        float r2 = 0.f;
+        for (int k = 0; k < 3; k++) {
+            const float vmax = (float)c.vmax[k], dv = (float)c.amax[k] * dtf / (float)(kN - 1);
+            float bound[4 * kM + 1];
+            bound[0] = fabsf(in.velocity[k]);
+            bound[1] = fabsf(in.velocity[k] + in.acceleration[k] * dtf / (float)(kN - 1));
+            for (int t = 2; t <= 4 * kM; t++) bound[t] = fminf(vmax, bound[t - 1] + dv);
+            // a feasible trajectory also keeps the fixed first two within vmax only if the state does; use them as is
+            float reach = 0.f;
+            for (int t = 0; t < 5 * (m + 1); t++) reach += bound[4 * (t / 5) + (t % 5)] * dtf / (float)kN;
+            r2 += reach * reach;
         }
-        const float r = 1.7320509f * vmax * dtf * (float)(m + 1) + sqrtf(fix2) + sqrtf(far2);
+        const float r = sqrtf(r2) + sqrtf(far2);
         L.reach[(size_t)a * kM + m] = r * 1.0001f + 1e-3f;
     }
 }
@@ -113,7 +117,8 @@ __global__ void __launch_bounds__(kLscThreads) k_lsc_build(LscLaunch L) {
     __shared__ float4 own_sphere[kM];
     __shared__ float own_reach[kM];
     __shared__ int queue[kLscThreads * (kM + 1)];
-    __shared__ int q_count, kept_base;
+    __shared__ int q_count, kept_base, near_base[2];
+    __shared__ int warp_cnt[kM + 2][kLscThreads / 32];     // per-warp counts of the order-preserving compactions
     const int al = blockIdx.x;
     const int a = L.a0 + al;
     const int n_obs = L.n_agents - 1;
@@ -128,7 +133,9 @@ __global__ void __launch_bounds__(kLscThreads) k_lsc_build(LscLaunch L) {
     }
     for (int e = tid; e < kAx; e += kLscThreads) inv_gn[e] = 1.0 / L.T->gnorm[ts - 1][e];
     if (tid < kM) { own_sphere[tid] = L.sphere[(size_t)tid * L.n_pad + a]; own_reach[tid] = L.reach[(size_t)a * kM + tid]; }
-    if (tid == 0) { q_count = 0; kept_base = 0; }
+    if (tid == 0) { q_count = 0; kept_base = 0; near_base[0] = near_base[1] = 0; }
+    const int warp = tid >> 5, lane = tid & 31;
+    constexpr int kWarps = kLscThreads / 32;
     __syncthreads();
 
     const AgentConstDev ca = L.consts[a];
@@ -141,6 +148,10 @@ __global__ void __launch_bounds__(kLscThreads) k_lsc_build(LscLaunch L) {
 
     for (int j0 = 0; j0 < n_obs; j0 += kLscThreads) {
         const int jj = j0 + tid;
+        unsigned keep_mask[kM];
+        bool keep[kM];
+#pragma unroll
+        for (int m = 0; m < kM; m++) keep[m] = false;
         if (jj < n_obs) {
             const int j = jj < a ? jj : jj + 1;
             const AgentConstDev cj = L.consts[j];
@@ -155,9 +166,29 @@ __global__ void __launch_bounds__(kLscThreads) k_lsc_build(LscLaunch L) {
                 const float dx = so.x - sj.x, dy = so.y - sj.y, dz = (so.z - sj.z) * inv_dw;
                 const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
                 const float d_lb = dist * 0.9999f - smax * (so.w + sj.w);        // lower bound of the hull distance
-                const bool cull = d_lb - rho > 2.0f * smax * own_reach[m];
-                if (!cull) queue[atomicAdd(&q_count, 1)] = m * n_obs + jj;
+                keep[m] = !(d_lb - rho > 2.0f * smax * own_reach[m]);
             }
+        }
+        // order-preserving compaction (segment-major, then neighbour index): the queue, and with it every list this
+        // kernel writes, has the same order in every run
+#pragma unroll
+        for (int m = 0; m < kM; m++) {
+            keep_mask[m] = __ballot_sync(0xffffffffu, keep[m]);
+            if (lane == 0) warp_cnt[m][warp] = __popc(keep_mask[m]);
+        }
+        __syncthreads();
+        {
+            int off = q_count, total = 0;
+#pragma unroll
+            for (int m = 0; m < kM; m++)
+#pragma unroll
+                for (int w = 0; w < kWarps; w++) {
+                    const int c = warp_cnt[m][w];
+                    if (keep[m] && w == warp) queue[off + __popc(keep_mask[m] & ((1u << lane) - 1u))] = m * n_obs + jj;
+                    off += c; total += c;
+                }
+            __syncthreads();
+            if (tid == 0) q_count += total;
         }
         __syncthreads();
         // drain full batches (and everything after the last chunk)
@@ -169,6 +200,7 @@ __global__ void __launch_bounds__(kLscThreads) k_lsc_build(LscLaunch L) {
             if (tid < n_items) p = queue[total - n_items + tid];      // take the batch from the END of the queue
             __syncthreads();
             if (tid == 0) q_count = total - n_items;
+            double mu_min = INFINITY, mu_near = INFINITY;
             if (p >= 0) {
                 const int m = p / n_obs, jj2 = p % n_obs;
                 const int j = jj2 < a ? jj2 : jj2 + 1;
@@ -189,7 +221,7 @@ __global__ void __launch_bounds__(kLscThreads) k_lsc_build(LscLaunch L) {
                 const double an = sqrt(ax * ax + ay * ay + az * az);
                 const float inv_an = an > 0.0 ? (float)(1.0 / an) : INFINITY;
                 nrm_out[p] = make_float4(seg.normal.x, seg.normal.y, seg.normal.z, inv_an);
-                double mu_min = INFINITY, mu_near = INFINITY;
+                mu_min = INFINITY; mu_near = INFINITY;
 #pragma unroll
                 for (int i = 0; i < 6; i++) {
                     // row  a . c_{m,i} >= d_i + a . o_{m,i}      (src/traj_optimizer.cpp:437-466)
@@ -205,23 +237,76 @@ __global__ void __launch_bounds__(kLscThreads) k_lsc_build(LscLaunch L) {
                     const double slack_c = ax * (double)ow[i].x + ay * (double)ow[i].y + az * (double)ow[i].z - rhs;
                     mu_near = fmin(mu_near, an > 0.0 ? slack_c * (double)inv_an * inv_gn[vi] : -INFINITY);
                 }
-                if (!(mu_near >= L.near_threshold)) {
-                    const int slot = atomicAdd(L.near_count + 2 * al, 1);
-                    if (slot < L.near_cap) L.near[(size_t)(2 * al) * L.near_cap + slot] = p;
-                }
-                if (!(mu_min >= 0.0)) {
-                    const int slot = atomicAdd(L.near_count + 2 * al + 1, 1);
-                    if (slot < L.near_cap) L.near[(size_t)(2 * al + 1) * L.near_cap + slot] = p;
-                }
                 kept_out[kept_base + tid] = p;
                 safe_out[kept_base + tid] = mu_min > 0.0 ? mu_min * 0.999999 : mu_min;
             }
-            __syncthreads();
-            if (tid == 0) kept_base += n_items;
-            __syncthreads();
+            // working-set list 0 (nearly active at initial_traj), appended in batch order
+            {
+                const bool flag = p >= 0 && !(mu_near >= L.near_threshold);
+                const unsigned fmask = __ballot_sync(0xffffffffu, flag);
+                if (lane == 0) warp_cnt[kM][warp] = __popc(fmask);
+                __syncthreads();
+                int off = near_base[0];
+                for (int w = 0; w < warp; w++) off += warp_cnt[kM][w];
+                off += __popc(fmask & ((1u << lane) - 1u));
+                if (flag && off < L.near_cap) L.near[(size_t)(2 * al) * L.near_cap + off] = p;
+                __syncthreads();
+                if (tid == 0) {
+                    kept_base += n_items;
+                    for (int w = 0; w < kWarps; w++) near_base[0] += warp_cnt[kM][w];
+                }
+                __syncthreads();
+            }
         }
     }
-    if (tid == 0) L.kept_count[al] = kept_base;
+    // Working-set list 1: the pairs whose rows are MOST violated at x0 (at most near_cap of them). Depth buckets of
+    // the whitened violation (0.25 wide, 64 buckets), fully taken from the deepest down, the last bucket in kept order.
+    {
+        __shared__ int hist[64];
+        __shared__ int cut_depth, cut_take;
+        const int n_kept = kept_base;
+        if (tid < 64) hist[tid] = 0;
+        __syncthreads();
+        auto depth_of = [](double v) { return v < 0.0 ? min(63, (int)(-v * 4.0)) : -1; };
+        for (int sidx = tid; sidx < n_kept; sidx += kLscThreads) {
+            const int d = depth_of(safe_out[sidx]);
+            if (d >= 0) atomicAdd(&hist[d], 1);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int room = L.near_cap, cum = 0;
+            cut_depth = -1; cut_take = 0;              // buckets deeper than cut_depth are taken whole
+            int d = 63;
+            for (; d >= 0; d--) {
+                if (cum + hist[d] > room) break;
+                cum += hist[d];
+            }
+            cut_depth = d;                              // -1: everything fits
+            cut_take = d >= 0 ? room - cum : 0;
+        }
+        __syncthreads();
+        for (int pass = 0; pass < 2; pass++) {
+            if (pass == 1 && (cut_depth < 0 || cut_take == 0)) break;
+            for (int s0 = 0; s0 < n_kept; s0 += kLscThreads) {
+                const int sidx = s0 + tid;
+                const int d = sidx < n_kept ? depth_of(safe_out[sidx]) : -1;
+                const bool flag = pass == 0 ? d > cut_depth : (d >= 0 && d == cut_depth);
+                const unsigned fmask = __ballot_sync(0xffffffffu, flag);
+                if (lane == 0) warp_cnt[kM + 1][warp] = __popc(fmask);
+                __syncthreads();
+                int off = near_base[1];
+                for (int w = 0; w < warp; w++) off += warp_cnt[kM + 1][w];
+                off += __popc(fmask & ((1u << lane) - 1u));
+                const int limit = pass == 0 ? L.near_cap : min(L.near_cap, near_base[1] + cut_take);
+                (void)limit;
+                if (flag && off < L.near_cap) L.near[(size_t)(2 * al + 1) * L.near_cap + off] = kept_out[sidx];
+                __syncthreads();
+                if (tid == 0) for (int w = 0; w < kWarps; w++) near_base[1] += warp_cnt[kM + 1][w];
+                __syncthreads();
+            }
+        }
+    }
+    if (tid == 0) { L.kept_count[al] = kept_base; L.near_count[2 * al] = near_base[0]; L.near_count[2 * al + 1] = near_base[1]; }
     if (L.counters) {
         const int tot = warp_sum_int(gjk_it);
         if ((tid & 31) == 0) atomicAdd(&L.counters->gjk_iterations, (unsigned long long)tot);

@@ -33,6 +33,7 @@ namespace lscgpu {
 
 constexpr int NR = kRed;        // 39
 constexpr int LD = 39;          // row pitch of Q and R (odd: row-per-lane accesses are bank-conflict free)
+constexpr int kEvalCap = 192;   // batch of gated pairs evaluated together (one pair per lane per round)
 constexpr int WC = 48;          // working-set capacity (pairs cached in shared memory)
 // Primal feasibility tolerance = CPLEX's default EpRHS (the reference sets no tolerance, src/traj_optimizer.cpp:42-54):
 // like a dual simplex, a row enters the working set only when violated by more than this; entered rows are then met
@@ -58,6 +59,7 @@ struct QpShared {
     double w_rhs[WC * 6];
     float4 w_nrm[WC];
     int w_pair[WC];
+    int eval_list[kEvalCap];    // kept-list positions a sweep has to evaluate
     int act[NR];
     SelectedRow sel;
 };
@@ -300,18 +302,18 @@ __global__ void __launch_bounds__(32) k_qp_solve(QpLaunch L) {
     // initial working set
     int n_work = 0;
     if (L.near) {
-        // list 0 (nearly active at initial_traj) first, then list 1 (violated at x0) while there is room
-        const int n0 = min(min(L.near_count[2 * b], L.near_cap), WC);
-        const int* near = L.near + (size_t)(2 * b) * L.near_cap;
-        for (int w = lane; w < n0; w += 32) S.w_pair[w] = near[w];
-        n_work = n0;
+        // list 1 (most violated at x0) first — those rows are pivoted on at once — then list 0 (nearly active at
+        // initial_traj) while there is room
+        const int* lists = L.near + (size_t)(2 * b) * L.near_cap;
+        const int n1 = min(min(L.near_count[2 * b + 1], L.near_cap), WC);
+        for (int w = lane; w < n1; w += 32) S.w_pair[w] = lists[L.near_cap + w];
+        n_work = n1;
         __syncwarp();
-        const int n1 = min(L.near_count[2 * b + 1], L.near_cap);
-        const int* viol = near + L.near_cap;
-        for (int w0 = 0; w0 < n1 && n_work < WC; w0 += 32) {
-            const int p = w0 + lane < n1 ? viol[w0 + lane] : -1;
+        const int n0 = min(L.near_count[2 * b], L.near_cap);
+        for (int w0 = 0; w0 < n0 && n_work < WC; w0 += 32) {
+            const int p = w0 + lane < n0 ? lists[w0 + lane] : -1;
             bool fresh = p >= 0;
-            for (int k = 0; k < n0 && fresh; k++) fresh = S.w_pair[k] != p;
+            for (int k = 0; k < n1 && fresh; k++) fresh = S.w_pair[k] != p;
             const unsigned mask = __ballot_sync(0xffffffffu, fresh);
             const int slot = n_work + __popc(mask & ((1u << lane) - 1u));
             if (fresh && slot < WC) S.w_pair[slot] = p;
@@ -340,32 +342,45 @@ __global__ void __launch_bounds__(32) k_qp_solve(QpLaunch L) {
         best = warp_argmin(best);
         if (best.id < 0) {
             // ---- tier 2: distance-gated sweep over the kept pairs -------------------------------------------------
+            // scan the gate values (4 per lane in flight), compact the positions that need evaluation into shared
+            // memory, and evaluate them one pair per lane per round so that all row loads of a round are in flight
             full_passes++;
-            int evaluated = 0;
-            for (int s0 = 0; s0 < n_kept; s0 += 128) {
-                double sv[4];
+            int evaluated = 0, n_list = 0;
+            for (int s0 = 0; s0 < n_kept || n_list > 0; s0 += 128) {
+                if (s0 < n_kept) {
+                    double sv[4];
 #pragma unroll
-                for (int h = 0; h < 4; h++) {           // four gate values per lane in flight
-                    const int si = s0 + 32 * h + lane;
-                    sv[h] = si < n_kept ? safe[si] : INFINITY;
+                    for (int h = 0; h < 4; h++) {
+                        const int si = s0 + 32 * h + lane;
+                        sv[h] = si < n_kept ? safe[si] : INFINITY;
+                    }
+#pragma unroll
+                    for (int h = 0; h < 4; h++) {
+                        const bool need = !(sv[h] > travelled);
+                        const unsigned mask = __ballot_sync(0xffffffffu, need);
+                        if (need) S.eval_list[n_list + __popc(mask & ((1u << lane) - 1u))] = s0 + 32 * h + lane;
+                        n_list += __popc(mask);
+                    }
+                    __syncwarp();
                 }
-#pragma unroll
-                for (int h = 0; h < 4; h++) {
-                    const int si = s0 + 32 * h + lane;
+                const bool last = s0 + 128 >= n_kept;
+                if (n_list <= kEvalCap - 128 && !last) continue;     // room for another chunk: keep scanning
+                for (int e0 = 0; e0 < n_list; e0 += 32) {
+                    const int e = e0 + lane;
                     bool viol = false;
                     int p = -1;
                     float4 nr; double r6[6];
-                    if (!(sv[h] > travelled)) {
+                    if (e < n_list) {
+                        const int si = S.eval_list[e];
                         p = kept[si];
                         load_pair(p, nrm, rhs, pitch, nr, r6);
                         const double mu_min = price_pair_vals(best, S, q, p, p / n_obs, nr, r6);
                         // 1e-6 relative margin: the stored 1/|a| is float32, so mu carries ~6e-8 relative error
                         safe[si] = travelled + (mu_min > 0.0 ? mu_min * 0.999999 : mu_min);
                         evaluated++;
-                        // does a row of this pair exceed the tolerance? (consider() already took it as a candidate)
+                        const int m = p / n_obs;
 #pragma unroll
                         for (int i = 0; i < 6; i++) {
-                            const int m = p / n_obs;
                             if (m == 0 && i < kPhi) continue;
                             const int vi = m * 6 + i;
                             viol |= (double)nr.x * S.x[vi] + (double)nr.y * S.x[kAx + vi] + (double)nr.z * S.x[2 * kAx + vi] - r6[i] < -kFeasTol;
@@ -382,6 +397,8 @@ __global__ void __launch_bounds__(32) k_qp_solve(QpLaunch L) {
                     }
                     n_work = min(n_work + __popc(mask), WC);
                 }
+                n_list = 0;
+                __syncwarp();
             }
             rows_priced += 6ull * warp_sum_int(evaluated);
             __syncwarp();

@@ -18,6 +18,7 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <stdexcept>
 #include <vector>
@@ -303,6 +304,7 @@ inline bool row_get(const QpTables& T, const QpProblem& p, int id, RowView& r) {
 // exactly like k_qp_solve — a working set of (obstacle, segment) pairs whose whitened slack at x0 is below this
 // threshold, extended by a full sweep whenever nothing in it is violated. Default: every row priced every iteration.
 inline double g_tier_threshold = INFINITY;
+inline int g_trace_agent = -1;            // debugging: >= 0 prints every pivot of the solve (stderr)
 
 // Goldfarb-Idnani dual active set on  min |v|^2  s.t.  n_j . v >= -slack0_j   (x = x0 + G v)
 inline void qp_solve(const QpTables& T, const QpProblem& p, QpResult& out, int max_iter = 2000) {
@@ -391,6 +393,7 @@ inline void qp_solve(const QpTables& T, const QpProblem& p, QpResult& out, int m
                 for (int id = 450; id < n_ids; id++) if (price(id)) in_work[(id - 450) / 6] = 1;
         }
         if (pbest < 0) break;
+        if (g_trace_agent >= 0) std::fprintf(stderr, "  pick id %d (%s) mu %.4g q %d\n", pbest, pbest < 180 ? "bound" : pbest < 450 ? "dyn" : "lsc", mu_best, q);
         double nrm = row_normal(rb, nv);
         (void)nb;
         if (!(nrm > 0)) { out.status = QP_INFEASIBLE; break; }
@@ -419,6 +422,7 @@ inline void qp_solve(const QpTables& T, const QpProblem& p, QpResult& out, int m
             if (!(t < INFINITY)) { out.status = QP_INFEASIBLE; fail = true; break; }
             for (int k = 0; k < q; k++) lam[k] -= t * rr[k];
             lam_p += t;
+            if (g_trace_agent >= 0 && !(t2 <= t1)) std::fprintf(stderr, "    drop id %d (t1 %.3g t2 %.3g)\n", act[l], t1, t2);
             if (!primal) { drop(l); continue; }
             for (int c = 0; c < n; c++) v[c] += t * z[c];
             for (int k = 0; k < 3; k++)
