@@ -20,23 +20,21 @@ struct AgentConstDev {
     int pad;
 };
 
-// LSC row storage of ONE agent, structure of arrays over P = 5 * (N-1) (obstacle, segment) pairs,
-// pair index p = m * n_obs + obstacle  (segment-major: neighbouring threads of the LSC kernel own
-// neighbouring obstacles, so every store below is coalesced):
-//   nrm[p]   = (a_x, a_y, a_z, 1/|a|)   float4, a = LSC normal with z un-scaled (widened to double on use)
-//   rhs[i][p] = d_i + a . o_{m,i}       double, i = 0..5   -> row:  a . c_{m,i} >= rhs[i][p]
-struct RowStore {
-    float4* nrm;          // [L][P_pad]
-    double* rhs;          // [L][6][P_pad]
-    float* dmargin;       // optional capture of d_i (float would lose bits) -> stored as double in `dcap`
-    double* dcap;         // [L][6][P_pad] safety margins d (only when capture is on), else nullptr
-    int P_pad;            // pairs per agent, padded to a multiple of 32
+// LSC row storage of ONE agent: one 64-byte record per KEPT (obstacle, segment) pair, in kept-list order (slot s),
+// so that pricing a pair is two fully used 32-byte sectors:
+//   a = LSC normal with z un-scaled (float32, widened to double on use), inv_an = 1/|a|,
+//   rhs[i] = d_i + a . o_{m,i}  (i = 0..5)      ->  row:  a . c_{m,i} >= rhs[i]
+// kept[s] = dense pair index p = m * n_obs + obstacle (gives the segment m of the slot).
+struct __align__(16) RowRec {
+    float ax, ay, az, inv_an;
+    double rhs[6];
 };
+static_assert(sizeof(RowRec) == 64, "RowRec must be 64 bytes");
 
 // canonical inequality row ids inside the QP kernel:
 //   [0,180)    variable bounds  ((k*5+m)*6+i)*2 + side          side 0: x >= lb, side 1: x <= ub
 //   [180,450)  dynamic limits   180 + ((k*5+m)*9+j)*2 + side    j<5 velocity, j>=5 acceleration
-//   [450, ..)  LSC              450 + p*6 + i
+//   [450, ..)  LSC              450 + s*6 + i      (s = slot in the agent's kept list)
 constexpr int kFixedRows = 450;
 
 struct StepCounters {

@@ -79,13 +79,10 @@ struct lscgpu_engine {
     double *d_state9 = nullptr, *d_goal3 = nullptr, *d_last_cost = nullptr;
     int *d_ts = nullptr, *d_flags = nullptr, *d_init_sfc = nullptr;
     // row store of the local shard
-    float4* d_nrm = nullptr;
-    double* d_rhs = nullptr;
+    RowRec* d_rows = nullptr;
     int P_pad = 0, n_rows_alloc = 0;
-    int *d_kept = nullptr, *d_kept_count = nullptr, *d_near = nullptr, *d_near_count = nullptr;
+    int *d_kept = nullptr, *d_kept_count = nullptr;
     double* d_safe = nullptr;
-    int near_cap = 48;
-    double near_threshold = 1.0;
     float4* d_sphere = nullptr;      // [5][n_pad]
     float* d_reach = nullptr;        // [N][5]
     StepCounters* d_counters = nullptr;
@@ -105,10 +102,9 @@ struct lscgpu_engine {
 };
 
 static void free_rows(lscgpu_engine* e) {
-    cudaFree(e->d_nrm); cudaFree(e->d_rhs); cudaFree(e->d_safe);
-    cudaFree(e->d_kept); cudaFree(e->d_kept_count); cudaFree(e->d_near); cudaFree(e->d_near_count);
-    e->d_near = nullptr; e->d_near_count = nullptr;
-    e->d_nrm = nullptr; e->d_rhs = nullptr; e->d_safe = nullptr;
+    cudaFree(e->d_rows); cudaFree(e->d_safe);
+    cudaFree(e->d_kept); cudaFree(e->d_kept_count);
+    e->d_rows = nullptr; e->d_safe = nullptr;
     e->d_kept = nullptr; e->d_kept_count = nullptr;
     e->n_rows_alloc = 0;
 }
@@ -119,11 +115,8 @@ static int alloc_rows(lscgpu_engine* e) {
     free_rows(e);
     const int P = kPairsPerObs * std::max(e->N - 1, 1);
     e->P_pad = (P + 31) / 32 * 32;
-    CU(cudaMalloc(&e->d_nrm, sizeof(float4) * (size_t)n_local * e->P_pad));
-    CU(cudaMalloc(&e->d_rhs, sizeof(double) * (size_t)n_local * 6 * e->P_pad));
+    CU(cudaMalloc(&e->d_rows, sizeof(RowRec) * (size_t)n_local * e->P_pad));
     CU(cudaMalloc(&e->d_safe, sizeof(double) * (size_t)n_local * e->P_pad));
-    CU(cudaMalloc(&e->d_near, sizeof(int) * (size_t)n_local * 2 * e->near_cap));
-    CU(cudaMalloc(&e->d_near_count, sizeof(int) * (size_t)n_local * 2));
     CU(cudaMalloc(&e->d_kept, sizeof(int) * (size_t)n_local * e->P_pad));
     CU(cudaMalloc(&e->d_kept_count, sizeof(int) * (size_t)n_local));
     e->n_rows_alloc = n_local;
@@ -186,7 +179,7 @@ extern "C" int lscgpu_create(const lscgpu_params* p, int n_agents, const lscgpu_
     e->a0 = 0; e->a1 = n_agents; e->block = n_agents; e->n_out = n_agents;
     e->consts_host.assign(agents, agents + n_agents);
     if (const char* s = getenv("LSCGPU_MAX_ITER")) e->max_iter = atoi(s);
-    if (const char* s = getenv("LSCGPU_NEAR_THRESHOLD")) e->near_threshold = atof(s);
+
     auto bail = [&](int code) { lscgpu_destroy(e); return code; };
 #define CUB(expr)                                                                                         \
     do {                                                                                                  \
@@ -403,10 +396,7 @@ static int step_device(lscgpu_engine* e) {
         }
         ev = e->ev_pool[e->pending].ev;
     }
-    if (n_local > 0) {
-        CU(cudaMemsetAsync(e->d_kept_count, 0, sizeof(int) * n_local, s));
-        CU(cudaMemsetAsync(e->d_near_count, 0, sizeof(int) * n_local * 2, s));
-    }
+    if (n_local > 0) CU(cudaMemsetAsync(e->d_kept_count, 0, sizeof(int) * n_local, s));
     if (e->pending == 0) CU(cudaEventRecord(e->ev_begin, s));
     if (prof) CU(cudaEventRecord(ev[0], s));
 
@@ -436,9 +426,8 @@ static int step_device(lscgpu_engine* e) {
         ll.pred = e->d_pred; ll.predT = e->d_predT; ll.consts = e->d_consts; ll.T = e->d_tables;
         ll.state9 = e->d_state9; ll.goal3 = e->d_goal3; ll.ts = e->d_ts;
         ll.sphere = e->d_sphere; ll.reach = e->d_reach;
-        ll.nrm = e->d_nrm; ll.rhs = e->d_rhs; ll.P_pad = e->P_pad;
+        ll.rows = e->d_rows; ll.P_pad = e->P_pad;
         ll.kept = e->d_kept; ll.kept_count = e->d_kept_count; ll.safe = e->d_safe;
-        ll.near = e->d_near; ll.near_count = e->d_near_count; ll.near_cap = e->near_cap; ll.near_threshold = e->near_threshold;
         ll.counters = e->d_counters;
         launch_lsc_build(ll, s); launches++;
     }
@@ -451,9 +440,8 @@ static int step_device(lscgpu_engine* e) {
         ql.state9 = e->d_state9; ql.goal3 = e->d_goal3; ql.ts = e->d_ts;
         ql.boxes = e->prm.world_use_octomap ? e->d_boxes : nullptr;
         for (int k = 0; k < 3; k++) { ql.wmin[k] = e->prm.world_min[k]; ql.wmax[k] = e->prm.world_max[k]; }
-        ql.nrm = e->d_nrm; ql.rhs = e->d_rhs; ql.obs_offset = nullptr; ql.n_obs = e->N - 1; ql.P_pad = e->P_pad;
+        ql.rows = e->d_rows; ql.obs_offset = nullptr; ql.n_obs = e->N - 1; ql.P_pad = e->P_pad;
         ql.kept = e->d_kept; ql.kept_count = e->d_kept_count; ql.safe = e->d_safe; ql.max_iter = e->max_iter;
-        ql.near = e->d_near; ql.near_count = e->d_near_count; ql.near_cap = e->near_cap;
         ql.out = e->d_out; ql.prev_traj = e->d_traj; ql.last_cost = e->d_last_cost; ql.flags = e->d_flags;
         ql.counters = e->d_counters;
         launch_qp_solve(ql, s); launches++;
@@ -673,17 +661,17 @@ extern "C" int lscgpu_qp_solve_batch(lscgpu_engine* e, int nb, const int32_t* ag
     cudaStream_t s = e->stream;
     DevBuf B;
     int *d_ai, *d_off, *d_ts, *d_status, *d_iters, *d_kept, *d_kc;
-    double *d_state, *d_goal, *d_d, *d_rhs, *d_x, *d_cost, *d_safe;
+    double *d_state, *d_goal, *d_d, *d_x, *d_cost, *d_safe;
     float *d_sfc = nullptr, *d_n, *d_p;
-    float4* d_nrm;
+    RowRec* d_rows;
     const size_t pairs = (size_t)total_obs * kPairsPerObs;
     CU(B.get(&d_ai, nb)); CU(B.get(&d_off, nb + 1)); CU(B.get(&d_ts, nb)); CU(B.get(&d_safe, pairs));
     CU(B.get(&d_status, nb)); CU(B.get(&d_iters, nb));
     CU(B.get(&d_kept, pairs)); CU(B.get(&d_kc, nb));
     CU(cudaMemsetAsync(d_kc, 0, sizeof(int) * nb, s));
     CU(B.get(&d_state, (size_t)nb * 9)); CU(B.get(&d_goal, (size_t)nb * 3)); CU(B.get(&d_d, pairs * 6));
-    CU(B.get(&d_rhs, pairs * 6)); CU(B.get(&d_x, (size_t)nb * kNv)); CU(B.get(&d_cost, nb));
-    CU(B.get(&d_n, pairs * 3)); CU(B.get(&d_p, pairs * 18)); CU(B.get(&d_nrm, pairs));
+    CU(B.get(&d_x, (size_t)nb * kNv)); CU(B.get(&d_cost, nb));
+    CU(B.get(&d_n, pairs * 3)); CU(B.get(&d_p, pairs * 18)); CU(B.get(&d_rows, pairs));
     CU(cudaMemcpyAsync(d_ai, agent_index, sizeof(int) * nb, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(d_off, obs_offset, sizeof(int) * (nb + 1), cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(d_state, state, sizeof(double) * 9 * nb, cudaMemcpyHostToDevice, s));
@@ -697,13 +685,13 @@ extern "C" int lscgpu_qp_solve_batch(lscgpu_engine* e, int nb, const int32_t* ag
         CU(cudaMemcpyAsync(d_p, lsc_point, sizeof(float) * pairs * 18, cudaMemcpyHostToDevice, s));
         CU(cudaMemcpyAsync(d_d, lsc_d, sizeof(double) * pairs * 6, cudaMemcpyHostToDevice, s));
     }
-    launch_rows_from_lsc(nb, d_off, total_obs, d_n, d_p, d_d, d_nrm, d_rhs, d_kept, d_kc, d_safe, s);
+    launch_rows_from_lsc(nb, d_off, total_obs, d_n, d_p, d_d, d_rows, d_kept, d_kc, d_safe, s);
     launch_terminal_segments(nb, d_state, d_goal, d_ai, e->d_consts, e->prm.dt, d_ts, s);
     QpLaunch ql{};
     ql.n_problems = nb; ql.T = e->d_tables; ql.consts = e->d_consts; ql.agent_index = d_ai; ql.agent_base = 0;
     ql.state9 = d_state; ql.goal3 = d_goal; ql.ts = d_ts; ql.boxes = d_sfc;
     for (int k = 0; k < 3; k++) { ql.wmin[k] = e->prm.world_min[k]; ql.wmax[k] = e->prm.world_max[k]; }
-    ql.nrm = d_nrm; ql.rhs = d_rhs; ql.obs_offset = d_off; ql.n_obs = 0; ql.P_pad = (int)pairs;
+    ql.rows = d_rows; ql.obs_offset = d_off; ql.n_obs = 0; ql.P_pad = (int)pairs;
     ql.kept = d_kept; ql.kept_count = d_kc; ql.safe = d_safe; ql.max_iter = e->max_iter;
     ql.x_out = d_x; ql.cost_out = d_cost; ql.status_out = d_status; ql.iters_out = d_iters;
     ql.out = nullptr; ql.counters = nullptr;

@@ -38,17 +38,11 @@ struct LscLaunch {
     const int* ts;
     const float4* sphere;          // [5][n_pad]
     const float* reach;            // [N][5]
-    float4* nrm;                   // [n_local][P_pad]   written only for kept pairs
-    double* rhs;                   // [n_local][6][P_pad]
+    RowRec* rows;                  // [n_local][P_pad]   one record per kept pair, kept-list order
     int P_pad;
     int* kept;                     // [n_local][P_pad] pair indices that survive the exact culling test
     int* kept_count;               // [n_local]  (zeroed by the launcher)
     double* safe;                  // [n_local][P_pad] per kept pair: smallest whitened slack of its rows at x0
-    int* near;                     // [n_local][2][near_cap] list 0: pairs with a row nearly active at initial_traj,
-                                   //                        list 1: pairs with a row violated at x0
-    int* near_count;               // [n_local][2]  (zeroed by the launcher)
-    int near_cap;
-    double near_threshold;
     StepCounters* counters;
 };
 void launch_lsc_build(const LscLaunch& L, cudaStream_t s);
@@ -59,7 +53,7 @@ void launch_lsc_capture(int n_agents, int agent, const float* pred, const AgentC
 void launch_gjk_batch(int n, const double* hulls, double* v, int* iters, cudaStream_t s);
 // LSC arrays of the reference container -> row store (operator-level QP entry)
 void launch_rows_from_lsc(int n_problems, const int* obs_offset, int total_obs, const float* lsc_normal,
-                          const float* lsc_point, const double* lsc_d, float4* nrm, double* rhs, int* kept,
+                          const float* lsc_point, const double* lsc_d, RowRec* rows, int* kept,
                           int* kept_count, double* safe, cudaStream_t s);
 
 void launch_terminal_segments(int n, const double* state9, const double* goal3, const int* agent_index,
@@ -77,14 +71,12 @@ struct QpLaunch {
     const int* ts;
     const float* boxes;            // [..][5][6] or null (no SFC rows); indexed like state9
     float wmin[3], wmax[3];
-    const float4* nrm;
-    const double* rhs;
+    const RowRec* rows;
     const int* obs_offset;         // batch mode: obstacles of problem b = [obs_offset[b], obs_offset[b+1]); null: swarm mode
     int n_obs;                     // swarm mode: N-1
-    int P_pad;                     // swarm mode row pitch; batch mode: total pairs (rhs pitch)
+    int P_pad;                     // swarm mode: row pitch per agent
     const int* kept; const int* kept_count;   // pairs to price: swarm mode [b][P_pad]; batch mode at 5*obs_offset[b]
     double* safe;                             // per kept pair: travelled distance up to which it cannot be violated
-    const int* near; const int* near_count; int near_cap;   // initial working set (swarm mode; null in batch mode)
     int max_iter;
     // outputs
     double* x_out;                 // [n_problems][90] or null

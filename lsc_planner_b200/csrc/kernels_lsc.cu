@@ -102,11 +102,9 @@ void launch_predict(const PredictLaunch& L, cudaStream_t s) { k_predict<<<L.n_ag
 //     be violated by any trajectory that respects the velocity limits, so dropping is
 //     solution-preserving; survivors go to a shared-memory queue.
 //   Phase B (whenever the queue holds a full batch, and at the end): one queued (neighbour, segment) hull per thread —
-//     GJK in FP64 registers, LSC rows written to the agent's row store at the pair's dense index p = m*(N-1) + jj,
+//     GJK in FP64 registers, LSC rows written as one 64-byte record at the pair's slot of the agent's row store,
 //     p appended to the agent's kept list together with the smallest whitened slack of its rows at the unconstrained
-//     QP minimiser x0 (the QP kernel's verification sweeps skip a pair until the iterate has travelled that far), and
-//     to the agent's initial working-set lists: pairs with a row nearly active at initial_traj (the shifted previous
-//     solution, which is where the new solution usually ends up) and pairs with a row violated at x0.
+//     QP minimiser x0 (the QP kernel does not look at a pair again until the iterate has travelled that far).
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kLscThreads = 128;
 
@@ -117,8 +115,8 @@ __global__ void __launch_bounds__(kLscThreads) k_lsc_build(LscLaunch L) {
     __shared__ float4 own_sphere[kM];
     __shared__ float own_reach[kM];
     __shared__ int queue[kLscThreads * (kM + 1)];
-    __shared__ int q_count, kept_base, near_base[2];
-    __shared__ int warp_cnt[kM + 2][kLscThreads / 32];     // per-warp counts of the order-preserving compactions
+    __shared__ int q_count, kept_base;
+    __shared__ int warp_cnt[kM][kLscThreads / 32];     // per-warp counts of the order-preserving compactions
     const int al = blockIdx.x;
     const int a = L.a0 + al;
     const int n_obs = L.n_agents - 1;
@@ -133,14 +131,13 @@ __global__ void __launch_bounds__(kLscThreads) k_lsc_build(LscLaunch L) {
     }
     for (int e = tid; e < kAx; e += kLscThreads) inv_gn[e] = 1.0 / L.T->gnorm[ts - 1][e];
     if (tid < kM) { own_sphere[tid] = L.sphere[(size_t)tid * L.n_pad + a]; own_reach[tid] = L.reach[(size_t)a * kM + tid]; }
-    if (tid == 0) { q_count = 0; kept_base = 0; near_base[0] = near_base[1] = 0; }
+    if (tid == 0) { q_count = 0; kept_base = 0; }
     const int warp = tid >> 5, lane = tid & 31;
     constexpr int kWarps = kLscThreads / 32;
     __syncthreads();
 
     const AgentConstDev ca = L.consts[a];
-    float4* nrm_out = L.nrm + (size_t)al * L.P_pad;
-    double* rhs_out = L.rhs + (size_t)al * 6 * L.P_pad;
+    RowRec* rows_out = L.rows + (size_t)al * L.P_pad;
     int* kept_out = L.kept + (size_t)al * L.P_pad;
     double* safe_out = L.safe + (size_t)al * L.P_pad;
     int gjk_it = 0;
@@ -200,7 +197,7 @@ __global__ void __launch_bounds__(kLscThreads) k_lsc_build(LscLaunch L) {
             if (tid < n_items) p = queue[total - n_items + tid];      // take the batch from the END of the queue
             __syncthreads();
             if (tid == 0) q_count = total - n_items;
-            double mu_min = INFINITY, mu_near = INFINITY;
+            double mu_min = INFINITY;
             if (p >= 0) {
                 const int m = p / n_obs, jj2 = p % n_obs;
                 const int j = jj2 < a ? jj2 : jj2 + 1;
@@ -220,93 +217,35 @@ __global__ void __launch_bounds__(kLscThreads) k_lsc_build(LscLaunch L) {
                 const double ax = (double)seg.normal.x, ay = (double)seg.normal.y, az = (double)seg.normal.z;
                 const double an = sqrt(ax * ax + ay * ay + az * az);
                 const float inv_an = an > 0.0 ? (float)(1.0 / an) : INFINITY;
-                nrm_out[p] = make_float4(seg.normal.x, seg.normal.y, seg.normal.z, inv_an);
-                mu_min = INFINITY; mu_near = INFINITY;
+                RowRec rec;
+                rec.ax = seg.normal.x; rec.ay = seg.normal.y; rec.az = seg.normal.z; rec.inv_an = inv_an;
+                mu_min = INFINITY;
 #pragma unroll
                 for (int i = 0; i < 6; i++) {
                     // row  a . c_{m,i} >= d_i + a . o_{m,i}      (src/traj_optimizer.cpp:437-466)
                     const double rhs = seg.d[i] + (__dmul_rn(ax, (double)ob[i].x) + __dmul_rn(ay, (double)ob[i].y) +
                                                    __dmul_rn(az, (double)ob[i].z));
-                    rhs_out[(size_t)i * L.P_pad + p] = rhs;
+                    rec.rhs[i] = rhs;
                     if (m == 0 && i < kPhi) continue;
                     const int vi = m * 6 + i;
                     const double slack = ax * x0[vi] + ay * x0[kAx + vi] + az * x0[2 * kAx + vi] - rhs;
                     const double mu = an > 0.0 ? slack * (double)inv_an * inv_gn[vi] : (slack < 0.0 ? -INFINITY : INFINITY);
                     mu_min = fmin(mu_min, mu);
-                    // the same row at the agent's own initial_traj point (feasible when the previous step was)
-                    const double slack_c = ax * (double)ow[i].x + ay * (double)ow[i].y + az * (double)ow[i].z - rhs;
-                    mu_near = fmin(mu_near, an > 0.0 ? slack_c * (double)inv_an * inv_gn[vi] : -INFINITY);
                 }
                 kept_out[kept_base + tid] = p;
                 safe_out[kept_base + tid] = mu_min > 0.0 ? mu_min * 0.999999 : mu_min;
-            }
-            // working-set list 0 (nearly active at initial_traj), appended in batch order
-            {
-                const bool flag = p >= 0 && !(mu_near >= L.near_threshold);
-                const unsigned fmask = __ballot_sync(0xffffffffu, flag);
-                if (lane == 0) warp_cnt[kM][warp] = __popc(fmask);
-                __syncthreads();
-                int off = near_base[0];
-                for (int w = 0; w < warp; w++) off += warp_cnt[kM][w];
-                off += __popc(fmask & ((1u << lane) - 1u));
-                if (flag && off < L.near_cap) L.near[(size_t)(2 * al) * L.near_cap + off] = p;
-                __syncthreads();
-                if (tid == 0) {
-                    kept_base += n_items;
-                    for (int w = 0; w < kWarps; w++) near_base[0] += warp_cnt[kM][w];
+                {   // 64-byte record, four 16-byte stores
+                    float4* dst = reinterpret_cast<float4*>(rows_out + kept_base + tid);
+                    const float4* src = reinterpret_cast<const float4*>(&rec);
+                    dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
                 }
-                __syncthreads();
             }
+            __syncthreads();
+            if (tid == 0) kept_base += n_items;
+            __syncthreads();
         }
     }
-    // Working-set list 1: the pairs whose rows are MOST violated at x0 (at most near_cap of them). Depth buckets of
-    // the whitened violation (0.25 wide, 64 buckets), fully taken from the deepest down, the last bucket in kept order.
-    {
-        __shared__ int hist[64];
-        __shared__ int cut_depth, cut_take;
-        const int n_kept = kept_base;
-        if (tid < 64) hist[tid] = 0;
-        __syncthreads();
-        auto depth_of = [](double v) { return v < 0.0 ? min(63, (int)(-v * 4.0)) : -1; };
-        for (int sidx = tid; sidx < n_kept; sidx += kLscThreads) {
-            const int d = depth_of(safe_out[sidx]);
-            if (d >= 0) atomicAdd(&hist[d], 1);
-        }
-        __syncthreads();
-        if (tid == 0) {
-            int room = L.near_cap, cum = 0;
-            cut_depth = -1; cut_take = 0;              // buckets deeper than cut_depth are taken whole
-            int d = 63;
-            for (; d >= 0; d--) {
-                if (cum + hist[d] > room) break;
-                cum += hist[d];
-            }
-            cut_depth = d;                              // -1: everything fits
-            cut_take = d >= 0 ? room - cum : 0;
-        }
-        __syncthreads();
-        for (int pass = 0; pass < 2; pass++) {
-            if (pass == 1 && (cut_depth < 0 || cut_take == 0)) break;
-            for (int s0 = 0; s0 < n_kept; s0 += kLscThreads) {
-                const int sidx = s0 + tid;
-                const int d = sidx < n_kept ? depth_of(safe_out[sidx]) : -1;
-                const bool flag = pass == 0 ? d > cut_depth : (d >= 0 && d == cut_depth);
-                const unsigned fmask = __ballot_sync(0xffffffffu, flag);
-                if (lane == 0) warp_cnt[kM + 1][warp] = __popc(fmask);
-                __syncthreads();
-                int off = near_base[1];
-                for (int w = 0; w < warp; w++) off += warp_cnt[kM + 1][w];
-                off += __popc(fmask & ((1u << lane) - 1u));
-                const int limit = pass == 0 ? L.near_cap : min(L.near_cap, near_base[1] + cut_take);
-                (void)limit;
-                if (flag && off < L.near_cap) L.near[(size_t)(2 * al + 1) * L.near_cap + off] = kept_out[sidx];
-                __syncthreads();
-                if (tid == 0) for (int w = 0; w < kWarps; w++) near_base[1] += warp_cnt[kM + 1][w];
-                __syncthreads();
-            }
-        }
-    }
-    if (tid == 0) { L.kept_count[al] = kept_base; L.near_count[2 * al] = near_base[0]; L.near_count[2 * al + 1] = near_base[1]; }
+    if (tid == 0) L.kept_count[al] = kept_base;
     if (L.counters) {
         const int tot = warp_sum_int(gjk_it);
         if ((tid & 31) == 0) atomicAdd(&L.counters->gjk_iterations, (unsigned long long)tot);
@@ -371,7 +310,7 @@ void launch_gjk_batch(int n, const double* hulls, double* v, int* iters, cudaStr
 // Pair layout inside problem b with n_b obstacles: p = m * n_b + o, stored at pair offset 5 * obs_offset[b].
 // ------------------------------------------------------------------------------------------------------------
 __global__ void k_rows_from_lsc(int n_problems, const int* obs_offset, int total_obs, const float* lsc_normal,
-                                const float* lsc_point, const double* lsc_d, float4* nrm, double* rhs, int* kept,
+                                const float* lsc_point, const double* lsc_d, RowRec* rows, int* kept,
                                 int* kept_count, double* safe) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;     // global (obstacle, segment)
     if (t >= total_obs * kM) return;
@@ -384,23 +323,23 @@ __global__ void k_rows_from_lsc(int n_problems, const int* obs_offset, int total
     kept[p] = p - kM * obs_offset[b];                 // every pair is priced (no culling at the operator level)
     safe[p] = -INFINITY;                              // ... starting with the first iteration
     if (o == obs_offset[b] && m == 0) kept_count[b] = kM * n_b;
-    const size_t pitch = (size_t)total_obs * kM;
     const float* nv = lsc_normal + ((size_t)o * kM + m) * 3;
     const double ax = (double)nv[0], ay = (double)nv[1], az = (double)nv[2];
     const double an = sqrt(ax * ax + ay * ay + az * az);
-    nrm[p] = make_float4(nv[0], nv[1], nv[2], an > 0.0 ? (float)(1.0 / an) : INFINITY);
+    RowRec& rec = rows[p];
+    rec.ax = nv[0]; rec.ay = nv[1]; rec.az = nv[2]; rec.inv_an = an > 0.0 ? (float)(1.0 / an) : INFINITY;
     for (int i = 0; i < 6; i++) {
         const float* pt = lsc_point + (((size_t)o * kM + m) * 6 + i) * 3;
-        rhs[(size_t)i * pitch + p] = lsc_d[((size_t)o * kM + m) * 6 + i] +
+        rec.rhs[i] = lsc_d[((size_t)o * kM + m) * 6 + i] +
             (__dmul_rn(ax, (double)pt[0]) + __dmul_rn(ay, (double)pt[1]) + __dmul_rn(az, (double)pt[2]));
     }
 }
 void launch_rows_from_lsc(int n_problems, const int* obs_offset, int total_obs, const float* lsc_normal,
-                          const float* lsc_point, const double* lsc_d, float4* nrm, double* rhs, int* kept,
+                          const float* lsc_point, const double* lsc_d, RowRec* rows, int* kept,
                           int* kept_count, double* safe, cudaStream_t s) {
     if (total_obs <= 0) return;
     const int n = total_obs * kM;
-    k_rows_from_lsc<<<(n + 127) / 128, 128, 0, s>>>(n_problems, obs_offset, total_obs, lsc_normal, lsc_point, lsc_d, nrm, rhs,
+    k_rows_from_lsc<<<(n + 127) / 128, 128, 0, s>>>(n_problems, obs_offset, total_obs, lsc_normal, lsc_point, lsc_d, rows,
                                                     kept, kept_count, safe);
 }
 

@@ -1,4 +1,5 @@
-// k_qp_solve — the Bernstein trajectory QP of one agent per warp (sm_100a, FP64).
+// k_qp_solve — the Bernstein trajectory QP, one agent per thread block (sm_100a, FP64): warp 0 runs the dual
+// active-set iteration, all warps of the block price the rows.
 //
 // Replaces TrajOptimizer::solve (src/traj_optimizer.cpp:31-154): buildDeq (:239-259), populatebyrow (:261-539) and the
 // CPLEX dual-simplex call (:76; IBM ILOG CPLEX 20.1, third party, not in the reference tree).
@@ -16,25 +17,25 @@
 // the O(39^2) of a full orthogonal factor.
 //
 // Rows are never assembled as a matrix. Bounds (SFC boxes + world box), velocity and acceleration limits are priced
-// from x with per-lane constants held in registers. LSC rows come from the row store written by k_lsc_build (three
-// non-zeros each) and are priced in two tiers.
-//   Tier 1, every iteration: a working set of at most 48 pairs cached in shared memory — the pairs k_lsc_build found
-//     nearly active at initial_traj, plus pairs found violated by a sweep.
-//   Tier 2, only when tier 1 and the fixed rows show no violation: a distance-gated sweep over the kept pairs (those
-//     that survived k_lsc_build's exact culling). In the whitened space every row normal has unit length, so a row's
-//     slack cannot fall faster than the iterate travels: per pair we keep `safe` = (distance travelled when it was
-//     last evaluated) + (smallest whitened slack of its rows then); the sweep reads that one number per pair (8 B,
-//     coalesced) and loads and evaluates the 64 B row only if the travelled distance has reached it.
-// The solve ends when a sweep finds no row violated beyond the feasibility tolerance; every skipped row is provably
-// satisfied.
+// from x with per-thread constants held in registers (225 variables / stencils spread over the block). LSC rows come
+// from the row store written by k_lsc_build (three non-zeros each) and are priced EVERY iteration over all kept pairs
+// (those that survived k_lsc_build's exact culling), so the pivot is always the globally most violated row — the rule
+// that keeps the iteration count low (4-20) — but distance-gated: in the whitened space every row normal has unit
+// length, so a row's slack cannot fall faster than the iterate travels. Per pair we keep `safe` = (distance travelled
+// when it was last evaluated) + (smallest whitened slack of its rows then); a thread reads that one number per pair
+// (8 B, coalesced) and loads and evaluates the 64 B row only if the travelled distance has reached it. The solve ends
+// when no evaluated row is violated beyond the feasibility tolerance; every skipped row is provably satisfied.
+// The whole block prices (per-thread best -> warp shuffle argmin -> one shared-memory exchange); warp 0 then does the
+// factorisation update while the other warps wait at the barrier: the step time of a swarm is the slowest agent's
+// solve, so the design minimises one agent's latency, not aggregate throughput.
+#include <cstdlib>
+
 #include "kernels.hpp"
 
 namespace lscgpu {
 
 constexpr int NR = kRed;        // 39
 constexpr int LD = 39;          // row pitch of Q and R (odd: row-per-lane accesses are bank-conflict free)
-constexpr int kEvalCap = 192;   // batch of gated pairs evaluated together (one pair per lane per round)
-constexpr int WC = 48;          // working-set capacity (pairs cached in shared memory)
 // Primal feasibility tolerance = CPLEX's default EpRHS (the reference sets no tolerance, src/traj_optimizer.cpp:42-54):
 // like a dual simplex, a row enters the working set only when violated by more than this; entered rows are then met
 // exactly. Trajectories travel as float32, so agents in contact see hulls ~1e-7 closer than r_i + r_j; an exact
@@ -56,10 +57,11 @@ struct QpShared {
     double x[kNv];
     double nv[NR], z[NR], d[NR], tmp[NR], rr[NR], lam[NR], inv_diag[NR];
     double inv_gn[kAx];
-    double w_rhs[WC * 6];
-    float4 w_nrm[WC];
-    int w_pair[WC];
-    int eval_list[kEvalCap];    // kept-list positions a sweep has to evaluate
+    double lb[15], ub[15], vmax[3], amax[3];
+    double travelled;           // path length of the iterate in the whitened space
+    double best_mu[8];          // per-warp pricing result
+    int best_id[8];
+    int stop;                   // 0 run, 1 finished/failed (set by warp 0)
     int act[NR];
     SelectedRow sel;
 };
@@ -87,37 +89,8 @@ __device__ __forceinline__ Best warp_argmin(Best b) {
     return b;
 }
 
-// Per-lane constants of the fixed rows (ids 0..449): 3 variables and 5 dynamic-limit stencils per lane.
-struct FixedRows {
-    int bvar[3];            // variable index or -1
-    double blo[3], bhi[3], big[3];
-    int dbase[5];           // first variable of the stencil or -1
-    int dkind[5];           // 0 velocity, 1 acceleration
-    int did[5];             // row id of side 0
-    double dlim[5], dinv[5];
-};
-
-__device__ __forceinline__ void price_fixed(Best& best, const QpShared& S, int q, const FixedRows& F, double vel_coef,
-                                            double acc_coef) {
-#pragma unroll
-    for (int t = 0; t < 3; t++) {
-        if (F.bvar[t] < 0) continue;
-        const double xv = S.x[F.bvar[t]];
-        consider(best, S, q, xv - F.blo[t], F.big[t], F.bvar[t] * 2);
-        consider(best, S, q, F.bhi[t] - xv, F.big[t], F.bvar[t] * 2 + 1);
-    }
-#pragma unroll
-    for (int t = 0; t < 5; t++) {
-        if (F.dbase[t] < 0) continue;
-        const double* c = S.x + F.dbase[t];
-        const double expr = F.dkind[t] == 0 ? vel_coef * (c[1] - c[0]) : acc_coef * (c[2] - 2.0 * c[1] + c[0]);
-        consider(best, S, q, F.dlim[t] - expr, F.dinv[t], F.did[t]);
-        consider(best, S, q, F.dlim[t] + expr, F.dinv[t], F.did[t] + 1);
-    }
-}
-
 // one (obstacle, segment) pair: up to 6 rows. Returns the smallest whitened slack of the pair's rows.
-__device__ __forceinline__ double price_pair_vals(Best& best, const QpShared& S, int q, int p, int m, float4 nr,
+__device__ __forceinline__ double price_pair_vals(Best& best, const QpShared& S, int q, int slot, int m, float4 nr,
                                                   const double* r6) {
     const double ax = (double)nr.x, ay = (double)nr.y, az = (double)nr.z, inv = (double)nr.w;
     double mu_min = INFINITY;
@@ -129,20 +102,22 @@ __device__ __forceinline__ double price_pair_vals(Best& best, const QpShared& S,
         const double scale = inv * S.inv_gn[vi];
         const double mu = scale < INFINITY ? slack * scale : (slack < 0.0 ? -INFINITY : INFINITY);
         mu_min = fmin(mu_min, mu);
-        consider(best, S, q, slack, scale, kFixedRows + p * 6 + i);
+        consider(best, S, q, slack, scale, kFixedRows + slot * 6 + i);
     }
     return mu_min;
 }
 
-__device__ __forceinline__ void load_pair(int p, const float4* nrm, const double* rhs, size_t pitch, float4& nr,
-                                          double* r6) {
-    nr = nrm[p];
-#pragma unroll
-    for (int i = 0; i < 6; i++) r6[i] = rhs[(size_t)i * pitch + p];
+// one 64-byte row record: four 16-byte loads
+__device__ __forceinline__ void load_pair(const RowRec* rows, int slot, float4& nr, double* r6) {
+    const float4* src = reinterpret_cast<const float4*>(rows + slot);
+    nr = src[0];
+    const double2 a = *reinterpret_cast<const double2*>(src + 1), b = *reinterpret_cast<const double2*>(src + 2),
+                  c = *reinterpret_cast<const double2*>(src + 3);
+    r6[0] = a.x; r6[1] = a.y; r6[2] = b.x; r6[3] = b.y; r6[4] = c.x; r6[5] = c.y;
 }
 
-__device__ __forceinline__ void decode_row(QpShared& S, int id, int n_obs, const float4* nrm, const double* rhs,
-                                           size_t pitch, double vel_coef, double acc_coef, const double* lb,
+__device__ __forceinline__ void decode_row(QpShared& S, int id, int n_obs, const RowRec* rows, const int* kept,
+                                           double vel_coef, double acc_coef, const double* lb,
                                            const double* ub, const double* vmax, const double* amax) {
     SelectedRow& r = S.sel;
     if (id < 180) {
@@ -165,12 +140,12 @@ __device__ __forceinline__ void decode_row(QpShared& S, int id, int n_obs, const
             r.a[0] = sg * acc_coef; r.a[1] = -2.0 * sg * acc_coef; r.a[2] = sg * acc_coef; r.b = -amax[k];
         }
     } else {
-        const int e = id - kFixedRows, p = e / 6, i = e % 6, m = p / n_obs, vi = m * 6 + i;
-        const float4 nr = nrm[p];
+        const int e = id - kFixedRows, slot = e / 6, i = e % 6, m = kept[slot] / n_obs, vi = m * 6 + i;
+        const RowRec& rec = rows[slot];
         r.nnz = 3;
         r.idx[0] = vi; r.idx[1] = kAx + vi; r.idx[2] = 2 * kAx + vi;
-        r.a[0] = (double)nr.x; r.a[1] = (double)nr.y; r.a[2] = (double)nr.z;
-        r.b = rhs[(size_t)i * pitch + p];
+        r.a[0] = (double)rec.ax; r.a[1] = (double)rec.ay; r.a[2] = (double)rec.az;
+        r.b = rec.rhs[i];
     }
     for (int t = 0; t < r.nnz; t++) { r.axis[t] = r.idx[t] / kAx; r.var[t] = r.idx[t] % kAx; }
 }
@@ -215,19 +190,29 @@ __device__ __forceinline__ void drop_active(QpShared& S, int& q, int l, int lane
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(32) k_qp_solve(QpLaunch L) {
+// Fixed rows (ids 0..449) are 90 variable-bound pairs and 135 dynamic-limit stencil pairs = 225 items, spread over the
+// threads of the block; each thread keeps the constants of its items in registers.
+template <int kItems>
+struct FixedItems {
+    int base[kItems];       // bounds: variable index; stencils: first variable; -1: none
+    int kind[kItems];       // 0 bound, 1 velocity, 2 acceleration
+    int id[kItems];         // row id of side 0
+    double lo[kItems], hi[kItems], inv[kItems];     // bounds: lb, ub, 1/gnorm; stencils: limit, -, 1/|n|
+};
+
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads, 512 / kThreads) k_qp_solve(QpLaunch L) {
+    constexpr int kWarps = kThreads / 32;
+    constexpr int kItems = (225 + kThreads - 1) / kThreads;
     __shared__ QpShared S;
-    __shared__ double s_lb[15], s_ub[15], s_vmax[3], s_amax[3];
     const long long t_start = clock64();
     const int b = blockIdx.x;
-    const int lane = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool batch = L.obs_offset != nullptr;
     const int agent = L.agent_index ? L.agent_index[b] : L.agent_base + b;
     const int di = batch ? b : agent;                 // index into state9/goal3/ts/boxes
     const int n_obs = batch ? (L.obs_offset[b + 1] - L.obs_offset[b]) : L.n_obs;
-    const size_t pitch = (size_t)L.P_pad;
-    const float4* nrm = batch ? L.nrm + (size_t)kPairsPerObs * L.obs_offset[b] : L.nrm + (size_t)b * L.P_pad;
-    const double* rhs = batch ? L.rhs + (size_t)kPairsPerObs * L.obs_offset[b] : L.rhs + (size_t)b * 6 * L.P_pad;
+    const RowRec* rows = batch ? L.rows + (size_t)kPairsPerObs * L.obs_offset[b] : L.rows + (size_t)b * L.P_pad;
     double* safe = batch ? L.safe + (size_t)kPairsPerObs * L.obs_offset[b] : L.safe + (size_t)b * L.P_pad;
     const int* kept = batch ? L.kept + (size_t)kPairsPerObs * L.obs_offset[b] : L.kept + (size_t)b * L.P_pad;
     const int n_kept = L.kept_count[b];
@@ -238,326 +223,273 @@ __global__ void __launch_bounds__(32) k_qp_solve(QpLaunch L) {
 
     // ---- stage tables and problem data ------------------------------------------------------------------------
     const double* __restrict__ Gt = &T.G[ts - 1][0][0];      // whitened basis of this ts (read-only, L1-resident)
-    for (int e = lane; e < kAx; e += 32) S.inv_gn[e] = 1.0 / T.gnorm[ts - 1][e];
-    if (lane < 15) {
-        const int m = lane / 3, k = lane % 3;
+    for (int e = tid; e < kAx; e += kThreads) S.inv_gn[e] = 1.0 / T.gnorm[ts - 1][e];
+    if (tid < 15) {
+        const int m = tid / 3, k = tid % 3;
         double lo = (double)L.wmin[k], hi = (double)L.wmax[k];
         if (L.boxes) {      // SFC rows == per-variable bounds (src/traj_optimizer.cpp:409-434)
             const float* bx = L.boxes + (size_t)di * 30 + m * 6;
             lo = fmax(lo, (double)bx[k]);
             hi = fmin(hi, (double)bx[3 + k]);
         }
-        s_lb[lane] = lo; s_ub[lane] = hi;
+        S.lb[tid] = lo; S.ub[tid] = hi;
     }
-    if (lane < 3) { s_vmax[lane] = ac.vmax[lane]; s_amax[lane] = ac.amax[lane]; }
+    if (tid < 3) { S.vmax[tid] = ac.vmax[tid]; S.amax[tid] = ac.amax[tid]; }
     const double* st = L.state9 + (size_t)di * 9;
     const double* gl = L.goal3 + (size_t)di * 3;
-    for (int e = lane; e < kNv; e += 32) {
+    for (int e = tid; e < kNv; e += kThreads) {
         const int k = e / kAx, i = e % kAx;
         const double* Xs = T.Xs[ts - 1][i];
         S.x[e] = Xs[0] * st[k] + Xs[1] * st[3 + k] + Xs[2] * st[6 + k] + T.xg[ts - 1][i] * gl[k];
     }
-    __syncwarp();
-    // per-lane constants of the fixed rows
-    FixedRows F;
+    for (int e = tid; e < NR * LD; e += kThreads) S.R[e] = 0.0;
+    if (tid == 0) { S.travelled = 0.0; S.stop = 0; }
+    __syncthreads();
+    FixedItems<kItems> F;
 #pragma unroll
-    for (int t = 0; t < 3; t++) {
-        const int var = lane + 32 * t;
-        F.bvar[t] = -1; F.blo[t] = F.bhi[t] = F.big[t] = 0.0;
-        if (var < kNv) {
-            const int k = var / kAx, mi = var % kAx, m = mi / 6, i = mi % 6;
+    for (int t = 0; t < kItems; t++) {
+        const int item = tid + kThreads * t;
+        F.base[t] = -1; F.kind[t] = 0; F.id[t] = 0; F.lo[t] = F.hi[t] = F.inv[t] = 0.0;
+        if (item < kNv) {
+            const int k = item / kAx, mi = item % kAx, m = mi / 6, i = mi % 6;
             if (!(m == 0 && i < kPhi)) {
-                F.bvar[t] = var; F.blo[t] = s_lb[m * 3 + k]; F.bhi[t] = s_ub[m * 3 + k]; F.big[t] = S.inv_gn[mi];
+                F.base[t] = item; F.kind[t] = 0; F.id[t] = item * 2;
+                F.lo[t] = S.lb[m * 3 + k]; F.hi[t] = S.ub[m * 3 + k]; F.inv[t] = S.inv_gn[mi];
             }
-        }
-    }
-#pragma unroll
-    for (int t = 0; t < 5; t++) {
-        const int idx = lane + 32 * t;
-        F.dbase[t] = -1; F.dkind[t] = 0; F.did[t] = 0; F.dlim[t] = F.dinv[t] = 0.0;
-        if (idx < 135) {
+        } else if (item < kNv + 135) {
+            const int idx = item - kNv;
             const int k = idx / 45, rem = idx % 45, m = rem / 9, j = rem % 9;
             const bool vel = j < 5;
             const int i = vel ? j : j - 5;
             const bool skip = vel ? (m == 0 && j < 2) : (m == 0 && i == 0);
             if (!skip) {
-                F.dbase[t] = k * kAx + m * 6 + i;
-                F.dkind[t] = vel ? 0 : 1;
-                F.did[t] = 180 + idx * 2;
-                F.dlim[t] = vel ? s_vmax[k] : s_amax[k];
-                F.dinv[t] = 1.0 / T.dyn_norm[ts - 1][m][j];
+                F.base[t] = k * kAx + m * 6 + i; F.kind[t] = vel ? 1 : 2; F.id[t] = 180 + idx * 2;
+                F.lo[t] = vel ? S.vmax[k] : S.amax[k]; F.inv[t] = 1.0 / T.dyn_norm[ts - 1][m][j];
             }
         }
     }
-
-    for (int e = lane; e < NR * LD; e += 32) S.R[e] = 0.0;
-    // per-lane index constants (no divisions in the loop)
+    // warp 0: per-lane index constants of the factorisation update (no divisions in the loop)
     const int c_axis0 = lane / kFree, c_col0 = lane % kFree;      // whitened coordinate c = lane
     int x_axis[3], x_var[3];
 #pragma unroll
     for (int h = 0; h < 3; h++) { const int e = min(lane + 32 * h, kNv - 1); x_axis[h] = e / kAx; x_var[h] = e % kAx; }
     int q = 0, iters = 0, status = LSCGPU_QP_OK;
-    double travelled = 0.0;          // path length of the iterate in the whitened space
-    unsigned long long rows_priced = 0, full_passes = 0;
-    // initial working set
-    int n_work = 0;
-    if (L.near) {
-        // list 1 (most violated at x0) first — those rows are pivoted on at once — then list 0 (nearly active at
-        // initial_traj) while there is room
-        const int* lists = L.near + (size_t)(2 * b) * L.near_cap;
-        const int n1 = min(min(L.near_count[2 * b + 1], L.near_cap), WC);
-        for (int w = lane; w < n1; w += 32) S.w_pair[w] = lists[L.near_cap + w];
-        n_work = n1;
-        __syncwarp();
-        const int n0 = min(L.near_count[2 * b], L.near_cap);
-        for (int w0 = 0; w0 < n0 && n_work < WC; w0 += 32) {
-            const int p = w0 + lane < n0 ? lists[w0 + lane] : -1;
-            bool fresh = p >= 0;
-            for (int k = 0; k < n1 && fresh; k++) fresh = S.w_pair[k] != p;
-            const unsigned mask = __ballot_sync(0xffffffffu, fresh);
-            const int slot = n_work + __popc(mask & ((1u << lane) - 1u));
-            if (fresh && slot < WC) S.w_pair[slot] = p;
-            n_work = min(n_work + __popc(mask), WC);
-        }
-        __syncwarp();
-        for (int w = lane; w < n_work; w += 32) {
-            float4 nr; double r6[6];
-            load_pair(S.w_pair[w], nrm, rhs, pitch, nr, r6);
-            S.w_nrm[w] = nr;
-#pragma unroll
-            for (int i = 0; i < 6; i++) S.w_rhs[w * 6 + i] = r6[i];
-        }
-    }
-    __syncwarp();
+    unsigned long long pairs_evaluated = 0, passes = 0;
 
     while (true) {
-        // ---- pricing: tier 1 --------------------------------------------------------------------------------------
+        // ---- pricing by the whole block ---------------------------------------------------------------------------
         Best best{0.0, -1};
-        price_fixed(best, S, q, F, vel_coef, acc_coef);
-        for (int w = lane; w < n_work; w += 32) {
-            const int p = S.w_pair[w];
-            price_pair_vals(best, S, q, p, p / n_obs, S.w_nrm[w], S.w_rhs + w * 6);
-        }
-        rows_priced += 414 + 6ull * n_work;
-        best = warp_argmin(best);
-        if (best.id < 0) {
-            // ---- tier 2: distance-gated sweep over the kept pairs -------------------------------------------------
-            // scan the gate values (4 per lane in flight), compact the positions that need evaluation into shared
-            // memory, and evaluate them one pair per lane per round so that all row loads of a round are in flight
-            full_passes++;
-            int evaluated = 0, n_list = 0;
-            for (int s0 = 0; s0 < n_kept || n_list > 0; s0 += 128) {
-                if (s0 < n_kept) {
-                    double sv[4];
+        const double travelled = S.travelled;
 #pragma unroll
-                    for (int h = 0; h < 4; h++) {
-                        const int si = s0 + 32 * h + lane;
-                        sv[h] = si < n_kept ? safe[si] : INFINITY;
-                    }
-#pragma unroll
-                    for (int h = 0; h < 4; h++) {
-                        const bool need = !(sv[h] > travelled);
-                        const unsigned mask = __ballot_sync(0xffffffffu, need);
-                        if (need) S.eval_list[n_list + __popc(mask & ((1u << lane) - 1u))] = s0 + 32 * h + lane;
-                        n_list += __popc(mask);
-                    }
-                    __syncwarp();
-                }
-                const bool last = s0 + 128 >= n_kept;
-                if (n_list <= kEvalCap - 128 && !last) continue;     // room for another chunk: keep scanning
-                for (int e0 = 0; e0 < n_list; e0 += 32) {
-                    const int e = e0 + lane;
-                    bool viol = false;
-                    int p = -1;
-                    float4 nr; double r6[6];
-                    if (e < n_list) {
-                        const int si = S.eval_list[e];
-                        p = kept[si];
-                        load_pair(p, nrm, rhs, pitch, nr, r6);
-                        const double mu_min = price_pair_vals(best, S, q, p, p / n_obs, nr, r6);
-                        // 1e-6 relative margin: the stored 1/|a| is float32, so mu carries ~6e-8 relative error
-                        safe[si] = travelled + (mu_min > 0.0 ? mu_min * 0.999999 : mu_min);
-                        evaluated++;
-                        const int m = p / n_obs;
-#pragma unroll
-                        for (int i = 0; i < 6; i++) {
-                            if (m == 0 && i < kPhi) continue;
-                            const int vi = m * 6 + i;
-                            viol |= (double)nr.x * S.x[vi] + (double)nr.y * S.x[kAx + vi] + (double)nr.z * S.x[2 * kAx + vi] - r6[i] < -kFeasTol;
-                        }
-                    }
-                    const unsigned mask = __ballot_sync(0xffffffffu, viol);
-                    if (viol) {
-                        const int slot = n_work + __popc(mask & ((1u << lane) - 1u));
-                        if (slot < WC) {
-                            S.w_pair[slot] = p; S.w_nrm[slot] = nr;
-#pragma unroll
-                            for (int i = 0; i < 6; i++) S.w_rhs[slot * 6 + i] = r6[i];
-                        }
-                    }
-                    n_work = min(n_work + __popc(mask), WC);
-                }
-                n_list = 0;
-                __syncwarp();
-            }
-            rows_priced += 6ull * warp_sum_int(evaluated);
-            __syncwarp();
-            best = warp_argmin(best);
-            if (best.id < 0) break;             // no row violated beyond the tolerance anywhere: done
-        }
-        {
-            bool dup = false;
-            for (int k = lane; k < q; k += 32) dup |= S.act[k] == best.id;
-            if (__any_sync(0xffffffffu, dup)) { status = LSCGPU_QP_MAXITER; break; }   // numerical breakdown
-        }
-        if (lane == 0) decode_row(S, best.id, n_obs, nrm, rhs, pitch, vel_coef, acc_coef, s_lb, s_ub, s_vmax, s_amax);
-        __syncwarp();
-        // whitened normal  nv = (G (+) G (+) G)^T a, normalised
-        double part = 0.0;
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int c = lane + 32 * h;
-            if (c < NR) {
-                const int k = h == 0 ? c_axis0 : 2, cc = h == 0 ? c_col0 : c - 2 * kFree;
-                double s = 0.0;
-                for (int t = 0; t < S.sel.nnz; t++)
-                    if (S.sel.axis[t] == k) s += S.sel.a[t] * __ldg(Gt + S.sel.var[t] * kFree + cc);
-                S.nv[c] = s;
-                part += s * s;
-            }
-        }
-        const double nrm_len = sqrt(warp_sum(part));
-        if (!(nrm_len > 0.0)) { status = LSCGPU_QP_INFEASIBLE; break; }
-        const double inv_len = 1.0 / nrm_len;
-        __syncwarp();
-        for (int c = lane; c < NR; c += 32) S.nv[c] *= inv_len;
-        __syncwarp();
-        double lam_p = 0.0;
-        bool fail = false;
-        while (true) {
-            if (++iters > L.max_iter) { status = LSCGPU_QP_MAXITER; fail = true; break; }
-            // ---- z = (I - Q Q^T) nv by two Gram-Schmidt passes; d = Q^T nv ---------------------------------------
-            for (int c = lane; c < NR; c += 32) { S.z[c] = S.nv[c]; S.d[c] = 0.0; }
-            __syncwarp();
-            double zz = 1.0;                 // |nv| = 1
-            if (q > 0) {
-#pragma unroll 1
-                for (int pass = 0; pass < 2; pass++) {
-                    for (int k = lane; k < q; k += 32) {          // lane k: column k of Q against z
-                        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-#pragma unroll
-                        for (int r = 0; r < NR; r += 3) {
-                            s0 += S.Q[r * LD + k] * S.z[r];
-                            s1 += S.Q[(r + 1) * LD + k] * S.z[r + 1];
-                            s2 += S.Q[(r + 2) * LD + k] * S.z[r + 2];
-                        }
-                        const double s = s0 + s1 + s2;
-                        S.tmp[k] = s;
-                        S.d[k] += s;
-                    }
-                    __syncwarp();
-                    double zp = 0.0;
-                    for (int r = lane; r < NR; r += 32) {         // lane r: row r of Q against the coefficients
-                        double s0 = 0.0, s1 = 0.0;
-                        int k = 0;
-                        for (; k + 1 < q; k += 2) {
-                            s0 += S.Q[r * LD + k] * S.tmp[k];
-                            s1 += S.Q[r * LD + k + 1] * S.tmp[k + 1];
-                        }
-                        if (k < q) s0 += S.Q[r * LD + k] * S.tmp[k];
-                        const double zr = S.z[r] - (s0 + s1);
-                        S.z[r] = zr;
-                        zp += zr * zr;
-                    }
-                    const double zz_new = warp_sum(zp);
-                    __syncwarp();
-                    // "twice is enough": a second pass only when the first one cancelled most of the vector
-                    const bool again = zz_new < 0.25 * zz;
-                    zz = zz_new;
-                    if (!again) break;
-                }
-            }
-            // rr = R^-1 d (change of the active multipliers per unit step): column-oriented back substitution,
-            // rr[k] lives in lane k's register while q <= 32
-            if (q <= 32) {
-                double rk = lane < q ? S.d[lane] : 0.0;
-                for (int c = q - 1; c >= 0; c--) {
-                    const double piv = __shfl_sync(0xffffffffu, rk, c) * S.inv_diag[c];
-                    if (lane < c) rk -= S.R[lane * LD + c] * piv;
-                    if (lane == c) rk = piv;
-                }
-                if (lane < q) S.rr[lane] = rk;
+        for (int t = 0; t < kItems; t++) {
+            if (F.base[t] < 0) continue;
+            const double* c = S.x + F.base[t];
+            if (F.kind[t] == 0) {
+                consider(best, S, q, c[0] - F.lo[t], F.inv[t], F.id[t]);
+                consider(best, S, q, F.hi[t] - c[0], F.inv[t], F.id[t] + 1);
             } else {
-                for (int k = lane; k < q; k += 32) S.rr[k] = S.d[k];
-                for (int c = q - 1; c >= 0; c--) {
-                    __syncwarp();
-                    const double piv = S.rr[c] * S.inv_diag[c];
-                    __syncwarp();
-                    for (int k = lane; k < c; k += 32) S.rr[k] -= S.R[k * LD + c] * piv;
-                    if (lane == 0) S.rr[c] = piv;
-                }
+                const double expr = F.kind[t] == 1 ? vel_coef * (c[1] - c[0]) : acc_coef * (c[2] - 2.0 * c[1] + c[0]);
+                consider(best, S, q, F.lo[t] - expr, F.inv[t], F.id[t]);
+                consider(best, S, q, F.lo[t] + expr, F.inv[t], F.id[t] + 1);
             }
-            __syncwarp();
-            // ratio test over the active multipliers
-            double t1 = INFINITY;
-            int l = -1;
-            for (int k = lane; k < q; k += 32)
-                if (S.rr[k] > kZeroTol) {
-                    const double t = S.lam[k] / S.rr[k];
-                    if (t < t1) { t1 = t; l = k; }
-                }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double ot = __shfl_xor_sync(0xffffffffu, t1, o);
-                const int ol = __shfl_xor_sync(0xffffffffu, l, o);
-                if (ol >= 0 && (l < 0 || ot < t1 || (ot == t1 && ol < l))) { t1 = ot; l = ol; }
-            }
-            const bool primal = zz > kZeroTol;
-            const double slack = selected_slack(S) * inv_len;
-            double t2 = primal ? -slack / zz : INFINITY;
-            if (t2 < 0.0) t2 = 0.0;
-            const double t = fmin(t1, t2);
-            if (!(t < INFINITY)) { status = LSCGPU_QP_INFEASIBLE; fail = true; break; }
-            for (int k = lane; k < q; k += 32) S.lam[k] -= t * S.rr[k];
-            lam_p += t;
-            if (!primal) { drop_active(S, q, l, lane); continue; }
-            travelled += t * sqrt(zz) * (1.0 + 1e-9) + 1e-13;
-#pragma unroll
-            for (int h = 0; h < 3; h++) {
-                const int e = lane + 32 * h;
-                if (e < kNv) {
-                    const double* g = Gt + x_var[h] * kFree;
-                    const double* zk = S.z + x_axis[h] * kFree;
-                    double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-                    for (int c = 0; c + 1 < kFree; c += 2) { s0 += __ldg(g + c) * zk[c]; s1 += __ldg(g + c + 1) * zk[c + 1]; }
-                    s0 += __ldg(g + kFree - 1) * zk[kFree - 1];
-                    S.x[e] += t * (s0 + s1);
-                }
-            }
-            __syncwarp();
-            if (t2 <= t1) {
-                // the row becomes active: new basis column z / |z|, new column (d, |z|) of R
-                const double zn = sqrt(zz), izn = 1.0 / zn;
-                for (int r = lane; r < NR; r += 32) S.Q[r * LD + q] = S.z[r] * izn;
-                for (int k = lane; k < q; k += 32) S.R[k * LD + q] = S.d[k];
-                if (lane == 0) {
-                    S.R[q * LD + q] = zn;
-                    S.inv_diag[q] = izn;
-                    S.act[q] = best.id;
-                    S.lam[q] = lam_p;
-                }
-                q++;
-                __syncwarp();
-                break;
-            }
-            drop_active(S, q, l, lane);
         }
-        if (fail) break;
+        for (int s0 = 0; s0 < n_kept; s0 += 4 * kThreads) {
+            double sv[4];
+#pragma unroll
+            for (int h = 0; h < 4; h++) {               // four gate values per thread in flight
+                const int si = s0 + kThreads * h + tid;
+                sv[h] = si < n_kept ? safe[si] : INFINITY;
+            }
+#pragma unroll
+            for (int h = 0; h < 4; h++) {
+                if (sv[h] > travelled) continue;        // cannot be violated yet
+                const int si = s0 + kThreads * h + tid;
+                float4 nr; double r6[6];
+                load_pair(rows, si, nr, r6);
+                const double mu_min = price_pair_vals(best, S, q, si, kept[si] / n_obs, nr, r6);
+                // 1e-6 relative margin: the stored 1/|a| is float32, so mu carries ~6e-8 relative error
+                safe[si] = travelled + (mu_min > 0.0 ? mu_min * 0.999999 : mu_min);
+                pairs_evaluated++;
+            }
+        }
+        passes++;
+        best = warp_argmin(best);
+        if (lane == 0) { S.best_mu[warp] = best.mu; S.best_id[warp] = best.id; }
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < kWarps; w++) {
+            const double mu = S.best_mu[w];
+            const int id = S.best_id[w];
+            if (w == 0) { best.mu = mu; best.id = id; }
+            else if (id >= 0 && (best.id < 0 || mu < best.mu || (mu == best.mu && id < best.id))) { best.mu = mu; best.id = id; }
+        }
+        if (best.id < 0) break;                 // no row violated beyond the tolerance anywhere: done (block-uniform)
+
+        // ---- factorisation update by warp 0 -----------------------------------------------------------------------
+        if (warp == 0) {
+            bool done = false;          // set when the solve must stop (failure)
+            do {
+                {
+                    bool dup = false;
+                    for (int k = lane; k < q; k += 32) dup |= S.act[k] == best.id;
+                    if (__any_sync(0xffffffffu, dup)) { status = LSCGPU_QP_MAXITER; done = true; break; }   // numerical breakdown
+                }
+                if (lane == 0) decode_row(S, best.id, n_obs, rows, kept, vel_coef, acc_coef, S.lb, S.ub, S.vmax, S.amax);
+                __syncwarp();
+                // whitened normal  nv = (G (+) G (+) G)^T a, normalised
+                double part = 0.0;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int c = lane + 32 * h;
+                    if (c < NR) {
+                        const int k = h == 0 ? c_axis0 : 2, cc = h == 0 ? c_col0 : c - 2 * kFree;
+                        double sacc = 0.0;
+                        for (int t = 0; t < S.sel.nnz; t++)
+                            if (S.sel.axis[t] == k) sacc += S.sel.a[t] * __ldg(Gt + S.sel.var[t] * kFree + cc);
+                        S.nv[c] = sacc;
+                        part += sacc * sacc;
+                    }
+                }
+                const double nrm_len = sqrt(warp_sum(part));
+                if (!(nrm_len > 0.0)) { status = LSCGPU_QP_INFEASIBLE; done = true; break; }
+                const double inv_len = 1.0 / nrm_len;
+                __syncwarp();
+                for (int c = lane; c < NR; c += 32) S.nv[c] *= inv_len;
+                __syncwarp();
+                double lam_p = 0.0;
+                while (true) {
+                    if (++iters > L.max_iter) { status = LSCGPU_QP_MAXITER; done = true; break; }
+                    // ---- z = (I - Q Q^T) nv by Gram-Schmidt (second pass when needed); d = Q^T nv --------------------
+                    for (int c = lane; c < NR; c += 32) { S.z[c] = S.nv[c]; S.d[c] = 0.0; }
+                    __syncwarp();
+                    double zz = 1.0;                 // |nv| = 1
+                    if (q > 0) {
+#pragma unroll 1
+                        for (int pass = 0; pass < 2; pass++) {
+                            for (int k = lane; k < q; k += 32) {          // lane k: column k of Q against z
+                                double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+                                for (int r = 0; r < NR; r += 3) {
+                                    s0 += S.Q[r * LD + k] * S.z[r];
+                                    s1 += S.Q[(r + 1) * LD + k] * S.z[r + 1];
+                                    s2 += S.Q[(r + 2) * LD + k] * S.z[r + 2];
+                                }
+                                const double sdot = s0 + s1 + s2;
+                                S.tmp[k] = sdot;
+                                S.d[k] += sdot;
+                            }
+                            __syncwarp();
+                            double zp = 0.0;
+                            for (int r = lane; r < NR; r += 32) {         // lane r: row r of Q against the coefficients
+                                double s0 = 0.0, s1 = 0.0;
+                                int k = 0;
+                                for (; k + 1 < q; k += 2) {
+                                    s0 += S.Q[r * LD + k] * S.tmp[k];
+                                    s1 += S.Q[r * LD + k + 1] * S.tmp[k + 1];
+                                }
+                                if (k < q) s0 += S.Q[r * LD + k] * S.tmp[k];
+                                const double zr = S.z[r] - (s0 + s1);
+                                S.z[r] = zr;
+                                zp += zr * zr;
+                            }
+                            const double zz_new = warp_sum(zp);
+                            __syncwarp();
+                            // "twice is enough": a second pass only when the first one cancelled most of the vector
+                            const bool again = zz_new < 0.25 * zz;
+                            zz = zz_new;
+                            if (!again) break;
+                        }
+                    }
+                    // rr = R^-1 d (change of the active multipliers per unit step): column-oriented back
+                    // substitution, rr[k] lives in lane k's register while q <= 32
+                    if (q <= 32) {
+                        double rk = lane < q ? S.d[lane] : 0.0;
+                        for (int c = q - 1; c >= 0; c--) {
+                            const double piv = __shfl_sync(0xffffffffu, rk, c) * S.inv_diag[c];
+                            if (lane < c) rk -= S.R[lane * LD + c] * piv;
+                            if (lane == c) rk = piv;
+                        }
+                        if (lane < q) S.rr[lane] = rk;
+                    } else {
+                        for (int k = lane; k < q; k += 32) S.rr[k] = S.d[k];
+                        for (int c = q - 1; c >= 0; c--) {
+                            __syncwarp();
+                            const double piv = S.rr[c] * S.inv_diag[c];
+                            __syncwarp();
+                            for (int k = lane; k < c; k += 32) S.rr[k] -= S.R[k * LD + c] * piv;
+                            if (lane == 0) S.rr[c] = piv;
+                        }
+                    }
+                    __syncwarp();
+                    // ratio test over the active multipliers
+                    double t1 = INFINITY;
+                    int l = -1;
+                    for (int k = lane; k < q; k += 32)
+                        if (S.rr[k] > kZeroTol) {
+                            const double t = S.lam[k] / S.rr[k];
+                            if (t < t1) { t1 = t; l = k; }
+                        }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const double ot = __shfl_xor_sync(0xffffffffu, t1, o);
+                        const int ol = __shfl_xor_sync(0xffffffffu, l, o);
+                        if (ol >= 0 && (l < 0 || ot < t1 || (ot == t1 && ol < l))) { t1 = ot; l = ol; }
+                    }
+                    const bool primal = zz > kZeroTol;
+                    const double slack = selected_slack(S) * inv_len;
+                    double t2 = primal ? -slack / zz : INFINITY;
+                    if (t2 < 0.0) t2 = 0.0;
+                    const double t = fmin(t1, t2);
+                    if (!(t < INFINITY)) { status = LSCGPU_QP_INFEASIBLE; done = true; break; }
+                    for (int k = lane; k < q; k += 32) S.lam[k] -= t * S.rr[k];
+                    lam_p += t;
+                    if (!primal) { drop_active(S, q, l, lane); continue; }
+                    if (lane == 0) S.travelled += t * sqrt(zz) * (1.0 + 1e-9) + 1e-13;
+#pragma unroll
+                    for (int h = 0; h < 3; h++) {
+                        const int e = lane + 32 * h;
+                        if (e < kNv) {
+                            const double* g = Gt + x_var[h] * kFree;
+                            const double* zk = S.z + x_axis[h] * kFree;
+                            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                            for (int c = 0; c + 1 < kFree; c += 2) { s0 += __ldg(g + c) * zk[c]; s1 += __ldg(g + c + 1) * zk[c + 1]; }
+                            s0 += __ldg(g + kFree - 1) * zk[kFree - 1];
+                            S.x[e] += t * (s0 + s1);
+                        }
+                    }
+                    __syncwarp();
+                    if (t2 <= t1) {
+                        // the row becomes active: new basis column z / |z|, new column (d, |z|) of R
+                        const double zn = sqrt(zz), izn = 1.0 / zn;
+                        for (int r = lane; r < NR; r += 32) S.Q[r * LD + q] = S.z[r] * izn;
+                        for (int k = lane; k < q; k += 32) S.R[k * LD + q] = S.d[k];
+                        if (lane == 0) {
+                            S.R[q * LD + q] = zn;
+                            S.inv_diag[q] = izn;
+                            S.act[q] = best.id;
+                            S.lam[q] = lam_p;
+                        }
+                        q++;
+                        __syncwarp();
+                        break;
+                    }
+                    drop_active(S, q, l, lane);
+                }
+            } while (false);
+            if (done && lane == 0) S.stop = 1;
+        }
+        __syncthreads();
+        if (S.stop) break;
     }
-    __syncwarp();
+    __syncthreads();
 
     // ---- epilogue ---------------------------------------------------------------------------------------------
+    if (L.counters) {
+        const unsigned long long ev = warp_sum((double)pairs_evaluated) + 0.5;
+        if (lane == 0) atomicAdd(&L.counters->rows_priced, 6ull * ev + (warp == 0 ? 414ull * passes : 0ull));
+    }
+    if (warp != 0) return;
     // objective as the reference reports it (getObjValue incl. the constant of the terminal cost)
     double jpart = 0.0;
     if (lane < 15) {
@@ -569,9 +501,8 @@ __global__ void __launch_bounds__(32) k_qp_solve(QpLaunch L) {
     }
     const double cost = warp_sum(jpart);
     if (L.counters && lane == 0) {
-        atomicAdd(&L.counters->rows_priced, rows_priced);
         atomicAdd(&L.counters->qp_iterations, (unsigned long long)iters);
-        atomicAdd(&L.counters->full_passes, full_passes);
+        atomicAdd(&L.counters->full_passes, passes);
     }
     if (L.x_out)
         for (int e = lane; e < kNv; e += 32) L.x_out[(size_t)b * kNv + e] = S.x[e];
@@ -607,7 +538,7 @@ __global__ void __launch_bounds__(32) k_qp_solve(QpLaunch L) {
             o.qp_active = q;
             o.flags = L.flags ? L.flags[agent] : 0;
             o.terminal_segments = ts;
-            o.qp_sweeps = (int)full_passes;
+            o.qp_sweeps = (int)passes;
             o.qp_kcycles = (int)((clock64() - t_start) >> 10);
         }
     }
@@ -615,7 +546,17 @@ __global__ void __launch_bounds__(32) k_qp_solve(QpLaunch L) {
 
 void launch_qp_solve(const QpLaunch& L, cudaStream_t s) {
     if (L.n_problems <= 0) return;
-    k_qp_solve<<<L.n_problems, 32, 0, s>>>(L);
+    // the step time is the slowest agent's solve, so every agent gets several warps for pricing: eight while the
+    // launch still fits one wave at 2 blocks per SM, four otherwise (measured faster than two even when that means
+    // a second wave)
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    static const int forced = getenv("LSCGPU_QP_THREADS") ? atoi(getenv("LSCGPU_QP_THREADS")) : 0;
+    const int threads = forced ? forced : (L.n_problems <= 2 * sms ? 256 : 128);
+    if (threads == 256) k_qp_solve<256><<<L.n_problems, 256, 0, s>>>(L);
+    else if (threads == 128) k_qp_solve<128><<<L.n_problems, 128, 0, s>>>(L);
+    else k_qp_solve<64><<<L.n_problems, 64, 0, s>>>(L);
 }
 
 }  // namespace lscgpu
