@@ -75,7 +75,7 @@ struct lscgpu_engine {
     lscgpu_agent_in* d_in = nullptr;
     lscgpu_agent_out* d_out = nullptr;     // [n_out] gather buffer
     int n_out = 0;
-    float *d_traj = nullptr, *d_pred = nullptr, *d_predT = nullptr, *d_boxes = nullptr;
+    float *d_traj = nullptr, *d_pred = nullptr, *d_predT = nullptr, *d_predZs = nullptr, *d_boxes = nullptr;
     double *d_state9 = nullptr, *d_goal3 = nullptr, *d_last_cost = nullptr;
     int *d_ts = nullptr, *d_flags = nullptr, *d_init_sfc = nullptr;
     // row store of the local shard
@@ -132,7 +132,7 @@ extern "C" void lscgpu_destroy(lscgpu_engine* e) {
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     free_rows(e);
     cudaFree(e->d_tables); cudaFree(e->d_consts); cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_traj);
-    cudaFree(e->d_pred); cudaFree(e->d_predT); cudaFree(e->d_boxes); cudaFree(e->d_state9); cudaFree(e->d_goal3);
+    cudaFree(e->d_pred); cudaFree(e->d_predT); cudaFree(e->d_predZs); cudaFree(e->d_boxes); cudaFree(e->d_state9); cudaFree(e->d_goal3);
     cudaFree(e->d_last_cost); cudaFree(e->d_ts); cudaFree(e->d_flags); cudaFree(e->d_init_sfc); cudaFree(e->d_counters);
     cudaFree(e->dm.sqdist); cudaFree(e->dm.sat); cudaFree(e->d_sphere); cudaFree(e->d_reach);
     for (auto& se : e->ev_pool) for (auto& ev : se.ev) if (ev) cudaEventDestroy(ev);
@@ -227,6 +227,8 @@ extern "C" int lscgpu_create(const lscgpu_params* p, int n_agents, const lscgpu_
     CUB(cudaMalloc(&e->d_pred, sizeof(float) * N * kTrajFloats));
     CUB(cudaMalloc(&e->d_predT, sizeof(float) * (size_t)kTrajFloats * e->n_pad));
     CUB(cudaMemset(e->d_predT, 0, sizeof(float) * (size_t)kTrajFloats * e->n_pad));
+    CUB(cudaMalloc(&e->d_predZs, sizeof(float) * (size_t)30 * e->n_pad));
+    CUB(cudaMemset(e->d_predZs, 0, sizeof(float) * (size_t)30 * e->n_pad));
     CUB(cudaMalloc(&e->d_sphere, sizeof(float4) * (size_t)kM * e->n_pad));
     CUB(cudaMemset(e->d_sphere, 0, sizeof(float4) * (size_t)kM * e->n_pad));
     CUB(cudaMalloc(&e->d_reach, sizeof(float) * N * kM));
@@ -404,7 +406,7 @@ static int step_device(lscgpu_engine* e) {
     pl.n_agents = e->N; pl.n_pad = e->n_pad; pl.planner_seq = e->planner_seq;
     pl.dt = e->prm.dt; pl.reset_threshold = e->prm.reset_threshold;
     pl.in = e->d_in; pl.prev_traj = e->d_traj; pl.consts = e->d_consts;
-    pl.pred = e->d_pred; pl.predT = e->d_predT; pl.state9 = e->d_state9; pl.goal3 = e->d_goal3;
+    pl.pred = e->d_pred; pl.predT = e->d_predT; pl.predZs = e->d_predZs; pl.state9 = e->d_state9; pl.goal3 = e->d_goal3;
     pl.ts = e->d_ts; pl.flags = e->d_flags; pl.sphere = e->d_sphere; pl.reach = e->d_reach;
     launch_predict(pl, s); launches++;
     if (prof) CU(cudaEventRecord(ev[1], s));
@@ -423,7 +425,7 @@ static int step_device(lscgpu_engine* e) {
     if (n_local > 0 && e->N > 1) {
         LscLaunch ll{};
         ll.n_agents = e->N; ll.n_pad = e->n_pad; ll.a0 = e->a0; ll.n_local = n_local;
-        ll.pred = e->d_pred; ll.predT = e->d_predT; ll.consts = e->d_consts; ll.T = e->d_tables;
+        ll.pred = e->d_pred; ll.predT = e->d_predT; ll.predZs = e->d_predZs; ll.consts = e->d_consts; ll.T = e->d_tables;
         ll.state9 = e->d_state9; ll.goal3 = e->d_goal3; ll.ts = e->d_ts;
         ll.sphere = e->d_sphere; ll.reach = e->d_reach;
         ll.rows = e->d_rows; ll.P_pad = e->P_pad;

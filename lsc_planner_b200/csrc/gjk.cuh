@@ -154,16 +154,17 @@ struct LscSegment {
     int iterations;
 };
 
-__device__ __forceinline__ void lsc_segment(const F3* own, const F3* obs, double downwash, double collision_dist,
-                                            LscSegment& out) {
+// coordinateTransform (include/util.hpp:231-240): z divided by the pair's downwash ratio, in double, stored as float
+__device__ __forceinline__ float downwash_scaled_z(float z, double downwash) { return (float)__ddiv_rn((double)z, downwash); }
+
+// own_s/obs_s: the 6 control points with z ALREADY downwash-scaled
+__device__ __forceinline__ void lsc_segment_scaled(const F3* own_s, const F3* obs_s, double downwash, double collision_dist,
+                                                   LscSegment& out) {
     F3 rel_f[6];
     D3 rel[6];
 #pragma unroll
     for (int i = 0; i < 6; i++) {
-        F3 a = own[i], o = obs[i];
-        a.z = (float)__ddiv_rn((double)a.z, downwash);         // coordinateTransform, include/util.hpp:231-240
-        o.z = (float)__ddiv_rn((double)o.z, downwash);
-        rel_f[i] = f3_sub(a, o);
+        rel_f[i] = f3_sub(own_s[i], obs_s[i]);
         rel[i] = D3{(double)rel_f[i].x, (double)rel_f[i].y, (double)rel_f[i].z};
     }
     D3 v;
@@ -178,6 +179,18 @@ __device__ __forceinline__ void lsc_segment(const F3* own, const F3* obs, double
     for (int i = 0; i < 6; i++) out.d[i] = 0.5 * (collision_dist + f3_dot(rel_f[i], nrm));
     nrm.z = (float)__ddiv_rn((double)nrm.z, downwash);
     out.normal = nrm;
+}
+
+__device__ __forceinline__ void lsc_segment(const F3* own, const F3* obs, double downwash, double collision_dist,
+                                            LscSegment& out) {
+    F3 a[6], o[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        a[i] = own[i]; o[i] = obs[i];
+        a[i].z = downwash_scaled_z(a[i].z, downwash);
+        o[i].z = downwash_scaled_z(o[i].z, downwash);
+    }
+    lsc_segment_scaled(a, o, downwash, collision_dist, out);
 }
 
 }  // namespace lscgpu

@@ -17,6 +17,7 @@ struct PredictLaunch {
     const AgentConstDev* consts;   // [N]
     float* pred;                   // [N][90]    initial_traj, AoS
     float* predT;                  // [90][n_pad] same, element-major (coalesced reads by the LSC kernel)
+    float* predZs;                 // [30][n_pad] z of every control point divided by the agent's own downwash ratio
     double* state9;                // [N][9]
     double* goal3;                 // [N][3]
     int* ts;                       // [N]
@@ -31,6 +32,7 @@ struct LscLaunch {
     int n_agents, n_pad, a0, n_local;
     const float* pred;             // [N][90]
     const float* predT;            // [90][n_pad]
+    const float* predZs;           // [30][n_pad]
     const AgentConstDev* consts;
     const QpTablesDev* T;
     const double* state9;          // [N][9]

@@ -29,6 +29,13 @@ __global__ void __launch_bounds__(96) k_predict(PredictLaunch L) {
         }
         L.pred[(size_t)a * kTrajFloats + e] = val;
         L.predT[(size_t)e * L.n_pad + a] = val;
+        if (axis == 2) {
+            // z pre-scaled by the downwash ratio of a pair of agents with this agent's coefficient (the common case:
+            // homogeneous swarm); k_lsc_build uses it whenever the pair's ratio is bitwise the same
+            const AgentConstDev& c = L.consts[a];
+            const double dw_self = (c.downwash * c.radius + c.downwash * c.radius) / (c.radius + c.radius);
+            L.predZs[(size_t)cp * L.n_pad + a] = downwash_scaled_z(val, dw_self);
+        }
         if (e < 9) {
             const float s = e < 3 ? in.position[e] : (e < 6 ? in.velocity[e - 3] : in.acceleration[e - 6]);
             L.state9[(size_t)a * 9 + e] = (double)s;
@@ -110,6 +117,7 @@ constexpr int kLscThreads = 128;
 
 __global__ void __launch_bounds__(kLscThreads) k_lsc_build(LscLaunch L) {
     __shared__ float own[kTrajFloats];
+    __shared__ float own_zs[30];
     __shared__ double x0[kNv];
     __shared__ double inv_gn[kAx];
     __shared__ float4 own_sphere[kM];
@@ -123,6 +131,7 @@ __global__ void __launch_bounds__(kLscThreads) k_lsc_build(LscLaunch L) {
     const int ts = L.ts[a];
     const int tid = threadIdx.x;
     for (int e = tid; e < kTrajFloats; e += kLscThreads) own[e] = L.pred[(size_t)a * kTrajFloats + e];
+    if (tid < 30) own_zs[tid] = L.predZs[(size_t)tid * L.n_pad + a];
     for (int e = tid; e < kNv; e += kLscThreads) {
         const int k = e / kAx, i = e % kAx;
         const double* s = L.state9 + (size_t)a * 9;
@@ -137,6 +146,7 @@ __global__ void __launch_bounds__(kLscThreads) k_lsc_build(LscLaunch L) {
     __syncthreads();
 
     const AgentConstDev ca = L.consts[a];
+    const double dw_self_a = (ca.downwash * ca.radius + ca.downwash * ca.radius) / (ca.radius + ca.radius);
     RowRec* rows_out = L.rows + (size_t)al * L.P_pad;
     int* kept_out = L.kept + (size_t)al * L.P_pad;
     double* safe_out = L.safe + (size_t)al * L.P_pad;
@@ -203,16 +213,21 @@ __global__ void __launch_bounds__(kLscThreads) k_lsc_build(LscLaunch L) {
                 const int j = jj2 < a ? jj2 : jj2 + 1;
                 const AgentConstDev cj = L.consts[j];
                 const double downwash = (ca.downwash * ca.radius + cj.downwash * cj.radius) / (ca.radius + cj.radius);
+                // pre-scaled z is valid when the pair's ratio equals both agents' own ratio bit for bit
+                const bool pre = downwash == dw_self_a &&
+                                 downwash == (cj.downwash * cj.radius + cj.downwash * cj.radius) / (cj.radius + cj.radius);
                 F3 ow[6], ob[6];
+                float obz[6];
 #pragma unroll
                 for (int i = 0; i < 6; i++) {
-                    const int e = (m * 6 + i) * 3;
-                    ow[i] = F3{own[e], own[e + 1], own[e + 2]};
+                    const int cp = m * 6 + i, e = cp * 3;
+                    obz[i] = L.predT[(size_t)(e + 2) * L.n_pad + j];
+                    ow[i] = F3{own[e], own[e + 1], pre ? own_zs[cp] : downwash_scaled_z(own[e + 2], downwash)};
                     ob[i] = F3{L.predT[(size_t)e * L.n_pad + j], L.predT[(size_t)(e + 1) * L.n_pad + j],
-                               L.predT[(size_t)(e + 2) * L.n_pad + j]};
+                               pre ? L.predZs[(size_t)cp * L.n_pad + j] : downwash_scaled_z(obz[i], downwash)};
                 }
                 LscSegment seg;
-                lsc_segment(ow, ob, downwash, cj.radius + ca.radius, seg);
+                lsc_segment_scaled(ow, ob, downwash, cj.radius + ca.radius, seg);
                 gjk_it += seg.iterations;
                 const double ax = (double)seg.normal.x, ay = (double)seg.normal.y, az = (double)seg.normal.z;
                 const double an = sqrt(ax * ax + ay * ay + az * az);
@@ -224,7 +239,7 @@ __global__ void __launch_bounds__(kLscThreads) k_lsc_build(LscLaunch L) {
                 for (int i = 0; i < 6; i++) {
                     // row  a . c_{m,i} >= d_i + a . o_{m,i}      (src/traj_optimizer.cpp:437-466)
                     const double rhs = seg.d[i] + (__dmul_rn(ax, (double)ob[i].x) + __dmul_rn(ay, (double)ob[i].y) +
-                                                   __dmul_rn(az, (double)ob[i].z));
+                                                   __dmul_rn(az, (double)obz[i]));
                     rec.rhs[i] = rhs;
                     if (m == 0 && i < kPhi) continue;
                     const int vi = m * 6 + i;
