@@ -326,7 +326,15 @@ def run_ours(args):
                          f"from the engine's state after the timed region, {reps}x, {threads} threads, {el:.1f} s",
                "per_replan": {"gjk_iterations": c["gjk_iters"] / s_total, "qp_iterations": c["qp_iters"] / s_total,
                               "edt_lookups": l_sfc, "qp_rows": c["qp_rows"] / s_total}}
-    b_alg = alg_bytes_per_replan(n, l_sfc) * n_local
+    # Algorithmic bytes split by the kernel that consumes / produces each term:
+    #   k_lsc_build : neighbours' previous trajectories + radius/downwash, own trajectory, the kept rows it writes
+    #   k_sfc_expand: the reference's EDT lookups (4 B each, oracle count), SFC window in/out, goal
+    #   k_qp_solve  : the kept rows (64 B record + 8 B gate + 4 B pair index), state, goal, SFC window, result record
+    kept_per_replan = st["lsc_pairs_kept"] / max(st["steps"] * n_local, 1)
+    kernel_bytes = {"k_lsc_build": (n - 1) * 368 + 360 + 76.0 * kept_per_replan,
+                    "k_sfc_expand": 4.0 * l_sfc + 48 + 12 + 36,
+                    "k_qp_solve": 76.0 * kept_per_replan + 36 + 12 + 48 + 360 + 16}
+    b_alg = kernel_bytes[dom] * n_local
     achieved = b_alg / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -335,8 +343,19 @@ def run_ours(args):
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": f"MEASURED_PEAKS.json ({pk_kind})",
                 "ms_per_launch": dom_ms, "algorithmic_bytes_per_launch": b_alg,
-                "note": "latency/FP64-issue bound path (SURVEY.md §8d): unique bytes are L2-resident, so the HBM fraction is "
-                        "low by construction; see DESIGN.md §5"}
+                "kept_pairs_per_replan": kept_per_replan,
+                "note": "latency bound, not bandwidth bound (SURVEY.md §8d): the kernel's data is L2-resident and its time "
+                        "is the slowest agent's chain of dependent FP64 steps; the fraction is low by construction; "
+                        "see DESIGN.md §5 and fma_roofline"}
+    # whole path, SURVEY.md §8(d) B_alg per agent-replan (every neighbour read and every EDT lookup of the reference's
+    # algorithm counted as if from HBM) over the whole step's device time
+    b_path = alg_bytes_per_replan(n, l_sfc) * n_local
+    step_ms = ms_total / args.steps
+    path_roofline = {"algorithmic_bytes_per_step": b_path, "ms_per_step": step_ms,
+                     "achieved": b_path / (step_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                     "frac": b_path / (step_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+                     "note": "upper bound on necessary traffic: counts the reference's brute-force EDT sampling "
+                             "(4 B x L_sfc) that k_sfc_expand replaces by summed-volume-table reads"}
     fma = None
     fp = fma_peaks()
     if cpu is not None and fp is not None:
@@ -362,7 +381,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": n * A.AGENT_OUT.itemsize},
             "gpu_launches": int(launches.item()),
             "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]},
-            "roofline": roofline,
+            "roofline": roofline, "path_roofline": path_roofline,
             "fma_roofline": fma,
             "cpu_baseline": cpu,
             "kernel_ms_per_step": {k: v / max(st["steps"], 1) for k, v in per_kernel.items()},
