@@ -217,7 +217,9 @@ def run_ours(args):
     stream = torch.cuda.ExternalStream(eng.stream, device=local)
 
     row_store_bytes = n_local * 5 * (n - 1) * 64
-    flush = row_store_bytes < 2 * L2_BYTES
+    # every step is timed on its own (begin/end events on the engine stream) with a 256 MB write flushing the 126 MB
+    # L2 in between: the data one step touches (kept rows, distance field tables) is smaller than L2
+    flush = True
     flush_buf = torch.empty(256 * 2 ** 20, dtype=torch.uint8, device=f"cuda:{local}") if flush else None
 
     def barrier():
@@ -233,9 +235,23 @@ def run_ours(args):
                     flush_buf.zero_()
             eng.replan_resident(1, sync=False)
 
-    # ---- device-resident throughput (`value`) -----------------------------------------------------------------
+    # ---- per-kernel breakdown: the same W + K closed-loop steps with the kernels serialised and CUDA events between
+    # them (profiling mode); the timed pass below overlaps kernels of different agent groups, where per-kernel
+    # durations are not separable
     eng.set_states(scn.start); eng.set_goals(scn.goal)
     eng.set_profiling(True)
+    resident_steps(args.warmup)
+    eng.synchronize()
+    resident_steps(args.steps)
+    eng.synchronize()
+    st = eng.step_stats()
+    kernel_ms = st["ms_predict"] + st["ms_sfc"] + st["ms_lsc"] + st["ms_qp"] + st["ms_exchange"] + st["ms_commit"]
+    ms_serial = st["ms_total"]
+
+    # ---- device-resident throughput (`value`) -----------------------------------------------------------------
+    eng.reset()
+    eng.set_states(scn.start); eng.set_goals(scn.goal)
+    eng.set_profiling(False)
     resident_steps(args.warmup)
     eng.synchronize()
     barrier()
@@ -246,12 +262,11 @@ def run_ours(args):
     ev1.record(stream)
     eng.synchronize()
     barrier()
-    st = eng.step_stats()
-    kernel_ms = st["ms_predict"] + st["ms_sfc"] + st["ms_lsc"] + st["ms_qp"] + st["ms_exchange"] + st["ms_commit"]
+    st_timed = eng.step_stats()
     # with an L2 flush between steps only the steps themselves count; otherwise the whole bracket
-    ms_region = kernel_ms if flush else ev0.elapsed_time(ev1)
+    ms_region = st_timed["ms_steps"] if flush else ev0.elapsed_time(ev1)
     t = torch.tensor([ms_region], dtype=torch.float64, device=f"cuda:{local}")
-    launches = torch.tensor([st["kernel_launches"]], dtype=torch.int64, device=f"cuda:{local}")
+    launches = torch.tensor([st_timed["kernel_launches"]], dtype=torch.int64, device=f"cuda:{local}")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(launches, op=dist.ReduceOp.SUM)
     ms_total = float(t.item())
@@ -373,9 +388,8 @@ def run_ours(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{args.workload}_{n}", "agents": n, "agents_per_gpu": n_local,
                        "octomap": bool(scn.use_octomap), "parallelism": f"agents block-partitioned x{world}",
-                       "l2": ("L2 flushed (256 MB write) between steps; steps timed individually" if flush else
-                              f"no flush: every step rewrites and re-reads a {row_store_bytes / 2**20:.0f} MB row store (> L2) "
-                              "and its inputs change every step (closed loop)"),
+                       "l2": "L2 flushed (256 MB write) between steps; every step timed on its own with CUDA events on the "
+                             "engine stream; e2e is not flushed (its inputs arrive from host memory every step)",
                        "goals": "fixed to the mission goals (goal planning is outside the path, SURVEY.md §8f)"},
             "e2e": {"value": e2e_value, "unit": "agent-replans/s", "h2d_bytes_per_step": n * A.AGENT_IN.itemsize,
                     "d2h_bytes_per_step": n * A.AGENT_OUT.itemsize},

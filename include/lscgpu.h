@@ -100,6 +100,8 @@ typedef struct lscgpu_agent_out {
     int32_t terminal_segments;  /* getTerminalSegments (src/traj_optimizer.cpp:541-548) */
     int32_t qp_sweeps;          /* verification sweeps over all kept LSC pairs */
     int32_t qp_kcycles;         /* SM clock cycles / 1024 this agent's QP took (its traj_optimization_time) */
+    int32_t qp_price_kcycles;   /* ... of which: pricing the rows (the rest is the factorisation update) */
+    int32_t lsc_pairs_kept;     /* (neighbour, segment) pairs that survived the exact culling test */
 } lscgpu_agent_out;
 
 typedef struct lscgpu_engine lscgpu_engine;
@@ -202,6 +204,9 @@ typedef struct lscgpu_step_stats {
     int64_t qp_rows_priced;         /* inequality rows evaluated by the QP kernel (all local agents) */
     int64_t qp_iterations;          /* active-set iterations (all local agents) */
     int64_t qp_full_passes;         /* verification sweeps over the complete LSC row set (all local agents) */
+    float ms_steps;                 /* sum over the steps of (last kernel end - first kernel start): like ms_total without
+                                       whatever the caller enqueued on the stream between steps */
+    float reserved_;
 } lscgpu_step_stats;
 int lscgpu_get_step_stats(lscgpu_engine* e, lscgpu_step_stats* out);
 /* enable per-kernel event timing (event records between the kernels of every step; off by default) */

@@ -33,7 +33,8 @@ class StepStats(C.Structure):
     _fields_ = [("steps", C.c_int32), ("ms_total", C.c_float), ("ms_predict", C.c_float), ("ms_lsc", C.c_float),
                 ("ms_sfc", C.c_float), ("ms_qp", C.c_float), ("ms_exchange", C.c_float), ("ms_commit", C.c_float),
                 ("kernel_launches", C.c_int32), ("lsc_pairs", C.c_int64), ("lsc_pairs_kept", C.c_int64), ("gjk_iterations", C.c_int64),
-                ("qp_rows_priced", C.c_int64), ("qp_iterations", C.c_int64), ("qp_full_passes", C.c_int64)]
+                ("qp_rows_priced", C.c_int64), ("qp_iterations", C.c_int64), ("qp_full_passes", C.c_int64),
+                ("ms_steps", C.c_float), ("reserved_", C.c_float)]
 
 
 # numpy views of lscgpu_agent_in / lscgpu_agent_out (C layout, natural alignment)
@@ -43,8 +44,9 @@ AGENT_OUT = np.dtype([("traj", np.float32, (5, 6, 3)), ("next_position", np.floa
                       ("next_velocity", np.float32, 3), ("next_acceleration", np.float32, 3),
                       ("qp_cost", np.float64), ("report", np.int32), ("qp_status", np.int32),
                       ("qp_iterations", np.int32), ("qp_active", np.int32), ("flags", np.int32),
-                      ("terminal_segments", np.int32), ("qp_sweeps", np.int32), ("qp_kcycles", np.int32)], align=True)
-assert AGENT_IN.itemsize == 48 and AGENT_OUT.itemsize == 440, (AGENT_IN.itemsize, AGENT_OUT.itemsize)
+                      ("terminal_segments", np.int32), ("qp_sweeps", np.int32), ("qp_kcycles", np.int32),
+                      ("qp_price_kcycles", np.int32), ("lsc_pairs_kept", np.int32)], align=True)
+assert AGENT_IN.itemsize == 48 and AGENT_OUT.itemsize == 448, (AGENT_IN.itemsize, AGENT_OUT.itemsize)
 
 _lib = None
 ptr = C.c_void_p

@@ -62,6 +62,15 @@ struct lscgpu_engine {
     int a0 = 0, a1 = 0;              // local shard
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream_sfc = nullptr;     // k_sfc_expand runs beside k_lsc_build (independent until k_qp_solve)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool overlap_sfc = true, lpt_order = true;
+    static constexpr int kMaxGroups = 8;
+    int pipeline_groups = 2;
+    cudaStream_t stream_grp[kMaxGroups] = {};
+    cudaEvent_t ev_lsc[kMaxGroups] = {}, ev_qp[kMaxGroups] = {};
+    long long* d_dbg = nullptr;
+    int* d_order = nullptr;          // [n_local] local agents, most expensive QP of the previous step first
     int planner_seq = 0;
     bool profiling = false;
     int max_iter = 2000;
@@ -94,16 +103,18 @@ struct lscgpu_engine {
     NcclComm comm = nullptr;
     int rank = 0, n_ranks = 1, block = 0;
     // instrumentation: steps enqueued since the last synchronize
-    struct StepEvents { cudaEvent_t ev[7]; };
+    struct StepEvents { cudaEvent_t ev[9]; };   // begin, predict|, sfc[ (side stream) ]sfc, lsc|, qp[ ]qp, exchange|, commit|
     std::vector<StepEvents> ev_pool;    // per-kernel events of every pending step (profiling mode)
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> step_ev;   // begin / end of every pending step
     int pending = 0, pending_launches = 0;
     lscgpu_step_stats stats{};
 };
 
 static void free_rows(lscgpu_engine* e) {
     cudaFree(e->d_rows); cudaFree(e->d_safe);
-    cudaFree(e->d_kept); cudaFree(e->d_kept_count);
+    cudaFree(e->d_kept); cudaFree(e->d_kept_count); cudaFree(e->d_order);
+    e->d_order = nullptr;
     e->d_rows = nullptr; e->d_safe = nullptr;
     e->d_kept = nullptr; e->d_kept_count = nullptr;
     e->n_rows_alloc = 0;
@@ -119,6 +130,7 @@ static int alloc_rows(lscgpu_engine* e) {
     CU(cudaMalloc(&e->d_safe, sizeof(double) * (size_t)n_local * e->P_pad));
     CU(cudaMalloc(&e->d_kept, sizeof(int) * (size_t)n_local * e->P_pad));
     CU(cudaMalloc(&e->d_kept_count, sizeof(int) * (size_t)n_local));
+    CU(cudaMalloc(&e->d_order, sizeof(int) * (size_t)n_local));
     e->n_rows_alloc = n_local;
     return LSCGPU_OK;
 }
@@ -136,8 +148,17 @@ extern "C" void lscgpu_destroy(lscgpu_engine* e) {
     cudaFree(e->d_last_cost); cudaFree(e->d_ts); cudaFree(e->d_flags); cudaFree(e->d_init_sfc); cudaFree(e->d_counters);
     cudaFree(e->dm.sqdist); cudaFree(e->dm.sat); cudaFree(e->d_sphere); cudaFree(e->d_reach);
     for (auto& se : e->ev_pool) for (auto& ev : se.ev) if (ev) cudaEventDestroy(ev);
+    for (auto& pr : e->step_ev) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     if (e->ev_begin) cudaEventDestroy(e->ev_begin);
     if (e->ev_end) cudaEventDestroy(e->ev_end);
+    for (int g = 0; g < lscgpu_engine::kMaxGroups; g++) {
+        if (e->ev_lsc[g]) cudaEventDestroy(e->ev_lsc[g]);
+        if (e->ev_qp[g]) cudaEventDestroy(e->ev_qp[g]);
+        if (e->stream_grp[g]) cudaStreamDestroy(e->stream_grp[g]);
+    }
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    if (e->ev_join) cudaEventDestroy(e->ev_join);
+    if (e->stream_sfc) cudaStreamDestroy(e->stream_sfc);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -190,6 +211,17 @@ extern "C" int lscgpu_create(const lscgpu_params* p, int n_agents, const lscgpu_
         }                                                                                                 \
     } while (0)
     CUB(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CUB(cudaStreamCreateWithFlags(&e->stream_sfc, cudaStreamNonBlocking));
+    CUB(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+    CUB(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+    if (const char* v = getenv("LSCGPU_OVERLAP_SFC")) e->overlap_sfc = atoi(v) != 0;
+    if (const char* v = getenv("LSCGPU_LPT_ORDER")) e->lpt_order = atoi(v) != 0;
+    if (const char* v = getenv("LSCGPU_PIPELINE_GROUPS")) e->pipeline_groups = std::min(std::max(atoi(v), 1), (int)lscgpu_engine::kMaxGroups);
+    for (int g = 0; g < lscgpu_engine::kMaxGroups; g++) {
+        CUB(cudaStreamCreateWithFlags(&e->stream_grp[g], cudaStreamNonBlocking));
+        CUB(cudaEventCreateWithFlags(&e->ev_lsc[g], cudaEventDisableTiming));
+        CUB(cudaEventCreateWithFlags(&e->ev_qp[g], cudaEventDisableTiming));
+    }
     CUB(cudaEventCreate(&e->ev_begin));
     CUB(cudaEventCreate(&e->ev_end));
 
@@ -399,7 +431,13 @@ static int step_device(lscgpu_engine* e) {
         ev = e->ev_pool[e->pending].ev;
     }
     if (n_local > 0) CU(cudaMemsetAsync(e->d_kept_count, 0, sizeof(int) * n_local, s));
+    if ((int)e->step_ev.size() <= e->pending) {
+        std::pair<cudaEvent_t, cudaEvent_t> pr;
+        CU(cudaEventCreate(&pr.first)); CU(cudaEventCreate(&pr.second));
+        e->step_ev.push_back(pr);
+    }
     if (e->pending == 0) CU(cudaEventRecord(e->ev_begin, s));
+    CU(cudaEventRecord(e->step_ev[e->pending].first, s));
     if (prof) CU(cudaEventRecord(ev[0], s));
 
     PredictLaunch pl{};
@@ -409,46 +447,84 @@ static int step_device(lscgpu_engine* e) {
     pl.pred = e->d_pred; pl.predT = e->d_predT; pl.predZs = e->d_predZs; pl.state9 = e->d_state9; pl.goal3 = e->d_goal3;
     pl.ts = e->d_ts; pl.flags = e->d_flags; pl.sphere = e->d_sphere; pl.reach = e->d_reach;
     launch_predict(pl, s); launches++;
+    // scheduling order of this step's QP blocks from the cost of the previous step's solves (still in d_out)
+    const bool ordered = e->lpt_order && e->planner_seq > 1 && n_local > 1;
+    if (ordered) { launch_qp_order(n_local, e->a0, e->d_out, e->d_order, s); launches++; }
     if (prof) CU(cudaEventRecord(ev[1], s));
 
-    if (e->prm.world_use_octomap && n_local > 0) {
+    // k_sfc_expand depends on k_predict (flags) only and k_qp_solve is its only consumer: it runs on a side stream
+    // beside k_lsc_build
+    const bool do_sfc = e->prm.world_use_octomap && n_local > 0;
+    cudaStream_t ss = e->overlap_sfc ? e->stream_sfc : s;
+    if (do_sfc) {
+        if (e->overlap_sfc) { CU(cudaEventRecord(e->ev_fork, s)); CU(cudaStreamWaitEvent(ss, e->ev_fork, 0)); }
+        if (prof) CU(cudaEventRecord(ev[2], ss));
         SfcLaunch sl{};
         sl.n = n_local; sl.dm = e->dm; sl.res = e->prm.world_resolution;
         for (int k = 0; k < 3; k++) { sl.wmin[k] = e->prm.world_min[k]; sl.wmax[k] = e->prm.world_max[k]; }
         sl.mode = 0; sl.agent_base = e->a0;
         sl.in = e->d_in; sl.prev_traj = e->d_traj; sl.consts = e->d_consts;
         sl.boxes = e->d_boxes; sl.init_sfc = e->d_init_sfc; sl.flags = e->d_flags;
-        launch_sfc_expand(sl, s); launches++;
+        launch_sfc_expand(sl, ss); launches++;
+        if (prof) CU(cudaEventRecord(ev[3], ss));
+        if (e->overlap_sfc) CU(cudaEventRecord(e->ev_join, ss));
+    } else if (prof) {
+        CU(cudaEventRecord(ev[2], s)); CU(cudaEventRecord(ev[3], s));
     }
-    if (prof) CU(cudaEventRecord(ev[2], s));
 
-    if (n_local > 0 && e->N > 1) {
-        LscLaunch ll{};
-        ll.n_agents = e->N; ll.n_pad = e->n_pad; ll.a0 = e->a0; ll.n_local = n_local;
-        ll.pred = e->d_pred; ll.predT = e->d_predT; ll.predZs = e->d_predZs; ll.consts = e->d_consts; ll.T = e->d_tables;
-        ll.state9 = e->d_state9; ll.goal3 = e->d_goal3; ll.ts = e->d_ts;
-        ll.sphere = e->d_sphere; ll.reach = e->d_reach;
-        ll.rows = e->d_rows; ll.P_pad = e->P_pad;
-        ll.kept = e->d_kept; ll.kept_count = e->d_kept_count; ll.safe = e->d_safe;
-        ll.counters = e->d_counters;
-        launch_lsc_build(ll, s); launches++;
+    // LSC + QP, pipelined over groups of agents in scheduling order: k_lsc_build of group g+1 runs beside k_qp_solve of
+    // group g (own stream per group), so the long solves of the few crowded agents (first in the LPT order) overlap
+    // with the corridor construction of everybody else. Profiling mode serialises everything (one group, per-kernel
+    // events); results do not depend on the grouping.
+    int groups = 1;
+    if (!prof && ordered && e->pipeline_groups > 1 && n_local >= 128 * e->pipeline_groups) groups = e->pipeline_groups;
+    LscLaunch ll{};
+    ll.n_agents = e->N; ll.n_pad = e->n_pad; ll.a0 = e->a0; ll.n_local = n_local;
+    ll.order = ordered ? e->d_order : nullptr;
+    ll.pred = e->d_pred; ll.predT = e->d_predT; ll.predZs = e->d_predZs; ll.consts = e->d_consts; ll.T = e->d_tables;
+    ll.state9 = e->d_state9; ll.goal3 = e->d_goal3; ll.ts = e->d_ts;
+    ll.sphere = e->d_sphere; ll.reach = e->d_reach;
+    ll.rows = e->d_rows; ll.P_pad = e->P_pad;
+    ll.kept = e->d_kept; ll.kept_count = e->d_kept_count; ll.safe = e->d_safe;
+    ll.counters = e->d_counters;
+    QpLaunch ql{};
+    ql.T = e->d_tables; ql.consts = e->d_consts;
+    ql.order = ordered ? e->d_order : nullptr;
+    ql.agent_index = nullptr; ql.agent_base = e->a0;
+    ql.state9 = e->d_state9; ql.goal3 = e->d_goal3; ql.ts = e->d_ts;
+    ql.boxes = e->prm.world_use_octomap ? e->d_boxes : nullptr;
+    for (int k = 0; k < 3; k++) { ql.wmin[k] = e->prm.world_min[k]; ql.wmax[k] = e->prm.world_max[k]; }
+    ql.rows = e->d_rows; ql.obs_offset = nullptr; ql.n_obs = e->N - 1; ql.P_pad = e->P_pad;
+    ql.kept = e->d_kept; ql.kept_count = e->d_kept_count; ql.safe = e->d_safe; ql.max_iter = e->max_iter;
+    ql.out = e->d_out; ql.prev_traj = e->d_traj; ql.last_cost = e->d_last_cost; ql.flags = e->d_flags;
+    ql.counters = e->d_counters;
+    if (getenv("LSCGPU_QP_DEBUG")) { if (!e->d_dbg) CU(cudaMalloc(&e->d_dbg, sizeof(long long) * 8 * (size_t)e->N)); ql.dbg = e->d_dbg; }
+    if (groups == 1) {
+        if (n_local > 0 && e->N > 1) { ll.first = 0; ll.count = n_local; launch_lsc_build(ll, s); launches++; }
+        if (prof) CU(cudaEventRecord(ev[4], s));
+        if (do_sfc && e->overlap_sfc) CU(cudaStreamWaitEvent(s, e->ev_join, 0));
+        if (prof) CU(cudaEventRecord(ev[5], s));
+        if (n_local > 0) { ql.first = 0; ql.n_problems = n_local; launch_qp_solve(ql, s); launches++; }
+    } else {
+        // group sizes: the first (most expensive) groups are the smallest, so their solves start early
+        int first = 0;
+        CU(cudaEventRecord(e->ev_lsc[0], s));           // predictions (and the order) are ready
+        for (int g = 0; g < groups; g++) {
+            const int rest = n_local - first;
+            const int count = g == groups - 1 ? rest : std::max(64, (int)(n_local * (g + 1.0) / (groups * (groups + 1) / 2.0)));
+            const int cnt = std::min(count, rest);
+            if (cnt <= 0) { CU(cudaEventRecord(e->ev_qp[g], s)); continue; }
+            cudaStream_t sg = e->stream_grp[g];
+            CU(cudaStreamWaitEvent(sg, e->ev_lsc[0], 0));
+            ll.first = first; ll.count = cnt; launch_lsc_build(ll, sg); launches++;
+            if (do_sfc && e->overlap_sfc) CU(cudaStreamWaitEvent(sg, e->ev_join, 0));
+            ql.first = first; ql.n_problems = cnt; launch_qp_solve(ql, sg); launches++;
+            CU(cudaEventRecord(e->ev_qp[g], sg));
+            first += cnt;
+        }
+        for (int g = 0; g < groups; g++) CU(cudaStreamWaitEvent(s, e->ev_qp[g], 0));
     }
-    if (prof) CU(cudaEventRecord(ev[3], s));
-
-    if (n_local > 0) {
-        QpLaunch ql{};
-        ql.n_problems = n_local; ql.T = e->d_tables; ql.consts = e->d_consts;
-        ql.agent_index = nullptr; ql.agent_base = e->a0;
-        ql.state9 = e->d_state9; ql.goal3 = e->d_goal3; ql.ts = e->d_ts;
-        ql.boxes = e->prm.world_use_octomap ? e->d_boxes : nullptr;
-        for (int k = 0; k < 3; k++) { ql.wmin[k] = e->prm.world_min[k]; ql.wmax[k] = e->prm.world_max[k]; }
-        ql.rows = e->d_rows; ql.obs_offset = nullptr; ql.n_obs = e->N - 1; ql.P_pad = e->P_pad;
-        ql.kept = e->d_kept; ql.kept_count = e->d_kept_count; ql.safe = e->d_safe; ql.max_iter = e->max_iter;
-        ql.out = e->d_out; ql.prev_traj = e->d_traj; ql.last_cost = e->d_last_cost; ql.flags = e->d_flags;
-        ql.counters = e->d_counters;
-        launch_qp_solve(ql, s); launches++;
-    }
-    if (prof) CU(cudaEventRecord(ev[4], s));
+    if (prof) CU(cudaEventRecord(ev[6], s));
 
     if (e->comm && e->n_ranks > 1) {
         // in-place all-gather: every rank's block of results lands in every replica
@@ -456,9 +532,10 @@ static int step_device(lscgpu_engine* e) {
         const int rc = g_nccl.AllGather((const char*)e->d_out + bytes * e->rank, e->d_out, bytes, /*ncclInt8*/ 0, e->comm, s);
         if (rc != 0) return fail(LSCGPU_ERR_NCCL, std::string("ncclAllGather: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
     }
-    if (prof) CU(cudaEventRecord(ev[5], s));
+    if (prof) CU(cudaEventRecord(ev[7], s));
     launch_commit(e->N, e->d_out, e->d_traj, e->d_in, s); launches++;
-    if (prof) CU(cudaEventRecord(ev[6], s));
+    if (prof) CU(cudaEventRecord(ev[8], s));
+    CU(cudaEventRecord(e->step_ev[e->pending].second, s));
     CU(cudaEventRecord(e->ev_end, s));
     CU(cudaGetLastError());
     e->pending++;
@@ -477,14 +554,32 @@ static int finish_steps(lscgpu_engine* e) {
     CU(cudaStreamSynchronize(e->stream));
     st.steps = e->pending;
     CU(cudaEventElapsedTime(&st.ms_total, e->ev_begin, e->ev_end));
+    for (int i = 0; i < e->pending; i++) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, e->step_ev[i].first, e->step_ev[i].second));
+        st.ms_steps += ms;
+    }
     if (e->profiling) {
         for (int i = 0; i < e->pending && i < (int)e->ev_pool.size(); i++) {
             cudaEvent_t* ev = e->ev_pool[i].ev;
-            float ms[6];
-            for (int k = 0; k < 6; k++) CU(cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]));
-            st.ms_predict += ms[0]; st.ms_sfc += ms[1]; st.ms_lsc += ms[2]; st.ms_qp += ms[3];
-            st.ms_exchange += ms[4]; st.ms_commit += ms[5];
+            float ms[8];
+            for (int k = 0; k < 8; k++) CU(cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]));
+            // ev: begin, predict|, sfc[ ]sfc (side stream when overlapped), lsc|, join|, qp|, exchange|, commit|
+            st.ms_predict += ms[0]; st.ms_sfc += ms[2]; st.ms_qp += ms[5]; st.ms_exchange += ms[6]; st.ms_commit += ms[7];
+            float lsc = 0.f;
+            CU(cudaEventElapsedTime(&lsc, e->overlap_sfc ? ev[1] : ev[3], ev[4]));
+            st.ms_lsc += lsc;
         }
+    }
+    if (e->d_dbg && getenv("LSCGPU_QP_DEBUG")) {
+        const int nl = e->a1 - e->a0;
+        std::vector<long long> h((size_t)nl * 8);
+        CU(cudaMemcpy(h.data(), e->d_dbg, sizeof(long long) * 8 * nl, cudaMemcpyDeviceToHost));
+        int worst = 0; long long wt = -1; long long tot[8] = {0};
+        for (int i = 0; i < nl; i++) { long long t = 0; for (int k = 0; k < 8; k++) { t += h[(size_t)i * 8 + k]; tot[k] += h[(size_t)i * 8 + k]; } if (t > wt) { wt = t; worst = i; } }
+        fprintf(stderr, "[qp dbg] worst local agent %d kcycles: price %lld nv %lld gs %lld solve %lld xupd %lld add %lld drop %lld | mean: price %lld nv %lld gs %lld solve %lld xupd %lld add %lld drop %lld\n", worst,
+                h[(size_t)worst*8]>>10, h[(size_t)worst*8+1]>>10, h[(size_t)worst*8+2]>>10, h[(size_t)worst*8+3]>>10, h[(size_t)worst*8+4]>>10, h[(size_t)worst*8+5]>>10, h[(size_t)worst*8+6]>>10,
+                tot[0]/nl>>10, tot[1]/nl>>10, tot[2]/nl>>10, tot[3]/nl>>10, tot[4]/nl>>10, tot[5]/nl>>10, tot[6]/nl>>10);
     }
     st.kernel_launches = e->pending_launches;
     st.lsc_pairs = (int64_t)e->pending * (e->a1 - e->a0) * (e->N - 1) * kPairsPerObs;

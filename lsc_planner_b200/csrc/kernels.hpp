@@ -30,6 +30,8 @@ void launch_predict(const PredictLaunch& L, cudaStream_t s);
 // ---- k_lsc_build ------------------------------------------------------------------------------------------
 struct LscLaunch {
     int n_agents, n_pad, a0, n_local;
+    const int* order;              // null, or scheduling order of the local agents (see QpLaunch::order)
+    int first, count;              // this launch covers positions [first, first + count) of that order
     const float* pred;             // [N][90]
     const float* predT;            // [90][n_pad]
     const float* predZs;           // [30][n_pad]
@@ -66,6 +68,8 @@ struct QpLaunch {
     int n_problems;
     const QpTablesDev* T;
     const AgentConstDev* consts;
+    const int* order;              // null, or scheduling order: block i solves problem order[first + i]
+    int first;                     // ... else problem first + i; n_problems = blocks of this launch
     const int* agent_index;        // null: agent = agent_base + b
     int agent_base;
     const double* state9;          // indexed by agent when agent_index == null, else by problem
@@ -88,8 +92,10 @@ struct QpLaunch {
     double* last_cost;             // [N]
     const int* flags;              // [N]
     StepCounters* counters;
+    long long* dbg;                // null, or [n_problems][8] section cycle counts (LSCGPU_QP_DEBUG)
 };
 void launch_qp_solve(const QpLaunch& L, cudaStream_t s);
+void launch_qp_order(int n_local, int a0, const lscgpu_agent_out* out, int* order, cudaStream_t s);
 
 // commit: every agent's new trajectory becomes traj_curr, advanced state becomes the next resident input
 void launch_commit(int n_agents, const lscgpu_agent_out* out, float* prev_traj, lscgpu_agent_in* in, cudaStream_t s);

@@ -1,4 +1,6 @@
 // k_predict, k_lsc_build and the small glue kernels around them (sm_100a).
+#include <cstdlib>
+
 #include "gjk.cuh"
 #include "kernels.hpp"
 
@@ -115,7 +117,8 @@ void launch_predict(const PredictLaunch& L, cudaStream_t s) { k_predict<<<L.n_ag
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kLscThreads = 128;
 
-__global__ void __launch_bounds__(kLscThreads) k_lsc_build(LscLaunch L) {
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kLscThreads, kMinBlocks) k_lsc_build(LscLaunch L) {
     __shared__ float own[kTrajFloats];
     __shared__ float own_zs[30];
     __shared__ double x0[kNv];
@@ -125,7 +128,7 @@ __global__ void __launch_bounds__(kLscThreads) k_lsc_build(LscLaunch L) {
     __shared__ int queue[kLscThreads * (kM + 1)];
     __shared__ int q_count, kept_base;
     __shared__ int warp_cnt[kM][kLscThreads / 32];     // per-warp counts of the order-preserving compactions
-    const int al = blockIdx.x;
+    const int al = L.order ? L.order[L.first + blockIdx.x] : L.first + blockIdx.x;
     const int a = L.a0 + al;
     const int n_obs = L.n_agents - 1;
     const int ts = L.ts[a];
@@ -270,8 +273,11 @@ __global__ void __launch_bounds__(kLscThreads) k_lsc_build(LscLaunch L) {
 
 void launch_lsc_build(const LscLaunch& L, cudaStream_t s) {
     const int n_obs = L.n_agents - 1;
-    if (n_obs <= 0 || L.n_local <= 0) return;
-    k_lsc_build<<<L.n_local, kLscThreads, 0, s>>>(L);
+    if (n_obs <= 0 || L.count <= 0) return;
+    static const int occ = getenv("LSCGPU_LSC_OCC") ? atoi(getenv("LSCGPU_LSC_OCC")) : 2;
+    if (occ >= 4) k_lsc_build<4><<<L.count, kLscThreads, 0, s>>>(L);
+    else if (occ == 3) k_lsc_build<3><<<L.count, kLscThreads, 0, s>>>(L);
+    else k_lsc_build<2><<<L.count, kLscThreads, 0, s>>>(L);
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -59,9 +59,10 @@ struct QpShared {
     double inv_gn[kAx];
     double lb[15], ub[15], vmax[3], amax[3];
     double travelled;           // path length of the iterate in the whitened space
-    double best_mu[8];          // per-warp pricing result
-    int best_id[8];
+    double best_mu[16];          // per-warp pricing result
+    int best_id[16];
     int stop;                   // 0 run, 1 finished/failed (set by warp 0)
+    int open_count[2];          // pairs in the open list of the current / next chunk
     int act[NR];
     SelectedRow sel;
 };
@@ -201,12 +202,16 @@ struct FixedItems {
 };
 
 template <int kThreads>
-__global__ void __launch_bounds__(kThreads, 512 / kThreads) k_qp_solve(QpLaunch L) {
+__global__ void __launch_bounds__(kThreads, kThreads >= 512 ? 1 : 512 / kThreads) k_qp_solve(QpLaunch L) {
     constexpr int kWarps = kThreads / 32;
     constexpr int kItems = (225 + kThreads - 1) / kThreads;
+    constexpr int kGate = 8;                       // gate values per thread per chunk
     __shared__ QpShared S;
+    __shared__ int open_list[kGate * kThreads];
     const long long t_start = clock64();
-    const int b = blockIdx.x;
+    // scheduling order != data order: blocks are dispatched in blockIdx order, so the launcher may hand the agents
+    // with the most expensive solve of the previous step out first (longest-processing-time-first)
+    const int b = L.order ? L.order[L.first + blockIdx.x] : L.first + blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool batch = L.obs_offset != nullptr;
     const int agent = L.agent_index ? L.agent_index[b] : L.agent_base + b;
@@ -275,11 +280,22 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) k_qp_solve(QpLaunch 
     for (int h = 0; h < 3; h++) { const int e = min(lane + 32 * h, kNv - 1); x_axis[h] = e / kAx; x_var[h] = e % kAx; }
     int q = 0, iters = 0, status = LSCGPU_QP_OK;
     unsigned long long pairs_evaluated = 0, passes = 0;
+    long long price_cycles = 0;
+#ifdef LSCGPU_QP_SECTION_TIMERS      // build with -DLSCGPU_QP_SECTION_TIMERS and run with LSCGPU_QP_DEBUG=1: cycles per section
+    long long sec[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tk = 0;
+#define TICK() (tk = clock64())
+#define TOCK(i) do { const long long now_ = clock64(); sec[i] += now_ - tk; tk = now_; } while (0)
+#else
+#define TICK() ((void)0)
+#define TOCK(i) ((void)0)
+#endif
 
     while (true) {
         // ---- pricing by the whole block ---------------------------------------------------------------------------
         Best best{0.0, -1};
         const double travelled = S.travelled;
+        const long long t_price = clock64();
 #pragma unroll
         for (int t = 0; t < kItems; t++) {
             if (F.base[t] < 0) continue;
@@ -293,23 +309,48 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) k_qp_solve(QpLaunch 
                 consider(best, S, q, F.lo[t] + expr, F.inv[t], F.id[t] + 1);
             }
         }
-        for (int s0 = 0; s0 < n_kept; s0 += 4 * kThreads) {
-            double sv[4];
+        // LSC rows, chunk by chunk: (1) every thread reads kGate gate values (coalesced, all loads in flight at once),
+        // (2) the pairs whose gate is open are compacted into a shared-memory list, (3) the list is evaluated evenly
+        // spread over the block, the next record being loaded while the current one is evaluated.
+        if (tid == 0) S.open_count[0] = 0;
+        for (int s0 = 0, chunk = 0; s0 < n_kept; s0 += kGate * kThreads, chunk++) {
+            double sv[kGate];
 #pragma unroll
-            for (int h = 0; h < 4; h++) {               // four gate values per thread in flight
+            for (int h = 0; h < kGate; h++) {
                 const int si = s0 + kThreads * h + tid;
                 sv[h] = si < n_kept ? safe[si] : INFINITY;
             }
+            __syncthreads();        // list of the previous chunk consumed, counter of this one zeroed
+            int* cnt = &S.open_count[chunk & 1];
 #pragma unroll
-            for (int h = 0; h < 4; h++) {
-                if (sv[h] > travelled) continue;        // cannot be violated yet
-                const int si = s0 + kThreads * h + tid;
-                float4 nr; double r6[6];
-                load_pair(rows, si, nr, r6);
-                const double mu_min = price_pair_vals(best, S, q, si, kept[si] / n_obs, nr, r6);
+            for (int h = 0; h < kGate; h++) {
+                const bool open = !(sv[h] > travelled);         // may be violated by now
+                const unsigned mask = __ballot_sync(0xffffffffu, open);
+                if (mask == 0u) continue;
+                int base = 0;
+                if (lane == 0) base = atomicAdd(cnt, __popc(mask));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (open) open_list[base + __popc(mask & ((1u << lane) - 1u))] = s0 + kThreads * h + tid;
+            }
+            __syncthreads();
+            const int n_open = *cnt;
+            if (tid == 0) S.open_count[(chunk + 1) & 1] = 0;
+            int idx = tid, si = 0, kp = 0;
+            float4 nr; double r6[6];
+            if (idx < n_open) { si = open_list[idx]; load_pair(rows, si, nr, r6); kp = kept[si]; }
+            while (idx < n_open) {
+                const int nidx = idx + kThreads;
+                int si2 = 0, kp2 = 0;
+                float4 nr2 = nr; double r62[6];
+                if (nidx < n_open) { si2 = open_list[nidx]; load_pair(rows, si2, nr2, r62); kp2 = kept[si2]; }
+                const int m = (kp >= n_obs) + (kp >= 2 * n_obs) + (kp >= 3 * n_obs) + (kp >= 4 * n_obs);
+                const double mu_min = price_pair_vals(best, S, q, si, m, nr, r6);
                 // 1e-6 relative margin: the stored 1/|a| is float32, so mu carries ~6e-8 relative error
                 safe[si] = travelled + (mu_min > 0.0 ? mu_min * 0.999999 : mu_min);
                 pairs_evaluated++;
+                idx = nidx; si = si2; kp = kp2; nr = nr2;
+#pragma unroll
+                for (int i = 0; i < 6; i++) r6[i] = r62[i];
             }
         }
         passes++;
@@ -323,11 +364,13 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) k_qp_solve(QpLaunch 
             if (w == 0) { best.mu = mu; best.id = id; }
             else if (id >= 0 && (best.id < 0 || mu < best.mu || (mu == best.mu && id < best.id))) { best.mu = mu; best.id = id; }
         }
+        if (tid == 0) price_cycles += clock64() - t_price;
         if (best.id < 0) break;                 // no row violated beyond the tolerance anywhere: done (block-uniform)
 
         // ---- factorisation update by warp 0 -----------------------------------------------------------------------
         if (warp == 0) {
             bool done = false;          // set when the solve must stop (failure)
+            TICK();
             do {
                 {
                     bool dup = false;
@@ -357,6 +400,7 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) k_qp_solve(QpLaunch 
                 for (int c = lane; c < NR; c += 32) S.nv[c] *= inv_len;
                 __syncwarp();
                 double lam_p = 0.0;
+                TOCK(1);
                 while (true) {
                     if (++iters > L.max_iter) { status = LSCGPU_QP_MAXITER; done = true; break; }
                     // ---- z = (I - Q Q^T) nv by Gram-Schmidt (second pass when needed); d = Q^T nv --------------------
@@ -400,6 +444,7 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) k_qp_solve(QpLaunch 
                             if (!again) break;
                         }
                     }
+                    TOCK(2);
                     // rr = R^-1 d (change of the active multipliers per unit step): column-oriented back
                     // substitution, rr[k] lives in lane k's register while q <= 32
                     if (q <= 32) {
@@ -443,7 +488,8 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) k_qp_solve(QpLaunch 
                     if (!(t < INFINITY)) { status = LSCGPU_QP_INFEASIBLE; done = true; break; }
                     for (int k = lane; k < q; k += 32) S.lam[k] -= t * S.rr[k];
                     lam_p += t;
-                    if (!primal) { drop_active(S, q, l, lane); continue; }
+                    TOCK(3);
+                    if (!primal) { drop_active(S, q, l, lane); TOCK(6); continue; }
                     if (lane == 0) S.travelled += t * sqrt(zz) * (1.0 + 1e-9) + 1e-13;
 #pragma unroll
                     for (int h = 0; h < 3; h++) {
@@ -459,6 +505,7 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) k_qp_solve(QpLaunch 
                         }
                     }
                     __syncwarp();
+                    TOCK(4);
                     if (t2 <= t1) {
                         // the row becomes active: new basis column z / |z|, new column (d, |z|) of R
                         const double zn = sqrt(zz), izn = 1.0 / zn;
@@ -472,9 +519,11 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) k_qp_solve(QpLaunch 
                         }
                         q++;
                         __syncwarp();
+                        TOCK(5);
                         break;
                     }
                     drop_active(S, q, l, lane);
+                    TOCK(6);
                 }
             } while (false);
             if (done && lane == 0) S.stop = 1;
@@ -540,8 +589,48 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) k_qp_solve(QpLaunch 
             o.terminal_segments = ts;
             o.qp_sweeps = (int)passes;
             o.qp_kcycles = (int)((clock64() - t_start) >> 10);
+            o.qp_price_kcycles = (int)(price_cycles >> 10);
+            o.lsc_pairs_kept = n_kept;
+#ifdef LSCGPU_QP_SECTION_TIMERS
+            if (L.dbg) { for (int i = 1; i < 8; i++) L.dbg[(size_t)b * 8 + i] = sec[i]; L.dbg[(size_t)b * 8] = price_cycles; }
+#endif
         }
     }
+}
+
+// Longest-processing-time-first order of the local agents from the cycle count each solve recorded in its result
+// record at the previous step: counting sort on the (clamped) kilo-cycle count, descending. The order inside a bucket
+// is arbitrary; it only affects scheduling, never results.
+__global__ void __launch_bounds__(1024) k_qp_order(int n_local, int a0, const lscgpu_agent_out* out, int* order) {
+    __shared__ int hist[1024];
+    __shared__ int warp_tot[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    hist[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < n_local; i += 1024) atomicAdd(&hist[1023 - min(max(out[a0 + i].qp_kcycles, 0), 1023)], 1);
+    __syncthreads();
+    const int mine = hist[tid];
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int t = warp_tot[lane], inc2 = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc2, o); if (lane >= o) inc2 += u; }
+        warp_tot[lane] = inc2 - t;
+    }
+    __syncthreads();
+    hist[tid] = warp_tot[warp] + incl - mine;       // exclusive prefix
+    __syncthreads();
+    for (int i = tid; i < n_local; i += 1024) {
+        const int pos = atomicAdd(&hist[1023 - min(max(out[a0 + i].qp_kcycles, 0), 1023)], 1);
+        order[pos] = i;
+    }
+}
+void launch_qp_order(int n_local, int a0, const lscgpu_agent_out* out, int* order, cudaStream_t s) {
+    if (n_local > 0) k_qp_order<<<1, 1024, 0, s>>>(n_local, a0, out, order);
 }
 
 void launch_qp_solve(const QpLaunch& L, cudaStream_t s) {
@@ -553,8 +642,10 @@ void launch_qp_solve(const QpLaunch& L, cudaStream_t s) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     static const int forced = getenv("LSCGPU_QP_THREADS") ? atoi(getenv("LSCGPU_QP_THREADS")) : 0;
-    const int threads = forced ? forced : (L.n_problems <= 2 * sms ? 256 : 128);
-    if (threads == 256) k_qp_solve<256><<<L.n_problems, 256, 0, s>>>(L);
+    const int threads = forced ? forced : 256;
+    (void)sms;
+    if (threads >= 512) k_qp_solve<512><<<L.n_problems, 512, 0, s>>>(L);
+    else if (threads == 256) k_qp_solve<256><<<L.n_problems, 256, 0, s>>>(L);
     else if (threads == 128) k_qp_solve<128><<<L.n_problems, 128, 0, s>>>(L);
     else k_qp_solve<64><<<L.n_problems, 64, 0, s>>>(L);
 }

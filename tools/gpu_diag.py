@@ -24,7 +24,8 @@ for s in range(a.steps):
         o = e.fetch(); st = e.step_stats()
         it = o["qp_iterations"]; kc = o["qp_kcycles"].astype(float) * 1024 / 1.965e3   # us
         slow = np.argsort(-kc)[:3]
-        print("      slowest agents:", [(int(a), f"{kc[a]:.0f}us", int(it[a]), int(o["qp_sweeps"][a]), int(o["qp_status"][a]), int(o["qp_active"][a])) for a in slow],
+        pk = o["qp_price_kcycles"].astype(float) * 1024 / 1.965e3
+        print("      slowest agents (id, us, price us, iters, sweeps, status, active, kept):", [(int(a), f"{kc[a]:.0f}", f"{pk[a]:.0f}", int(it[a]), int(o["qp_sweeps"][a]), int(o["qp_status"][a]), int(o["qp_active"][a]), int(o["lsc_pairs_kept"][a])) for a in slow],
               f"| us p50 {np.percentile(kc,50):.0f} p90 {np.percentile(kc,90):.0f} p99 {np.percentile(kc,99):.0f}",
               "| sweeps p50 %.0f p99 %.0f max %.0f" % tuple(np.percentile(o["qp_sweeps"], [50, 99, 100])),
               f"| rows priced/iter {st['qp_rows_priced'] / max(st['qp_iterations'] + scn.n, 1):.0f}")
