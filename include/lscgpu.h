@@ -70,6 +70,15 @@ typedef struct lscgpu_params {
     float world_min[3];            /* Mission::world_min / world_max (src/mission.cpp:60-75) */
     float world_max[3];
     int M, n, phi, dim;            /* must be 5, 5, 3, 3 (traj/horizon 1.0, traj/n, traj/phi, world/dimension) */
+    /* Goal planning, the step before the path (src/traj_planner.cpp:477-608). 0 = GoalMode::STATIC: lscgpu_agent_in::goal
+     * is the current goal. 1 = GoalMode::PRIORBASED (the reference's default) on the GPU: lscgpu_agent_in::goal is the
+     * DESIRED goal and the engine derives the current goal (priority rule, retreat point, clip to goal_radius). Only
+     * without an octomap, where the reference's line-of-sight goal does not depend on its A* path; with an octomap the
+     * host planner (lsc_planner_b200/host/grid_based_planner.hpp) computes the goals and passes them with goal_mode 0. */
+    int goal_mode;
+    double goal_threshold;             /* plan/goal_threshold (0.1) */
+    double goal_radius;                /* plan/goal_radius (2.0) */
+    double priority_dist_threshold;    /* plan/priority_dist_threshold (0.4) */
 } lscgpu_params;
 
 /* Constant part of Agent (include/sp_const.hpp:153-165). */
@@ -102,6 +111,9 @@ typedef struct lscgpu_agent_out {
     int32_t qp_kcycles;         /* SM clock cycles / 1024 this agent's QP took (its traj_optimization_time) */
     int32_t qp_price_kcycles;   /* ... of which: pricing the rows (the rest is the factorisation update) */
     int32_t lsc_pairs_kept;     /* (neighbour, segment) pairs that survived the exact culling test */
+    float current_goal[3];      /* Agent::current_goal_position the QP used (getCurrentGoalPosition): the input goal, or the
+                                   goal chosen by goal planning when lscgpu_params::goal_mode == 1 */
+    int32_t goal_kind;          /* goal planning: 0 line-of-sight goal, 1 retreat from the closest higher-priority agent */
 } lscgpu_agent_out;
 
 typedef struct lscgpu_engine lscgpu_engine;

@@ -21,6 +21,8 @@ class Params(C.Structure):
         ("world_resolution", C.c_double), ("reset_threshold", C.c_double), ("world_use_octomap", C.c_int),
         ("world_min", C.c_float * 3), ("world_max", C.c_float * 3),
         ("M", C.c_int), ("n", C.c_int), ("phi", C.c_int), ("dim", C.c_int),
+        ("goal_mode", C.c_int), ("goal_threshold", C.c_double), ("goal_radius", C.c_double),
+        ("priority_dist_threshold", C.c_double),
     ]
 
 
@@ -45,8 +47,9 @@ AGENT_OUT = np.dtype([("traj", np.float32, (5, 6, 3)), ("next_position", np.floa
                       ("qp_cost", np.float64), ("report", np.int32), ("qp_status", np.int32),
                       ("qp_iterations", np.int32), ("qp_active", np.int32), ("flags", np.int32),
                       ("terminal_segments", np.int32), ("qp_sweeps", np.int32), ("qp_kcycles", np.int32),
-                      ("qp_price_kcycles", np.int32), ("lsc_pairs_kept", np.int32)], align=True)
-assert AGENT_IN.itemsize == 48 and AGENT_OUT.itemsize == 448, (AGENT_IN.itemsize, AGENT_OUT.itemsize)
+                      ("qp_price_kcycles", np.int32), ("lsc_pairs_kept", np.int32),
+                      ("current_goal", np.float32, 3), ("goal_kind", np.int32)], align=True)
+assert AGENT_IN.itemsize == 48 and AGENT_OUT.itemsize == 464, (AGENT_IN.itemsize, AGENT_OUT.itemsize)
 
 _lib = None
 ptr = C.c_void_p

@@ -14,6 +14,10 @@
 
 using namespace lscgpu;
 
+// the ctypes / numpy mirrors in lsc_planner_b200/_capi.py assume these layouts (tests/test_capi_load.py)
+static_assert(sizeof(lscgpu_params) == 112 && sizeof(lscgpu_agent_in) == 48 && sizeof(lscgpu_agent_out) == 464 &&
+              sizeof(lscgpu_agent_const) == 72, "C-ABI struct layout changed: update _capi.py and the tests");
+
 static thread_local std::string g_error;
 static int fail(int code, const std::string& msg) { g_error = msg; return code; }
 
@@ -86,7 +90,7 @@ struct lscgpu_engine {
     int n_out = 0;
     float *d_traj = nullptr, *d_pred = nullptr, *d_predT = nullptr, *d_predZs = nullptr, *d_boxes = nullptr;
     double *d_state9 = nullptr, *d_goal3 = nullptr, *d_last_cost = nullptr;
-    int *d_ts = nullptr, *d_flags = nullptr, *d_init_sfc = nullptr;
+    int *d_ts = nullptr, *d_flags = nullptr, *d_init_sfc = nullptr, *d_goal_kind = nullptr;
     // row store of the local shard
     RowRec* d_rows = nullptr;
     int P_pad = 0, n_rows_alloc = 0;
@@ -145,7 +149,7 @@ extern "C" void lscgpu_destroy(lscgpu_engine* e) {
     free_rows(e);
     cudaFree(e->d_tables); cudaFree(e->d_consts); cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_traj);
     cudaFree(e->d_pred); cudaFree(e->d_predT); cudaFree(e->d_predZs); cudaFree(e->d_boxes); cudaFree(e->d_state9); cudaFree(e->d_goal3);
-    cudaFree(e->d_last_cost); cudaFree(e->d_ts); cudaFree(e->d_flags); cudaFree(e->d_init_sfc); cudaFree(e->d_counters);
+    cudaFree(e->d_last_cost); cudaFree(e->d_ts); cudaFree(e->d_flags); cudaFree(e->d_init_sfc); cudaFree(e->d_goal_kind); cudaFree(e->d_counters);
     cudaFree(e->dm.sqdist); cudaFree(e->dm.sat); cudaFree(e->d_sphere); cudaFree(e->d_reach);
     for (auto& se : e->ev_pool) for (auto& ev : se.ev) if (ev) cudaEventDestroy(ev);
     for (auto& pr : e->step_ev) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
@@ -180,6 +184,10 @@ static int reset_state(lscgpu_engine* e) {
 extern "C" int lscgpu_create(const lscgpu_params* p, int n_agents, const lscgpu_agent_const* agents, int device,
                              lscgpu_engine** out) {
     if (!p || !agents || !out || n_agents < 1) return fail(LSCGPU_ERR_ARG, "null argument or n_agents < 1");
+    if (p->goal_mode != 0 && p->goal_mode != 1) return fail(LSCGPU_ERR_ARG, "goal_mode must be 0 (static) or 1 (prior_based)");
+    if (p->goal_mode == 1 && p->world_use_octomap)
+        return fail(LSCGPU_ERR_ARG, "goal_mode 1 (prior_based on the GPU) needs world_use_octomap = 0: with an octomap the goals "
+                                    "come from the host grid planner (lsc_planner_b200/host/grid_based_planner.hpp)");
     if (p->M != 5 || p->n != 5 || p->phi != 3 || p->dim != 3)
         return fail(LSCGPU_ERR_ARG, "only M=5 (horizon/dt), n=5, phi=3, dim=3 is supported (launch/simulation.launch)");
     if (!(p->dt > 0) || !(p->world_resolution > 0)) return fail(LSCGPU_ERR_ARG, "dt and world_resolution must be positive");
@@ -270,6 +278,8 @@ extern "C" int lscgpu_create(const lscgpu_params* p, int n_agents, const lscgpu_
     CUB(cudaMalloc(&e->d_last_cost, sizeof(double) * N));
     CUB(cudaMalloc(&e->d_ts, sizeof(int) * N));
     CUB(cudaMalloc(&e->d_flags, sizeof(int) * N));
+    CUB(cudaMalloc(&e->d_goal_kind, sizeof(int) * N));
+    CUB(cudaMemset(e->d_goal_kind, 0, sizeof(int) * N));
     CUB(cudaMalloc(&e->d_init_sfc, sizeof(int) * N));
     CUB(cudaMalloc(&e->d_counters, sizeof(StepCounters)));
     CUB(cudaMemset(e->d_counters, 0, sizeof(StepCounters)));
@@ -447,6 +457,14 @@ static int step_device(lscgpu_engine* e) {
     pl.pred = e->d_pred; pl.predT = e->d_predT; pl.predZs = e->d_predZs; pl.state9 = e->d_state9; pl.goal3 = e->d_goal3;
     pl.ts = e->d_ts; pl.flags = e->d_flags; pl.sphere = e->d_sphere; pl.reach = e->d_reach;
     launch_predict(pl, s); launches++;
+    if (e->prm.goal_mode == 1) {
+        GoalLaunch gl{};
+        gl.n_agents = e->N; gl.dt = e->prm.dt; gl.goal_threshold = e->prm.goal_threshold; gl.goal_radius = e->prm.goal_radius;
+        gl.priority_dist_threshold = e->prm.priority_dist_threshold;
+        gl.in = e->d_in; gl.prev_traj = e->d_traj; gl.pred = e->d_pred; gl.consts = e->d_consts;
+        gl.goal3 = e->d_goal3; gl.ts = e->d_ts; gl.goal_kind = e->d_goal_kind;
+        launch_goal_plan(gl, s); launches++;
+    }
     // scheduling order of this step's QP blocks from the cost of the previous step's solves (still in d_out)
     const bool ordered = e->lpt_order && e->planner_seq > 1 && n_local > 1;
     if (ordered) { launch_qp_order(n_local, e->a0, e->d_out, e->d_order, s); launches++; }
@@ -497,6 +515,7 @@ static int step_device(lscgpu_engine* e) {
     ql.rows = e->d_rows; ql.obs_offset = nullptr; ql.n_obs = e->N - 1; ql.P_pad = e->P_pad;
     ql.kept = e->d_kept; ql.kept_count = e->d_kept_count; ql.safe = e->d_safe; ql.max_iter = e->max_iter;
     ql.out = e->d_out; ql.prev_traj = e->d_traj; ql.last_cost = e->d_last_cost; ql.flags = e->d_flags;
+    ql.goal_kind = e->d_goal_kind;
     ql.counters = e->d_counters;
     if (getenv("LSCGPU_QP_DEBUG")) { if (!e->d_dbg) CU(cudaMalloc(&e->d_dbg, sizeof(long long) * 8 * (size_t)e->N)); ql.dbg = e->d_dbg; }
     if (groups == 1) {

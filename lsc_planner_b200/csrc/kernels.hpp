@@ -27,6 +27,20 @@ struct PredictLaunch {
 };
 void launch_predict(const PredictLaunch& L, cudaStream_t s);
 
+// ---- k_goal_plan: goalPlanningWithPriority without an octomap ----------------------------------------------
+struct GoalLaunch {
+    int n_agents;
+    double dt, goal_threshold, goal_radius, priority_dist_threshold;
+    const lscgpu_agent_in* in;     // [N] goal = DESIRED goal
+    const float* prev_traj;        // [N][90] traj_curr of every agent (obs_prev_trajs)
+    const float* pred;             // [N][90] initial_traj
+    const AgentConstDev* consts;
+    double* goal3;                 // [N][3] current goal (overwrites what k_predict stored)
+    int* ts;                       // [N]
+    int* goal_kind;                // [N] 0 line-of-sight goal, 1 retreat from the closest higher-priority agent
+};
+void launch_goal_plan(const GoalLaunch& L, cudaStream_t s);
+
 // ---- k_lsc_build ------------------------------------------------------------------------------------------
 struct LscLaunch {
     int n_agents, n_pad, a0, n_local;
@@ -91,6 +105,7 @@ struct QpLaunch {
     const float* prev_traj;        // [N][90]  (kept when the QP fails)
     double* last_cost;             // [N]
     const int* flags;              // [N]
+    const int* goal_kind;          // [N] or null
     StepCounters* counters;
     long long* dbg;                // null, or [n_problems][8] section cycle counts (LSCGPU_QP_DEBUG)
 };

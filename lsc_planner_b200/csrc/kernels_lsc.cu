@@ -13,6 +13,18 @@ namespace lscgpu {
 // and getTerminalSegments (src/traj_optimizer.cpp:541-548). Because every agent runs the same planner on the same
 // snapshot, agent j's initial trajectory IS the prediction every neighbour makes of j, so it is computed once.
 // ------------------------------------------------------------------------------------------------------------
+// getTerminalSegments (src/traj_optimizer.cpp:541-548)
+__device__ __forceinline__ int terminal_segments_of(F3 goal, F3 pos, double v_nom, double dt) {
+    const F3 gd = f3_sub(goal, pos);
+    const double ideal = __ddiv_rn(sqrt(f3_dot(gd, gd)), v_nom);
+    const double horizon = __dmul_rn((double)kM, dt);
+    const double q = __ddiv_rn(__dadd_rn(__dsub_rn(horizon, ideal), 1e-9), dt);
+    int ts = (int)q;
+    if (ts < 1) ts = 1;
+    if (ts > kM) ts = kM;     // the reference throws here (src/traj_optimizer.cpp:356-358); unreachable for ideal >= 0
+    return ts;
+}
+
 __global__ void __launch_bounds__(96) k_predict(PredictLaunch L) {
     const int a = blockIdx.x;
     const int e = threadIdx.x;
@@ -54,14 +66,7 @@ __global__ void __launch_bounds__(96) k_predict(PredictLaunch L) {
         if (sqrt(f3_dot(dlt, dlt)) > L.reset_threshold) fl |= LSCGPU_FLAG_SLACK_NEEDED;
         L.flags[a] = fl;
         const F3 g{in.goal[0], in.goal[1], in.goal[2]};
-        const F3 gd = f3_sub(g, pos);
-        const double ideal = __ddiv_rn(sqrt(f3_dot(gd, gd)), L.consts[a].v_nom);
-        const double horizon = __dmul_rn((double)kM, L.dt);
-        const double q = __ddiv_rn(__dadd_rn(__dsub_rn(horizon, ideal), 1e-9), L.dt);
-        int ts = (int)q;
-        if (ts < 1) ts = 1;
-        if (ts > kM) ts = kM;     // the reference throws here (src/traj_optimizer.cpp:356-358); unreachable for ideal >= 0
-        L.ts[a] = ts;
+        L.ts[a] = terminal_segments_of(g, pos, L.consts[a].v_nom, L.dt);
     }
     if (e >= 32 && e < 32 + kM) {
         // Culling data of segment m. Bounding sphere of the 6 control points, and `reach`: an upper
@@ -103,6 +108,80 @@ __global__ void __launch_bounds__(96) k_predict(PredictLaunch L) {
 }
 
 void launch_predict(const PredictLaunch& L, cudaStream_t s) { k_predict<<<L.n_agents, 96, 0, s>>>(L); }
+
+// ------------------------------------------------------------------------------------------------------------
+// k_goal_plan — goalPlanningWithPriority (src/traj_planner.cpp:540-608) for worlds WITHOUT an octomap, one block of
+// 128 threads per agent. Every other agent is an obstacle seen at its current position with its desired goal and its
+// previous trajectory (src/multi_sync_simulator.cpp:269-299). Higher-priority agents: closer to their goal than this
+// agent (all of them when this agent is at its goal), not at their goal, and not moving away from this agent. If the
+// nearest of them is closer than priority_dist_threshold the goal is a retreat point; otherwise the grid planner runs,
+// but with distmap_obj == nullptr findLOSFreeGoal accepts every path point (src/grid_based_planner.cpp:355-407), so
+// the line-of-sight goal is the desired goal whatever path A* returns: only the clip to goal_radius around the end of
+// the initial trajectory remains. Float arithmetic of octomath::Vector3 with explicit roundings.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ F3 f3_normalized(F3 v) {
+    const double len = sqrt(f3_dot(v, v));
+    if (len > 0.0) { const float l = (float)len; v.x = __fdiv_rn(v.x, l); v.y = __fdiv_rn(v.y, l); v.z = __fdiv_rn(v.z, l); }
+    return v;
+}
+
+__global__ void __launch_bounds__(128) k_goal_plan(GoalLaunch L) {
+    __shared__ double s_dist[4];
+    __shared__ int s_idx[4];
+    const int a = blockIdx.x, tid = threadIdx.x;
+    const lscgpu_agent_in& me = L.in[a];
+    const F3 pos{me.position[0], me.position[1], me.position[2]};
+    const F3 desired{me.goal[0], me.goal[1], me.goal[2]};
+    const F3 to_goal = f3_sub(pos, desired);
+    const double dist_to_goal = sqrt(f3_dot(to_goal, to_goal));
+    double best = 1e9;                                   // SP_INFINITY
+    int best_j = -1;
+    for (int j = tid; j < L.n_agents; j += 128) {
+        if (j == a) continue;
+        const lscgpu_agent_in& o = L.in[j];
+        const F3 op{o.position[0], o.position[1], o.position[2]}, og{o.goal[0], o.goal[1], o.goal[2]};
+        const F3 d1 = f3_sub(op, og), d2 = f3_sub(op, pos);
+        const double obs_dist_to_goal = sqrt(f3_dot(d1, d1));
+        const double dist_to_obs = sqrt(f3_dot(d2, d2));
+        if (obs_dist_to_goal < L.goal_threshold) continue;
+        const float* t = L.prev_traj + (size_t)j * kTrajFloats;
+        const F3 first_end{t[15], t[16], t[17]}, last_end{t[87], t[88], t[89]};          // [0][n], [M-1][n]
+        if (dist_to_goal > L.goal_threshold && f3_dot(f3_sub(last_end, first_end), f3_sub(first_end, pos)) > 0.0) continue;
+        if (dist_to_goal < L.goal_threshold || obs_dist_to_goal < dist_to_goal)
+            if (dist_to_obs < best) { best = dist_to_obs; best_j = j; }     // ascending j per thread: first minimum kept
+    }
+    // block argmin, ties to the smallest index (the reference scans obstacles in id order with a strict <)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oj = __shfl_xor_sync(0xffffffffu, best_j, o);
+        if (oj >= 0 && (best_j < 0 || ob < best || (ob == best && oj < best_j))) { best = ob; best_j = oj; }
+    }
+    if ((tid & 31) == 0) { s_dist[tid >> 5] = best; s_idx[tid >> 5] = best_j; }
+    __syncthreads();
+    if (tid != 0) return;
+    for (int w = 1; w < 4; w++)
+        if (s_idx[w] >= 0 && (best_j < 0 || s_dist[w] < best || (s_dist[w] == best && s_idx[w] < best_j))) { best = s_dist[w]; best_j = s_idx[w]; }
+    F3 goal;
+    int kind = 0;
+    if (best_j >= 0 && best < L.priority_dist_threshold) {
+        const lscgpu_agent_in& o = L.in[best_j];
+        const F3 op{o.position[0], o.position[1], o.position[2]};
+        const double dist_keep = L.priority_dist_threshold + 0.1;
+        goal = f3_sub(pos, f3_scale(f3_normalized(f3_sub(op, pos)), (float)dist_keep));
+        kind = 1;
+    } else {
+        const float* p = L.pred + (size_t)a * kTrajFloats;
+        const F3 init_end{p[87], p[88], p[89]};
+        const F3 delta = f3_sub(desired, init_end);
+        goal = desired;
+        if (sqrt(f3_dot(delta, delta)) > L.goal_radius) goal = f3_add(init_end, f3_scale(f3_normalized(delta), (float)L.goal_radius));
+    }
+    L.goal3[(size_t)a * 3] = (double)goal.x; L.goal3[(size_t)a * 3 + 1] = (double)goal.y; L.goal3[(size_t)a * 3 + 2] = (double)goal.z;
+    L.ts[a] = terminal_segments_of(goal, pos, L.consts[a].v_nom, L.dt);
+    L.goal_kind[a] = kind;
+}
+void launch_goal_plan(const GoalLaunch& L, cudaStream_t s) { k_goal_plan<<<L.n_agents, 128, 0, s>>>(L); }
 
 // ------------------------------------------------------------------------------------------------------------
 // k_lsc_build — one block of 128 threads per local agent.

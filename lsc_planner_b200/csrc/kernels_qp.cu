@@ -587,6 +587,8 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 512 ? 1 : 512 / kThreads
             o.qp_active = q;
             o.flags = L.flags ? L.flags[agent] : 0;
             o.terminal_segments = ts;
+            for (int k = 0; k < 3; k++) o.current_goal[k] = (float)gl[k];
+            o.goal_kind = L.goal_kind ? L.goal_kind[agent] : 0;
             o.qp_sweeps = (int)passes;
             o.qp_kcycles = (int)((clock64() - t_start) >> 10);
             o.qp_price_kcycles = (int)(price_cycles >> 10);

@@ -29,6 +29,10 @@ class Param:
     n: int = 5
     phi: int = 3
     dim: int = 3
+    goal_mode: int = 0              # 0 static (goal = current goal), 1 prior_based on the GPU (goal = desired goal; no octomap)
+    goal_threshold: float = 0.1
+    goal_radius: float = 2.0
+    priority_dist_threshold: float = 0.4
 
     def to_c(self) -> A.Params:
         p = A.Params()
@@ -38,6 +42,8 @@ class Param:
         for k in range(3):
             p.world_min[k] = float(np.float32(self.world_min[k])); p.world_max[k] = float(np.float32(self.world_max[k]))
         p.M, p.n, p.phi, p.dim = self.M, self.n, self.phi, self.dim
+        p.goal_mode, p.goal_threshold, p.goal_radius = self.goal_mode, self.goal_threshold, self.goal_radius
+        p.priority_dist_threshold = self.priority_dist_threshold
         return p
 
 

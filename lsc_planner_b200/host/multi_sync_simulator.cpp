@@ -156,6 +156,7 @@ private:
         std::cout << "[MultiSyncSimulator] total flight time: " << total_flight_time << "\n"
                   << "[MultiSyncSimulator] total distance: " << total_distance << "\n"
                   << "[MultiSyncSimulator] planning time per agent: " << planning_time.total_planning_time.average << "\n"
+                  << "[MultiSyncSimulator] goal planning time per agent: " << planning_time.goal_planning_time.average << "\n"
                   << "[MultiSyncSimulator] safety ratio between agent: " << safety_ratio_agent << "\n"
                   << "[MultiSyncSimulator] is_collided: " << is_collided << " qp_failures: " << qp_failures << "\n";
         if (summary_file.empty()) return;

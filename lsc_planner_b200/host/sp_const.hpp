@@ -99,6 +99,7 @@ struct Param {
     int n = 5, phi = 3, phi_n = 1, M = 4;
     double control_input_weight = 1, terminal_weight = 1, slack_collision_weight = 1;
     int N_constraint_segments = -1;
+    double grid_resolution = 0.3, grid_margin = 0.1;            // src/param.cpp:93-94
     double goal_threshold = 0.1, goal_radius = 100.0, priority_dist_threshold = 0.4;
     std::string mission_file_name = "default.json", world_file_name = "default.bt", package_path = ".";
 
@@ -107,7 +108,7 @@ struct Param {
         Param p;
         p.world_use_octomap = true; p.multisim_time_step = 0.2; p.multisim_max_noise = 0.02;
         p.multisim_reset_threshold = 0.15; p.dt = 0.2; p.horizon = 1.0; p.control_input_weight = 0.01;
-        p.terminal_weight = 1; p.slack_collision_weight = 1e5; p.goal_radius = 2.0;
+        p.terminal_weight = 1; p.slack_collision_weight = 1e5; p.goal_radius = 2.0; p.grid_resolution = 0.25;
         p.multisim_save_result = true;
         p.finalize();
         return p;
@@ -149,6 +150,8 @@ struct Param {
         else if (key == "opt/terminal_weight") terminal_weight = d();
         else if (key == "opt/slack_collision_weight") slack_collision_weight = d();
         else if (key == "opt/N_constraint_segments") N_constraint_segments = i();
+        else if (key == "grid/resolution") grid_resolution = d();
+        else if (key == "grid/margin") grid_margin = d();
         else if (key == "plan/goal_threshold") goal_threshold = d();
         else if (key == "plan/goal_radius") goal_radius = d();
         else if (key == "plan/priority_dist_threshold") priority_dist_threshold = d();

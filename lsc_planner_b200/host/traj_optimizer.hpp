@@ -24,6 +24,10 @@ inline lscgpu_params toEngineParams(const Param& param, const Mission& mission) 
     p.world_use_octomap = param.world_use_octomap ? 1 : 0;
     for (int k = 0; k < 3; k++) { p.world_min[k] = mission.world_min(k); p.world_max[k] = mission.world_max(k); }
     p.M = param.M; p.n = param.n; p.phi = param.phi; p.dim = param.world_dimension;
+    // prior_based goal planning: on the GPU without an octomap, by the host grid planner (goal_mode 0 for the engine) with one
+    p.goal_mode = (param.goal_mode == GoalMode::PRIORBASED && !param.world_use_octomap) ? 1 : 0;
+    p.goal_threshold = param.goal_threshold; p.goal_radius = param.goal_radius;
+    p.priority_dist_threshold = param.priority_dist_threshold;
     return p;
 }
 

@@ -12,6 +12,9 @@
 #include <memory>
 #include <vector>
 
+#include <thread>
+
+#include "grid_based_planner.hpp"
 #include "traj_optimizer.hpp"
 
 namespace DynamicPlanning {
@@ -63,6 +66,7 @@ public:
         if (lscgpu_set_octomap_file(engine.get(), file.c_str()) != LSCGPU_OK)
             throw std::invalid_argument(std::string("[lscgpu] ") + lscgpu_last_error());
     }
+    // goal: the current goal (GoalMode::STATIC) or the desired goal (GoalMode::PRIORBASED, resolved in ensurePlanned)
     void setInput(int qi, const State& s, const point3d& goal) {
         for (int k = 0; k < 3; k++) {
             in[qi].position[k] = s.position(k); in[qi].velocity[k] = s.velocity(k);
@@ -76,6 +80,11 @@ public:
         if (planned_seq >= planner_seq) return;
         for (bool f : fresh) if (!f) throw PlanningReport::WAITFORROSMSG;
         const auto t0 = std::chrono::steady_clock::now();
+        goal_seconds = 0;
+        if (param.goal_mode == GoalMode::PRIORBASED && param.world_use_octomap) {
+            planGoalsOnHost(planner_seq);
+            goal_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        }
         if (lscgpu_replan_batch(engine.get(), in.data(), out.data()) != LSCGPU_OK)
             throw std::invalid_argument(std::string("[lscgpu] ") + lscgpu_last_error());
         wall_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -85,12 +94,66 @@ public:
     }
     const lscgpu_agent_out& result(int qi) const { return out[qi]; }
     double wallSecondsPerAgent() const { return wall_seconds / std::max(1, mission.qn); }
+    double goalSecondsPerAgent() const { return goal_seconds / std::max(1, mission.qn); }
+    long long astarExpansions() const { return astar_expansions; }
     const lscgpu_step_stats& stepStats() const { return stats; }
 
 private:
+    // goalPlanningWithPriority for every agent (src/traj_planner.cpp:540-608) with the grid planner and A* on the host,
+    // agents spread over the host threads. Inputs are exactly what MultiSyncSimulator::update() hands every planner
+    // (src/multi_sync_simulator.cpp:269-299): the others' current positions, desired goals and previous trajectories
+    // (the result records of the previous step; zero before the first, src/traj_planner.cpp:36-39).
+    void planGoalsOnHost(int planner_seq) {
+        const int N = mission.qn;
+        if (distmap.sqdist.empty()) {
+            int32_t size[3], off[3]; int64_t n_occ = 0;
+            if (lscgpu_get_distmap_info(engine.get(), size, off, &n_occ) != LSCGPU_OK)
+                throw std::invalid_argument(std::string("[lscgpu] ") + lscgpu_last_error());
+            distmap.res = param.world_resolution;
+            for (int k = 0; k < 3; k++) { distmap.size[k] = size[k]; distmap.off[k] = off[k]; }
+            distmap.sqdist.resize((size_t)size[0] * size[1] * size[2]);
+            if (lscgpu_get_distmap_sqdist(engine.get(), distmap.sqdist.data()) != LSCGPU_OK)
+                throw std::invalid_argument(std::string("[lscgpu] ") + lscgpu_last_error());
+        }
+        auto P = [](const float* v) { return point3d(v[0], v[1], v[2]); };
+        std::vector<GoalObstacle> all(N);
+        for (int j = 0; j < N; j++) {
+            all[j].id = j; all[j].position = P(in[j].position); all[j].goal_point = P(in[j].goal);
+            all[j].radius = mission.agents[j].radius; all[j].downwash = mission.agents[j].downwash;
+            all[j].prev_traj_first_end = P(out[j].traj[0][5]); all[j].prev_traj_last_end = P(out[j].traj[4][5]);
+        }
+        std::vector<point3d> goals(N);
+        std::vector<long long> expanded(N, 0);
+        const int threads = (int)std::max(1u, std::min((unsigned)N, std::thread::hardware_concurrency()));
+        std::vector<std::thread> pool;
+        for (int t = 0; t < threads; t++)
+            pool.emplace_back([&, t]() {
+                std::vector<GoalObstacle> obstacles;
+                for (int a = t; a < N; a += threads) {
+                    obstacles.clear();
+                    for (int j = 0; j < N; j++) if (j != a) obstacles.push_back(all[j]);
+                    const point3d pos = P(in[a].position), vel = P(in[a].velocity);
+                    // initial_traj[M-1][n]: straight line at the first step (src/traj_planner.cpp:1030-1037), else the end
+                    // of the previous trajectory (:997-1016)
+                    const point3d init_end = planner_seq < 2 ? pos + (vel * (float)5.0) * (float)param.dt : P(out[a].traj[4][5]);
+                    const GoalPlanResult r = goalPlanningWithPriority(pos, P(in[a].goal), init_end, mission.agents[a].radius,
+                                                                      mission.agents[a].downwash, obstacles, &distmap, mission, param);
+                    goals[a] = r.goal; expanded[a] = r.expansions;
+                }
+            });
+        for (auto& th : pool) th.join();
+        for (int a = 0; a < N; a++) {
+            for (int k = 0; k < 3; k++) in[a].goal[k] = goals[a](k);
+            astar_expansions += expanded[a];
+        }
+    }
+
     Param param;
     Mission mission;
     EnginePtr engine;
+    HostDistMap distmap;
+    double goal_seconds = 0;
+    long long astar_expansions = 0;
     std::vector<lscgpu_agent_in> in;
     std::vector<lscgpu_agent_out> out;
     std::vector<bool> fresh;
@@ -126,6 +189,7 @@ public:
         const lscgpu_agent_out& o = batch->result(agent.id);
         for (int m = 0; m < M; m++)
             for (int i = 0; i < n + 1; i++) traj_curr[m][i] = point3d(o.traj[m][i][0], o.traj[m][i][1], o.traj[m][i][2]);
+        agent.current_goal_position = point3d(o.current_goal[0], o.current_goal[1], o.current_goal[2]);
         current_qp_cost = o.qp_cost;
         qp_status = o.qp_status;
         planning_report = (PlanningReport)o.report;
@@ -134,7 +198,7 @@ public:
         PlanningTimeStatistics t;
         t.obstacle_prediction_time.current = 0.5 * st.ms_predict * per;
         t.initial_traj_planning_time.current = 0.5 * st.ms_predict * per;
-        t.goal_planning_time.current = 0;
+        t.goal_planning_time.current = batch->goalSecondsPerAgent();
         t.lsc_generation_time.current = st.ms_lsc * per;
         t.sfc_generation_time.current = st.ms_sfc * per;
         t.traj_optimization_time.current = st.ms_qp * per;
@@ -176,9 +240,13 @@ public:
     }
 
 private:
-    // Goal planning (src/traj_planner.cpp:477-608) is the step BEFORE the path; only the static goal is provided here:
-    // current_goal_position = desired goal (GoalMode::STATIC); the grid/A* modes are listed as "next" in DESIGN.md.
+    // Goal planning (src/traj_planner.cpp:477-608) is the step BEFORE the path. GoalMode::STATIC: current goal = desired
+    // goal. GoalMode::PRIORBASED (the reference's default): the desired goal is handed to the batch, which resolves it for
+    // all agents at once — on the GPU without an octomap (k_goal_plan), by the host grid planner with one
+    // (grid_based_planner.hpp) — and collect() reads the chosen goal back. ORCA / right-hand modes: not provided.
     void goalPlanning() {
+        if (param.goal_mode != GoalMode::STATIC && param.goal_mode != GoalMode::PRIORBASED)
+            throw std::invalid_argument("[TrajPlanner] Invalid goal mode");
         agent.current_goal_position = planner_state == PlannerState::GOBACK ? agent.start_position : agent.desired_goal_position;
     }
 

@@ -3,7 +3,7 @@
 Within one synchronous replanning step every agent depends only on the PREVIOUS step's trajectories of all agents
 (Jacobi snapshot, reference src/multi_sync_simulator.cpp:190-318), so agents are block-partitioned: rank r plans
 agents [r*B, min(N, (r+1)*B)), B = ceil(N / world). Every rank keeps a replica of all trajectories; the step ends with
-ONE all-gather of the per-agent result records (448 B each), issued by liblscgpu.so on its own stream with its own
+ONE all-gather of the per-agent result records (464 B each), issued by liblscgpu.so on its own stream with its own
 communicator (lscgpu_nccl_init). torch.distributed is only the out-of-band channel that carries the NCCL unique id.
 """
 from __future__ import annotations

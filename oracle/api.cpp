@@ -184,6 +184,48 @@ void orc_swarm_set_boxes(void* sv, const float* boxes /*N*5*6*/, const int* init
     }
     for (int a = 0; a < s->N; a++) s->init_sfc[a] = init_sfc[a];
 }
+// goal planning: mode 0 static (goal = input), 1 prior_based (goal computed from the desired goals)
+void orc_swarm_set_goal_mode(void* sv, int mode, double grid_resolution, double grid_margin, double goal_threshold,
+                             double goal_radius, double priority_dist_threshold) {
+    Swarm* s = (Swarm*)sv;
+    s->goal_mode = mode;
+    s->gp.grid_resolution = grid_resolution; s->gp.grid_margin = grid_margin; s->gp.goal_threshold = goal_threshold;
+    s->gp.goal_radius = goal_radius; s->gp.priority_dist_threshold = priority_dist_threshold;
+}
+void orc_swarm_set_desired_goals(void* sv, const float* goal) { Swarm* s = (Swarm*)sv; std::memcpy(s->desired.data(), goal, s->N * 12); }
+void orc_swarm_get_goals(void* sv, float* goal, int* kind) {
+    Swarm* s = (Swarm*)sv;
+    std::memcpy(goal, s->goal.data(), s->N * 12);
+    if (kind) std::memcpy(kind, s->goal_kind.data(), s->N * 4);
+}
+long long orc_swarm_astar_expansions(void* sv) { return ((Swarm*)sv)->astar_expansions; }
+// A* on an explicit occupancy grid (pins the restatement against oracle/_ref): returns the path length in cells
+int orc_astar(const int* dim, const unsigned char* grid, const int* start, const int* goal, int* path_out, int max_len,
+              long long* expansions) {
+    std::vector<uint8_t> g(grid, grid + (size_t)dim[0] * dim[1] * dim[2]);
+    const auto path = astar_search(g, dim, start, goal, expansions);
+    const int n = (int)path.size();
+    for (int k = 0; k < n && k < max_len; k++) { path_out[3 * k] = path[k][0]; path_out[3 * k + 1] = path[k][1]; path_out[3 * k + 2] = path[k][2]; }
+    return n;
+}
+// one agent's goal planning on explicit inputs
+int orc_goal_plan(int a, int n, const float* pos, const float* desired, const float* prev_traj, const float* init_end,
+                  const double* radius, const double* downwash, void* map, double world_res, const float* wmin, const float* wmax,
+                  double grid_resolution, double grid_margin, double goal_threshold, double goal_radius,
+                  double priority_dist_threshold, float* goal_out, long long* expansions) {
+    std::vector<AgentConst> ac(n);
+    for (int i = 0; i < n; i++) { ac[i] = AgentConst{}; ac[i].radius = radius[i]; ac[i].downwash = downwash[i]; }
+    GoalParams gp; gp.grid_resolution = grid_resolution; gp.grid_margin = grid_margin; gp.goal_threshold = goal_threshold;
+    gp.goal_radius = goal_radius; gp.priority_dist_threshold = priority_dist_threshold; gp.world_resolution = world_res;
+    const GoalResult r = goal_planning_priority(a, n, reinterpret_cast<const F3*>(pos), reinterpret_cast<const F3*>(desired),
+                                                reinterpret_cast<const F3*>(prev_traj), f3(init_end[0], init_end[1], init_end[2]),
+                                                ac.data(), map ? &((MapHandle*)map)->dm : nullptr, gp, f3(wmin[0], wmin[1], wmin[2]),
+                                                f3(wmax[0], wmax[1], wmax[2]));
+    goal_out[0] = r.goal.x; goal_out[1] = r.goal.y; goal_out[2] = r.goal.z;
+    if (expansions) *expansions = r.expansions;
+    return r.mode;
+}
+
 void orc_swarm_step(void* sv, int a0, int a1, int threads) { ((Swarm*)sv)->step(a0, a1, threads); }
 void orc_swarm_advance(void* sv) { ((Swarm*)sv)->advance_states(); }
 int orc_swarm_seq(void* sv) { return ((Swarm*)sv)->seq; }

@@ -11,7 +11,9 @@
 //   src/traj_planner.cpp:1548-1585         trajOptimization (failure keeps the optimizer's last
 //                                          successful trajectory and still reports SUCCESS)
 //   include/polynomial.hpp:63-121          getStateFromControlPoints at t = dt
-// Goal planning (src/traj_planner.cpp:477-608) is NOT on the path: current_goal_position is an input.
+// Goal planning (src/traj_planner.cpp:477-608) is the step before the path: with goal_mode == 0 current_goal_position is
+// an input (goalPlanningWithStaticGoal), with goal_mode == 1 it is computed per agent by goal.hpp
+// (goalPlanningWithPriority, the reference's default) from the desired goals.
 #pragma once
 #include <thread>
 #include <vector>
@@ -30,6 +32,10 @@ struct SwarmParams {
 
 struct AgentConst { double radius, downwash, vmax[3], amax[3], v_nom; };
 
+}  // namespace orc
+#include "goal.hpp"      // needs AgentConst
+namespace orc {
+
 enum StepFlags { FLAG_SLACK_NEEDED = 1, FLAG_SFC_SEED_BLOCKED = 2 };
 
 struct Swarm {
@@ -41,7 +47,12 @@ struct Swarm {
     int seq = 0;                                 // planner_seq (lock-step for all agents)
     std::vector<F3> traj;                        // [N][30] traj_curr
     std::vector<F3> pos, vel, acc;               // current state (input of the step)
-    std::vector<F3> goal;                        // current_goal_position (input of the step)
+    std::vector<F3> goal;                        // current_goal_position (input of the step, or output of goal planning)
+    std::vector<F3> desired;                     // desired_goal_position (goal_mode == 1)
+    int goal_mode = 0;                           // 0 static, 1 prior_based
+    GoalParams gp;
+    std::vector<int> goal_kind;                  // per agent: 0 A* + line of sight, 1 retreat from a higher-priority agent
+    long long astar_expansions = 0;
     std::vector<F3> box_min, box_max;            // [N][5] persistent SFC
     std::vector<int> init_sfc;                   // flag_initialize_sfc
     // step outputs
@@ -57,7 +68,7 @@ struct Swarm {
         prm = p; N = n_agents; ac.assign(consts, consts + N);
         build_tables(p.dt, p.w, p.wT, T);
         traj.assign((size_t)N * 30, f3(0, 0, 0));                   // traj_planner.cpp:36-39
-        pos.assign(N, f3(0, 0, 0)); vel = pos; acc = pos; goal = pos;
+        pos.assign(N, f3(0, 0, 0)); vel = pos; acc = pos; goal = pos; desired = pos; goal_kind.assign(N, 0);
         box_min.assign((size_t)N * 5, f3(0, 0, 0)); box_max = box_min;
         init_sfc.assign(N, 1);                                      // traj_planner.cpp:49
         qp_cost.assign(N, 0); qp_status.assign(N, 0); qp_iters.assign(N, 0); qp_active.assign(N, 0);
@@ -163,6 +174,25 @@ struct Swarm {
         __atomic_fetch_add(&counters[3], (long long)(450 + 6 * rows_buf.size()), __ATOMIC_RELAXED);
     }
 
+    // goalPlanningWithPriority for agents [a0, a1): every obstacle is another agent of the swarm, seen at its current
+    // state with its desired goal and its previous trajectory (src/multi_sync_simulator.cpp:269-299)
+    void plan_goals(int a0, int a1, int threads) {
+        gp.world_resolution = prm.res;
+        const F3 wmin = f3(prm.world_min[0], prm.world_min[1], prm.world_min[2]);
+        const F3 wmax = f3(prm.world_max[0], prm.world_max[1], prm.world_max[2]);
+        const DistMap* map = prm.use_octomap ? dm : nullptr;
+        auto work = [&](int a) {
+            GoalResult r = goal_planning_priority(a, N, pos.data(), desired.data(), traj.data(), pred[(size_t)a * 30 + 29],
+                                                  ac.data(), map, gp, wmin, wmax);
+            goal[a] = r.goal; goal_kind[a] = r.mode;
+            __atomic_fetch_add(&astar_expansions, r.expansions, __ATOMIC_RELAXED);
+        };
+        if (threads <= 1) { for (int a = a0; a < a1; a++) work(a); return; }
+        std::vector<std::thread> th;
+        for (int t = 0; t < threads; t++) th.emplace_back([&, t]() { for (int a = a0 + t; a < a1; a += threads) work(a); });
+        for (auto& t : th) t.join();
+    }
+
     // one synchronous replanning step for agents [a0, a1)
     void step(int a0, int a1, int threads) {
         seq++;                                                         // traj_planner.cpp:127
@@ -171,6 +201,7 @@ struct Swarm {
             cap_normal.assign((size_t)N * N * 5, f3(0, 0, 0)); cap_d.assign((size_t)N * N * 30, 0.0); cap_gjk.assign((size_t)N * N * 5, 0);
         }
         predict_all();
+        if (goal_mode == 1) plan_goals(a0, a1, threads);                // traj_planner.cpp:360-364 (after the initial trajectory)
         std::vector<F3> new_traj = traj;
         if (threads <= 1) {
             std::vector<LscRows> rows;

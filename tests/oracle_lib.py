@@ -22,7 +22,7 @@ i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
 
 def build(force: bool = False) -> str:
     so = os.path.join(ORACLE_DIR, "liblsc_oracle.so")
-    srcs = [os.path.join(ORACLE_DIR, f) for f in ("api.cpp", "geom.hpp", "edt.hpp", "qp.hpp", "swarm.hpp")]
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("api.cpp", "geom.hpp", "edt.hpp", "qp.hpp", "swarm.hpp", "goal.hpp")]
     stale = (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
     if force or stale:
         subprocess.run(["make", "-C", ORACLE_DIR, "liblsc_oracle.so"], check=True, capture_output=True)
@@ -64,6 +64,15 @@ def lib():
         L.orc_swarm_set_traj.argtypes = [C.c_void_p, f32p, C.c_int]
         L.orc_swarm_set_boxes.argtypes = [C.c_void_p, f32p, i32p]
         L.orc_swarm_step.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.orc_swarm_set_goal_mode.argtypes = [C.c_void_p, C.c_int] + [C.c_double] * 5
+        L.orc_swarm_set_desired_goals.argtypes = [C.c_void_p, f32p]
+        L.orc_swarm_get_goals.argtypes = [C.c_void_p, f32p, i32p]
+        L.orc_swarm_astar_expansions.argtypes = [C.c_void_p]; L.orc_swarm_astar_expansions.restype = C.c_longlong
+        u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+        L.orc_astar.argtypes = [i32p, u8p, i32p, i32p, i32p, C.c_int, C.POINTER(C.c_longlong)]; L.orc_astar.restype = C.c_int
+        L.orc_goal_plan.argtypes = [C.c_int, C.c_int, f32p, f32p, f32p, f32p, f64p, f64p, C.c_void_p, C.c_double, f32p, f32p,
+                                    C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, f32p, C.POINTER(C.c_longlong)]
+        L.orc_goal_plan.restype = C.c_int
         L.orc_swarm_advance.argtypes = [C.c_void_p]
         L.orc_swarm_seq.argtypes = [C.c_void_p]; L.orc_swarm_seq.restype = C.c_int
         L.orc_swarm_get_traj.argtypes = [C.c_void_p, f32p]
@@ -92,6 +101,30 @@ def lsc_pair(own, obs, r_i=0.15, dw_i=2.0, r_j=0.15, dw_j=2.0):
     n = np.zeros((5, 3), np.float32); d = np.zeros((5, 6)); it = np.zeros(5, np.int32)
     lib().orc_lsc_pair(own, obs, r_i, dw_i, r_j, dw_j, n, d, it)
     return n, d, it
+
+
+def astar(grid: np.ndarray, start, goal):
+    """Oracle A* on an occupancy grid [i][j][k] (non-zero = occupied): (path cells [n][3], expansions)."""
+    grid = np.ascontiguousarray(grid, np.uint8)
+    dim = np.asarray(grid.shape, np.int32)
+    path = np.zeros((int(dim.sum()) * 8 + 16, 3), np.int32); ex = C.c_longlong(0)
+    n = lib().orc_astar(dim, grid, np.asarray(start, np.int32), np.asarray(goal, np.int32), path, len(path), C.byref(ex))
+    assert n <= len(path)
+    return path[:n].copy(), ex.value
+
+
+def goal_plan(a, pos, desired, prev_traj, init_end, radius, downwash, omap, wmin, wmax, res=0.1, grid_resolution=0.25,
+              grid_margin=0.1, goal_threshold=0.1, goal_radius=2.0, priority_dist_threshold=0.4):
+    """Oracle goalPlanningWithPriority for agent a: (goal[3], kind, A* expansions)."""
+    n = len(pos)
+    out = np.zeros(3, np.float32); ex = C.c_longlong(0)
+    kind = lib().orc_goal_plan(a, n, np.ascontiguousarray(pos, np.float32), np.ascontiguousarray(desired, np.float32),
+                               np.ascontiguousarray(prev_traj, np.float32).reshape(n, 90), np.ascontiguousarray(init_end, np.float32),
+                               np.ascontiguousarray(np.broadcast_to(radius, (n,)), np.float64),
+                               np.ascontiguousarray(np.broadcast_to(downwash, (n,)), np.float64),
+                               omap.h if omap is not None else None, res, np.asarray(wmin, np.float32), np.asarray(wmax, np.float32),
+                               grid_resolution, grid_margin, goal_threshold, goal_radius, priority_dist_threshold, out, C.byref(ex))
+    return out, kind, ex.value
 
 
 class Map:
@@ -216,6 +249,20 @@ class Swarm:
     def set_boxes(self, boxes, init_sfc):
         lib().orc_swarm_set_boxes(self.h, np.ascontiguousarray(boxes, np.float32).reshape(self.n, 30),
                                   np.ascontiguousarray(init_sfc, np.int32))
+
+    def set_goal_mode(self, mode, grid_resolution=0.25, grid_margin=0.1, goal_threshold=0.1, goal_radius=2.0,
+                      priority_dist_threshold=0.4):
+        """0: static (set_goals = current goals); 1: prior_based (set_desired_goals; goals planned every step)."""
+        lib().orc_swarm_set_goal_mode(self.h, mode, grid_resolution, grid_margin, goal_threshold, goal_radius, priority_dist_threshold)
+
+    def set_desired_goals(self, goal):
+        lib().orc_swarm_set_desired_goals(self.h, np.ascontiguousarray(goal, np.float32).reshape(self.n, 3))
+
+    def goals(self):
+        g = np.zeros((self.n, 3), np.float32); k = np.zeros(self.n, np.int32)
+        lib().orc_swarm_get_goals(self.h, g, k); return g, k
+
+    def astar_expansions(self): return int(lib().orc_swarm_astar_expansions(self.h))
 
     def step(self, a0=0, a1=None, threads=1): lib().orc_swarm_step(self.h, a0, self.n if a1 is None else a1, threads)
 

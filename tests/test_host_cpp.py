@@ -50,7 +50,7 @@ def test_simulator_matches_oracle_closed_loop(built, tmp_path, mission):
     scn = L.scenarios.load_mission(os.path.join(MISSIONS, mission))
     res, summ = str(tmp_path / "result.csv"), str(tmp_path / "summary.csv")
     r = subprocess.run([os.path.join(built, "lsc_sim"), "mission=" + os.path.join(MISSIONS, mission),
-                        "multisim/record_time_step=0.2", "multisim/max_planner_iteration=151", "result=" + res,
+                        "mode/goal=static", "multisim/record_time_step=0.2", "multisim/max_planner_iteration=151", "result=" + res,
                         "summary=" + summ],
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr

@@ -11,6 +11,9 @@ Fixtures written (all DATA, no reference source code):
   golden/missions/*.json         the two mission files BASELINE.json names (re-dumped JSON)
   golden/worlds/simple_forest.bt the octomap BASELINE.json names (binary data, byte copy)
   golden/simple_forest_voxels.npz occupied finest voxels of that map as decoded by the oracle's reader
+  golden/astar_ref_vectors.npz   occupancy grids, start / goal cells and the cell paths returned by the REFERENCE's own
+                                 A* (oracle/_ref/libref_astar.so, compiled from <ref>/src/Astar-3D), including grids
+                                 built to provoke the (F, g) ties that the reference resolves by hash-map iteration order
 """
 import ctypes as C
 import json
@@ -27,6 +30,52 @@ import qp_pyref as R     # noqa: E402
 
 REF = os.environ.get("LSC_REFERENCE", "/root/reference")
 G = os.path.join(ROOT, "tests", "golden")
+
+
+def astar_cases(seed=2024, count=160):
+    """Deterministic test grids: random clutter, forests of vertical columns, and mirror-symmetric layouts (start and
+    goal in the same grid column with an obstacle between them) where equal-length detours tie."""
+    rng = np.random.default_rng(seed)
+    cases = []
+    for t in range(count):
+        dim = (int(rng.integers(3, 42)), int(rng.integers(3, 42)), int(rng.integers(1, 12)))
+        dens = float(rng.choice([0.0, 0.05, 0.15, 0.3]))
+        grid = (rng.random(dim) < dens).astype(np.uint8)
+        if t % 3 == 0:
+            grid[:] = 0
+            for _ in range(int(dens * 40)):
+                a, b = int(rng.integers(0, dim[0])), int(rng.integers(0, dim[1])); grid[a:a + 2, b:b + 2, :] = 1
+        s = [int(rng.integers(0, d)) for d in dim]; g = [int(rng.integers(0, d)) for d in dim]
+        if t % 4 == 0:
+            g[1] = s[1]
+        if t % 5 == 0:
+            g[2] = s[2]
+        if t % 8 == 0 and dim[0] > 8 and dim[1] > 8:          # symmetric wall across the straight line
+            grid[:] = 0
+            s = [1, dim[1] // 2, dim[2] // 2]; g = [dim[0] - 2, dim[1] // 2, dim[2] // 2]
+            w = int(rng.integers(1, max(2, dim[1] // 2 - 1)))
+            grid[dim[0] // 2, dim[1] // 2 - w:dim[1] // 2 + w + 1, :] = 1
+        grid[tuple(s)] = 0
+        cases.append((np.ascontiguousarray(grid), np.array(s, np.int32), np.array(g, np.int32)))
+    return cases
+
+
+def astar_fixture():
+    so = os.path.join(ROOT, "oracle", "_ref", "libref_astar.so")
+    R_ = C.CDLL(so)
+    i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS"); u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+    R_.ref_astar_plan.argtypes = [i32p, u8p, i32p, i32p, i32p, C.c_int]; R_.ref_astar_plan.restype = C.c_int
+    out = {}
+    n_found = 0
+    for k, (grid, s, g) in enumerate(astar_cases()):
+        path = np.zeros((4096, 3), np.int32)
+        n = R_.ref_astar_plan(np.asarray(grid.shape, np.int32), grid, s, g, path, len(path))
+        out[f"grid{k}"] = np.packbits(grid); out[f"dim{k}"] = np.asarray(grid.shape, np.int32)
+        out[f"start{k}"] = s; out[f"goal{k}"] = g; out[f"path{k}"] = path[:n].astype(np.int16)
+        n_found += n > 0
+    out["count"] = np.array(len(astar_cases()))
+    np.savez_compressed(os.path.join(G, "astar_ref_vectors.npz"), **out)
+    print("astar_ref_vectors.npz:", len(astar_cases()), "cases,", n_found, "with a path")
 
 
 def lp_fixture():
@@ -100,4 +149,6 @@ def data_fixtures():
 if __name__ == "__main__":
     os.makedirs(os.path.join(G, "missions"), exist_ok=True)
     os.makedirs(os.path.join(G, "worlds"), exist_ok=True)
-    lp_fixture(); gjk_fixture(); data_fixtures()
+    if "--astar-only" in sys.argv:
+        astar_fixture(); sys.exit(0)
+    lp_fixture(); gjk_fixture(); data_fixtures(); astar_fixture()
