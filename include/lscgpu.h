@@ -202,6 +202,13 @@ int lscgpu_gjk_batch(lscgpu_engine* e, int n_hulls, const double* hulls, double*
 int lscgpu_sfc_expand_batch(lscgpu_engine* e, int n, const float* point, const float* goal, const double* radius,
                             float* box, int32_t* ok);
 
+/* Replaces the O(N^2) minimum-distance audit of MultiSyncSimulator::savePlanningResult (src/multi_sync_simulator.cpp:
+ * 446-475): for every recorded sub-time t = 0, record_time_step, ... < time_step of the step just planned and every agent,
+ * the smallest downwash-scaled distance to another agent (include/util.hpp:225-229) over the sum of the two radii, from
+ * the trajectories resident on the device. ratio[a] = minimum over the sub-times and the other agents, closest[a] = that
+ * agent (first minimum in time, then id order). safety_ratio_agent = min(ratio), is_collided = any ratio < 1. */
+int lscgpu_safety_audit(lscgpu_engine* e, double record_time_step, double time_step, double* ratio, int32_t* closest);
+
 /* ---- instrumentation -------------------------------------------------------------------------- */
 typedef struct lscgpu_step_stats {
     /* Totals over the steps enqueued since the previous lscgpu_synchronize / lscgpu_replan_batch return. */

@@ -869,6 +869,26 @@ extern "C" int lscgpu_sfc_expand_batch(lscgpu_engine* e, int n, const float* poi
     return LSCGPU_OK;
 }
 
+extern "C" int lscgpu_safety_audit(lscgpu_engine* e, double record_time_step, double time_step, double* ratio, int32_t* closest) {
+    if (!e || !ratio || !closest) return fail(LSCGPU_ERR_ARG, "null argument");
+    if (!(record_time_step > 0.0) || !(time_step > 0.0)) return fail(LSCGPU_ERR_ARG, "record_time_step and time_step must be positive");
+    CU(cudaSetDevice(e->device));
+    int n_samples = 0;
+    for (double ft = 0; ft < time_step - 1e-5; ft += record_time_step) n_samples++;      // src/multi_sync_simulator.cpp:447
+    if (n_samples > 4096) return fail(LSCGPU_ERR_ARG, "record_time_step too small");
+    float* d_pos = nullptr; double* d_ratio = nullptr; int* d_closest = nullptr;
+    CU(cudaMalloc(&d_pos, sizeof(float) * 3 * (size_t)e->N * n_samples));
+    CU(cudaMalloc(&d_ratio, sizeof(double) * e->N));
+    CU(cudaMalloc(&d_closest, sizeof(int) * e->N));
+    launch_safety_audit(e->N, e->d_traj, e->d_consts, e->prm.dt, n_samples, record_time_step, d_pos, d_ratio, d_closest, e->stream);
+    CU(cudaMemcpyAsync(ratio, d_ratio, sizeof(double) * e->N, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(closest, d_closest, sizeof(int) * e->N, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    cudaFree(d_pos); cudaFree(d_ratio); cudaFree(d_closest);
+    CU(cudaGetLastError());
+    return LSCGPU_OK;
+}
+
 extern "C" int lscgpu_get_step_stats(lscgpu_engine* e, lscgpu_step_stats* out) {
     if (!e || !out) return fail(LSCGPU_ERR_ARG, "null argument");
     *out = e->stats;

@@ -115,6 +115,11 @@ void launch_qp_order(int n_local, int a0, const lscgpu_agent_out* out, int* orde
 // commit: every agent's new trajectory becomes traj_curr, advanced state becomes the next resident input
 void launch_commit(int n_agents, const lscgpu_agent_out* out, float* prev_traj, lscgpu_agent_in* in, cudaStream_t s);
 
+// safety audit of the planned step (src/multi_sync_simulator.cpp:446-475)
+void launch_safety_audit(int n_agents, const float* traj, const AgentConstDev* consts, double dt, int n_samples,
+                         double record_time_step, float* sample_pos /*[n_samples][N][3]*/, double* ratio, int* closest,
+                         cudaStream_t s);
+
 // ---- distance field / SFC ---------------------------------------------------------------------------------
 struct DistMapDev {
     int size[3];                   // cells per axis

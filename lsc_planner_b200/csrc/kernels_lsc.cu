@@ -463,6 +463,82 @@ void launch_commit(int n_agents, const lscgpu_agent_out* out, float* prev_traj, 
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Safety audit of the planned step (MultiSyncSimulator::savePlanningResult, src/multi_sync_simulator.cpp:446-475).
+// k_audit_positions: getFutureStateMsg(t).position of every agent at every recorded sub-time (Bernstein sum in double,
+// include/polynomial.hpp:22-45). k_audit_pairs: one block per agent, threads over the other agents, block argmin.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_audit_positions(int n_agents, const float* traj, double dt, int n_samples, double record_time_step,
+                                  float* sample_pos) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_agents * n_samples) return;
+    const int s = t / n_agents, a = t % n_agents;
+    double ft = 0.0;
+    for (int k = 0; k < s; k++) ft += record_time_step;        // the reference accumulates future_time the same way
+    int m = (int)(ft / dt);
+    if (m == kM && ft < kM * dt + 1e-9) m = kM - 1;
+    if (m >= kM) m = kM - 1;
+    const double tn = ft / dt - m;
+    const double binom[6] = {1.0, 5.0, 10.0, 10.0, 5.0, 1.0};
+    const float* c = traj + (size_t)a * kTrajFloats + m * 18;
+    double x = 0.0, y = 0.0, z = 0.0;
+    for (int i = 0; i < 6; i++) {
+        const double b = __dmul_rn(__dmul_rn(binom[i], pow(tn, (double)i)), pow(1.0 - tn, (double)(5 - i)));
+        x = __dadd_rn(x, __dmul_rn((double)c[3 * i], b));
+        y = __dadd_rn(y, __dmul_rn((double)c[3 * i + 1], b));
+        z = __dadd_rn(z, __dmul_rn((double)c[3 * i + 2], b));
+    }
+    float* o = sample_pos + ((size_t)s * n_agents + a) * 3;
+    o[0] = (float)x; o[1] = (float)y; o[2] = (float)z;
+}
+
+__global__ void __launch_bounds__(128) k_audit_pairs(int n_agents, const float* sample_pos, const AgentConstDev* consts,
+                                                     int n_samples, double* ratio, int* closest) {
+    __shared__ double s_r[4];
+    __shared__ int s_j[4], s_s[4];
+    const int a = blockIdx.x, tid = threadIdx.x;
+    const AgentConstDev ca = consts[a];
+    double best = 1e9;
+    int best_j = -1, best_s = 0;
+    for (int s = 0; s < n_samples; s++) {
+        const float* pa = sample_pos + ((size_t)s * n_agents + a) * 3;
+        const F3 p{pa[0], pa[1], pa[2]};
+        for (int j = tid; j < n_agents; j += 128) {
+            if (j == a) continue;
+            const AgentConstDev cj = consts[j];
+            const double dw = (ca.downwash * ca.radius + cj.downwash * cj.radius) / (ca.radius + cj.radius);
+            const float* pj = sample_pos + ((size_t)s * n_agents + j) * 3;
+            F3 d = f3_sub(p, F3{pj[0], pj[1], pj[2]});
+            d.z = (float)__ddiv_rn((double)d.z, dw);
+            const double r = __ddiv_rn(sqrt(f3_dot(d, d)), ca.radius + cj.radius);
+            if (r < best) { best = r; best_j = j; best_s = s; }       // (s, j) ascending per thread: first minimum kept
+        }
+    }
+    // block argmin; ties to the earliest sub-time, then the smallest id (the reference's scan order with a strict <)
+    auto better = [](double r1, int s1, int j1, double r0, int s0, int j0) {
+        return j1 >= 0 && (j0 < 0 || r1 < r0 || (r1 == r0 && (s1 < s0 || (s1 == s0 && j1 < j0))));
+    };
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double orr = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oj = __shfl_xor_sync(0xffffffffu, best_j, o), os = __shfl_xor_sync(0xffffffffu, best_s, o);
+        if (better(orr, os, oj, best, best_s, best_j)) { best = orr; best_j = oj; best_s = os; }
+    }
+    if ((tid & 31) == 0) { s_r[tid >> 5] = best; s_j[tid >> 5] = best_j; s_s[tid >> 5] = best_s; }
+    __syncthreads();
+    if (tid != 0) return;
+    for (int w = 1; w < 4; w++)
+        if (better(s_r[w], s_s[w], s_j[w], best, best_s, best_j)) { best = s_r[w]; best_j = s_j[w]; best_s = s_s[w]; }
+    ratio[a] = best; closest[a] = best_j;
+}
+void launch_safety_audit(int n_agents, const float* traj, const AgentConstDev* consts, double dt, int n_samples,
+                         double record_time_step, float* sample_pos, double* ratio, int* closest, cudaStream_t s) {
+    if (n_agents <= 0 || n_samples <= 0) return;
+    const int n = n_agents * n_samples;
+    k_audit_positions<<<(n + 127) / 128, 128, 0, s>>>(n_agents, traj, dt, n_samples, record_time_step, sample_pos);
+    k_audit_pairs<<<n_agents, 128, 0, s>>>(n_agents, sample_pos, consts, n_samples, ratio, closest);
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // getTerminalSegments (src/traj_optimizer.cpp:541-548) for the operator-level QP entry: float3 norm of
 // goal - position, double division by the nominal velocity.
 // ------------------------------------------------------------------------------------------------------------

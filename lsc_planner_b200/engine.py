@@ -165,6 +165,13 @@ class ReplanEngine:
         A.check(self.lib.lscgpu_fetch(self.h, A.p(out)))
         return out
 
+    def safety_audit(self, record_time_step: float = 0.1, time_step: float = 0.2):
+        """Minimum-distance audit of the step just planned (MultiSyncSimulator::savePlanningResult): per agent the
+        smallest safety ratio over the recorded sub-times and the agent it is attained with."""
+        r = np.zeros(self.n, np.float64); c = np.zeros(self.n, np.int32)
+        A.check(self.lib.lscgpu_safety_audit(self.h, record_time_step, time_step, A.p(r), A.p(c)))
+        return r, c
+
     def reset(self):
         A.check(self.lib.lscgpu_reset(self.h))
 

@@ -96,31 +96,19 @@ private:
         return true;
     }
 
-    static double distBetweenAgents(const point3d& a, const point3d& b, double downwash) {
-        point3d d = a - b;
-        d.z() = (float)(d.z() / downwash);
-        return d.norm();
-    }
-
     void savePlanningResult() {                                                      // :408-511 (safety audit + timing)
-        const double record = param.multisim_record_time_step;
-        double future_time = 0;
-        while (future_time < param.multisim_time_step - SP_EPSILON_FLOAT) {
-            std::vector<point3d> pos(mission.qn);
-            for (int qi = 0; qi < mission.qn; qi++) pos[qi] = agents[qi]->getFutureStateMsg(future_time).position;
+        // minimum distance between agents over the recorded sub-times of the step: O(N^2) pairs, on the device
+        // (lscgpu_safety_audit) from the trajectories the engine just committed
+        if (mission.qn > 1) {
+            std::vector<double> ratio(mission.qn);
+            std::vector<int32_t> closest(mission.qn);
+            if (lscgpu_safety_audit(batch->getEngine().get(), param.multisim_record_time_step, param.multisim_time_step,
+                                    ratio.data(), closest.data()) != LSCGPU_OK)
+                throw std::invalid_argument(std::string("[lscgpu] ") + lscgpu_last_error());
             for (int qi = 0; qi < mission.qn; qi++) {
-                double current = SP_INFINITY;
-                for (int qj = 0; qj < mission.qn; qj++) {
-                    if (qi == qj) continue;
-                    const Agent &ai = mission.agents[qi], &aj = mission.agents[qj];
-                    const double downwash = (ai.downwash * ai.radius + aj.downwash * aj.radius) / (ai.radius + aj.radius);
-                    const double ratio = distBetweenAgents(pos[qi], pos[qj], downwash) / (ai.radius + aj.radius);
-                    if (ratio < current) current = ratio;
-                    if (ratio < safety_ratio_agent) safety_ratio_agent = ratio;
-                }
-                if (current < 1) is_collided = true;
+                if (ratio[qi] < safety_ratio_agent) safety_ratio_agent = ratio[qi];
+                if (ratio[qi] < 1) is_collided = true;
             }
-            future_time += record;
         }
         for (int qi = 0; qi < mission.qn; qi++) {
             planning_time.update(agents[qi]->getPlanningTime());

@@ -226,6 +226,9 @@ int orc_goal_plan(int a, int n, const float* pos, const float* desired, const fl
     return r.mode;
 }
 
+void orc_swarm_safety_audit(void* sv, double record_time_step, double time_step, double* ratio, int* closest) {
+    ((Swarm*)sv)->safety_audit(record_time_step, time_step, ratio, closest);
+}
 void orc_swarm_step(void* sv, int a0, int a1, int threads) { ((Swarm*)sv)->step(a0, a1, threads); }
 void orc_swarm_advance(void* sv) { ((Swarm*)sv)->advance_states(); }
 int orc_swarm_seq(void* sv) { return ((Swarm*)sv)->seq; }

@@ -227,6 +227,39 @@ struct Swarm {
         v = v0;
         ac_ = ((v1 - v0) * 4.0f) * (float)std::pow(prm.dt, -1);
     }
+    // getStateFromControlPoints(...).position at an arbitrary time (include/polynomial.hpp:22-45,63-77)
+    F3 future_position(int a, double t) const {
+        int m = (int)(t / prm.dt);
+        if (m == 5 && t < 5 * prm.dt + 1e-9) m = 4;
+        const double tn = t / prm.dt - m;
+        static const int binom[6] = {1, 5, 10, 10, 5, 1};
+        const F3* c = &traj[(size_t)a * 30 + m * 6];
+        double x = 0, y = 0, z = 0;
+        for (int i = 0; i < 6; i++) {
+            const double b = binom[i] * std::pow(tn, i) * std::pow(1 - tn, 5 - i);
+            x += c[i].x * b; y += c[i].y * b; z += c[i].z * b;
+        }
+        return f3((float)x, (float)y, (float)z);
+    }
+    // minimum-distance audit of MultiSyncSimulator::savePlanningResult (src/multi_sync_simulator.cpp:446-475): for every
+    // recorded sub-time of the step and every agent, the smallest downwash-scaled distance to another agent over the sum of
+    // the radii (include/util.hpp:225-229). ratio[a] / closest[a]: minimum over the sub-times (first minimum kept).
+    void safety_audit(double record_time_step, double time_step, double* ratio, int* closest) const {
+        for (int a = 0; a < N; a++) { ratio[a] = 1e9; closest[a] = -1; }
+        std::vector<F3> p(N);
+        for (double ft = 0; ft < time_step - 1e-5; ft += record_time_step) {
+            for (int a = 0; a < N; a++) p[a] = future_position(a, ft);
+            for (int a = 0; a < N; a++)
+                for (int j = 0; j < N; j++) {
+                    if (j == a) continue;
+                    const double dw = (ac[a].downwash * ac[a].radius + ac[j].downwash * ac[j].radius) / (ac[a].radius + ac[j].radius);
+                    F3 d = p[a] - p[j];
+                    d.z = (float)((double)d.z / dw);
+                    const double r = normf(d) / (ac[a].radius + ac[j].radius);
+                    if (r < ratio[a]) { ratio[a] = r; closest[a] = j; }
+                }
+        }
+    }
     void advance_states() {
         for (int a = 0; a < N; a++) future_state(a, pos[a], vel[a], acc[a]);
     }

@@ -64,6 +64,7 @@ def lib():
         L.orc_swarm_set_traj.argtypes = [C.c_void_p, f32p, C.c_int]
         L.orc_swarm_set_boxes.argtypes = [C.c_void_p, f32p, i32p]
         L.orc_swarm_step.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.orc_swarm_safety_audit.argtypes = [C.c_void_p, C.c_double, C.c_double, f64p, i32p]
         L.orc_swarm_set_goal_mode.argtypes = [C.c_void_p, C.c_int] + [C.c_double] * 5
         L.orc_swarm_set_desired_goals.argtypes = [C.c_void_p, f32p]
         L.orc_swarm_get_goals.argtypes = [C.c_void_p, f32p, i32p]
@@ -261,6 +262,11 @@ class Swarm:
     def goals(self):
         g = np.zeros((self.n, 3), np.float32); k = np.zeros(self.n, np.int32)
         lib().orc_swarm_get_goals(self.h, g, k); return g, k
+
+    def safety_audit(self, record_time_step=0.1, time_step=0.2):
+        """(ratio[n], closest[n]) of the current trajectories over the recorded sub-times of one step."""
+        r = np.zeros(self.n); c = np.zeros(self.n, np.int32)
+        lib().orc_swarm_safety_audit(self.h, record_time_step, time_step, r, c); return r, c
 
     def astar_expansions(self): return int(lib().orc_swarm_astar_expansions(self.h))
 

@@ -130,3 +130,32 @@ def test_simulator_prior_based_forest_matches_oracle(tmp_path, golden_dir):
         n_astar = sw.astar_expansions()
     assert n_astar > 1000                     # the grid planner really ran
     assert "goal planning" in r.stdout
+
+
+@pytest.mark.parametrize("record", [0.1, 0.05, 0.07])
+def test_safety_audit_matches_oracle(record):
+    """lscgpu_safety_audit (the O(N^2) minimum-distance audit of savePlanningResult, on the device) against the oracle on
+    the same trajectories. Dyadic sub-times (t/dt = 0.5, 0.25, ...) make the Bernstein powers exact: identical ratios;
+    otherwise pow() may differ in the last place and positions by one float32 ulp."""
+    import lsc_planner_b200 as L
+    scn = L.scenarios.circle_swap(64)
+    sw = O.Swarm(scn.n, scn.world_min, scn.world_max)
+    sw.set_state(scn.start); sw.set_goals(scn.goal)
+    e = L.ReplanEngine(scn.n, L.Param(world_min=scn.world_min, world_max=scn.world_max), scn.agents)
+    for step in range(25):
+        pos, vel, acc = sw.state()
+        e.set_prev_traj(sw.traj(), sw.seq)
+        sw.step()
+        out = e.replan(pos, vel, acc, scn.goal)
+        if step % 6 == 0:
+            # audit the ORACLE's trajectories on both sides (the engine's own differ by the QP tolerance)
+            e.set_prev_traj(sw.traj(), sw.seq)
+            r_g, c_g = e.safety_audit(record, 0.2)
+            r_o, c_o = sw.safety_audit(record, 0.2)
+            if record in (0.1, 0.05):
+                assert np.array_equal(r_g, r_o) and np.array_equal(c_g, c_o), step
+            else:
+                assert np.abs(r_g - r_o).max() <= 1e-6 and (c_g == c_o).mean() > 0.95
+            assert r_o.min() > 0.99
+        sw.advance()
+    e.close()
