@@ -473,9 +473,10 @@ static int step_device(lscgpu_engine* e) {
     // k_sfc_expand depends on k_predict (flags) only and k_qp_solve is its only consumer: it runs on a side stream
     // beside k_lsc_build
     const bool do_sfc = e->prm.world_use_octomap && n_local > 0;
-    cudaStream_t ss = e->overlap_sfc ? e->stream_sfc : s;
+    const bool side = e->overlap_sfc && !prof;              // profiling mode serialises the kernels
+    cudaStream_t ss = side ? e->stream_sfc : s;
     if (do_sfc) {
-        if (e->overlap_sfc) { CU(cudaEventRecord(e->ev_fork, s)); CU(cudaStreamWaitEvent(ss, e->ev_fork, 0)); }
+        if (side) { CU(cudaEventRecord(e->ev_fork, s)); CU(cudaStreamWaitEvent(ss, e->ev_fork, 0)); }
         if (prof) CU(cudaEventRecord(ev[2], ss));
         SfcLaunch sl{};
         sl.n = n_local; sl.dm = e->dm; sl.res = e->prm.world_resolution;
@@ -485,7 +486,7 @@ static int step_device(lscgpu_engine* e) {
         sl.boxes = e->d_boxes; sl.init_sfc = e->d_init_sfc; sl.flags = e->d_flags;
         launch_sfc_expand(sl, ss); launches++;
         if (prof) CU(cudaEventRecord(ev[3], ss));
-        if (e->overlap_sfc) CU(cudaEventRecord(e->ev_join, ss));
+        if (side) CU(cudaEventRecord(e->ev_join, ss));
     } else if (prof) {
         CU(cudaEventRecord(ev[2], s)); CU(cudaEventRecord(ev[3], s));
     }
@@ -521,7 +522,7 @@ static int step_device(lscgpu_engine* e) {
     if (groups == 1) {
         if (n_local > 0 && e->N > 1) { ll.first = 0; ll.count = n_local; launch_lsc_build(ll, s); launches++; }
         if (prof) CU(cudaEventRecord(ev[4], s));
-        if (do_sfc && e->overlap_sfc) CU(cudaStreamWaitEvent(s, e->ev_join, 0));
+        if (do_sfc && side) CU(cudaStreamWaitEvent(s, e->ev_join, 0));
         if (prof) CU(cudaEventRecord(ev[5], s));
         if (n_local > 0) { ql.first = 0; ql.n_problems = n_local; launch_qp_solve(ql, s); launches++; }
     } else {
@@ -536,7 +537,7 @@ static int step_device(lscgpu_engine* e) {
             cudaStream_t sg = e->stream_grp[g];
             CU(cudaStreamWaitEvent(sg, e->ev_lsc[0], 0));
             ll.first = first; ll.count = cnt; launch_lsc_build(ll, sg); launches++;
-            if (do_sfc && e->overlap_sfc) CU(cudaStreamWaitEvent(sg, e->ev_join, 0));
+            if (do_sfc && side) CU(cudaStreamWaitEvent(sg, e->ev_join, 0));
             ql.first = first; ql.n_problems = cnt; launch_qp_solve(ql, sg); launches++;
             CU(cudaEventRecord(e->ev_qp[g], sg));
             first += cnt;
@@ -586,7 +587,7 @@ static int finish_steps(lscgpu_engine* e) {
             // ev: begin, predict|, sfc[ ]sfc (side stream when overlapped), lsc|, join|, qp|, exchange|, commit|
             st.ms_predict += ms[0]; st.ms_sfc += ms[2]; st.ms_qp += ms[5]; st.ms_exchange += ms[6]; st.ms_commit += ms[7];
             float lsc = 0.f;
-            CU(cudaEventElapsedTime(&lsc, e->overlap_sfc ? ev[1] : ev[3], ev[4]));
+            CU(cudaEventElapsedTime(&lsc, ev[3], ev[4]));
             st.ms_lsc += lsc;
         }
     }

@@ -43,14 +43,6 @@ constexpr int LD = 39;          // row pitch of Q and R (odd: row-per-lane acces
 constexpr double kFeasTol = 1e-6;
 constexpr double kZeroTol = 1e-13;
 
-struct SelectedRow {
-    int nnz;
-    int idx[3];
-    int axis[3], var[3];      // idx = axis * 30 + var
-    double a[3];
-    double b;
-};
-
 struct QpShared {
     double Q[NR * LD];          // columns 0..q-1: orthonormal basis of the active normals
     double R[NR * LD];          // upper triangle, row-major
@@ -64,7 +56,7 @@ struct QpShared {
     int stop;                   // 0 run, 1 finished/failed (set by warp 0)
     int open_count[2];          // pairs in the open list of the current / next chunk
     int act[NR];
-    SelectedRow sel;
+    double vacc[NR + 1];        // whitened step accumulated by warp 0 since the last block-wide update of x
 };
 
 struct Best {
@@ -117,13 +109,22 @@ __device__ __forceinline__ void load_pair(const RowRec* rows, int slot, float4& 
     r6[0] = a.x; r6[1] = a.y; r6[2] = b.x; r6[3] = b.y; r6[4] = c.x; r6[5] = c.y;
 }
 
-__device__ __forceinline__ void decode_row(QpShared& S, int id, int n_obs, const RowRec* rows, const int* kept,
-                                           double vel_coef, double acc_coef, const double* lb,
-                                           const double* ub, const double* vmax, const double* amax) {
-    SelectedRow& r = S.sel;
+// The selected row in registers, decoded redundantly by every lane of warp 0 (uniform branches, no shared-memory
+// round trip): at most three non-zeros a[t] at variables idx[t] = axis * 30 + var, right-hand side b.
+struct RowRegs {
+    int nnz;
+    int idx[3];
+    double a[3];
+    double b;
+};
+__device__ __forceinline__ RowRegs decode_row(int id, int n_obs, const RowRec* rows, const int* kept, double vel_coef,
+                                              double acc_coef, const double* lb, const double* ub, const double* vmax,
+                                              const double* amax) {
+    RowRegs r;
+    r.idx[1] = r.idx[2] = 0; r.a[1] = r.a[2] = 0.0;
     if (id < 180) {
         const int var = id >> 1, side = id & 1;
-        const int k = var / kAx, mi = var % kAx, m = mi / 6;
+        const int k = var / kAx, m = (var % kAx) / 6;
         r.nnz = 1; r.idx[0] = var;
         if (side == 0) { r.a[0] = 1.0; r.b = lb[m * 3 + k]; }
         else { r.a[0] = -1.0; r.b = -ub[m * 3 + k]; }
@@ -141,20 +142,16 @@ __device__ __forceinline__ void decode_row(QpShared& S, int id, int n_obs, const
             r.a[0] = sg * acc_coef; r.a[1] = -2.0 * sg * acc_coef; r.a[2] = sg * acc_coef; r.b = -amax[k];
         }
     } else {
-        const int e = id - kFixedRows, slot = e / 6, i = e % 6, m = kept[slot] / n_obs, vi = m * 6 + i;
+        const int e = id - kFixedRows, slot = e / 6, i = e % 6;
+        const int kp = kept[slot];
+        const int m = (kp >= n_obs) + (kp >= 2 * n_obs) + (kp >= 3 * n_obs) + (kp >= 4 * n_obs), vi = m * 6 + i;
         const RowRec& rec = rows[slot];
         r.nnz = 3;
         r.idx[0] = vi; r.idx[1] = kAx + vi; r.idx[2] = 2 * kAx + vi;
         r.a[0] = (double)rec.ax; r.a[1] = (double)rec.ay; r.a[2] = (double)rec.az;
         r.b = rec.rhs[i];
     }
-    for (int t = 0; t < r.nnz; t++) { r.axis[t] = r.idx[t] / kAx; r.var[t] = r.idx[t] % kAx; }
-}
-
-__device__ __forceinline__ double selected_slack(const QpShared& S) {
-    double s = -S.sel.b;
-    for (int t = 0; t < S.sel.nnz; t++) s += S.sel.a[t] * S.x[S.sel.idx[t]];
-    return s;
+    return r;
 }
 
 // remove active row l: delete column l of R, restore the triangle with Givens rotations (rows j, j+1 of R,
@@ -173,7 +170,7 @@ __device__ __forceinline__ void drop_active(QpShared& S, int& q, int l, int lane
         const double a = S.R[j * LD + j], b = S.R[(j + 1) * LD + j];
         __syncwarp();
         if (b == 0.0) continue;
-        const double h = hypot(a, b), c = a / h, s = b / h;
+        const double ih = 1.0 / sqrt(a * a + b * b), c = a * ih, s = b * ih;       // entries of R are <= 1: no overflow concerns
         for (int k = j + lane; k < q; k += 32) {
             const double t1 = S.R[j * LD + k], t2 = S.R[(j + 1) * LD + k];
             S.R[j * LD + k] = c * t1 + s * t2;
@@ -275,9 +272,6 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 512 ? 1 : 512 / kThreads
     }
     // warp 0: per-lane index constants of the factorisation update (no divisions in the loop)
     const int c_axis0 = lane / kFree, c_col0 = lane % kFree;      // whitened coordinate c = lane
-    int x_axis[3], x_var[3];
-#pragma unroll
-    for (int h = 0; h < 3; h++) { const int e = min(lane + 32 * h, kNv - 1); x_axis[h] = e / kAx; x_var[h] = e % kAx; }
     int q = 0, iters = 0, status = LSCGPU_QP_OK;
     unsigned long long pairs_evaluated = 0, passes = 0;
     long long price_cycles = 0;
@@ -371,33 +365,45 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 512 ? 1 : 512 / kThreads
         if (warp == 0) {
             bool done = false;          // set when the solve must stop (failure)
             TICK();
+            S.vacc[lane] = 0.0;
+            if (lane + 32 < NR + 1) S.vacc[lane + 32] = 0.0;
+            __syncwarp();
             do {
                 {
                     bool dup = false;
                     for (int k = lane; k < q; k += 32) dup |= S.act[k] == best.id;
                     if (__any_sync(0xffffffffu, dup)) { status = LSCGPU_QP_MAXITER; done = true; break; }   // numerical breakdown
                 }
-                if (lane == 0) decode_row(S, best.id, n_obs, rows, kept, vel_coef, acc_coef, S.lb, S.ub, S.vmax, S.amax);
-                __syncwarp();
-                // whitened normal  nv = (G (+) G (+) G)^T a, normalised
-                double part = 0.0;
+                const RowRegs row = decode_row(best.id, n_obs, rows, kept, vel_coef, acc_coef, S.lb, S.ub, S.vmax, S.amax);
+                // whitened normal  nv = (G (+) G (+) G)^T a: lane c owns coordinates c and c + 32 (axis = c / 13)
+                double part = 0.0, nv_reg[2];
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     const int c = lane + 32 * h;
+                    nv_reg[h] = 0.0;
                     if (c < NR) {
                         const int k = h == 0 ? c_axis0 : 2, cc = h == 0 ? c_col0 : c - 2 * kFree;
                         double sacc = 0.0;
-                        for (int t = 0; t < S.sel.nnz; t++)
-                            if (S.sel.axis[t] == k) sacc += S.sel.a[t] * __ldg(Gt + S.sel.var[t] * kFree + cc);
-                        S.nv[c] = sacc;
+#pragma unroll
+                        for (int t = 0; t < 3; t++) {
+                            const int ax_t = row.idx[t] / kAx;
+                            if (t < row.nnz && ax_t == k) sacc += row.a[t] * __ldg(Gt + (row.idx[t] - ax_t * kAx) * kFree + cc);
+                        }
+                        nv_reg[h] = sacc;
                         part += sacc * sacc;
                     }
                 }
                 const double nrm_len = sqrt(warp_sum(part));
                 if (!(nrm_len > 0.0)) { status = LSCGPU_QP_INFEASIBLE; done = true; break; }
                 const double inv_len = 1.0 / nrm_len;
-                __syncwarp();
-                for (int c = lane; c < NR; c += 32) S.nv[c] *= inv_len;
+                S.nv[lane] = nv_reg[0] * inv_len;
+                if (lane + 32 < NR) S.nv[lane + 32] = nv_reg[1] * inv_len;
+                // slack of the selected row (normalised); along the step it grows by t |z|^2 (a . G z = |G^T a| nv . z and
+                // nv . z = z . z for the projection z of nv), so x itself is only brought up to date once per update
+                double slack = -row.b;
+#pragma unroll
+                for (int t = 0; t < 3; t++) if (t < row.nnz) slack += row.a[t] * S.x[row.idx[t]];
+                slack *= inv_len;
                 __syncwarp();
                 double lam_p = 0.0;
                 TOCK(1);
@@ -481,7 +487,6 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 512 ? 1 : 512 / kThreads
                         if (ol >= 0 && (l < 0 || ot < t1 || (ot == t1 && ol < l))) { t1 = ot; l = ol; }
                     }
                     const bool primal = zz > kZeroTol;
-                    const double slack = selected_slack(S) * inv_len;
                     double t2 = primal ? -slack / zz : INFINITY;
                     if (t2 < 0.0) t2 = 0.0;
                     const double t = fmin(t1, t2);
@@ -491,19 +496,9 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 512 ? 1 : 512 / kThreads
                     TOCK(3);
                     if (!primal) { drop_active(S, q, l, lane); TOCK(6); continue; }
                     if (lane == 0) S.travelled += t * sqrt(zz) * (1.0 + 1e-9) + 1e-13;
-#pragma unroll
-                    for (int h = 0; h < 3; h++) {
-                        const int e = lane + 32 * h;
-                        if (e < kNv) {
-                            const double* g = Gt + x_var[h] * kFree;
-                            const double* zk = S.z + x_axis[h] * kFree;
-                            double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-                            for (int c = 0; c + 1 < kFree; c += 2) { s0 += __ldg(g + c) * zk[c]; s1 += __ldg(g + c + 1) * zk[c + 1]; }
-                            s0 += __ldg(g + kFree - 1) * zk[kFree - 1];
-                            S.x[e] += t * (s0 + s1);
-                        }
-                    }
+                    S.vacc[lane] += t * S.z[lane];
+                    if (lane + 32 < NR) S.vacc[lane + 32] += t * S.z[lane + 32];
+                    slack += t * zz;
                     __syncwarp();
                     TOCK(4);
                     if (t2 <= t1) {
@@ -527,6 +522,18 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 512 ? 1 : 512 / kThreads
                 }
             } while (false);
             if (done && lane == 0) S.stop = 1;
+        }
+        __syncthreads();
+        // x += (G (+) G (+) G) vacc by the whole block: element e = axis * 30 + var, 13 products each
+        for (int e = tid; e < kNv; e += kThreads) {
+            const int k = e / kAx;
+            const double* g = Gt + (e - k * kAx) * kFree;
+            const double* va = S.vacc + k * kFree;
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int c = 0; c + 1 < kFree; c += 2) { s0 += __ldg(g + c) * va[c]; s1 += __ldg(g + c + 1) * va[c + 1]; }
+            s0 += __ldg(g + kFree - 1) * va[kFree - 1];
+            S.x[e] += s0 + s1;
         }
         __syncthreads();
         if (S.stop) break;
