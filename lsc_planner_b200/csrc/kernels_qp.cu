@@ -429,18 +429,29 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 512 ? 1 : 512 / kThreads
                                 S.d[k] += sdot;
                             }
                             __syncwarp();
-                            double zp = 0.0;
-                            for (int r = lane; r < NR; r += 32) {         // lane r: row r of Q against the coefficients
-                                double s0 = 0.0, s1 = 0.0;
+                            // lane r: rows r and r + 32 of Q against the coefficients, both in one pass over k
+                            // (lanes without a second row read row 38 and drop the result)
+                            double zp;
+                            {
+                                const int r2 = min(lane + 32, NR - 1);
+                                const double* q1 = S.Q + lane * LD;
+                                const double* q2 = S.Q + r2 * LD;
+                                double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
                                 int k = 0;
                                 for (; k + 1 < q; k += 2) {
-                                    s0 += S.Q[r * LD + k] * S.tmp[k];
-                                    s1 += S.Q[r * LD + k + 1] * S.tmp[k + 1];
+                                    const double t0 = S.tmp[k], t1 = S.tmp[k + 1];
+                                    a0 += q1[k] * t0; a1 += q1[k + 1] * t1;
+                                    b0 += q2[k] * t0; b1 += q2[k + 1] * t1;
                                 }
-                                if (k < q) s0 += S.Q[r * LD + k] * S.tmp[k];
-                                const double zr = S.z[r] - (s0 + s1);
-                                S.z[r] = zr;
-                                zp += zr * zr;
+                                if (k < q) { const double t0 = S.tmp[k]; a0 += q1[k] * t0; b0 += q2[k] * t0; }
+                                const double z1 = S.z[lane] - (a0 + a1);
+                                S.z[lane] = z1;
+                                zp = z1 * z1;
+                                if (lane + 32 < NR) {
+                                    const double z2 = S.z[lane + 32] - (b0 + b1);
+                                    S.z[lane + 32] = z2;
+                                    zp += z2 * z2;
+                                }
                             }
                             const double zz_new = warp_sum(zp);
                             __syncwarp();
@@ -453,6 +464,8 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 512 ? 1 : 512 / kThreads
                     TOCK(2);
                     // rr = R^-1 d (change of the active multipliers per unit step): column-oriented back
                     // substitution, rr[k] lives in lane k's register while q <= 32
+                    double t1 = INFINITY;
+                    int l = -1;
                     if (q <= 32) {
                         double rk = lane < q ? S.d[lane] : 0.0;
                         for (int c = q - 1; c >= 0; c--) {
@@ -461,6 +474,24 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 512 ? 1 : 512 / kThreads
                             if (lane == c) rk = piv;
                         }
                         if (lane < q) S.rr[lane] = rk;
+                        // ratio test over the active multipliers: lane k holds candidate k; warp minimum of the ratio through
+                        // its order-preserving 64-bit key (two 32-bit min reductions), ties to the smallest index
+                        const bool cand = lane < q && rk > kZeroTol;
+                        unsigned long long key = ~0ull;
+                        if (cand) {
+                            const unsigned long long bits = (unsigned long long)__double_as_longlong(S.lam[lane] / rk);
+                            key = bits ^ ((bits >> 63) ? ~0ull : 0x8000000000000000ull);
+                        }
+                        const unsigned hi = (unsigned)(key >> 32);
+                        const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+                        const unsigned lo = hi == mhi ? (unsigned)key : 0xffffffffu;
+                        const unsigned mlo = __reduce_min_sync(0xffffffffu, lo);
+                        const unsigned win = __ballot_sync(0xffffffffu, cand && hi == mhi && (unsigned)key == mlo);
+                        if (win) {
+                            l = __ffs(win) - 1;
+                            const unsigned long long mk = ((unsigned long long)mhi << 32) | mlo;
+                            t1 = __longlong_as_double((long long)(mk ^ ((mk >> 63) ? 0x8000000000000000ull : ~0ull)));
+                        }
                     } else {
                         for (int k = lane; k < q; k += 32) S.rr[k] = S.d[k];
                         for (int c = q - 1; c >= 0; c--) {
@@ -470,22 +501,20 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 512 ? 1 : 512 / kThreads
                             for (int k = lane; k < c; k += 32) S.rr[k] -= S.R[k * LD + c] * piv;
                             if (lane == 0) S.rr[c] = piv;
                         }
+                        __syncwarp();
+                        for (int k = lane; k < q; k += 32)
+                            if (S.rr[k] > kZeroTol) {
+                                const double t = S.lam[k] / S.rr[k];
+                                if (t < t1) { t1 = t; l = k; }
+                            }
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            const double ot = __shfl_xor_sync(0xffffffffu, t1, o);
+                            const int ol = __shfl_xor_sync(0xffffffffu, l, o);
+                            if (ol >= 0 && (l < 0 || ot < t1 || (ot == t1 && ol < l))) { t1 = ot; l = ol; }
+                        }
                     }
                     __syncwarp();
-                    // ratio test over the active multipliers
-                    double t1 = INFINITY;
-                    int l = -1;
-                    for (int k = lane; k < q; k += 32)
-                        if (S.rr[k] > kZeroTol) {
-                            const double t = S.lam[k] / S.rr[k];
-                            if (t < t1) { t1 = t; l = k; }
-                        }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        const double ot = __shfl_xor_sync(0xffffffffu, t1, o);
-                        const int ol = __shfl_xor_sync(0xffffffffu, l, o);
-                        if (ol >= 0 && (l < 0 || ot < t1 || (ot == t1 && ol < l))) { t1 = ot; l = ol; }
-                    }
                     const bool primal = zz > kZeroTol;
                     double t2 = primal ? -slack / zz : INFINITY;
                     if (t2 < 0.0) t2 = 0.0;
