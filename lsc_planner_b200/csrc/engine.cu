@@ -85,6 +85,7 @@ struct lscgpu_engine {
     // device buffers
     QpTablesDev* d_tables = nullptr;
     AgentConstDev* d_consts = nullptr;
+    float2* d_rdw = nullptr;         // [N] (radius, downwash * radius) in float: all the culling pass of k_lsc_build needs
     lscgpu_agent_in* d_in = nullptr;
     lscgpu_agent_out* d_out = nullptr;     // [n_out] gather buffer
     int n_out = 0;
@@ -147,6 +148,7 @@ extern "C" void lscgpu_destroy(lscgpu_engine* e) {
     cudaSetDevice(e->device);
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     free_rows(e);
+    cudaFree(e->d_rdw);
     cudaFree(e->d_tables); cudaFree(e->d_consts); cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_traj);
     cudaFree(e->d_pred); cudaFree(e->d_predT); cudaFree(e->d_predZs); cudaFree(e->d_boxes); cudaFree(e->d_state9); cudaFree(e->d_goal3);
     cudaFree(e->d_last_cost); cudaFree(e->d_ts); cudaFree(e->d_flags); cudaFree(e->d_init_sfc); cudaFree(e->d_goal_kind); cudaFree(e->d_counters);
@@ -261,6 +263,12 @@ extern "C" int lscgpu_create(const lscgpu_params* p, int n_agents, const lscgpu_
     const size_t N = n_agents;
     CUB(cudaMalloc(&e->d_consts, sizeof(AgentConstDev) * N));
     CUB(cudaMemcpy(e->d_consts, cd.data(), sizeof(AgentConstDev) * N, cudaMemcpyHostToDevice));
+    {
+        std::vector<float2> rdw(N);
+        for (size_t a = 0; a < N; a++) rdw[a] = make_float2((float)cd[a].radius, (float)(cd[a].downwash * cd[a].radius));
+        CUB(cudaMalloc(&e->d_rdw, sizeof(float2) * N));
+        CUB(cudaMemcpy(e->d_rdw, rdw.data(), sizeof(float2) * N, cudaMemcpyHostToDevice));
+    }
     CUB(cudaMalloc(&e->d_in, sizeof(lscgpu_agent_in) * N));
     CUB(cudaMalloc(&e->d_out, sizeof(lscgpu_agent_out) * N));
     CUB(cudaMalloc(&e->d_traj, sizeof(float) * N * kTrajFloats));
@@ -500,7 +508,7 @@ static int step_device(lscgpu_engine* e) {
     LscLaunch ll{};
     ll.n_agents = e->N; ll.n_pad = e->n_pad; ll.a0 = e->a0; ll.n_local = n_local;
     ll.order = ordered ? e->d_order : nullptr;
-    ll.pred = e->d_pred; ll.predT = e->d_predT; ll.predZs = e->d_predZs; ll.consts = e->d_consts; ll.T = e->d_tables;
+    ll.pred = e->d_pred; ll.predT = e->d_predT; ll.predZs = e->d_predZs; ll.consts = e->d_consts; ll.rdw = e->d_rdw; ll.T = e->d_tables;
     ll.state9 = e->d_state9; ll.goal3 = e->d_goal3; ll.ts = e->d_ts;
     ll.sphere = e->d_sphere; ll.reach = e->d_reach;
     ll.rows = e->d_rows; ll.P_pad = e->P_pad;

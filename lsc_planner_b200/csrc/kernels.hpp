@@ -50,6 +50,7 @@ struct LscLaunch {
     const float* predT;            // [90][n_pad]
     const float* predZs;           // [30][n_pad]
     const AgentConstDev* consts;
+    const float2* rdw;             // [N] (radius, downwash * radius) as float, for the culling pass
     const QpTablesDev* T;
     const double* state9;          // [N][9]
     const double* goal3;

@@ -194,9 +194,8 @@ void launch_goal_plan(const GoalLaunch& L, cudaStream_t s) { k_goal_plan<<<L.n_a
 //     p appended to the agent's kept list together with the smallest whitened slack of its rows at the unconstrained
 //     QP minimiser x0 (the QP kernel does not look at a pair again until the iterate has travelled that far).
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kLscThreads = 128;
 
-template <int kMinBlocks>
+template <int kLscThreads, int kMinBlocks>
 __global__ void __launch_bounds__(kLscThreads, kMinBlocks) k_lsc_build(LscLaunch L) {
     __shared__ float own[kTrajFloats];
     __shared__ float own_zs[30];
@@ -228,6 +227,7 @@ __global__ void __launch_bounds__(kLscThreads, kMinBlocks) k_lsc_build(LscLaunch
     __syncthreads();
 
     const AgentConstDev ca = L.consts[a];
+    const float ra_f = (float)ca.radius, rdwa_f = (float)(ca.downwash * ca.radius);
     const double dw_self_a = (ca.downwash * ca.radius + ca.downwash * ca.radius) / (ca.radius + ca.radius);
     RowRec* rows_out = L.rows + (size_t)al * L.P_pad;
     int* kept_out = L.kept + (size_t)al * L.P_pad;
@@ -243,11 +243,11 @@ __global__ void __launch_bounds__(kLscThreads, kMinBlocks) k_lsc_build(LscLaunch
         for (int m = 0; m < kM; m++) keep[m] = false;
         if (jj < n_obs) {
             const int j = jj < a ? jj : jj + 1;
-            const AgentConstDev cj = L.consts[j];
-            const float dw = (float)((ca.downwash * ca.radius + cj.downwash * cj.radius) / (ca.radius + cj.radius));
-            const float inv_dw = 1.0f / dw;
+            // downwash ratio of the pair in float: the test below is conservative by 1e-4 relative, float rounding is 1e-7
+            const float2 rj = L.rdw[j];
+            const float inv_dw = (ra_f + rj.x) / (rdwa_f + rj.y);
             const float smax = fmaxf(1.0f, inv_dw);
-            const float rho = (float)(ca.radius + cj.radius);
+            const float rho = ra_f + rj.x;
 #pragma unroll
             for (int m = 0; m < kM; m++) {
                 const float4 so = own_sphere[m];
@@ -353,10 +353,12 @@ __global__ void __launch_bounds__(kLscThreads, kMinBlocks) k_lsc_build(LscLaunch
 void launch_lsc_build(const LscLaunch& L, cudaStream_t s) {
     const int n_obs = L.n_agents - 1;
     if (n_obs <= 0 || L.count <= 0) return;
-    static const int occ = getenv("LSCGPU_LSC_OCC") ? atoi(getenv("LSCGPU_LSC_OCC")) : 2;
-    if (occ >= 4) k_lsc_build<4><<<L.count, kLscThreads, 0, s>>>(L);
-    else if (occ == 3) k_lsc_build<3><<<L.count, kLscThreads, 0, s>>>(L);
-    else k_lsc_build<2><<<L.count, kLscThreads, 0, s>>>(L);
+    // 128 threads x 2 blocks per SM (231 registers) or 256 threads x 1 block: same occupancy, the larger block halves one
+    // agent's latency (what matters when few agents are local), the smaller one packs the tail better
+    static const int thr = getenv("LSCGPU_LSC_THREADS") ? atoi(getenv("LSCGPU_LSC_THREADS")) : 0;
+    const int threads = thr ? thr : 256;
+    if (threads >= 256) k_lsc_build<256, 1><<<L.count, 256, 0, s>>>(L);
+    else k_lsc_build<128, 2><<<L.count, 128, 0, s>>>(L);
 }
 
 // ------------------------------------------------------------------------------------------------------------

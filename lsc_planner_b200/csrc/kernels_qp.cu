@@ -72,14 +72,27 @@ __device__ __forceinline__ void consider(Best& b, const QpShared& S, int q, doub
     const double mu = scale < INFINITY ? slack * scale : -INFINITY;   // zero normal with positive rhs: infeasible row
     if (mu < b.mu) { b.mu = mu; b.id = id; }
 }
+// most violated candidate of the warp (smallest mu, ties to the smallest row id): three 32-bit `redux.min` on an
+// order-preserving key of the double instead of five shuffle rounds
 __device__ __forceinline__ Best warp_argmin(Best b) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double mu = __shfl_xor_sync(0xffffffffu, b.mu, o);
-        const int id = __shfl_xor_sync(0xffffffffu, b.id, o);
-        if (id >= 0 && (b.id < 0 || mu < b.mu || (mu == b.mu && id < b.id))) { b.mu = mu; b.id = id; }
+    unsigned long long key = ~0ull;
+    if (b.id >= 0) {
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(b.mu);
+        key = bits ^ ((bits >> 63) ? ~0ull : 0x8000000000000000ull);
     }
-    return b;
+    const unsigned hi = (unsigned)(key >> 32);
+    const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned lo = hi == mhi ? (unsigned)key : 0xffffffffu;
+    const unsigned mlo = __reduce_min_sync(0xffffffffu, lo);
+    const bool win = b.id >= 0 && hi == mhi && (unsigned)key == mlo;
+    const unsigned wid = __reduce_min_sync(0xffffffffu, win ? (unsigned)b.id : 0xffffffffu);
+    Best r{0.0, -1};
+    if (wid != 0xffffffffu) {
+        const unsigned long long mk = ((unsigned long long)mhi << 32) | mlo;
+        r.mu = __longlong_as_double((long long)(mk ^ ((mk >> 63) ? 0x8000000000000000ull : ~0ull)));
+        r.id = (int)wid;
+    }
+    return r;
 }
 
 // one (obstacle, segment) pair: up to 6 rows. Returns the smallest whitened slack of the pair's rows.
@@ -351,12 +364,10 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 512 ? 1 : 512 / kThreads
         best = warp_argmin(best);
         if (lane == 0) { S.best_mu[warp] = best.mu; S.best_id[warp] = best.id; }
         __syncthreads();
-#pragma unroll
-        for (int w = 0; w < kWarps; w++) {
-            const double mu = S.best_mu[w];
-            const int id = S.best_id[w];
-            if (w == 0) { best.mu = mu; best.id = id; }
-            else if (id >= 0 && (best.id < 0 || mu < best.mu || (mu == best.mu && id < best.id))) { best.mu = mu; best.id = id; }
+        {   // every warp reduces the per-warp results again (lane w holds warp w's): same answer in all threads
+            Best wb{0.0, -1};
+            if (lane < kWarps) { wb.mu = S.best_mu[lane]; wb.id = S.best_id[lane]; }
+            best = warp_argmin(wb);
         }
         if (tid == 0) price_cycles += clock64() - t_price;
         if (best.id < 0) break;                 // no row violated beyond the tolerance anywhere: done (block-uniform)

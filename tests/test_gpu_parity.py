@@ -285,3 +285,67 @@ def test_swarm_property_n256():
     assert e.planner_seq == sw.seq
     assert sw.qp()["status"][3] == 0
     assert np.abs(o2["traj"][3] - sw.traj()[3]).max() <= 1e-6
+
+
+def _full_size_check(workload, agents, steps, n_sample):
+    """BASELINE configs 4 / 5 at full size: closed loop on the device for `steps` steps, then (i) size-independent
+    properties of EVERY agent's solution (continuity, terminal stop, dynamic limits, SFC boxes, LSC rows of spot
+    agents) and (ii) the next step of a sample of agents — the most crowded ones and a spread over the swarm —
+    re-planned by the oracle from the very same inputs."""
+    import bench
+    import lsc_planner_b200 as L
+    scn, bt = bench.make_scenario(workload, agents)
+    if scn is None:
+        tmp = L.ReplanEngine(2, L.Param(world_use_octomap=True)); tmp.set_octomap_file(bt); dm = tmp.distmap()
+        scn = L.scenarios.random_forest(agents, dm["sqdist"], dm["off"], seed=0); tmp.close()
+    n = scn.n
+    e = L.ReplanEngine(n, L.Param(world_min=scn.world_min, world_max=scn.world_max, world_use_octomap=True), scn.agents)
+    e.set_octomap_file(bt)
+    e.set_states(scn.start); e.set_goals(scn.goal)
+    e.replan_resident(steps)
+    out = e.fetch().copy()
+    boxes, _ = e.get_sfc()
+    ok = out["qp_status"] == 0
+    assert ok.mean() > 0.85                                       # static goals: some crowded agents are infeasible (as in the oracle)
+    x = out["traj"].astype(np.float64)[ok]
+    vel = (x[:, :, 1:] - x[:, :, :-1]) * 25.0
+    acc = (x[:, :, 2:] - 2 * x[:, :, 1:-1] + x[:, :, :-2]) * 500.0
+    assert np.abs(vel[:, 1:]).max() <= 1.0 + 1e-4 and np.abs(acc[:, 1:]).max() <= 2.0 + 2e-2
+    assert np.abs(x[:, 1:, 0] - x[:, :-1, 5]).max() <= 1e-6
+    assert np.abs(x[:, 4, 5] - x[:, 4, 4]).max() <= 1e-6 and np.abs(x[:, 4, 5] - x[:, 4, 3]).max() <= 1e-6
+    b = boxes.astype(np.float64)[ok]                              # [n][5][6] = min xyz, max xyz of every segment's box
+    inside_lo = x - b[:, :, None, :3]; inside_hi = b[:, :, None, 3:] - x
+    inside_lo[:, 0, :3] = 0; inside_hi[:, 0, :3] = 0              # the first three points are fixed by the state
+    assert inside_lo.min() >= -4e-6 and inside_hi.min() >= -4e-6       # 1e-6 band + float32 rounding at |x| ~ 17 m
+    # (ii) oracle re-plan of sampled agents, one step further, from identical inputs
+    crowded = np.argsort(-out["lsc_pairs_kept"])[:n_sample // 2]
+    spread = np.linspace(0, n - 1, n_sample - len(crowded)).astype(int)
+    sample = sorted(set(crowded.tolist()) | set(spread.tolist()))
+    pos, vel_, acc_ = out["next_position"].copy(), out["next_velocity"].copy(), out["next_acceleration"].copy()
+    seq = e.planner_seq
+    sw = bench.oracle_swarm(scn, bt)
+    o2 = e.replan(pos, vel_, acc_, scn.goal).copy()
+    boxes2, _ = e.get_sfc()
+    worst = 0.0
+    for a in sample:
+        sw.set_state(pos, vel_, acc_); sw.set_goals(scn.goal)
+        sw.set_traj(out["traj"], seq); sw.set_boxes(boxes, np.zeros(n, np.int32))
+        sw.step(a, a + 1)
+        q = sw.qp()
+        assert q["status"][a] == o2["qp_status"][a], (a, q["status"][a], o2["qp_status"][a])
+        assert np.array_equal(sw.boxes()[a].view(np.uint32), boxes2[a].view(np.uint32)), a
+        if q["status"][a] == 0:
+            d = float(np.abs(o2["traj"][a] - sw.traj()[a]).max())
+            worst = max(worst, d)
+            assert d <= (2e-5 if q["maxviol"][a] > 1e-9 else 4e-6), (a, d, q["maxviol"][a])   # 2 float32 ulps at 17 m
+            assert abs(o2["qp_cost"][a] - q["cost"][a]) <= 1e-5 * max(1.0, abs(q["cost"][a]))
+    e.close()
+    return worst
+
+
+def test_full_size_random_forest_512():
+    _full_size_check("random_forest", 512, 30, 16)
+
+
+def test_full_size_circle_forest_1024():
+    _full_size_check("circle_forest", 1024, 60, 16)
