@@ -218,10 +218,35 @@ struct GoalObstacle {
     point3d prev_traj_first_end, prev_traj_last_end;        // obs_prev_trajs[oi][0][n], [M-1][n]
 };
 
+// The distance-field part of the occupancy grid (src/grid_based_planner.cpp:103-117) depends only on the map and the
+// agent radius: computed once per radius and copied, instead of 18 000 getDistance calls per agent per step.
+struct StaticGridCache {
+    std::vector<std::pair<double, std::vector<uint8_t>>> by_radius;
+    const std::vector<uint8_t>* find(double radius) const {
+        for (const auto& e : by_radius) if (e.first == radius) return &e.second;
+        return nullptr;
+    }
+};
+
 class GridBasedPlanner {
 public:
-    GridBasedPlanner(const HostDistMap* _distmap, const Mission& _mission, const Param& _param)
-        : distmap(_distmap), mission(_mission), param(_param) {}
+    GridBasedPlanner(const HostDistMap* _distmap, const Mission& _mission, const Param& _param,
+                     const StaticGridCache* _cache = nullptr)
+        : distmap(_distmap), mission(_mission), param(_param), cache(_cache) {}
+
+    // the static occupancy of one radius, for StaticGridCache (same arithmetic as updateGridMap)
+    std::vector<uint8_t> staticGrid(double agent_radius) {
+        updateGridInfo();
+        std::vector<uint8_t> g((size_t)dim[0] * dim[1] * dim[2], GP_EMPTY);
+        if (distmap != nullptr) {
+            const float grid_margin = (float)param.grid_margin;
+            for (int i = 0; i < dim[0]; i++)
+                for (int j = 0; j < dim[1]; j++)
+                    for (int k = 0; k < dim[2]; k++)
+                        if (distmap->getDistance(gridVectorToPoint3D(i, j, k)) < agent_radius + grid_margin) g[at(i, j, k)] = GP_OCCUPIED;
+        }
+        return g;
+    }
 
     // plan (:53-66). high_priority == nullptr: no agent is an obstacle ("A* without priority")
     const std::vector<point3d>& plan(const point3d& current_position, const point3d& goal_position, double agent_radius,
@@ -294,14 +319,9 @@ private:
     size_t at(int i, int j, int k) const { return ((size_t)i * dim[1] + j) * dim[2] + k; }
     void updateGridMap(const std::vector<GoalObstacle>& obstacles, double agent_radius, double agent_downwash,
                        const std::vector<char>* high_priority) {                                                        // :90-190
-        grid.assign((size_t)dim[0] * dim[1] * dim[2], GP_EMPTY);
-        if (distmap != nullptr) {
-            const float grid_margin = (float)param.grid_margin;
-            for (int i = 0; i < dim[0]; i++)
-                for (int j = 0; j < dim[1]; j++)
-                    for (int k = 0; k < dim[2]; k++)
-                        if (distmap->getDistance(gridVectorToPoint3D(i, j, k)) < agent_radius + grid_margin) grid[at(i, j, k)] = GP_OCCUPIED;
-        }
+        const std::vector<uint8_t>* cached = cache ? cache->find(agent_radius) : nullptr;
+        if (cached && cached->size() == (size_t)dim[0] * dim[1] * dim[2]) grid = *cached;
+        else grid = staticGrid(agent_radius);
         const double r = param.grid_resolution;
         for (size_t oi = 0; oi < obstacles.size(); oi++) {
             if (high_priority == nullptr || !(*high_priority)[oi]) continue;
@@ -347,6 +367,7 @@ private:
     const HostDistMap* distmap;
     const Mission& mission;
     const Param& param;
+    const StaticGridCache* cache;
     double grid_min[3] = {0, 0, 0}, grid_max[3] = {0, 0, 0};
     int dim[3] = {0, 0, 0};
     std::vector<uint8_t> grid;
@@ -364,7 +385,8 @@ struct GoalPlanResult {
 inline GoalPlanResult goalPlanningWithPriority(const point3d& current_position, const point3d& desired_goal_position,
                                                const point3d& initial_traj_end, double agent_radius, double agent_downwash,
                                                const std::vector<GoalObstacle>& obstacles, const HostDistMap* distmap,
-                                               const Mission& mission, const Param& param) {
+                                               const Mission& mission, const Param& param,
+                                               const StaticGridCache* cache = nullptr) {
     GoalPlanResult out;
     std::vector<char> high(obstacles.size(), 0);
     int closest_obs_id = -1;
@@ -388,7 +410,7 @@ inline GoalPlanResult goalPlanningWithPriority(const point3d& current_position, 
         out.kind = 1;
         return out;
     }
-    GridBasedPlanner planner(distmap, mission, param);
+    GridBasedPlanner planner(distmap, mission, param, cache);
     if (planner.plan(current_position, desired_goal_position, agent_radius, agent_downwash, obstacles, &high).empty())
         planner.plan(current_position, desired_goal_position, agent_radius, agent_downwash, obstacles, nullptr);
     out.goal = planner.findLOSFreeGoal(initial_traj_end, desired_goal_position, agent_radius);

@@ -115,6 +115,12 @@ private:
             if (lscgpu_get_distmap_sqdist(engine.get(), distmap.sqdist.data()) != LSCGPU_OK)
                 throw std::invalid_argument(std::string("[lscgpu] ") + lscgpu_last_error());
         }
+        if (grid_cache.by_radius.empty()) {
+            GridBasedPlanner probe(&distmap, mission, param);
+            for (int j = 0; j < N; j++)
+                if (!grid_cache.find(mission.agents[j].radius))
+                    grid_cache.by_radius.emplace_back(mission.agents[j].radius, probe.staticGrid(mission.agents[j].radius));
+        }
         auto P = [](const float* v) { return point3d(v[0], v[1], v[2]); };
         std::vector<GoalObstacle> all(N);
         for (int j = 0; j < N; j++) {
@@ -137,7 +143,7 @@ private:
                     // of the previous trajectory (:997-1016)
                     const point3d init_end = planner_seq < 2 ? pos + (vel * (float)5.0) * (float)param.dt : P(out[a].traj[4][5]);
                     const GoalPlanResult r = goalPlanningWithPriority(pos, P(in[a].goal), init_end, mission.agents[a].radius,
-                                                                      mission.agents[a].downwash, obstacles, &distmap, mission, param);
+                                                                      mission.agents[a].downwash, obstacles, &distmap, mission, param, &grid_cache);
                     goals[a] = r.goal; expanded[a] = r.expansions;
                 }
             });
@@ -152,6 +158,7 @@ private:
     Mission mission;
     EnginePtr engine;
     HostDistMap distmap;
+    StaticGridCache grid_cache;
     double goal_seconds = 0;
     long long astar_expansions = 0;
     std::vector<lscgpu_agent_in> in;
