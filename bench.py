@@ -28,6 +28,9 @@ FOREST = os.path.join(ROOT, "tests", "golden", "worlds", "simple_forest.bt")
 L2_BYTES = 126 * 2 ** 20
 
 
+GOAL_MODES = {"static": 0, "prior_based": 1}
+
+
 def make_scenario(workload: str, agents: int):
     from lsc_planner_b200 import scenarios as S
     if workload == "circle_forest":
@@ -118,7 +121,7 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle (port of the reference's CPU path; CPLEX/ROS/octomap are not installable here)
 # ------------------------------------------------------------------------------------------------------------
-def oracle_swarm(scn, bt):
+def oracle_swarm(scn, bt, goal_mode=0):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
     omap = O.Map.from_bt(bt, scn.world_min, scn.world_max) if (bt and scn.use_octomap) else None
@@ -127,6 +130,8 @@ def oracle_swarm(scn, bt):
                  vmax=[a.max_vel for a in scn.agents], amax=[a.max_acc for a in scn.agents],
                  v_nom=[a.nominal_velocity for a in scn.agents])
     sw.set_state(scn.start); sw.set_goals(scn.goal)
+    if goal_mode:
+        sw.set_goal_mode(1); sw.set_desired_goals(scn.goal)
     return sw
 
 
@@ -142,7 +147,7 @@ def run_reference(args):
         from lsc_planner_b200 import scenarios as S
         m = O.Map.from_bt(bt, [-5, -5, 0], [5, 5, 2.5])
         scn = S.random_forest(args.agents, m.sqdist(), m.off, seed=0)
-    sw = oracle_swarm(scn, bt)
+    sw = oracle_swarm(scn, bt, GOAL_MODES[args.goal_mode])
     n = scn.n
     budget = 150.0
     t_start = time.perf_counter()
@@ -206,7 +211,11 @@ def run_ours(args):
         scn = L.scenarios.random_forest(args.agents, dm["sqdist"], dm["off"], seed=0)
         tmp.close()
     n = scn.n
-    prm = L.Param(world_min=scn.world_min, world_max=scn.world_max, world_use_octomap=scn.use_octomap)
+    if GOAL_MODES[args.goal_mode] and scn.use_octomap:
+        raise SystemExit("--goal-mode prior_based on the GPU needs a workload without octomap (--workload circle): with an "
+                         "octomap the goals come from the host grid planner (lsc_sim)")
+    prm = L.Param(world_min=scn.world_min, world_max=scn.world_max, world_use_octomap=scn.use_octomap,
+                  goal_mode=GOAL_MODES[args.goal_mode])
     eng = L.ReplanEngine(n, prm, scn.agents, device=local)
     if scn.use_octomap:
         eng.set_octomap_file(bt)
@@ -314,7 +323,7 @@ def run_ours(args):
     l_sfc = 0.0
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        sw = oracle_swarm(scn, bt)
+        sw = oracle_swarm(scn, bt, GOAL_MODES[args.goal_mode])
         # same step as the end of the timed region: the oracle is loaded with the engine's planner state
         sw.set_state(out_mid["next_position"], out_mid["next_velocity"], out_mid["next_acceleration"])
         def restore():
@@ -390,7 +399,8 @@ def run_ours(args):
                        "octomap": bool(scn.use_octomap), "parallelism": f"agents block-partitioned x{world}",
                        "l2": "L2 flushed (256 MB write) between steps; every step timed on its own with CUDA events on the "
                              "engine stream; e2e is not flushed (its inputs arrive from host memory every step)",
-                       "goals": "fixed to the mission goals (goal planning is outside the path, SURVEY.md §8f)"},
+                       "goals": ("prior_based goal planning on the GPU every step (k_goal_plan, SURVEY.md §8f #1)" if GOAL_MODES[args.goal_mode]
+                                 else "fixed to the mission goals (goal planning is outside the path, SURVEY.md §8f)")},
             "e2e": {"value": e2e_value, "unit": "agent-replans/s", "h2d_bytes_per_step": n * A.AGENT_IN.itemsize,
                     "d2h_bytes_per_step": n * A.AGENT_OUT.itemsize},
             "gpu_launches": int(launches.item()),
@@ -420,6 +430,7 @@ def main():
     ap.add_argument("--workload", default="circle_forest", choices=["circle_forest", "circle", "random_forest"])
     ap.add_argument("--agents", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--goal-mode", default="static", choices=list(GOAL_MODES))
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
