@@ -427,15 +427,35 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 512 ? 1 : 512 / kThreads
                     if (q > 0) {
 #pragma unroll 1
                         for (int pass = 0; pass < 2; pass++) {
-                            for (int k = lane; k < q; k += 32) {          // lane k: column k of Q against z
+                            // lane k: column k of Q against z. Three chunks of 13 rows: the 13 column entries are loaded
+                            // into registers first (independent shared-memory loads in flight together), then multiplied
+                            // against the broadcast z values; without the staging the compiler funnels all 39 loads
+                            // through one register pair and exposes the load latency 39 times.
+                            if (lane < q) {
+                                const double* qc = S.Q + lane;
                                 double s0 = 0.0, s1 = 0.0, s2 = 0.0;
 #pragma unroll
-                                for (int r = 0; r < NR; r += 3) {
-                                    s0 += S.Q[r * LD + k] * S.z[r];
-                                    s1 += S.Q[(r + 1) * LD + k] * S.z[r + 1];
-                                    s2 += S.Q[(r + 2) * LD + k] * S.z[r + 2];
+                                for (int r0 = 0; r0 < NR; r0 += 13) {
+                                    double qv[13];
+#pragma unroll
+                                    for (int i = 0; i < 13; i++) qv[i] = qc[(r0 + i) * LD];
+#pragma unroll
+                                    for (int i = 0; i < 13; i++) {
+                                        const double pz = S.z[r0 + i];
+                                        if (i % 3 == 0) s0 += qv[i] * pz;
+                                        else if (i % 3 == 1) s1 += qv[i] * pz;
+                                        else s2 += qv[i] * pz;
+                                    }
                                 }
                                 const double sdot = s0 + s1 + s2;
+                                S.tmp[lane] = sdot;
+                                S.d[lane] += sdot;
+                            }
+#pragma unroll 1
+                            for (int k = lane + 32; k < q; k += 32) {     // q > 32 only
+                                double sdot = 0.0;
+#pragma unroll 1
+                                for (int r = 0; r < NR; r++) sdot += S.Q[r * LD + k] * S.z[r];
                                 S.tmp[k] = sdot;
                                 S.d[k] += sdot;
                             }
@@ -449,12 +469,14 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 512 ? 1 : 512 / kThreads
                                 const double* q2 = S.Q + r2 * LD;
                                 double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
                                 int k = 0;
-                                for (; k + 1 < q; k += 2) {
-                                    const double t0 = S.tmp[k], t1 = S.tmp[k + 1];
-                                    a0 += q1[k] * t0; a1 += q1[k + 1] * t1;
-                                    b0 += q2[k] * t0; b1 += q2[k + 1] * t1;
+                                for (; k + 3 < q; k += 4) {                 // four columns per trip: 12 loads, then 8 FMAs
+                                    const double t0 = S.tmp[k], t1 = S.tmp[k + 1], t2 = S.tmp[k + 2], t3 = S.tmp[k + 3];
+                                    const double u0 = q1[k], u1 = q1[k + 1], u2 = q1[k + 2], u3 = q1[k + 3];
+                                    const double w0 = q2[k], w1 = q2[k + 1], w2 = q2[k + 2], w3 = q2[k + 3];
+                                    a0 += u0 * t0; a1 += u1 * t1; b0 += w0 * t0; b1 += w1 * t1;
+                                    a0 += u2 * t2; a1 += u3 * t3; b0 += w2 * t2; b1 += w3 * t3;
                                 }
-                                if (k < q) { const double t0 = S.tmp[k]; a0 += q1[k] * t0; b0 += q2[k] * t0; }
+                                for (; k < q; k++) { const double t0 = S.tmp[k]; a0 += q1[k] * t0; b0 += q2[k] * t0; }
                                 const double z1 = S.z[lane] - (a0 + a1);
                                 S.z[lane] = z1;
                                 zp = z1 * z1;
