@@ -46,8 +46,9 @@ constexpr double kZeroTol = 1e-13;
 struct QpShared {
     double Q[NR * LD];          // columns 0..q-1: orthonormal basis of the active normals
     double R[NR * LD];          // upper triangle, row-major
+    double W[NR * LD];          // R^-1 (upper triangle, zeros below): the multiplier step is a product, not a substitution
     double x[kNv];
-    double nv[NR], z[NR], d[NR], tmp[NR], rr[NR], lam[NR], inv_diag[NR];
+    double nv[NR], z[NR], d[NR], tmp[NR], rr[NR], lam[NR];
     double inv_gn[kAx];
     double lb[15], ub[15], vmax[3], amax[3];
     double travelled;           // path length of the iterate in the whitened space
@@ -169,11 +170,17 @@ __device__ __forceinline__ RowRegs decode_row(int id, int n_obs, const RowRec* r
 
 // remove active row l: delete column l of R, restore the triangle with Givens rotations (rows j, j+1 of R,
 // columns j, j+1 of Q)
+// With W = R^-1: R' = (G R P)[:q-1] (P deletes column l, G the rotations) gives W' = (P^T W G^T)[:, :q-1]: delete ROW l of W
+// and rotate its COLUMNS with the same coefficients.
 __device__ __forceinline__ void drop_active(QpShared& S, int& q, int l, int lane) {
     __syncwarp();
     for (int r = lane; r < q; r += 32) {
         for (int j = l; j < q - 1; j++) S.R[r * LD + j] = S.R[r * LD + j + 1];
         S.R[r * LD + q - 1] = 0.0;
+    }
+    for (int c = lane; c < q; c += 32) {
+        for (int r = l; r < q - 1; r++) S.W[r * LD + c] = S.W[(r + 1) * LD + c];
+        S.W[(q - 1) * LD + c] = 0.0;
     }
     if (lane == 0)
         for (int j = l; j < q - 1; j++) { S.act[j] = S.act[j + 1]; S.lam[j] = S.lam[j + 1]; }
@@ -190,6 +197,11 @@ __device__ __forceinline__ void drop_active(QpShared& S, int& q, int l, int lane
             S.R[(j + 1) * LD + k] = -s * t1 + c * t2;
         }
         if (lane == 0) S.R[(j + 1) * LD + j] = 0.0;
+        for (int r = lane; r <= j; r += 32) {                  // rows below j have zeros in both columns
+            const double t1 = S.W[r * LD + j], t2 = S.W[r * LD + j + 1];
+            S.W[r * LD + j] = c * t1 + s * t2;
+            S.W[r * LD + j + 1] = -s * t1 + c * t2;
+        }
         for (int r = lane; r < NR; r += 32) {
             const double t1 = S.Q[r * LD + j], t2 = S.Q[r * LD + j + 1];
             S.Q[r * LD + j] = c * t1 + s * t2;
@@ -197,7 +209,7 @@ __device__ __forceinline__ void drop_active(QpShared& S, int& q, int l, int lane
         }
     }
     __syncwarp();
-    for (int k = l + lane; k < q; k += 32) S.inv_diag[k] = 1.0 / S.R[k * LD + k];
+    for (int r = lane; r <= q; r += 32) S.W[r * LD + q] = 0.0;         // the column that fell off
     __syncwarp();
 }
 
@@ -212,7 +224,7 @@ struct FixedItems {
 };
 
 template <int kThreads>
-__global__ void __launch_bounds__(kThreads, kThreads >= 512 ? 1 : 512 / kThreads) k_qp_solve(QpLaunch L) {
+__global__ void __launch_bounds__(kThreads, 512 / kThreads) k_qp_solve(QpLaunch L) {
     constexpr int kWarps = kThreads / 32;
     constexpr int kItems = (225 + kThreads - 1) / kThreads;
     constexpr int kGate = 8;                       // gate values per thread per chunk
@@ -257,7 +269,7 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 512 ? 1 : 512 / kThreads
         const double* Xs = T.Xs[ts - 1][i];
         S.x[e] = Xs[0] * st[k] + Xs[1] * st[3 + k] + Xs[2] * st[6 + k] + T.xg[ts - 1][i] * gl[k];
     }
-    for (int e = tid; e < NR * LD; e += kThreads) S.R[e] = 0.0;
+    for (int e = tid; e < NR * LD; e += kThreads) { S.R[e] = 0.0; S.W[e] = 0.0; }
     if (tid == 0) { S.travelled = 0.0; S.stop = 0; }
     __syncthreads();
     FixedItems<kItems> F;
@@ -499,14 +511,23 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 512 ? 1 : 512 / kThreads
                     // substitution, rr[k] lives in lane k's register while q <= 32
                     double t1 = INFINITY;
                     int l = -1;
-                    if (q <= 32) {
-                        double rk = lane < q ? S.d[lane] : 0.0;
-                        for (int c = q - 1; c >= 0; c--) {
-                            const double piv = __shfl_sync(0xffffffffu, rk, c) * S.inv_diag[c];
-                            if (lane < c) rk -= S.R[lane * LD + c] * piv;
-                            if (lane == c) rk = piv;
+                    // rr = R^-1 d = W d (change of the active multipliers per unit step): lane k owns row k; the zeros below
+                    // the diagonal make the product predicate free; four columns per trip, loads staged before the FMAs
+                    for (int k = lane; k < q; k += 32) {
+                        const double* wk = S.W + k * LD;
+                        double a0 = 0.0, a1 = 0.0;
+                        int c = 0;
+                        for (; c + 3 < q; c += 4) {
+                            const double w0 = wk[c], w1 = wk[c + 1], w2 = wk[c + 2], w3 = wk[c + 3];
+                            const double d0 = S.d[c], d1 = S.d[c + 1], d2 = S.d[c + 2], d3 = S.d[c + 3];
+                            a0 += w0 * d0; a1 += w1 * d1; a0 += w2 * d2; a1 += w3 * d3;
                         }
-                        if (lane < q) S.rr[lane] = rk;
+                        for (; c < q; c++) a0 += wk[c] * S.d[c];
+                        S.rr[k] = a0 + a1;
+                    }
+                    __syncwarp();
+                    if (q <= 32) {
+                        const double rk = lane < q ? S.rr[lane] : 0.0;
                         // ratio test over the active multipliers: lane k holds candidate k; warp minimum of the ratio through
                         // its order-preserving 64-bit key (two 32-bit min reductions), ties to the smallest index
                         const bool cand = lane < q && rk > kZeroTol;
@@ -526,15 +547,6 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 512 ? 1 : 512 / kThreads
                             t1 = __longlong_as_double((long long)(mk ^ ((mk >> 63) ? 0x8000000000000000ull : ~0ull)));
                         }
                     } else {
-                        for (int k = lane; k < q; k += 32) S.rr[k] = S.d[k];
-                        for (int c = q - 1; c >= 0; c--) {
-                            __syncwarp();
-                            const double piv = S.rr[c] * S.inv_diag[c];
-                            __syncwarp();
-                            for (int k = lane; k < c; k += 32) S.rr[k] -= S.R[k * LD + c] * piv;
-                            if (lane == 0) S.rr[c] = piv;
-                        }
-                        __syncwarp();
                         for (int k = lane; k < q; k += 32)
                             if (S.rr[k] > kZeroTol) {
                                 const double t = S.lam[k] / S.rr[k];
@@ -567,10 +579,10 @@ __global__ void __launch_bounds__(kThreads, kThreads >= 512 ? 1 : 512 / kThreads
                         // the row becomes active: new basis column z / |z|, new column (d, |z|) of R
                         const double zn = sqrt(zz), izn = 1.0 / zn;
                         for (int r = lane; r < NR; r += 32) S.Q[r * LD + q] = S.z[r] * izn;
-                        for (int k = lane; k < q; k += 32) S.R[k * LD + q] = S.d[k];
+                        for (int k = lane; k < q; k += 32) { S.R[k * LD + q] = S.d[k]; S.W[k * LD + q] = -S.rr[k] * izn; }
                         if (lane == 0) {
                             S.R[q * LD + q] = zn;
-                            S.inv_diag[q] = izn;
+                            S.W[q * LD + q] = izn;
                             S.act[q] = best.id;
                             S.lam[q] = lam_p;
                         }
@@ -715,8 +727,7 @@ void launch_qp_solve(const QpLaunch& L, cudaStream_t s) {
     static const int forced = getenv("LSCGPU_QP_THREADS") ? atoi(getenv("LSCGPU_QP_THREADS")) : 0;
     const int threads = forced ? forced : 256;
     (void)sms;
-    if (threads >= 512) k_qp_solve<512><<<L.n_problems, 512, 0, s>>>(L);
-    else if (threads == 256) k_qp_solve<256><<<L.n_problems, 256, 0, s>>>(L);
+    if (threads >= 256) k_qp_solve<256><<<L.n_problems, 256, 0, s>>>(L);
     else if (threads == 128) k_qp_solve<128><<<L.n_problems, 128, 0, s>>>(L);
     else k_qp_solve<64><<<L.n_problems, 64, 0, s>>>(L);
 }
