@@ -8,10 +8,10 @@
 //   closestPointsBetweenPointAndConvexHull include/geometry.hpp:364-394
 //   normalVectorBetweenPolys               src/traj_planner.cpp:2030-2043
 //   generateLSC                            src/traj_planner.cpp:1310-1407 (downwash scaling, margins d_i)
-// The closest-point-of-simplex step is NOT openGJK's signed-volume recursion (GPLv3, not restated): it scores every
-// feature of the (<= 4 vertex) simplex — vertices, open edges, open faces — and keeps the nearest one, which is exact
-// for any simplex, including the degenerate (collinear / coincident control points) hulls that straight-line
-// predictions produce at the first replanning step.
+// The closest-point-of-simplex step is NOT openGJK's signed-volume recursion (GPLv3, not restated): it scores the
+// features of the (<= 4 vertex) simplex that contain the newest vertex — that vertex, its open edges, its open faces —
+// and keeps the nearest one, which is exact for any simplex, including the degenerate (collinear / coincident control
+// points) hulls that straight-line predictions produce at the first replanning step.
 #pragma once
 #include "device_common.cuh"
 
@@ -75,21 +75,20 @@ __device__ __forceinline__ void simplex_nearest(SimplexD& s, D3& v) {
     if (n == 4 && tetra_contains_origin(s.p)) { v = D3{0.0, 0.0, 0.0}; return; }
     NearestFeature best;
     best.n2 = INFINITY; best.keep = 0u; best.v = D3{0.0, 0.0, 0.0};
+    // The newest vertex w strictly improves on the previous closest point (the outer loop only adds it
+    // when v.v - v.w exceeds the tolerances), so the closest point of the enlarged simplex lies in the relative interior
+    // of a feature that CONTAINS w: vertex w, the edges (a, w), the faces (a, b, w). Features of the old simplex alone
+    // cannot win and are not evaluated (7 instead of 14 candidates for a tetrahedron).
+    // (the outer loop keeps the newest vertex at index 0)
+    feature_try(best, s.p[0], 1u);
 #pragma unroll
-    for (int a = 0; a < 4; a++)
-        if (a < n) feature_try(best, s.p[a], 1u << a);
+    for (int a = 1; a < 4; a++)
+        if (a < n) feature_edge(best, s.p[0], s.p[a], 1u | (1u << a));
 #pragma unroll
-    for (int a = 0; a < 4; a++)
+    for (int a = 1; a < 4; a++)
 #pragma unroll
         for (int b = a + 1; b < 4; b++)
-            if (b < n) feature_edge(best, s.p[a], s.p[b], (1u << a) | (1u << b));
-#pragma unroll
-    for (int a = 0; a < 4; a++)
-#pragma unroll
-        for (int b = a + 1; b < 4; b++)
-#pragma unroll
-            for (int c = b + 1; c < 4; c++)
-                if (c < n) feature_face(best, s.p[a], s.p[b], s.p[c], (1u << a) | (1u << b) | (1u << c));
+            if (b < n) feature_face(best, s.p[0], s.p[a], s.p[b], 1u | (1u << a) | (1u << b));
     int m = 0;
 #pragma unroll
     for (int a = 0; a < 4; a++)
@@ -119,6 +118,7 @@ __device__ __forceinline__ int gjk_origin_hull6(const D3* P, D3& v) {
     v = P[0];
     int sup = 0, k = 0;
     double norm2_max = 0.0;
+#pragma unroll 1
     do {
         k++;
         double best = -d3_dot(pick6(P, sup), v);
@@ -134,8 +134,7 @@ __device__ __forceinline__ int gjk_origin_hull6(const D3* P, D3& v) {
         const double exceed = vv - d3_dot(v, w);
         if (exceed <= eps_rel * vv || exceed < eps_tot) break;
         if (vv < eps_rel * eps_rel) break;
-#pragma unroll
-        for (int t = 0; t < 4; t++) if (t == s.n) s.p[t] = w;
+        s.p[3] = s.p[2]; s.p[2] = s.p[1]; s.p[1] = s.p[0]; s.p[0] = w;       // newest vertex first (s.n <= 3 here)
         s.n++;
         simplex_nearest(s, v);
 #pragma unroll

@@ -1,5 +1,6 @@
 // k_predict, k_lsc_build and the small glue kernels around them (sm_100a).
 #include <cstdlib>
+#include <string>
 
 #include "gjk.cuh"
 #include "kernels.hpp"
@@ -353,12 +354,17 @@ __global__ void __launch_bounds__(kLscThreads, kMinBlocks) k_lsc_build(LscLaunch
 void launch_lsc_build(const LscLaunch& L, cudaStream_t s) {
     const int n_obs = L.n_agents - 1;
     if (n_obs <= 0 || L.count <= 0) return;
-    // 128 threads x 2 blocks per SM (231 registers) or 256 threads x 1 block: same occupancy, the larger block halves one
-    // agent's latency (what matters when few agents are local), the smaller one packs the tail better
-    static const int thr = getenv("LSCGPU_LSC_THREADS") ? atoi(getenv("LSCGPU_LSC_THREADS")) : 0;
-    const int threads = thr ? thr : 256;
-    if (threads >= 256) k_lsc_build<256, 1><<<L.count, 256, 0, s>>>(L);
-    else k_lsc_build<128, 2><<<L.count, 128, 0, s>>>(L);
+    // block size x blocks per SM (register cap): 128x4 and 256x2 run at 128 registers (16 warps per SM), 128x3 at 168,
+    // 256x1 / 128x2 at the unconstrained 180. Larger blocks shorten one agent's latency (what matters when the launch
+    // is a single wave), more resident warps hide the FP64 dependency chains of the GJK (what matters otherwise).
+    static const char* cfg_env = getenv("LSCGPU_LSC_CFG");
+    const char* cfg = cfg_env ? cfg_env : "256x2";
+    const std::string c(cfg);
+    if (c == "256x1") k_lsc_build<256, 1><<<L.count, 256, 0, s>>>(L);
+    else if (c == "256x2") k_lsc_build<256, 2><<<L.count, 256, 0, s>>>(L);
+    else if (c == "128x2") k_lsc_build<128, 2><<<L.count, 128, 0, s>>>(L);
+    else if (c == "128x3") k_lsc_build<128, 3><<<L.count, 128, 0, s>>>(L);
+    else k_lsc_build<128, 4><<<L.count, 128, 0, s>>>(L);
 }
 
 // ------------------------------------------------------------------------------------------------------------
