@@ -96,21 +96,34 @@ __device__ __forceinline__ Best warp_argmin(Best b) {
     return r;
 }
 
-// one (obstacle, segment) pair: up to 6 rows. Returns the smallest whitened slack of the pair's rows.
+// one (obstacle, segment) pair: up to 6 rows. Returns the smallest whitened slack of the pair's rows. Branch free: the
+// six rows are evaluated as six independent chains (all shared-memory loads first), rows that do not exist (initial-state
+// control points of segment 0) or are not violated beyond the tolerance become +inf by selects, and only the pair's most
+// violated row (smallest i on ties, as a sequential scan would keep) is offered to the thread's running best.
 __device__ __forceinline__ double price_pair_vals(Best& best, const QpShared& S, int q, int slot, int m, float4 nr,
                                                   const double* r6) {
     const double ax = (double)nr.x, ay = (double)nr.y, az = (double)nr.z, inv = (double)nr.w;
-    double mu_min = INFINITY;
+    const double* xb = S.x + m * 6;
+    const double* gb = S.inv_gn + m * 6;
+    double slack[6], scale[6];
 #pragma unroll
     for (int i = 0; i < 6; i++) {
-        if (m == 0 && i < kPhi) continue;
-        const int vi = m * 6 + i;
-        const double slack = ax * S.x[vi] + ay * S.x[kAx + vi] + az * S.x[2 * kAx + vi] - r6[i];
-        const double scale = inv * S.inv_gn[vi];
-        const double mu = scale < INFINITY ? slack * scale : (slack < 0.0 ? -INFINITY : INFINITY);
-        mu_min = fmin(mu_min, mu);
-        consider(best, S, q, slack, scale, kFixedRows + slot * 6 + i);
+        slack[i] = ax * xb[i] + ay * xb[kAx + i] + az * xb[2 * kAx + i] - r6[i];
+        scale[i] = inv * gb[i];
     }
+    double mu_min = INFINITY, cand_mu = INFINITY;
+    int cand_i = -1;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        const bool exists = !(i < kPhi && m == 0);
+        const bool finite = scale[i] < INFINITY;
+        const double mu = finite ? slack[i] * scale[i] : (slack[i] < 0.0 ? -INFINITY : INFINITY);
+        mu_min = fmin(mu_min, exists ? mu : INFINITY);
+        // candidate value as `consider` computes it: zero normal with positive rhs = infeasible row (-inf)
+        const double mu_c = (exists && slack[i] < -kFeasTol) ? (finite ? mu : -INFINITY) : INFINITY;
+        if (mu_c < cand_mu) { cand_mu = mu_c; cand_i = i; }
+    }
+    if (cand_i >= 0 && cand_mu < best.mu) { best.mu = cand_mu; best.id = kFixedRows + slot * 6 + cand_i; }
     return mu_min;
 }
 
