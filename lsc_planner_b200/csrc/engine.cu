@@ -68,6 +68,8 @@ struct lscgpu_engine {
     cudaStream_t stream = nullptr;
     cudaStream_t stream_sfc = nullptr;     // k_sfc_expand runs beside k_lsc_build (independent until k_qp_solve)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t stream_aux = nullptr;     // k_qp_order (needs only the previous step's records) beside k_predict
+    cudaEvent_t ev_order = nullptr;
     bool overlap_sfc = true, lpt_order = true;
     static constexpr int kMaxGroups = 8;
     int pipeline_groups = 2;
@@ -162,6 +164,8 @@ extern "C" void lscgpu_destroy(lscgpu_engine* e) {
         if (e->ev_qp[g]) cudaEventDestroy(e->ev_qp[g]);
         if (e->stream_grp[g]) cudaStreamDestroy(e->stream_grp[g]);
     }
+    if (e->ev_order) cudaEventDestroy(e->ev_order);
+    if (e->stream_aux) cudaStreamDestroy(e->stream_aux);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
     if (e->stream_sfc) cudaStreamDestroy(e->stream_sfc);
@@ -222,6 +226,8 @@ extern "C" int lscgpu_create(const lscgpu_params* p, int n_agents, const lscgpu_
     } while (0)
     CUB(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CUB(cudaStreamCreateWithFlags(&e->stream_sfc, cudaStreamNonBlocking));
+    CUB(cudaStreamCreateWithFlags(&e->stream_aux, cudaStreamNonBlocking));
+    CUB(cudaEventCreateWithFlags(&e->ev_order, cudaEventDisableTiming));
     CUB(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
     CUB(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
     if (const char* v = getenv("LSCGPU_OVERLAP_SFC")) e->overlap_sfc = atoi(v) != 0;
@@ -448,7 +454,6 @@ static int step_device(lscgpu_engine* e) {
         }
         ev = e->ev_pool[e->pending].ev;
     }
-    if (n_local > 0) CU(cudaMemsetAsync(e->d_kept_count, 0, sizeof(int) * n_local, s));
     if ((int)e->step_ev.size() <= e->pending) {
         std::pair<cudaEvent_t, cudaEvent_t> pr;
         CU(cudaEventCreate(&pr.first)); CU(cudaEventCreate(&pr.second));
@@ -457,6 +462,19 @@ static int step_device(lscgpu_engine* e) {
     if (e->pending == 0) CU(cudaEventRecord(e->ev_begin, s));
     CU(cudaEventRecord(e->step_ev[e->pending].first, s));
     if (prof) CU(cudaEventRecord(ev[0], s));
+    if (n_local > 0) CU(cudaMemsetAsync(e->d_kept_count, 0, sizeof(int) * n_local, s));
+    CU(cudaMemsetAsync(e->d_flags, 0, sizeof(int) * (size_t)e->N, s));      // k_predict and k_sfc_expand OR their bits in
+    const bool do_sfc = e->prm.world_use_octomap && n_local > 0;
+    const bool side = e->overlap_sfc && !e->profiling;      // profiling mode serialises the kernels
+    // scheduling order of this step's LSC / QP blocks from the cost of the previous step's solves (still in d_out)
+    const bool ordered = e->lpt_order && e->planner_seq > 1 && n_local > 1;
+    if (side && (do_sfc || ordered)) CU(cudaEventRecord(e->ev_fork, s));   // k_sfc_expand / k_qp_order need only the inputs
+    if (ordered) {
+        cudaStream_t so = side ? e->stream_aux : s;
+        if (side) CU(cudaStreamWaitEvent(so, e->ev_fork, 0));
+        launch_qp_order(n_local, e->a0, e->d_out, e->d_order, so); launches++;
+        if (side) CU(cudaEventRecord(e->ev_order, so));
+    }
 
     PredictLaunch pl{};
     pl.n_agents = e->N; pl.n_pad = e->n_pad; pl.planner_seq = e->planner_seq;
@@ -473,18 +491,13 @@ static int step_device(lscgpu_engine* e) {
         gl.goal3 = e->d_goal3; gl.ts = e->d_ts; gl.goal_kind = e->d_goal_kind;
         launch_goal_plan(gl, s); launches++;
     }
-    // scheduling order of this step's QP blocks from the cost of the previous step's solves (still in d_out)
-    const bool ordered = e->lpt_order && e->planner_seq > 1 && n_local > 1;
-    if (ordered) { launch_qp_order(n_local, e->a0, e->d_out, e->d_order, s); launches++; }
     if (prof) CU(cudaEventRecord(ev[1], s));
 
-    // k_sfc_expand depends on k_predict (flags) only and k_qp_solve is its only consumer: it runs on a side stream
-    // beside k_lsc_build
-    const bool do_sfc = e->prm.world_use_octomap && n_local > 0;
-    const bool side = e->overlap_sfc && !prof;              // profiling mode serialises the kernels
+    // k_sfc_expand depends on the step's inputs only (state, goal, previous trajectory, its own windows) and k_qp_solve is
+    // its only consumer: it runs on a side stream beside k_predict and k_lsc_build
     cudaStream_t ss = side ? e->stream_sfc : s;
     if (do_sfc) {
-        if (side) { CU(cudaEventRecord(e->ev_fork, s)); CU(cudaStreamWaitEvent(ss, e->ev_fork, 0)); }
+        if (side) CU(cudaStreamWaitEvent(ss, e->ev_fork, 0));
         if (prof) CU(cudaEventRecord(ev[2], ss));
         SfcLaunch sl{};
         sl.n = n_local; sl.dm = e->dm; sl.res = e->prm.world_resolution;
@@ -528,6 +541,7 @@ static int step_device(lscgpu_engine* e) {
     ql.counters = e->d_counters;
     if (getenv("LSCGPU_QP_DEBUG")) { if (!e->d_dbg) CU(cudaMalloc(&e->d_dbg, sizeof(long long) * 8 * (size_t)e->N)); ql.dbg = e->d_dbg; }
     if (groups == 1) {
+        if (ordered && side) CU(cudaStreamWaitEvent(s, e->ev_order, 0));
         if (n_local > 0 && e->N > 1) { ll.first = 0; ll.count = n_local; launch_lsc_build(ll, s); launches++; }
         if (prof) CU(cudaEventRecord(ev[4], s));
         if (do_sfc && side) CU(cudaStreamWaitEvent(s, e->ev_join, 0));
@@ -544,6 +558,7 @@ static int step_device(lscgpu_engine* e) {
             if (cnt <= 0) { CU(cudaEventRecord(e->ev_qp[g], s)); continue; }
             cudaStream_t sg = e->stream_grp[g];
             CU(cudaStreamWaitEvent(sg, e->ev_lsc[0], 0));
+            if (ordered && side) CU(cudaStreamWaitEvent(sg, e->ev_order, 0));
             ll.first = first; ll.count = cnt; launch_lsc_build(ll, sg); launches++;
             if (do_sfc && side) CU(cudaStreamWaitEvent(sg, e->ev_join, 0));
             ql.first = first; ql.n_problems = cnt; launch_qp_solve(ql, sg); launches++;

@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(96) k_predict(PredictLaunch L) {
         const F3 dlt = f3_sub(p0, pos);
         int fl = 0;
         if (sqrt(f3_dot(dlt, dlt)) > L.reset_threshold) fl |= LSCGPU_FLAG_SLACK_NEEDED;
-        L.flags[a] = fl;
+        if (fl) atomicOr(&L.flags[a], fl);        // zeroed by the launcher; k_sfc_expand ORs its bit concurrently
         const F3 g{in.goal[0], in.goal[1], in.goal[2]};
         L.ts[a] = terminal_segments_of(g, pos, L.consts[a].v_nom, L.dt);
     }
@@ -94,13 +94,16 @@ __global__ void __launch_bounds__(96) k_predict(PredictLaunch L) {
         float r2 = 0.f;
         for (int k = 0; k < 3; k++) {
             const float vmax = (float)c.vmax[k], dv = (float)c.amax[k] * dtf / (float)(kN - 1);
-            float bound[4 * kM + 1];
+            float bound[4 * kM + 1];                          // fully unrolled below: stays in registers
             bound[0] = fabsf(in.velocity[k]);
             bound[1] = fabsf(in.velocity[k] + in.acceleration[k] * dtf / (float)(kN - 1));
+#pragma unroll
             for (int t = 2; t <= 4 * kM; t++) bound[t] = fminf(vmax, bound[t - 1] + dv);
             // a feasible trajectory also keeps the fixed first two within vmax only if the state does; use them as is
             float reach = 0.f;
-            for (int t = 0; t < 5 * (m + 1); t++) reach += bound[4 * (t / 5) + (t % 5)] * dtf / (float)kN;
+#pragma unroll
+            for (int t = 0; t < 5 * kM; t++)
+                if (t < 5 * (m + 1)) reach += bound[4 * (t / 5) + (t % 5)] * dtf / (float)kN;
             r2 += reach * reach;
         }
         const float r = sqrtf(r2) + sqrtf(far2);
