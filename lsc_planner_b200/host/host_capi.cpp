@@ -8,6 +8,35 @@ using namespace DynamicPlanning;
 
 extern "C" {
 
+// HashOrderModel against the real std::unordered_map<uint32_t, int> of this toolchain: random insertions / erasures of
+// keys below `key_range`, the full iteration order compared after every operation. Returns the number of mismatching
+// operations (0 = the model reproduces the container's node order).
+int host_hash_order_check(unsigned seed, int key_range, int n_ops) {
+    std::unordered_map<uint32_t, int> ref;
+    HashOrderModel model;
+    model.reset();
+    std::vector<int> next(key_range, -1);
+    std::vector<char> present(key_range, 0);
+    auto key_of = [](int node) { return (uint32_t)(node * 7919u + 13u); };          // any injective key
+    unsigned long long state = seed * 6364136223846793005ull + 1442695040888963407ull;
+    int bad = 0;
+    for (int op = 0; op < n_ops; op++) {
+        state = state * 6364136223846793005ull + 1442695040888963407ull;
+        const int node = (int)((state >> 33) % (unsigned)key_range);
+        state = state * 6364136223846793005ull + 1442695040888963407ull;
+        const bool erase = present[node] && ((state >> 40) & 3u) != 0;              // erase 3 of 4 times when present
+        if (erase) { ref.erase(key_of(node)); model.erase(node, next, key_of); present[node] = 0; }
+        else if (!present[node]) { ref[key_of(node)] = node; model.insert(node, next, key_of); present[node] = 1; }
+        else continue;
+        int c = model.begin();
+        bool same = ref.size() == model.size();
+        for (auto it = ref.begin(); same && it != ref.end(); ++it) { same = c >= 0 && it->second == c; if (same) c = next[c]; }
+        if (same && c >= 0) same = false;
+        bad += !same;
+    }
+    return bad;
+}
+
 int host_astar(const int* dim, const unsigned char* grid, const int* start, const int* goal, int* path_out, int max_len,
                long long* expansions) {
     std::vector<uint8_t> g(grid, grid + (size_t)dim[0] * dim[1] * dim[2]);

@@ -82,6 +82,14 @@ def test_astar_live_against_reference_library(host):
         assert len(po) == n == len(ph) and (po == ref[:n]).all() and (ph == ref[:n]).all(), (dim, s, g)
 
 
+def test_hash_order_model_matches_unordered_map(host):
+    """The product's A* reproduces the reference's tie-breaking through an explicit model of libstdc++'s unordered_map
+    node order (host/grid_based_planner.hpp); here that model against the real container, operation by operation."""
+    host.host_hash_order_check.argtypes = [C.c_uint, C.c_int, C.c_int]; host.host_hash_order_check.restype = C.c_int
+    for seed, key_range, ops in [(1, 8, 2000), (2, 40, 5000), (3, 451, 20000), (4, 1771, 40000), (5, 5000, 60000)]:
+        assert host.host_hash_order_check(seed, key_range, ops) == 0, (seed, key_range)
+
+
 def test_astar_properties(host):
     """6-connected unit steps, free cells only, shortest length in an empty grid, goal test ignores the altitude
     (src/Astar-3D/isearch.cpp:74), no path when the goal column is walled in."""
