@@ -208,8 +208,7 @@ __global__ void __launch_bounds__(kLscThreads, kMinBlocks) k_lsc_build(LscLaunch
     __shared__ float4 own_sphere[kM];
     __shared__ float own_reach[kM];
     __shared__ int queue[kLscThreads * (kM + 1)];
-    __shared__ int q_count, kept_base;
-    __shared__ int warp_cnt[kM][kLscThreads / 32];     // per-warp counts of the order-preserving compactions
+    __shared__ int warp_tot[2][kLscThreads / 32];      // survivors of every warp in the current chunk (double buffered)
     const int al = L.order ? L.order[L.first + blockIdx.x] : L.first + blockIdx.x;
     const int a = L.a0 + al;
     const int n_obs = L.n_agents - 1;
@@ -225,7 +224,6 @@ __global__ void __launch_bounds__(kLscThreads, kMinBlocks) k_lsc_build(LscLaunch
     }
     for (int e = tid; e < kAx; e += kLscThreads) inv_gn[e] = 1.0 / L.T->gnorm[ts - 1][e];
     if (tid < kM) { own_sphere[tid] = L.sphere[(size_t)tid * L.n_pad + a]; own_reach[tid] = L.reach[(size_t)a * kM + tid]; }
-    if (tid == 0) { q_count = 0; kept_base = 0; }
     const int warp = tid >> 5, lane = tid & 31;
     constexpr int kWarps = kLscThreads / 32;
     __syncthreads();
@@ -237,9 +235,10 @@ __global__ void __launch_bounds__(kLscThreads, kMinBlocks) k_lsc_build(LscLaunch
     int* kept_out = L.kept + (size_t)al * L.P_pad;
     double* safe_out = L.safe + (size_t)al * L.P_pad;
     int gjk_it = 0;
+    // queue length and kept-list length: block-uniform values every thread keeps in a register
+    int q_count = 0, kept_base = 0, chunk = 0;
 
-
-    for (int j0 = 0; j0 < n_obs; j0 += kLscThreads) {
+    for (int j0 = 0; j0 < n_obs; j0 += kLscThreads, chunk++) {
         const int jj = j0 + tid;
         unsigned keep_mask[kM];
         bool keep[kM];
@@ -262,37 +261,40 @@ __global__ void __launch_bounds__(kLscThreads, kMinBlocks) k_lsc_build(LscLaunch
                 keep[m] = !(d_lb - rho > 2.0f * smax * own_reach[m]);
             }
         }
-        // order-preserving compaction (segment-major, then neighbour index): the queue, and with it every list this
-        // kernel writes, has the same order in every run
+        // order-preserving compaction (warp, then segment, then lane): the queue, and with it every list this kernel
+        // writes, has the same order in every run. One shared-memory exchange of the per-warp totals per chunk.
+        int cnt[kM], wtot = 0;
 #pragma unroll
         for (int m = 0; m < kM; m++) {
             keep_mask[m] = __ballot_sync(0xffffffffu, keep[m]);
-            if (lane == 0) warp_cnt[m][warp] = __popc(keep_mask[m]);
+            cnt[m] = __popc(keep_mask[m]);
+            wtot += cnt[m];
         }
+        if (lane == 0) warp_tot[chunk & 1][warp] = wtot;
         __syncthreads();
         {
             int off = q_count, total = 0;
 #pragma unroll
-            for (int m = 0; m < kM; m++)
+            for (int w = 0; w < kWarps; w++) {
+                const int c = warp_tot[chunk & 1][w];
+                if (w < warp) off += c;
+                total += c;
+            }
 #pragma unroll
-                for (int w = 0; w < kWarps; w++) {
-                    const int c = warp_cnt[m][w];
-                    if (keep[m] && w == warp) queue[off + __popc(keep_mask[m] & ((1u << lane) - 1u))] = m * n_obs + jj;
-                    off += c; total += c;
-                }
-            __syncthreads();
-            if (tid == 0) q_count += total;
+            for (int m = 0; m < kM; m++) {
+                if (keep[m]) queue[off + __popc(keep_mask[m] & ((1u << lane) - 1u))] = m * n_obs + jj;
+                off += cnt[m];
+            }
+            q_count += total;
         }
         __syncthreads();
         // drain full batches (and everything after the last chunk)
         const bool last = j0 + kLscThreads >= n_obs;
         while (q_count >= kLscThreads || (last && q_count > 0)) {
             const int n_items = min(q_count, kLscThreads);
-            const int total = q_count;
             int p = -1;
-            if (tid < n_items) p = queue[total - n_items + tid];      // take the batch from the END of the queue
-            __syncthreads();
-            if (tid == 0) q_count = total - n_items;
+            if (tid < n_items) p = queue[q_count - n_items + tid];    // take the batch from the END of the queue
+            q_count -= n_items;
             double mu_min = INFINITY;
             if (p >= 0) {
                 const int m = p / n_obs, jj2 = p % n_obs;
@@ -341,10 +343,9 @@ __global__ void __launch_bounds__(kLscThreads, kMinBlocks) k_lsc_build(LscLaunch
                     dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
                 }
             }
-            __syncthreads();
-            if (tid == 0) kept_base += n_items;
-            __syncthreads();
+            kept_base += n_items;
         }
+        // the queue tail that stays for the next chunk is only read after that chunk's barriers; nothing to wait for here
     }
     if (tid == 0) L.kept_count[al] = kept_base;
     if (L.counters) {
