@@ -326,8 +326,10 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) k_qp_solve(QpLaunch 
     while (true) {
         // ---- pricing by the whole block ---------------------------------------------------------------------------
         Best best{0.0, -1};
-        const double travelled = S.travelled;
         const long long t_price = clock64();
+        if (tid == 0) S.open_count[0] = 0;
+        __syncthreads();        // x of the previous update is complete (block-wide update below), list counter zeroed
+        const double travelled = S.travelled;
 #pragma unroll
         for (int t = 0; t < kItems; t++) {
             if (F.base[t] < 0) continue;
@@ -344,7 +346,6 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) k_qp_solve(QpLaunch 
         // LSC rows, chunk by chunk: (1) every thread reads kGate gate values (coalesced, all loads in flight at once),
         // (2) the pairs whose gate is open are compacted into a shared-memory list, (3) the list is evaluated evenly
         // spread over the block, the next record being loaded while the current one is evaluated.
-        if (tid == 0) S.open_count[0] = 0;
         for (int s0 = 0, chunk = 0; s0 < n_kept; s0 += kGate * kThreads, chunk++) {
             double sv[kGate];
 #pragma unroll
@@ -352,7 +353,7 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) k_qp_solve(QpLaunch 
                 const int si = s0 + kThreads * h + tid;
                 sv[h] = si < n_kept ? safe[si] : INFINITY;
             }
-            __syncthreads();        // list of the previous chunk consumed, counter of this one zeroed
+            if (chunk > 0) __syncthreads();     // list of the previous chunk consumed, counter of this one zeroed
             int* cnt = &S.open_count[chunk & 1];
 #pragma unroll
             for (int h = 0; h < kGate; h++) {
@@ -611,7 +612,9 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) k_qp_solve(QpLaunch 
             if (done && lane == 0) S.stop = 1;
         }
         __syncthreads();
-        // x += (G (+) G (+) G) vacc by the whole block: element e = axis * 30 + var, 13 products each
+        const bool stop = S.stop != 0;
+        // x += (G (+) G (+) G) vacc by the whole block: element e = axis * 30 + var, 13 products each (the barrier at the
+        // top of the next pass makes it visible)
         for (int e = tid; e < kNv; e += kThreads) {
             const int k = e / kAx;
             const double* g = Gt + (e - k * kAx) * kFree;
@@ -622,8 +625,7 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) k_qp_solve(QpLaunch 
             s0 += __ldg(g + kFree - 1) * va[kFree - 1];
             S.x[e] += s0 + s1;
         }
-        __syncthreads();
-        if (S.stop) break;
+        if (stop) break;
     }
     __syncthreads();
 
