@@ -76,6 +76,8 @@ struct lscgpu_engine {
     cudaStream_t stream_grp[kMaxGroups] = {};
     cudaEvent_t ev_lsc[kMaxGroups] = {}, ev_qp[kMaxGroups] = {};
     long long* d_dbg = nullptr;
+    float* d_audit_pos = nullptr; double* d_audit_ratio = nullptr; int* d_audit_closest = nullptr;   // lscgpu_safety_audit scratch
+    int audit_samples = 0;
     int* d_order = nullptr;          // [n_local] local agents, most expensive QP of the previous step first
     int planner_seq = 0;
     bool profiling = false;
@@ -150,7 +152,7 @@ extern "C" void lscgpu_destroy(lscgpu_engine* e) {
     cudaSetDevice(e->device);
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     free_rows(e);
-    cudaFree(e->d_rdw);
+    cudaFree(e->d_rdw); cudaFree(e->d_audit_pos); cudaFree(e->d_audit_ratio); cudaFree(e->d_audit_closest); cudaFree(e->d_dbg);
     cudaFree(e->d_tables); cudaFree(e->d_consts); cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_traj);
     cudaFree(e->d_pred); cudaFree(e->d_predT); cudaFree(e->d_predZs); cudaFree(e->d_boxes); cudaFree(e->d_state9); cudaFree(e->d_goal3);
     cudaFree(e->d_last_cost); cudaFree(e->d_ts); cudaFree(e->d_flags); cudaFree(e->d_init_sfc); cudaFree(e->d_goal_kind); cudaFree(e->d_counters);
@@ -900,15 +902,20 @@ extern "C" int lscgpu_safety_audit(lscgpu_engine* e, double record_time_step, do
     int n_samples = 0;
     for (double ft = 0; ft < time_step - 1e-5; ft += record_time_step) n_samples++;      // src/multi_sync_simulator.cpp:447
     if (n_samples > 4096) return fail(LSCGPU_ERR_ARG, "record_time_step too small");
-    float* d_pos = nullptr; double* d_ratio = nullptr; int* d_closest = nullptr;
-    CU(cudaMalloc(&d_pos, sizeof(float) * 3 * (size_t)e->N * n_samples));
-    CU(cudaMalloc(&d_ratio, sizeof(double) * e->N));
-    CU(cudaMalloc(&d_closest, sizeof(int) * e->N));
-    launch_safety_audit(e->N, e->d_traj, e->d_consts, e->prm.dt, n_samples, record_time_step, d_pos, d_ratio, d_closest, e->stream);
-    CU(cudaMemcpyAsync(ratio, d_ratio, sizeof(double) * e->N, cudaMemcpyDeviceToHost, e->stream));
-    CU(cudaMemcpyAsync(closest, d_closest, sizeof(int) * e->N, cudaMemcpyDeviceToHost, e->stream));
+    if (n_samples > e->audit_samples) {             // scratch kept for the engine's lifetime
+        cudaFree(e->d_audit_pos); e->d_audit_pos = nullptr;
+        CU(cudaMalloc(&e->d_audit_pos, sizeof(float) * 3 * (size_t)e->N * n_samples));
+        e->audit_samples = n_samples;
+    }
+    if (!e->d_audit_ratio) {
+        CU(cudaMalloc(&e->d_audit_ratio, sizeof(double) * e->N));
+        CU(cudaMalloc(&e->d_audit_closest, sizeof(int) * e->N));
+    }
+    launch_safety_audit(e->N, e->d_traj, e->d_consts, e->prm.dt, n_samples, record_time_step, e->d_audit_pos, e->d_audit_ratio,
+                        e->d_audit_closest, e->stream);
+    CU(cudaMemcpyAsync(ratio, e->d_audit_ratio, sizeof(double) * e->N, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(closest, e->d_audit_closest, sizeof(int) * e->N, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
-    cudaFree(d_pos); cudaFree(d_ratio); cudaFree(d_closest);
     CU(cudaGetLastError());
     return LSCGPU_OK;
 }
