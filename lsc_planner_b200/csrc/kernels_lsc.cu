@@ -69,10 +69,48 @@ __global__ void __launch_bounds__(96) k_predict(PredictLaunch L) {
         const F3 g{in.goal[0], in.goal[1], in.goal[2]};
         L.ts[a] = terminal_segments_of(g, pos, L.consts[a].v_nom, L.dt);
     }
+    // reach bounds per (segment, axis): 15 threads, combined per segment below
+    __shared__ float s_reach[kM][3], s_dreach[kM][3];
+    if (e >= 64 && e < 64 + 3 * kM) {
+        const int m = (e - 64) / 3, k = (e - 64) % 3;
+        const AgentConstDev& c = L.consts[a];
+        const float dtf = (float)L.dt;
+        // Reachable offset of any control point of segment m from the current position, per axis, from the velocity
+        // AND acceleration rows (src/traj_optimizer.cpp:469-525): the velocity control points v_t satisfy
+        // |v_{t+1} - v_t| <= amax dt/(n-1) and |v_t| <= vmax (the first two are fixed by the state), consecutive
+        // position control points differ by v_t dt/n, and C1/C2 continuity carries both bounds across segments.
+        const float vmax = (float)c.vmax[k], dv = (float)c.amax[k] * dtf / (float)(kN - 1);
+        float bound[4 * kM + 1];                          // fully unrolled below: stays in registers
+        bound[0] = fabsf(in.velocity[k]);
+        bound[1] = fabsf(in.velocity[k] + in.acceleration[k] * dtf / (float)(kN - 1));
+#pragma unroll
+        for (int t = 2; t <= 4 * kM; t++) bound[t] = fminf(vmax, bound[t - 1] + dv);
+        // a feasible trajectory also keeps the fixed first two within vmax only if the state does; use them as is
+        float reach = 0.f;
+#pragma unroll
+        for (int t = 0; t < 5 * kM; t++)
+            if (t < 5 * (m + 1)) reach += bound[4 * (t / 5) + (t % 5)] * dtf / (float)kN;
+        // Second bound, on x - c directly: both satisfy the same rows, so their velocity control points differ by at
+        // most what the acceleration rows let them drift apart, 2 dv per step (and 2 vmax), starting from the mismatch
+        // of the first two (zero unless the state was reset: the state IS the previous plan at t = dt). 1 % head room
+        // on the limits for the 1e-6 row tolerance and the float32 rounding of c.
+        const float v0c = (o[3 + k] - o[k]) * (float)kN / dtf, v1c = (o[6 + k] - o[3 + k]) * (float)kN / dtf;
+        float dbound[4 * kM + 1];
+        dbound[0] = fabsf(v0c - in.velocity[k]);
+        dbound[1] = fabsf(v1c - (in.velocity[k] + in.acceleration[k] * dtf / (float)(kN - 1)));
+#pragma unroll
+        for (int t = 2; t <= 4 * kM; t++) dbound[t] = fminf(2.02f * vmax, dbound[t - 1] + 2.02f * dv);
+        float dreach = fabsf(o[k] - in.position[k]);
+#pragma unroll
+        for (int t = 0; t < 5 * kM; t++)
+            if (t < 5 * (m + 1)) dreach += dbound[4 * (t / 5) + (t % 5)] * dtf / (float)kN;
+        s_reach[m][k] = reach; s_dreach[m][k] = dreach;
+    }
+    __syncthreads();
     if (e >= 32 && e < 32 + kM) {
         // Culling data of segment m. Bounding sphere of the 6 control points, and `reach`: an upper
-        // bound of |x - c| for ANY point x the QP may give control point (m,i) and its initial_traj point c:
-        // |x - c| <= |x - p| + |c - p| with p the current position.
+        // bound of |x - c| for ANY point x the QP may give control point (m,i) and its initial_traj point c: the smaller
+        // of |x - p| + |c - p| (p the current position) and a direct bound on x - c (below).
         const int m = e - 32;
         float cx = 0.f, cy = 0.f, cz = 0.f;
         for (int i = 0; i < 6; i++) { cx += o[(m * 6 + i) * 3]; cy += o[(m * 6 + i) * 3 + 1]; cz += o[(m * 6 + i) * 3 + 2]; }
@@ -85,28 +123,9 @@ __global__ void __launch_bounds__(96) k_predict(PredictLaunch L) {
             far2 = fmaxf(far2, dx * dx + dy * dy + dz * dz);
         }
         L.sphere[(size_t)m * L.n_pad + a] = make_float4(cx, cy, cz, sqrtf(rad2) * 1.0001f + 1e-5f);
-        // Reachable offset of any control point of segment m from the current position, per axis, from the velocity
-        // AND acceleration rows (src/traj_optimizer.cpp:469-525): the velocity control points v_t satisfy
-        // |v_{t+1} - v_t| <= amax dt/(n-1) and |v_t| <= vmax (the first two are fixed by the state), consecutive
-        // position control points differ by v_t dt/n, and C1/C2 continuity carries both bounds across segments.
-        const AgentConstDev& c = L.consts[a];
-        const float dtf = (float)L.dt;
-        float r2 = 0.f;
-        for (int k = 0; k < 3; k++) {
-            const float vmax = (float)c.vmax[k], dv = (float)c.amax[k] * dtf / (float)(kN - 1);
-            float bound[4 * kM + 1];                          // fully unrolled below: stays in registers
-            bound[0] = fabsf(in.velocity[k]);
-            bound[1] = fabsf(in.velocity[k] + in.acceleration[k] * dtf / (float)(kN - 1));
-#pragma unroll
-            for (int t = 2; t <= 4 * kM; t++) bound[t] = fminf(vmax, bound[t - 1] + dv);
-            // a feasible trajectory also keeps the fixed first two within vmax only if the state does; use them as is
-            float reach = 0.f;
-#pragma unroll
-            for (int t = 0; t < 5 * kM; t++)
-                if (t < 5 * (m + 1)) reach += bound[4 * (t / 5) + (t % 5)] * dtf / (float)kN;
-            r2 += reach * reach;
-        }
-        const float r = sqrtf(r2) + sqrtf(far2);
+        float r2 = 0.f, d2 = 0.f;
+        for (int k = 0; k < 3; k++) { r2 += s_reach[m][k] * s_reach[m][k]; d2 += s_dreach[m][k] * s_dreach[m][k]; }
+        const float r = fminf(sqrtf(r2) + sqrtf(far2), sqrtf(d2));
         L.reach[(size_t)a * kM + m] = r * 1.0001f + 1e-3f;
     }
 }
