@@ -165,8 +165,9 @@ private:
             << planning_time.goal_planning_time.average << "," << planning_time.lsc_generation_time.average << ","
             << planning_time.sfc_generation_time.average << "," << planning_time.traj_optimization_time.average << ","
             << mission.mission_file_name << "," << mission.world_file_name << ",LSC,previous_solution,previous_solution,none,"
-            << (param.goal_mode == GoalMode::PRIORBASED ? "prior_based" : param.goal_mode == GoalMode::RIGHTHAND ? "right_hand" : "static")
-            << "," << param.world_dimension << "," << param.dt << "," << param.horizon << "," << param.N_constraint_segments << "\n";
+            // Param::getGoalModeStr indexes its table with planner_mode (src/param.cpp:168-171): "static" for the LSC planner
+            // whatever mode/goal says; kept so that the column matches the reference's files
+            << "static," << param.world_dimension << "," << param.dt << "," << param.horizon << "," << param.N_constraint_segments << "\n";
     }
 };
 
