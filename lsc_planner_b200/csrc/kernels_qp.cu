@@ -10,11 +10,13 @@
 // row, move along the projection z of its normal onto the orthogonal complement of the active normals until the row
 // is met or an active multiplier reaches zero (then that row leaves), repeat.
 //
-// Factorisation: only a THIN orthonormal basis Q (39 x q) of the q active normals and the q x q triangle R
-// (N_active = Q R) are kept, in shared memory. The projection is two passes of classical Gram-Schmidt against Q
-// (re-orthogonalised, so it is as accurate as a full QR), adding a row appends z/|z| as a new column, dropping a row
-// is a sequence of Givens rotations on R's rows and Q's columns. Work per iteration is O(39 q), q ~ 5, instead of
-// the O(39^2) of a full orthogonal factor.
+// Factorisation: only a THIN orthonormal basis Q (39 x q) of the q active normals, the q x q triangle R
+// (N_active = Q R) and its inverse W are kept, in shared memory. The projection is classical Gram-Schmidt against Q with
+// a second pass when the first cancelled most of the vector (so it is as accurate as a full QR), the multiplier step
+// is the product W d, adding a row appends a column to Q, R and W, dropping a row is a sequence of Givens rotations on
+// R's rows and on Q's and W's columns. Work per iteration is O(39 q), q ~ 5-20, instead of the O(39^2) of a full
+// orthogonal factor. Shared-memory operands are staged in registers ahead of the FMAs throughout: the update runs in
+// ONE warp and is a chain of dependent steps, so exposed load latencies, not throughput, set its speed.
 //
 // Rows are never assembled as a matrix. Bounds (SFC boxes + world box), velocity and acceleration limits are priced
 // from x with per-thread constants held in registers (225 variables / stencils spread over the block). LSC rows come
@@ -23,9 +25,10 @@
 // that keeps the iteration count low (4-20) — but distance-gated: in the whitened space every row normal has unit
 // length, so a row's slack cannot fall faster than the iterate travels. Per pair we keep `safe` = (distance travelled
 // when it was last evaluated) + (smallest whitened slack of its rows then); a thread reads that one number per pair
-// (8 B, coalesced) and loads and evaluates the 64 B row only if the travelled distance has reached it. The solve ends
-// when no evaluated row is violated beyond the feasibility tolerance; every skipped row is provably satisfied.
-// The whole block prices (per-thread best -> warp shuffle argmin -> one shared-memory exchange); warp 0 then does the
+// (8 B, coalesced), the pairs whose gate is open are compacted into a shared-memory list, and the list is evaluated
+// evenly spread over the block (branch-free, next record prefetched). The solve ends when no evaluated row is violated
+// beyond the feasibility tolerance; every skipped row is provably satisfied.
+// The whole block prices (per-thread best -> warp redux arg-min -> one shared-memory exchange); warp 0 then does the
 // factorisation update while the other warps wait at the barrier: the step time of a swarm is the slowest agent's
 // solve, so the design minimises one agent's latency, not aggregate throughput.
 #include <cstdlib>
