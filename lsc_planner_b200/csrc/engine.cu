@@ -70,7 +70,7 @@ struct lscgpu_engine {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaStream_t stream_aux = nullptr;     // k_qp_order (needs only the previous step's records) beside k_predict
     cudaEvent_t ev_order = nullptr;
-    bool overlap_sfc = true, lpt_order = true;
+    bool overlap_sfc = true, lpt_order = true, qp_debug = false;
     static constexpr int kMaxGroups = 8;
     int pipeline_groups = 2;
     cudaStream_t stream_grp[kMaxGroups] = {};
@@ -234,6 +234,7 @@ extern "C" int lscgpu_create(const lscgpu_params* p, int n_agents, const lscgpu_
     CUB(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
     if (const char* v = getenv("LSCGPU_OVERLAP_SFC")) e->overlap_sfc = atoi(v) != 0;
     if (const char* v = getenv("LSCGPU_LPT_ORDER")) e->lpt_order = atoi(v) != 0;
+    e->qp_debug = getenv("LSCGPU_QP_DEBUG") != nullptr;
     if (const char* v = getenv("LSCGPU_PIPELINE_GROUPS")) e->pipeline_groups = std::min(std::max(atoi(v), 1), (int)lscgpu_engine::kMaxGroups);
     for (int g = 0; g < lscgpu_engine::kMaxGroups; g++) {
         CUB(cudaStreamCreateWithFlags(&e->stream_grp[g], cudaStreamNonBlocking));
@@ -541,7 +542,7 @@ static int step_device(lscgpu_engine* e) {
     ql.out = e->d_out; ql.prev_traj = e->d_traj; ql.last_cost = e->d_last_cost; ql.flags = e->d_flags;
     ql.goal_kind = e->d_goal_kind;
     ql.counters = e->d_counters;
-    if (getenv("LSCGPU_QP_DEBUG")) { if (!e->d_dbg) CU(cudaMalloc(&e->d_dbg, sizeof(long long) * 8 * (size_t)e->N)); ql.dbg = e->d_dbg; }
+    if (e->qp_debug) { if (!e->d_dbg) CU(cudaMalloc(&e->d_dbg, sizeof(long long) * 8 * (size_t)e->N)); ql.dbg = e->d_dbg; }
     if (groups == 1) {
         if (ordered && side) CU(cudaStreamWaitEvent(s, e->ev_order, 0));
         if (n_local > 0 && e->N > 1) { ll.first = 0; ll.count = n_local; launch_lsc_build(ll, s); launches++; }
@@ -616,7 +617,7 @@ static int finish_steps(lscgpu_engine* e) {
             st.ms_lsc += lsc;
         }
     }
-    if (e->d_dbg && getenv("LSCGPU_QP_DEBUG")) {
+    if (e->d_dbg && e->qp_debug) {
         const int nl = e->a1 - e->a0;
         std::vector<long long> h((size_t)nl * 8);
         CU(cudaMemcpy(h.data(), e->d_dbg, sizeof(long long) * 8 * nl, cudaMemcpyDeviceToHost));

@@ -380,14 +380,18 @@ void launch_lsc_build(const LscLaunch& L, cudaStream_t s) {
     // block size x blocks per SM (register cap): 128x4 and 256x2 run at 128 registers (16 warps per SM), 128x3 at 168,
     // 256x1 / 128x2 at the unconstrained 180. Larger blocks shorten one agent's latency (what matters when the launch
     // is a single wave), more resident warps hide the FP64 dependency chains of the GJK (what matters otherwise).
-    static const char* cfg_env = getenv("LSCGPU_LSC_CFG");
-    const char* cfg = cfg_env ? cfg_env : "256x2";
-    const std::string c(cfg);
-    if (c == "256x1") k_lsc_build<256, 1><<<L.count, 256, 0, s>>>(L);
-    else if (c == "256x2") k_lsc_build<256, 2><<<L.count, 256, 0, s>>>(L);
-    else if (c == "128x2") k_lsc_build<128, 2><<<L.count, 128, 0, s>>>(L);
-    else if (c == "128x3") k_lsc_build<128, 3><<<L.count, 128, 0, s>>>(L);
-    else k_lsc_build<128, 4><<<L.count, 128, 0, s>>>(L);
+    static const int cfg = [] {             // parsed once: 0 = 256x2 (default), 1 = 256x1, 2 = 128x2, 3 = 128x3, 4 = 128x4
+        const char* v = getenv("LSCGPU_LSC_CFG");
+        const std::string c(v ? v : "256x2");
+        return c == "256x1" ? 1 : c == "128x2" ? 2 : c == "128x3" ? 3 : c == "128x4" ? 4 : 0;
+    }();
+    switch (cfg) {
+        case 1: k_lsc_build<256, 1><<<L.count, 256, 0, s>>>(L); break;
+        case 2: k_lsc_build<128, 2><<<L.count, 128, 0, s>>>(L); break;
+        case 3: k_lsc_build<128, 3><<<L.count, 128, 0, s>>>(L); break;
+        case 4: k_lsc_build<128, 4><<<L.count, 128, 0, s>>>(L); break;
+        default: k_lsc_build<256, 2><<<L.count, 256, 0, s>>>(L); break;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------

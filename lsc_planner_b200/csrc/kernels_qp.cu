@@ -736,15 +736,10 @@ void launch_qp_order(int n_local, int a0, const lscgpu_agent_out* out, int* orde
 
 void launch_qp_solve(const QpLaunch& L, cudaStream_t s) {
     if (L.n_problems <= 0) return;
-    // the step time is the slowest agent's solve, so every agent gets several warps for pricing: eight while the
-    // launch still fits one wave at 2 blocks per SM, four otherwise (measured faster than two even when that means
-    // a second wave)
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // the step time is the slowest agent's solve, so every agent gets eight warps for pricing (256 threads, two blocks
+    // per SM); 128 / 64 are kept for experiments (LSCGPU_QP_THREADS)
     static const int forced = getenv("LSCGPU_QP_THREADS") ? atoi(getenv("LSCGPU_QP_THREADS")) : 0;
     const int threads = forced ? forced : 256;
-    (void)sms;
     if (threads >= 256) k_qp_solve<256><<<L.n_problems, 256, 0, s>>>(L);
     else if (threads == 128) k_qp_solve<128><<<L.n_problems, 128, 0, s>>>(L);
     else k_qp_solve<64><<<L.n_problems, 64, 0, s>>>(L);
