@@ -138,7 +138,7 @@ void launch_predict(const PredictLaunch& L, cudaStream_t s) { k_predict<<<L.n_ag
 // previous trajectory (src/multi_sync_simulator.cpp:269-299). Higher-priority agents: closer to their goal than this
 // agent (all of them when this agent is at its goal), not at their goal, and not moving away from this agent. If the
 // nearest of them is closer than priority_dist_threshold the goal is a retreat point; otherwise the grid planner runs,
-// but with distmap_obj == nullptr findLOSFreeGoal accepts every path point (src/grid_based_planner.cpp:355-407), so
+// but with distmap_obj == nullptr findLOSFreeGoal accepts every path point (src/grid_based_planner.cpp:350-407), so
 // the line-of-sight goal is the desired goal whatever path A* returns: only the clip to goal_radius around the end of
 // the initial trajectory remains. Float arithmetic of octomath::Vector3 with explicit roundings.
 // ------------------------------------------------------------------------------------------------------------

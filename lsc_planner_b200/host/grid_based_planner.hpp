@@ -9,7 +9,7 @@
 //
 // The search itself is this repository's own statement of the reference's algorithm on flat arrays: dense per-cell
 // F / g / parent tables instead of node objects, and — because the reference breaks (F, g) ties inside a grid row by
-// the ITERATION ORDER of a std::unordered_map (src/Astar-3D/isearch.cpp:213-249) — an explicit model of that
+// the ITERATION ORDER of a std::unordered_map (src/Astar-3D/isearch.cpp:209-242) — an explicit model of that
 // container's node order (libstdc++ _Hashtable: one forward list, every bucket a contiguous run, new nodes at the
 // front of their bucket's run or of the list, rehash re-threads the list in iteration order), driven by libstdc++'s
 // own growth policy object. Keys hash to themselves, so no hashing code is involved.
@@ -123,7 +123,7 @@ private:
 
 typedef std::array<int, 3> GridCell;
 
-// A* of src/Astar-3D (isearch.cpp:48-288, astar.cpp:17-30) with the options GridBasedPlanner::planAstar passes
+// A* of src/Astar-3D (isearch.cpp:48-284, astar.cpp:18-30) with the options GridBasedPlanner::planAstar passes
 // (environmentoptions.cpp:13-21: Euclidean heuristic, 6-connected, unit cost; hweight 1, g-max tie break).
 // grid[(i * dim[1] + j) * dim[2] + k] != 0 : occupied.
 class AstarExact {
@@ -144,7 +144,7 @@ public:
         auto heur = [&](int i, int j, int z) {
             return std::sqrt((double)((goal[0] - i) * (goal[0] - i) + (goal[1] - j) * (goal[1] - j) + (goal[2] - z) * (goal[2] - z)));
         };
-        auto add_open = [&](int i, int c, double f, double g, int par) {                 // isearch.cpp:251-288
+        auto add_open = [&](int i, int c, double f, double g, int par) {                 // isearch.cpp:244-284
             bool inserted = false;
             HashOrderModel& row = rows[i];
             if (state[c] == 1) {
@@ -166,7 +166,7 @@ public:
         int cur = -1;
         bool found = false;
         while (open_size != 0) {
-            // findMin (:180-211): rows ascending, a later row replaces the incumbent on equal F unless its g is smaller
+            // findMin (:177-207): rows ascending, a later row replaces the incumbent on equal F unless its g is smaller
             cur = -1;
             for (int i = 0; i < H; i++) {
                 if (rows[i].empty()) continue;
@@ -176,7 +176,7 @@ public:
             const int ci = cur / (W * A), cj = (cur / A) % W, cz = cur % A;
             state[cur] = 2;                                  // closed
             expansions++;
-            // deleteMin (:213-249): erase, then re-scan the row in the container's iteration order
+            // deleteMin (:209-242): erase, then re-scan the row in the container's iteration order
             rows[ci].erase(cur, next, key_of);
             int best = -1;
             for (int c = rows[ci].begin(); c >= 0; c = next[c])
@@ -218,7 +218,7 @@ struct GoalObstacle {
     point3d prev_traj_first_end, prev_traj_last_end;        // obs_prev_trajs[oi][0][n], [M-1][n]
 };
 
-// The distance-field part of the occupancy grid (src/grid_based_planner.cpp:103-117) depends only on the map and the
+// The distance-field part of the occupancy grid (src/grid_based_planner.cpp:109-123) depends only on the map and the
 // agent radius: computed once per radius and copied, instead of 18 000 getDistance calls per agent per step.
 struct StaticGridCache {
     std::vector<std::pair<double, std::vector<uint8_t>>> by_radius;
@@ -248,7 +248,7 @@ public:
         return g;
     }
 
-    // plan (:53-66). high_priority == nullptr: no agent is an obstacle ("A* without priority")
+    // plan (:53-68). high_priority == nullptr: no agent is an obstacle ("A* without priority")
     const std::vector<point3d>& plan(const point3d& current_position, const point3d& goal_position, double agent_radius,
                                      double agent_downwash, const std::vector<GoalObstacle>& obstacles,
                                      const std::vector<char>* high_priority) {
@@ -265,7 +265,7 @@ public:
         return path;
     }
 
-    point3d findLOSFreeGoal(const point3d& current_position, const point3d& goal_position, double agent_radius) const {   // :355-407
+    point3d findLOSFreeGoal(const point3d& current_position, const point3d& goal_position, double agent_radius) const {   // :350-407
         point3d los_free_goal = current_position;
         std::vector<point3d> pts = path;
         pts.push_back(goal_position);
@@ -284,7 +284,7 @@ public:
         return los_free_goal;
     }
 
-    bool castRay(const point3d& current_position, const point3d& goal_position, double agent_radius) const {            // :409-433
+    bool castRay(const point3d& current_position, const point3d& goal_position, double agent_radius) const {            // :409-434
         const double max_dist = 1.0;
         const double dist_to_goal = (current_position - goal_position).norm();
         const double dist_threshold = std::sqrt(0.25 * dist_to_goal * dist_to_goal + agent_radius * agent_radius);
@@ -299,7 +299,7 @@ public:
     long long expansions = 0;
 
 private:
-    void updateGridInfo() {                                                                                             // :68-88
+    void updateGridInfo() {                                                                                             // :70-90
         const double r = param.grid_resolution;
         for (int i = 0; i < 3; i++) {
             grid_min[i] = -std::floor((-(double)mission.world_min(i) + SP_EPSILON) / r) * r;
@@ -307,18 +307,18 @@ private:
         }
         for (int i = 0; i < 3; i++) dim[i] = (int)std::round((grid_max[i] - grid_min[i]) / r) + 1;
     }
-    point3d gridVectorToPoint3D(int i, int j, int k) const {                                                            // :318-323
+    point3d gridVectorToPoint3D(int i, int j, int k) const {                                                            // :305-310
         const double r = param.grid_resolution;
         return point3d((float)(grid_min[0] + i * r), (float)(grid_min[1] + j * r), (float)(grid_min[2] + k * r));
     }
-    GridCell point3DToGridVector(const point3d& p) const {                                                              // :343-348
+    GridCell point3DToGridVector(const point3d& p) const {                                                              // :329-334
         const double r = param.grid_resolution;
         return {(int)std::round(((double)p.x() - grid_min[0]) / r), (int)std::round(((double)p.y() - grid_min[1]) / r),
                 (int)std::round(((double)p.z() - grid_min[2]) / r)};
     }
     size_t at(int i, int j, int k) const { return ((size_t)i * dim[1] + j) * dim[2] + k; }
     void updateGridMap(const std::vector<GoalObstacle>& obstacles, double agent_radius, double agent_downwash,
-                       const std::vector<char>* high_priority) {                                                        // :90-190
+                       const std::vector<char>* high_priority) {                                                        // :92-195
         const std::vector<uint8_t>* cached = cache ? cache->find(agent_radius) : nullptr;
         if (cached && cached->size() == (size_t)dim[0] * dim[1] * dim[2]) grid = *cached;
         else grid = staticGrid(agent_radius);
@@ -343,11 +343,11 @@ private:
                     }
         }
     }
-    bool isOccupied(const GridCell& c) const {                                                                          // :252-259
+    bool isOccupied(const GridCell& c) const {                                                                          // :257-264
         for (int i = 0; i < 3; i++) if (c[i] < 0 || c[i] > dim[i] - 1) return true;
         return grid[at(c[0], c[1], c[2])] == GP_OCCUPIED;
     }
-    void updateGridMission(GridCell& start) {                                                                           // :192-240
+    void updateGridMission(GridCell& start) {                                                                           // :197-245
         if (grid[at(start[0], start[1], start[2])] != GP_OCCUPIED) return;
         int min_dist = (int)SP_INFINITY;
         GridCell closest = start;

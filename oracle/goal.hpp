@@ -1,20 +1,20 @@
 // ORACLE — test infrastructure only (see oracle/README.md). CPU restatement of the reference's goal planning, the
 // step before the hot path. Citations relative to /root/reference:
 //   src/traj_planner.cpp:540-608            goalPlanningWithPriority
-//   src/grid_based_planner.cpp:53-66        plan
-//   src/grid_based_planner.cpp:68-88        updateGridInfo
-//   src/grid_based_planner.cpp:90-190       updateGridMap (distance field + higher-priority agents)
-//   src/grid_based_planner.cpp:192-240      updateGridMission (start cell repair)
-//   src/grid_based_planner.cpp:355-407      findLOSFreeGoal
-//   src/grid_based_planner.cpp:409-433      castRay
+//   src/grid_based_planner.cpp:53-68        plan
+//   src/grid_based_planner.cpp:70-90        updateGridInfo
+//   src/grid_based_planner.cpp:92-195       updateGridMap (distance field + higher-priority agents)
+//   src/grid_based_planner.cpp:197-245     updateGridMission (start cell repair)
+//   src/grid_based_planner.cpp:350-407      findLOSFreeGoal
+//   src/grid_based_planner.cpp:409-434      castRay
 //   src/Astar-3D/isearch.cpp:48-105         startSearch (goal test ignores the altitude, :74)
-//   src/Astar-3D/isearch.cpp:107-146        findSuccessors (6-connected: environmentoptions.cpp:13-21)
-//   src/Astar-3D/isearch.cpp:180-288        findMin / deleteMin / addOpen (per-row open lists, g-max tie break)
-//   src/Astar-3D/astar.cpp:17-30            Euclidean heuristic
+//   src/Astar-3D/isearch.cpp:107-144        findSuccessors (6-connected: environmentoptions.cpp:13-21)
+//   src/Astar-3D/isearch.cpp:177-284        findMin / deleteMin / addOpen (per-row open lists, g-max tie break)
+//   src/Astar-3D/astar.cpp:18-30            Euclidean heuristic
 // The open list of the reference is one std::unordered_map per grid row; when a row's minimum is re-scanned after a
 // pop, ties in (F, g) go to the LAST node in the container's iteration order. That order is implementation defined
 // (libstdc++ here); this restatement keeps the same container and the same sequence of insertions and erasures, so
-// it reproduces it. tests/test_oracle_goal.py pins the search against the reference's own Astar-3D sources compiled
+// it reproduces it. tests/test_goal_planning.py pins the search against the reference's own Astar-3D sources compiled
 // into oracle/_ref.
 #pragma once
 #include <array>
@@ -53,7 +53,7 @@ inline std::vector<std::array<int, 3>> astar_search(const std::vector<uint8_t>& 
     std::vector<AstarNode> done;
     int open_size = 0;
 
-    auto add_open = [&](const AstarNode& nn, uint32_t key) {                               // isearch.cpp:251-288
+    auto add_open = [&](const AstarNode& nn, uint32_t key) {                               // isearch.cpp:244-284
         bool inserted = false;
         auto& row = open[nn.i];
         auto it = row.find(key);
@@ -74,11 +74,11 @@ inline std::vector<std::array<int, 3>> astar_search(const std::vector<uint8_t>& 
     AstarNode cur{start[0], start[1], start[2], 0.0, 0.0, -1};
     cur.F = 1.0 * heur(cur.i, cur.j, cur.z);
     add_open(cur, key_of(cur.i, cur.j, cur.z));
-    open_size = 1;                                                                          // isearch.cpp:66
+    open_size = 1;                                                                          // isearch.cpp:67
     bool found = false;
     int cur_idx = -1;
     while (open_size != 0) {
-        // findMin (:180-211): rows in ascending order; on equal F the later row wins when its g is not smaller
+        // findMin (:177-207): rows in ascending order; on equal F the later row wins when its g is not smaller
         AstarNode mn{}; mn.F = std::numeric_limits<double>::infinity(); mn.g = 0;
         bool first = true;
         for (int i = 0; i < H; i++) {
@@ -93,7 +93,7 @@ inline std::vector<std::array<int, 3>> astar_search(const std::vector<uint8_t>& 
         cur = mn;
         done.push_back(cur); cur_idx = (int)done.size() - 1;
         closed.insert({close_key(cur.i, cur.j, cur.z), cur_idx});
-        // deleteMin (:213-249)
+        // deleteMin (:209-242)
         {
             auto& row = open[cur.i];
             row.erase(key_of(cur.i, cur.j, cur.z));
@@ -142,11 +142,11 @@ struct GridPlanner {
     long long expansions = 0;
 
     size_t cidx(int i, int j, int k) const { return ((size_t)i * dim[1] + j) * dim[2] + k; }
-    F3 cell_point(int i, int j, int k) const {                                              // gridVectorToPoint3D :318-323
+    F3 cell_point(int i, int j, int k) const {                                              // gridVectorToPoint3D :305-310
         return f3((float)(grid_min[0] + i * gp.grid_resolution), (float)(grid_min[1] + j * gp.grid_resolution),
                   (float)(grid_min[2] + k * gp.grid_resolution));
     }
-    void update_info() {                                                                    // :68-88
+    void update_info() {                                                                    // :70-90
         const double r = gp.grid_resolution;
         for (int i = 0; i < 3; i++) {
             grid_min[i] = -std::floor((-(double)world_min(i) + 1e-9) / r) * r;
@@ -156,7 +156,7 @@ struct GridPlanner {
     }
     // obstacles: every other agent j: position, radius, downwash; `high[j]` = higher priority
     void update_map(double radius, double downwash, int n, int self, const F3* pos, const AgentConst* ac,
-                    const std::vector<char>* high) {                                        // :90-190
+                    const std::vector<char>* high) {                                        // :92-195
         grid.assign((size_t)dim[0] * dim[1] * dim[2], 0);
         if (dm) {
             const float margin = (float)gp.grid_margin;
@@ -188,17 +188,17 @@ struct GridPlanner {
                     }
         }
     }
-    void to_cell(F3 p, int out[3]) const {                                                  // point3DToGridVector :343-348
+    void to_cell(F3 p, int out[3]) const {                                                  // point3DToGridVector :329-334
         out[0] = (int)std::round(((double)p.x - grid_min[0]) / gp.grid_resolution);
         out[1] = (int)std::round(((double)p.y - grid_min[1]) / gp.grid_resolution);
         out[2] = (int)std::round(((double)p.z - grid_min[2]) / gp.grid_resolution);
     }
-    bool is_occupied(const int c[3]) const {                                                // :252-259
+    bool is_occupied(const int c[3]) const {                                                // :257-264
         for (int i = 0; i < 3; i++) if (c[i] < 0 || c[i] > dim[i] - 1) return true;
         return grid[cidx(c[0], c[1], c[2])] != 0;
     }
     // returns false when the start / goal cell lies outside the grid (the reference would index out of bounds)
-    bool update_mission(F3 current, F3 goal, int start[3], int goal_c[3]) {                 // :192-240
+    bool update_mission(F3 current, F3 goal, int start[3], int goal_c[3]) {                 // :197-245
         to_cell(current, start); to_cell(goal, goal_c);
         for (int i = 0; i < 3; i++) if (start[i] < 0 || start[i] >= dim[i] || goal_c[i] < 0 || goal_c[i] >= dim[i]) return false;
         if (grid[cidx(start[0], start[1], start[2])] != 0) {
@@ -217,7 +217,7 @@ struct GridPlanner {
         }
         return true;
     }
-    // plan (:53-66): fills `path` (world points of the cell path; empty when none)
+    // plan (:53-68): fills `path` (world points of the cell path; empty when none)
     void plan(F3 current, F3 goal, double radius, double downwash, int n, int self, const F3* pos, const AgentConst* ac,
               const std::vector<char>* high) {
         update_info();
@@ -230,7 +230,7 @@ struct GridPlanner {
         expansions += ex;
         for (const auto& c : cells) path.push_back(cell_point(c[0], c[1], c[2]));
     }
-    bool cast_ray(F3 a, F3 b, double radius) const {                                        // :409-433
+    bool cast_ray(F3 a, F3 b, double radius) const {                                        // :409-434
         const double dist = normf(a - b);
         const double thr = std::sqrt(0.25 * dist * dist + radius * radius);
         const double sa = (double)dm->distance(a), sb = (double)dm->distance(b);
@@ -240,7 +240,7 @@ struct GridPlanner {
         const F3 mid = (a + b) * 0.5f;
         return cast_ray(a, mid, radius) && cast_ray(mid, b, radius);
     }
-    F3 los_free_goal(F3 current, F3 goal, double radius) const {                            // :355-407
+    F3 los_free_goal(F3 current, F3 goal, double radius) const {                            // :350-407
         F3 los = current;
         std::vector<F3> pts = path;
         pts.push_back(goal);

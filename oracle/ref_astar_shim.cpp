@@ -2,7 +2,7 @@
 // sources where they lie under /root/reference into oracle/_ref/libref_astar.so. Used only by tests/test_oracle_goal.py
 // to pin the oracle's restatement of the search (including its tie-breaking, which depends on the iteration order of
 // std::unordered_map); never linked into the product. Mirrors GridBasedPlanner::planAstar
-// (src/grid_based_planner.cpp:273-291): AstarPlanner::plan(grid, start, goal, default EnvironmentOptions).
+// (src/grid_based_planner.cpp:278-295): AstarPlanner::plan(grid, start, goal, default EnvironmentOptions).
 // map.h includes "tinyxml2.h" without using it; the build passes -I oracle/ref_stub (an empty header of that name).
 #include <array>
 #include <vector>
