@@ -150,6 +150,7 @@ extern "C" int lscgpu_version(void) { return 100; }
 extern "C" void lscgpu_destroy(lscgpu_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);      // every side stream is joined into this one at the end of a step
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     free_rows(e);
     cudaFree(e->d_rdw); cudaFree(e->d_audit_pos); cudaFree(e->d_audit_ratio); cudaFree(e->d_audit_closest); cudaFree(e->d_dbg);
