@@ -6,7 +6,8 @@
 A "step" is one synchronous replanning step of the whole swarm (every agent replans once), closed loop: the next
 step's states are the new trajectories evaluated at t = dt. Default workload = BASELINE.json configs[4]'s swarm
 (synthetic circle-swap, 1024 agents, simple_forest.bt at the centre), which fits one GPU; with --gpus N the same
-swarm is block-partitioned over N ranks (strong scaling) and every step ends with one NCCL all-gather.
+swarm is dealt out over N ranks in longest-plan-first order (strong scaling) and every step ends with one NCCL
+all-gather; rank 0 then replays the run on a single engine and asserts identical trajectories.
 Prints ONE JSON line (rank 0). See DESIGN.md §6 for the definition of every field.
 """
 from __future__ import annotations
@@ -73,12 +74,6 @@ def peaks():
     return {"hbm_gbs": 6650.0}, "fallback"
 
 
-def fma_peaks():
-    """FP32 / FP64 FMA peaks measured on this pool's B200 by tools/fma_peak.cu (profiles/fma_peaks.json)."""
-    p = os.path.join(ROOT, "profiles", "fma_peaks.json")
-    return json.load(open(p)) if os.path.exists(p) else None
-
-
 def alg_flops_per_replan(n_agents: int, octomap: bool, gjk_iters: float, qp_iters: float):
     """F_lsc = (N-1) M (90 + 46 I_gjk) [FP64 GJK + float margins], F_qp = (K+1)(2 nnz(A) + 1080 + 2*39^2)
     + 2/3 39^3; I_gjk (per hull) and K come from the ORACLE's counters on the same inputs."""
@@ -87,12 +82,6 @@ def alg_flops_per_replan(n_agents: int, octomap: bool, gjk_iters: float, qp_iter
     nnz = 81 * (n_agents - 1) + 618 + (162 if octomap else 0) + 174
     f_qp = (qp_iters + 1) * (2 * nnz + 1080 + 2 * 39 ** 2) + (2.0 / 3.0) * 39 ** 3
     return f_lsc, f_qp
-
-
-def alg_bytes_per_replan(n_agents: int, l_sfc: float) -> float:
-    """neighbours' previous trajectories + radius/downwash, own trajectory, state, goal, SFC window
-    in/out, EDT lookups (4 B each, oracle count), output trajectory, status + cost."""
-    return (n_agents - 1) * 368 + 360 + 36 + 12 + 48 + 4.0 * l_sfc + 360 + 16
 
 
 class ClockSampler:
@@ -172,6 +161,8 @@ def run_reference(args):
         scn = S.random_forest(args.agents, m.sqdist(), m.off, seed=0)
     sw = oracle_swarm(scn, bt, GOAL_MODES[args.goal_mode])
     n = scn.n
+    for _ in range(args.preroll):           # untimed: bring the swarm to the same mission phase as the GPU arm
+        sw.step(0, n, threads); sw.advance()
     budget = 150.0
     t_start = time.perf_counter()
     # warm-up steps plan the whole swarm (closed loop); the first one calibrates the per-agent cost
@@ -202,6 +193,7 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{args.workload}_{n}", "agents": n, "octomap": bool(scn.use_octomap)},
+        "run": {"preroll_steps": args.preroll},
         "cpu_baseline": {"value": value, "unit": "agent-replans/s", "cores": threads, "kind": "port", "sample": what},
         "e2e": {"value": value, "unit": "agent-replans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "oracle_counters_per_replan": {k: v / max(sample * args.steps, 1) for k, v in c.items()},
@@ -210,12 +202,18 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------------------
+def _traj_digest(traj: np.ndarray) -> str:
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(traj).tobytes()).hexdigest()[:16]
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
     import lsc_planner_b200 as L
     from lsc_planner_b200 import _capi as A
+    from lsc_planner_b200 import engine as E
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -239,20 +237,23 @@ def run_ours(args):
                          "octomap the goals come from the host grid planner (lsc_sim)")
     prm = L.Param(world_min=scn.world_min, world_max=scn.world_max, world_use_octomap=scn.use_octomap,
                   goal_mode=GOAL_MODES[args.goal_mode])
-    eng = L.ReplanEngine(n, prm, scn.agents, device=local)
-    if scn.use_octomap:
-        eng.set_octomap_file(bt)
+
+    def new_engine():
+        e = L.ReplanEngine(n, prm, scn.agents, device=local)
+        if scn.use_octomap:
+            e.set_octomap_file(bt)
+        return e
+
+    eng = new_engine()
     if world > 1:
         from lsc_planner_b200 import sharding
         sharding.connect(eng, rank, world)
-    n_local = eng.a1 - eng.a0
+    n_local = eng.n_planned
     stream = torch.cuda.ExternalStream(eng.stream, device=local)
 
-    row_store_bytes = n_local * 5 * (n - 1) * 64
     # every step is timed on its own (begin/end events on the engine stream) with a 256 MB write flushing the 126 MB
-    # L2 in between: the data one step touches (kept rows, distance field tables) is smaller than L2
-    flush = True
-    flush_buf = torch.empty(256 * 2 ** 20, dtype=torch.uint8, device=f"cuda:{local}") if flush else None
+    # L2 in between: the data one step touches (swarm state, distance-field tables) is smaller than L2
+    flush_buf = torch.empty(256 * 2 ** 20, dtype=torch.uint8, device=f"cuda:{local}")
 
     def barrier():
         torch.cuda.synchronize()
@@ -260,43 +261,44 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def resident_steps(k):
+    def resident_steps(k, flush=True):
         for _ in range(k):
             if flush:
                 with torch.cuda.stream(stream):
                     flush_buf.zero_()
             eng.replan_resident(1, sync=False)
 
-    # ---- per-kernel breakdown: the same W + K closed-loop steps with the kernels serialised and CUDA events between
-    # them (profiling mode); the timed pass below overlaps kernels of different agent groups, where per-kernel
-    # durations are not separable
-    eng.set_states(scn.start); eng.set_goals(scn.goal)
+    def restart():
+        eng.reset(); eng.set_states(scn.start); eng.set_goals(scn.goal)
+        resident_steps(args.preroll, flush=False)       # untimed closed-loop steps: choose the mission phase
+        eng.synchronize()
+
+    # ---- FMA peaks of THIS device, in this run (not in MEASURED_PEAKS.json) ----------------------
+    fp = E.measure_fma_peaks(local)
+    lat = E.measure_latencies(local)
+
+    # ---- per-kernel breakdown: the same closed-loop steps with events between the kernels (profiling mode) --------
+    restart()
     eng.set_profiling(True)
     resident_steps(args.warmup)
     eng.synchronize()
     resident_steps(args.steps)
     eng.synchronize()
     st = eng.step_stats()
-    kernel_ms = st["ms_predict"] + st["ms_sfc"] + st["ms_lsc"] + st["ms_qp"] + st["ms_exchange"] + st["ms_commit"]
-    ms_serial = st["ms_total"]
+    prof_out = eng.fetch().copy()
 
     # ---- device-resident throughput (`value`) -----------------------------------------------------------------
-    eng.reset()
-    eng.set_states(scn.start); eng.set_goals(scn.goal)
     eng.set_profiling(False)
+    restart()
     resident_steps(args.warmup)
     eng.synchronize()
     barrier()
     clocks = ClockSampler(local)
-    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
     resident_steps(args.steps)
-    ev1.record(stream)
     eng.synchronize()
     barrier()
     st_timed = eng.step_stats()
-    # with an L2 flush between steps only the steps themselves count; otherwise the whole bracket
-    ms_region = st_timed["ms_steps"] if flush else ev0.elapsed_time(ev1)
+    ms_region = st_timed["ms_steps"]             # sum of the per-step (begin, end) event pairs: the L2 flushes are outside
     t = torch.tensor([ms_region], dtype=torch.float64, device=f"cuda:{local}")
     launches = torch.tensor([st_timed["kernel_launches"]], dtype=torch.int64, device=f"cuda:{local}")
     if world > 1:
@@ -305,16 +307,45 @@ def run_ours(args):
     out_mid = eng.fetch().copy()
     boxes_mid = eng.get_sfc()[0] if scn.use_octomap else None
     assert (out_mid["report"] == 5).all()
+    assert sorted(out_mid["agent_id"].tolist()) == list(range(n)), "every agent must have been planned exactly once"
     qp_fail = int((out_mid["qp_status"] != 0).sum())
     value = n * args.steps / (ms_total * 1e-3)
+    total_steps = args.preroll + args.warmup + args.steps
+
+    # ---- multi-GPU correctness: every replica holds the same swarm, and it is the swarm ONE engine computes --------
+    sharded_check = None
+    if world > 1:
+        mine = torch.from_numpy(out_mid["traj"].copy()).cuda()
+        ref = mine.clone(); dist.broadcast(ref, src=0)
+        same = torch.tensor([int(torch.equal(mine, ref))], device=f"cuda:{local}")
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        single_digest = None
+        if rank == 0:
+            single = new_engine()
+            single.set_states(scn.start); single.set_goals(scn.goal)
+            single.replan_resident(total_steps)
+            so = single.fetch()
+            single_digest = _traj_digest(so["traj"])
+            status_equal = bool(np.array_equal(so["qp_status"], out_mid["qp_status"]))
+            single.close()
+            sharded_check = {"replicas_identical": bool(same.item()), "single_engine_digest": single_digest,
+                             "sharded_digest": _traj_digest(out_mid["traj"]), "qp_status_equal": status_equal,
+                             "steps_replayed": total_steps}
+            assert sharded_check["replicas_identical"], "replicas diverged"
+            assert sharded_check["single_engine_digest"] == sharded_check["sharded_digest"] and status_equal, \
+                f"sharded run differs from the single-engine replay: {sharded_check}"
 
     # ---- end to end through the C-ABI with pinned HOST buffers (`e2e`) ----------------------------------------
-    eng.reset()
-    eng.set_profiling(False)
+    restart()
+    st0 = eng.fetch().copy() if args.preroll else None
     pin_in = torch.zeros(n * A.AGENT_IN.itemsize, dtype=torch.uint8).pin_memory()
     pin_out = torch.zeros(n * A.AGENT_OUT.itemsize, dtype=torch.uint8).pin_memory()
     h_in = pin_in.numpy().view(A.AGENT_IN); h_out = pin_out.numpy().view(A.AGENT_OUT)
-    h_in["position"] = scn.start; h_in["velocity"] = 0; h_in["acceleration"] = 0; h_in["goal"] = scn.goal
+    if st0 is None:
+        h_in["position"] = scn.start; h_in["velocity"] = 0; h_in["acceleration"] = 0
+    else:
+        h_in["position"] = st0["next_position"]; h_in["velocity"] = st0["next_velocity"]; h_in["acceleration"] = st0["next_acceleration"]
+    h_in["goal"] = scn.goal
 
     def host_step():
         eng.replan_ptr(pin_in.data_ptr(), pin_out.data_ptr())      # H2D + kernels (+ all-gather) + D2H, synchronous
@@ -333,13 +364,21 @@ def run_ours(args):
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = n * args.steps / float(e2e_s.item())
     clk = clocks.stop()
+    e2e_matches_resident = bool(np.array_equal(h_out["traj"], out_mid["traj"]))
 
     # ---- roofline of the dominant kernel ------------------------------------------------------------------------
     pk, pk_kind = peaks()
-    per_kernel = {"k_lsc_build": st["ms_lsc"], "k_qp_solve": st["ms_qp"], "k_sfc_expand": st["ms_sfc"],
-                  "k_predict": st["ms_predict"], "k_commit": st["ms_commit"], "nccl_all_gather": st["ms_exchange"]}
-    dom = max(("k_lsc_build", "k_qp_solve", "k_sfc_expand"), key=lambda k: per_kernel[k])
-    dom_ms = per_kernel[dom] / max(st["steps"], 1)
+    n_steps_prof = max(st["steps"], 1)
+    per_kernel = {"k_agent_plan": st["ms_plan"] / n_steps_prof, "k_predict": st["ms_predict"] / n_steps_prof,
+                  "k_commit": st["ms_commit"] / n_steps_prof, "nccl_all_gather": st["ms_exchange"] / n_steps_prof}
+    dom = "k_agent_plan"
+    dom_ms = per_kernel[dom]
+    # split of the fused kernel per agent, from the cycle counters of the result records (last profiled step)
+    cyc = {"corridors_lsc_sfc": float(prof_out["lsc_kcycles"].mean()),
+           "qp": float((prof_out["qp_kcycles"] - prof_out["lsc_kcycles"]).mean()),
+           "qp_pricing": float(prof_out["qp_price_kcycles"].mean())}
+    sm_khz = A.lib().lscgpu_sm_clock_khz(eng.h)
+    per_agent_us = {k: v * 1024.0 / (sm_khz * 1e-3) for k, v in cyc.items()}
 
     # ---- CPU baseline on a bounded sample of the same workload (rank 0, single-GPU runs only) -------------------
     cpu = None
@@ -350,7 +389,7 @@ def run_ours(args):
         # same step as the end of the timed region: the oracle is loaded with the engine's planner state
         sw.set_state(out_mid["next_position"], out_mid["next_velocity"], out_mid["next_acceleration"])
         def restore():
-            sw.set_traj(out_mid["traj"], args.warmup + args.steps)
+            sw.set_traj(out_mid["traj"], total_steps)
             if boxes_mid is not None:
                 sw.set_boxes(boxes_mid, np.zeros(n, np.int32))
         # calibrate on one batch of `threads` agents, then re-plan a sample sized for ~10 s (repeating the same step
@@ -373,75 +412,80 @@ def run_ours(args):
         restore()
         t0 = time.perf_counter(); sw.step(0, s1, 1); one_thread = s1 / max(time.perf_counter() - t0, 1e-9)
         cpu = {"value": s_total / el, "unit": "agent-replans/s", "cores": threads, "kind": "port",
-               "sample": f"oracle (CPU port of the reference path, oracle/) re-plans agents [0,{s}) of the {n}-agent swarm "
-                         f"from the engine's state after the timed region, {reps}x, {threads} threads, {el:.1f} s",
+               "sample": f"oracle (CPU port of the reference path, oracle/, -O3 -march=x86-64-v3) re-plans agents [0,{s}) of the "
+                         f"{n}-agent swarm from the engine's state after the timed region, {reps}x, {threads} threads, {el:.1f} s",
                "one_thread": {"value": one_thread, "unit": "agent-replans/s", "sample": f"agents [0,{s1}) once, 1 thread"},
+               "thread_scaling": (s_total / el) / max(one_thread, 1e-9),
                "per_replan": {"gjk_iterations": c["gjk_iters"] / s_total, "qp_iterations": c["qp_iters"] / s_total,
                               "edt_lookups": l_sfc, "qp_rows": c["qp_rows"] / s_total}}
-    # Algorithmic bytes split by the kernel that consumes / produces each term:
-    #   k_lsc_build : neighbours' previous trajectories + radius/downwash, own trajectory, the kept rows it writes
-    #   k_sfc_expand: the reference's EDT lookups (4 B each, oracle count), SFC window in/out, goal
-    #   k_qp_solve  : the kept rows (64 B record + 8 B gate + 4 B pair index), state, goal, SFC window, result record
-    kept_per_replan = st["lsc_pairs_kept"] / max(st["steps"] * n_local, 1)
-    kernel_bytes = {"k_lsc_build": (n - 1) * 368 + 360 + 76.0 * kept_per_replan,
-                    "k_sfc_expand": 4.0 * l_sfc + 48 + 12 + 36,
-                    "k_qp_solve": 76.0 * kept_per_replan + 36 + 12 + 48 + 360 + 16}
-    b_alg = kernel_bytes[dom] * n_local
+    # Algorithmic bytes of one launch of the dominant kernel = SURVEY.md §8(d)'s per-agent-replan figure without its
+    # `4 L_sfc` term (the reference's brute-force EDT sampling, which this kernel replaces by a few hundred reads of the
+    # L2-resident summed-volume table): every neighbour's prediction + radius/downwash, own trajectory, state, goal, SFC
+    # window in/out, the result record. x agents planned per launch / the kernel's mean duration in the profiled pass.
+    kept_per_replan = st["lsc_pairs_kept"] / max(n_steps_prof * n_local, 1)
+    bytes_per_replan = (n - 1) * 368 + 360 + 36 + 12 + 48 + A.AGENT_OUT.itemsize
+    b_alg = bytes_per_replan * n_local
     achieved = b_alg / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     traffic = None
+    traffic_note = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(f"{args.workload}_{n}", {}).get(dom)
+        ent = json.load(open(tp)).get(f"{args.workload}_{n}", {}).get(dom)
+        if isinstance(ent, dict):
+            traffic, traffic_note = ent.get("bytes_per_launch"), ent.get("captured")
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": f"MEASURED_PEAKS.json ({pk_kind})",
+                "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "traffic_captured": traffic_note,
+                "peak_source": f"MEASURED_PEAKS.json ({pk_kind})",
                 "ms_per_launch": dom_ms, "algorithmic_bytes_per_launch": b_alg,
                 "kept_pairs_per_replan": kept_per_replan,
-                "note": "latency bound, not bandwidth bound (SURVEY.md §8d): the kernel's data is L2-resident and its time "
-                        "is the slowest agent's chain of dependent FP64 steps; the fraction is low by construction; "
-                        "see DESIGN.md §5 and fma_roofline"}
-    # whole path, SURVEY.md §8(d) B_alg per agent-replan (every neighbour read and every EDT lookup of the reference's
-    # algorithm counted as if from HBM) over the whole step's device time
-    b_path = alg_bytes_per_replan(n, l_sfc) * n_local
+                "note": "the swarm state is L2-resident (SURVEY.md §8d): the kernel is bound by FP64 issue (GJK) and by the "
+                        "latency of each agent's active-set chain, see fma_roofline and DESIGN.md §5"}
     step_ms = ms_total / args.steps
+    b_path = bytes_per_replan * n_local
     path_roofline = {"algorithmic_bytes_per_step": b_path, "ms_per_step": step_ms,
                      "achieved": b_path / (step_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                      "frac": b_path / (step_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
-                     "note": "upper bound on necessary traffic: counts the reference's brute-force EDT sampling "
-                             "(4 B x L_sfc) that k_sfc_expand replaces by summed-volume-table reads"}
+                     "note": "SURVEY.md §8(d) B_alg without the 4 L_sfc term, over the whole step's device time; every neighbour "
+                             "read counted as if from HBM (upper bound on necessary traffic)"}
     fma = None
-    fp = fma_peaks()
-    if cpu is not None and fp is not None:
+    if cpu is not None:
         f_lsc, f_qp = alg_flops_per_replan(n, scn.use_octomap, cpu["per_replan"]["gjk_iterations"], cpu["per_replan"]["qp_iterations"])
-        rate = value
         fma = {"algorithmic_flops_per_replan": {"lsc": f_lsc, "qp": f_qp},
-               "achieved_tflops": (f_lsc + f_qp) * rate * 1e-12,
+               "achieved_tflops": (f_lsc + f_qp) * value * 1e-12,
                "fp64_peak_tflops": fp["fp64_tflops"], "fp32_peak_tflops": fp["fp32_tflops"],
-               "frac_of_fp64_peak": (f_lsc + f_qp) * rate * 1e-12 / fp["fp64_tflops"],
-               "note": "all hot-path arithmetic runs in FP64 (GJK, QP); counters from the oracle on the same step"}
+               "peak_source": "lscgpu_measure_fma_peaks, measured in this run on this device",
+               "frac_of_fp64_peak": (f_lsc + f_qp) * value * 1e-12 / max(fp["fp64_tflops"], 1e-9),
+               "note": "SURVEY.md §8d F_alg: the ORACLE's counters on the step after the timed region (un-culled row set, "
+                       "full pricing passes) — work the kernel partly avoids, so this overstates its FMA utilisation"}
     if rank == 0:
         line = {
             "metric": "agent-replans/sec", "value": value, "unit": "agent-replans/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.workload}_{n}", "agents": n, "agents_per_gpu": n_local,
-                       "octomap": bool(scn.use_octomap), "parallelism": f"agents block-partitioned x{world}",
-                       "l2": "L2 flushed (256 MB write) between steps; every step timed on its own with CUDA events on the "
-                             "engine stream; e2e is not flushed (its inputs arrive from host memory every step)",
-                       "goals": ("prior_based goal planning on the GPU every step (k_goal_plan, SURVEY.md §8f #1)" if GOAL_MODES[args.goal_mode]
-                                 else "fixed to the mission goals (goal planning is outside the path, SURVEY.md §8f)")},
+            "config": {"workload": f"{args.workload}_{n}", "agents": n, "octomap": bool(scn.use_octomap)},
+            "run": {"agents_per_gpu": n_local, "preroll_steps": args.preroll,
+                    "parallelism": f"LPT order of the swarm dealt round-robin over {world} rank(s); one NCCL all-gather of "
+                                   f"{A.AGENT_OUT.itemsize} B records per step" if world > 1 else "one engine plans every agent",
+                    "l2": "L2 flushed (256 MB write) between steps; every step timed on its own with CUDA events on the "
+                          "engine stream; e2e is not flushed (its inputs arrive from host memory every step)",
+                    "goals": ("prior_based goal planning on the GPU every step (k_goal_plan, SURVEY.md §8f #1)" if GOAL_MODES[args.goal_mode]
+                              else "fixed to the mission goals (goal planning is outside the path, SURVEY.md §8f)")},
             "e2e": {"value": e2e_value, "unit": "agent-replans/s", "h2d_bytes_per_step": n * A.AGENT_IN.itemsize,
-                    "d2h_bytes_per_step": n * A.AGENT_OUT.itemsize},
+                    "d2h_bytes_per_step": n * A.AGENT_OUT.itemsize, "same_trajectories_as_resident_pass": e2e_matches_resident},
             "gpu_launches": int(launches.item()),
             "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]},
             "roofline": roofline, "path_roofline": path_roofline,
             "fma_roofline": fma,
             "cpu_baseline": cpu,
-            "kernel_ms_per_step": {k: v / max(st["steps"], 1) for k, v in per_kernel.items()},
-            "qp": {"iterations_per_replan": st["qp_iterations"] / max(n_local * st["steps"], 1),
-                   "rows_priced_per_replan": st["qp_rows_priced"] / max(n_local * st["steps"], 1),
-                   "full_sweeps_per_replan": st["qp_full_passes"] / max(n_local * st["steps"], 1),
+            "kernel_ms_per_step": per_kernel,
+            "k_agent_plan_per_agent_us": per_agent_us,
+            "latency_cycles": lat,
+            "qp": {"iterations_per_replan": st["qp_iterations"] / max(n_local * n_steps_prof, 1),
+                   "rows_priced_per_replan": st["qp_rows_priced"] / max(n_local * n_steps_prof, 1),
+                   "pricing_passes_per_replan": st["qp_full_passes"] / max(n_local * n_steps_prof, 1),
                    "gjk_iterations_per_hull": st["gjk_iterations"] / max(st["lsc_pairs"], 1),
-                   "failed_last_step": qp_fail},
+                   "failed_last_step": qp_fail, "qp_failed_fraction": qp_fail / n},
+            "sharded_check": sharded_check,
         }
         print(json.dumps(line), flush=True)
     eng.close()
@@ -459,6 +503,8 @@ def main():
     ap.add_argument("--agents", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--goal-mode", default="static", choices=list(GOAL_MODES))
+    ap.add_argument("--preroll", type=int, default=0,
+                    help="untimed closed-loop steps before the warm-up (e.g. 80: the contact phase of the circle swap)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

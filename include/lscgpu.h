@@ -99,6 +99,7 @@ typedef struct lscgpu_agent_in {
 typedef struct lscgpu_agent_out {
     float traj[LSCGPU_M][LSCGPU_NCP][3];
     float next_position[3], next_velocity[3], next_acceleration[3];   /* trajectory evaluated at t = dt */
+    int32_t agent_id;           /* the agent this record belongs to (records travel between GPUs in scheduling order) */
     double qp_cost;             /* getObjValue incl. the constant of the terminal cost */
     int32_t report;             /* PlanningReport; the reference reports SUCCESS even when the QP failed and keeps the
                                    previous trajectory (src/traj_planner.cpp:1553-1584) — so does this field */
@@ -108,12 +109,17 @@ typedef struct lscgpu_agent_out {
     int32_t flags;              /* LSCGPU_FLAG_* */
     int32_t terminal_segments;  /* getTerminalSegments (src/traj_optimizer.cpp:541-548) */
     int32_t qp_sweeps;          /* verification sweeps over all kept LSC pairs */
-    int32_t qp_kcycles;         /* SM clock cycles / 1024 this agent's QP took (its traj_optimization_time) */
+    int32_t qp_kcycles;         /* SM clock cycles / 1024 this agent's plan took (corridors + QP: its planning time) */
     int32_t qp_price_kcycles;   /* ... of which: pricing the rows (the rest is the factorisation update) */
     int32_t lsc_pairs_kept;     /* (neighbour, segment) pairs that survived the exact culling test */
     float current_goal[3];      /* Agent::current_goal_position the QP used (getCurrentGoalPosition): the input goal, or the
                                    goal chosen by goal planning when lscgpu_params::goal_mode == 1 */
     int32_t goal_kind;          /* goal planning: 0 line-of-sight goal, 1 retreat from the closest higher-priority agent */
+    float sfc_box[6];           /* the SFC box grown in this step (min xyz, max xyz; CorridorConstructor::expandBoxFromPoint):
+                                   the last box of the agent's window, or all five at the first step. Zero without octomap
+                                   or when the seed was blocked (LSCGPU_FLAG_SFC_SEED_BLOCKED) */
+    int32_t lsc_kcycles;        /* ... of qp_kcycles: corridor construction (LSC rows + SFC box) before the QP started */
+    int32_t sfc_in_block;       /* 1: the planning block grew the SFC box itself (k_sfc_step's result was not there in time) */
 } lscgpu_agent_out;
 
 typedef struct lscgpu_engine lscgpu_engine;
@@ -138,9 +144,18 @@ int lscgpu_get_distmap_info(lscgpu_engine* e, int32_t size[3], int32_t offset[3]
 int lscgpu_get_distmap_sqdist(lscgpu_engine* e, uint8_t* out /* size[0]*size[1]*size[2], x-major */);
 
 /* ---- multi-GPU ---------------------------------------------------------------------------------
- * Agents [a0, a1) are planned by this engine; all engines of the job hold a replica of every agent's previous
- * trajectory. No counterpart in the reference (single process; agents planned sequentially,
- * src/multi_sync_simulator.cpp:320-337). */
+ * No counterpart in the reference (single process; agents planned sequentially, src/multi_sync_simulator.cpp:320-337).
+ * Every engine of a job holds a replica of every agent's planner state (previous trajectory, SFC window, last cost).
+ *
+ * lscgpu_nccl_init: G engines (one per GPU / rank) plan one swarm. Each step all ranks derive the same
+ * longest-processing-time-first order of the agents from their replicas, rank r plans entries r, r+G, r+2G, ... of it,
+ * one in-place ncclAllGather of the result records (issued by the library on the engine's stream) completes every
+ * replica, and every rank returns every agent.
+ *
+ * lscgpu_set_shard: no communicator; this engine plans agents [a0, a1) only and commits only those. Records, previous
+ * trajectories and states of the other agents keep whatever the caller last uploaded: a caller that shards by hand must
+ * gather the results itself and refresh every replica (lscgpu_set_prev_traj + the next lscgpu_replan_batch's inputs)
+ * before the next step. */
 int lscgpu_set_shard(lscgpu_engine* e, int a0, int a1);
 int lscgpu_nccl_unique_id(uint8_t id_out[128]);
 int lscgpu_nccl_init(lscgpu_engine* e, const uint8_t id[128], int rank, int n_ranks);
@@ -175,6 +190,12 @@ int lscgpu_get_planner_seq(lscgpu_engine* e);
  * (src/collision_constraints.cpp:362-364): for local agent `agent` and every other agent in id order,
  * normals float[n_agents-1][5][3], margins d double[n_agents-1][5][6]. */
 int lscgpu_get_lsc(lscgpu_engine* e, int agent, float* normals, double* d);
+/* Same, reading what the planning kernel itself built: after lscgpu_set_capture_rows(e, 1) every step also mirrors the
+ * agents' LSC rows (normally shared-memory resident) to global memory; the kept (neighbour, segment) pairs — those the
+ * exact culling test could not prove inactive — are decoded from that row store (kept[n_agents-1][5] = 1), the culled
+ * ones are recomputed. The agent must have been planned by this engine in the last step. */
+int lscgpu_set_capture_rows(lscgpu_engine* e, int on);
+int lscgpu_get_lsc_ex(lscgpu_engine* e, int agent, float* normals, double* d, uint8_t* kept);
 /* initial_traj of every agent of the last step (= the prediction its neighbours used), float[n_agents][90]. */
 int lscgpu_get_initial_traj(lscgpu_engine* e, float* out);
 
@@ -215,7 +236,9 @@ typedef struct lscgpu_step_stats {
     int32_t steps;
     float ms_total;        /* device time, first kernel of the first step to last kernel of the last (CUDA events on
                               the engine stream) */
-    float ms_predict, ms_lsc, ms_sfc, ms_qp, ms_exchange, ms_commit;   /* per-kernel sums; 0 unless profiling is on */
+    /* per-kernel sums, 0 unless profiling is on: k_predict (+ k_goal_plan), k_agent_plan (LSC + SFC + QP of every agent;
+     * lscgpu_agent_out::lsc_kcycles / qp_kcycles split it per agent), the all-gather, k_commit */
+    float ms_predict, ms_plan, ms_sfc /* k_sfc_step: runs beside the others unless profiling */, ms_reserved1_, ms_exchange, ms_commit;
     int32_t kernel_launches;        /* kernels of this library launched */
     int64_t lsc_pairs;              /* (agent, neighbour, segment) pairs of the swarm: (N-1) * 5 per local agent */
     int64_t lsc_pairs_kept;         /* pairs that survived the exact culling test, i.e. GJK hull tests actually run */
@@ -230,6 +253,14 @@ typedef struct lscgpu_step_stats {
 int lscgpu_get_step_stats(lscgpu_engine* e, lscgpu_step_stats* out);
 /* enable per-kernel event timing (event records between the kernels of every step; off by default) */
 int lscgpu_set_profiling(lscgpu_engine* e, int on);
+/* Roofline denominators of `device`, measured now (FMA-chain microbenchmark, ~50 ms): dense FP32 / FP64 FMA TFLOP/s.
+ * MEASURED_PEAKS.json carries only HBM and bf16 tensor figures; this path computes in FP64 on CUDA cores. */
+int lscgpu_measure_fma_peaks(int device, double* fp32_tflops, double* fp64_tflops);
+/* Dependent-issue latencies in SM cycles per operation (one warp, one chain): DFMA, FFMA, shared-memory load, shuffle+DADD
+ * (one round of a double warp reduction), rsqrt(double), double division, redux.sync. They bound the QP's active-set update. */
+int lscgpu_measure_latencies(int device, double cycles_out[7]);
+/* SM clock of the engine's device in kHz (converts the cycle counters of lscgpu_agent_out into seconds) */
+int lscgpu_sm_clock_khz(lscgpu_engine* e);
 /* the CUDA stream all work of this engine is enqueued on (cudaStream_t as void*) */
 void* lscgpu_stream(lscgpu_engine* e);
 

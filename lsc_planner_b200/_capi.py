@@ -7,7 +7,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "liblscgpu.so")
+# LSCGPU_LIB: an instrumented build of the same library (tools/gpu_diag.py with -DLSCGPU_QP_SECTION_TIMERS); never a fallback
+LIB_PATH = os.environ.get("LSCGPU_LIB") or os.path.join(HERE, "liblscgpu.so")
 
 OK = 0
 QP_OK, QP_INFEASIBLE, QP_MAXITER = 0, 1, 2
@@ -32,8 +33,8 @@ class AgentConst(C.Structure):
 
 
 class StepStats(C.Structure):
-    _fields_ = [("steps", C.c_int32), ("ms_total", C.c_float), ("ms_predict", C.c_float), ("ms_lsc", C.c_float),
-                ("ms_sfc", C.c_float), ("ms_qp", C.c_float), ("ms_exchange", C.c_float), ("ms_commit", C.c_float),
+    _fields_ = [("steps", C.c_int32), ("ms_total", C.c_float), ("ms_predict", C.c_float), ("ms_plan", C.c_float),
+                ("ms_sfc", C.c_float), ("ms_reserved1_", C.c_float), ("ms_exchange", C.c_float), ("ms_commit", C.c_float),
                 ("kernel_launches", C.c_int32), ("lsc_pairs", C.c_int64), ("lsc_pairs_kept", C.c_int64), ("gjk_iterations", C.c_int64),
                 ("qp_rows_priced", C.c_int64), ("qp_iterations", C.c_int64), ("qp_full_passes", C.c_int64),
                 ("ms_steps", C.c_float), ("reserved_", C.c_float)]
@@ -44,12 +45,13 @@ AGENT_IN = np.dtype([("position", np.float32, 3), ("velocity", np.float32, 3), (
                      ("goal", np.float32, 3)], align=True)
 AGENT_OUT = np.dtype([("traj", np.float32, (5, 6, 3)), ("next_position", np.float32, 3),
                       ("next_velocity", np.float32, 3), ("next_acceleration", np.float32, 3),
-                      ("qp_cost", np.float64), ("report", np.int32), ("qp_status", np.int32),
+                      ("agent_id", np.int32), ("qp_cost", np.float64), ("report", np.int32), ("qp_status", np.int32),
                       ("qp_iterations", np.int32), ("qp_active", np.int32), ("flags", np.int32),
                       ("terminal_segments", np.int32), ("qp_sweeps", np.int32), ("qp_kcycles", np.int32),
                       ("qp_price_kcycles", np.int32), ("lsc_pairs_kept", np.int32),
-                      ("current_goal", np.float32, 3), ("goal_kind", np.int32)], align=True)
-assert AGENT_IN.itemsize == 48 and AGENT_OUT.itemsize == 464, (AGENT_IN.itemsize, AGENT_OUT.itemsize)
+                      ("current_goal", np.float32, 3), ("goal_kind", np.int32), ("sfc_box", np.float32, 6),
+                      ("lsc_kcycles", np.int32), ("sfc_in_block", np.int32)], align=True)
+assert AGENT_IN.itemsize == 48 and AGENT_OUT.itemsize == 496, (AGENT_IN.itemsize, AGENT_OUT.itemsize)
 
 _lib = None
 ptr = C.c_void_p
@@ -61,9 +63,11 @@ def symbols():
             "lscgpu_set_octomap_voxels", "lscgpu_get_distmap_info", "lscgpu_get_distmap_sqdist", "lscgpu_set_shard",
             "lscgpu_nccl_unique_id", "lscgpu_nccl_init", "lscgpu_replan_batch", "lscgpu_safety_audit", "lscgpu_set_goals",
             "lscgpu_set_states", "lscgpu_replan_resident", "lscgpu_synchronize", "lscgpu_fetch", "lscgpu_reset", "lscgpu_set_prev_traj",
-            "lscgpu_set_sfc", "lscgpu_get_sfc", "lscgpu_get_planner_seq", "lscgpu_get_lsc",
+            "lscgpu_set_sfc", "lscgpu_get_sfc", "lscgpu_get_planner_seq", "lscgpu_get_lsc", "lscgpu_get_lsc_ex",
+            "lscgpu_set_capture_rows",
             "lscgpu_get_initial_traj", "lscgpu_qp_solve_batch", "lscgpu_gjk_batch", "lscgpu_sfc_expand_batch",
-            "lscgpu_get_step_stats", "lscgpu_set_profiling", "lscgpu_stream"]
+            "lscgpu_get_step_stats", "lscgpu_set_profiling", "lscgpu_sm_clock_khz", "lscgpu_stream",
+            "lscgpu_measure_fma_peaks", "lscgpu_measure_latencies"]
 
 
 def lib():
@@ -99,12 +103,17 @@ def lib():
     L.lscgpu_get_sfc.argtypes = [ptr, ptr, ptr]
     L.lscgpu_get_planner_seq.argtypes = [ptr]
     L.lscgpu_get_lsc.argtypes = [ptr, C.c_int, ptr, ptr]
+    L.lscgpu_get_lsc_ex.argtypes = [ptr, C.c_int, ptr, ptr, ptr]
+    L.lscgpu_set_capture_rows.argtypes = [ptr, C.c_int]
     L.lscgpu_get_initial_traj.argtypes = [ptr, ptr]
     L.lscgpu_qp_solve_batch.argtypes = [ptr, C.c_int] + [ptr] * 12
     L.lscgpu_gjk_batch.argtypes = [ptr, C.c_int, ptr, ptr, ptr]
     L.lscgpu_sfc_expand_batch.argtypes = [ptr, C.c_int, ptr, ptr, ptr, ptr, ptr]
     L.lscgpu_get_step_stats.argtypes = [ptr, C.POINTER(StepStats)]
     L.lscgpu_set_profiling.argtypes = [ptr, C.c_int]
+    L.lscgpu_sm_clock_khz.argtypes = [ptr]
+    L.lscgpu_measure_fma_peaks.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.lscgpu_measure_latencies.argtypes = [C.c_int, C.POINTER(C.c_double)]
     L.lscgpu_stream.argtypes = [ptr]; L.lscgpu_stream.restype = ptr
     _lib = L
     return L

@@ -15,7 +15,7 @@
 using namespace lscgpu;
 
 // the ctypes / numpy mirrors in lsc_planner_b200/_capi.py assume these layouts (tests/test_capi_load.py)
-static_assert(sizeof(lscgpu_params) == 112 && sizeof(lscgpu_agent_in) == 48 && sizeof(lscgpu_agent_out) == 464 &&
+static_assert(sizeof(lscgpu_params) == 112 && sizeof(lscgpu_agent_in) == 48 && sizeof(lscgpu_agent_out) == 496 &&
               sizeof(lscgpu_agent_const) == 72, "C-ABI struct layout changed: update _capi.py and the tests");
 
 static thread_local std::string g_error;
@@ -60,25 +60,52 @@ bool load_nccl(std::string& err) {
 }
 }  // namespace
 
+// pinned / device scratch that grows on demand and lives as long as the engine (operator-level entries, setters)
+namespace {
+struct Scratch {
+    void* p = nullptr;
+    size_t bytes = 0;
+    cudaError_t reserve(size_t need) {
+        if (need <= bytes) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; bytes = 0;
+        const size_t grow = std::max(need, (size_t)4096);
+        cudaError_t rc = cudaMalloc(&p, grow);
+        if (rc == cudaSuccess) bytes = grow;
+        return rc;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+// carve typed arrays out of one scratch allocation (256-byte aligned)
+struct Carver {
+    size_t off = 0;
+    template <class T> size_t take(size_t count) {
+        const size_t at = off;
+        off = (off + count * sizeof(T) + 255) & ~(size_t)255;
+        return at;
+    }
+};
+}  // namespace
+
 struct lscgpu_engine {
     lscgpu_params prm{};
     int N = 0, n_pad = 0;            // agents; n_pad = row pitch of the transposed prediction table
-    int a0 = 0, a1 = 0;              // local shard
+    int a0 = 0, a1 = 0;              // agents this engine plans when no communicator is attached
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t stream_sfc = nullptr;     // k_sfc_expand runs beside k_lsc_build (independent until k_qp_solve)
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaStream_t stream_aux = nullptr;     // k_qp_order (needs only the previous step's records) beside k_predict
-    cudaEvent_t ev_order = nullptr;
-    bool overlap_sfc = true, lpt_order = true, qp_debug = false;
-    static constexpr int kMaxGroups = 8;
-    int pipeline_groups = 2;
-    cudaStream_t stream_grp[kMaxGroups] = {};
-    cudaEvent_t ev_lsc[kMaxGroups] = {}, ev_qp[kMaxGroups] = {};
+    cudaEvent_t ev_fork = nullptr, ev_order = nullptr;
+    bool lpt_order = true, qp_debug = false, use_graph = true;
+    int row_cap = 1024;              // kept pairs per agent held in shared memory by k_agent_plan
+    bool mirror_rows = false;        // also write every row to the global store (lscgpu_get_lsc reads production rows)
     long long* d_dbg = nullptr;
     float* d_audit_pos = nullptr; double* d_audit_ratio = nullptr; int* d_audit_closest = nullptr;   // lscgpu_safety_audit scratch
     int audit_samples = 0;
-    int* d_order = nullptr;          // [n_local] local agents, most expensive QP of the previous step first
+    int* d_order = nullptr;          // [N] agents, most expensive plan of the previous step first
+    int* d_block_of = nullptr;       // [N] block (= row-store row) that planned the agent in the last step, -1: not planned here
+    int* d_epoch = nullptr;          // device step counter (k_commit): stamps the results of k_sfc_step
+    int* d_sfc_ready = nullptr; float* d_sfc_box = nullptr; int* d_sfc_ok = nullptr;   // [N] k_sfc_step -> k_agent_plan
+    cudaEvent_t ev_sfc = nullptr;
     int planner_seq = 0;
     bool profiling = false;
     int max_iter = 2000;
@@ -89,14 +116,15 @@ struct lscgpu_engine {
     // device buffers
     QpTablesDev* d_tables = nullptr;
     AgentConstDev* d_consts = nullptr;
-    float2* d_rdw = nullptr;         // [N] (radius, downwash * radius) in float: all the culling pass of k_lsc_build needs
+    float2* d_rdw = nullptr;         // [N] (radius, downwash * radius) in float: all the culling pass needs
     lscgpu_agent_in* d_in = nullptr;
-    lscgpu_agent_out* d_out = nullptr;     // [n_out] gather buffer
-    int n_out = 0;
+    lscgpu_agent_out* d_gather = nullptr;  // [n_slots] records in scheduling order, rank-major: the all-gather buffer
+    lscgpu_agent_out* d_res = nullptr;     // [N] the same records in agent order (k_commit)
+    int n_slots = 0;
     float *d_traj = nullptr, *d_pred = nullptr, *d_predT = nullptr, *d_predZs = nullptr, *d_boxes = nullptr;
     double *d_state9 = nullptr, *d_goal3 = nullptr, *d_last_cost = nullptr;
     int *d_ts = nullptr, *d_flags = nullptr, *d_init_sfc = nullptr, *d_goal_kind = nullptr;
-    // row store of the local shard
+    // overflow / mirror row store: one row of P_pad slots per block of k_agent_plan
     RowRec* d_rows = nullptr;
     int P_pad = 0, n_rows_alloc = 0;
     int *d_kept = nullptr, *d_kept_count = nullptr;
@@ -104,6 +132,8 @@ struct lscgpu_engine {
     float4* d_sphere = nullptr;      // [5][n_pad]
     float* d_reach = nullptr;        // [N][5]
     StepCounters* d_counters = nullptr;
+    Scratch scratch;                 // operator-level entries and setters
+    std::vector<char> host_buf;      // results of an operator-level call, one D2H copy
     // map
     bool have_map = false;
     DistMapDev dm{};
@@ -111,50 +141,78 @@ struct lscgpu_engine {
     // exchange
     NcclComm comm = nullptr;
     int rank = 0, n_ranks = 1, block = 0;
+    // the step as a CUDA graph (steps with planner_seq >= 2 are identical launches)
+    cudaGraphExec_t graph = nullptr;
+    bool graph_failed = false;
+    int graph_launches = 0;
     // instrumentation: steps enqueued since the last synchronize
-    struct StepEvents { cudaEvent_t ev[9]; };   // begin, predict|, sfc[ (side stream) ]sfc, lsc|, qp[ ]qp, exchange|, commit|
+    struct StepEvents { cudaEvent_t ev[7]; };   // begin, predict|, plan|, exchange|, commit|, sfc[ ]sfc
     std::vector<StepEvents> ev_pool;    // per-kernel events of every pending step (profiling mode)
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> step_ev;   // begin / end of every pending step
     int pending = 0, pending_launches = 0;
+    int done_steps = 0, done_launches = 0;      // of the batch the last synchronize completed (stats computed lazily)
+    bool stats_fresh = true;
     lscgpu_step_stats stats{};
+
+    int n_plan() const { return comm ? std::max(0, (N - rank + n_ranks - 1) / n_ranks) : a1 - a0; }
+    int n_plan_max() const { return comm ? (N + n_ranks - 1) / n_ranks : a1 - a0; }
 };
+
+static void drop_graph(lscgpu_engine* e) {
+    if (e->graph) cudaGraphExecDestroy(e->graph);
+    e->graph = nullptr;
+}
 
 static void free_rows(lscgpu_engine* e) {
     cudaFree(e->d_rows); cudaFree(e->d_safe);
-    cudaFree(e->d_kept); cudaFree(e->d_kept_count); cudaFree(e->d_order);
-    e->d_order = nullptr;
+    cudaFree(e->d_kept); cudaFree(e->d_kept_count);
     e->d_rows = nullptr; e->d_safe = nullptr;
     e->d_kept = nullptr; e->d_kept_count = nullptr;
     e->n_rows_alloc = 0;
 }
 
 static int alloc_rows(lscgpu_engine* e) {
-    const int n_local = e->a1 - e->a0;
-    if (n_local <= e->n_rows_alloc) return LSCGPU_OK;
+    drop_graph(e);
+    const int n_rows = std::max(e->n_plan_max(), 1);
+    if (n_rows <= e->n_rows_alloc) return LSCGPU_OK;
     free_rows(e);
     const int P = kPairsPerObs * std::max(e->N - 1, 1);
     e->P_pad = (P + 31) / 32 * 32;
-    CU(cudaMalloc(&e->d_rows, sizeof(RowRec) * (size_t)n_local * e->P_pad));
-    CU(cudaMalloc(&e->d_safe, sizeof(double) * (size_t)n_local * e->P_pad));
-    CU(cudaMalloc(&e->d_kept, sizeof(int) * (size_t)n_local * e->P_pad));
-    CU(cudaMalloc(&e->d_kept_count, sizeof(int) * (size_t)n_local));
-    CU(cudaMalloc(&e->d_order, sizeof(int) * (size_t)n_local));
-    e->n_rows_alloc = n_local;
+    CU(cudaMalloc(&e->d_rows, sizeof(RowRec) * (size_t)n_rows * e->P_pad));
+    CU(cudaMalloc(&e->d_safe, sizeof(double) * (size_t)n_rows * e->P_pad));
+    CU(cudaMalloc(&e->d_kept, sizeof(int) * (size_t)n_rows * e->P_pad));
+    CU(cudaMalloc(&e->d_kept_count, sizeof(int) * (size_t)n_rows));
+    CU(cudaMemset(e->d_kept_count, 0, sizeof(int) * (size_t)n_rows));
+    e->n_rows_alloc = n_rows;
+    return LSCGPU_OK;
+}
+
+static int alloc_gather(lscgpu_engine* e, int n_slots) {
+    if (n_slots <= e->n_slots) return LSCGPU_OK;
+    cudaFree(e->d_gather);
+    e->d_gather = nullptr; e->n_slots = 0;
+    CU(cudaMalloc(&e->d_gather, sizeof(lscgpu_agent_out) * (size_t)n_slots));
+    e->n_slots = n_slots;
     return LSCGPU_OK;
 }
 
 extern "C" const char* lscgpu_last_error(void) { return g_error.c_str(); }
-extern "C" int lscgpu_version(void) { return 100; }
+extern "C" int lscgpu_version(void) { return 200; }
 
 extern "C" void lscgpu_destroy(lscgpu_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
-    if (e->stream) cudaStreamSynchronize(e->stream);      // every side stream is joined into this one at the end of a step
+    if (e->stream) cudaStreamSynchronize(e->stream);      // the aux stream is joined into this one inside every step
+    drop_graph(e);
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     free_rows(e);
+    e->scratch.release();
+    cudaFree(e->d_order); cudaFree(e->d_block_of);
+    cudaFree(e->d_epoch); cudaFree(e->d_sfc_ready); cudaFree(e->d_sfc_box); cudaFree(e->d_sfc_ok);
+    if (e->ev_sfc) cudaEventDestroy(e->ev_sfc);
     cudaFree(e->d_rdw); cudaFree(e->d_audit_pos); cudaFree(e->d_audit_ratio); cudaFree(e->d_audit_closest); cudaFree(e->d_dbg);
-    cudaFree(e->d_tables); cudaFree(e->d_consts); cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_traj);
+    cudaFree(e->d_tables); cudaFree(e->d_consts); cudaFree(e->d_in); cudaFree(e->d_gather); cudaFree(e->d_res); cudaFree(e->d_traj);
     cudaFree(e->d_pred); cudaFree(e->d_predT); cudaFree(e->d_predZs); cudaFree(e->d_boxes); cudaFree(e->d_state9); cudaFree(e->d_goal3);
     cudaFree(e->d_last_cost); cudaFree(e->d_ts); cudaFree(e->d_flags); cudaFree(e->d_init_sfc); cudaFree(e->d_goal_kind); cudaFree(e->d_counters);
     cudaFree(e->dm.sqdist); cudaFree(e->dm.sat); cudaFree(e->d_sphere); cudaFree(e->d_reach);
@@ -162,31 +220,28 @@ extern "C" void lscgpu_destroy(lscgpu_engine* e) {
     for (auto& pr : e->step_ev) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     if (e->ev_begin) cudaEventDestroy(e->ev_begin);
     if (e->ev_end) cudaEventDestroy(e->ev_end);
-    for (int g = 0; g < lscgpu_engine::kMaxGroups; g++) {
-        if (e->ev_lsc[g]) cudaEventDestroy(e->ev_lsc[g]);
-        if (e->ev_qp[g]) cudaEventDestroy(e->ev_qp[g]);
-        if (e->stream_grp[g]) cudaStreamDestroy(e->stream_grp[g]);
-    }
     if (e->ev_order) cudaEventDestroy(e->ev_order);
-    if (e->stream_aux) cudaStreamDestroy(e->stream_aux);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
-    if (e->ev_join) cudaEventDestroy(e->ev_join);
-    if (e->stream_sfc) cudaStreamDestroy(e->stream_sfc);
+    if (e->stream_aux) cudaStreamDestroy(e->stream_aux);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
 
 static int reset_state(lscgpu_engine* e) {
     const size_t N = e->N;
+    CU(cudaStreamSynchronize(e->stream));
     CU(cudaMemsetAsync(e->d_traj, 0, sizeof(float) * N * kTrajFloats, e->stream));      // src/traj_planner.cpp:36-39
     CU(cudaMemsetAsync(e->d_boxes, 0, sizeof(float) * N * 30, e->stream));
     CU(cudaMemsetAsync(e->d_last_cost, 0, sizeof(double) * N, e->stream));
     CU(cudaMemsetAsync(e->d_in, 0, sizeof(lscgpu_agent_in) * N, e->stream));
-    CU(cudaMemsetAsync(e->d_out, 0, sizeof(lscgpu_agent_out) * (size_t)e->n_out, e->stream));
+    CU(cudaMemsetAsync(e->d_res, 0, sizeof(lscgpu_agent_out) * N, e->stream));
+    CU(cudaMemsetAsync(e->d_gather, 0xff, sizeof(lscgpu_agent_out) * (size_t)e->n_slots, e->stream));   // agent_id = -1: empty slot
+    CU(cudaMemsetAsync(e->d_block_of, 0xff, sizeof(int) * N, e->stream));
     std::vector<int> ones(N, 1);                                                         // flag_initialize_sfc, :49
     CU(cudaMemcpyAsync(e->d_init_sfc, ones.data(), sizeof(int) * N, cudaMemcpyHostToDevice, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     e->planner_seq = 0;
+    e->pending = 0; e->pending_launches = 0;
     return LSCGPU_OK;
 }
 
@@ -209,12 +264,14 @@ extern "C" int lscgpu_create(const lscgpu_params* p, int n_agents, const lscgpu_
     CU(cudaSetDevice(device));
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10) return fail(LSCGPU_ERR_CUDA, "device is not sm_100 class; kernels are built for sm_100a only");
+    // the library carries sm_100a SASS only (arch-specific, not forward compatible)
+    if (prop.major != 10 || prop.minor != 0)
+        return fail(LSCGPU_ERR_CUDA, "device is not sm_100 (B200); the kernels are built for sm_100a only");
 
     lscgpu_engine* e = new lscgpu_engine;
     e->prm = *p; e->N = n_agents; e->device = device;
     e->n_pad = (n_agents + 31) / 32 * 32;
-    e->a0 = 0; e->a1 = n_agents; e->block = n_agents; e->n_out = n_agents;
+    e->a0 = 0; e->a1 = n_agents; e->block = n_agents;
     e->consts_host.assign(agents, agents + n_agents);
     if (const char* s = getenv("LSCGPU_MAX_ITER")) e->max_iter = atoi(s);
 
@@ -227,21 +284,16 @@ extern "C" int lscgpu_create(const lscgpu_params* p, int n_agents, const lscgpu_
             return bail(LSCGPU_ERR_CUDA);                                                                 \
         }                                                                                                 \
     } while (0)
+    CUB(configure_agent_plan());
     CUB(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-    CUB(cudaStreamCreateWithFlags(&e->stream_sfc, cudaStreamNonBlocking));
     CUB(cudaStreamCreateWithFlags(&e->stream_aux, cudaStreamNonBlocking));
     CUB(cudaEventCreateWithFlags(&e->ev_order, cudaEventDisableTiming));
     CUB(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
-    CUB(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
-    if (const char* v = getenv("LSCGPU_OVERLAP_SFC")) e->overlap_sfc = atoi(v) != 0;
+    CUB(cudaEventCreateWithFlags(&e->ev_sfc, cudaEventDisableTiming));
     if (const char* v = getenv("LSCGPU_LPT_ORDER")) e->lpt_order = atoi(v) != 0;
+    if (const char* v = getenv("LSCGPU_GRAPH")) e->use_graph = atoi(v) != 0;
+    if (const char* v = getenv("LSCGPU_ROW_CAP")) e->row_cap = std::min(std::max(atoi(v), 0), 2560) / 32 * 32;
     e->qp_debug = getenv("LSCGPU_QP_DEBUG") != nullptr;
-    if (const char* v = getenv("LSCGPU_PIPELINE_GROUPS")) e->pipeline_groups = std::min(std::max(atoi(v), 1), (int)lscgpu_engine::kMaxGroups);
-    for (int g = 0; g < lscgpu_engine::kMaxGroups; g++) {
-        CUB(cudaStreamCreateWithFlags(&e->stream_grp[g], cudaStreamNonBlocking));
-        CUB(cudaEventCreateWithFlags(&e->ev_lsc[g], cudaEventDisableTiming));
-        CUB(cudaEventCreateWithFlags(&e->ev_qp[g], cudaEventDisableTiming));
-    }
     CUB(cudaEventCreate(&e->ev_begin));
     CUB(cudaEventCreate(&e->ev_end));
 
@@ -280,7 +332,15 @@ extern "C" int lscgpu_create(const lscgpu_params* p, int n_agents, const lscgpu_
         CUB(cudaMemcpy(e->d_rdw, rdw.data(), sizeof(float2) * N, cudaMemcpyHostToDevice));
     }
     CUB(cudaMalloc(&e->d_in, sizeof(lscgpu_agent_in) * N));
-    CUB(cudaMalloc(&e->d_out, sizeof(lscgpu_agent_out) * N));
+    CUB(cudaMalloc(&e->d_res, sizeof(lscgpu_agent_out) * N));
+    CUB(cudaMalloc(&e->d_order, sizeof(int) * N));
+    CUB(cudaMalloc(&e->d_block_of, sizeof(int) * N));
+    CUB(cudaMalloc(&e->d_epoch, sizeof(int)));
+    CUB(cudaMemset(e->d_epoch, 0, sizeof(int)));
+    CUB(cudaMalloc(&e->d_sfc_ready, sizeof(int) * N));
+    CUB(cudaMemset(e->d_sfc_ready, 0xff, sizeof(int) * N));
+    CUB(cudaMalloc(&e->d_sfc_box, sizeof(float) * 6 * N));
+    CUB(cudaMalloc(&e->d_sfc_ok, sizeof(int) * N));
     CUB(cudaMalloc(&e->d_traj, sizeof(float) * N * kTrajFloats));
     CUB(cudaMalloc(&e->d_pred, sizeof(float) * N * kTrajFloats));
     CUB(cudaMalloc(&e->d_predT, sizeof(float) * (size_t)kTrajFloats * e->n_pad));
@@ -296,12 +356,15 @@ extern "C" int lscgpu_create(const lscgpu_params* p, int n_agents, const lscgpu_
     CUB(cudaMalloc(&e->d_last_cost, sizeof(double) * N));
     CUB(cudaMalloc(&e->d_ts, sizeof(int) * N));
     CUB(cudaMalloc(&e->d_flags, sizeof(int) * N));
+    CUB(cudaMemset(e->d_flags, 0, sizeof(int) * N));
     CUB(cudaMalloc(&e->d_goal_kind, sizeof(int) * N));
     CUB(cudaMemset(e->d_goal_kind, 0, sizeof(int) * N));
     CUB(cudaMalloc(&e->d_init_sfc, sizeof(int) * N));
     CUB(cudaMalloc(&e->d_counters, sizeof(StepCounters)));
     CUB(cudaMemset(e->d_counters, 0, sizeof(StepCounters)));
-    int rc = alloc_rows(e);
+    int rc = alloc_gather(e, n_agents);
+    if (rc != LSCGPU_OK) return bail(rc);
+    rc = alloc_rows(e);
     if (rc != LSCGPU_OK) return bail(rc);
     rc = reset_state(e);
     if (rc != LSCGPU_OK) return bail(rc);
@@ -315,6 +378,8 @@ static int coord_to_key(double c, double res) { return (int)std::floor((1.0 / re
 
 static int build_map(lscgpu_engine* e, const int32_t* keys, int n) {
     CU(cudaSetDevice(e->device));
+    CU(cudaStreamSynchronize(e->stream));
+    drop_graph(e);                          // the step graph carries the table pointers
     cudaFree(e->dm.sqdist); cudaFree(e->dm.sat);
     e->dm = DistMapDev{};
     e->have_map = false;
@@ -402,9 +467,13 @@ extern "C" int lscgpu_get_distmap_sqdist(lscgpu_engine* e, uint8_t* out) {
 // ---- sharding / NCCL ---------------------------------------------------------------------------------------------
 extern "C" int lscgpu_set_shard(lscgpu_engine* e, int a0, int a1) {
     if (!e || a0 < 0 || a1 > e->N || a0 > a1) return fail(LSCGPU_ERR_ARG, "bad shard range");
-    if (e->comm) return fail(LSCGPU_ERR_STATE, "shard is fixed by lscgpu_nccl_init");
+    if (e->comm) return fail(LSCGPU_ERR_STATE, "the partition is fixed by lscgpu_nccl_init");
+    if (e->pending) return fail(LSCGPU_ERR_STATE, "lscgpu_synchronize first");
     CU(cudaSetDevice(e->device));
     e->a0 = a0; e->a1 = a1;
+    // slots of the gather buffer beyond the shard must read "empty"
+    CU(cudaMemsetAsync(e->d_gather, 0xff, sizeof(lscgpu_agent_out) * (size_t)e->n_slots, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
     return alloc_rows(e);
 }
 
@@ -420,34 +489,127 @@ extern "C" int lscgpu_nccl_unique_id(uint8_t id_out[128]) {
 
 extern "C" int lscgpu_nccl_init(lscgpu_engine* e, const uint8_t id_bytes[128], int rank, int n_ranks) {
     if (!e || !id_bytes || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(LSCGPU_ERR_ARG, "bad rank / n_ranks");
+    if (e->comm) return fail(LSCGPU_ERR_STATE, "a communicator is already attached to this engine");
+    if (e->pending) return fail(LSCGPU_ERR_STATE, "lscgpu_synchronize first");
     std::string err;
     if (!load_nccl(err)) return fail(LSCGPU_ERR_NCCL, err);
     CU(cudaSetDevice(e->device));
     NcclId id;
     std::memcpy(id.internal, id_bytes, 128);
-    const int rc = g_nccl.CommInitRank(&e->comm, n_ranks, id, rank);
-    if (rc != 0) { e->comm = nullptr; return fail(LSCGPU_ERR_NCCL, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?")); }
+    NcclComm comm = nullptr;
+    const int rc = g_nccl.CommInitRank(&comm, n_ranks, id, rank);
+    if (rc != 0) return fail(LSCGPU_ERR_NCCL, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+    e->comm = comm;
     e->rank = rank; e->n_ranks = n_ranks;
-    e->block = (e->N + n_ranks - 1) / n_ranks;           // contiguous blocks; the last ranks may own fewer (or no) agents
-    e->a0 = std::min(e->N, rank * e->block);
-    e->a1 = std::min(e->N, e->a0 + e->block);
-    if (e->block * n_ranks > e->n_out) {
-        cudaFree(e->d_out);
-        e->n_out = e->block * n_ranks;
-        CU(cudaMalloc(&e->d_out, sizeof(lscgpu_agent_out) * (size_t)e->n_out));
-        CU(cudaMemset(e->d_out, 0, sizeof(lscgpu_agent_out) * (size_t)e->n_out));
-    }
+    e->block = (e->N + n_ranks - 1) / n_ranks;           // slots per rank in the gather buffer; the last may stay empty
+    e->a0 = 0; e->a1 = e->N;                             // every rank may plan any agent: the LPT order is dealt out
+    const int r1 = alloc_gather(e, e->block * n_ranks);
+    if (r1 != LSCGPU_OK) return r1;
+    CU(cudaMemset(e->d_gather, 0xff, sizeof(lscgpu_agent_out) * (size_t)e->n_slots));
     return alloc_rows(e);
 }
 
 // ---- the step ----------------------------------------------------------------------------------------------------
+// Kernels of one step on the engine stream `s` (k_qp_order forks onto the aux stream and is joined before the plan):
+//   k_qp_order || k_predict [-> k_goal_plan] -> k_agent_plan -> [ncclAllGather] -> k_commit
+// `ev` (profiling) gets an event after each stage. Callable under stream capture.
+static int enqueue_step_kernels(lscgpu_engine* e, int planner_seq, cudaEvent_t* ev, int* launches_out) {
+    cudaStream_t s = e->stream;
+    int launches = 0;
+    const int n_plan = e->n_plan();
+    const bool dealt = e->comm != nullptr;
+    // scheduling order of this step's blocks from the cost of the previous step's plans (records in d_res)
+    const int n_order = dealt ? e->N : e->a1 - e->a0;
+    const bool ordered = e->lpt_order && planner_seq > 1 && n_order > 1;
+    const bool use_sfc = e->prm.world_use_octomap != 0;
+    const bool side = !e->profiling;
+    cudaStream_t so = side ? e->stream_aux : s;
+    if (side && (ordered || use_sfc)) { CU(cudaEventRecord(e->ev_fork, s)); CU(cudaStreamWaitEvent(so, e->ev_fork, 0)); }
+    if (ordered) {
+        launch_qp_order(n_order, dealt ? 0 : e->a0, e->d_res, e->d_order, so); launches++;
+        if (side) CU(cudaEventRecord(e->ev_order, so));
+    }
+    if (use_sfc && n_plan > 0) {
+        // the step's new SFC boxes depend on the step's inputs only: grown beside k_predict and the LSC rows
+        SfcStepLaunch sl{};
+        sl.n = n_plan;
+        sl.order = ordered ? e->d_order : nullptr;
+        sl.order_first = dealt ? e->rank : 0; sl.order_stride = dealt ? e->n_ranks : 1;
+        sl.agent_base = dealt ? e->rank : e->a0; sl.agent_stride = dealt ? e->n_ranks : 1;
+        sl.dm = e->dm; sl.res = e->prm.world_resolution;
+        for (int k = 0; k < 3; k++) { sl.wmin[k] = e->prm.world_min[k]; sl.wmax[k] = e->prm.world_max[k]; }
+        sl.in = e->d_in; sl.prev_traj = e->d_traj; sl.consts = e->d_consts; sl.init_sfc = e->d_init_sfc;
+        sl.epoch = e->d_epoch; sl.sfc_box_g = e->d_sfc_box; sl.sfc_ok_g = e->d_sfc_ok; sl.sfc_ready = e->d_sfc_ready;
+        if (ev) CU(cudaEventRecord(ev[5], so));
+        launch_sfc_step(sl, so); launches++;
+        if (ev) CU(cudaEventRecord(ev[6], so));
+        if (side) CU(cudaEventRecord(e->ev_sfc, so));
+    }
+    PredictLaunch pl{};
+    pl.n_agents = e->N; pl.n_pad = e->n_pad; pl.planner_seq = planner_seq;
+    pl.dt = e->prm.dt; pl.reset_threshold = e->prm.reset_threshold;
+    pl.in = e->d_in; pl.prev_traj = e->d_traj; pl.consts = e->d_consts;
+    pl.pred = e->d_pred; pl.predT = e->d_predT; pl.predZs = e->d_predZs; pl.state9 = e->d_state9; pl.goal3 = e->d_goal3;
+    pl.ts = e->d_ts; pl.flags = e->d_flags; pl.sphere = e->d_sphere; pl.reach = e->d_reach;
+    launch_predict(pl, s); launches++;
+    if (e->prm.goal_mode == 1) {
+        GoalLaunch gl{};
+        gl.n_agents = e->N; gl.dt = e->prm.dt; gl.goal_threshold = e->prm.goal_threshold; gl.goal_radius = e->prm.goal_radius;
+        gl.priority_dist_threshold = e->prm.priority_dist_threshold;
+        gl.in = e->d_in; gl.prev_traj = e->d_traj; gl.pred = e->d_pred; gl.consts = e->d_consts;
+        gl.goal3 = e->d_goal3; gl.ts = e->d_ts; gl.goal_kind = e->d_goal_kind;
+        launch_goal_plan(gl, s); launches++;
+    }
+    if (ev) CU(cudaEventRecord(ev[1], s));
+    if (ordered && !e->profiling) CU(cudaStreamWaitEvent(s, e->ev_order, 0));
+
+    PlanLaunch L{};
+    L.n_agents = e->N; L.n_pad = e->n_pad; L.n_blocks = n_plan;
+    L.order = ordered ? e->d_order : nullptr;
+    L.order_first = dealt ? e->rank : 0; L.order_stride = dealt ? e->n_ranks : 1;
+    // without an order (first step): rank r of a dealt job takes agents r, r + G, ... through an identity "order"
+    L.agent_base = e->a0;
+    L.agent_stride = dealt ? e->n_ranks : 1;
+    if (dealt) L.agent_base = e->rank;
+    L.pred = e->d_pred; L.predT = e->d_predT; L.predZs = e->d_predZs; L.consts = e->d_consts; L.rdw = e->d_rdw; L.T = e->d_tables;
+    L.state9 = e->d_state9; L.goal3 = e->d_goal3; L.ts = e->d_ts; L.sphere = e->d_sphere; L.reach = e->d_reach;
+    L.row_cap = e->row_cap; L.P_pad = e->P_pad; L.mirror_rows = e->mirror_rows ? 1 : 0;
+    L.rows = e->d_rows; L.kept = e->d_kept; L.kept_count = e->d_kept_count; L.safe = e->d_safe;
+    L.block_of = e->mirror_rows ? e->d_block_of : nullptr;
+    L.use_sfc = e->prm.world_use_octomap ? 1 : 0;
+    L.dm = e->dm; L.res = e->prm.world_resolution;
+    L.epoch = e->d_epoch; L.sfc_ready = e->d_sfc_ready; L.sfc_box_g = e->d_sfc_box; L.sfc_ok_g = e->d_sfc_ok;
+    L.in = e->d_in; L.boxes = e->d_boxes; L.init_sfc = e->d_init_sfc; L.flags = e->d_flags;
+    for (int k = 0; k < 3; k++) { L.wmin[k] = e->prm.world_min[k]; L.wmax[k] = e->prm.world_max[k]; }
+    L.max_iter = e->max_iter;
+    L.out = e->d_gather; L.out_base = dealt ? e->rank * e->block : 0;
+    L.prev_traj = e->d_traj; L.last_cost = e->d_last_cost; L.goal_kind = e->d_goal_kind;
+    L.counters = e->d_counters;
+    if (e->qp_debug) { if (!e->d_dbg) CU(cudaMalloc(&e->d_dbg, sizeof(long long) * 10 * (size_t)e->N)); L.dbg = e->d_dbg; }
+    if (n_plan > 0) { launch_agent_plan(L, s); launches++; }
+    if (ev) CU(cudaEventRecord(ev[2], s));
+
+    if (dealt && e->n_ranks > 1) {
+        // in-place all-gather: every rank's block of records lands in every replica
+        const size_t bytes = sizeof(lscgpu_agent_out) * (size_t)e->block;
+        const int rc = g_nccl.AllGather((const char*)e->d_gather + bytes * e->rank, e->d_gather, bytes, /*ncclInt8*/ 0, e->comm, s);
+        if (rc != 0) return fail(LSCGPU_ERR_NCCL, std::string("ncclAllGather: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+    }
+    if (ev) CU(cudaEventRecord(ev[3], s));
+    const int n_slots = dealt ? e->block * e->n_ranks : n_plan;
+    if (use_sfc && n_plan > 0 && side) CU(cudaStreamWaitEvent(s, e->ev_sfc, 0));     // k_commit rewrites what k_sfc_step reads
+    launch_commit(n_slots, e->d_gather, e->d_res, e->d_traj, e->d_in, e->d_last_cost,
+                  use_sfc ? e->d_boxes : nullptr, e->d_init_sfc, e->d_epoch, s); launches++;
+    if (ev) CU(cudaEventRecord(ev[4], s));
+    *launches_out = launches;
+    return LSCGPU_OK;
+}
+
 static int step_device(lscgpu_engine* e) {
     if (e->prm.world_use_octomap && !e->have_map)
         return fail(LSCGPU_ERR_STATE, "world_use_octomap is set but no octomap was uploaded (lscgpu_set_octomap_*)");
     cudaStream_t s = e->stream;
-    const int n_local = e->a1 - e->a0;
-    e->planner_seq++;                                       // src/traj_planner.cpp:127
-    int launches = 0;
+    const int seq = e->planner_seq + 1;                     // src/traj_planner.cpp:127; committed once the step is enqueued
     const bool prof = e->profiling;
     cudaEvent_t* ev = nullptr;
     if (prof) {
@@ -463,179 +625,119 @@ static int step_device(lscgpu_engine* e) {
         CU(cudaEventCreate(&pr.first)); CU(cudaEventCreate(&pr.second));
         e->step_ev.push_back(pr);
     }
+    if (e->pending == 0 && !e->stats_fresh) {
+        // nobody asked for the statistics of the previous batch: its events are about to be reused, drop its counters too
+        CU(cudaMemsetAsync(e->d_counters, 0, sizeof(StepCounters), s));
+        e->stats = lscgpu_step_stats{};
+        e->stats_fresh = true;
+    }
     if (e->pending == 0) CU(cudaEventRecord(e->ev_begin, s));
     CU(cudaEventRecord(e->step_ev[e->pending].first, s));
     if (prof) CU(cudaEventRecord(ev[0], s));
-    if (n_local > 0) CU(cudaMemsetAsync(e->d_kept_count, 0, sizeof(int) * n_local, s));
-    CU(cudaMemsetAsync(e->d_flags, 0, sizeof(int) * (size_t)e->N, s));      // k_predict and k_sfc_expand OR their bits in
-    const bool do_sfc = e->prm.world_use_octomap && n_local > 0;
-    const bool side = e->overlap_sfc && !e->profiling;      // profiling mode serialises the kernels
-    // scheduling order of this step's LSC / QP blocks from the cost of the previous step's solves (still in d_out)
-    const bool ordered = e->lpt_order && e->planner_seq > 1 && n_local > 1;
-    if (side && (do_sfc || ordered)) CU(cudaEventRecord(e->ev_fork, s));   // k_sfc_expand / k_qp_order need only the inputs
-    if (ordered) {
-        cudaStream_t so = side ? e->stream_aux : s;
-        if (side) CU(cudaStreamWaitEvent(so, e->ev_fork, 0));
-        launch_qp_order(n_local, e->a0, e->d_out, e->d_order, so); launches++;
-        if (side) CU(cudaEventRecord(e->ev_order, so));
-    }
-
-    PredictLaunch pl{};
-    pl.n_agents = e->N; pl.n_pad = e->n_pad; pl.planner_seq = e->planner_seq;
-    pl.dt = e->prm.dt; pl.reset_threshold = e->prm.reset_threshold;
-    pl.in = e->d_in; pl.prev_traj = e->d_traj; pl.consts = e->d_consts;
-    pl.pred = e->d_pred; pl.predT = e->d_predT; pl.predZs = e->d_predZs; pl.state9 = e->d_state9; pl.goal3 = e->d_goal3;
-    pl.ts = e->d_ts; pl.flags = e->d_flags; pl.sphere = e->d_sphere; pl.reach = e->d_reach;
-    launch_predict(pl, s); launches++;
-    if (e->prm.goal_mode == 1) {
-        GoalLaunch gl{};
-        gl.n_agents = e->N; gl.dt = e->prm.dt; gl.goal_threshold = e->prm.goal_threshold; gl.goal_radius = e->prm.goal_radius;
-        gl.priority_dist_threshold = e->prm.priority_dist_threshold;
-        gl.in = e->d_in; gl.prev_traj = e->d_traj; gl.pred = e->d_pred; gl.consts = e->d_consts;
-        gl.goal3 = e->d_goal3; gl.ts = e->d_ts; gl.goal_kind = e->d_goal_kind;
-        launch_goal_plan(gl, s); launches++;
-    }
-    if (prof) CU(cudaEventRecord(ev[1], s));
-
-    // k_sfc_expand depends on the step's inputs only (state, goal, previous trajectory, its own windows) and k_qp_solve is
-    // its only consumer: it runs on a side stream beside k_predict and k_lsc_build
-    cudaStream_t ss = side ? e->stream_sfc : s;
-    if (do_sfc) {
-        if (side) CU(cudaStreamWaitEvent(ss, e->ev_fork, 0));
-        if (prof) CU(cudaEventRecord(ev[2], ss));
-        SfcLaunch sl{};
-        sl.n = n_local; sl.dm = e->dm; sl.res = e->prm.world_resolution;
-        for (int k = 0; k < 3; k++) { sl.wmin[k] = e->prm.world_min[k]; sl.wmax[k] = e->prm.world_max[k]; }
-        sl.mode = 0; sl.agent_base = e->a0;
-        sl.in = e->d_in; sl.prev_traj = e->d_traj; sl.consts = e->d_consts;
-        sl.boxes = e->d_boxes; sl.init_sfc = e->d_init_sfc; sl.flags = e->d_flags;
-        launch_sfc_expand(sl, ss); launches++;
-        if (prof) CU(cudaEventRecord(ev[3], ss));
-        if (side) CU(cudaEventRecord(e->ev_join, ss));
-    } else if (prof) {
-        CU(cudaEventRecord(ev[2], s)); CU(cudaEventRecord(ev[3], s));
-    }
-
-    // LSC + QP, pipelined over groups of agents in scheduling order: k_lsc_build of group g+1 runs beside k_qp_solve of
-    // group g (own stream per group), so the long solves of the few crowded agents (first in the LPT order) overlap
-    // with the corridor construction of everybody else. Profiling mode serialises everything (one group, per-kernel
-    // events); results do not depend on the grouping.
-    int groups = 1;
-    if (!prof && ordered && e->pipeline_groups > 1 && n_local >= 128 * e->pipeline_groups) groups = e->pipeline_groups;
-    LscLaunch ll{};
-    ll.n_agents = e->N; ll.n_pad = e->n_pad; ll.a0 = e->a0; ll.n_local = n_local;
-    ll.order = ordered ? e->d_order : nullptr;
-    ll.pred = e->d_pred; ll.predT = e->d_predT; ll.predZs = e->d_predZs; ll.consts = e->d_consts; ll.rdw = e->d_rdw; ll.T = e->d_tables;
-    ll.state9 = e->d_state9; ll.goal3 = e->d_goal3; ll.ts = e->d_ts;
-    ll.sphere = e->d_sphere; ll.reach = e->d_reach;
-    ll.rows = e->d_rows; ll.P_pad = e->P_pad;
-    ll.kept = e->d_kept; ll.kept_count = e->d_kept_count; ll.safe = e->d_safe;
-    ll.counters = e->d_counters;
-    QpLaunch ql{};
-    ql.T = e->d_tables; ql.consts = e->d_consts;
-    ql.order = ordered ? e->d_order : nullptr;
-    ql.agent_index = nullptr; ql.agent_base = e->a0;
-    ql.state9 = e->d_state9; ql.goal3 = e->d_goal3; ql.ts = e->d_ts;
-    ql.boxes = e->prm.world_use_octomap ? e->d_boxes : nullptr;
-    for (int k = 0; k < 3; k++) { ql.wmin[k] = e->prm.world_min[k]; ql.wmax[k] = e->prm.world_max[k]; }
-    ql.rows = e->d_rows; ql.obs_offset = nullptr; ql.n_obs = e->N - 1; ql.P_pad = e->P_pad;
-    ql.kept = e->d_kept; ql.kept_count = e->d_kept_count; ql.safe = e->d_safe; ql.max_iter = e->max_iter;
-    ql.out = e->d_out; ql.prev_traj = e->d_traj; ql.last_cost = e->d_last_cost; ql.flags = e->d_flags;
-    ql.goal_kind = e->d_goal_kind;
-    ql.counters = e->d_counters;
-    if (e->qp_debug) { if (!e->d_dbg) CU(cudaMalloc(&e->d_dbg, sizeof(long long) * 8 * (size_t)e->N)); ql.dbg = e->d_dbg; }
-    if (groups == 1) {
-        if (ordered && side) CU(cudaStreamWaitEvent(s, e->ev_order, 0));
-        if (n_local > 0 && e->N > 1) { ll.first = 0; ll.count = n_local; launch_lsc_build(ll, s); launches++; }
-        if (prof) CU(cudaEventRecord(ev[4], s));
-        if (do_sfc && side) CU(cudaStreamWaitEvent(s, e->ev_join, 0));
-        if (prof) CU(cudaEventRecord(ev[5], s));
-        if (n_local > 0) { ql.first = 0; ql.n_problems = n_local; launch_qp_solve(ql, s); launches++; }
-    } else {
-        // group sizes: the first (most expensive) groups are the smallest, so their solves start early
-        int first = 0;
-        CU(cudaEventRecord(e->ev_lsc[0], s));           // predictions (and the order) are ready
-        for (int g = 0; g < groups; g++) {
-            const int rest = n_local - first;
-            const int count = g == groups - 1 ? rest : std::max(64, (int)(n_local * (g + 1.0) / (groups * (groups + 1) / 2.0)));
-            const int cnt = std::min(count, rest);
-            if (cnt <= 0) { CU(cudaEventRecord(e->ev_qp[g], s)); continue; }
-            cudaStream_t sg = e->stream_grp[g];
-            CU(cudaStreamWaitEvent(sg, e->ev_lsc[0], 0));
-            if (ordered && side) CU(cudaStreamWaitEvent(sg, e->ev_order, 0));
-            ll.first = first; ll.count = cnt; launch_lsc_build(ll, sg); launches++;
-            if (do_sfc && side) CU(cudaStreamWaitEvent(sg, e->ev_join, 0));
-            ql.first = first; ql.n_problems = cnt; launch_qp_solve(ql, sg); launches++;
-            CU(cudaEventRecord(e->ev_qp[g], sg));
-            first += cnt;
+    int launches = 0;
+    // Steps from the second on are the same launches with the same arguments: one CUDA graph, instantiated at the
+    // first such step and re-launched afterwards (profiling and debug modes enqueue the kernels directly).
+    const bool graphable = e->use_graph && !e->graph_failed && !prof && !e->qp_debug && seq >= 2;
+    if (graphable && !e->graph) {
+        cudaGraph_t g = nullptr;
+        int rc = LSCGPU_OK;
+        if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            rc = enqueue_step_kernels(e, seq, nullptr, &launches);
+            const cudaError_t ce = cudaStreamEndCapture(s, &g);
+            if (rc == LSCGPU_OK && ce == cudaSuccess && g &&
+                cudaGraphInstantiate(&e->graph, g, nullptr, nullptr, 0) == cudaSuccess) {
+                e->graph_launches = launches;
+            } else {
+                e->graph = nullptr; e->graph_failed = true;
+                cudaGetLastError();             // clear the capture error; the kernels are enqueued directly below
+            }
+            if (g) cudaGraphDestroy(g);
+        } else {
+            e->graph_failed = true;
+            cudaGetLastError();
         }
-        for (int g = 0; g < groups; g++) CU(cudaStreamWaitEvent(s, e->ev_qp[g], 0));
     }
-    if (prof) CU(cudaEventRecord(ev[6], s));
-
-    if (e->comm && e->n_ranks > 1) {
-        // in-place all-gather: every rank's block of results lands in every replica
-        const size_t bytes = sizeof(lscgpu_agent_out) * (size_t)e->block;
-        const int rc = g_nccl.AllGather((const char*)e->d_out + bytes * e->rank, e->d_out, bytes, /*ncclInt8*/ 0, e->comm, s);
-        if (rc != 0) return fail(LSCGPU_ERR_NCCL, std::string("ncclAllGather: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+    if (graphable && e->graph) {
+        CU(cudaGraphLaunch(e->graph, s));
+        launches = e->graph_launches;
+    } else {
+        const int rc = enqueue_step_kernels(e, seq, ev, &launches);
+        if (rc != LSCGPU_OK) return rc;
     }
-    if (prof) CU(cudaEventRecord(ev[7], s));
-    launch_commit(e->N, e->d_out, e->d_traj, e->d_in, s); launches++;
-    if (prof) CU(cudaEventRecord(ev[8], s));
     CU(cudaEventRecord(e->step_ev[e->pending].second, s));
     CU(cudaEventRecord(e->ev_end, s));
     CU(cudaGetLastError());
+    e->planner_seq = seq;
     e->pending++;
     e->pending_launches += launches;
     return LSCGPU_OK;
 }
 
+// wait for the enqueued steps; the statistics of the batch are computed when somebody asks for them
 static int finish_steps(lscgpu_engine* e) {
     CU(cudaStreamSynchronize(e->stream));
+    if (e->pending > 0) {
+        e->done_steps = e->pending; e->done_launches = e->pending_launches;
+        e->stats_fresh = false;
+    }
+    e->pending = 0; e->pending_launches = 0;
+    return LSCGPU_OK;
+}
+
+static int compute_stats(lscgpu_engine* e) {
+    if (e->stats_fresh) return LSCGPU_OK;
     lscgpu_step_stats& st = e->stats;
     st = lscgpu_step_stats{};
-    if (e->pending == 0) return LSCGPU_OK;
     StepCounters c;
     CU(cudaMemcpyAsync(&c, e->d_counters, sizeof c, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaMemsetAsync(e->d_counters, 0, sizeof(StepCounters), e->stream));
     CU(cudaStreamSynchronize(e->stream));
-    st.steps = e->pending;
+    st.steps = e->done_steps;
     CU(cudaEventElapsedTime(&st.ms_total, e->ev_begin, e->ev_end));
-    for (int i = 0; i < e->pending; i++) {
+    for (int i = 0; i < e->done_steps; i++) {
         float ms = 0.f;
         CU(cudaEventElapsedTime(&ms, e->step_ev[i].first, e->step_ev[i].second));
         st.ms_steps += ms;
     }
     if (e->profiling) {
-        for (int i = 0; i < e->pending && i < (int)e->ev_pool.size(); i++) {
+        for (int i = 0; i < e->done_steps && i < (int)e->ev_pool.size(); i++) {
             cudaEvent_t* ev = e->ev_pool[i].ev;
-            float ms[8];
-            for (int k = 0; k < 8; k++) CU(cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]));
-            // ev: begin, predict|, sfc[ ]sfc (side stream when overlapped), lsc|, join|, qp|, exchange|, commit|
-            st.ms_predict += ms[0]; st.ms_sfc += ms[2]; st.ms_qp += ms[5]; st.ms_exchange += ms[6]; st.ms_commit += ms[7];
-            float lsc = 0.f;
-            CU(cudaEventElapsedTime(&lsc, ev[3], ev[4]));
-            st.ms_lsc += lsc;
+            float ms[4];
+            for (int k = 0; k < 4; k++) CU(cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]));
+            st.ms_predict += ms[0]; st.ms_plan += ms[1]; st.ms_exchange += ms[2]; st.ms_commit += ms[3];
+            if (e->prm.world_use_octomap && e->n_plan() > 0) {      // serialised in front of k_predict in this mode
+                float sf = 0.f;
+                CU(cudaEventElapsedTime(&sf, ev[5], ev[6]));
+                st.ms_sfc += sf; st.ms_predict -= sf;
+            }
         }
     }
     if (e->d_dbg && e->qp_debug) {
-        const int nl = e->a1 - e->a0;
-        std::vector<long long> h((size_t)nl * 8);
-        CU(cudaMemcpy(h.data(), e->d_dbg, sizeof(long long) * 8 * nl, cudaMemcpyDeviceToHost));
-        int worst = 0; long long wt = -1; long long tot[8] = {0};
-        for (int i = 0; i < nl; i++) { long long t = 0; for (int k = 0; k < 8; k++) { t += h[(size_t)i * 8 + k]; tot[k] += h[(size_t)i * 8 + k]; } if (t > wt) { wt = t; worst = i; } }
-        fprintf(stderr, "[qp dbg] worst local agent %d kcycles: price %lld nv %lld gs %lld solve %lld xupd %lld add %lld drop %lld | mean: price %lld nv %lld gs %lld solve %lld xupd %lld add %lld drop %lld\n", worst,
-                h[(size_t)worst*8]>>10, h[(size_t)worst*8+1]>>10, h[(size_t)worst*8+2]>>10, h[(size_t)worst*8+3]>>10, h[(size_t)worst*8+4]>>10, h[(size_t)worst*8+5]>>10, h[(size_t)worst*8+6]>>10,
-                tot[0]/nl>>10, tot[1]/nl>>10, tot[2]/nl>>10, tot[3]/nl>>10, tot[4]/nl>>10, tot[5]/nl>>10, tot[6]/nl>>10);
+        // section cycle counts of the last step (build with -DLSCGPU_QP_SECTION_TIMERS): slowest block and swarm mean
+        const int nl = e->n_plan();
+        std::vector<long long> h((size_t)nl * 10);
+        CU(cudaMemcpy(h.data(), e->d_dbg, sizeof(long long) * 10 * nl, cudaMemcpyDeviceToHost));
+        int worst = 0; long long wt = -1; long long tot[10] = {0};
+        for (int i = 0; i < nl; i++) {
+            long long t = 0;
+            for (int k = 0; k < 10; k++) { if (k < 8) t += h[(size_t)i * 10 + k]; tot[k] += h[(size_t)i * 10 + k]; }
+            if (t > wt) { wt = t; worst = i; }
+        }
+        const char* names[10] = {"price", "normal", "gs", "ratio", "step", "add", "drop", "corridor", "sfc-warp", "lsc-warps"};
+        std::string line = "[qp dbg] kcycles, slowest block " + std::to_string(worst) + ":";
+        for (int k = 0; k < 10; k++) line += std::string(" ") + names[k] + " " + std::to_string(h[(size_t)worst * 10 + k] >> 10);
+        line += " | mean:";
+        for (int k = 0; k < 10; k++) line += std::string(" ") + names[k] + " " + std::to_string((tot[k] / std::max(nl, 1)) >> 10);
+        fprintf(stderr, "%s\n", line.c_str());
     }
-    st.kernel_launches = e->pending_launches;
-    st.lsc_pairs = (int64_t)e->pending * (e->a1 - e->a0) * (e->N - 1) * kPairsPerObs;
+    st.kernel_launches = e->done_launches;
+    st.lsc_pairs = (int64_t)e->done_steps * e->n_plan() * (e->N - 1) * kPairsPerObs;
     st.lsc_pairs_kept = (int64_t)c.kept_pairs;
     st.gjk_iterations = (int64_t)c.gjk_iterations;
     st.qp_rows_priced = (int64_t)c.rows_priced;
     st.qp_iterations = (int64_t)c.qp_iterations;
     st.qp_full_passes = (int64_t)c.full_passes;
-    e->pending = 0; e->pending_launches = 0;
+    e->stats_fresh = true;
     return LSCGPU_OK;
 }
 
@@ -645,7 +747,7 @@ extern "C" int lscgpu_replan_batch(lscgpu_engine* e, const lscgpu_agent_in* in, 
     CU(cudaMemcpyAsync(e->d_in, in, sizeof(lscgpu_agent_in) * (size_t)e->N, cudaMemcpyHostToDevice, e->stream));
     const int rc = step_device(e);
     if (rc != LSCGPU_OK) return rc;
-    CU(cudaMemcpyAsync(out, e->d_out, sizeof(lscgpu_agent_out) * (size_t)e->N, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(out, e->d_res, sizeof(lscgpu_agent_out) * (size_t)e->N, cudaMemcpyDeviceToHost, e->stream));
     return finish_steps(e);
 }
 
@@ -664,7 +766,7 @@ extern "C" int lscgpu_synchronize(lscgpu_engine* e) {
 extern "C" int lscgpu_fetch(lscgpu_engine* e, lscgpu_agent_out* out) {
     if (!e || !out) return fail(LSCGPU_ERR_ARG, "null argument");
     CU(cudaSetDevice(e->device));
-    CU(cudaMemcpyAsync(out, e->d_out, sizeof(lscgpu_agent_out) * (size_t)e->N, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(out, e->d_res, sizeof(lscgpu_agent_out) * (size_t)e->N, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     return LSCGPU_OK;
 }
@@ -687,28 +789,28 @@ __global__ void k_set_states(int n, const float* pos, const float* vel, const fl
 extern "C" int lscgpu_set_goals(lscgpu_engine* e, const float* goals) {
     if (!e || !goals) return fail(LSCGPU_ERR_ARG, "null argument");
     CU(cudaSetDevice(e->device));
-    float* d = nullptr;
     const size_t bytes = sizeof(float) * 3 * (size_t)e->N;
-    CU(cudaMalloc(&d, bytes));
+    CU(cudaStreamSynchronize(e->stream));
+    CU(e->scratch.reserve(bytes));
+    float* d = (float*)e->scratch.p;
     CU(cudaMemcpyAsync(d, goals, bytes, cudaMemcpyHostToDevice, e->stream));
     k_set_goals<<<(e->N * 3 + 127) / 128, 128, 0, e->stream>>>(e->N, d, e->d_in);
     CU(cudaStreamSynchronize(e->stream));
-    cudaFree(d);
     return LSCGPU_OK;
 }
 
 extern "C" int lscgpu_set_states(lscgpu_engine* e, const float* pos, const float* vel, const float* acc) {
     if (!e || !pos || !vel || !acc) return fail(LSCGPU_ERR_ARG, "null argument");
     CU(cudaSetDevice(e->device));
-    float* d = nullptr;
     const size_t n3 = 3 * (size_t)e->N;
-    CU(cudaMalloc(&d, sizeof(float) * 3 * n3));
+    CU(cudaStreamSynchronize(e->stream));
+    CU(e->scratch.reserve(sizeof(float) * 3 * n3));
+    float* d = (float*)e->scratch.p;
     CU(cudaMemcpyAsync(d, pos, sizeof(float) * n3, cudaMemcpyHostToDevice, e->stream));
     CU(cudaMemcpyAsync(d + n3, vel, sizeof(float) * n3, cudaMemcpyHostToDevice, e->stream));
     CU(cudaMemcpyAsync(d + 2 * n3, acc, sizeof(float) * n3, cudaMemcpyHostToDevice, e->stream));
     k_set_states<<<(e->N * 3 + 127) / 128, 128, 0, e->stream>>>(e->N, d, d + n3, d + 2 * n3, e->d_in);
     CU(cudaStreamSynchronize(e->stream));
-    cudaFree(d);
     return LSCGPU_OK;
 }
 
@@ -747,20 +849,70 @@ extern "C" int lscgpu_get_sfc(lscgpu_engine* e, float* boxes, int32_t* init) {
 
 extern "C" int lscgpu_get_planner_seq(lscgpu_engine* e) { return e ? e->planner_seq : -1; }
 
-extern "C" int lscgpu_get_lsc(lscgpu_engine* e, int agent, float* normals, double* d) {
+extern "C" int lscgpu_set_capture_rows(lscgpu_engine* e, int on) {
+    if (!e) return fail(LSCGPU_ERR_ARG, "null engine");
+    if (e->pending) return fail(LSCGPU_ERR_STATE, "lscgpu_synchronize first");
+    e->mirror_rows = on != 0;
+    drop_graph(e);
+    return LSCGPU_OK;
+}
+
+// Rows of `agent` as k_agent_plan built them in the last step (needs lscgpu_set_capture_rows before that step): the kept
+// (neighbour, segment) pairs decoded from the mirrored row store — normal = the record's a, d_i = rhs_i - a . o_{m,i} —
+// and, for the pairs the exact culling test dropped, the values k_lsc_capture recomputes. kept_out (optional) marks which
+// is which.
+extern "C" int lscgpu_get_lsc_ex(lscgpu_engine* e, int agent, float* normals, double* d, uint8_t* kept_out) {
     if (!e || !normals || !d || agent < 0 || agent >= e->N) return fail(LSCGPU_ERR_ARG, "bad argument");
     if (e->N < 2) return LSCGPU_OK;
     CU(cudaSetDevice(e->device));
     const size_t n_obs = e->N - 1;
-    float* dn = nullptr; double* dd = nullptr;
-    CU(cudaMalloc(&dn, sizeof(float) * n_obs * 15));
-    CU(cudaMalloc(&dd, sizeof(double) * n_obs * 30));
+    CU(cudaStreamSynchronize(e->stream));
+    Carver cv;
+    const size_t o_n = cv.take<float>(n_obs * 15), o_d = cv.take<double>(n_obs * 30);
+    CU(e->scratch.reserve(cv.off));
+    float* dn = (float*)((char*)e->scratch.p + o_n); double* dd = (double*)((char*)e->scratch.p + o_d);
     launch_lsc_capture(e->N, agent, e->d_pred, e->d_consts, dn, dd, e->stream);
     CU(cudaMemcpyAsync(normals, dn, sizeof(float) * n_obs * 15, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaMemcpyAsync(d, dd, sizeof(double) * n_obs * 30, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
-    cudaFree(dn); cudaFree(dd);
+    if (kept_out) std::memset(kept_out, 0, n_obs * kPairsPerObs);
+    if (!e->mirror_rows) {
+        if (kept_out) return fail(LSCGPU_ERR_STATE, "lscgpu_set_capture_rows(e, 1) before the step to read the production rows");
+        return LSCGPU_OK;
+    }
+    int bi = -1;
+    CU(cudaMemcpy(&bi, e->d_block_of + agent, sizeof(int), cudaMemcpyDeviceToHost));
+    if (bi < 0) return fail(LSCGPU_ERR_STATE, "the agent was not planned by this engine in the last step");
+    int n_kept = 0;
+    CU(cudaMemcpy(&n_kept, e->d_kept_count + bi, sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<RowRec> rows(n_kept);
+    std::vector<int> kept(n_kept);
+    std::vector<float> pred((size_t)e->N * kTrajFloats);
+    if (n_kept > 0) {
+        CU(cudaMemcpy(rows.data(), e->d_rows + (size_t)bi * e->P_pad, sizeof(RowRec) * n_kept, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(kept.data(), e->d_kept + (size_t)bi * e->P_pad, sizeof(int) * n_kept, cudaMemcpyDeviceToHost));
+    }
+    CU(cudaMemcpy(pred.data(), e->d_pred, sizeof(float) * pred.size(), cudaMemcpyDeviceToHost));
+    for (int sidx = 0; sidx < n_kept; sidx++) {
+        const int p = kept[sidx];
+        const int m = p / (int)n_obs, jj = p % (int)n_obs;
+        const int j = jj < agent ? jj : jj + 1;
+        const RowRec& r = rows[sidx];
+        float* no = normals + ((size_t)jj * kM + m) * 3;
+        no[0] = r.ax; no[1] = r.ay; no[2] = r.az;
+        const double ax = r.ax, ay = r.ay, az = r.az;
+        for (int i = 0; i < 6; i++) {
+            const float* o = pred.data() + (size_t)j * kTrajFloats + (m * 6 + i) * 3;
+            const double t0 = ax * (double)o[0], t1 = ay * (double)o[1], t2 = az * (double)o[2];
+            d[((size_t)jj * kM + m) * 6 + i] = r.rhs[i] - ((t0 + t1) + t2);
+        }
+        if (kept_out) kept_out[(size_t)jj * kM + m] = 1;
+    }
     return LSCGPU_OK;
+}
+
+extern "C" int lscgpu_get_lsc(lscgpu_engine* e, int agent, float* normals, double* d) {
+    return lscgpu_get_lsc_ex(e, agent, normals, d, nullptr);
 }
 
 extern "C" int lscgpu_get_initial_traj(lscgpu_engine* e, float* out) {
@@ -772,21 +924,8 @@ extern "C" int lscgpu_get_initial_traj(lscgpu_engine* e, float* out) {
 }
 
 // ---- operator-level entries ------------------------------------------------------------------------------------------
-namespace {
-struct DevBuf {
-    std::vector<void*> ptrs;
-    ~DevBuf() { for (void* p : ptrs) cudaFree(p); }
-    template <class T>
-    cudaError_t get(T** out, size_t count) {
-        void* p = nullptr;
-        cudaError_t rc = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
-        if (rc == cudaSuccess) ptrs.push_back(p);
-        *out = (T*)p;
-        return rc;
-    }
-};
-}  // namespace
-
+// Device scratch comes from the engine's pool (one allocation that only grows): a batch-of-one TrajOptimizer::solve
+// pays four copies in, one kernel chain and one copy out, no cudaMalloc.
 extern "C" int lscgpu_qp_solve_batch(lscgpu_engine* e, int nb, const int32_t* agent_index, const double* state,
                                      const double* goal, const float* sfc, const int32_t* obs_offset,
                                      const float* lsc_normal, const float* lsc_point, const double* lsc_d, double* x,
@@ -803,49 +942,56 @@ extern "C" int lscgpu_qp_solve_batch(lscgpu_engine* e, int nb, const int32_t* ag
     if (total_obs > 0 && (!lsc_normal || !lsc_point || !lsc_d)) return fail(LSCGPU_ERR_ARG, "null LSC arrays");
     CU(cudaSetDevice(e->device));
     cudaStream_t s = e->stream;
-    DevBuf B;
-    int *d_ai, *d_off, *d_ts, *d_status, *d_iters, *d_kept, *d_kc;
-    double *d_state, *d_goal, *d_d, *d_x, *d_cost, *d_safe;
-    float *d_sfc = nullptr, *d_n, *d_p;
-    RowRec* d_rows;
-    const size_t pairs = (size_t)total_obs * kPairsPerObs;
-    CU(B.get(&d_ai, nb)); CU(B.get(&d_off, nb + 1)); CU(B.get(&d_ts, nb)); CU(B.get(&d_safe, pairs));
-    CU(B.get(&d_status, nb)); CU(B.get(&d_iters, nb));
-    CU(B.get(&d_kept, pairs)); CU(B.get(&d_kc, nb));
-    CU(cudaMemsetAsync(d_kc, 0, sizeof(int) * nb, s));
-    CU(B.get(&d_state, (size_t)nb * 9)); CU(B.get(&d_goal, (size_t)nb * 3)); CU(B.get(&d_d, pairs * 6));
-    CU(B.get(&d_x, (size_t)nb * kNv)); CU(B.get(&d_cost, nb));
-    CU(B.get(&d_n, pairs * 3)); CU(B.get(&d_p, pairs * 18)); CU(B.get(&d_rows, pairs));
-    CU(cudaMemcpyAsync(d_ai, agent_index, sizeof(int) * nb, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(d_off, obs_offset, sizeof(int) * (nb + 1), cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(d_state, state, sizeof(double) * 9 * nb, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(d_goal, goal, sizeof(double) * 3 * nb, cudaMemcpyHostToDevice, s));
-    if (sfc) {
-        CU(B.get(&d_sfc, (size_t)nb * 30));
-        CU(cudaMemcpyAsync(d_sfc, sfc, sizeof(float) * 30 * nb, cudaMemcpyHostToDevice, s));
-    }
+    CU(cudaStreamSynchronize(s));                 // the pool may still be in use by an enqueued step's caller
+    const size_t pairs = (size_t)total_obs * kPairsPerObs, pp = std::max<size_t>(pairs, 1);
+    Carver cv;
+    // results first, contiguous: x | cost | status | iterations come back in one copy
+    const size_t o_x = cv.off; cv.off += sizeof(double) * kNv * nb;
+    const size_t o_cost = cv.off; cv.off += sizeof(double) * nb;
+    const size_t o_status = cv.off; cv.off += sizeof(int) * nb;
+    const size_t o_iters = cv.off; cv.off += sizeof(int) * nb;
+    const size_t out_bytes = cv.off;
+    cv.off = (cv.off + 255) & ~(size_t)255;
+    const size_t o_ai = cv.take<int>(nb), o_off = cv.take<int>(nb + 1), o_ts = cv.take<int>(nb), o_kc = cv.take<int>(nb);
+    const size_t o_state = cv.take<double>((size_t)nb * 9), o_goal = cv.take<double>((size_t)nb * 3);
+    const size_t o_sfc = cv.take<float>((size_t)nb * 30);
+    const size_t o_n = cv.take<float>(pp * 3), o_p = cv.take<float>(pp * 18), o_d = cv.take<double>(pp * 6);
+    const size_t o_rows = cv.take<RowRec>(pp), o_kept = cv.take<int>(pp), o_safe = cv.take<double>(pp);
+    CU(e->scratch.reserve(cv.off));
+    char* base = (char*)e->scratch.p;
+    auto at = [&](size_t o) { return base + o; };
+    CU(cudaMemcpyAsync(at(o_ai), agent_index, sizeof(int) * nb, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(at(o_off), obs_offset, sizeof(int) * (nb + 1), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(at(o_state), state, sizeof(double) * 9 * nb, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(at(o_goal), goal, sizeof(double) * 3 * nb, cudaMemcpyHostToDevice, s));
+    if (sfc) CU(cudaMemcpyAsync(at(o_sfc), sfc, sizeof(float) * 30 * nb, cudaMemcpyHostToDevice, s));
+    CU(cudaMemsetAsync(at(o_kc), 0, sizeof(int) * nb, s));
     if (pairs) {
-        CU(cudaMemcpyAsync(d_n, lsc_normal, sizeof(float) * pairs * 3, cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(d_p, lsc_point, sizeof(float) * pairs * 18, cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(d_d, lsc_d, sizeof(double) * pairs * 6, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(at(o_n), lsc_normal, sizeof(float) * pairs * 3, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(at(o_p), lsc_point, sizeof(float) * pairs * 18, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(at(o_d), lsc_d, sizeof(double) * pairs * 6, cudaMemcpyHostToDevice, s));
     }
-    launch_rows_from_lsc(nb, d_off, total_obs, d_n, d_p, d_d, d_rows, d_kept, d_kc, d_safe, s);
-    launch_terminal_segments(nb, d_state, d_goal, d_ai, e->d_consts, e->prm.dt, d_ts, s);
-    QpLaunch ql{};
-    ql.n_problems = nb; ql.T = e->d_tables; ql.consts = e->d_consts; ql.agent_index = d_ai; ql.agent_base = 0;
-    ql.state9 = d_state; ql.goal3 = d_goal; ql.ts = d_ts; ql.boxes = d_sfc;
+    launch_rows_from_lsc(nb, (int*)at(o_off), total_obs, (float*)at(o_n), (float*)at(o_p), (double*)at(o_d), (RowRec*)at(o_rows),
+                         (int*)at(o_kept), (int*)at(o_kc), (double*)at(o_safe), s);
+    launch_terminal_segments(nb, (double*)at(o_state), (double*)at(o_goal), (int*)at(o_ai), e->d_consts, e->prm.dt, (int*)at(o_ts), s);
+    QpBatchLaunch ql{};
+    ql.n_problems = nb; ql.T = e->d_tables; ql.consts = e->d_consts; ql.agent_index = (int*)at(o_ai);
+    ql.state9 = (double*)at(o_state); ql.goal3 = (double*)at(o_goal); ql.ts = (int*)at(o_ts);
+    ql.boxes = sfc ? (float*)at(o_sfc) : nullptr;
     for (int k = 0; k < 3; k++) { ql.wmin[k] = e->prm.world_min[k]; ql.wmax[k] = e->prm.world_max[k]; }
-    ql.rows = d_rows; ql.obs_offset = d_off; ql.n_obs = 0; ql.P_pad = (int)pairs;
-    ql.kept = d_kept; ql.kept_count = d_kc; ql.safe = d_safe; ql.max_iter = e->max_iter;
-    ql.x_out = d_x; ql.cost_out = d_cost; ql.status_out = d_status; ql.iters_out = d_iters;
-    ql.out = nullptr; ql.counters = nullptr;
-    launch_qp_solve(ql, s);
+    ql.rows = (RowRec*)at(o_rows); ql.obs_offset = (int*)at(o_off);
+    ql.kept = (int*)at(o_kept); ql.kept_count = (int*)at(o_kc); ql.safe = (double*)at(o_safe); ql.max_iter = e->max_iter;
+    ql.x_out = (double*)at(o_x); ql.cost_out = (double*)at(o_cost); ql.status_out = (int*)at(o_status); ql.iters_out = (int*)at(o_iters);
+    launch_qp_batch(ql, s);
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(x, d_x, sizeof(double) * kNv * nb, cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(cost, d_cost, sizeof(double) * nb, cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(status, d_status, sizeof(int) * nb, cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(iterations, d_iters, sizeof(int) * nb, cudaMemcpyDeviceToHost, s));
+    std::vector<char>& hb = e->host_buf;
+    hb.resize(out_bytes);
+    CU(cudaMemcpyAsync(hb.data(), base, out_bytes, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
+    std::memcpy(x, hb.data() + o_x, sizeof(double) * kNv * nb);
+    std::memcpy(cost, hb.data() + o_cost, sizeof(double) * nb);
+    std::memcpy(status, hb.data() + o_status, sizeof(int) * nb);
+    std::memcpy(iterations, hb.data() + o_iters, sizeof(int) * nb);
     return LSCGPU_OK;
 }
 
@@ -853,9 +999,12 @@ extern "C" int lscgpu_gjk_batch(lscgpu_engine* e, int n, const double* hulls, do
     if (!e || n < 0 || !hulls || !v || !iterations) return fail(LSCGPU_ERR_ARG, "null argument");
     if (n == 0) return LSCGPU_OK;
     CU(cudaSetDevice(e->device));
-    DevBuf B;
-    double *dh, *dv; int* di;
-    CU(B.get(&dh, (size_t)n * 18)); CU(B.get(&dv, (size_t)n * 3)); CU(B.get(&di, n));
+    CU(cudaStreamSynchronize(e->stream));
+    Carver cv;
+    const size_t o_h = cv.take<double>((size_t)n * 18), o_v = cv.take<double>((size_t)n * 3), o_i = cv.take<int>(n);
+    CU(e->scratch.reserve(cv.off));
+    char* base = (char*)e->scratch.p;
+    double* dh = (double*)(base + o_h); double* dv = (double*)(base + o_v); int* di = (int*)(base + o_i);
     CU(cudaMemcpyAsync(dh, hulls, sizeof(double) * 18 * n, cudaMemcpyHostToDevice, e->stream));
     launch_gjk_batch(n, dh, dv, di, e->stream);
     CU(cudaGetLastError());
@@ -878,17 +1027,21 @@ extern "C" int lscgpu_sfc_expand_batch(lscgpu_engine* e, int n, const float* poi
         sat[i] = (int)t;
     }
     CU(cudaSetDevice(e->device));
-    DevBuf B;
-    float *dp, *dg, *db; int *ds, *dk;
-    CU(B.get(&dp, (size_t)n * 3)); CU(B.get(&dg, (size_t)n * 3)); CU(B.get(&db, (size_t)n * 6));
-    CU(B.get(&ds, n)); CU(B.get(&dk, n));
+    CU(cudaStreamSynchronize(e->stream));
+    Carver cv;
+    const size_t o_p = cv.take<float>((size_t)n * 3), o_g = cv.take<float>((size_t)n * 3), o_b = cv.take<float>((size_t)n * 6);
+    const size_t o_s = cv.take<int>(n), o_k = cv.take<int>(n);
+    CU(e->scratch.reserve(cv.off));
+    char* base = (char*)e->scratch.p;
+    float* dp = (float*)(base + o_p); float* dg = (float*)(base + o_g); float* db = (float*)(base + o_b);
+    int* ds = (int*)(base + o_s); int* dk = (int*)(base + o_k);
     CU(cudaMemcpyAsync(dp, point, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, e->stream));
     CU(cudaMemcpyAsync(dg, goal, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, e->stream));
     CU(cudaMemcpyAsync(ds, sat.data(), sizeof(int) * n, cudaMemcpyHostToDevice, e->stream));
     SfcLaunch sl{};
     sl.n = n; sl.dm = e->dm; sl.res = e->prm.world_resolution;
     for (int k = 0; k < 3; k++) { sl.wmin[k] = e->prm.world_min[k]; sl.wmax[k] = e->prm.world_max[k]; }
-    sl.mode = 1; sl.point = dp; sl.goal = dg; sl.sat_index = ds; sl.box_out = db; sl.ok_out = dk;
+    sl.point = dp; sl.goal = dg; sl.sat_index = ds; sl.box_out = db; sl.ok_out = dk;
     launch_sfc_expand(sl, e->stream);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(box, db, sizeof(float) * 6 * n, cudaMemcpyDeviceToHost, e->stream));
@@ -924,13 +1077,24 @@ extern "C" int lscgpu_safety_audit(lscgpu_engine* e, double record_time_step, do
 
 extern "C" int lscgpu_get_step_stats(lscgpu_engine* e, lscgpu_step_stats* out) {
     if (!e || !out) return fail(LSCGPU_ERR_ARG, "null argument");
+    CU(cudaSetDevice(e->device));
+    const int rc = compute_stats(e);
+    if (rc != LSCGPU_OK) return rc;
     *out = e->stats;
     return LSCGPU_OK;
 }
 extern "C" int lscgpu_set_profiling(lscgpu_engine* e, int on) {
     if (!e) return fail(LSCGPU_ERR_ARG, "null engine");
     if (e->pending) return fail(LSCGPU_ERR_STATE, "lscgpu_synchronize first");
+    const int rc = compute_stats(e);        // close the books of the finished batch under the mode it ran in
+    if (rc != LSCGPU_OK) return rc;
     e->profiling = on != 0;
     return LSCGPU_OK;
+}
+extern "C" int lscgpu_sm_clock_khz(lscgpu_engine* e) {
+    if (!e) return -1;
+    int khz = 0;
+    if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, e->device) != cudaSuccess) return -1;
+    return khz;
 }
 extern "C" void* lscgpu_stream(lscgpu_engine* e) { return e ? (void*)e->stream : nullptr; }

@@ -41,11 +41,27 @@ struct GoalLaunch {
 };
 void launch_goal_plan(const GoalLaunch& L, cudaStream_t s);
 
-// ---- k_lsc_build ------------------------------------------------------------------------------------------
-struct LscLaunch {
-    int n_agents, n_pad, a0, n_local;
-    const int* order;              // null, or scheduling order of the local agents (see QpLaunch::order)
-    int first, count;              // this launch covers positions [first, first + count) of that order
+// ---- k_agent_plan: LSC construction + SFC window + trajectory QP of one agent per thread block ------------------
+struct DistMapDev {
+    int size[3];                   // cells per axis
+    int off[3];                    // signed key of cell 0
+    uint8_t* sqdist;               // [x][y][z] squared cell distance clamped at max_sq
+    int max_sq;
+    int* sat;                      // [n_tables][(sx+1)][(sy+1)][(sz+1)] inclusive-exclusive prefix sums of "blocked"
+    int n_tables;
+};
+
+struct PlanLaunch {
+    int n_agents, n_pad;
+    int n_blocks;                  // blocks of this launch = agents this engine plans in this step
+    // block i plans agent order[order_first + i * order_stride] (global id), or agent_base + i when order == null.
+    // The order is longest-processing-time-first over the agents of the job (k_qp_order); one GPU takes every entry, G
+    // ranks deal the entries out round-robin (rank r: order_first = r, order_stride = G) so that every rank gets the
+    // same mix of expensive and cheap agents.
+    const int* order;
+    int order_stride, order_first, agent_base, agent_stride;   // order == null: block i plans agent_base + i * agent_stride
+    int* block_of;                 // null, or [N]: block_of[agent] = i (lscgpu_get_lsc finds the agent's row-store row)
+    // predictions / culling data (k_predict)
     const float* pred;             // [N][90]
     const float* predT;            // [90][n_pad]
     const float* predZs;           // [30][n_pad]
@@ -53,18 +69,43 @@ struct LscLaunch {
     const float2* rdw;             // [N] (radius, downwash * radius) as float, for the culling pass
     const QpTablesDev* T;
     const double* state9;          // [N][9]
-    const double* goal3;
-    const int* ts;
+    const double* goal3;           // [N][3]
+    const int* ts;                 // [N]
     const float4* sphere;          // [5][n_pad]
     const float* reach;            // [N][5]
-    RowRec* rows;                  // [n_local][P_pad]   one record per kept pair, kept-list order
-    int P_pad;
-    int* kept;                     // [n_local][P_pad] pair indices that survive the exact culling test
-    int* kept_count;               // [n_local]  (zeroed by the launcher)
-    double* safe;                  // [n_local][P_pad] per kept pair: smallest whitened slack of its rows at x0
+    // row store: slots [0, row_cap) of every agent live in shared memory, the rest (everything when mirror_rows) in
+    // the global overflow arrays [n_blocks][P_pad] (row i belongs to block i)
+    int row_cap, P_pad, mirror_rows;
+    RowRec* rows; int* kept; int* kept_count; double* safe;
+    // SFC (world_use_octomap): one warp of the block grows the agent's new box while the others build the LSCs
+    int use_sfc;
+    DistMapDev dm;
+    double res;
+    // The step's new SFC box of every agent is grown by k_sfc_step, launched beside k_predict; the block reads it when
+    // the agent's flag carries this step's epoch, and grows the box itself when it is not there by the time the LSC
+    // rows are done (nobody ever waits for another kernel's progress).
+    const int* epoch;              // device step counter (k_commit increments it)
+    const int* sfc_ready;          // [N] epoch of the step sfc_box_g / sfc_ok_g belong to
+    const float* sfc_box_g;        // [N][6]
+    const int* sfc_ok_g;           // [N]
+    const lscgpu_agent_in* in;     // [N]
+    const float* boxes;            // [N][5][6] persistent windows BEFORE this step (k_commit applies the step's new box)
+    const int* init_sfc;           // [N] flag_initialize_sfc
+    const int* flags;              // [N] k_predict's flag bits; the SFC warp adds its own in the result record
+    float wmin[3], wmax[3];
+    int max_iter;
+    // outputs
+    lscgpu_agent_out* out;         // block i writes record out[out_base + i] (gather buffer: rank-major, carries agent_id)
+    int out_base;
+    const float* prev_traj;        // [N][90]  (kept when the QP fails)
+    double* last_cost;             // [N]
+    const int* goal_kind;          // [N] or null
     StepCounters* counters;
+    long long* dbg;                // null, or [n_blocks][8] section cycle counts (LSCGPU_QP_DEBUG)
 };
-void launch_lsc_build(const LscLaunch& L, cudaStream_t s);
+void launch_agent_plan(const PlanLaunch& L, cudaStream_t s);
+size_t agent_plan_smem_bytes(int row_cap);
+cudaError_t configure_agent_plan();     // once per device, before the first launch
 
 // one agent's LSCs recomputed into CollisionConstraints layout (debug / parity)
 void launch_lsc_capture(int n_agents, int agent, const float* pred, const AgentConstDev* consts, float* normals,
@@ -78,43 +119,35 @@ void launch_rows_from_lsc(int n_problems, const int* obs_offset, int total_obs, 
 void launch_terminal_segments(int n, const double* state9, const double* goal3, const int* agent_index,
                               const AgentConstDev* consts, double dt, int* ts_out, cudaStream_t s);
 
-// ---- k_qp_solve -------------------------------------------------------------------------------------------
-struct QpLaunch {
+// ---- k_qp_batch: TrajOptimizer::solve for independent problems (operator-level entry) ---------------------
+struct QpBatchLaunch {
     int n_problems;
     const QpTablesDev* T;
     const AgentConstDev* consts;
-    const int* order;              // null, or scheduling order: block i solves problem order[first + i]
-    int first;                     // ... else problem first + i; n_problems = blocks of this launch
-    const int* agent_index;        // null: agent = agent_base + b
-    int agent_base;
-    const double* state9;          // indexed by agent when agent_index == null, else by problem
-    const double* goal3;
-    const int* ts;
-    const float* boxes;            // [..][5][6] or null (no SFC rows); indexed like state9
+    const int* agent_index;        // [n_problems] which created agent's limits to use
+    const double* state9;          // [n_problems][9]
+    const double* goal3;           // [n_problems][3]
+    const int* ts;                 // [n_problems]
+    const float* boxes;            // [n_problems][5][6] or null (no SFC rows)
     float wmin[3], wmax[3];
-    const RowRec* rows;
-    const int* obs_offset;         // batch mode: obstacles of problem b = [obs_offset[b], obs_offset[b+1]); null: swarm mode
-    int n_obs;                     // swarm mode: N-1
-    int P_pad;                     // swarm mode: row pitch per agent
-    const int* kept; const int* kept_count;   // pairs to price: swarm mode [b][P_pad]; batch mode at 5*obs_offset[b]
-    double* safe;                             // per kept pair: travelled distance up to which it cannot be violated
+    RowRec* rows;                  // pairs of problem b at 5 * obs_offset[b] (k_rows_from_lsc)
+    const int* obs_offset;         // [n_problems + 1]
+    int* kept; const int* kept_count;
+    double* safe;
     int max_iter;
-    // outputs
-    double* x_out;                 // [n_problems][90] or null
-    double* cost_out; int* status_out; int* iters_out;   // batch mode
-    lscgpu_agent_out* out;         // swarm mode: indexed by agent
-    const float* prev_traj;        // [N][90]  (kept when the QP fails)
-    double* last_cost;             // [N]
-    const int* flags;              // [N]
-    const int* goal_kind;          // [N] or null
-    StepCounters* counters;
-    long long* dbg;                // null, or [n_problems][8] section cycle counts (LSCGPU_QP_DEBUG)
+    double* x_out;                 // [n_problems][90]
+    double* cost_out; int* status_out; int* iters_out;
 };
-void launch_qp_solve(const QpLaunch& L, cudaStream_t s);
-void launch_qp_order(int n_local, int a0, const lscgpu_agent_out* out, int* order, cudaStream_t s);
+void launch_qp_batch(const QpBatchLaunch& L, cudaStream_t s);
+// order[0..n) = agents a0 .. a0+n-1 (global ids), most expensive solve of the previous step first; deterministic
+// (every rank of a job computes the same permutation from its replica of the result records)
+void launch_qp_order(int n, int a0, const lscgpu_agent_out* res, int* order, cudaStream_t s);
 
-// commit: every agent's new trajectory becomes traj_curr, advanced state becomes the next resident input
-void launch_commit(int n_agents, const lscgpu_agent_out* out, float* prev_traj, lscgpu_agent_in* in, cudaStream_t s);
+// commit: for every filled slot of the gather buffer (agent_id >= 0) the record goes to res[agent_id], the new
+// trajectory becomes traj_curr, the advanced state becomes the next resident input
+// (and, with an octomap, the agent's SFC window takes the step's new box, src/traj_planner.cpp:1451-1491)
+void launch_commit(int n_slots, const lscgpu_agent_out* gather, lscgpu_agent_out* res, float* prev_traj, lscgpu_agent_in* in,
+                   double* last_cost, float* boxes /* null: no octomap */, int* init_sfc, int* planner_seq_dev, cudaStream_t s);
 
 // safety audit of the planned step (src/multi_sync_simulator.cpp:446-475)
 void launch_safety_audit(int n_agents, const float* traj, const AgentConstDev* consts, double dt, int n_samples,
@@ -122,31 +155,28 @@ void launch_safety_audit(int n_agents, const float* traj, const AgentConstDev* c
                          cudaStream_t s);
 
 // ---- distance field / SFC ---------------------------------------------------------------------------------
-struct DistMapDev {
-    int size[3];                   // cells per axis
-    int off[3];                    // signed key of cell 0
-    uint8_t* sqdist;               // [x][y][z] squared cell distance clamped at max_sq
-    int max_sq;
-    int* sat;                      // [n_tables][(sx+1)][(sy+1)][(sz+1)] inclusive-exclusive prefix sums of "blocked"
-    int n_tables;
-};
 void launch_edt_build(const int32_t* keys_dev, int n_keys, DistMapDev dm, const int* thresholds_dev, int n_tables,
                       uint8_t* scratch_a, uint8_t* scratch_b, cudaStream_t s);
+
+// k_sfc_step: the step's new SFC box (generateFeasibleSFC) of the agents this engine plans, one warp per agent, in the
+// same scheduling order as k_agent_plan's blocks
+struct SfcStepLaunch {
+    int n;                         // agents
+    const int* order; int order_stride, order_first, agent_base, agent_stride;   // as PlanLaunch
+    DistMapDev dm;
+    double res;
+    float wmin[3], wmax[3];
+    const lscgpu_agent_in* in; const float* prev_traj; const AgentConstDev* consts; const int* init_sfc;
+    const int* epoch;
+    float* sfc_box_g; int* sfc_ok_g; int* sfc_ready;
+};
+void launch_sfc_step(const SfcStepLaunch& L, cudaStream_t s);
 
 struct SfcLaunch {
     int n;                         // seeds
     DistMapDev dm;
     double res;
     float wmin[3], wmax[3];
-    // swarm mode (mode 0): seeds from agent inputs / previous trajectories, persistent windows updated in place
-    int mode, agent_base, planner_window;
-    const lscgpu_agent_in* in;
-    const float* prev_traj;
-    const AgentConstDev* consts;
-    float* boxes;                  // [N][5][6]
-    int* init_sfc;                 // [N]
-    int* flags;                    // [N]
-    // batch mode (mode 1)
     const float* point; const float* goal; const int* sat_index; float* box_out; int* ok_out;
 };
 void launch_sfc_expand(const SfcLaunch& L, cudaStream_t s);

@@ -1,9 +1,10 @@
-// k_predict, k_lsc_build and the small glue kernels around them (sm_100a).
+// k_predict, k_goal_plan, k_commit and the small glue kernels around the per-agent plan (sm_100a).
 #include <cstdlib>
 #include <string>
 
 #include "gjk.cuh"
 #include "kernels.hpp"
+#include "sfc.cuh"
 
 namespace lscgpu {
 
@@ -65,7 +66,7 @@ __global__ void __launch_bounds__(96) k_predict(PredictLaunch L) {
         const F3 dlt = f3_sub(p0, pos);
         int fl = 0;
         if (sqrt(f3_dot(dlt, dlt)) > L.reset_threshold) fl |= LSCGPU_FLAG_SLACK_NEEDED;
-        if (fl) atomicOr(&L.flags[a], fl);        // zeroed by the launcher; k_sfc_expand ORs its bit concurrently
+        L.flags[a] = fl;                          // the SFC warp of k_agent_plan adds its bit in the result record
         const F3 g{in.goal[0], in.goal[1], in.goal[2]};
         L.ts[a] = terminal_segments_of(g, pos, L.consts[a].v_nom, L.dt);
     }
@@ -207,194 +208,6 @@ __global__ void __launch_bounds__(128) k_goal_plan(GoalLaunch L) {
 void launch_goal_plan(const GoalLaunch& L, cudaStream_t s) { k_goal_plan<<<L.n_agents, 128, 0, s>>>(L); }
 
 // ------------------------------------------------------------------------------------------------------------
-// k_lsc_build — one block of 128 threads per local agent.
-//   Phase A (all threads, one neighbour each per chunk of 128): exact culling test per (neighbour, segment) from the
-//     bounding spheres — 80 B per neighbour, coalesced float4 reads. A pair is dropped only when its LSC rows cannot
-//     be violated by any trajectory that respects the velocity limits, so dropping is
-//     solution-preserving; survivors go to a shared-memory queue.
-//   Phase B (whenever the queue holds a full batch, and at the end): one queued (neighbour, segment) hull per thread —
-//     GJK in FP64 registers, LSC rows written as one 64-byte record at the pair's slot of the agent's row store,
-//     p appended to the agent's kept list together with the smallest whitened slack of its rows at the unconstrained
-//     QP minimiser x0 (the QP kernel does not look at a pair again until the iterate has travelled that far).
-// ------------------------------------------------------------------------------------------------------------
-
-template <int kLscThreads, int kMinBlocks>
-__global__ void __launch_bounds__(kLscThreads, kMinBlocks) k_lsc_build(LscLaunch L) {
-    __shared__ float own[kTrajFloats];
-    __shared__ float own_zs[30];
-    __shared__ double x0[kNv];
-    __shared__ double inv_gn[kAx];
-    __shared__ float4 own_sphere[kM];
-    __shared__ float own_reach[kM];
-    __shared__ int queue[kLscThreads * (kM + 1)];
-    __shared__ int warp_tot[2][kLscThreads / 32];      // survivors of every warp in the current chunk (double buffered)
-    const int al = L.order ? L.order[L.first + blockIdx.x] : L.first + blockIdx.x;
-    const int a = L.a0 + al;
-    const int n_obs = L.n_agents - 1;
-    const int ts = L.ts[a];
-    const int tid = threadIdx.x;
-    for (int e = tid; e < kTrajFloats; e += kLscThreads) own[e] = L.pred[(size_t)a * kTrajFloats + e];
-    if (tid < 30) own_zs[tid] = L.predZs[(size_t)tid * L.n_pad + a];
-    for (int e = tid; e < kNv; e += kLscThreads) {
-        const int k = e / kAx, i = e % kAx;
-        const double* s = L.state9 + (size_t)a * 9;
-        const double* Xs = L.T->Xs[ts - 1][i];
-        x0[e] = Xs[0] * s[k] + Xs[1] * s[3 + k] + Xs[2] * s[6 + k] + L.T->xg[ts - 1][i] * L.goal3[(size_t)a * 3 + k];
-    }
-    for (int e = tid; e < kAx; e += kLscThreads) inv_gn[e] = 1.0 / L.T->gnorm[ts - 1][e];
-    if (tid < kM) { own_sphere[tid] = L.sphere[(size_t)tid * L.n_pad + a]; own_reach[tid] = L.reach[(size_t)a * kM + tid]; }
-    const int warp = tid >> 5, lane = tid & 31;
-    constexpr int kWarps = kLscThreads / 32;
-    __syncthreads();
-
-    const AgentConstDev ca = L.consts[a];
-    const float ra_f = (float)ca.radius, rdwa_f = (float)(ca.downwash * ca.radius);
-    const double dw_self_a = (ca.downwash * ca.radius + ca.downwash * ca.radius) / (ca.radius + ca.radius);
-    RowRec* rows_out = L.rows + (size_t)al * L.P_pad;
-    int* kept_out = L.kept + (size_t)al * L.P_pad;
-    double* safe_out = L.safe + (size_t)al * L.P_pad;
-    int gjk_it = 0;
-    // queue length and kept-list length: block-uniform values every thread keeps in a register
-    int q_count = 0, kept_base = 0, chunk = 0;
-
-    for (int j0 = 0; j0 < n_obs; j0 += kLscThreads, chunk++) {
-        const int jj = j0 + tid;
-        unsigned keep_mask[kM];
-        bool keep[kM];
-#pragma unroll
-        for (int m = 0; m < kM; m++) keep[m] = false;
-        if (jj < n_obs) {
-            const int j = jj < a ? jj : jj + 1;
-            // downwash ratio of the pair in float: the test below is conservative by 1e-4 relative, float rounding is 1e-7
-            const float2 rj = L.rdw[j];
-            const float inv_dw = (ra_f + rj.x) / (rdwa_f + rj.y);
-            const float smax = fmaxf(1.0f, inv_dw);
-            const float rho = ra_f + rj.x;
-#pragma unroll
-            for (int m = 0; m < kM; m++) {
-                const float4 so = own_sphere[m];
-                const float4 sj = L.sphere[(size_t)m * L.n_pad + j];
-                const float dx = so.x - sj.x, dy = so.y - sj.y, dz = (so.z - sj.z) * inv_dw;
-                const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
-                const float d_lb = dist * 0.9999f - smax * (so.w + sj.w);        // lower bound of the hull distance
-                keep[m] = !(d_lb - rho > 2.0f * smax * own_reach[m]);
-            }
-        }
-        // order-preserving compaction (warp, then segment, then lane): the queue, and with it every list this kernel
-        // writes, has the same order in every run. One shared-memory exchange of the per-warp totals per chunk.
-        int cnt[kM], wtot = 0;
-#pragma unroll
-        for (int m = 0; m < kM; m++) {
-            keep_mask[m] = __ballot_sync(0xffffffffu, keep[m]);
-            cnt[m] = __popc(keep_mask[m]);
-            wtot += cnt[m];
-        }
-        if (lane == 0) warp_tot[chunk & 1][warp] = wtot;
-        __syncthreads();
-        {
-            int off = q_count, total = 0;
-#pragma unroll
-            for (int w = 0; w < kWarps; w++) {
-                const int c = warp_tot[chunk & 1][w];
-                if (w < warp) off += c;
-                total += c;
-            }
-#pragma unroll
-            for (int m = 0; m < kM; m++) {
-                if (keep[m]) queue[off + __popc(keep_mask[m] & ((1u << lane) - 1u))] = m * n_obs + jj;
-                off += cnt[m];
-            }
-            q_count += total;
-        }
-        __syncthreads();
-        // drain full batches (and everything after the last chunk)
-        const bool last = j0 + kLscThreads >= n_obs;
-        while (q_count >= kLscThreads || (last && q_count > 0)) {
-            const int n_items = min(q_count, kLscThreads);
-            int p = -1;
-            if (tid < n_items) p = queue[q_count - n_items + tid];    // take the batch from the END of the queue
-            q_count -= n_items;
-            double mu_min = INFINITY;
-            if (p >= 0) {
-                const int m = p / n_obs, jj2 = p % n_obs;
-                const int j = jj2 < a ? jj2 : jj2 + 1;
-                const AgentConstDev cj = L.consts[j];
-                const double downwash = (ca.downwash * ca.radius + cj.downwash * cj.radius) / (ca.radius + cj.radius);
-                // pre-scaled z is valid when the pair's ratio equals both agents' own ratio bit for bit
-                const bool pre = downwash == dw_self_a &&
-                                 downwash == (cj.downwash * cj.radius + cj.downwash * cj.radius) / (cj.radius + cj.radius);
-                F3 ow[6], ob[6];
-                float obz[6];
-#pragma unroll
-                for (int i = 0; i < 6; i++) {
-                    const int cp = m * 6 + i, e = cp * 3;
-                    obz[i] = L.predT[(size_t)(e + 2) * L.n_pad + j];
-                    ow[i] = F3{own[e], own[e + 1], pre ? own_zs[cp] : downwash_scaled_z(own[e + 2], downwash)};
-                    ob[i] = F3{L.predT[(size_t)e * L.n_pad + j], L.predT[(size_t)(e + 1) * L.n_pad + j],
-                               pre ? L.predZs[(size_t)cp * L.n_pad + j] : downwash_scaled_z(obz[i], downwash)};
-                }
-                LscSegment seg;
-                lsc_segment_scaled(ow, ob, downwash, cj.radius + ca.radius, seg);
-                gjk_it += seg.iterations;
-                const double ax = (double)seg.normal.x, ay = (double)seg.normal.y, az = (double)seg.normal.z;
-                const double an = sqrt(ax * ax + ay * ay + az * az);
-                const float inv_an = an > 0.0 ? (float)(1.0 / an) : INFINITY;
-                RowRec rec;
-                rec.ax = seg.normal.x; rec.ay = seg.normal.y; rec.az = seg.normal.z; rec.inv_an = inv_an;
-                mu_min = INFINITY;
-#pragma unroll
-                for (int i = 0; i < 6; i++) {
-                    // row  a . c_{m,i} >= d_i + a . o_{m,i}      (src/traj_optimizer.cpp:437-466)
-                    const double rhs = seg.d[i] + (__dmul_rn(ax, (double)ob[i].x) + __dmul_rn(ay, (double)ob[i].y) +
-                                                   __dmul_rn(az, (double)obz[i]));
-                    rec.rhs[i] = rhs;
-                    if (m == 0 && i < kPhi) continue;
-                    const int vi = m * 6 + i;
-                    const double slack = ax * x0[vi] + ay * x0[kAx + vi] + az * x0[2 * kAx + vi] - rhs;
-                    const double mu = an > 0.0 ? slack * (double)inv_an * inv_gn[vi] : (slack < 0.0 ? -INFINITY : INFINITY);
-                    mu_min = fmin(mu_min, mu);
-                }
-                kept_out[kept_base + tid] = p;
-                safe_out[kept_base + tid] = mu_min > 0.0 ? mu_min * 0.999999 : mu_min;
-                {   // 64-byte record, four 16-byte stores
-                    float4* dst = reinterpret_cast<float4*>(rows_out + kept_base + tid);
-                    const float4* src = reinterpret_cast<const float4*>(&rec);
-                    dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
-                }
-            }
-            kept_base += n_items;
-        }
-        // the queue tail that stays for the next chunk is only read after that chunk's barriers; nothing to wait for here
-    }
-    if (tid == 0) L.kept_count[al] = kept_base;
-    if (L.counters) {
-        const int tot = warp_sum_int(gjk_it);
-        if ((tid & 31) == 0) atomicAdd(&L.counters->gjk_iterations, (unsigned long long)tot);
-        if (tid == 0) atomicAdd(&L.counters->kept_pairs, (unsigned long long)kept_base);
-    }
-}
-
-void launch_lsc_build(const LscLaunch& L, cudaStream_t s) {
-    const int n_obs = L.n_agents - 1;
-    if (n_obs <= 0 || L.count <= 0) return;
-    // block size x blocks per SM (register cap): 128x4 and 256x2 run at 128 registers (16 warps per SM), 128x3 at 168,
-    // 256x1 / 128x2 at the unconstrained 180. Larger blocks shorten one agent's latency (what matters when the launch
-    // is a single wave), more resident warps hide the FP64 dependency chains of the GJK (what matters otherwise).
-    static const int cfg = [] {             // parsed once: 0 = 256x2 (default), 1 = 256x1, 2 = 128x2, 3 = 128x3, 4 = 128x4
-        const char* v = getenv("LSCGPU_LSC_CFG");
-        const std::string c(v ? v : "256x2");
-        return c == "256x1" ? 1 : c == "128x2" ? 2 : c == "128x3" ? 3 : c == "128x4" ? 4 : 0;
-    }();
-    switch (cfg) {
-        case 1: k_lsc_build<256, 1><<<L.count, 256, 0, s>>>(L); break;
-        case 2: k_lsc_build<128, 2><<<L.count, 128, 0, s>>>(L); break;
-        case 3: k_lsc_build<128, 3><<<L.count, 128, 0, s>>>(L); break;
-        case 4: k_lsc_build<128, 4><<<L.count, 128, 0, s>>>(L); break;
-        default: k_lsc_build<256, 2><<<L.count, 256, 0, s>>>(L); break;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------------
 // Debug / parity: CollisionConstraints::getLSC layout for one agent.
 // ------------------------------------------------------------------------------------------------------------
 __global__ void k_lsc_capture(int n_agents, int a, const float* pred, const AgentConstDev* consts, float* normals,
@@ -479,22 +292,46 @@ void launch_rows_from_lsc(int n_problems, const int* obs_offset, int total_obs, 
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// k_commit — after the (all-gathered) results are complete: traj_curr <- new trajectory, and the advanced state
-// becomes the input of a device-resident next step (MultiSyncSimulator::update(), src/multi_sync_simulator.cpp:203).
+// k_commit — after the (all-gathered) records are complete: one block per slot of the gather buffer. The record of
+// agent `agent_id` goes to res[agent_id] (agent order: what the host reads and what the next step's LPT order and
+// failure path look at), traj_curr <- new trajectory, the advanced state becomes the input of a device-resident next
+// step (MultiSyncSimulator::update(), src/multi_sync_simulator.cpp:203), and the agent's SFC window takes the step's new
+// box (generateFeasibleSFC, src/traj_planner.cpp:1451-1491) — on every replica, so any rank can plan the agent next.
+// Slots with agent_id < 0 are empty (ranks that own fewer agents).
 // ------------------------------------------------------------------------------------------------------------
-__global__ void k_commit(int n_agents, const lscgpu_agent_out* out, float* prev_traj, lscgpu_agent_in* in) {
-    const int a = blockIdx.x;
+__global__ void __launch_bounds__(128) k_commit(int n_slots, const lscgpu_agent_out* gather, lscgpu_agent_out* res,
+                                                float* prev_traj, lscgpu_agent_in* in, double* last_cost, float* boxes,
+                                                int* init_sfc, int* planner_seq_dev) {
+    const int slot = blockIdx.x;
     const int e = threadIdx.x;
-    const lscgpu_agent_out& o = out[a];
+    if (slot == 0 && e == 0 && planner_seq_dev) *planner_seq_dev += 1;
+    const lscgpu_agent_out& o = gather[slot];
+    const int a = o.agent_id;
+    if (a < 0) return;
+    // the record, 16 bytes per thread
+    constexpr int kVec = sizeof(lscgpu_agent_out) / 16;
+    static_assert(sizeof(lscgpu_agent_out) % 16 == 0, "record must be a multiple of 16 bytes");
+    if (e < kVec) reinterpret_cast<uint4*>(res + a)[e] = reinterpret_cast<const uint4*>(&o)[e];
     if (e < kTrajFloats) prev_traj[(size_t)a * kTrajFloats + e] = (&o.traj[0][0][0])[e];
     if (e < 3) {
         in[a].position[e] = o.next_position[e];
         in[a].velocity[e] = o.next_velocity[e];
         in[a].acceleration[e] = o.next_acceleration[e];
     }
+    if (e == 0) last_cost[a] = o.qp_cost;
+    if (boxes) {
+        float* bx = boxes + (size_t)a * 30;
+        const bool first = init_sfc[a] != 0, ok = !(o.flags & LSCGPU_FLAG_SFC_SEED_BLOCKED);
+        float v = 0.f;
+        if (e >= 96 && e < 126) v = sfc_window_elem(bx, first, ok, o.sfc_box, e - 96);
+        __syncthreads();
+        if (e >= 96 && e < 126) bx[e - 96] = v;
+        if (e == 127) init_sfc[a] = 0;
+    }
 }
-void launch_commit(int n_agents, const lscgpu_agent_out* out, float* prev_traj, lscgpu_agent_in* in, cudaStream_t s) {
-    k_commit<<<n_agents, 96, 0, s>>>(n_agents, out, prev_traj, in);
+void launch_commit(int n_slots, const lscgpu_agent_out* gather, lscgpu_agent_out* res, float* prev_traj, lscgpu_agent_in* in,
+                   double* last_cost, float* boxes, int* init_sfc, int* planner_seq_dev, cudaStream_t s) {
+    if (n_slots > 0) k_commit<<<n_slots, 128, 0, s>>>(n_slots, gather, res, prev_traj, in, last_cost, boxes, init_sfc, planner_seq_dev);
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -1,0 +1,449 @@
+// k_agent_plan — the whole per-agent replan of one synchronous step in ONE thread block (sm_100a):
+//   phase 1  LSC construction against every neighbour (exact culling, GJK) — the rows stay in shared memory —
+//            while one warp grows the agent's new SFC box against the distance-field tables;
+//   phase 2  the Bernstein trajectory QP (qp_core.cuh) priced straight from those shared-memory rows;
+//   epilogue result record (trajectory, advanced state, cost, counters) into the step's gather buffer.
+// Also k_qp_batch (TrajOptimizer::solve for independent problems, rows from global memory) and k_qp_order (LPT order).
+//
+// Replaces, per agent (TrajPlanner::planLSC, src/traj_planner.cpp:389-425):
+//   generateLSC + normalVectorBetweenPolys        src/traj_planner.cpp:1310-1407,2030-2043
+//   closestPointsBetweenPointAndConvexHull / gjk  include/geometry.hpp:364-394, src/openGJK/openGJK.cpp:674-780
+//   generateFeasibleSFC                           src/traj_planner.cpp:1442-1491 (sfc.cuh)
+//   TrajOptimizer::solve                          src/traj_optimizer.cpp:31-154,239-539 (qp_core.cuh)
+//   getStateFromControlPoints at t = dt           include/polynomial.hpp:63-121
+//
+// Why one kernel: the rows one agent's LSC phase produces (64 B per kept (neighbour, segment) pair, 250-2000 pairs) are
+// consumed only by that agent's QP. Kept in shared memory they cost one 29-cycle LDS per pricing pass instead of an L2
+// round trip, never touch HBM, and the QP of an agent starts the moment ITS corridors are done instead of after the
+// slowest block of a separate corridor kernel. Blocks are issued longest-processing-time first (k_qp_order).
+#include <climits>
+#include <cstdlib>
+#include <string>
+
+#include "gjk.cuh"
+#include "kernels.hpp"
+#include "qp_core.cuh"
+#include "sfc.cuh"
+
+namespace lscgpu {
+
+constexpr int kPlanThreads = 256;
+constexpr int kPlanWarps = kPlanThreads / 32;
+
+// LSC-phase scratch (beside QpShared; the survivor queue aliases QpShared::Q, which the QP only touches afterwards)
+struct LscShared {
+    float own[kTrajFloats];
+    float own_zs[30];
+    float4 own_sphere[kM];
+    float own_reach[kM];
+    int warp_tot[2][kPlanWarps];
+    int sfc_ok;
+    float sfc_box[6];           // the box the SFC warp grew in this step
+    long long t_sfc, t_lsc;     // cycles the SFC warp / the LSC warps needed (diagnostics)
+    int lsc_done;               // set when the LSC warps are through (the SFC warp stops waiting for k_sfc_step)
+    int sfc_self;               // 1: the block grew the box itself
+};
+
+__host__ __device__ constexpr size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
+struct PlanSmemLayout {
+    size_t qp, lists, lsc, nr, rhs, gate, seg, total;
+    __host__ __device__ explicit PlanSmemLayout(int cap) {
+        qp = 0;
+        lists = align16(qp + sizeof(QpShared));
+        lsc = align16(lists + sizeof(int) * kPlanWarps * kWarpList);
+        nr = align16(lsc + sizeof(LscShared));
+        rhs = nr + sizeof(float4) * (size_t)cap;
+        gate = rhs + sizeof(double2) * 3 * (size_t)cap;
+        seg = gate + sizeof(double) * (size_t)cap;
+        total = align16(seg + (size_t)cap);
+    }
+};
+size_t agent_plan_smem_bytes(int row_cap) { return PlanSmemLayout(row_cap).total; }
+
+// barrier over the first n_threads threads of the block (whole warps); id 1 is the LSC phase's
+__device__ __forceinline__ void lsc_barrier(int n_threads) {
+    asm volatile("bar.sync 1, %0;" ::"r"(n_threads) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// LSC phase of agent a by threads [0, kT) of the block.
+//   Phase A (one neighbour per thread per chunk of kT): exact culling test per (neighbour, segment) from the bounding
+//     spheres — 80 B per neighbour, coalesced float4 reads. A pair is dropped only when its LSC rows cannot be violated
+//     by any trajectory that respects the velocity / acceleration limits, so dropping is
+//     solution-preserving; survivors go to a shared-memory queue.
+//   Phase B (whenever the queue holds a full batch, and at the end): one queued (neighbour, segment) hull per thread —
+//     GJK in FP64 registers, the LSC rows as one record at the pair's slot of the row source, together with the
+//     smallest whitened slack of its rows at the unconstrained QP minimiser x0 (the QP does not look at a pair again
+//     until the iterate has travelled that far).
+// Returns the number of kept pairs (same value in all participating threads).
+// ------------------------------------------------------------------------------------------------------------
+template <int kT>
+__device__ __forceinline__ int lsc_phase(const PlanLaunch& L, int a, const RowSrc& rows, LscShared& X, const QpShared& S,
+                                         int* queue, int& gjk_it) {
+    constexpr int kW = kT / 32;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_obs = L.n_agents - 1;
+    const AgentConstDev ca = L.consts[a];
+    const float ra_f = (float)ca.radius, rdwa_f = (float)(ca.downwash * ca.radius);
+    const double dw_self_a = (ca.downwash * ca.radius + ca.downwash * ca.radius) / (ca.radius + ca.radius);
+    // queue length and kept-list length: uniform values every participating thread keeps in a register
+    int q_count = 0, kept_base = 0, chunk = 0;
+
+    for (int j0 = 0; j0 < n_obs; j0 += kT, chunk++) {
+        const int jj = j0 + tid;
+        unsigned keep_mask[kM];
+        bool keep[kM];
+#pragma unroll
+        for (int m = 0; m < kM; m++) keep[m] = false;
+        if (jj < n_obs) {
+            const int j = jj < a ? jj : jj + 1;
+            // downwash ratio of the pair in float: the test below is conservative by 1e-4 relative, float rounding is 1e-7
+            const float2 rj = L.rdw[j];
+            const float inv_dw = (ra_f + rj.x) / (rdwa_f + rj.y);
+            const float smax = fmaxf(1.0f, inv_dw);
+            const float rho = ra_f + rj.x;
+#pragma unroll
+            for (int m = 0; m < kM; m++) {
+                const float4 so = X.own_sphere[m];
+                const float4 sj = L.sphere[(size_t)m * L.n_pad + j];
+                const float dx = so.x - sj.x, dy = so.y - sj.y, dz = (so.z - sj.z) * inv_dw;
+                const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
+                const float d_lb = dist * 0.9999f - smax * (so.w + sj.w);        // lower bound of the hull distance
+                keep[m] = !(d_lb - rho > 2.0f * smax * X.own_reach[m]);
+            }
+        }
+        // order-preserving compaction (warp, then segment, then lane): the queue, and with it the slot order of the row
+        // store, is the same in every run. One shared-memory exchange of the per-warp totals per chunk.
+        int cnt[kM], wtot = 0;
+#pragma unroll
+        for (int m = 0; m < kM; m++) {
+            keep_mask[m] = __ballot_sync(0xffffffffu, keep[m]);
+            cnt[m] = __popc(keep_mask[m]);
+            wtot += cnt[m];
+        }
+        if (lane == 0) X.warp_tot[chunk & 1][warp] = wtot;
+        lsc_barrier(kT);
+        {
+            int off = q_count, total = 0;
+#pragma unroll
+            for (int w = 0; w < kW; w++) {
+                const int c = X.warp_tot[chunk & 1][w];
+                if (w < warp) off += c;
+                total += c;
+            }
+#pragma unroll
+            for (int m = 0; m < kM; m++) {
+                if (keep[m]) queue[off + __popc(keep_mask[m] & ((1u << lane) - 1u))] = m * n_obs + jj;
+                off += cnt[m];
+            }
+            q_count += total;
+        }
+        lsc_barrier(kT);
+        // drain full batches (and everything after the last chunk)
+        const bool last = j0 + kT >= n_obs;
+        while (q_count >= kT || (last && q_count > 0)) {
+            const int n_items = min(q_count, kT);
+            int p = -1;
+            if (tid < n_items) p = queue[q_count - n_items + tid];    // take the batch from the END of the queue
+            q_count -= n_items;
+            if (p >= 0) {
+                const int m = p / n_obs, jj2 = p - m * n_obs;
+                const int j = jj2 < a ? jj2 : jj2 + 1;
+                const AgentConstDev cj = L.consts[j];
+                const double downwash = (ca.downwash * ca.radius + cj.downwash * cj.radius) / (ca.radius + cj.radius);
+                // pre-scaled z is valid when the pair's ratio equals both agents' own ratio bit for bit
+                const bool pre = downwash == dw_self_a &&
+                                 downwash == (cj.downwash * cj.radius + cj.downwash * cj.radius) / (cj.radius + cj.radius);
+                F3 ow[6], ob[6];
+                float obz[6];
+#pragma unroll
+                for (int i = 0; i < 6; i++) {
+                    const int cp = m * 6 + i, e = cp * 3;
+                    obz[i] = L.predT[(size_t)(e + 2) * L.n_pad + j];
+                    ow[i] = F3{X.own[e], X.own[e + 1], pre ? X.own_zs[cp] : downwash_scaled_z(X.own[e + 2], downwash)};
+                    ob[i] = F3{L.predT[(size_t)e * L.n_pad + j], L.predT[(size_t)(e + 1) * L.n_pad + j],
+                               pre ? L.predZs[(size_t)cp * L.n_pad + j] : downwash_scaled_z(obz[i], downwash)};
+                }
+                LscSegment seg;
+                lsc_segment_scaled(ow, ob, downwash, cj.radius + ca.radius, seg);
+                gjk_it += seg.iterations;
+                const double ax = (double)seg.normal.x, ay = (double)seg.normal.y, az = (double)seg.normal.z;
+                const double an = sqrt(ax * ax + ay * ay + az * az);
+                const float inv_an = an > 0.0 ? (float)(1.0 / an) : INFINITY;
+                RowRec rec;
+                rec.ax = seg.normal.x; rec.ay = seg.normal.y; rec.az = seg.normal.z; rec.inv_an = inv_an;
+                double mu_min = INFINITY;
+#pragma unroll
+                for (int i = 0; i < 6; i++) {
+                    // row  a . c_{m,i} >= d_i + a . o_{m,i}      (src/traj_optimizer.cpp:437-466)
+                    const double rhs = seg.d[i] + (__dmul_rn(ax, (double)ob[i].x) + __dmul_rn(ay, (double)ob[i].y) +
+                                                   __dmul_rn(az, (double)obz[i]));
+                    rec.rhs[i] = rhs;
+                    if (m == 0 && i < kPhi) continue;
+                    const int vi = m * 6 + i;
+                    const double slack = ax * S.x[vi] + ay * S.x[kAx + vi] + az * S.x[2 * kAx + vi] - rhs;
+                    const double mu = an > 0.0 ? slack * (double)inv_an * S.inv_gn[vi] : (slack < 0.0 ? -INFINITY : INFINITY);
+                    mu_min = fmin(mu_min, mu);
+                }
+                rows.store(kept_base + tid, rec, m, p, mu_min > 0.0 ? mu_min * 0.999999 : mu_min, L.mirror_rows != 0);
+            }
+            kept_base += n_items;
+        }
+        // the queue tail that stays for the next chunk is only read after that chunk's barriers; nothing to wait for here
+    }
+    return kept_base;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+template <bool kSfc>
+__global__ void __launch_bounds__(kPlanThreads, 2) k_agent_plan(PlanLaunch L) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const PlanSmemLayout lay(L.row_cap);
+    QpShared& S = *reinterpret_cast<QpShared*>(smem + lay.qp);
+    int* open_lists = reinterpret_cast<int*>(smem + lay.lists);
+    LscShared& X = *reinterpret_cast<LscShared*>(smem + lay.lsc);
+    const long long t_start = clock64();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int bi = blockIdx.x;
+    // scheduling order != data order: blocks are dispatched in blockIdx order, so the agents with the most expensive
+    // plan of the previous step go first (longest-processing-time-first)
+    const int a = L.order ? L.order[L.order_first + bi * L.order_stride] : L.agent_base + bi * L.agent_stride;
+    const QpTablesDev& T = *L.T;
+    const int ts = L.ts[a];
+    const int n_obs = L.n_agents - 1;
+
+    RowSrc rows;
+    rows.s_nr = reinterpret_cast<float4*>(smem + lay.nr);
+    rows.s_rhs = reinterpret_cast<double2*>(smem + lay.rhs);
+    rows.s_gate = reinterpret_cast<double*>(smem + lay.gate);
+    rows.s_seg = smem + lay.seg;
+    rows.cap = L.row_cap;
+    rows.g_rows = L.rows + (size_t)bi * L.P_pad;
+    rows.g_gate = L.safe + (size_t)bi * L.P_pad;
+    rows.g_kept = L.kept + (size_t)bi * L.P_pad;
+    rows.n_obs = n_obs;
+
+    // ---- stage: QP tables + x0 (bounds come later, from the SFC warp), own prediction ---------------------------
+    const double* st = L.state9 + (size_t)a * 9;
+    const double* gl = L.goal3 + (size_t)a * 3;
+    for (int e = tid; e < kTrajFloats; e += kPlanThreads) X.own[e] = L.pred[(size_t)a * kTrajFloats + e];
+    if (tid < 30) X.own_zs[tid] = L.predZs[(size_t)tid * L.n_pad + a];
+    if (tid < kM) { X.own_sphere[tid] = L.sphere[(size_t)tid * L.n_pad + a]; X.own_reach[tid] = L.reach[(size_t)a * kM + tid]; }
+    if (tid == 0) { X.sfc_ok = 1; X.lsc_done = 0; X.sfc_self = 0; }
+    qp_stage<kPlanThreads>(S, T, ts, st, gl, nullptr, L.wmin, L.wmax, L.consts[a]);     // ends with a block barrier
+
+    // ---- phase 1: corridors -------------------------------------------------------------------------------------
+    int n_kept = 0, gjk_it = 0;
+    int* queue = reinterpret_cast<int*>(S.Q);          // kPlanThreads * (kM + 1) ints = 6 KB of Q's 12 KB
+    if (kSfc) {
+        constexpr int kT = kPlanThreads - 32;
+        if (warp < kPlanWarps - 1) {
+            if (n_obs > 0) n_kept = lsc_phase<kT>(L, a, rows, X, S, queue, gjk_it);
+            if (tid == 0) { X.t_lsc = clock64() - t_start; *(volatile int*)&X.lsc_done = 1; }
+        } else {
+            // the box normally comes from k_sfc_step (launched beside k_predict): wait for it only as long as the LSC
+            // warps are busy anyway, then grow it here
+            const int epoch = *L.epoch;
+            bool have = false;
+            while (true) {
+                int ready = 0;
+                if (lane == 0) ready = *(volatile const int*)(L.sfc_ready + a) == epoch ? 1 : (*(volatile int*)&X.lsc_done ? 2 : 0);
+                ready = __shfl_sync(0xffffffffu, ready, 0);
+                if (ready == 1) { have = true; break; }
+                if (ready == 2) break;
+                __nanosleep(256);
+            }
+            if (have) {
+                __threadfence();
+                if (lane < 6) X.sfc_box[lane] = __ldcg(L.sfc_box_g + (size_t)a * 6 + lane);
+                if (lane == 0) { X.sfc_ok = __ldcg(L.sfc_ok_g + a); X.t_sfc = clock64() - t_start; }
+            } else {
+                SfcCtx c;
+                sfc_ctx_init(c, L.dm, L.wmin, L.wmax, L.res, lane);
+                double face;
+                const bool ok = sfc_agent_box(c, L.dm, L.consts[a].sat_index, L.res, L.in[a], L.prev_traj + (size_t)a * kTrajFloats,
+                                              L.init_sfc[a] != 0, face);
+                if (lane < 6) X.sfc_box[lane] = ok ? (float)face : 0.0f;
+                if (lane == 0) { X.sfc_ok = ok ? 1 : 0; X.sfc_self = 1; X.t_sfc = clock64() - t_start; }
+            }
+        }
+    } else {
+        if (n_obs > 0) n_kept = lsc_phase<kPlanThreads>(L, a, rows, X, S, queue, gjk_it);
+        if (tid == 0) { X.t_lsc = clock64() - t_start; X.t_sfc = 0; }
+    }
+    if (tid == 0) X.warp_tot[0][0] = n_kept;
+    __syncthreads();
+    n_kept = X.warp_tot[0][0];
+    if (L.counters) {
+        const int tot = warp_sum_int(gjk_it);
+        if (lane == 0 && tot) atomicAdd(&L.counters->gjk_iterations, (unsigned long long)tot);
+        if (tid == 0) atomicAdd(&L.counters->kept_pairs, (unsigned long long)n_kept);
+    }
+    if (tid == 0) { L.kept_count[bi] = n_kept; if (L.block_of) L.block_of[a] = bi; }
+    // bounds: world box, intersected with the agent's SFC window as it stands after this step's new box
+    if (tid < 15) {
+        const int m = tid / 3, k = tid % 3;
+        double lo = (double)L.wmin[k], hi = (double)L.wmax[k];
+        if (kSfc) {         // SFC rows == per-variable bounds (src/traj_optimizer.cpp:409-434)
+            const float* old_win = L.boxes + (size_t)a * 30;
+            const bool first = L.init_sfc[a] != 0, ok = X.sfc_ok != 0;
+            lo = fmax(lo, (double)sfc_window_elem(old_win, first, ok, X.sfc_box, m * 6 + k));
+            hi = fmin(hi, (double)sfc_window_elem(old_win, first, ok, X.sfc_box, m * 6 + 3 + k));
+        }
+        S.lb[tid] = lo; S.ub[tid] = hi;
+    }
+    // Q / W start empty (the queue lived in Q)
+    __syncthreads();
+    const long long t_lsc = clock64();
+
+    // ---- phase 2: the QP ----------------------------------------------------------------------------------------
+#ifdef LSCGPU_QP_SECTION_TIMERS
+    long long sec[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long* secp = sec;
+#else
+    long long* secp = nullptr;
+#endif
+    const QpResultRegs R = qp_solve_core<kPlanThreads>(S, open_lists, rows, n_kept, T.vel_coef, T.acc_coef, L.max_iter, secp);
+
+    // ---- epilogue -----------------------------------------------------------------------------------------------
+    if (L.counters) {
+        const unsigned long long ev = (unsigned long long)(warp_sum((double)R.pairs_evaluated) + 0.5);
+        if (lane == 0) atomicAdd(&L.counters->rows_priced, 6ull * ev + (warp == 0 ? 414ull * R.passes : 0ull));
+    }
+    if (warp != 0) return;
+    const double cost = qp_objective(S, T, ts, gl, lane);
+    if (L.counters && lane == 0) {
+        atomicAdd(&L.counters->qp_iterations, (unsigned long long)R.iters);
+        atomicAdd(&L.counters->full_passes, R.passes);
+    }
+    lscgpu_agent_out& o = L.out[L.out_base + bi];
+    float* tr = &o.traj[0][0][0];
+    const bool ok = R.status == LSCGPU_QP_OK;
+    // failure: the optimizer keeps its last successful trajectory and cost (src/traj_planner.cpp:1553-1584)
+    for (int e = lane; e < kTrajFloats; e += 32) {
+        const int axis = e % 3, cp = e / 3;
+        tr[e] = ok ? (float)S.x[axis * kAx + cp] : L.prev_traj[(size_t)a * kTrajFloats + e];
+    }
+    __syncwarp();
+    __threadfence_block();
+    if (lane < 3) {
+        // getStateFromControlPoints at t = dt: segment 1, local time 0 (include/polynomial.hpp:63-121)
+        const float inv_dt = (float)(1.0 / T.dt);
+        const float c0 = tr[(6 + 0) * 3 + lane], c1 = tr[(6 + 1) * 3 + lane], c2 = tr[(6 + 2) * 3 + lane];
+        const float v0 = __fmul_rn(__fmul_rn(__fsub_rn(c1, c0), (float)kN), inv_dt);
+        const float v1 = __fmul_rn(__fmul_rn(__fsub_rn(c2, c1), (float)kN), inv_dt);
+        o.next_position[lane] = c0;
+        o.next_velocity[lane] = v0;
+        o.next_acceleration[lane] = __fmul_rn(__fmul_rn(__fsub_rn(v1, v0), (float)(kN - 1)), inv_dt);
+    }
+    if (lane == 0) {
+        const double c_rep = ok ? cost : L.last_cost[a];
+        o.agent_id = a;
+        o.qp_cost = c_rep;
+        L.last_cost[a] = c_rep;
+        o.report = LSCGPU_REPORT_SUCCESS;
+        o.qp_status = R.status;
+        o.qp_iterations = R.iters;
+        o.qp_active = R.q;
+        int fl = L.flags ? L.flags[a] : 0;
+        if (kSfc && !X.sfc_ok) fl |= LSCGPU_FLAG_SFC_SEED_BLOCKED;
+        o.flags = fl;
+        o.terminal_segments = ts;
+        for (int k = 0; k < 3; k++) o.current_goal[k] = (float)gl[k];
+        o.goal_kind = L.goal_kind ? L.goal_kind[a] : 0;
+        for (int f = 0; f < 6; f++) o.sfc_box[f] = kSfc ? X.sfc_box[f] : 0.0f;
+        o.sfc_in_block = kSfc ? X.sfc_self : 0;
+        o.qp_sweeps = (int)R.passes;
+        const long long t_end = clock64();
+        o.qp_kcycles = (int)((t_end - t_start) >> 10);
+        o.qp_price_kcycles = (int)(R.price_cycles >> 10);
+        o.lsc_kcycles = (int)((t_lsc - t_start) >> 10);
+        o.lsc_pairs_kept = n_kept;
+#ifdef LSCGPU_QP_SECTION_TIMERS
+        if (L.dbg) {
+            for (int i = 1; i < 7; i++) L.dbg[(size_t)bi * 10 + i] = sec[i];
+            L.dbg[(size_t)bi * 10] = R.price_cycles;
+            L.dbg[(size_t)bi * 10 + 7] = t_lsc - t_start;
+            L.dbg[(size_t)bi * 10 + 8] = X.t_sfc;
+            L.dbg[(size_t)bi * 10 + 9] = X.t_lsc;
+        }
+#endif
+    }
+}
+
+// opt in to > 48 KB of dynamic shared memory and the largest shared-memory carve-out (two blocks per SM); per device
+cudaError_t configure_agent_plan() {
+    cudaError_t rc = cudaFuncSetAttribute(k_agent_plan<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (rc == cudaSuccess) rc = cudaFuncSetAttribute(k_agent_plan<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (rc == cudaSuccess) rc = cudaFuncSetAttribute(k_agent_plan<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (rc == cudaSuccess) rc = cudaFuncSetAttribute(k_agent_plan<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    return rc;
+}
+
+void launch_agent_plan(const PlanLaunch& L, cudaStream_t s) {
+    if (L.n_blocks <= 0) return;
+    const size_t smem = agent_plan_smem_bytes(L.row_cap);
+    if (L.use_sfc) k_agent_plan<true><<<L.n_blocks, kPlanThreads, smem, s>>>(L);
+    else k_agent_plan<false><<<L.n_blocks, kPlanThreads, smem, s>>>(L);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// k_qp_batch — TrajOptimizer::solve (src/traj_optimizer.cpp:31-154) for independent problems whose LSC rows arrive
+// from the host in the reference's container layout (k_rows_from_lsc); rows are priced from global memory.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPlanThreads, 2) k_qp_batch(QpBatchLaunch L) {
+    __shared__ __align__(16) QpShared S;
+    __shared__ int open_lists[kPlanWarps * kWarpList];
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int agent = L.agent_index[b];
+    const QpTablesDev& T = *L.T;
+    const int ts = L.ts[b];
+    const size_t pair0 = (size_t)kPairsPerObs * L.obs_offset[b];
+    RowSrc rows;
+    rows.s_nr = nullptr; rows.s_rhs = nullptr; rows.s_gate = nullptr; rows.s_seg = nullptr; rows.cap = 0;
+    rows.g_rows = L.rows + pair0; rows.g_gate = L.safe + pair0; rows.g_kept = L.kept + pair0;
+    rows.n_obs = L.obs_offset[b + 1] - L.obs_offset[b];
+    const double* gl = L.goal3 + (size_t)b * 3;
+    qp_stage<kPlanThreads>(S, T, ts, L.state9 + (size_t)b * 9, gl, L.boxes ? L.boxes + (size_t)b * 30 : nullptr, L.wmin, L.wmax,
+                           L.consts[agent]);
+    const QpResultRegs R = qp_solve_core<kPlanThreads>(S, open_lists, rows, L.kept_count[b], T.vel_coef, T.acc_coef, L.max_iter, nullptr);
+    if (warp != 0) return;
+    const double cost = qp_objective(S, T, ts, gl, lane);
+    for (int e = lane; e < kNv; e += 32) L.x_out[(size_t)b * kNv + e] = S.x[e];
+    if (lane == 0) { L.cost_out[b] = cost; L.status_out[b] = R.status; L.iters_out[b] = R.iters; }
+}
+
+void launch_qp_batch(const QpBatchLaunch& L, cudaStream_t s) {
+    if (L.n_problems <= 0) return;
+    k_qp_batch<<<L.n_problems, kPlanThreads, 0, s>>>(L);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// k_qp_order — longest-processing-time-first order of agents a0 .. a0+n-1 from the cycle count each plan recorded in
+// its result record at the previous step. Rank sort (position = number of agents with a larger key, ties by id), so
+// the permutation is a pure function of the records: every rank of a multi-GPU job derives the same one from its
+// replica and takes every G-th entry. It only affects scheduling, never results.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_qp_order(int n, int a0, const lscgpu_agent_out* res, int* order) {
+    __shared__ int tile[256];
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const int mine = i < n ? res[a0 + i].qp_kcycles : 0;
+    int pos = 0;
+    for (int j0 = 0; j0 < n; j0 += 256) {
+        const int j = j0 + threadIdx.x;
+        tile[threadIdx.x] = j < n ? res[a0 + j].qp_kcycles : INT_MIN;
+        __syncthreads();
+        const int cnt = min(256, n - j0);
+        for (int t = 0; t < cnt; t++) {
+            const int other = tile[t];
+            pos += (other > mine) || (other == mine && j0 + t < i);
+        }
+        __syncthreads();
+    }
+    if (i < n) order[pos] = a0 + i;
+}
+void launch_qp_order(int n, int a0, const lscgpu_agent_out* res, int* order, cudaStream_t s) {
+    if (n > 0) k_qp_order<<<(n + 255) / 256, 256, 0, s>>>(n, a0, res, order);
+}
+
+}  // namespace lscgpu

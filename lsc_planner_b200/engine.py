@@ -57,6 +57,20 @@ class AgentType:
     max_acc: Sequence[float] = (2.0, 2.0, 2.0)
 
 
+def measure_fma_peaks(device: int = 0) -> dict:
+    """FP32 / FP64 FMA peaks of the device in TFLOP/s (lscgpu_measure_fma_peaks)."""
+    a, b = C.c_double(0), C.c_double(0)
+    A.check(A.lib().lscgpu_measure_fma_peaks(device, C.byref(a), C.byref(b)))
+    return {"fp32_tflops": a.value, "fp64_tflops": b.value}
+
+
+def measure_latencies(device: int = 0) -> dict:
+    """Dependent-issue latencies in cycles (lscgpu_measure_latencies)."""
+    v = (C.c_double * 7)()
+    A.check(A.lib().lscgpu_measure_latencies(device, v))
+    return dict(zip(["dfma", "ffma", "lds", "shfl_dadd", "rsqrt_f64", "div_f64", "redux"], [float(x) for x in v]))
+
+
 class ReplanEngine:
     """One GPU's replanning engine for a swarm of `n_agents` (include/lscgpu.h)."""
 
@@ -121,8 +135,16 @@ class ReplanEngine:
     def nccl_init(self, unique_id: bytes, rank: int, n_ranks: int):
         buf = np.frombuffer(unique_id, np.uint8).copy()
         A.check(self.lib.lscgpu_nccl_init(self.h, A.p(buf), rank, n_ranks))
-        block = (self.n + n_ranks - 1) // n_ranks
-        self.a0 = min(self.n, rank * block); self.a1 = min(self.n, self.a0 + block)
+        # the job's LPT order is dealt out round-robin: this rank plans every n_ranks-th entry, starting at `rank`
+        self.a0, self.a1 = 0, self.n
+        self.rank, self.n_ranks = rank, n_ranks
+
+    @property
+    def n_planned(self) -> int:
+        """Agents this engine plans per step."""
+        if getattr(self, "n_ranks", 1) > 1:
+            return max(0, (self.n - self.rank + self.n_ranks - 1) // self.n_ranks)
+        return self.a1 - self.a0
 
     # ---- stepping ------------------------------------------------------------------------------------------
     def replan(self, pos, vel, acc, goal, out: Optional[np.ndarray] = None, inp: Optional[np.ndarray] = None):
@@ -198,6 +220,18 @@ class ReplanEngine:
         nr = np.zeros((max(self.n - 1, 0), 5, 3), np.float32); d = np.zeros((max(self.n - 1, 0), 5, 6), np.float64)
         A.check(self.lib.lscgpu_get_lsc(self.h, agent, A.p(nr), A.p(d)))
         return nr, d
+
+    def set_capture_rows(self, on: bool = True):
+        """Mirror the rows k_agent_plan builds into global memory, so that get_lsc_rows returns the production rows."""
+        A.check(self.lib.lscgpu_set_capture_rows(self.h, int(on)))
+
+    def get_lsc_rows(self, agent: int):
+        """(normals, d, kept [N-1][5] bool): like get_lsc, with the kept (neighbour, segment) pairs decoded from the row
+        store the planning kernel wrote in the last step; the culled pairs are recomputed."""
+        nr = np.zeros((max(self.n - 1, 0), 5, 3), np.float32); d = np.zeros((max(self.n - 1, 0), 5, 6), np.float64)
+        kept = np.zeros((max(self.n - 1, 0), 5), np.uint8)
+        A.check(self.lib.lscgpu_get_lsc_ex(self.h, agent, A.p(nr), A.p(d), A.p(kept)))
+        return nr, d, kept.astype(bool)
 
     def initial_traj(self):
         out = np.zeros((self.n, 5, 6, 3), np.float32)

@@ -12,6 +12,7 @@
 #include <memory>
 #include <vector>
 
+#include <exception>
 #include <thread>
 
 #include "grid_based_planner.hpp"
@@ -58,8 +59,12 @@ public:
     ReplanBatch(const Param& _param, const Mission& _mission, int device = 0)
         : param(_param), mission(_mission), engine(createEngine(_param, _mission, device)), in(_mission.qn), out(_mission.qn),
           fresh(_mission.qn, false) {
-        lscgpu_set_profiling(engine.get(), 1);
+        // per-phase times come from the cycle counters of the result records (lsc_kcycles / qp_kcycles): the engine
+        // keeps its normal scheduling (profiling mode would serialise the kernels of every step)
+        sm_clock_hz = 1e3 * std::max(1, lscgpu_sm_clock_khz(engine.get()));
     }
+    void setProfiling(bool on) { lscgpu_set_profiling(engine.get(), on ? 1 : 0); }
+    double smClockHz() const { return sm_clock_hz; }
     EnginePtr getEngine() const { return engine; }
 
     void setOctomap(const std::string& file) {      // MultiSyncSimulator::setOctomap (src/multi_sync_simulator.cpp:153-167)
@@ -132,8 +137,10 @@ private:
         std::vector<long long> expanded(N, 0);
         const int threads = (int)std::max(1u, std::min((unsigned)N, std::thread::hardware_concurrency()));
         std::vector<std::thread> pool;
+        std::vector<std::exception_ptr> errors(threads);      // an exception must not leave a std::thread body
         for (int t = 0; t < threads; t++)
             pool.emplace_back([&, t]() {
+              try {
                 std::vector<GoalObstacle> obstacles;
                 for (int a = t; a < N; a += threads) {
                     obstacles.clear();
@@ -146,8 +153,10 @@ private:
                                                                       mission.agents[a].downwash, obstacles, &distmap, mission, param, &grid_cache);
                     goals[a] = r.goal; expanded[a] = r.expansions;
                 }
+              } catch (...) { errors[t] = std::current_exception(); }
             });
         for (auto& th : pool) th.join();
+        for (auto& err : errors) if (err) std::rethrow_exception(err);
         for (int a = 0; a < N; a++) {
             for (int k = 0; k < 3; k++) in[a].goal[k] = goals[a](k);
             astar_expansions += expanded[a];
@@ -166,6 +175,7 @@ private:
     std::vector<bool> fresh;
     int planned_seq = 0;
     double wall_seconds = 0;
+    double sm_clock_hz = 1.965e9;
     lscgpu_step_stats stats{};
 };
 
@@ -194,6 +204,10 @@ public:
         if (flag_planned) return planning_report;
         batch->ensurePlanned(planner_seq);
         const lscgpu_agent_out& o = batch->result(agent.id);
+        // the reference throws from expandBoxFromPoint when the SFC seed cell is occupied
+        // (include/corridor_constructor.hpp:35-38); the engine reports it as a flag
+        if (o.flags & LSCGPU_FLAG_SFC_SEED_BLOCKED)
+            throw std::invalid_argument("[CorridorConstructor] invalid initial trajectory, obstacle exists at the initial trajectory");
         for (int m = 0; m < M; m++)
             for (int i = 0; i < n + 1; i++) traj_curr[m][i] = point3d(o.traj[m][i][0], o.traj[m][i][1], o.traj[m][i][2]);
         agent.current_goal_position = point3d(o.current_goal[0], o.current_goal[1], o.current_goal[2]);
@@ -206,9 +220,11 @@ public:
         t.obstacle_prediction_time.current = 0.5 * st.ms_predict * per;
         t.initial_traj_planning_time.current = 0.5 * st.ms_predict * per;
         t.goal_planning_time.current = batch->goalSecondsPerAgent();
-        t.lsc_generation_time.current = st.ms_lsc * per;
-        t.sfc_generation_time.current = st.ms_sfc * per;
-        t.traj_optimization_time.current = st.ms_qp * per;
+        // corridors (LSC rows with the SFC box grown beside them) and QP of THIS agent, from its block's cycle counters
+        const double corridor_s = 1024.0 * o.lsc_kcycles / batch->smClockHz();
+        t.lsc_generation_time.current = corridor_s;
+        t.sfc_generation_time.current = param.world_use_octomap ? corridor_s : 0.0;
+        t.traj_optimization_time.current = 1024.0 * std::max(0, o.qp_kcycles - o.lsc_kcycles) / batch->smClockHz();
         t.total_planning_time.current = batch->wallSecondsPerAgent();
         planning_time.update(t);
         flag_current_state_updated = false;                                           // :132-136

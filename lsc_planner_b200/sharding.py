@@ -1,10 +1,15 @@
 """Agent sharding across ranks (one process per GPU) and the rendezvous of the engine's own NCCL communicator.
 
 Within one synchronous replanning step every agent depends only on the PREVIOUS step's trajectories of all agents
-(Jacobi snapshot, reference src/multi_sync_simulator.cpp:190-318), so agents are block-partitioned: rank r plans
-agents [r*B, min(N, (r+1)*B)), B = ceil(N / world). Every rank keeps a replica of all trajectories; the step ends with
-ONE all-gather of the per-agent result records (464 B each), issued by liblscgpu.so on its own stream with its own
-communicator (lscgpu_nccl_init). torch.distributed is only the out-of-band channel that carries the NCCL unique id.
+(Jacobi snapshot, reference src/multi_sync_simulator.cpp:190-318), so any rank can plan any agent from its replica of
+the swarm state. The step time of a rank is the sum of its agents' plans and those differ by 10x between a crowded and
+a free agent, so the agents are DEALT OUT: every rank derives the same longest-processing-time-first order of all agents
+from the previous step's records (`lpt_order`, the rule of k_qp_order) and rank r plans entries r, r + G, r + 2G, ...
+(`deal`). Records land in a rank-major gather buffer of ceil(N / G) slots per rank, carry their agent id, and ONE
+all-gather (496 B per record), issued by liblscgpu.so on its own stream with its own communicator (lscgpu_nccl_init),
+completes every replica; `scatter_records` is the host mirror of what k_commit does with the gathered buffer.
+torch.distributed is only the out-of-band channel that carries the NCCL unique id. `partition` (contiguous blocks) is
+the rule for callers that shard by hand with lscgpu_set_shard.
 """
 from __future__ import annotations
 
@@ -17,8 +22,27 @@ def block_size(n_agents: int, world: int) -> int:
     return (n_agents + world - 1) // world
 
 
+def lpt_order(cost: np.ndarray) -> np.ndarray:
+    """Agents by decreasing cost of their previous plan, ties by id (k_qp_order, csrc/kernels_plan.cu)."""
+    cost = np.asarray(cost)
+    return np.lexsort((np.arange(len(cost)), -cost.astype(np.int64))).astype(np.int32)
+
+
+def deal(order: np.ndarray, world: int, rank: int) -> np.ndarray:
+    """The agents rank `rank` plans, in the order its blocks are issued (lscgpu_nccl_init's rule)."""
+    return np.asarray(order)[rank::world]
+
+
+def scatter_records(gathered: np.ndarray, agent_ids: np.ndarray, n_agents: int) -> np.ndarray:
+    """k_commit's rule: slot s of the gather buffer belongs to agent agent_ids[s]; negative ids are empty slots."""
+    out = np.zeros((n_agents,) + gathered.shape[1:], gathered.dtype)
+    ok = agent_ids >= 0
+    out[agent_ids[ok]] = gathered[ok]
+    return out
+
+
 def partition(n_agents: int, world: int, rank: int) -> Tuple[int, int]:
-    """Same rule as lscgpu_nccl_init (csrc/engine.cu)."""
+    """Contiguous blocks (for lscgpu_set_shard callers)."""
     b = block_size(n_agents, world)
     a0 = min(n_agents, rank * b)
     return a0, min(n_agents, a0 + b)
@@ -39,16 +63,21 @@ def connect(engine, rank: int, world: int):
     return engine
 
 
-def all_gather_blocks(local: np.ndarray, n_agents: int, world: int) -> np.ndarray:
-    """Host-side mirror of the in-place device all-gather (used by the CPU tests with the gloo backend):
-    `local` holds this rank's block of per-agent records; returns all n_agents records in agent order."""
+def all_gather_dealt(local: np.ndarray, my_agents: np.ndarray, n_agents: int, world: int) -> np.ndarray:
+    """Host-side mirror of the device exchange (CPU tests with the gloo backend): `local[i]` is the record of agent
+    my_agents[i]; every rank contributes a block of ceil(N / world) slots (unused ones carry id -1), the blocks are
+    all-gathered rank-major and scattered by agent id. Returns all n_agents records in agent order."""
     import torch
     import torch.distributed as dist
     b = block_size(n_agents, world)
     rec = local.reshape(local.shape[0], -1)
     pad = np.zeros((b, rec.shape[1]), rec.dtype)
     pad[: rec.shape[0]] = rec
+    ids = np.full(b, -1, np.int64)
+    ids[: len(my_agents)] = my_agents
     out = [torch.empty_like(torch.from_numpy(pad)) for _ in range(world)]
+    out_ids = [torch.empty_like(torch.from_numpy(ids)) for _ in range(world)]
     dist.all_gather(out, torch.from_numpy(pad))
-    full = np.concatenate([t.numpy() for t in out])[:n_agents]
+    dist.all_gather(out_ids, torch.from_numpy(ids))
+    full = scatter_records(np.concatenate([t.numpy() for t in out]), np.concatenate([t.numpy() for t in out_ids]), n_agents)
     return full.reshape((n_agents,) + local.shape[1:])

@@ -230,6 +230,7 @@ void orc_swarm_safety_audit(void* sv, double record_time_step, double time_step,
     ((Swarm*)sv)->safety_audit(record_time_step, time_step, ratio, closest);
 }
 void orc_swarm_step(void* sv, int a0, int a1, int threads) { ((Swarm*)sv)->step(a0, a1, threads); }
+void orc_swarm_step_list(void* sv, const int* ids, int n, int threads) { ((Swarm*)sv)->step_list(ids, n, threads); }
 void orc_swarm_advance(void* sv) { ((Swarm*)sv)->advance_states(); }
 int orc_swarm_seq(void* sv) { return ((Swarm*)sv)->seq; }
 void orc_swarm_get_traj(void* sv, float* out) { Swarm* s = (Swarm*)sv; std::memcpy(out, s->traj.data(), (size_t)s->N * 360); }

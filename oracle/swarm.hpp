@@ -195,23 +195,32 @@ struct Swarm {
 
     // one synchronous replanning step for agents [a0, a1)
     void step(int a0, int a1, int threads) {
+        std::vector<int> ids;
+        for (int a = a0; a < a1; a++) ids.push_back(a);
+        step_list(ids.data(), (int)ids.size(), threads, a0, a1);
+    }
+    // ... for an arbitrary set of agents (a multi-GPU rank's share of the swarm): all of them plan from the same snapshot
+    void step_list(const int* ids, int n_ids, int threads, int goal_a0 = -1, int goal_a1 = -1) {
         seq++;                                                         // traj_planner.cpp:127
         std::fill(flags.begin(), flags.end(), 0);
         if (capture) {
             cap_normal.assign((size_t)N * N * 5, f3(0, 0, 0)); cap_d.assign((size_t)N * N * 30, 0.0); cap_gjk.assign((size_t)N * N * 5, 0);
         }
         predict_all();
-        if (goal_mode == 1) plan_goals(a0, a1, threads);                // traj_planner.cpp:360-364 (after the initial trajectory)
+        if (goal_mode == 1) {                                           // traj_planner.cpp:360-364 (after the initial trajectory)
+            if (goal_a0 >= 0) plan_goals(goal_a0, goal_a1, threads);
+            else for (int t = 0; t < n_ids; t++) plan_goals(ids[t], ids[t] + 1, 1);
+        }
         std::vector<F3> new_traj = traj;
         if (threads <= 1) {
             std::vector<LscRows> rows;
-            for (int a = a0; a < a1; a++) plan_agent(a, new_traj, rows);
+            for (int t = 0; t < n_ids; t++) plan_agent(ids[t], new_traj, rows);
         } else {
             std::vector<std::thread> th;
             for (int t = 0; t < threads; t++)
                 th.emplace_back([&, t]() {
                     std::vector<LscRows> rows;
-                    for (int a = a0 + t; a < a1; a += threads) plan_agent(a, new_traj, rows);
+                    for (int k = t; k < n_ids; k += threads) plan_agent(ids[k], new_traj, rows);
                 });
             for (auto& t : th) t.join();
         }

@@ -64,6 +64,7 @@ def lib():
         L.orc_swarm_set_traj.argtypes = [C.c_void_p, f32p, C.c_int]
         L.orc_swarm_set_boxes.argtypes = [C.c_void_p, f32p, i32p]
         L.orc_swarm_step.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.orc_swarm_step_list.argtypes = [C.c_void_p, i32p, C.c_int, C.c_int]
         L.orc_swarm_safety_audit.argtypes = [C.c_void_p, C.c_double, C.c_double, f64p, i32p]
         L.orc_swarm_set_goal_mode.argtypes = [C.c_void_p, C.c_int] + [C.c_double] * 5
         L.orc_swarm_set_desired_goals.argtypes = [C.c_void_p, f32p]
@@ -271,6 +272,11 @@ class Swarm:
     def astar_expansions(self): return int(lib().orc_swarm_astar_expansions(self.h))
 
     def step(self, a0=0, a1=None, threads=1): lib().orc_swarm_step(self.h, a0, self.n if a1 is None else a1, threads)
+
+    def step_agents(self, ids, threads=1):
+        """One synchronous step in which only the listed agents re-plan (all from the same snapshot)."""
+        ids = np.ascontiguousarray(ids, np.int32)
+        lib().orc_swarm_step_list(self.h, ids, len(ids), threads)
 
     def advance(self): lib().orc_swarm_advance(self.h)
 

@@ -117,6 +117,15 @@ def test_shard_plans_only_its_block_and_reset():
     o_part = part.replan(scn.start, z, z, scn.goal).copy()
     assert np.array_equal(o_part["traj"][5:17], o_full["traj"][5:17])
     assert np.all(o_part["traj"][:5] == 0) and np.all(o_part["traj"][17:] == 0)
+    # second step of the hand-sharded engine: the caller gathers and refreshes the replicas (include/lscgpu.h); the
+    # engine itself only commits the agents it planned and must leave the other replicas alone
+    part.set_prev_traj(o_full["traj"], 1)
+    o_part2 = part.replan(o_full["next_position"], o_full["next_velocity"], o_full["next_acceleration"], scn.goal).copy()
+    o_full2 = full.replan(o_full["next_position"], o_full["next_velocity"], o_full["next_acceleration"], scn.goal).copy()
+    assert np.array_equal(o_part2["traj"][5:17], o_full2["traj"][5:17])
+    assert np.array_equal(o_part2["qp_status"][5:17], o_full2["qp_status"][5:17])
+    full.reset()
+    o_full = full.replan(scn.start, z, z, scn.goal).copy()
     o2 = full.replan(o_full["next_position"], o_full["next_velocity"], o_full["next_acceleration"], scn.goal).copy()
     assert full.planner_seq == 2
     full.reset()

@@ -21,7 +21,7 @@ scn = L.scenarios.circle_swap(150)
 prm = L.Param(world_min=scn.world_min, world_max=scn.world_max)
 sharded = L.ReplanEngine(scn.n, prm, scn.agents, device=local)
 sharding.connect(sharded, rank, world)
-assert (sharded.a0, sharded.a1) == sharding.partition(scn.n, world, rank)
+assert sharded.n_planned == len(sharding.deal(np.arange(scn.n), world, rank))
 single = L.ReplanEngine(scn.n, prm, scn.agents, device=local)
 pos = scn.start.copy(); vel = np.zeros_like(pos); acc = np.zeros_like(pos)
 for step in range(25):

@@ -150,7 +150,9 @@ def _teacher_forced(scn, steps, omap=None, bt=None, check_lsc_agents=(0,), traj_
                        scn.agents)
     if bt:
         e.set_octomap_file(bt)
+    e.set_capture_rows(True)          # the LSC assertions below read the rows the planning kernel itself built
     worst = []
+    n_culled = n_kept = 0
     for step in range(steps):
         pos, vel, acc = sw.state()
         traj_prev = sw.traj(); seq = sw.seq
@@ -164,11 +166,21 @@ def _teacher_forced(scn, steps, omap=None, bt=None, check_lsc_agents=(0,), traj_
         # initial trajectories / predictions: same float arithmetic -> bit-identical
         assert np.array_equal(e.initial_traj().view(np.uint32), sw.pred().view(np.uint32))
         nr_o, d_o, _ = sw.capture()
+        pred_o = sw.pred().astype(np.float64)
+        t_o_now = sw.traj().astype(np.float64)
         for a in check_lsc_agents:
-            nr, d = e.get_lsc(a)
+            nr, d, kept = e.get_lsc_rows(a)       # kept pairs: decoded from the production row store; culled: recomputed
             others = [j for j in range(n) if j != a]
             assert np.abs(nr - nr_o[a, others]).max() <= 1e-6
             assert np.abs(d - d_o[a, others]).max() <= 1e-6
+            assert kept.sum() == out["lsc_pairs_kept"][a]
+            n_kept += int(kept.sum()); n_culled += int((~kept).sum())
+            # exact culling: a dropped pair's rows are strictly satisfied at the oracle's (un-culled) solution
+            if q["status"][a] == 0 and (~kept).any():
+                rel = t_o_now[a][None] - pred_o[others]                                   # [n-1][5][6][3]
+                lhs = np.einsum("omik,omk->omi", rel, nr_o[a, others].astype(np.float64)) - d_o[a, others]
+                lhs[:, 0, :3] = np.inf                                                    # rows skipped for the initial state
+                assert lhs[~kept].min() > 0.0, (step, a, lhs[~kept].min())
         if omap is not None:
             bx, _ = e.get_sfc()
             assert np.array_equal(bx.view(np.uint32), sw.boxes().view(np.uint32)), step
@@ -190,6 +202,7 @@ def _teacher_forced(scn, steps, omap=None, bt=None, check_lsc_agents=(0,), traj_
         assert np.abs(out["next_velocity"] - v2).max() <= 1e-3 and np.abs(out["next_acceleration"] - a2).max() <= 5e-2
     worst = np.concatenate(worst)
     assert (worst > traj_tol).mean() <= 0.05
+    assert n_kept > 0
     return worst
 
 
@@ -349,3 +362,84 @@ def test_full_size_random_forest_512():
 
 def test_full_size_circle_forest_1024():
     _full_size_check("circle_forest", 1024, 60, 16)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE configs 3 / 4 / 5 at full size, EVERY agent compared with the oracle (threaded), teacher-forced, in two
+# mission phases: from rest, and after `skip` closed-loop steps on the device (agents in contact).
+# ---------------------------------------------------------------------------------------------------------
+def _report(entry):
+    import json
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, "parity_report.jsonl"), "a") as f:
+            f.write(json.dumps(entry) + "\n")
+
+
+def _teacher_forced_all_agents(workload, agents, skip, steps):
+    import bench
+    import lsc_planner_b200 as L
+    scn, bt = bench.make_scenario(workload, agents)
+    if scn is None:
+        tmp = L.ReplanEngine(2, L.Param(world_use_octomap=True)); tmp.set_octomap_file(bt); dm = tmp.distmap()
+        scn = L.scenarios.random_forest(agents, dm["sqdist"], dm["off"], seed=0); tmp.close()
+    n = scn.n
+    use_map = bool(scn.use_octomap)
+    e = L.ReplanEngine(n, L.Param(world_min=scn.world_min, world_max=scn.world_max, world_use_octomap=use_map), scn.agents)
+    if use_map:
+        e.set_octomap_file(bt)
+    sw = bench.oracle_swarm(scn, bt)
+    threads = os.cpu_count() or 1
+    ulp = float(np.spacing(np.float32(np.abs(np.concatenate([scn.world_min, scn.world_max])).max())))
+    tol_exact = 2.0 * ulp                       # trajectories are handed on as float32: two ulps at the world's extent
+    if skip:
+        # reach the phase on the device, then load the oracle with the engine's planner state
+        e.set_states(scn.start); e.set_goals(scn.goal)
+        e.replan_resident(skip)
+        o = e.fetch().copy()
+        sw.set_state(o["next_position"], o["next_velocity"], o["next_acceleration"])
+        sw.set_traj(o["traj"], e.planner_seq)
+        if use_map:
+            sw.set_boxes(e.get_sfc()[0], np.zeros(n, np.int32))
+    stats = dict(agent_steps=0, in_band=0, above_exact_tol=0, failed=0, worst_exact=0.0, worst_band=0.0, worst_cost_gap=0.0)
+    for step in range(steps):
+        pos, vel, acc = sw.state()
+        first = sw.seq == 0
+        if use_map:
+            e.set_sfc(sw.boxes(), np.full(n, 1 if first else 0, np.int32))
+        e.set_prev_traj(sw.traj(), sw.seq)
+        sw.step(0, n, threads)
+        out = e.replan(pos, vel, acc, scn.goal)
+        q = sw.qp()
+        assert e.planner_seq == sw.seq
+        assert np.array_equal(e.initial_traj().view(np.uint32), sw.pred().view(np.uint32))
+        if use_map:
+            assert np.array_equal(e.get_sfc()[0].view(np.uint32), sw.boxes().view(np.uint32)), step
+        assert np.array_equal(out["qp_status"], q["status"]), (step, np.flatnonzero(out["qp_status"] != q["status"]))
+        assert np.array_equal(out["flags"], q["flags"])
+        diffs = np.abs(out["traj"] - sw.traj()).reshape(n, -1).max(1)
+        in_band = q["maxviol"] > 1e-9
+        ok = q["status"] == 0
+        assert diffs[~in_band].max(initial=0) <= tol_exact, (step, diffs[~in_band].max(), tol_exact)
+        assert diffs.max() <= 2e-5, (step, diffs.max())
+        rel = np.abs(out["qp_cost"] - q["cost"]) / np.maximum(1.0, np.abs(q["cost"]))
+        assert rel[ok & ~in_band].max(initial=0) <= 1e-6 and rel[ok].max(initial=0) <= 1e-5
+        stats["agent_steps"] += n; stats["in_band"] += int(in_band.sum()); stats["failed"] += int((~ok).sum())
+        stats["above_exact_tol"] += int((diffs > tol_exact).sum())
+        stats["worst_exact"] = max(stats["worst_exact"], float(diffs[~in_band].max(initial=0)))
+        stats["worst_band"] = max(stats["worst_band"], float(diffs[in_band].max(initial=0)))
+        stats["worst_cost_gap"] = max(stats["worst_cost_gap"], float(rel[ok].max(initial=0)))
+        sw.advance()
+    stats.update(workload=f"{workload}_{n}", skip=skip, steps=steps, tol_exact=tol_exact,
+                 in_band_share=stats["in_band"] / stats["agent_steps"], above_tol_share=stats["above_exact_tol"] / stats["agent_steps"])
+    _report(stats)
+    assert stats["above_tol_share"] <= 0.02, stats
+    e.close()
+    return stats
+
+
+@pytest.mark.parametrize("workload,agents,skip", [("circle", 256, 0), ("circle", 256, 50),
+                                                  ("random_forest", 512, 0), ("random_forest", 512, 25),
+                                                  ("circle_forest", 1024, 0), ("circle_forest", 1024, 60)])
+def test_full_size_every_agent_teacher_forced(workload, agents, skip):
+    _teacher_forced_all_agents(workload, agents, skip, 10)

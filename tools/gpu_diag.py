@@ -30,7 +30,8 @@ for s in range(a.steps):
               "| sweeps p50 %.0f p99 %.0f max %.0f" % tuple(np.percentile(o["qp_sweeps"], [50, 99, 100])),
               f"| rows priced/iter {st['qp_rows_priced'] / max(st['qp_iterations'] + scn.n, 1):.0f}")
         dist = np.linalg.norm(o["next_position"] - scn.goal, axis=1)
-        print(f"step {s:4d} ms tot {st['ms_total']:.3f} lsc {st['ms_lsc']:.3f} sfc {st['ms_sfc']:.3f} qp {st['ms_qp']:.3f} | iters mean {it.mean():.1f} "
+        lk = o["lsc_kcycles"].astype(float) * 1024 / 1.965e3
+        print(f"step {s:4d} ms tot {st['ms_total']:.3f} predict {st['ms_predict']:.3f} plan {st['ms_plan']:.3f} commit {st['ms_commit']:.3f} | corridor us p50 {np.percentile(lk,50):.0f} p99 {np.percentile(lk,99):.0f} max {lk.max():.0f} | iters mean {it.mean():.1f} "
               f"p50 {np.percentile(it,50):.0f} p99 {np.percentile(it,99):.0f} max {it.max()} | status {np.bincount(o['qp_status'], minlength=3)} "
               f"active max {o['qp_active'].max()} | kept/agent {st['lsc_pairs_kept']/scn.n:.0f} sweeps {st['qp_full_passes']/scn.n:.2f} "
               f"flags {np.bincount(o['flags'], minlength=4)} | dist-to-goal mean {dist.mean():.2f}")
