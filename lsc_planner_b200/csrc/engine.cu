@@ -96,7 +96,17 @@ struct lscgpu_engine {
     cudaStream_t stream_aux = nullptr;     // k_qp_order (needs only the previous step's records) beside k_predict
     cudaEvent_t ev_fork = nullptr, ev_order = nullptr;
     bool lpt_order = true, qp_debug = false, use_graph = true;
-    int row_cap = 1024;              // kept pairs per agent held in shared memory by k_agent_plan
+    // Block size of k_agent_plan. 128 threads (4 blocks per SM, 256 rows in shared memory) overlaps four agents'
+    // latency-bound QP chains per SM; 256 threads (2 blocks, 1024 rows) is faster when the corridors dominate (crowded
+    // swarm, ~1000 kept pairs per agent). 0 = choose per step from the kept pairs of the last completed step. Results do
+    // not depend on the choice (the row order is canonical).
+    int plan_threads = 0;
+    int wide_kept = 500;             // mean kept pairs per agent from which the 256-thread configuration is used
+    int row_cap_forced = -1;
+    int* d_kept_step = nullptr;      // device: kept pairs of the step being planned
+    int* h_kept_last = nullptr;      // mapped host word: kept pairs of the last committed step
+    int* d_kept_last_map = nullptr;  // its device alias
+    long long sfc_wait_cycles = 60000;
     bool mirror_rows = false;        // also write every row to the global store (lscgpu_get_lsc reads production rows)
     long long* d_dbg = nullptr;
     float* d_audit_pos = nullptr; double* d_audit_ratio = nullptr; int* d_audit_closest = nullptr;   // lscgpu_safety_audit scratch
@@ -142,9 +152,9 @@ struct lscgpu_engine {
     NcclComm comm = nullptr;
     int rank = 0, n_ranks = 1, block = 0;
     // the step as a CUDA graph (steps with planner_seq >= 2 are identical launches)
-    cudaGraphExec_t graph = nullptr;
+    cudaGraphExec_t graph[2] = {nullptr, nullptr};   // [0] 256-thread, [1] 128-thread configuration
     bool graph_failed = false;
-    int graph_launches = 0;
+    int graph_launches[2] = {0, 0};
     // instrumentation: steps enqueued since the last synchronize
     struct StepEvents { cudaEvent_t ev[7]; };   // begin, predict|, plan|, exchange|, commit|, sfc[ ]sfc
     std::vector<StepEvents> ev_pool;    // per-kernel events of every pending step (profiling mode)
@@ -160,8 +170,7 @@ struct lscgpu_engine {
 };
 
 static void drop_graph(lscgpu_engine* e) {
-    if (e->graph) cudaGraphExecDestroy(e->graph);
-    e->graph = nullptr;
+    for (auto& g : e->graph) { if (g) cudaGraphExecDestroy(g); g = nullptr; }
 }
 
 static void free_rows(lscgpu_engine* e) {
@@ -209,6 +218,7 @@ extern "C" void lscgpu_destroy(lscgpu_engine* e) {
     free_rows(e);
     e->scratch.release();
     cudaFree(e->d_order); cudaFree(e->d_block_of);
+    cudaFree(e->d_kept_step); if (e->h_kept_last) cudaFreeHost(e->h_kept_last);
     cudaFree(e->d_epoch); cudaFree(e->d_sfc_ready); cudaFree(e->d_sfc_box); cudaFree(e->d_sfc_ok);
     if (e->ev_sfc) cudaEventDestroy(e->ev_sfc);
     cudaFree(e->d_rdw); cudaFree(e->d_audit_pos); cudaFree(e->d_audit_ratio); cudaFree(e->d_audit_closest); cudaFree(e->d_dbg);
@@ -242,6 +252,7 @@ static int reset_state(lscgpu_engine* e) {
     CU(cudaStreamSynchronize(e->stream));
     e->planner_seq = 0;
     e->pending = 0; e->pending_launches = 0;
+    if (e->h_kept_last) *e->h_kept_last = 0;
     return LSCGPU_OK;
 }
 
@@ -292,7 +303,10 @@ extern "C" int lscgpu_create(const lscgpu_params* p, int n_agents, const lscgpu_
     CUB(cudaEventCreateWithFlags(&e->ev_sfc, cudaEventDisableTiming));
     if (const char* v = getenv("LSCGPU_LPT_ORDER")) e->lpt_order = atoi(v) != 0;
     if (const char* v = getenv("LSCGPU_GRAPH")) e->use_graph = atoi(v) != 0;
-    if (const char* v = getenv("LSCGPU_ROW_CAP")) e->row_cap = std::min(std::max(atoi(v), 0), 2560) / 32 * 32;
+    if (const char* v = getenv("LSCGPU_PLAN_THREADS")) { const int t = atoi(v); e->plan_threads = t == 128 ? 128 : (t == 256 ? 256 : 0); }
+    if (const char* v = getenv("LSCGPU_WIDE_KEPT")) e->wide_kept = atoi(v);
+    if (const char* v = getenv("LSCGPU_ROW_CAP")) e->row_cap_forced = std::min(std::max(atoi(v), 0), 2560) / 32 * 32;
+    if (const char* v = getenv("LSCGPU_SFC_WAIT_CYCLES")) e->sfc_wait_cycles = atoll(v);
     e->qp_debug = getenv("LSCGPU_QP_DEBUG") != nullptr;
     CUB(cudaEventCreate(&e->ev_begin));
     CUB(cudaEventCreate(&e->ev_end));
@@ -335,6 +349,11 @@ extern "C" int lscgpu_create(const lscgpu_params* p, int n_agents, const lscgpu_
     CUB(cudaMalloc(&e->d_res, sizeof(lscgpu_agent_out) * N));
     CUB(cudaMalloc(&e->d_order, sizeof(int) * N));
     CUB(cudaMalloc(&e->d_block_of, sizeof(int) * N));
+    CUB(cudaMalloc(&e->d_kept_step, sizeof(int)));
+    CUB(cudaMemset(e->d_kept_step, 0, sizeof(int)));
+    CUB(cudaHostAlloc(&e->h_kept_last, sizeof(int), cudaHostAllocMapped));
+    if (e->h_kept_last) *e->h_kept_last = 0;
+    CUB(cudaHostGetDevicePointer(&e->d_kept_last_map, e->h_kept_last, 0));
     CUB(cudaMalloc(&e->d_epoch, sizeof(int)));
     CUB(cudaMemset(e->d_epoch, 0, sizeof(int)));
     CUB(cudaMalloc(&e->d_sfc_ready, sizeof(int) * N));
@@ -513,7 +532,7 @@ extern "C" int lscgpu_nccl_init(lscgpu_engine* e, const uint8_t id_bytes[128], i
 // Kernels of one step on the engine stream `s` (k_qp_order forks onto the aux stream and is joined before the plan):
 //   k_qp_order || k_predict [-> k_goal_plan] -> k_agent_plan -> [ncclAllGather] -> k_commit
 // `ev` (profiling) gets an event after each stage. Callable under stream capture.
-static int enqueue_step_kernels(lscgpu_engine* e, int planner_seq, cudaEvent_t* ev, int* launches_out) {
+static int enqueue_step_kernels(lscgpu_engine* e, int planner_seq, int threads, cudaEvent_t* ev, int* launches_out) {
     cudaStream_t s = e->stream;
     int launches = 0;
     const int n_plan = e->n_plan();
@@ -565,6 +584,7 @@ static int enqueue_step_kernels(lscgpu_engine* e, int planner_seq, cudaEvent_t* 
 
     PlanLaunch L{};
     L.n_agents = e->N; L.n_pad = e->n_pad; L.n_blocks = n_plan;
+    L.threads = threads; L.sfc_wait_cycles = e->sfc_wait_cycles;
     L.order = ordered ? e->d_order : nullptr;
     L.order_first = dealt ? e->rank : 0; L.order_stride = dealt ? e->n_ranks : 1;
     // without an order (first step): rank r of a dealt job takes agents r, r + G, ... through an identity "order"
@@ -573,7 +593,9 @@ static int enqueue_step_kernels(lscgpu_engine* e, int planner_seq, cudaEvent_t* 
     if (dealt) L.agent_base = e->rank;
     L.pred = e->d_pred; L.predT = e->d_predT; L.predZs = e->d_predZs; L.consts = e->d_consts; L.rdw = e->d_rdw; L.T = e->d_tables;
     L.state9 = e->d_state9; L.goal3 = e->d_goal3; L.ts = e->d_ts; L.sphere = e->d_sphere; L.reach = e->d_reach;
-    L.row_cap = e->row_cap; L.P_pad = e->P_pad; L.mirror_rows = e->mirror_rows ? 1 : 0;
+    L.row_cap = e->row_cap_forced >= 0 ? e->row_cap_forced : (threads == 128 ? 256 : 1024);
+    L.P_pad = e->P_pad; L.mirror_rows = e->mirror_rows ? 1 : 0;
+    L.kept_step = e->d_kept_step;
     L.rows = e->d_rows; L.kept = e->d_kept; L.kept_count = e->d_kept_count; L.safe = e->d_safe;
     L.block_of = e->mirror_rows ? e->d_block_of : nullptr;
     L.use_sfc = e->prm.world_use_octomap ? 1 : 0;
@@ -599,7 +621,7 @@ static int enqueue_step_kernels(lscgpu_engine* e, int planner_seq, cudaEvent_t* 
     const int n_slots = dealt ? e->block * e->n_ranks : n_plan;
     if (use_sfc && n_plan > 0 && side) CU(cudaStreamWaitEvent(s, e->ev_sfc, 0));     // k_commit rewrites what k_sfc_step reads
     launch_commit(n_slots, e->d_gather, e->d_res, e->d_traj, e->d_in, e->d_last_cost,
-                  use_sfc ? e->d_boxes : nullptr, e->d_init_sfc, e->d_epoch, s); launches++;
+                  use_sfc ? e->d_boxes : nullptr, e->d_init_sfc, e->d_epoch, e->d_kept_step, e->d_kept_last_map, s); launches++;
     if (ev) CU(cudaEventRecord(ev[4], s));
     *launches_out = launches;
     return LSCGPU_OK;
@@ -637,18 +659,25 @@ static int step_device(lscgpu_engine* e) {
     int launches = 0;
     // Steps from the second on are the same launches with the same arguments: one CUDA graph, instantiated at the
     // first such step and re-launched afterwards (profiling and debug modes enqueue the kernels directly).
+    int threads = e->plan_threads;
+    if (threads == 0) {
+        const int n_plan = std::max(e->n_plan(), 1);
+        const int kept_last = *(volatile int*)e->h_kept_last;          // of the last step the GPU has completed
+        threads = kept_last / n_plan >= e->wide_kept ? 256 : 128;
+    }
+    const int gi = threads == 128 ? 1 : 0;
     const bool graphable = e->use_graph && !e->graph_failed && !prof && !e->qp_debug && seq >= 2;
-    if (graphable && !e->graph) {
+    if (graphable && !e->graph[gi]) {
         cudaGraph_t g = nullptr;
         int rc = LSCGPU_OK;
         if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-            rc = enqueue_step_kernels(e, seq, nullptr, &launches);
+            rc = enqueue_step_kernels(e, seq, threads, nullptr, &launches);
             const cudaError_t ce = cudaStreamEndCapture(s, &g);
             if (rc == LSCGPU_OK && ce == cudaSuccess && g &&
-                cudaGraphInstantiate(&e->graph, g, nullptr, nullptr, 0) == cudaSuccess) {
-                e->graph_launches = launches;
+                cudaGraphInstantiate(&e->graph[gi], g, nullptr, nullptr, 0) == cudaSuccess) {
+                e->graph_launches[gi] = launches;
             } else {
-                e->graph = nullptr; e->graph_failed = true;
+                e->graph[gi] = nullptr; e->graph_failed = true;
                 cudaGetLastError();             // clear the capture error; the kernels are enqueued directly below
             }
             if (g) cudaGraphDestroy(g);
@@ -657,11 +686,11 @@ static int step_device(lscgpu_engine* e) {
             cudaGetLastError();
         }
     }
-    if (graphable && e->graph) {
-        CU(cudaGraphLaunch(e->graph, s));
-        launches = e->graph_launches;
+    if (graphable && e->graph[gi]) {
+        CU(cudaGraphLaunch(e->graph[gi], s));
+        launches = e->graph_launches[gi];
     } else {
-        const int rc = enqueue_step_kernels(e, seq, ev, &launches);
+        const int rc = enqueue_step_kernels(e, seq, threads, ev, &launches);
         if (rc != LSCGPU_OK) return rc;
     }
     CU(cudaEventRecord(e->step_ev[e->pending].second, s));

@@ -54,6 +54,8 @@ struct DistMapDev {
 struct PlanLaunch {
     int n_agents, n_pad;
     int n_blocks;                  // blocks of this launch = agents this engine plans in this step
+    int threads;                   // 256 (two blocks per SM) or 128 (four)
+    long long sfc_wait_cycles;     // how long an early block waits for k_sfc_step's box before growing it itself
     // block i plans agent order[order_first + i * order_stride] (global id), or agent_base + i when order == null.
     // The order is longest-processing-time-first over the agents of the job (k_qp_order); one GPU takes every entry, G
     // ranks deal the entries out round-robin (rank r: order_first = r, order_stride = G) so that every rank gets the
@@ -101,10 +103,11 @@ struct PlanLaunch {
     double* last_cost;             // [N]
     const int* goal_kind;          // [N] or null
     StepCounters* counters;
-    long long* dbg;                // null, or [n_blocks][8] section cycle counts (LSCGPU_QP_DEBUG)
+    int* kept_step;                // sum of the kept pairs of this launch (k_commit hands it to the host: block-size choice)
+    long long* dbg;                // null, or [n_blocks][10] section cycle counts (LSCGPU_QP_DEBUG)
 };
 void launch_agent_plan(const PlanLaunch& L, cudaStream_t s);
-size_t agent_plan_smem_bytes(int row_cap);
+size_t agent_plan_smem_bytes(int row_cap, int threads);
 cudaError_t configure_agent_plan();     // once per device, before the first launch
 
 // one agent's LSCs recomputed into CollisionConstraints layout (debug / parity)
@@ -147,7 +150,8 @@ void launch_qp_order(int n, int a0, const lscgpu_agent_out* res, int* order, cud
 // trajectory becomes traj_curr, the advanced state becomes the next resident input
 // (and, with an octomap, the agent's SFC window takes the step's new box, src/traj_planner.cpp:1451-1491)
 void launch_commit(int n_slots, const lscgpu_agent_out* gather, lscgpu_agent_out* res, float* prev_traj, lscgpu_agent_in* in,
-                   double* last_cost, float* boxes /* null: no octomap */, int* init_sfc, int* planner_seq_dev, cudaStream_t s);
+                   double* last_cost, float* boxes /* null: no octomap */, int* init_sfc, int* epoch, int* kept_step,
+                   volatile int* kept_host /* mapped host word or null */, cudaStream_t s);
 
 // safety audit of the planned step (src/multi_sync_simulator.cpp:446-475)
 void launch_safety_audit(int n_agents, const float* traj, const AgentConstDev* consts, double dt, int n_samples,

@@ -301,10 +301,16 @@ void launch_rows_from_lsc(int n_problems, const int* obs_offset, int total_obs, 
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_commit(int n_slots, const lscgpu_agent_out* gather, lscgpu_agent_out* res,
                                                 float* prev_traj, lscgpu_agent_in* in, double* last_cost, float* boxes,
-                                                int* init_sfc, int* planner_seq_dev) {
+                                                int* init_sfc, int* epoch, int* kept_step, volatile int* kept_host) {
     const int slot = blockIdx.x;
     const int e = threadIdx.x;
-    if (slot == 0 && e == 0 && planner_seq_dev) *planner_seq_dev += 1;
+    if (slot == 0 && e == 0) {
+        if (epoch) *epoch += 1;
+        if (kept_step) {            // kept pairs of the step just planned: the host picks the next steps' block size from it
+            if (kept_host) { *kept_host = *kept_step; __threadfence_system(); }
+            *kept_step = 0;
+        }
+    }
     const lscgpu_agent_out& o = gather[slot];
     const int a = o.agent_id;
     if (a < 0) return;
@@ -330,8 +336,9 @@ __global__ void __launch_bounds__(128) k_commit(int n_slots, const lscgpu_agent_
     }
 }
 void launch_commit(int n_slots, const lscgpu_agent_out* gather, lscgpu_agent_out* res, float* prev_traj, lscgpu_agent_in* in,
-                   double* last_cost, float* boxes, int* init_sfc, int* planner_seq_dev, cudaStream_t s) {
-    if (n_slots > 0) k_commit<<<n_slots, 128, 0, s>>>(n_slots, gather, res, prev_traj, in, last_cost, boxes, init_sfc, planner_seq_dev);
+                   double* last_cost, float* boxes, int* init_sfc, int* epoch, int* kept_step, volatile int* kept_host,
+                   cudaStream_t s) {
+    if (n_slots > 0) k_commit<<<n_slots, 128, 0, s>>>(n_slots, gather, res, prev_traj, in, last_cost, boxes, init_sfc, epoch, kept_step, kept_host);
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -27,8 +27,8 @@
 
 namespace lscgpu {
 
-constexpr int kPlanThreads = 256;
-constexpr int kPlanWarps = kPlanThreads / 32;
+constexpr int kBatchThreads = 256;       // k_qp_batch
+constexpr int kMaxPlanWarps = 8;
 
 // LSC-phase scratch (beside QpShared; the survivor queue aliases QpShared::Q, which the QP only touches afterwards)
 struct LscShared {
@@ -36,21 +36,20 @@ struct LscShared {
     float own_zs[30];
     float4 own_sphere[kM];
     float own_reach[kM];
-    int warp_tot[2][kPlanWarps];
+    int warp_tot[2][kMaxPlanWarps];
     int sfc_ok;
     float sfc_box[6];           // the box the SFC warp grew in this step
-    long long t_sfc, t_lsc;     // cycles the SFC warp / the LSC warps needed (diagnostics)
-    int lsc_done;               // set when the LSC warps are through (the SFC warp stops waiting for k_sfc_step)
+    long long t_sfc, t_lsc;     // cycles until the SFC box was there / the LSC rows were done (diagnostics)
     int sfc_self;               // 1: the block grew the box itself
 };
 
 __host__ __device__ constexpr size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 struct PlanSmemLayout {
     size_t qp, lists, lsc, nr, rhs, gate, seg, total;
-    __host__ __device__ explicit PlanSmemLayout(int cap) {
+    __host__ __device__ PlanSmemLayout(int cap, int threads) {
         qp = 0;
         lists = align16(qp + sizeof(QpShared));
-        lsc = align16(lists + sizeof(int) * kPlanWarps * kWarpList);
+        lsc = align16(lists + sizeof(int) * (threads / 32) * kWarpList);
         nr = align16(lsc + sizeof(LscShared));
         rhs = nr + sizeof(float4) * (size_t)cap;
         gate = rhs + sizeof(double2) * 3 * (size_t)cap;
@@ -58,15 +57,10 @@ struct PlanSmemLayout {
         total = align16(seg + (size_t)cap);
     }
 };
-size_t agent_plan_smem_bytes(int row_cap) { return PlanSmemLayout(row_cap).total; }
-
-// barrier over the first n_threads threads of the block (whole warps); id 1 is the LSC phase's
-__device__ __forceinline__ void lsc_barrier(int n_threads) {
-    asm volatile("bar.sync 1, %0;" ::"r"(n_threads) : "memory");
-}
+size_t agent_plan_smem_bytes(int row_cap, int threads) { return PlanSmemLayout(row_cap, threads).total; }
 
 // ------------------------------------------------------------------------------------------------------------
-// LSC phase of agent a by threads [0, kT) of the block.
+// LSC phase of agent a by the kT threads of the block.
 //   Phase A (one neighbour per thread per chunk of kT): exact culling test per (neighbour, segment) from the bounding
 //     spheres — 80 B per neighbour, coalesced float4 reads. A pair is dropped only when its LSC rows cannot be violated
 //     by any trajectory that respects the velocity / acceleration limits, so dropping is
@@ -79,15 +73,15 @@ __device__ __forceinline__ void lsc_barrier(int n_threads) {
 // ------------------------------------------------------------------------------------------------------------
 template <int kT>
 __device__ __forceinline__ int lsc_phase(const PlanLaunch& L, int a, const RowSrc& rows, LscShared& X, const QpShared& S,
-                                         int* queue, int& gjk_it) {
+                                         int2* queue, int& gjk_it) {
     constexpr int kW = kT / 32;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_obs = L.n_agents - 1;
     const AgentConstDev ca = L.consts[a];
     const float ra_f = (float)ca.radius, rdwa_f = (float)(ca.downwash * ca.radius);
     const double dw_self_a = (ca.downwash * ca.radius + ca.downwash * ca.radius) / (ca.radius + ca.radius);
-    // queue length and kept-list length: uniform values every participating thread keeps in a register
-    int q_count = 0, kept_base = 0, chunk = 0;
+    // queue length and number of survivors so far: uniform values every thread keeps in a register
+    int q_count = 0, kept_total = 0, chunk = 0;
 
     for (int j0 = 0; j0 < n_obs; j0 += kT, chunk++) {
         const int jj = j0 + tid;
@@ -112,8 +106,9 @@ __device__ __forceinline__ int lsc_phase(const PlanLaunch& L, int a, const RowSr
                 keep[m] = !(d_lb - rho > 2.0f * smax * X.own_reach[m]);
             }
         }
-        // order-preserving compaction (warp, then segment, then lane): the queue, and with it the slot order of the row
-        // store, is the same in every run. One shared-memory exchange of the per-warp totals per chunk.
+        // order-preserving compaction (warp, then segment, then lane). A survivor's SLOT in the row store is its rank in
+        // that order over the whole scan — the same for every block size and however the queue is drained, so results
+        // do not depend on the launch configuration. One shared-memory exchange of the per-warp totals per chunk.
         int cnt[kM], wtot = 0;
 #pragma unroll
         for (int m = 0; m < kM; m++) {
@@ -122,9 +117,9 @@ __device__ __forceinline__ int lsc_phase(const PlanLaunch& L, int a, const RowSr
             wtot += cnt[m];
         }
         if (lane == 0) X.warp_tot[chunk & 1][warp] = wtot;
-        lsc_barrier(kT);
+        __syncthreads();
         {
-            int off = q_count, total = 0;
+            int off = 0, total = 0;
 #pragma unroll
             for (int w = 0; w < kW; w++) {
                 const int c = X.warp_tot[chunk & 1][w];
@@ -133,18 +128,20 @@ __device__ __forceinline__ int lsc_phase(const PlanLaunch& L, int a, const RowSr
             }
 #pragma unroll
             for (int m = 0; m < kM; m++) {
-                if (keep[m]) queue[off + __popc(keep_mask[m] & ((1u << lane) - 1u))] = m * n_obs + jj;
+                const int r = off + __popc(keep_mask[m] & ((1u << lane) - 1u));
+                if (keep[m]) queue[q_count + r] = make_int2(m * n_obs + jj, kept_total + r);
                 off += cnt[m];
             }
             q_count += total;
+            kept_total += total;
         }
-        lsc_barrier(kT);
+        __syncthreads();
         // drain full batches (and everything after the last chunk)
         const bool last = j0 + kT >= n_obs;
         while (q_count >= kT || (last && q_count > 0)) {
             const int n_items = min(q_count, kT);
-            int p = -1;
-            if (tid < n_items) p = queue[q_count - n_items + tid];    // take the batch from the END of the queue
+            int p = -1, slot = 0;
+            if (tid < n_items) { const int2 it = queue[q_count - n_items + tid]; p = it.x; slot = it.y; }   // batch from the END
             q_count -= n_items;
             if (p >= 0) {
                 const int m = p / n_obs, jj2 = p - m * n_obs;
@@ -185,20 +182,20 @@ __device__ __forceinline__ int lsc_phase(const PlanLaunch& L, int a, const RowSr
                     const double mu = an > 0.0 ? slack * (double)inv_an * S.inv_gn[vi] : (slack < 0.0 ? -INFINITY : INFINITY);
                     mu_min = fmin(mu_min, mu);
                 }
-                rows.store(kept_base + tid, rec, m, p, mu_min > 0.0 ? mu_min * 0.999999 : mu_min, L.mirror_rows != 0);
+                rows.store(slot, rec, m, p, mu_min > 0.0 ? mu_min * 0.999999 : mu_min, L.mirror_rows != 0);
             }
-            kept_base += n_items;
         }
         // the queue tail that stays for the next chunk is only read after that chunk's barriers; nothing to wait for here
     }
-    return kept_base;
+    return kept_total;
 }
 
 // ------------------------------------------------------------------------------------------------------------
-template <bool kSfc>
-__global__ void __launch_bounds__(kPlanThreads, 2) k_agent_plan(PlanLaunch L) {
+template <int kPlanThreads, bool kSfc>
+__global__ void __launch_bounds__(kPlanThreads, 512 / kPlanThreads) k_agent_plan(PlanLaunch L) {
+    constexpr int kPlanWarps = kPlanThreads / 32;
     extern __shared__ __align__(16) unsigned char smem[];
-    const PlanSmemLayout lay(L.row_cap);
+    const PlanSmemLayout lay(L.row_cap, kPlanThreads);
     QpShared& S = *reinterpret_cast<QpShared*>(smem + lay.qp);
     int* open_lists = reinterpret_cast<int*>(smem + lay.lists);
     LscShared& X = *reinterpret_cast<LscShared*>(smem + lay.lsc);
@@ -223,53 +220,49 @@ __global__ void __launch_bounds__(kPlanThreads, 2) k_agent_plan(PlanLaunch L) {
     rows.g_kept = L.kept + (size_t)bi * L.P_pad;
     rows.n_obs = n_obs;
 
-    // ---- stage: QP tables + x0 (bounds come later, from the SFC warp), own prediction ---------------------------
+    // ---- stage: QP tables + x0 (bounds come later, with the SFC box), own prediction ----------------------------
     const double* st = L.state9 + (size_t)a * 9;
     const double* gl = L.goal3 + (size_t)a * 3;
     for (int e = tid; e < kTrajFloats; e += kPlanThreads) X.own[e] = L.pred[(size_t)a * kTrajFloats + e];
     if (tid < 30) X.own_zs[tid] = L.predZs[(size_t)tid * L.n_pad + a];
     if (tid < kM) { X.own_sphere[tid] = L.sphere[(size_t)tid * L.n_pad + a]; X.own_reach[tid] = L.reach[(size_t)a * kM + tid]; }
-    if (tid == 0) { X.sfc_ok = 1; X.lsc_done = 0; X.sfc_self = 0; }
+    if (tid == 0) { X.sfc_ok = 1; X.sfc_self = 0; X.t_sfc = 0; }
     qp_stage<kPlanThreads>(S, T, ts, st, gl, nullptr, L.wmin, L.wmax, L.consts[a]);     // ends with a block barrier
 
     // ---- phase 1: corridors -------------------------------------------------------------------------------------
     int n_kept = 0, gjk_it = 0;
-    int* queue = reinterpret_cast<int*>(S.Q);          // kPlanThreads * (kM + 1) ints = 6 KB of Q's 12 KB
-    if (kSfc) {
-        constexpr int kT = kPlanThreads - 32;
-        if (warp < kPlanWarps - 1) {
-            if (n_obs > 0) n_kept = lsc_phase<kT>(L, a, rows, X, S, queue, gjk_it);
-            if (tid == 0) { X.t_lsc = clock64() - t_start; *(volatile int*)&X.lsc_done = 1; }
-        } else {
-            // the box normally comes from k_sfc_step (launched beside k_predict): wait for it only as long as the LSC
-            // warps are busy anyway, then grow it here
-            const int epoch = *L.epoch;
-            bool have = false;
-            while (true) {
-                int ready = 0;
-                if (lane == 0) ready = *(volatile const int*)(L.sfc_ready + a) == epoch ? 1 : (*(volatile int*)&X.lsc_done ? 2 : 0);
-                ready = __shfl_sync(0xffffffffu, ready, 0);
-                if (ready == 1) { have = true; break; }
-                if (ready == 2) break;
-                __nanosleep(256);
-            }
-            if (have) {
-                __threadfence();
-                if (lane < 6) X.sfc_box[lane] = __ldcg(L.sfc_box_g + (size_t)a * 6 + lane);
-                if (lane == 0) { X.sfc_ok = __ldcg(L.sfc_ok_g + a); X.t_sfc = clock64() - t_start; }
-            } else {
-                SfcCtx c;
-                sfc_ctx_init(c, L.dm, L.wmin, L.wmax, L.res, lane);
-                double face;
-                const bool ok = sfc_agent_box(c, L.dm, L.consts[a].sat_index, L.res, L.in[a], L.prev_traj + (size_t)a * kTrajFloats,
-                                              L.init_sfc[a] != 0, face);
-                if (lane < 6) X.sfc_box[lane] = ok ? (float)face : 0.0f;
-                if (lane == 0) { X.sfc_ok = ok ? 1 : 0; X.sfc_self = 1; X.t_sfc = clock64() - t_start; }
-            }
+    int2* queue = reinterpret_cast<int2*>(S.Q);        // kPlanThreads * (kM + 1) entries <= 12 KB of Q + W's 24 KB
+    if (n_obs > 0) n_kept = lsc_phase<kPlanThreads>(L, a, rows, X, S, queue, gjk_it);
+    if (tid == 0) X.t_lsc = clock64() - t_start;
+    if (kSfc && warp == 0) {
+        // The step's new SFC box comes from k_sfc_step, launched at the start of the step beside k_predict. It is
+        // normally there by now; a block of the first wave may be early: it waits a bounded time (the walk takes
+        // 20-50 us), then grows the box itself — it never depends on another kernel's progress.
+        const int epoch = *L.epoch;
+        bool have = false;
+        const long long t_wait = clock64();
+        while (true) {
+            int ready = 0;
+            if (lane == 0) ready = *(volatile const int*)(L.sfc_ready + a) == epoch;
+            ready = __shfl_sync(0xffffffffu, ready, 0);
+            if (ready) { have = true; break; }
+            if (clock64() - t_wait > L.sfc_wait_cycles) break;
+            __nanosleep(512);
         }
-    } else {
-        if (n_obs > 0) n_kept = lsc_phase<kPlanThreads>(L, a, rows, X, S, queue, gjk_it);
-        if (tid == 0) { X.t_lsc = clock64() - t_start; X.t_sfc = 0; }
+        if (have) {
+            __threadfence();
+            if (lane < 6) X.sfc_box[lane] = __ldcg(L.sfc_box_g + (size_t)a * 6 + lane);
+            if (lane == 0) X.sfc_ok = __ldcg(L.sfc_ok_g + a);
+        } else {
+            SfcCtx c;
+            sfc_ctx_init(c, L.dm, L.wmin, L.wmax, L.res, lane);
+            double face;
+            const bool ok = sfc_agent_box(c, L.dm, L.consts[a].sat_index, L.res, L.in[a], L.prev_traj + (size_t)a * kTrajFloats,
+                                          L.init_sfc[a] != 0, face);
+            if (lane < 6) X.sfc_box[lane] = ok ? (float)face : 0.0f;
+            if (lane == 0) { X.sfc_ok = ok ? 1 : 0; X.sfc_self = 1; }
+        }
+        if (lane == 0) X.t_sfc = clock64() - t_start;
     }
     if (tid == 0) X.warp_tot[0][0] = n_kept;
     __syncthreads();
@@ -279,7 +272,11 @@ __global__ void __launch_bounds__(kPlanThreads, 2) k_agent_plan(PlanLaunch L) {
         if (lane == 0 && tot) atomicAdd(&L.counters->gjk_iterations, (unsigned long long)tot);
         if (tid == 0) atomicAdd(&L.counters->kept_pairs, (unsigned long long)n_kept);
     }
-    if (tid == 0) { L.kept_count[bi] = n_kept; if (L.block_of) L.block_of[a] = bi; }
+    if (tid == 0) {
+        L.kept_count[bi] = n_kept;
+        if (L.block_of) L.block_of[a] = bi;
+        if (L.kept_step) atomicAdd(L.kept_step, n_kept);
+    }
     // bounds: world box, intersected with the agent's SFC window as it stands after this step's new box
     if (tid < 15) {
         const int m = tid / 3, k = tid % 3;
@@ -372,28 +369,39 @@ __global__ void __launch_bounds__(kPlanThreads, 2) k_agent_plan(PlanLaunch L) {
 }
 
 // opt in to > 48 KB of dynamic shared memory and the largest shared-memory carve-out (two blocks per SM); per device
+template <int kT, bool kSfc>
+static cudaError_t configure_one() {
+    cudaError_t rc = cudaFuncSetAttribute(k_agent_plan<kT, kSfc>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (rc == cudaSuccess) rc = cudaFuncSetAttribute(k_agent_plan<kT, kSfc>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    return rc;
+}
 cudaError_t configure_agent_plan() {
-    cudaError_t rc = cudaFuncSetAttribute(k_agent_plan<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (rc == cudaSuccess) rc = cudaFuncSetAttribute(k_agent_plan<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (rc == cudaSuccess) rc = cudaFuncSetAttribute(k_agent_plan<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    if (rc == cudaSuccess) rc = cudaFuncSetAttribute(k_agent_plan<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaError_t rc = configure_one<256, true>();
+    if (rc == cudaSuccess) rc = configure_one<256, false>();
+    if (rc == cudaSuccess) rc = configure_one<128, true>();
+    if (rc == cudaSuccess) rc = configure_one<128, false>();
     return rc;
 }
 
 void launch_agent_plan(const PlanLaunch& L, cudaStream_t s) {
     if (L.n_blocks <= 0) return;
-    const size_t smem = agent_plan_smem_bytes(L.row_cap);
-    if (L.use_sfc) k_agent_plan<true><<<L.n_blocks, kPlanThreads, smem, s>>>(L);
-    else k_agent_plan<false><<<L.n_blocks, kPlanThreads, smem, s>>>(L);
+    const size_t smem = agent_plan_smem_bytes(L.row_cap, L.threads);
+    if (L.threads == 128) {
+        if (L.use_sfc) k_agent_plan<128, true><<<L.n_blocks, 128, smem, s>>>(L);
+        else k_agent_plan<128, false><<<L.n_blocks, 128, smem, s>>>(L);
+    } else {
+        if (L.use_sfc) k_agent_plan<256, true><<<L.n_blocks, 256, smem, s>>>(L);
+        else k_agent_plan<256, false><<<L.n_blocks, 256, smem, s>>>(L);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // k_qp_batch — TrajOptimizer::solve (src/traj_optimizer.cpp:31-154) for independent problems whose LSC rows arrive
 // from the host in the reference's container layout (k_rows_from_lsc); rows are priced from global memory.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kPlanThreads, 2) k_qp_batch(QpBatchLaunch L) {
+__global__ void __launch_bounds__(kBatchThreads, 2) k_qp_batch(QpBatchLaunch L) {
     __shared__ __align__(16) QpShared S;
-    __shared__ int open_lists[kPlanWarps * kWarpList];
+    __shared__ int open_lists[(kBatchThreads / 32) * kWarpList];
     const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int agent = L.agent_index[b];
     const QpTablesDev& T = *L.T;
@@ -404,9 +412,9 @@ __global__ void __launch_bounds__(kPlanThreads, 2) k_qp_batch(QpBatchLaunch L) {
     rows.g_rows = L.rows + pair0; rows.g_gate = L.safe + pair0; rows.g_kept = L.kept + pair0;
     rows.n_obs = L.obs_offset[b + 1] - L.obs_offset[b];
     const double* gl = L.goal3 + (size_t)b * 3;
-    qp_stage<kPlanThreads>(S, T, ts, L.state9 + (size_t)b * 9, gl, L.boxes ? L.boxes + (size_t)b * 30 : nullptr, L.wmin, L.wmax,
+    qp_stage<kBatchThreads>(S, T, ts, L.state9 + (size_t)b * 9, gl, L.boxes ? L.boxes + (size_t)b * 30 : nullptr, L.wmin, L.wmax,
                            L.consts[agent]);
-    const QpResultRegs R = qp_solve_core<kPlanThreads>(S, open_lists, rows, L.kept_count[b], T.vel_coef, T.acc_coef, L.max_iter, nullptr);
+    const QpResultRegs R = qp_solve_core<kBatchThreads>(S, open_lists, rows, L.kept_count[b], T.vel_coef, T.acc_coef, L.max_iter, nullptr);
     if (warp != 0) return;
     const double cost = qp_objective(S, T, ts, gl, lane);
     for (int e = lane; e < kNv; e += 32) L.x_out[(size_t)b * kNv + e] = S.x[e];
@@ -415,7 +423,7 @@ __global__ void __launch_bounds__(kPlanThreads, 2) k_qp_batch(QpBatchLaunch L) {
 
 void launch_qp_batch(const QpBatchLaunch& L, cudaStream_t s) {
     if (L.n_problems <= 0) return;
-    k_qp_batch<<<L.n_problems, kPlanThreads, 0, s>>>(L);
+    k_qp_batch<<<L.n_problems, kBatchThreads, 0, s>>>(L);
 }
 
 // ------------------------------------------------------------------------------------------------------------

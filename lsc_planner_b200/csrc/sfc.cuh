@@ -211,44 +211,57 @@ static __device__ bool expand_from_point(const SfcCtx& c, double res, F3 point, 
     const int g = c.lane >> 2, gl = c.lane & 3;
     while (n_cand > 0) {
         w.bc = w.box; w.bu = w.box;         // the first test after an erase is the whole box
-        bool pending = false;
-        int cooldown = 0;
         unsigned mask = 0;
         for (int k = 0; k < n_cand; k++) mask |= 1u << cand_at(cand, k);
-        while (true) {
-            if (pending && cooldown == 0) {
-                // `box` committed, slab of cand[i] proposed. One round-robin cycle = n_cand passed tests: every
-                // candidate face moves one step and cand[i]'s slab is proposed again. Skip k cycles that cannot fail.
-                const int k = free_cycles(c, w.box, mask, 1 << 14);
-                if (k > 0) {
-                    for (int t = 0; t < n_cand; t++) {
-                        const int axis = cand_at(cand, t);
-#pragma unroll
-                        for (int f = 0; f < 6; f++) if (axis == f) w.box.p[f] += f < 3 ? -k : k;
-                    }
-                    w.bc = w.box;
-                    w.i = w.i == 0 ? n_cand - 1 : w.i - 1;
-                    advance(w, cand, n_cand);          // re-propose cand[i]
-                } else cooldown = 2 * n_cand;
-            }
-            // speculative walk: group g tests the box reached after g further passed tests
-            Walk mine = w;
-            for (int t = 0; t < g; t++) advance(mine, cand, n_cand);
+        // That whole-box test, by all lanes together (its 8 sub-boxes over the lane groups). A failure erases the next
+        // candidate without any growth, exactly as the reference's loop does.
+        bool box_fail;
+        {
             int extra[3], lo[3], hi[3];
-            bool fail = !sample_cells(c, mine.bu, extra, lo, hi) || !in_boundary(c, mine.bu);
+            box_fail = !sample_cells(c, w.bu, extra, lo, hi) || !in_boundary(c, w.bu);
             int part = 0;
-            if (!fail) part = blocked_terms(c, extra, lo, hi, gl * 2, 2);
-            part += __shfl_xor_sync(0xffffffffu, part, 1);
-            part += __shfl_xor_sync(0xffffffffu, part, 2);
-            fail = fail || part != 0;
-            const unsigned fails = __ballot_sync(0xffffffffu, fail);
-            // first failing test (bit 4g of group g)
-            int first = 8;
-            for (int t = 7; t >= 0; t--) if (fails & (1u << (4 * t))) first = t;
-            for (int t = 0; t < first; t++) advance(w, cand, n_cand);
-            if (first > 0) pending = true;
-            if (cooldown > 0) cooldown = max(cooldown - first, 0);
-            if (first < 8) break;
+            if (!box_fail) part = blocked_terms(c, extra, lo, hi, g, 1);
+            box_fail = box_fail || warp_sum_int(gl == 0 ? part : 0) != 0;
+        }
+        if (!box_fail) {
+            advance(w, cand, n_cand);           // passed: the first candidate's slab is proposed
+            // `box` committed, slab of cand[i] proposed. One round-robin cycle = n_cand passed tests: every candidate
+            // face moves one step and cand[i]'s slab is proposed again. Skip the k cycles that cannot fail; the failing
+            // test then lies within the next cycle, which one speculative round (8 tests) covers.
+            int cooldown = 0;
+            while (true) {
+                if (cooldown == 0) {
+                    const int k = free_cycles(c, w.box, mask, 1 << 14);
+                    if (k > 0) {
+                        for (int t = 0; t < n_cand; t++) {
+                            const int axis = cand_at(cand, t);
+#pragma unroll
+                            for (int f = 0; f < 6; f++) if (axis == f) w.box.p[f] += f < 3 ? -k : k;
+                        }
+                        w.bc = w.box;
+                        w.i = w.i == 0 ? n_cand - 1 : w.i - 1;
+                        advance(w, cand, n_cand);          // re-propose cand[i]
+                    }
+                    cooldown = 2 * n_cand;
+                }
+                // speculative walk: group g tests the box reached after g further passed tests
+                Walk mine = w;
+                for (int t = 0; t < g; t++) advance(mine, cand, n_cand);
+                int extra[3], lo[3], hi[3];
+                bool fail = !sample_cells(c, mine.bu, extra, lo, hi) || !in_boundary(c, mine.bu);
+                int part = 0;
+                if (!fail) part = blocked_terms(c, extra, lo, hi, gl * 2, 2);
+                part += __shfl_xor_sync(0xffffffffu, part, 1);
+                part += __shfl_xor_sync(0xffffffffu, part, 2);
+                fail = fail || part != 0;
+                const unsigned fails = __ballot_sync(0xffffffffu, fail);
+                // first failing test (bit 4g of group g)
+                int first = 8;
+                for (int t = 7; t >= 0; t--) if (fails & (1u << (4 * t))) first = t;
+                for (int t = 0; t < first; t++) advance(w, cand, n_cand);
+                cooldown = max(cooldown - first, 0);
+                if (first < 8) break;
+            }
         }
         if (w.i < 0) w.i = 0;     // unreachable: the seed box was tested above
         // erase cand[i]

@@ -34,4 +34,4 @@ for s in range(a.steps):
         print(f"step {s:4d} ms tot {st['ms_total']:.3f} predict {st['ms_predict']:.3f} plan {st['ms_plan']:.3f} commit {st['ms_commit']:.3f} | corridor us p50 {np.percentile(lk,50):.0f} p99 {np.percentile(lk,99):.0f} max {lk.max():.0f} | iters mean {it.mean():.1f} "
               f"p50 {np.percentile(it,50):.0f} p99 {np.percentile(it,99):.0f} max {it.max()} | status {np.bincount(o['qp_status'], minlength=3)} "
               f"active max {o['qp_active'].max()} | kept/agent {st['lsc_pairs_kept']/scn.n:.0f} sweeps {st['qp_full_passes']/scn.n:.2f} "
-              f"flags {np.bincount(o['flags'], minlength=4)} | dist-to-goal mean {dist.mean():.2f}")
+              f"flags {np.bincount(o['flags'], minlength=4)} | sfc grown in block {o['sfc_in_block'].mean():.2f} | dist-to-goal mean {dist.mean():.2f}")
