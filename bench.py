@@ -98,6 +98,16 @@ class ClockSampler:
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
+        # nvidia-smi takes ~100 ms to come up and holds driver locks meanwhile: wait for its first sample, so that the
+        # start-up does not land inside a timed region that is only a few milliseconds long
+        t0 = time.perf_counter()
+        while self.proc is not None and time.perf_counter() - t0 < 3.0:
+            try:
+                if os.path.getsize(self.path) > 0:
+                    break
+            except OSError:
+                pass
+            time.sleep(0.02)
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
@@ -289,11 +299,11 @@ def run_ours(args):
 
     # ---- device-resident throughput (`value`) -----------------------------------------------------------------
     eng.set_profiling(False)
+    clocks = ClockSampler(local)          # samples every 100 ms through the timed pass and the e2e pass
     restart()
     resident_steps(args.warmup)
     eng.synchronize()
     barrier()
-    clocks = ClockSampler(local)
     resident_steps(args.steps)
     eng.synchronize()
     barrier()

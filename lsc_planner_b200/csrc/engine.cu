@@ -140,6 +140,7 @@ struct lscgpu_engine {
     int *d_kept = nullptr, *d_kept_count = nullptr;
     double* d_safe = nullptr;
     float4* d_sphere = nullptr;      // [5][n_pad]
+    float4* d_tsphere = nullptr;     // [n_pad]
     float* d_reach = nullptr;        // [N][5]
     StepCounters* d_counters = nullptr;
     Scratch scratch;                 // operator-level entries and setters
@@ -225,7 +226,7 @@ extern "C" void lscgpu_destroy(lscgpu_engine* e) {
     cudaFree(e->d_tables); cudaFree(e->d_consts); cudaFree(e->d_in); cudaFree(e->d_gather); cudaFree(e->d_res); cudaFree(e->d_traj);
     cudaFree(e->d_pred); cudaFree(e->d_predT); cudaFree(e->d_predZs); cudaFree(e->d_boxes); cudaFree(e->d_state9); cudaFree(e->d_goal3);
     cudaFree(e->d_last_cost); cudaFree(e->d_ts); cudaFree(e->d_flags); cudaFree(e->d_init_sfc); cudaFree(e->d_goal_kind); cudaFree(e->d_counters);
-    cudaFree(e->dm.sqdist); cudaFree(e->dm.sat); cudaFree(e->d_sphere); cudaFree(e->d_reach);
+    cudaFree(e->dm.sqdist); cudaFree(e->dm.sat); cudaFree(e->d_sphere); cudaFree(e->d_tsphere); cudaFree(e->d_reach);
     for (auto& se : e->ev_pool) for (auto& ev : se.ev) if (ev) cudaEventDestroy(ev);
     for (auto& pr : e->step_ev) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     if (e->ev_begin) cudaEventDestroy(e->ev_begin);
@@ -368,6 +369,8 @@ extern "C" int lscgpu_create(const lscgpu_params* p, int n_agents, const lscgpu_
     CUB(cudaMemset(e->d_predZs, 0, sizeof(float) * (size_t)30 * e->n_pad));
     CUB(cudaMalloc(&e->d_sphere, sizeof(float4) * (size_t)kM * e->n_pad));
     CUB(cudaMemset(e->d_sphere, 0, sizeof(float4) * (size_t)kM * e->n_pad));
+    CUB(cudaMalloc(&e->d_tsphere, sizeof(float4) * (size_t)e->n_pad));
+    CUB(cudaMemset(e->d_tsphere, 0, sizeof(float4) * (size_t)e->n_pad));
     CUB(cudaMalloc(&e->d_reach, sizeof(float) * N * kM));
     CUB(cudaMalloc(&e->d_boxes, sizeof(float) * N * 30));
     CUB(cudaMalloc(&e->d_state9, sizeof(double) * N * 9));
@@ -569,7 +572,7 @@ static int enqueue_step_kernels(lscgpu_engine* e, int planner_seq, int threads, 
     pl.dt = e->prm.dt; pl.reset_threshold = e->prm.reset_threshold;
     pl.in = e->d_in; pl.prev_traj = e->d_traj; pl.consts = e->d_consts;
     pl.pred = e->d_pred; pl.predT = e->d_predT; pl.predZs = e->d_predZs; pl.state9 = e->d_state9; pl.goal3 = e->d_goal3;
-    pl.ts = e->d_ts; pl.flags = e->d_flags; pl.sphere = e->d_sphere; pl.reach = e->d_reach;
+    pl.ts = e->d_ts; pl.flags = e->d_flags; pl.sphere = e->d_sphere; pl.tsphere = e->d_tsphere; pl.reach = e->d_reach;
     launch_predict(pl, s); launches++;
     if (e->prm.goal_mode == 1) {
         GoalLaunch gl{};
@@ -592,7 +595,7 @@ static int enqueue_step_kernels(lscgpu_engine* e, int planner_seq, int threads, 
     L.agent_stride = dealt ? e->n_ranks : 1;
     if (dealt) L.agent_base = e->rank;
     L.pred = e->d_pred; L.predT = e->d_predT; L.predZs = e->d_predZs; L.consts = e->d_consts; L.rdw = e->d_rdw; L.T = e->d_tables;
-    L.state9 = e->d_state9; L.goal3 = e->d_goal3; L.ts = e->d_ts; L.sphere = e->d_sphere; L.reach = e->d_reach;
+    L.state9 = e->d_state9; L.goal3 = e->d_goal3; L.ts = e->d_ts; L.sphere = e->d_sphere; L.tsphere = e->d_tsphere; L.reach = e->d_reach;
     L.row_cap = e->row_cap_forced >= 0 ? e->row_cap_forced : (threads == 128 ? 256 : 1024);
     L.P_pad = e->P_pad; L.mirror_rows = e->mirror_rows ? 1 : 0;
     L.kept_step = e->d_kept_step;

@@ -23,6 +23,7 @@ struct PredictLaunch {
     int* ts;                       // [N]
     int* flags;                    // [N]
     float4* sphere;                // [5][n_pad] bounding sphere (centre xyz, radius) of every segment's control points
+    float4* tsphere;               // [n_pad] bounding sphere of ALL control points of the trajectory (coarse culling pass)
     float* reach;                  // [N][5] how far ANY feasible control point of segment m can be from initial_traj's
 };
 void launch_predict(const PredictLaunch& L, cudaStream_t s);
@@ -74,6 +75,7 @@ struct PlanLaunch {
     const double* goal3;           // [N][3]
     const int* ts;                 // [N]
     const float4* sphere;          // [5][n_pad]
+    const float4* tsphere;         // [n_pad]
     const float* reach;            // [N][5]
     // row store: slots [0, row_cap) of every agent live in shared memory, the rest (everything when mirror_rows) in
     // the global overflow arrays [n_blocks][P_pad] (row i belongs to block i)

@@ -129,6 +129,19 @@ __global__ void __launch_bounds__(96) k_predict(PredictLaunch L) {
         const float r = fminf(sqrtf(r2) + sqrtf(far2), sqrtf(d2));
         L.reach[(size_t)a * kM + m] = r * 1.0001f + 1e-3f;
     }
+    if (e == 40) {
+        // bounding sphere of the whole trajectory: one 16-byte read per neighbour decides, for most pairs of a swarm
+        // that is much larger than an agent's reach, that none of the five segment pairs can matter
+        float cx = 0.f, cy = 0.f, cz = 0.f;
+        for (int i = 0; i < 30; i++) { cx += o[i * 3]; cy += o[i * 3 + 1]; cz += o[i * 3 + 2]; }
+        cx *= (1.f / 30.f); cy *= (1.f / 30.f); cz *= (1.f / 30.f);
+        float rad2 = 0.f;
+        for (int i = 0; i < 30; i++) {
+            const float x = o[i * 3] - cx, y = o[i * 3 + 1] - cy, z = o[i * 3 + 2] - cz;
+            rad2 = fmaxf(rad2, x * x + y * y + z * z);
+        }
+        L.tsphere[a] = make_float4(cx, cy, cz, sqrtf(rad2) * 1.0001f + 1e-5f);
+    }
 }
 
 void launch_predict(const PredictLaunch& L, cudaStream_t s) { k_predict<<<L.n_agents, 96, 0, s>>>(L); }

@@ -35,7 +35,9 @@ struct LscShared {
     float own[kTrajFloats];
     float own_zs[30];
     float4 own_sphere[kM];
+    float4 own_tsphere;
     float own_reach[kM];
+    float own_reach_max;
     int warp_tot[2][kMaxPlanWarps];
     int sfc_ok;
     float sfc_box[6];           // the box the SFC warp grew in this step
@@ -96,14 +98,22 @@ __device__ __forceinline__ int lsc_phase(const PlanLaunch& L, int a, const RowSr
             const float inv_dw = (ra_f + rj.x) / (rdwa_f + rj.y);
             const float smax = fmaxf(1.0f, inv_dw);
             const float rho = ra_f + rj.x;
+            // coarse pass: the trajectory spheres contain every segment hull, so their gap bounds every segment pair's
+            // hull distance from below; with the largest reach of the five segments the same test drops all five at once
+            const float4 to = X.own_tsphere;
+            const float4 tj = L.tsphere[j];
+            const float tx = to.x - tj.x, ty = to.y - tj.y, tz = (to.z - tj.z) * inv_dw;
+            const float t_lb = sqrtf(tx * tx + ty * ty + tz * tz) * 0.9999f - smax * (to.w + tj.w);
+            if (!(t_lb - rho > 2.0f * smax * X.own_reach_max)) {
 #pragma unroll
-            for (int m = 0; m < kM; m++) {
-                const float4 so = X.own_sphere[m];
-                const float4 sj = L.sphere[(size_t)m * L.n_pad + j];
-                const float dx = so.x - sj.x, dy = so.y - sj.y, dz = (so.z - sj.z) * inv_dw;
-                const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
-                const float d_lb = dist * 0.9999f - smax * (so.w + sj.w);        // lower bound of the hull distance
-                keep[m] = !(d_lb - rho > 2.0f * smax * X.own_reach[m]);
+                for (int m = 0; m < kM; m++) {
+                    const float4 so = X.own_sphere[m];
+                    const float4 sj = L.sphere[(size_t)m * L.n_pad + j];
+                    const float dx = so.x - sj.x, dy = so.y - sj.y, dz = (so.z - sj.z) * inv_dw;
+                    const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
+                    const float d_lb = dist * 0.9999f - smax * (so.w + sj.w);        // lower bound of the hull distance
+                    keep[m] = !(d_lb - rho > 2.0f * smax * X.own_reach[m]);
+                }
             }
         }
         // order-preserving compaction (warp, then segment, then lane). A survivor's SLOT in the row store is its rank in
@@ -226,6 +236,12 @@ __global__ void __launch_bounds__(kPlanThreads, 512 / kPlanThreads) k_agent_plan
     for (int e = tid; e < kTrajFloats; e += kPlanThreads) X.own[e] = L.pred[(size_t)a * kTrajFloats + e];
     if (tid < 30) X.own_zs[tid] = L.predZs[(size_t)tid * L.n_pad + a];
     if (tid < kM) { X.own_sphere[tid] = L.sphere[(size_t)tid * L.n_pad + a]; X.own_reach[tid] = L.reach[(size_t)a * kM + tid]; }
+    if (tid == 32) {
+        X.own_tsphere = L.tsphere[a];
+        float rm = 0.f;
+        for (int m = 0; m < kM; m++) rm = fmaxf(rm, L.reach[(size_t)a * kM + m]);
+        X.own_reach_max = rm;
+    }
     if (tid == 0) { X.sfc_ok = 1; X.sfc_self = 0; X.t_sfc = 0; }
     qp_stage<kPlanThreads>(S, T, ts, st, gl, nullptr, L.wmin, L.wmax, L.consts[a]);     // ends with a block barrier
 

@@ -133,6 +133,16 @@ __device__ __forceinline__ void consider(Best& b, double slack, double scale, in
     if (mu < b.mu) { b.mu = mu; b.id = id; }
 }
 
+// 1/x to ~1 ulp for normal x: hardware seed + two Newton steps (a third of the latency of an IEEE division)
+__device__ __forceinline__ double fast_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+
 __device__ __forceinline__ unsigned long long order_key(double v) {
     const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
     return bits ^ ((bits >> 63) ? ~0ull : 0x8000000000000000ull);
@@ -201,6 +211,7 @@ struct RowRegs {
     int idx[3];
     double a[3];
     double b, inv_len;
+    double nn;          // |normal * inv_len|^2: 1 up to the rounding of inv_len (the float32 1/|a| of an LSC record)
 };
 __device__ __forceinline__ RowRegs decode_row(int id, const QpShared& S, const RowSrc& rows, double vel_coef, double acc_coef) {
     RowRegs r;
@@ -212,6 +223,7 @@ __device__ __forceinline__ RowRegs decode_row(int id, const QpShared& S, const R
         if (side == 0) { r.a[0] = 1.0; r.b = S.lb[m * 3 + k]; }
         else { r.a[0] = -1.0; r.b = -S.ub[m * 3 + k]; }
         r.inv_len = S.inv_gn[mi];
+        r.nn = 1.0;
     } else if (id < kFixedRows) {
         const int e = id - 180, side = e & 1, idx = e >> 1;
         const int k = idx / 45, rem = idx - k * 45, m = rem / 9, j = rem - m * 9;
@@ -226,6 +238,7 @@ __device__ __forceinline__ RowRegs decode_row(int id, const QpShared& S, const R
             r.a[0] = sg * acc_coef; r.a[1] = -2.0 * sg * acc_coef; r.a[2] = sg * acc_coef; r.b = -S.amax[k];
         }
         r.inv_len = S.inv_dyn[m * 9 + j];
+        r.nn = 1.0;
     } else {
         const int e = id - kFixedRows, slot = e / 6, i = e - slot * 6;
         float4 nr; double r6[6]; int m;
@@ -238,8 +251,10 @@ __device__ __forceinline__ RowRegs decode_row(int id, const QpShared& S, const R
 #pragma unroll
         for (int t = 1; t < 6; t++) if (t == i) rb = r6[t];
         r.b = rb;
-        const double an2 = r.a[0] * r.a[0] + r.a[1] * r.a[1] + r.a[2] * r.a[2];
-        r.inv_len = an2 > 0.0 ? rsqrt(an2) * S.inv_gn[vi] : INFINITY;
+        // 1 / (|a| |G_vi|) with the record's float32 1/|a|: any consistent scale of normal and slack serves the update
+        // (the step, the multipliers and the travelled distance are invariant to it); 1/|a| = inf marks a zero normal
+        r.inv_len = (double)nr.w * S.inv_gn[vi];
+        r.nn = (r.a[0] * r.a[0] + r.a[1] * r.a[1] + r.a[2] * r.a[2]) * ((double)nr.w * (double)nr.w);
     }
     return r;
 }
@@ -255,7 +270,7 @@ __device__ __forceinline__ void drop_active(QpShared& S, int& q, int l, int lane
         const double nn = warp_sum(y0 * y0 + y1 * y1);              // > 0: W is invertible
         const double ny = nn * rsqrt(nn);
         const double sg = yj >= 0.0 ? 1.0 : -1.0;
-        const double beta = __drcp_rn(ny * (ny + fabs(yj)));        // 2 / (v . v),  v = y + sg |y| e_j
+        const double beta = fast_rcp(ny * (ny + fabs(yj)));         // 2 / (v . v),  v = y + sg |y| e_j
         if (lane < q) S.tmp[lane] = lane == j ? y0 + sg * ny : y0;
         if (lane + 32 < q) S.tmp[lane + 32] = lane + 32 == j ? y1 + sg * ny : y1;
         __syncwarp();
@@ -505,7 +520,7 @@ __device__ __forceinline__ QpResultRegs qp_solve_core(QpShared& S, int* open_lis
                     S.z[lane] = nv_reg[0]; S.d[lane] = 0.0;
                     if (lane + 32 < NR) { S.z[lane + 32] = nv_reg[1]; S.d[lane + 32] = 0.0; }
                     __syncwarp();
-                    double zz = 1.0;                 // |nv| = 1
+                    double zz = row.nn;              // |nv|^2
                     if (q > 0) {
 #pragma unroll 1
                         for (int pass = 0; pass < 2; pass++) {
@@ -601,7 +616,7 @@ __device__ __forceinline__ QpResultRegs qp_solve_core(QpShared& S, int* open_lis
                         for (int k = lane; k < q; k += 32) {
                             const double rk = S.rr[k];
                             if (rk > kZeroTol) {
-                                const unsigned long long kk = order_key(S.lam[k] * __drcp_rn(rk));
+                                const unsigned long long kk = order_key(S.lam[k] * fast_rcp(rk));
                                 if (kk < key) { key = kk; kbest = k; }
                             }
                         }
