@@ -449,25 +449,36 @@ void launch_qp_batch(const QpBatchLaunch& L, cudaStream_t s) {
 // replica and takes every G-th entry. It only affects scheduling, never results.
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_qp_order(int n, int a0, const lscgpu_agent_out* res, int* order) {
-    __shared__ int tile[256];
-    const int i = blockIdx.x * 256 + threadIdx.x;
+    // 32 agents per block (one per lane); the 8 warps split every tile of keys between them
+    constexpr int kTile = 2048;
+    __shared__ int tile[kTile];
+    __shared__ int part[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + lane;
     const int mine = i < n ? res[a0 + i].qp_kcycles : 0;
     int pos = 0;
-    for (int j0 = 0; j0 < n; j0 += 256) {
-        const int j = j0 + threadIdx.x;
-        tile[threadIdx.x] = j < n ? res[a0 + j].qp_kcycles : INT_MIN;
+    for (int j0 = 0; j0 < n; j0 += kTile) {
+        const int cnt = min(kTile, n - j0);
+        for (int t = threadIdx.x; t < cnt; t += 256) tile[t] = res[a0 + j0 + t].qp_kcycles;
         __syncthreads();
-        const int cnt = min(256, n - j0);
-        for (int t = 0; t < cnt; t++) {
+        const int per = (cnt + 7) / 8, t0 = warp * per, t1 = min(cnt, t0 + per);
+        for (int t = t0; t < t1; t++) {
             const int other = tile[t];
             pos += (other > mine) || (other == mine && j0 + t < i);
         }
         __syncthreads();
     }
-    if (i < n) order[pos] = a0 + i;
+    part[warp][lane] = pos;
+    __syncthreads();
+    if (warp == 0 && i < n) {
+        int p = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) p += part[w][lane];
+        order[p] = a0 + i;
+    }
 }
 void launch_qp_order(int n, int a0, const lscgpu_agent_out* res, int* order, cudaStream_t s) {
-    if (n > 0) k_qp_order<<<(n + 255) / 256, 256, 0, s>>>(n, a0, res, order);
+    if (n > 0) k_qp_order<<<(n + 31) / 32, 256, 0, s>>>(n, a0, res, order);
 }
 
 }  // namespace lscgpu
