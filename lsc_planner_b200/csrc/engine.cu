@@ -102,6 +102,7 @@ struct lscgpu_engine {
     // not depend on the choice (the row order is canonical).
     int plan_threads = 0;
     int wide_kept = 500;             // mean kept pairs per agent from which the 256-thread configuration is used
+    int n_sm = 148;
     int row_cap_forced = -1;
     int* d_kept_step = nullptr;      // device: kept pairs of the step being planned
     int* h_kept_last = nullptr;      // mapped host word: kept pairs of the last committed step
@@ -282,6 +283,7 @@ extern "C" int lscgpu_create(const lscgpu_params* p, int n_agents, const lscgpu_
 
     lscgpu_engine* e = new lscgpu_engine;
     e->prm = *p; e->N = n_agents; e->device = device;
+    e->n_sm = prop.multiProcessorCount;
     e->n_pad = (n_agents + 31) / 32 * 32;
     e->a0 = 0; e->a1 = n_agents; e->block = n_agents;
     e->consts_host.assign(agents, agents + n_agents);
@@ -666,7 +668,9 @@ static int step_device(lscgpu_engine* e) {
     if (threads == 0) {
         const int n_plan = std::max(e->n_plan(), 1);
         const int kept_last = *(volatile int*)e->h_kept_last;          // of the last step the GPU has completed
-        threads = kept_last / n_plan >= e->wide_kept ? 256 : 128;
+        // one wave of wide blocks (two per SM) holds every agent: the step is the slowest agent's chain, and eight warps
+        // shorten it (multi-GPU shares); otherwise four narrow blocks per SM overlap more QP chains
+        threads = (n_plan <= 2 * e->n_sm || kept_last / n_plan >= e->wide_kept) ? 256 : 128;
     }
     const int gi = threads == 128 ? 1 : 0;
     const bool graphable = e->use_graph && !e->graph_failed && !prof && !e->qp_debug && seq >= 2;

@@ -36,6 +36,8 @@
 // and evaluates the list one pair per lane. The solve ends when no evaluated row is violated beyond the tolerance
 // (every skipped row is provably satisfied).
 #pragma once
+#include <cstddef>
+
 #include "kernels.hpp"
 
 namespace lscgpu {
@@ -65,7 +67,29 @@ struct QpShared {
     int best_id[8];
     int act[NR + 1];
     int stop;                   // 0 run, 1 finished/failed (set by warp 0)
+    unsigned long long g_bar;   // mbarrier: completion of the bulk copy of G
 };
+
+// ---- bulk-asynchronous staging (TMA unit, non-tensor form): one thread arms an mbarrier with the byte count and issues
+// cp.async.bulk global -> shared; the copy proceeds while the block builds its corridors; consumers wait on the barrier
+// phase before the first use. (SASS: UBLKCP + SYNCS.)
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_stage_begin(unsigned long long* bar, void* dst_smem, const void* src_global, unsigned bytes) {
+    const unsigned b = smem_u32(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_global), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void bulk_stage_wait(unsigned long long* bar) {
+    const unsigned b = smem_u32(bar);
+    unsigned done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(b) : "memory");
+    } while (!done);
+}
 
 // Where the LSC rows of the agent live: slots [0, cap) in shared memory as structure-of-arrays (16-byte lanes of
 // consecutive slots fall into different banks), slots >= cap — and every slot when cap == 0 — in the global row store.
@@ -350,8 +374,11 @@ template <int kThreads>
 __device__ __forceinline__ void qp_stage(QpShared& S, const QpTablesDev& T, int ts, const double* st9, const double* gl3,
                                          const float* boxes, const float* wmin, const float* wmax, const AgentConstDev& ac) {
     const int tid = threadIdx.x;
-    const double* Gt = &T.G[ts - 1][0][0];
-    for (int e = tid; e < kAx * kFree; e += kThreads) S.G[e] = Gt[e];
+    // the whitened basis of this ts (3120 B, contiguous, 16-byte aligned on both sides) travels by one bulk-async copy
+    // that completes on S.g_bar; it is first needed by the factorisation update, long after the corridors are built
+    static_assert((sizeof(double) * kAx * kFree) % 16 == 0 && offsetof(QpTablesDev, G) % 16 == 0 && offsetof(QpShared, G) % 16 == 0,
+                  "bulk copy of G needs 16-byte alignment and size");
+    if (tid == 0) bulk_stage_begin(&S.g_bar, S.G, &T.G[ts - 1][0][0], (unsigned)(sizeof(double) * kAx * kFree));
     for (int e = tid; e < kAx; e += kThreads) S.inv_gn[e] = 1.0 / T.gnorm[ts - 1][e];
     for (int e = tid; e < kM * 9; e += kThreads) S.inv_dyn[e] = 1.0 / T.dyn_norm[ts - 1][e / 9][e % 9];
     if (tid < 15) {
@@ -388,6 +415,7 @@ __device__ __forceinline__ QpResultRegs qp_solve_core(QpShared& S, int* open_lis
 #endif
     (void)sec;
 
+    bulk_stage_wait(&S.g_bar);      // G has landed (the copy was issued before the corridor phase)
     FixedItems<kItems> F;
 #pragma unroll
     for (int t = 0; t < kItems; t++) {
