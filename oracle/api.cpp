@@ -148,6 +148,24 @@ int orc_qp_dense(void* tv, const double* state9, const double* goal3, int ts, co
 
 void orc_set_tier_threshold(double t) { g_tier_threshold = t; }
 
+// The QP with slack variables (qp_solve_slack): row_slack[r] = 1 marks the (obstacle, segment) entries of obstacles in
+// obs_slack_indices. eps_out[n_rows]; info = cost, iters, n_active, kkt, maxviol, slack_cost.
+int orc_qp_solve_slack(void* tv, const double* state9, const double* goal3, int ts, const double* lb, const double* ub,
+                       const double* vmax, const double* amax, int n_rows, const int* row_m, const double* row_a,
+                       const double* row_rhs, const int* row_slack, double slack_w, double* x90, double* eps_out, double* info) {
+    QpProblem p; std::vector<LscRows> rows;
+    fill_problem(p, rows, state9, goal3, ts, lb, ub, vmax, amax, n_rows, row_m, row_a, row_rhs);
+    for (int r = 0; r < n_rows; r++) rows[r].slack = row_slack[r];
+    p.slack_w = slack_w;
+    QpResult r;
+    qp_solve_slack(*(QpTables*)tv, p, r);
+    std::memcpy(x90, r.x, sizeof r.x);
+    for (int i = 0; i < n_rows; i++) eps_out[i] = r.eps[i];
+    info[0] = r.cost; info[1] = r.iters; info[2] = r.n_active; info[3] = r.kkt_stationarity; info[4] = r.max_violation;
+    info[5] = r.slack_cost;
+    return r.status;
+}
+
 // ---- swarm ------------------------------------------------------------------------------------
 void* orc_swarm_create(int n_agents, double dt, double w, double wT, double res, double reset_threshold,
                        int use_octomap, const float* wmin, const float* wmax, const double* radius,
@@ -168,6 +186,14 @@ void* orc_swarm_create(int n_agents, double dt, double w, double wT, double res,
 void orc_swarm_free(void* sv) { delete (Swarm*)sv; }
 void orc_swarm_set_map(void* sv, void* map) { ((Swarm*)sv)->dm = map ? &((MapHandle*)map)->dm : nullptr; }
 void orc_swarm_set_capture(void* sv, int on) { ((Swarm*)sv)->capture = on != 0; }
+void orc_swarm_set_slack_weight(void* sv, double w) { ((Swarm*)sv)->prm.slack_w = w; }
+// sticky disturbance state (who was ever reset) and the slack outputs of the last step
+void orc_swarm_get_reset_ever(void* sv, unsigned char* out) { Swarm* s = (Swarm*)sv; for (int a = 0; a < s->N; a++) out[a] = (unsigned char)s->reset_ever[a]; }
+void orc_swarm_set_reset_ever(void* sv, const unsigned char* in) { Swarm* s = (Swarm*)sv; for (int a = 0; a < s->N; a++) s->reset_ever[a] = (char)in[a]; }
+void orc_swarm_get_slack(void* sv, double* slack_cost, int* slack_rows) {
+    Swarm* s = (Swarm*)sv;
+    for (int a = 0; a < s->N; a++) { slack_cost[a] = s->qp_slack_cost[a]; slack_rows[a] = s->qp_slack_rows[a]; }
+}
 void orc_swarm_set_state(void* sv, const float* pos, const float* vel, const float* acc) {
     Swarm* s = (Swarm*)sv;
     std::memcpy(s->pos.data(), pos, s->N * 12); std::memcpy(s->vel.data(), vel, s->N * 12); std::memcpy(s->acc.data(), acc, s->N * 12);

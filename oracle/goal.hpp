@@ -266,7 +266,7 @@ struct GoalResult { F3 goal; int mode; int n_high; long long expansions; };   //
 //   prev_traj[j*30 ..] traj_curr of every agent (obs_prev_trajs), init_end = initial_traj[M-1][n] of agent a.
 inline GoalResult goal_planning_priority(int a, int n, const F3* pos, const F3* desired, const F3* prev_traj, F3 init_end,
                                          const AgentConst* ac, const DistMap* dm, const GoalParams& gp, F3 world_min,
-                                         F3 world_max) {
+                                         F3 world_max, const char* in_slack_set = nullptr) {
     GoalResult out{};
     std::vector<char> high(n, 0);
     int closest = -1;
@@ -274,6 +274,7 @@ inline GoalResult goal_planning_priority(int a, int n, const F3* pos, const F3* 
     double min_dist_to_obs = 1e9;
     for (int j = 0; j < n; j++) {
         if (j == a) continue;
+        if (in_slack_set && in_slack_set[j]) { high[j] = 1; out.n_high++; continue; }       // traj_planner.cpp:548-551
         const double obs_dist_to_goal = normf(pos[j] - desired[j]);
         const double dist_to_obs = normf(pos[j] - pos[a]);
         if (obs_dist_to_goal < gp.goal_threshold) continue;

@@ -220,6 +220,7 @@ struct LscRows {        // one entry per (obstacle, segment): a . c_{m,i} >= rhs
     int m;
     double a[3];        // widened float normal (traj_optimizer.cpp:446-452)
     double rhs[6];      // d_i + a . o_{m,i}
+    int slack = 0;      // 1: the obstacle is in obs_slack_indices -> rows read a . c - eps_{oi,m} >= rhs (traj_optimizer.cpp:455-457)
 };
 
 struct QpProblem {
@@ -229,6 +230,7 @@ struct QpProblem {
     double lb[QNV], ub[QNV];   // -inf/+inf where free (m == 0, i < 3)
     double vmax[3], amax[3];
     const LscRows* rows; int n_rows;
+    double slack_w = 1.0;   // opt/slack_collision_weight (src/param.cpp:75): cost w ((M - m) / M) eps^2 (traj_optimizer.cpp:383-390)
 };
 
 struct QpResult {
@@ -237,6 +239,8 @@ struct QpResult {
     int status, iters, n_active;
     double kkt_stationarity;     // | v - sum lambda_k n_k |_inf in the whitened space
     double max_violation;        // max over all rows of the (unnormalised) violation
+    std::vector<double> eps;     // qp_solve_slack: slack variable of every (obstacle, segment) row entry, <= 0
+    double slack_cost = 0;       // ... their share of `cost`
 };
 
 inline double objective(const QpTables& T, const QpProblem& p, const double* x) {
@@ -460,6 +464,218 @@ inline void qp_solve(const QpTables& T, const QpProblem& p, QpResult& out, int m
     out.kkt_stationarity = st;
     double mv = 0;
     for (int id = 0; id < n_ids; id++) { RowView r; if (!row_get(T, p, id, r)) continue; mv = std::max(mv, -row_slack(r)); }
+    out.max_violation = mv;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The QP with slack variables (src/traj_optimizer.cpp:317-326,383-390,455-457): once obs_slack_indices is not empty the
+// reference adds one variable eps_{oi,m} in (-inf, 0] per (obstacle, segment) with cost w_s ((M - m) / M) eps^2, and the
+// LSC rows of the obstacles IN the set read  a . (c_{m,i} - o_{m,i}) - d_i - eps_{oi,m} >= 0.  Variables of obstacles
+// outside the set appear in the objective only and stay 0.
+//
+// Same dual active set in the extended whitened space u = (v, e), e_p = sqrt(c_p) eps_p, objective |v|^2 + |e|^2:
+//   slack row   (G^T a, -1/sqrt(c_p) at coordinate p) . u >= -slack0        |N|^2 = |G^T a|^2 + 1/c_p
+//   bound row   (0, -1/sqrt(c_p) at p) . u >= 0                              (eps_p <= 0)
+// A coordinate p is created when a row of its pair first enters the working set (until then e_p = 0 and no active
+// normal touches it: the factorisation is extended by a unit column). Row ids: LSC rows as in qp_solve; the bound of
+// row entry r is 450 + 6 n_rows + r. Without slack rows the iteration is qp_solve's, operation for operation.
+// ---------------------------------------------------------------------------------------------
+inline void qp_solve_slack(const QpTables& T, const QpProblem& p, QpResult& out, int max_iter = 2000) {
+    const int ts = p.ts;
+    int n = QRED;                          // current dimension
+    int cap = QRED + 32;                   // stride of J, R, Nact
+    double x[QNV];
+    for (int k = 0; k < 3; k++)
+        for (int i = 0; i < QAX; i++)
+            x[k * QAX + i] = T.Xs[ts - 1][i][0] * p.s[0][k] + T.Xs[ts - 1][i][1] * p.s[1][k] +
+                             T.Xs[ts - 1][i][2] * p.s[2][k] + T.xg[ts - 1][i] * p.goal[k];
+    std::vector<double> J((size_t)cap * cap, 0.0), R((size_t)cap * cap, 0.0), Nact((size_t)cap * cap, 0.0), v(cap, 0.0);
+    for (int i = 0; i < n; i++) J[(size_t)i * cap + i] = 1.0;
+    int q = 0;
+    std::vector<int> act(cap); std::vector<double> lam(cap);
+    const int n_ids = 450 + 6 * p.n_rows + p.n_rows;
+    const int id_bound0 = 450 + 6 * p.n_rows;
+    std::vector<char> is_active(n_ids, 0);
+    std::vector<int> coord(p.n_rows, -1);          // row entry -> slack coordinate (index into u, >= QRED)
+    std::vector<double> isc(p.n_rows, 0.0);        // 1 / sqrt(c_p)
+    for (int r = 0; r < p.n_rows; r++)
+        if (p.rows[r].slack) isc[r] = 1.0 / std::sqrt(p.slack_w * ((double)(QM - p.rows[r].m) / QM));
+    const double tol = 1e-10;
+    int iters = 0;
+    out.status = QP_OK;
+
+    auto grow = [&]() {
+        const int ncap = cap * 2;
+        auto re = [&](std::vector<double>& A) {
+            std::vector<double> B((size_t)ncap * ncap, 0.0);
+            for (int r = 0; r < cap; r++) for (int c = 0; c < cap; c++) B[(size_t)r * ncap + c] = A[(size_t)r * cap + c];
+            A.swap(B);
+        };
+        re(J); re(R); re(Nact);
+        v.resize(ncap, 0.0); act.resize(ncap); lam.resize(ncap);
+        cap = ncap;
+    };
+    auto eps_of = [&](int r) { return coord[r] >= 0 ? v[coord[r]] * isc[r] : 0.0; };
+    // slack and extended norm of a row id; false when the row does not exist
+    struct Priced { double slack, norm; };
+    auto eval = [&](int id, Priced& pr) -> bool {
+        if (id >= id_bound0) {
+            const int r = id - id_bound0;
+            if (coord[r] < 0) return false;
+            pr.slack = -eps_of(r); pr.norm = isc[r];
+            return true;
+        }
+        RowView rv;
+        if (!row_get(T, p, id, rv)) return false;
+        double s = -rv.b;
+        for (int t = 0; t < rv.nnz; t++) s += rv.a[t] * x[rv.idx[t]];
+        double nn;
+        if (rv.nnz == 1) nn = T.gnorm[ts - 1][rv.idx[0] % QAX];
+        else if (id >= 450) nn = std::sqrt(rv.a[0] * rv.a[0] + rv.a[1] * rv.a[1] + rv.a[2] * rv.a[2]) * T.gnorm[ts - 1][rv.idx[0] % QAX];
+        else {
+            double nv[QRED] = {};
+            for (int t = 0; t < rv.nnz; t++) {
+                int k = rv.idx[t] / QAX, i = rv.idx[t] % QAX;
+                for (int c = 0; c < QFREE; c++) nv[k * QFREE + c] += rv.a[t] * T.G[ts - 1][i][c];
+            }
+            double s2 = 0; for (int c = 0; c < QRED; c++) s2 += nv[c] * nv[c];
+            nn = std::sqrt(s2);
+        }
+        if (id >= 450) {
+            const int r = (id - 450) / 6;
+            if (p.rows[r].slack) { s -= eps_of(r); nn = std::sqrt(nn * nn + isc[r] * isc[r]); }
+        }
+        pr.slack = s; pr.norm = nn;
+        return true;
+    };
+    // unnormalised extended normal of the entering row (creates the slack coordinate when needed); returns its length
+    std::vector<double> nv, d, z, rr;
+    auto ext_normal = [&](int id) -> double {
+        int r_slack = -1;
+        if (id >= id_bound0) r_slack = id - id_bound0;
+        else if (id >= 450 && p.rows[(id - 450) / 6].slack) r_slack = (id - 450) / 6;
+        if (r_slack >= 0 && coord[r_slack] < 0) {
+            if (n == cap) grow();
+            coord[r_slack] = n;
+            J[(size_t)n * cap + n] = 1.0;
+            n++;
+        }
+        nv.assign(cap, 0.0);
+        if (id < id_bound0) {
+            RowView rv; row_get(T, p, id, rv);
+            for (int t = 0; t < rv.nnz; t++) {
+                int k = rv.idx[t] / QAX, i = rv.idx[t] % QAX;
+                for (int c = 0; c < QFREE; c++) nv[k * QFREE + c] += rv.a[t] * T.G[ts - 1][i][c];
+            }
+        }
+        if (r_slack >= 0) nv[coord[r_slack]] = -isc[r_slack];
+        double s = 0; for (int c = 0; c < n; c++) s += nv[c] * nv[c];
+        return std::sqrt(s);
+    };
+    auto drop = [&](int l) {
+        is_active[act[l]] = 0;
+        for (int j = l; j < q - 1; j++) {
+            act[j] = act[j + 1]; lam[j] = lam[j + 1];
+            for (int r = 0; r < n; r++) { R[(size_t)r * cap + j] = R[(size_t)r * cap + j + 1]; Nact[(size_t)r * cap + j] = Nact[(size_t)r * cap + j + 1]; }
+        }
+        for (int r = 0; r < n; r++) R[(size_t)r * cap + q - 1] = 0.0;
+        q--;
+        for (int j = l; j < q; j++) {
+            double a = R[(size_t)j * cap + j], b = R[(size_t)(j + 1) * cap + j];
+            if (b == 0.0) continue;
+            double h = std::hypot(a, b), c = a / h, s = b / h;
+            for (int k = j; k < q; k++) {
+                double t1 = R[(size_t)j * cap + k], t2 = R[(size_t)(j + 1) * cap + k];
+                R[(size_t)j * cap + k] = c * t1 + s * t2; R[(size_t)(j + 1) * cap + k] = -s * t1 + c * t2;
+            }
+            for (int r = 0; r < n; r++) {
+                double t1 = J[(size_t)r * cap + j], t2 = J[(size_t)r * cap + j + 1];
+                J[(size_t)r * cap + j] = c * t1 + s * t2; J[(size_t)r * cap + j + 1] = -s * t1 + c * t2;
+            }
+        }
+    };
+
+    while (true) {
+        // pricing: most violated row by distance in the extended whitened space
+        int pbest = -1; double mu_best = -tol;
+        for (int id = 0; id < n_ids; id++) {
+            if (is_active[id]) continue;
+            Priced pr;
+            if (!eval(id, pr)) continue;
+            if (!(pr.slack < -QP_FEAS_TOL)) continue;
+            const double mu = pr.slack / std::max(pr.norm, 1e-300);
+            if (mu < mu_best) { mu_best = mu; pbest = id; }
+        }
+        if (pbest < 0) break;
+        const double nrm = ext_normal(pbest);
+        if (!(nrm > 0)) { out.status = QP_INFEASIBLE; break; }
+        d.assign(cap, 0.0); z.assign(cap, 0.0); rr.assign(cap, 0.0);
+        for (int c = 0; c < n; c++) nv[c] /= nrm;
+        double lam_p = 0;
+        bool fail = false;
+        while (true) {
+            if (++iters > max_iter) { out.status = QP_MAXITER; fail = true; break; }
+            for (int c = 0; c < n; c++) { double s = 0; for (int r = 0; r < n; r++) s += J[(size_t)r * cap + c] * nv[r]; d[c] = s; }
+            double zz = 0;
+            for (int c = q; c < n; c++) zz += d[c] * d[c];
+            for (int r = 0; r < n; r++) { double s = 0; for (int c = q; c < n; c++) s += J[(size_t)r * cap + c] * d[c]; z[r] = s; }
+            for (int k = q - 1; k >= 0; k--) {
+                double s = d[k];
+                for (int c = k + 1; c < q; c++) s -= R[(size_t)k * cap + c] * rr[c];
+                rr[k] = s / R[(size_t)k * cap + k];
+            }
+            double t1 = INFINITY; int l = -1;
+            for (int k = 0; k < q; k++)
+                if (rr[k] > 1e-13) { double t = lam[k] / rr[k]; if (t < t1) { t1 = t; l = k; } }
+            const bool primal = zz > 1e-13;
+            Priced pr{0.0, 1.0}; eval(pbest, pr);
+            const double slack = pr.slack / nrm;
+            double t2 = primal ? -slack / zz : INFINITY;
+            if (t2 < 0) t2 = 0;
+            double t = std::min(t1, t2);
+            if (!(t < INFINITY)) { out.status = QP_INFEASIBLE; fail = true; break; }
+            for (int k = 0; k < q; k++) lam[k] -= t * rr[k];
+            lam_p += t;
+            if (!primal) { drop(l); continue; }
+            for (int c = 0; c < n; c++) v[c] += t * z[c];
+            for (int k = 0; k < 3; k++)
+                for (int i = 0; i < QAX; i++) {
+                    double s = 0;
+                    for (int c = 0; c < QFREE; c++) s += T.G[ts - 1][i][c] * z[k * QFREE + c];
+                    x[k * QAX + i] += t * s;
+                }
+            if (t2 <= t1) {
+                for (int j = n - 1; j > q; j--) {
+                    double a = d[j - 1], b = d[j];
+                    if (b == 0.0) continue;
+                    double h = std::hypot(a, b), c = a / h, s = b / h;
+                    d[j - 1] = h; d[j] = 0;
+                    for (int r = 0; r < n; r++) {
+                        double u1 = J[(size_t)r * cap + j - 1], u2 = J[(size_t)r * cap + j];
+                        J[(size_t)r * cap + j - 1] = c * u1 + s * u2; J[(size_t)r * cap + j] = -s * u1 + c * u2;
+                    }
+                }
+                for (int k = 0; k <= q; k++) R[(size_t)k * cap + q] = d[k];
+                for (int r = 0; r < n; r++) Nact[(size_t)r * cap + q] = nv[r];
+                act[q] = pbest; lam[q] = lam_p; is_active[pbest] = 1; q++;
+                break;
+            }
+            drop(l);
+        }
+        if (fail) break;
+    }
+    std::memcpy(out.x, x, sizeof x);
+    out.eps.assign(p.n_rows, 0.0);
+    out.slack_cost = 0;
+    for (int r = 0; r < p.n_rows; r++)
+        if (coord[r] >= 0) { out.eps[r] = eps_of(r); out.slack_cost += v[coord[r]] * v[coord[r]]; }
+    out.cost = objective(T, p, x) + out.slack_cost;
+    out.iters = iters; out.n_active = q;
+    double st = 0;
+    for (int r = 0; r < n; r++) { double s = v[r]; for (int k = 0; k < q; k++) s -= lam[k] * Nact[(size_t)r * cap + k]; st = std::max(st, std::fabs(s)); }
+    out.kkt_stationarity = st;
+    double mv = 0;
+    for (int id = 0; id < n_ids; id++) { Priced pr{0.0, 1.0}; if (!eval(id, pr)) continue; mv = std::max(mv, -pr.slack); }
     out.max_violation = mv;
 }
 

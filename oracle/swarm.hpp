@@ -5,7 +5,9 @@
 //   src/traj_planner.cpp:99-145,344-425    plan / planImpl / planLSC
 //   src/traj_planner.cpp:829-864,699-712   obstaclePredictionWithPrevSol / ...WithCurrVel
 //   src/traj_planner.cpp:997-1016,1030-1037 initialTrajPlanningPrevSol / ...CurrVel
-//   src/traj_planner.cpp:866-878,1047-1061 prediction / initial-trajectory checks (detect only)
+//   src/traj_planner.cpp:866-878,1047-1061 prediction / initial-trajectory checks: collapse to the current position,
+//                                          sticky obs_slack_indices, flag_initialize_sfc re-armed
+//   src/traj_optimizer.cpp:317-326,383-390,455-457  slack variables of the obstacles in obs_slack_indices (qp.hpp)
 //   src/traj_planner.cpp:1225-1252         generateCollisionConstraints
 //   src/traj_planner.cpp:1442-1491         generateFeasibleSFC (window shift + one new box)
 //   src/traj_planner.cpp:1548-1585         trajOptimization (failure keeps the optimizer's last
@@ -26,6 +28,7 @@ namespace orc {
 
 struct SwarmParams {
     double dt = 0.2, w = 0.01, wT = 1.0, res = 0.1, reset_threshold = 0.15;
+    double slack_w = 1.0;                        // opt/slack_collision_weight (src/param.cpp:75)
     int use_octomap = 0;
     float world_min[3] = {-5, -5, 0}, world_max[3] = {5, 5, 2.5f};
 };
@@ -55,6 +58,11 @@ struct Swarm {
     long long astar_expansions = 0;
     std::vector<F3> box_min, box_max;            // [N][5] persistent SFC
     std::vector<int> init_sfc;                   // flag_initialize_sfc
+    // Disturbance handling. Every planner runs the same two checks on the same data (the shifted previous trajectory of
+    // agent j against j's observed position), so obs_slack_indices of planner i is: every obstacle once i itself was
+    // reset (:1049-1051), else the agents j that were ever reset (:869-870). Sticky: the reference never erases it.
+    std::vector<char> reset_ever;
+    std::vector<double> qp_slack_cost; std::vector<int> qp_slack_rows;   // step outputs: slack share of the cost, rows with eps < 0
     // step outputs
     std::vector<double> qp_cost; std::vector<int> qp_status, qp_iters, qp_active, flags;
     std::vector<double> qp_maxviol, qp_kkt;
@@ -71,6 +79,7 @@ struct Swarm {
         pos.assign(N, f3(0, 0, 0)); vel = pos; acc = pos; goal = pos; desired = pos; goal_kind.assign(N, 0);
         box_min.assign((size_t)N * 5, f3(0, 0, 0)); box_max = box_min;
         init_sfc.assign(N, 1);                                      // traj_planner.cpp:49
+        reset_ever.assign(N, 0); qp_slack_cost.assign(N, 0); qp_slack_rows.assign(N, 0);
         qp_cost.assign(N, 0); qp_status.assign(N, 0); qp_iters.assign(N, 0); qp_active.assign(N, 0);
         qp_maxviol.assign(N, 0); qp_kkt.assign(N, 0); flags.assign(N, 0);
         pred.assign((size_t)N * 30, f3(0, 0, 0));
@@ -91,7 +100,12 @@ struct Swarm {
                 for (int m = 0; m < 4; m++) for (int i = 0; i < 6; i++) o[m * 6 + i] = t[(m + 1) * 6 + i];
                 for (int i = 0; i < 6; i++) o[24 + i] = t[29];                               // :851-855
             }
-            if (normf(o[0] - pos[a]) > prm.reset_threshold) flags[a] |= FLAG_SLACK_NEEDED;    // :869, :1048
+            if (normf(o[0] - pos[a]) > prm.reset_threshold) {                                // :869, :1048
+                flags[a] |= FLAG_SLACK_NEEDED;
+                reset_ever[a] = 1;                                                           // :870, :1049-1051
+                for (int e = 0; e < 30; e++) o[e] = pos[a];                                  // :871-875, :1053-1057
+                init_sfc[a] = 1;                                                             // :1059
+            }
         }
     }
 
@@ -106,6 +120,7 @@ struct Swarm {
             lsc_pair(own, obs, 5, ac[a].radius, ac[a].downwash, ac[j].radius, ac[j].downwash, lp);
             for (int m = 0; m < 5; m++) {
                 LscRows r; r.m = m;
+                r.slack = (reset_ever[a] || reset_ever[j]) ? 1 : 0;                          // obs_slack_indices of planner a
                 r.a[0] = (double)lp.normal[m].x; r.a[1] = (double)lp.normal[m].y; r.a[2] = (double)lp.normal[m].z;
                 for (int i = 0; i < 6; i++) {
                     const F3 o = obs[m * 6 + i];
@@ -158,7 +173,13 @@ struct Swarm {
         for (int k = 0; k < 3; k++) { qp.vmax[k] = ac[a].vmax[k]; qp.amax[k] = ac[a].amax[k]; }
         qp.rows = rows_buf.data(); qp.n_rows = (int)rows_buf.size();
         QpResult res;
-        qp_solve(T, qp, res);
+        bool any_slack = false;
+        for (const LscRows& r : rows_buf) any_slack |= r.slack != 0;
+        qp.slack_w = prm.slack_w;
+        if (any_slack) qp_solve_slack(T, qp, res); else qp_solve(T, qp, res);
+        qp_slack_cost[a] = any_slack ? res.slack_cost : 0.0;
+        qp_slack_rows[a] = 0;
+        for (double e : res.eps) qp_slack_rows[a] += e < 0.0;
         qp_status[a] = res.status; qp_iters[a] = res.iters; qp_active[a] = res.n_active;
         qp_maxviol[a] = res.max_violation; qp_kkt[a] = res.kkt_stationarity;
         if (res.status == QP_OK) {
@@ -182,8 +203,12 @@ struct Swarm {
         const F3 wmax = f3(prm.world_max[0], prm.world_max[1], prm.world_max[2]);
         const DistMap* map = prm.use_octomap ? dm : nullptr;
         auto work = [&](int a) {
+            std::vector<char> in_set;
+            bool any = false;
+            for (int j = 0; j < N; j++) any |= reset_ever[j] != 0;
+            if (any) { in_set.resize(N); for (int j = 0; j < N; j++) in_set[j] = reset_ever[a] || reset_ever[j]; }
             GoalResult r = goal_planning_priority(a, N, pos.data(), desired.data(), traj.data(), pred[(size_t)a * 30 + 29],
-                                                  ac.data(), map, gp, wmin, wmax);
+                                                  ac.data(), map, gp, wmin, wmax, any ? in_set.data() : nullptr);
             goal[a] = r.goal; goal_kind[a] = r.mode;
             __atomic_fetch_add(&astar_expansions, r.expansions, __ATOMIC_RELAXED);
         };

@@ -53,6 +53,12 @@ def lib():
         L.orc_qp_dense.argtypes = qp_args + [C.c_void_p, f64p, f64p, f64p, f64p, f64p, f64p, f64p, C.c_int]
         L.orc_qp_dense.restype = C.c_int
         L.orc_set_tier_threshold.argtypes = [C.c_double]
+        L.orc_qp_solve_slack.argtypes = qp_args + [i32p, C.c_double, f64p, f64p, f64p]; L.orc_qp_solve_slack.restype = C.c_int
+        u8 = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+        L.orc_swarm_set_slack_weight.argtypes = [C.c_void_p, C.c_double]
+        L.orc_swarm_get_reset_ever.argtypes = [C.c_void_p, u8]
+        L.orc_swarm_set_reset_ever.argtypes = [C.c_void_p, u8]
+        L.orc_swarm_get_slack.argtypes = [C.c_void_p, f64p, i32p]
         L.orc_swarm_create.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int,
                                        f32p, f32p, f64p, f64p, f64p, f64p, f64p]
         L.orc_swarm_create.restype = C.c_void_p
@@ -198,6 +204,14 @@ class Tables:
         st = lib().orc_qp_solve(*self._args(state, goal, ts, lb, ub, vmax, amax, rows), x, info)
         return dict(x=x, cost=info[0], status=st, iters=int(info[1]), n_active=int(info[2]), kkt=info[3], maxviol=info[4])
 
+    def solve_slack(self, state, goal, ts, lb, ub, vmax, amax, rows, row_slack, slack_w=1.0):
+        """The QP with slack variables: row_slack[r] = 1 for the (m, a3, rhs6) entries of obstacles in obs_slack_indices."""
+        x = np.zeros(90); info = np.zeros(6); eps = np.zeros(max(len(rows), 1))
+        st = lib().orc_qp_solve_slack(*self._args(state, goal, ts, lb, ub, vmax, amax, rows),
+                                      np.ascontiguousarray(row_slack, np.int32), float(slack_w), x, eps, info)
+        return dict(x=x, eps=eps[:len(rows)], cost=info[0], status=st, iters=int(info[1]), n_active=int(info[2]), kkt=info[3],
+                    maxviol=info[4], slack_cost=info[5])
+
     def dense(self, state, goal, ts, lb, ub, vmax, amax, rows, boxes=None):
         max_in = 6 * len(rows) + 252 + 162 + 8
         P = np.zeros((90, 90)); q = np.zeros(90); c0 = np.zeros(1); Aeq = np.zeros((51, 90)); beq = np.zeros(51)
@@ -237,6 +251,17 @@ class Swarm:
             lib().orc_swarm_set_map(self.h, omap.h)
 
     def set_capture(self, on=True): lib().orc_swarm_set_capture(self.h, int(on))
+
+    def set_slack_weight(self, w): lib().orc_swarm_set_slack_weight(self.h, float(w))
+
+    def reset_ever(self):
+        out = np.zeros(self.n, np.uint8); lib().orc_swarm_get_reset_ever(self.h, out); return out
+
+    def set_reset_ever(self, flags): lib().orc_swarm_set_reset_ever(self.h, np.ascontiguousarray(flags, np.uint8))
+
+    def slack(self):
+        """(slack share of the QP cost, number of rows with eps < 0) per agent of the last step."""
+        c = np.zeros(self.n); r = np.zeros(self.n, np.int32); lib().orc_swarm_get_slack(self.h, c, r); return c, r
 
     def set_state(self, pos, vel=None, acc=None):
         pos = np.ascontiguousarray(pos, np.float32).reshape(self.n, 3)

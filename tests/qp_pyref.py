@@ -166,7 +166,7 @@ def solve_ldp(qp, tol=1e-9):
     P, q, c0 = qp["P"], qp["q"], qp["c0"]
     Aeq, beq = qp["Aeq"], qp["beq"]
     G = [qp["Ain"]]; h = [qp["bin"]]
-    I = np.eye(NV)
+    I = np.eye(P.shape[0])
     fin = np.isfinite(qp["lb"]); G.append(I[fin]); h.append(qp["lb"][fin])
     fin = np.isfinite(qp["ub"]); G.append(-I[fin]); h.append(-qp["ub"][fin])
     G = np.vstack(G); h = np.concatenate(h)
@@ -199,6 +199,34 @@ def solve_ldp(qp, tol=1e-9):
     x = xp + Z @ y
     obj = float(x @ P @ x + q @ x + c0)
     return x, obj, "ok"
+
+
+def with_slack(qp, lsc_rows, row_slack, slack_w, n_sfc_rows=0):
+    """Extend a dense QP (assemble / oracle dense) by the reference's slack variables (src/traj_optimizer.cpp:317-326,
+    383-390,455-457): one eps in (-inf, 0] per (obstacle, segment) entry r of `lsc_rows` (tuples whose first element is
+    m) with row_slack[r] != 0, cost slack_w * (M - m) / M * eps^2, subtracted from the left-hand side of the entry's LSC
+    rows (6 per entry, 3 for m == 0; they follow the n_sfc_rows SFC rows in Ain). Entries outside the set get no variable:
+    theirs only appears in the objective and stays 0. Returns the extended problem; the eps are the trailing variables."""
+    idx = [r for r in range(len(lsc_rows)) if row_slack[r]]
+    ns = len(idx)
+    n0 = qp["P"].shape[0]
+    n = n0 + ns
+    P = np.zeros((n, n)); P[:n0, :n0] = qp["P"]
+    for c, r in enumerate(idx):
+        P[n0 + c, n0 + c] = slack_w * (M - int(lsc_rows[r][0])) / M
+    q = np.concatenate([qp["q"], np.zeros(ns)])
+    Aeq = np.hstack([qp["Aeq"], np.zeros((qp["Aeq"].shape[0], ns))])
+    Ain = np.hstack([qp["Ain"], np.zeros((qp["Ain"].shape[0], ns))])
+    at = n_sfc_rows
+    col = {r: c for c, r in enumerate(idx)}
+    for r in range(len(lsc_rows)):
+        cnt = 3 if int(lsc_rows[r][0]) == 0 else 6
+        if r in col:
+            Ain[at:at + cnt, n0 + col[r]] = -1.0
+        at += cnt
+    lb = np.concatenate([qp["lb"], np.full(ns, -np.inf)])
+    ub = np.concatenate([qp["ub"], np.zeros(ns)])
+    return dict(P=P, q=q, c0=qp["c0"], Aeq=Aeq, beq=qp["beq"], Ain=Ain, bin=qp["bin"], lb=lb, ub=ub), idx
 
 
 def kkt_violation(qp, x):
