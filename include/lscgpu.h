@@ -54,9 +54,16 @@ enum { LSCGPU_QP_OK = 0, LSCGPU_QP_INFEASIBLE = 1, LSCGPU_QP_MAXITER = 2 };
 
 /* per-agent flag bits of one step */
 enum {
-    LSCGPU_FLAG_SLACK_NEEDED = 1,      /* |initial_traj start - state| > reset_threshold: the reference would enter the
-                                          slack branch (src/traj_planner.cpp:866-878,1047-1061); reported, not handled */
-    LSCGPU_FLAG_SFC_SEED_BLOCKED = 2   /* expandBoxFromPoint would throw (include/corridor_constructor.hpp:35-38) */
+    LSCGPU_FLAG_SLACK_NEEDED = 1,      /* |initial_traj start - state| > reset_threshold in this step: the agent's prediction
+                                          and initial trajectory were collapsed to its position, its corridor re-armed and
+                                          the agent entered everybody's obs_slack_indices for good
+                                          (src/traj_planner.cpp:866-878,1047-1061) */
+    LSCGPU_FLAG_SFC_SEED_BLOCKED = 2,  /* expandBoxFromPoint would throw (include/corridor_constructor.hpp:35-38) */
+    LSCGPU_FLAG_SLACK_MODE = 4,        /* the QP carried slack variables (some agent of the swarm was reset before or in this
+                                          step; src/traj_optimizer.cpp:317-326,383-390,455-457) */
+    LSCGPU_FLAG_SLACK_USED = 8,        /* ... and at least one of them is < 0 at the solution */
+    LSCGPU_FLAG_SLACK_OVERFLOW = 16    /* the QP needed more slack variables than the kernel holds per agent (25): reported
+                                          as LSCGPU_QP_MAXITER, the previous trajectory is kept */
 };
 
 /* The subset of Param (include/param.hpp, defaults src/param.cpp:4-107) that the hot path reads. */
@@ -185,6 +192,21 @@ int lscgpu_set_prev_traj(lscgpu_engine* e, const float* traj /* [n_agents][90] *
 int lscgpu_set_sfc(lscgpu_engine* e, const float* boxes, const int32_t* flag_initialize_sfc);
 int lscgpu_get_sfc(lscgpu_engine* e, float* boxes, int32_t* flag_initialize_sfc);
 int lscgpu_get_planner_seq(lscgpu_engine* e);
+
+/* ---- disturbance handling ------------------------------------------------------------------------
+ * Replaces obstaclePredictionCheck / initialTrajPlanningCheck (src/traj_planner.cpp:866-878,1047-1061) and the slack
+ * variables of TrajOptimizer::populatebyrow (src/traj_optimizer.cpp:317-326,383-390,455-457). The caller reports an
+ * externally observed pose the way MultiSyncSimulator::update does (src/multi_sync_simulator.cpp:229-246): the agent's
+ * lscgpu_agent_in carries the observed position with zero velocity and acceleration. A step whose position is farther
+ * than reset_threshold from the start of the agent's shifted previous trajectory collapses its prediction and initial
+ * trajectory to that position, re-arms its corridor and puts the agent into every planner's obs_slack_indices (and every
+ * obstacle into its own) for the rest of the mission, as the reference does. From then on every QP of the swarm carries the
+ * slack variables eps_{oi,m} <= 0 with cost slack_collision_weight ((M - m) / M) eps^2 (default 1, src/param.cpp:75;
+ * launch/simulation.launch sets 100000). qp_cost includes their cost. lscgpu_reset clears the sets.
+ * lscgpu_get/set_reset_state: the sticky per-agent "was ever reset" bytes (checkpoint / teacher-forced runs). */
+int lscgpu_set_slack_collision_weight(lscgpu_engine* e, double w);
+int lscgpu_get_reset_state(lscgpu_engine* e, uint8_t* reset_ever /* [n_agents] */);
+int lscgpu_set_reset_state(lscgpu_engine* e, const uint8_t* reset_ever);
 
 /* Constraints of the last step, as CollisionConstraints::getLSC would return them
  * (src/collision_constraints.cpp:362-364): for local agent `agent` and every other agent in id order,

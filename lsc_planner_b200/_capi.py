@@ -64,6 +64,7 @@ def symbols():
             "lscgpu_nccl_unique_id", "lscgpu_nccl_init", "lscgpu_replan_batch", "lscgpu_safety_audit", "lscgpu_set_goals",
             "lscgpu_set_states", "lscgpu_replan_resident", "lscgpu_synchronize", "lscgpu_fetch", "lscgpu_reset", "lscgpu_set_prev_traj",
             "lscgpu_set_sfc", "lscgpu_get_sfc", "lscgpu_get_planner_seq", "lscgpu_get_lsc", "lscgpu_get_lsc_ex",
+            "lscgpu_set_slack_collision_weight", "lscgpu_get_reset_state", "lscgpu_set_reset_state",
             "lscgpu_set_capture_rows",
             "lscgpu_get_initial_traj", "lscgpu_qp_solve_batch", "lscgpu_gjk_batch", "lscgpu_sfc_expand_batch",
             "lscgpu_get_step_stats", "lscgpu_set_profiling", "lscgpu_sm_clock_khz", "lscgpu_stream",
@@ -102,6 +103,9 @@ def lib():
     L.lscgpu_set_sfc.argtypes = [ptr, ptr, ptr]
     L.lscgpu_get_sfc.argtypes = [ptr, ptr, ptr]
     L.lscgpu_get_planner_seq.argtypes = [ptr]
+    L.lscgpu_set_slack_collision_weight.argtypes = [ptr, C.c_double]
+    L.lscgpu_get_reset_state.argtypes = [ptr, ptr]
+    L.lscgpu_set_reset_state.argtypes = [ptr, ptr]
     L.lscgpu_get_lsc.argtypes = [ptr, C.c_int, ptr, ptr]
     L.lscgpu_get_lsc_ex.argtypes = [ptr, C.c_int, ptr, ptr, ptr]
     L.lscgpu_set_capture_rows.argtypes = [ptr, C.c_int]

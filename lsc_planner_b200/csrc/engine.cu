@@ -118,6 +118,12 @@ struct lscgpu_engine {
     int* d_sfc_ready = nullptr; float* d_sfc_box = nullptr; int* d_sfc_ok = nullptr;   // [N] k_sfc_step -> k_agent_plan
     cudaEvent_t ev_sfc = nullptr;
     int planner_seq = 0;
+    // disturbance branch: sticky "was ever reset" per agent + "anybody was" (k_predict), slack weight, slack kernel on/off
+    unsigned char* d_reset_ever = nullptr;
+    int* d_any_reset = nullptr;
+    double slack_w = 1.0;            // opt/slack_collision_weight (src/param.cpp:75)
+    bool slack_kernel = true;
+    int row_cap_slack = 384;
     bool profiling = false;
     int max_iter = 2000;
 
@@ -222,6 +228,7 @@ extern "C" void lscgpu_destroy(lscgpu_engine* e) {
     cudaFree(e->d_order); cudaFree(e->d_block_of);
     cudaFree(e->d_kept_step); if (e->h_kept_last) cudaFreeHost(e->h_kept_last);
     cudaFree(e->d_epoch); cudaFree(e->d_sfc_ready); cudaFree(e->d_sfc_box); cudaFree(e->d_sfc_ok);
+    cudaFree(e->d_reset_ever); cudaFree(e->d_any_reset);
     if (e->ev_sfc) cudaEventDestroy(e->ev_sfc);
     cudaFree(e->d_rdw); cudaFree(e->d_audit_pos); cudaFree(e->d_audit_ratio); cudaFree(e->d_audit_closest); cudaFree(e->d_dbg);
     cudaFree(e->d_tables); cudaFree(e->d_consts); cudaFree(e->d_in); cudaFree(e->d_gather); cudaFree(e->d_res); cudaFree(e->d_traj);
@@ -249,6 +256,8 @@ static int reset_state(lscgpu_engine* e) {
     CU(cudaMemsetAsync(e->d_res, 0, sizeof(lscgpu_agent_out) * N, e->stream));
     CU(cudaMemsetAsync(e->d_gather, 0xff, sizeof(lscgpu_agent_out) * (size_t)e->n_slots, e->stream));   // agent_id = -1: empty slot
     CU(cudaMemsetAsync(e->d_block_of, 0xff, sizeof(int) * N, e->stream));
+    CU(cudaMemsetAsync(e->d_reset_ever, 0, N, e->stream));                              // obs_slack_indices start empty
+    CU(cudaMemsetAsync(e->d_any_reset, 0, sizeof(int), e->stream));
     std::vector<int> ones(N, 1);                                                         // flag_initialize_sfc, :49
     CU(cudaMemcpyAsync(e->d_init_sfc, ones.data(), sizeof(int) * N, cudaMemcpyHostToDevice, e->stream));
     CU(cudaStreamSynchronize(e->stream));
@@ -310,6 +319,7 @@ extern "C" int lscgpu_create(const lscgpu_params* p, int n_agents, const lscgpu_
     if (const char* v = getenv("LSCGPU_WIDE_KEPT")) e->wide_kept = atoi(v);
     if (const char* v = getenv("LSCGPU_ROW_CAP")) e->row_cap_forced = std::min(std::max(atoi(v), 0), 2560) / 32 * 32;
     if (const char* v = getenv("LSCGPU_SFC_WAIT_CYCLES")) e->sfc_wait_cycles = atoll(v);
+    if (const char* v = getenv("LSCGPU_SLACK_KERNEL")) e->slack_kernel = atoi(v) != 0;     // 0: measure the step without its launch
     e->qp_debug = getenv("LSCGPU_QP_DEBUG") != nullptr;
     CUB(cudaEventCreate(&e->ev_begin));
     CUB(cudaEventCreate(&e->ev_end));
@@ -359,6 +369,8 @@ extern "C" int lscgpu_create(const lscgpu_params* p, int n_agents, const lscgpu_
     CUB(cudaHostGetDevicePointer(&e->d_kept_last_map, e->h_kept_last, 0));
     CUB(cudaMalloc(&e->d_epoch, sizeof(int)));
     CUB(cudaMemset(e->d_epoch, 0, sizeof(int)));
+    CUB(cudaMalloc(&e->d_reset_ever, N));
+    CUB(cudaMalloc(&e->d_any_reset, sizeof(int)));
     CUB(cudaMalloc(&e->d_sfc_ready, sizeof(int) * N));
     CUB(cudaMemset(e->d_sfc_ready, 0xff, sizeof(int) * N));
     CUB(cudaMalloc(&e->d_sfc_box, sizeof(float) * 6 * N));
@@ -563,6 +575,7 @@ static int enqueue_step_kernels(lscgpu_engine* e, int planner_seq, int threads, 
         sl.dm = e->dm; sl.res = e->prm.world_resolution;
         for (int k = 0; k < 3; k++) { sl.wmin[k] = e->prm.world_min[k]; sl.wmax[k] = e->prm.world_max[k]; }
         sl.in = e->d_in; sl.prev_traj = e->d_traj; sl.consts = e->d_consts; sl.init_sfc = e->d_init_sfc;
+        sl.planner_seq = planner_seq; sl.reset_threshold = e->prm.reset_threshold;
         sl.epoch = e->d_epoch; sl.sfc_box_g = e->d_sfc_box; sl.sfc_ok_g = e->d_sfc_ok; sl.sfc_ready = e->d_sfc_ready;
         if (ev) CU(cudaEventRecord(ev[5], so));
         launch_sfc_step(sl, so); launches++;
@@ -575,9 +588,11 @@ static int enqueue_step_kernels(lscgpu_engine* e, int planner_seq, int threads, 
     pl.in = e->d_in; pl.prev_traj = e->d_traj; pl.consts = e->d_consts;
     pl.pred = e->d_pred; pl.predT = e->d_predT; pl.predZs = e->d_predZs; pl.state9 = e->d_state9; pl.goal3 = e->d_goal3;
     pl.ts = e->d_ts; pl.flags = e->d_flags; pl.sphere = e->d_sphere; pl.tsphere = e->d_tsphere; pl.reach = e->d_reach;
+    pl.reset_ever = e->d_reset_ever; pl.any_reset = e->d_any_reset; pl.init_sfc = e->d_init_sfc;
     launch_predict(pl, s); launches++;
     if (e->prm.goal_mode == 1) {
         GoalLaunch gl{};
+        gl.reset_ever = e->d_reset_ever;
         gl.n_agents = e->N; gl.dt = e->prm.dt; gl.goal_threshold = e->prm.goal_threshold; gl.goal_radius = e->prm.goal_radius;
         gl.priority_dist_threshold = e->prm.priority_dist_threshold;
         gl.in = e->d_in; gl.prev_traj = e->d_traj; gl.pred = e->d_pred; gl.consts = e->d_consts;
@@ -612,8 +627,10 @@ static int enqueue_step_kernels(lscgpu_engine* e, int planner_seq, int threads, 
     L.out = e->d_gather; L.out_base = dealt ? e->rank * e->block : 0;
     L.prev_traj = e->d_traj; L.last_cost = e->d_last_cost; L.goal_kind = e->d_goal_kind;
     L.counters = e->d_counters;
+    L.any_reset = e->slack_kernel ? e->d_any_reset : nullptr; L.reset_ever = e->d_reset_ever;
+    L.slack_w = e->slack_w; L.row_cap_slack = e->row_cap_slack;
     if (e->qp_debug) { if (!e->d_dbg) CU(cudaMalloc(&e->d_dbg, sizeof(long long) * 10 * (size_t)e->N)); L.dbg = e->d_dbg; }
-    if (n_plan > 0) { launch_agent_plan(L, s); launches++; }
+    if (n_plan > 0) { launch_agent_plan(L, s); launches += L.any_reset ? 2 : 1; }
     if (ev) CU(cudaEventRecord(ev[2], s));
 
     if (dealt && e->n_ranks > 1) {
@@ -885,6 +902,33 @@ extern "C" int lscgpu_get_sfc(lscgpu_engine* e, float* boxes, int32_t* init) {
 
 extern "C" int lscgpu_get_planner_seq(lscgpu_engine* e) { return e ? e->planner_seq : -1; }
 
+extern "C" int lscgpu_set_slack_collision_weight(lscgpu_engine* e, double w) {
+    if (!e || !(w > 0.0)) return fail(LSCGPU_ERR_ARG, "slack_collision_weight must be positive");
+    if (e->pending) return fail(LSCGPU_ERR_STATE, "lscgpu_synchronize first");
+    e->slack_w = w;
+    drop_graph(e);                          // the step graph carries the weight as a kernel argument
+    return LSCGPU_OK;
+}
+
+extern "C" int lscgpu_get_reset_state(lscgpu_engine* e, uint8_t* reset_ever) {
+    if (!e || !reset_ever) return fail(LSCGPU_ERR_ARG, "null argument");
+    CU(cudaSetDevice(e->device));
+    CU(cudaMemcpyAsync(reset_ever, e->d_reset_ever, (size_t)e->N, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return LSCGPU_OK;
+}
+
+extern "C" int lscgpu_set_reset_state(lscgpu_engine* e, const uint8_t* reset_ever) {
+    if (!e || !reset_ever) return fail(LSCGPU_ERR_ARG, "null argument");
+    CU(cudaSetDevice(e->device));
+    int any = 0;
+    for (int a = 0; a < e->N; a++) any |= reset_ever[a] != 0;
+    CU(cudaMemcpyAsync(e->d_reset_ever, reset_ever, (size_t)e->N, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->d_any_reset, &any, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return LSCGPU_OK;
+}
+
 extern "C" int lscgpu_set_capture_rows(lscgpu_engine* e, int on) {
     if (!e) return fail(LSCGPU_ERR_ARG, "null engine");
     if (e->pending) return fail(LSCGPU_ERR_STATE, "lscgpu_synchronize first");
@@ -930,7 +974,7 @@ extern "C" int lscgpu_get_lsc_ex(lscgpu_engine* e, int agent, float* normals, do
     }
     CU(cudaMemcpy(pred.data(), e->d_pred, sizeof(float) * pred.size(), cudaMemcpyDeviceToHost));
     for (int sidx = 0; sidx < n_kept; sidx++) {
-        const int p = kept[sidx];
+        const int p = kept[sidx] & 0xffffff;          // upper bits: slack code of the slot (qp_core.cuh)
         const int m = p / (int)n_obs, jj = p % (int)n_obs;
         const int j = jj < agent ? jj : jj + 1;
         const RowRec& r = rows[sidx];

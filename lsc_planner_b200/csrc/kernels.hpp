@@ -25,11 +25,17 @@ struct PredictLaunch {
     float4* sphere;                // [5][n_pad] bounding sphere (centre xyz, radius) of every segment's control points
     float4* tsphere;               // [n_pad] bounding sphere of ALL control points of the trajectory (coarse culling pass)
     float* reach;                  // [N][5] how far ANY feasible control point of segment m can be from initial_traj's
+    // disturbance branch: a state farther than reset_threshold from the start of the shifted previous trajectory collapses
+    // the agent's prediction / initial trajectory to the observed position, marks it for good and re-arms its corridor
+    unsigned char* reset_ever;     // [N] sticky
+    int* any_reset;                // device word
+    int* init_sfc;                 // [N] flag_initialize_sfc
 };
 void launch_predict(const PredictLaunch& L, cudaStream_t s);
 
 // ---- k_goal_plan: goalPlanningWithPriority without an octomap ----------------------------------------------
 struct GoalLaunch {
+    const unsigned char* reset_ever;   // [N] obstacles of obs_slack_indices are high priority but never the retreat target (:548-551)
     int n_agents;
     double dt, goal_threshold, goal_radius, priority_dist_threshold;
     const lscgpu_agent_in* in;     // [N] goal = DESIRED goal
@@ -106,10 +112,16 @@ struct PlanLaunch {
     const int* goal_kind;          // [N] or null
     StepCounters* counters;
     int* kept_step;                // sum of the kept pairs of this launch (k_commit hands it to the host: block-size choice)
+    // disturbance branch (src/traj_planner.cpp:866-878,1047-1061, src/traj_optimizer.cpp:317-326,383-390,455-457)
+    const int* any_reset;          // null: no slack kernel; else device word, != 0 once any agent was ever reset (k_predict)
+    const unsigned char* reset_ever;   // [N] sticky: the agent's state was reset at some step
+    double slack_w;                // opt/slack_collision_weight
+    int row_cap_slack;             // shared-memory row slots of the slack instantiation
     long long* dbg;                // null, or [n_blocks][10] section cycle counts (LSCGPU_QP_DEBUG)
 };
 void launch_agent_plan(const PlanLaunch& L, cudaStream_t s);
 size_t agent_plan_smem_bytes(int row_cap, int threads);
+size_t agent_plan_slack_smem_bytes(int row_cap, int threads);
 cudaError_t configure_agent_plan();     // once per device, before the first launch
 
 // one agent's LSCs recomputed into CollisionConstraints layout (debug / parity)
@@ -173,6 +185,7 @@ struct SfcStepLaunch {
     double res;
     float wmin[3], wmax[3];
     const lscgpu_agent_in* in; const float* prev_traj; const AgentConstDev* consts; const int* init_sfc;
+    int planner_seq; double reset_threshold;       // a reset in this step re-arms the corridor (k_predict runs beside this kernel)
     const int* epoch;
     float* sfc_box_g; int* sfc_ok_g; int* sfc_ready;
 };

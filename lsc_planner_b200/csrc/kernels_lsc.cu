@@ -11,9 +11,12 @@ namespace lscgpu {
 // ------------------------------------------------------------------------------------------------------------
 // k_predict — one block of 96 threads per agent; thread e < 90 owns trajectory element e = (m*6+i)*3 + axis.
 // Replaces obstaclePredictionWithPrevSol / ...WithCurrVel (src/traj_planner.cpp:829-864,699-712),
-// initialTrajPlanningPrevSol / ...CurrVel (:997-1016,1030-1037), the checks (:866-878,1047-1061, detection only)
-// and getTerminalSegments (src/traj_optimizer.cpp:541-548). Because every agent runs the same planner on the same
-// snapshot, agent j's initial trajectory IS the prediction every neighbour makes of j, so it is computed once.
+// initialTrajPlanningPrevSol / ...CurrVel (:997-1016,1030-1037), obstaclePredictionCheck / initialTrajPlanningCheck
+// (:866-878,1047-1061) and getTerminalSegments (src/traj_optimizer.cpp:541-548). Because every agent runs the same
+// planner on the same snapshot, agent j's initial trajectory IS the prediction every neighbour makes of j, so it is
+// computed once — and so are the two checks: when the observed position is farther than reset_threshold from the start of
+// the shifted previous trajectory, prediction and initial trajectory collapse to the position, the agent is marked for
+// good (it is in everybody's obs_slack_indices from now on, and everybody is in its own) and its corridor is re-armed.
 // ------------------------------------------------------------------------------------------------------------
 // getTerminalSegments (src/traj_optimizer.cpp:541-548)
 __device__ __forceinline__ int terminal_segments_of(F3 goal, F3 pos, double v_nom, double dt) {
@@ -31,6 +34,13 @@ __global__ void __launch_bounds__(96) k_predict(PredictLaunch L) {
     const int a = blockIdx.x;
     const int e = threadIdx.x;
     const lscgpu_agent_in& in = L.in[a];
+    // the check, by every thread alike: start of the shifted previous trajectory against the observed position
+    bool reset = false;
+    if (L.planner_seq >= 2) {
+        const float* t = L.prev_traj + (size_t)a * kTrajFloats + 18;      // traj_curr[1][0]
+        const F3 dlt = f3_sub(F3{t[0], t[1], t[2]}, F3{in.position[0], in.position[1], in.position[2]});
+        reset = sqrt(f3_dot(dlt, dlt)) > L.reset_threshold;
+    }
     if (e < kTrajFloats) {
         const int axis = e % 3, cp = e / 3, m = cp / 6, i = cp % 6;
         float val;
@@ -39,6 +49,8 @@ __global__ void __launch_bounds__(96) k_predict(PredictLaunch L) {
             const double m_intp = (double)m + (double)i / (double)kN;
             const float vel = in.velocity[axis];
             val = __fadd_rn(in.position[axis], __fmul_rn(__fmul_rn(vel, (float)m_intp), (float)L.dt));
+        } else if (reset) {
+            val = in.position[axis];                                       // :871-875, :1053-1057
         } else {
             const float* t = L.prev_traj + (size_t)a * kTrajFloats;
             val = (m < kM - 1) ? t[((m + 1) * 6 + i) * 3 + axis] : t[(kM * 6 - 1) * 3 + axis];
@@ -62,10 +74,14 @@ __global__ void __launch_bounds__(96) k_predict(PredictLaunch L) {
     __syncthreads();
     const float* o = L.pred + (size_t)a * kTrajFloats;
     if (e == 0) {
-        const F3 p0{o[0], o[1], o[2]}, pos{in.position[0], in.position[1], in.position[2]};
-        const F3 dlt = f3_sub(p0, pos);
+        const F3 pos{in.position[0], in.position[1], in.position[2]};
         int fl = 0;
-        if (sqrt(f3_dot(dlt, dlt)) > L.reset_threshold) fl |= LSCGPU_FLAG_SLACK_NEEDED;
+        if (reset) {
+            fl |= LSCGPU_FLAG_SLACK_NEEDED;
+            L.reset_ever[a] = 1;                  // :870, :1049-1051 (sticky)
+            *L.any_reset = 1;
+            L.init_sfc[a] = 1;                    // :1059
+        }
         L.flags[a] = fl;                          // the SFC warp of k_agent_plan adds its bit in the result record
         const F3 g{in.goal[0], in.goal[1], in.goal[2]};
         L.ts[a] = terminal_segments_of(g, pos, L.consts[a].v_nom, L.dt);
@@ -173,8 +189,10 @@ __global__ void __launch_bounds__(128) k_goal_plan(GoalLaunch L) {
     const double dist_to_goal = sqrt(f3_dot(to_goal, to_goal));
     double best = 1e9;                                   // SP_INFINITY
     int best_j = -1;
+    const bool self_reset = L.reset_ever[a] != 0;
     for (int j = tid; j < L.n_agents; j += 128) {
         if (j == a) continue;
+        if (self_reset || L.reset_ever[j]) continue;      // obs_slack_indices: high priority, never the retreat target (:548-551)
         const lscgpu_agent_in& o = L.in[j];
         const F3 op{o.position[0], o.position[1], o.position[2]}, og{o.goal[0], o.goal[1], o.goal[2]};
         const F3 d1 = f3_sub(op, og), d2 = f3_sub(op, pos);

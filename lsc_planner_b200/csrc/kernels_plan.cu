@@ -19,6 +19,7 @@
 #include <climits>
 #include <cstdlib>
 #include <string>
+#include <type_traits>
 
 #include "gjk.cuh"
 #include "kernels.hpp"
@@ -48,9 +49,9 @@ struct LscShared {
 __host__ __device__ constexpr size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 struct PlanSmemLayout {
     size_t qp, lists, lsc, nr, rhs, gate, seg, total;
-    __host__ __device__ PlanSmemLayout(int cap, int threads) {
+    __host__ __device__ PlanSmemLayout(int cap, int threads, size_t qp_bytes = sizeof(QpShared)) {
         qp = 0;
-        lists = align16(qp + sizeof(QpShared));
+        lists = align16(qp + qp_bytes);
         lsc = align16(lists + sizeof(int) * (threads / 32) * kWarpList);
         nr = align16(lsc + sizeof(LscShared));
         rhs = nr + sizeof(float4) * (size_t)cap;
@@ -60,6 +61,7 @@ struct PlanSmemLayout {
     }
 };
 size_t agent_plan_smem_bytes(int row_cap, int threads) { return PlanSmemLayout(row_cap, threads).total; }
+size_t agent_plan_slack_smem_bytes(int row_cap, int threads) { return PlanSmemLayout(row_cap, threads, sizeof(QpSharedSlack)).total; }
 
 // ------------------------------------------------------------------------------------------------------------
 // LSC phase of agent a by the kT threads of the block.
@@ -73,8 +75,11 @@ size_t agent_plan_smem_bytes(int row_cap, int threads) { return PlanSmemLayout(r
 //     until the iterate has travelled that far).
 // Returns the number of kept pairs (same value in all participating threads).
 // ------------------------------------------------------------------------------------------------------------
-template <int kT>
-__device__ __forceinline__ int lsc_phase(const PlanLaunch& L, int a, const RowSrc& rows, LscShared& X, const QpShared& S,
+// Slack kernels (SH::kE > 0): the pairs against obstacles of the agent's obs_slack_indices — every neighbour once the
+// agent itself was reset, else the neighbours that ever were (src/traj_planner.cpp:866-878,1047-1061) — are marked
+// kSlackUntouched, and their gate is the distance in the extended whitened space.
+template <int kT, class SH>
+__device__ __forceinline__ int lsc_phase(const PlanLaunch& L, int a, const RowSrc& rows, LscShared& X, const SH& S,
                                          int2* queue, int& gjk_it) {
     constexpr int kW = kT / 32;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -180,6 +185,12 @@ __device__ __forceinline__ int lsc_phase(const PlanLaunch& L, int a, const RowSr
                 RowRec rec;
                 rec.ax = seg.normal.x; rec.ay = seg.normal.y; rec.az = seg.normal.z; rec.inv_an = inv_an;
                 double mu_min = INFINITY;
+                bool soft = false;
+                double isc2 = 0.0;
+                if constexpr (SH::kE > 0) {
+                    soft = L.reset_ever[a] != 0 || L.reset_ever[j] != 0;
+                    isc2 = S.isc_m[m] * S.isc_m[m];
+                }
 #pragma unroll
                 for (int i = 0; i < 6; i++) {
                     // row  a . c_{m,i} >= d_i + a . o_{m,i}      (src/traj_optimizer.cpp:437-466)
@@ -189,10 +200,16 @@ __device__ __forceinline__ int lsc_phase(const PlanLaunch& L, int a, const RowSr
                     if (m == 0 && i < kPhi) continue;
                     const int vi = m * 6 + i;
                     const double slack = ax * S.x[vi] + ay * S.x[kAx + vi] + az * S.x[2 * kAx + vi] - rhs;
-                    const double mu = an > 0.0 ? slack * (double)inv_an * S.inv_gn[vi] : (slack < 0.0 ? -INFINITY : INFINITY);
+                    double mu = an > 0.0 ? slack * (double)inv_an * S.inv_gn[vi] : (slack < 0.0 ? -INFINITY : INFINITY);
+                    if constexpr (SH::kE > 0) {
+                        if (soft) {
+                            const double sc = an > 0.0 ? (double)inv_an * S.inv_gn[vi] : INFINITY;
+                            mu = slack * (sc < INFINITY ? sc * rsqrt(1.0 + isc2 * sc * sc) : rsqrt(isc2));
+                        }
+                    }
                     mu_min = fmin(mu_min, mu);
                 }
-                rows.store(slot, rec, m, p, mu_min > 0.0 ? mu_min * 0.999999 : mu_min, L.mirror_rows != 0);
+                rows.store(slot, rec, m, p, mu_min > 0.0 ? mu_min * 0.999999 : mu_min, L.mirror_rows != 0, soft ? kSlackUntouched : 0);
             }
         }
         // the queue tail that stays for the next chunk is only read after that chunk's barriers; nothing to wait for here
@@ -201,12 +218,18 @@ __device__ __forceinline__ int lsc_phase(const PlanLaunch& L, int a, const RowSr
 }
 
 // ------------------------------------------------------------------------------------------------------------
-template <int kPlanThreads, bool kSfc>
-__global__ void __launch_bounds__(kPlanThreads, 512 / kPlanThreads) k_agent_plan(PlanLaunch L) {
+// kSlack: the instantiation with slack coordinates (QpSharedSlack). Which one plans the step is a property of the whole
+// swarm — once any agent was reset, every planner's obs_slack_indices holds it — so both kernels are launched every step
+// and the one the step does not need returns at once (*L.any_reset, set by k_predict).
+template <int kPlanThreads, bool kSfc, bool kSlack>
+__global__ void __launch_bounds__(kPlanThreads, kSlack ? 2 : 512 / kPlanThreads) k_agent_plan(PlanLaunch L) {
+    using SH = typename std::conditional<kSlack, QpSharedSlack, QpShared>::type;
+    if (L.any_reset && (*L.any_reset != 0) != kSlack) return;
+    const int row_cap = kSlack ? L.row_cap_slack : L.row_cap;
     constexpr int kPlanWarps = kPlanThreads / 32;
     extern __shared__ __align__(16) unsigned char smem[];
-    const PlanSmemLayout lay(L.row_cap, kPlanThreads);
-    QpShared& S = *reinterpret_cast<QpShared*>(smem + lay.qp);
+    const PlanSmemLayout lay(row_cap, kPlanThreads, sizeof(SH));
+    SH& S = *reinterpret_cast<SH*>(smem + lay.qp);
     int* open_lists = reinterpret_cast<int*>(smem + lay.lists);
     LscShared& X = *reinterpret_cast<LscShared*>(smem + lay.lsc);
     const long long t_start = clock64();
@@ -224,7 +247,7 @@ __global__ void __launch_bounds__(kPlanThreads, 512 / kPlanThreads) k_agent_plan
     rows.s_rhs = reinterpret_cast<double2*>(smem + lay.rhs);
     rows.s_gate = reinterpret_cast<double*>(smem + lay.gate);
     rows.s_seg = smem + lay.seg;
-    rows.cap = L.row_cap;
+    rows.cap = row_cap;
     rows.g_rows = L.rows + (size_t)bi * L.P_pad;
     rows.g_gate = L.safe + (size_t)bi * L.P_pad;
     rows.g_kept = L.kept + (size_t)bi * L.P_pad;
@@ -243,12 +266,12 @@ __global__ void __launch_bounds__(kPlanThreads, 512 / kPlanThreads) k_agent_plan
         X.own_reach_max = rm;
     }
     if (tid == 0) { X.sfc_ok = 1; X.sfc_self = 0; X.t_sfc = 0; }
-    qp_stage<kPlanThreads>(S, T, ts, st, gl, nullptr, L.wmin, L.wmax, L.consts[a]);     // ends with a block barrier
+    qp_stage<kPlanThreads>(S, T, ts, st, gl, nullptr, L.wmin, L.wmax, L.consts[a], L.slack_w);     // ends with a block barrier
 
     // ---- phase 1: corridors -------------------------------------------------------------------------------------
     int n_kept = 0, gjk_it = 0;
     int2* queue = reinterpret_cast<int2*>(S.Q);        // kPlanThreads * (kM + 1) entries <= 12 KB of Q + W's 24 KB
-    if (n_obs > 0) n_kept = lsc_phase<kPlanThreads>(L, a, rows, X, S, queue, gjk_it);
+    if (n_obs > 0) n_kept = lsc_phase<kPlanThreads, SH>(L, a, rows, X, S, queue, gjk_it);
     if (tid == 0) X.t_lsc = clock64() - t_start;
     if (kSfc && warp == 0) {
         // The step's new SFC box comes from k_sfc_step, launched at the start of the step beside k_predict. It is
@@ -316,7 +339,8 @@ __global__ void __launch_bounds__(kPlanThreads, 512 / kPlanThreads) k_agent_plan
 #else
     long long* secp = nullptr;
 #endif
-    const QpResultRegs R = qp_solve_core<kPlanThreads>(S, open_lists, rows, n_kept, T.vel_coef, T.acc_coef, L.max_iter, secp);
+    const QpResultRegs R = qp_solve_core<kPlanThreads>(S, open_lists, rows, n_kept, T.vel_coef, T.acc_coef, L.max_iter, secp,
+                                                       L.mirror_rows != 0);
 
     // ---- epilogue -----------------------------------------------------------------------------------------------
     if (L.counters) {
@@ -360,6 +384,13 @@ __global__ void __launch_bounds__(kPlanThreads, 512 / kPlanThreads) k_agent_plan
         o.qp_active = R.q;
         int fl = L.flags ? L.flags[a] : 0;
         if (kSfc && !X.sfc_ok) fl |= LSCGPU_FLAG_SFC_SEED_BLOCKED;
+        if constexpr (kSlack) {
+            fl |= LSCGPU_FLAG_SLACK_MODE;
+            bool used = false;
+            for (int c = 0; c < S.n_e; c++) used |= S.e[c] < 0.0;
+            if (used && ok) fl |= LSCGPU_FLAG_SLACK_USED;
+            if (S.overflow) fl |= LSCGPU_FLAG_SLACK_OVERFLOW;
+        }
         o.flags = fl;
         o.terminal_segments = ts;
         for (int k = 0; k < 3; k++) o.current_goal[k] = (float)gl[k];
@@ -385,17 +416,19 @@ __global__ void __launch_bounds__(kPlanThreads, 512 / kPlanThreads) k_agent_plan
 }
 
 // opt in to > 48 KB of dynamic shared memory and the largest shared-memory carve-out (two blocks per SM); per device
-template <int kT, bool kSfc>
+template <int kT, bool kSfc, bool kSlack>
 static cudaError_t configure_one() {
-    cudaError_t rc = cudaFuncSetAttribute(k_agent_plan<kT, kSfc>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (rc == cudaSuccess) rc = cudaFuncSetAttribute(k_agent_plan<kT, kSfc>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaError_t rc = cudaFuncSetAttribute(k_agent_plan<kT, kSfc, kSlack>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (rc == cudaSuccess) rc = cudaFuncSetAttribute(k_agent_plan<kT, kSfc, kSlack>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     return rc;
 }
 cudaError_t configure_agent_plan() {
-    cudaError_t rc = configure_one<256, true>();
-    if (rc == cudaSuccess) rc = configure_one<256, false>();
-    if (rc == cudaSuccess) rc = configure_one<128, true>();
-    if (rc == cudaSuccess) rc = configure_one<128, false>();
+    cudaError_t rc = configure_one<256, true, false>();
+    if (rc == cudaSuccess) rc = configure_one<256, false, false>();
+    if (rc == cudaSuccess) rc = configure_one<128, true, false>();
+    if (rc == cudaSuccess) rc = configure_one<128, false, false>();
+    if (rc == cudaSuccess) rc = configure_one<256, true, true>();
+    if (rc == cudaSuccess) rc = configure_one<256, false, true>();
     return rc;
 }
 
@@ -403,11 +436,17 @@ void launch_agent_plan(const PlanLaunch& L, cudaStream_t s) {
     if (L.n_blocks <= 0) return;
     const size_t smem = agent_plan_smem_bytes(L.row_cap, L.threads);
     if (L.threads == 128) {
-        if (L.use_sfc) k_agent_plan<128, true><<<L.n_blocks, 128, smem, s>>>(L);
-        else k_agent_plan<128, false><<<L.n_blocks, 128, smem, s>>>(L);
+        if (L.use_sfc) k_agent_plan<128, true, false><<<L.n_blocks, 128, smem, s>>>(L);
+        else k_agent_plan<128, false, false><<<L.n_blocks, 128, smem, s>>>(L);
     } else {
-        if (L.use_sfc) k_agent_plan<256, true><<<L.n_blocks, 256, smem, s>>>(L);
-        else k_agent_plan<256, false><<<L.n_blocks, 256, smem, s>>>(L);
+        if (L.use_sfc) k_agent_plan<256, true, false><<<L.n_blocks, 256, smem, s>>>(L);
+        else k_agent_plan<256, false, false><<<L.n_blocks, 256, smem, s>>>(L);
+    }
+    if (L.any_reset) {
+        // the slack instantiation (256 threads, two blocks per SM): returns at once unless some agent was ever reset
+        const size_t smem_s = agent_plan_slack_smem_bytes(L.row_cap_slack, 256);
+        if (L.use_sfc) k_agent_plan<256, true, true><<<L.n_blocks, 256, smem_s, s>>>(L);
+        else k_agent_plan<256, false, true><<<L.n_blocks, 256, smem_s, s>>>(L);
     }
 }
 

@@ -133,8 +133,17 @@ __global__ void __launch_bounds__(128) k_sfc_step(SfcStepLaunch L) {
     SfcCtx c;
     sfc_ctx_init(c, L.dm, L.wmin, L.wmax, L.res, threadIdx.x & 31);
     double face;
+    // a state reset in this step re-arms the corridor (src/traj_planner.cpp:1047-1061); k_predict, which makes the same
+    // check, runs beside this kernel and may not have raised init_sfc yet
+    bool first = L.init_sfc[a] != 0;
+    if (L.planner_seq >= 2) {
+        const float* t = L.prev_traj + (size_t)a * kTrajFloats + 18;
+        const lscgpu_agent_in& in = L.in[a];
+        const F3 dlt = f3_sub(F3{t[0], t[1], t[2]}, F3{in.position[0], in.position[1], in.position[2]});
+        first = first || sqrt(f3_dot(dlt, dlt)) > L.reset_threshold;
+    }
     const bool ok = sfc_agent_box(c, L.dm, L.consts[a].sat_index, L.res, L.in[a], L.prev_traj + (size_t)a * kTrajFloats,
-                                  L.init_sfc[a] != 0, face);
+                                  first, face);
     if (c.lane < 6) L.sfc_box_g[(size_t)a * 6 + c.lane] = ok ? (float)face : 0.0f;
     if (c.lane == 0) L.sfc_ok_g[a] = ok ? 1 : 0;
     __threadfence();

@@ -35,6 +35,16 @@
 // slots: it reads the gates, compacts the open slots into its own shared-memory list (ballot + popc, no block barrier)
 // and evaluates the list one pair per lane. The solve ends when no evaluated row is violated beyond the tolerance
 // (every skipped row is provably satisfied).
+//
+// Slack variables (QpSharedT<kE> with kE > 0; src/traj_optimizer.cpp:317-326,383-390,455-457). Once an agent's
+// obs_slack_indices is not empty the reference relaxes the LSC rows of those obstacles by one variable eps_{oi,m} <= 0
+// per (obstacle, segment) with cost w_s ((M - m)/M) eps^2. In the whitened space that is one extra coordinate
+// e_p = sqrt(c_p) eps_p per such pair, objective |v|^2 + |e|^2, row normals (G^T a, -1/sqrt(c_p) at p) and the bound row
+// (0, -1/sqrt(c_p) at p). A coordinate is created when a row of its pair first enters the working set (until then
+// e_p = 0 and no active normal touches it): Q gets a zero row, nothing else changes — the same thin-Q / W update runs on
+// 39 + n_e rows. Up to kE coordinates per agent; an agent that needs more fails like an iteration-limit hit
+// (LSCGPU_FLAG_SLACK_OVERFLOW). The pair's slot carries its state in the upper bits of the segment byte: 0 hard rows,
+// 31 slack pair without a coordinate yet, 1 + c coordinate c.
 #pragma once
 #include <cstddef>
 
@@ -43,7 +53,6 @@
 namespace lscgpu {
 
 constexpr int NR = kRed;        // 39
-constexpr int LD = 39;          // row pitch of Q and W (odd: row-per-lane accesses are bank-conflict free)
 // Primal feasibility tolerance = CPLEX's default EpRHS (the reference sets no tolerance, src/traj_optimizer.cpp:42-54):
 // like a dual simplex, a row enters the working set only when violated by more than this; entered rows are then met
 // exactly. Trajectories travel as float32, so agents in contact see hulls ~1e-7 closer than r_i + r_j; an exact
@@ -52,23 +61,40 @@ constexpr double kFeasTol = 1e-6;
 constexpr double kZeroTol = 1e-13;
 constexpr int kWarpList = 128;  // slots one warp gates (and at most lists) per slice
 
-struct QpShared {
-    double Q[NR * LD];          // columns 0..q-1: orthonormal basis of the active normals
-    double W[NR * LD];          // rows/columns 0..q-1: N W = Q (row k belongs to active row act[k])
+constexpr int kSlackUntouched = 31;         // slot code of a slack pair that has no coordinate yet
+constexpr int kSlackBoundBase = 1 << 30;    // row id of the bound eps <= 0 of slack coordinate c: kSlackBoundBase + c
+
+template <int kE_>
+struct QpSharedT {
+    static constexpr int kE = kE_;              // slack coordinates an agent can hold (0: no slack variables)
+    static constexpr int NRX = NR + kE_;        // rows of Q = dimension of the (extended) whitened space
+    static constexpr int LDX = (NR + kE_) | 1;  // row pitch of Q and W (odd: row-per-lane accesses are bank-conflict free)
+    double Q[NRX * LDX];        // columns 0..q-1: orthonormal basis of the active normals
+    double W[NRX * LDX];        // rows/columns 0..q-1: N W = Q (row k belongs to active row act[k])
     double G[kAx * kFree];      // whitened basis of this agent's terminal-segment count
     double x[kNv];
-    double z[NR + 1], d[NR + 1], tmp[NR + 1], rr[NR + 1], lam[NR + 1];
-    double vacc[NR + 1];        // whitened step accumulated by warp 0 since the last block-wide update of x
+    double z[NRX + 1], d[NRX + 1], tmp[NRX + 1], rr[NRX + 1], lam[NRX + 1];
+    double vacc[NRX + 1];       // whitened step accumulated by warp 0 since the last block-wide update of x
     double inv_gn[kAx];         // 1 / |G row|
     double inv_dyn[kM * 9];     // 1 / whitened length of the velocity (j<5) / acceleration (j>=5) rows
     double lb[15], ub[15], vmax[3], amax[3];
     double travelled;           // path length of the iterate in the whitened space
     double best_mu[8];          // per-warp pricing result
     int best_id[8];
-    int act[NR + 1];
+    int act[NRX + 1];
     int stop;                   // 0 run, 1 finished/failed (set by warp 0)
     unsigned long long g_bar;   // mbarrier: completion of the bulk copy of G
+    // slack coordinates (kE > 0)
+    double e[kE_ > 0 ? kE_ : 1];        // e_c = sqrt(c_p) eps_p  (<= 0 at the solution)
+    double e_isc[kE_ > 0 ? kE_ : 1];    // 1 / sqrt(c_p), c_p = w_s (M - m) / M
+    int e_slot[kE_ > 0 ? kE_ : 1];      // slot of the pair the coordinate belongs to
+    double isc_m[kM];                   // 1 / sqrt(c_p) per segment
+    int n_e;                            // coordinates in use
+    int overflow;                       // 1: a row needed a coordinate beyond kE
 };
+using QpShared = QpSharedT<0>;
+constexpr int kSlackCoords = 25;            // 39 + 25 = 64 rows: lane r owns rows r and r + 32
+using QpSharedSlack = QpSharedT<kSlackCoords>;
 
 // ---- bulk-asynchronous staging (TMA unit, non-tensor form): one thread arms an mbarrier with the byte count and issues
 // cp.async.bulk global -> shared; the copy proceeds while the block builds its corridors; consumers wait on the barrier
@@ -111,36 +137,48 @@ struct RowSrc {
     __device__ __forceinline__ void set_gate(int slot, double v) const {
         if (slot < cap) s_gate[slot] = v; else g_gate[slot] = v;
     }
+    // kCoded: the slot's segment byte / pair word carries a slack code in its upper bits (slack kernels only)
+    template <bool kCoded = false>
     __device__ __forceinline__ void load(int slot, float4& nr, double* r6, int& m) const {
         if (slot < cap) {
             nr = s_nr[slot];
             const double2 a = s_rhs[slot], b = s_rhs[cap + slot], c = s_rhs[2 * cap + slot];
             r6[0] = a.x; r6[1] = a.y; r6[2] = b.x; r6[3] = b.y; r6[4] = c.x; r6[5] = c.y;
-            m = s_seg[slot];
+            m = kCoded ? (s_seg[slot] & 7) : s_seg[slot];
         } else {
             const float4* src = reinterpret_cast<const float4*>(g_rows + slot);
             nr = src[0];
             const double2 a = *reinterpret_cast<const double2*>(src + 1), b = *reinterpret_cast<const double2*>(src + 2),
                           c = *reinterpret_cast<const double2*>(src + 3);
             r6[0] = a.x; r6[1] = a.y; r6[2] = b.x; r6[3] = b.y; r6[4] = c.x; r6[5] = c.y;
-            m = seg_of_pair(g_kept[slot]);
+            m = seg_of_pair(kCoded ? (g_kept[slot] & 0xffffff) : g_kept[slot]);
         }
     }
-    __device__ __forceinline__ void store(int slot, const RowRec& rec, int m, int pair, double gate_v, bool mirror) const {
+    __device__ __forceinline__ int seg(int slot) const {
+        return slot < cap ? (s_seg[slot] & 7) : seg_of_pair(g_kept[slot] & 0xffffff);
+    }
+    __device__ __forceinline__ int code(int slot) const {
+        return slot < cap ? (s_seg[slot] >> 3) : ((g_kept[slot] >> 24) & 31);
+    }
+    __device__ __forceinline__ void set_code(int slot, int code, bool mirror) const {
+        if (slot < cap) s_seg[slot] = (unsigned char)((s_seg[slot] & 7) | (code << 3));
+        if (slot >= cap || mirror) g_kept[slot] = (g_kept[slot] & 0xffffff) | (code << 24);
+    }
+    __device__ __forceinline__ void store(int slot, const RowRec& rec, int m, int pair, double gate_v, bool mirror, int code = 0) const {
         if (slot < cap) {
             s_nr[slot] = make_float4(rec.ax, rec.ay, rec.az, rec.inv_an);
             s_rhs[slot] = make_double2(rec.rhs[0], rec.rhs[1]);
             s_rhs[cap + slot] = make_double2(rec.rhs[2], rec.rhs[3]);
             s_rhs[2 * cap + slot] = make_double2(rec.rhs[4], rec.rhs[5]);
             s_gate[slot] = gate_v;
-            s_seg[slot] = (unsigned char)m;
+            s_seg[slot] = (unsigned char)(m | (code << 3));
         }
         if (slot >= cap || mirror) {        // mirror: the whole row store also goes to global memory (lscgpu_get_lsc)
             float4* dst = reinterpret_cast<float4*>(g_rows + slot);
             const float4* src = reinterpret_cast<const float4*>(&rec);
             dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
             g_gate[slot] = gate_v;
-            g_kept[slot] = pair;
+            g_kept[slot] = pair | (code << 24);
         }
     }
 };
@@ -197,8 +235,21 @@ __device__ __forceinline__ Best warp_argmin(Best b) {
 // six rows are six independent chains, rows that do not exist (initial-state control points of segment 0) or are not
 // violated beyond the tolerance become +inf by selects, and only the pair's most violated row (smallest i on ties, as
 // a sequential scan would keep) is offered to the thread's running best.
-__device__ __forceinline__ double price_pair(Best& best, const QpShared& S, int slot, int m, float4 nr, const double* r6) {
+// `code` (slack kernels): 0 hard rows; otherwise the pair's rows read a . c - eps >= rhs with eps = e_c / sqrt(c_p) of
+// its coordinate (0 while it has none) and are normalised by the length of the extended normal.
+template <class SH>
+__device__ __forceinline__ double price_pair(Best& best, const SH& S, int slot, int m, float4 nr, const double* r6, int code = 0) {
     const double ax = (double)nr.x, ay = (double)nr.y, az = (double)nr.z, inv = (double)nr.w;
+    double eps = 0.0, isc2 = 0.0;
+    bool soft = false;
+    if constexpr (SH::kE > 0) {
+        soft = code != 0;
+        if (soft) {
+            const double isc = S.isc_m[m];
+            isc2 = isc * isc;
+            if (code != kSlackUntouched) eps = S.e[code - 1] * isc;
+        }
+    }
     // x[k][m][0..5] and inv_gn[m][0..5] are 16-byte aligned runs of six doubles
     const double2* xb0 = reinterpret_cast<const double2*>(S.x + m * 6);
     const double2* xb1 = reinterpret_cast<const double2*>(S.x + kAx + m * 6);
@@ -215,8 +266,15 @@ __device__ __forceinline__ double price_pair(Best& best, const QpShared& S, int 
     int cand_i = -1;
 #pragma unroll
     for (int i = 0; i < 6; i++) {
-        const double slack = ax * xs[i] + ay * ys[i] + az * zs[i] - r6[i];
-        const double scale = inv * gs[i];
+        double slack = ax * xs[i] + ay * ys[i] + az * zs[i] - r6[i];
+        double scale = inv * gs[i];
+        if constexpr (SH::kE > 0) {
+            if (soft) {
+                slack -= eps;
+                // 1 / sqrt(|a|^2 |G_i|^2 + 1/c_p) from 1 / (|a| |G_i|)
+                scale = scale < INFINITY ? scale * rsqrt(1.0 + isc2 * scale * scale) : rsqrt(isc2);
+            }
+        }
         const bool exists = !(i < kPhi && m == 0);
         const bool finite = scale < INFINITY;
         const double mu = finite ? slack * scale : (slack < 0.0 ? -INFINITY : INFINITY);
@@ -236,10 +294,24 @@ struct RowRegs {
     double a[3];
     double b, inv_len;
     double nn;          // |normal * inv_len|^2: 1 up to the rounding of inv_len (the float32 1/|a| of an LSC record)
+    int ec;             // slack coordinate the row touches (-1: none) ...
+    double ea;          // ... and its coefficient there, -1/sqrt(c_p)
 };
-__device__ __forceinline__ RowRegs decode_row(int id, const QpShared& S, const RowSrc& rows, double vel_coef, double acc_coef) {
+template <class SH>
+__device__ __forceinline__ RowRegs decode_row(int id, const SH& S, const RowSrc& rows, double vel_coef, double acc_coef) {
     RowRegs r;
     r.idx[1] = r.idx[2] = 0; r.a[1] = r.a[2] = 0.0;
+    r.ec = -1; r.ea = 0.0;
+    if constexpr (SH::kE > 0) {
+        if (id >= kSlackBoundBase) {            // eps_c <= 0:  -(1/sqrt(c_p)) e_c >= 0
+            const int c = id - kSlackBoundBase;
+            r.nnz = 0; r.idx[0] = 0; r.a[0] = 0.0; r.b = 0.0;
+            r.ec = c; r.ea = -S.e_isc[c];
+            r.inv_len = 1.0 / S.e_isc[c];
+            r.nn = 1.0;
+            return r;
+        }
+    }
     if (id < 180) {
         const int var = id >> 1, side = id & 1;
         const int k = var / kAx, mi = var - k * kAx, m = mi / 6;
@@ -266,7 +338,7 @@ __device__ __forceinline__ RowRegs decode_row(int id, const QpShared& S, const R
     } else {
         const int e = id - kFixedRows, slot = e / 6, i = e - slot * 6;
         float4 nr; double r6[6]; int m;
-        rows.load(slot, nr, r6, m);
+        rows.template load<(SH::kE > 0)>(slot, nr, r6, m);
         const int vi = m * 6 + i;
         r.nnz = 3;
         r.idx[0] = vi; r.idx[1] = kAx + vi; r.idx[2] = 2 * kAx + vi;
@@ -279,12 +351,25 @@ __device__ __forceinline__ RowRegs decode_row(int id, const QpShared& S, const R
         // (the step, the multipliers and the travelled distance are invariant to it); 1/|a| = inf marks a zero normal
         r.inv_len = (double)nr.w * S.inv_gn[vi];
         r.nn = (r.a[0] * r.a[0] + r.a[1] * r.a[1] + r.a[2] * r.a[2]) * ((double)nr.w * (double)nr.w);
+        if constexpr (SH::kE > 0) {
+            const int code = rows.code(slot);
+            if (code != 0) {                    // slack pair (it has a coordinate by now: the caller created it)
+                const double isc = S.isc_m[m];
+                r.ec = code - 1; r.ea = -isc;
+                const double an2 = r.a[0] * r.a[0] + r.a[1] * r.a[1] + r.a[2] * r.a[2];
+                const double gn = 1.0 / S.inv_gn[vi];
+                r.inv_len = rsqrt(an2 * gn * gn + isc * isc);      // an2 == 0 (zero normal): the row only bounds eps
+                r.nn = (an2 * gn * gn + isc * isc) * (r.inv_len * r.inv_len);
+            }
+        }
     }
     return r;
 }
 
 // Remove active row l (see the header comment): one Householder reflection on the columns of Q and W.
-__device__ __forceinline__ void drop_active(QpShared& S, int& q, int l, int lane) {
+template <class SH>
+__device__ __forceinline__ void drop_active(SH& S, int& q, int l, int lane, int nr = NR) {
+    constexpr int LD = SH::LDX;
     const int j = q - 1;
     __syncwarp();
     if (j > 0) {
@@ -300,7 +385,8 @@ __device__ __forceinline__ void drop_active(QpShared& S, int& q, int l, int lane
         __syncwarp();
         // Q <- Q - beta (Q v) v^T: lane r owns rows r and r + 32 (lanes without a second row redo row 38 and drop it)
         {
-            const int r2 = min(lane + 32, NR - 1);
+            const int nrows = SH::kE > 0 ? nr : NR;
+            const int r2 = min(lane + 32, nrows - 1);
             double* q1 = S.Q + lane * LD;
             double* q2 = S.Q + r2 * LD;
             double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
@@ -314,7 +400,7 @@ __device__ __forceinline__ void drop_active(QpShared& S, int& q, int l, int lane
             }
             for (; k < q; k++) { const double t0 = S.tmp[k]; a0 += q1[k] * t0; b0 += q2[k] * t0; }
             const double sa = beta * (a0 + a1), sb = beta * (b0 + b1);
-            const bool second = lane + 32 < NR;
+            const bool second = lane + 32 < nrows;
             for (k = 0; k < j; k++) {
                 const double t0 = S.tmp[k];
                 q1[k] -= sa * t0;
@@ -370,13 +456,19 @@ struct QpResultRegs {
 
 // Stage the agent-independent tables and the agent's problem data. Call with all threads; ends with a barrier.
 // boxes: this agent's SFC window [5][6] or null. S.x = x0 (equality-constrained minimiser).
-template <int kThreads>
-__device__ __forceinline__ void qp_stage(QpShared& S, const QpTablesDev& T, int ts, const double* st9, const double* gl3,
-                                         const float* boxes, const float* wmin, const float* wmax, const AgentConstDev& ac) {
+template <int kThreads, class SH>
+__device__ __forceinline__ void qp_stage(SH& S, const QpTablesDev& T, int ts, const double* st9, const double* gl3,
+                                         const float* boxes, const float* wmin, const float* wmax, const AgentConstDev& ac,
+                                         double slack_w = 1.0) {
     const int tid = threadIdx.x;
+    if constexpr (SH::kE > 0) {
+        // c_p = w_s (M - m) / M (src/traj_optimizer.cpp:386-387)
+        if (tid < kM) S.isc_m[tid] = rsqrt(slack_w * ((double)(kM - tid) / (double)kM));
+        if (tid == 0) { S.n_e = 0; S.overflow = 0; }
+    }
     // the whitened basis of this ts (3120 B, contiguous, 16-byte aligned on both sides) travels by one bulk-async copy
     // that completes on S.g_bar; it is first needed by the factorisation update, long after the corridors are built
-    static_assert((sizeof(double) * kAx * kFree) % 16 == 0 && offsetof(QpTablesDev, G) % 16 == 0 && offsetof(QpShared, G) % 16 == 0,
+    static_assert((sizeof(double) * kAx * kFree) % 16 == 0 && offsetof(QpTablesDev, G) % 16 == 0 && offsetof(SH, G) % 16 == 0,
                   "bulk copy of G needs 16-byte alignment and size");
     if (tid == 0) bulk_stage_begin(&S.g_bar, S.G, &T.G[ts - 1][0][0], (unsigned)(sizeof(double) * kAx * kFree));
     for (int e = tid; e < kAx; e += kThreads) S.inv_gn[e] = 1.0 / T.gnorm[ts - 1][e];
@@ -402,9 +494,11 @@ __device__ __forceinline__ void qp_stage(QpShared& S, const QpTablesDev& T, int 
 
 // The active-set solve. Preconditions: qp_stage done (S.x = x0), the row source holds n_kept pairs with their gates.
 // open_lists: kThreads / 32 lists of kWarpList ints in shared memory. Every thread returns the same result.
-template <int kThreads>
-__device__ __forceinline__ QpResultRegs qp_solve_core(QpShared& S, int* open_lists, const RowSrc& rows, int n_kept,
-                                                      double vel_coef, double acc_coef, int max_iter, long long* sec) {
+template <int kThreads, class SH>
+__device__ __forceinline__ QpResultRegs qp_solve_core(SH& S, int* open_lists, const RowSrc& rows, int n_kept,
+                                                      double vel_coef, double acc_coef, int max_iter, long long* sec,
+                                                      bool mirror_rows = false) {
+    constexpr int kE = SH::kE, NRX = SH::NRX, LD = SH::LDX;
     constexpr int kWarps = kThreads / 32;
     constexpr int kItems = (225 + kThreads - 1) / kThreads;
     constexpr int kGate = kWarpList / 32;
@@ -482,13 +576,18 @@ __device__ __forceinline__ QpResultRegs qp_solve_core(QpShared& S, int* open_lis
             for (int idx = lane; idx < n_open; idx += 32) {
                 const int slot = my_list[idx];
                 float4 nr; double r6[6]; int m;
-                rows.load(slot, nr, r6, m);
-                const double mu_min = price_pair(best, S, slot, m, nr, r6);
+                rows.template load<(kE > 0)>(slot, nr, r6, m);
+                const double mu_min = price_pair(best, S, slot, m, nr, r6, kE > 0 ? rows.code(slot) : 0);
                 // 1e-6 relative margin: the stored 1/|a| is float32, so mu carries ~6e-8 relative error
                 rows.set_gate(slot, travelled + (mu_min > 0.0 ? mu_min * 0.999999 : mu_min));
                 R.pairs_evaluated++;
             }
             __syncwarp();       // the list is rewritten by the next slice
+        }
+        if constexpr (kE > 0) {
+            // bounds eps_c <= 0 of the coordinates in use (whitened slack -e_c)
+            if (warp == 0)
+                for (int c = lane; c < S.n_e; c += 32) consider(best, -S.e[c] * S.e_isc[c], 1.0 / S.e_isc[c], kSlackBoundBase + c);
         }
         R.passes++;
         best = warp_argmin(best);
@@ -507,13 +606,33 @@ __device__ __forceinline__ QpResultRegs qp_solve_core(QpShared& S, int* open_lis
             bool done = false;          // set when the solve must stop (failure)
             QP_TICK();
             S.vacc[lane] = 0.0;
-            if (lane + 32 < NR + 1) S.vacc[lane + 32] = 0.0;
+            if (lane + 32 < NRX + 1) S.vacc[lane + 32] = 0.0;
             do {
                 {
                     bool dup = false;
                     for (int k = lane; k < q; k += 32) dup |= S.act[k] == best.id;
                     if (__any_sync(0xffffffffu, dup)) { status = LSCGPU_QP_MAXITER; done = true; break; }   // numerical breakdown
                 }
+                if constexpr (kE > 0) {
+                    // first row of a slack pair to enter: its slack variable becomes coordinate NR + c (e_c = 0, a zero row
+                    // of Q: no active normal touches it yet)
+                    if (best.id >= kFixedRows && best.id < kSlackBoundBase) {
+                        const int slot = (best.id - kFixedRows) / 6;
+                        if (rows.code(slot) == kSlackUntouched) {
+                            const int c = S.n_e;
+                            if (c >= kE) { if (lane == 0) S.overflow = 1; status = LSCGPU_QP_MAXITER; done = true; break; }
+                            const int m = rows.seg(slot);
+                            __syncwarp();
+                            if (lane == 0) {
+                                S.e[c] = 0.0; S.e_isc[c] = S.isc_m[m]; S.e_slot[c] = slot; S.n_e = c + 1;
+                                rows.set_code(slot, c + 1, mirror_rows);
+                            }
+                            for (int k = lane; k < LD; k += 32) S.Q[(NR + c) * LD + k] = 0.0;
+                            __syncwarp();
+                        }
+                    }
+                }
+                const int nr = kE > 0 ? NR + S.n_e : NR;        // rows of Q in use
                 const RowRegs row = decode_row(best.id, S, rows, vel_coef, acc_coef);
                 if (!(row.inv_len < INFINITY)) { status = LSCGPU_QP_INFEASIBLE; done = true; break; }
                 // unit whitened normal  nv = (G (+) G (+) G)^T a / |.|: lane c owns coordinates c and c + 32
@@ -531,6 +650,8 @@ __device__ __forceinline__ QpResultRegs qp_solve_core(QpShared& S, int* open_lis
                             if (t < row.nnz && ax_t == k) sacc += row.a[t] * S.G[(row.idx[t] - ax_t * kAx) * kFree + cc];
                         }
                         nv_reg[h] = sacc * row.inv_len;
+                    } else if (kE > 0 && c - NR == row.ec) {
+                        nv_reg[h] = row.ea * row.inv_len;
                     }
                 }
                 // slack of the selected row (normalised); along the step it grows by t |z|^2 (a . G z = |G^T a| nv . z and
@@ -538,6 +659,7 @@ __device__ __forceinline__ QpResultRegs qp_solve_core(QpShared& S, int* open_lis
                 double slack = -row.b;
 #pragma unroll
                 for (int t = 0; t < 3; t++) if (t < row.nnz) slack += row.a[t] * S.x[row.idx[t]];
+                if constexpr (kE > 0) { if (row.ec >= 0) slack += row.ea * S.e[row.ec]; }
                 slack *= row.inv_len;
                 double lam_p = 0.0;
                 QP_TOCK(1);
@@ -546,7 +668,7 @@ __device__ __forceinline__ QpResultRegs qp_solve_core(QpShared& S, int* open_lis
                     // ---- z = (I - Q Q^T) nv by Gram-Schmidt (second pass when needed); d = Q^T nv --------------------
                     __syncwarp();
                     S.z[lane] = nv_reg[0]; S.d[lane] = 0.0;
-                    if (lane + 32 < NR) { S.z[lane + 32] = nv_reg[1]; S.d[lane + 32] = 0.0; }
+                    if (lane + 32 < nr) { S.z[lane + 32] = nv_reg[1]; S.d[lane + 32] = 0.0; }
                     __syncwarp();
                     double zz = row.nn;              // |nv|^2
                     if (q > 0) {
@@ -571,6 +693,10 @@ __device__ __forceinline__ QpResultRegs qp_solve_core(QpShared& S, int* open_lis
                                         else s2 += qv[i] * pz;
                                     }
                                 }
+                                if constexpr (kE > 0) {
+#pragma unroll 1
+                                    for (int r = NR; r < nr; r++) s0 += qc[r * LD] * S.z[r];
+                                }
                                 const double sdot = s0 + s1 + s2;
                                 S.tmp[lane] = sdot;
                                 S.d[lane] += sdot;
@@ -579,7 +705,7 @@ __device__ __forceinline__ QpResultRegs qp_solve_core(QpShared& S, int* open_lis
                             for (int k = lane + 32; k < q; k += 32) {     // q > 32 only
                                 double sdot = 0.0;
 #pragma unroll 1
-                                for (int r = 0; r < NR; r++) sdot += S.Q[r * LD + k] * S.z[r];
+                                for (int r = 0; r < nr; r++) sdot += S.Q[r * LD + k] * S.z[r];
                                 S.tmp[k] = sdot;
                                 S.d[k] += sdot;
                             }
@@ -588,7 +714,7 @@ __device__ __forceinline__ QpResultRegs qp_solve_core(QpShared& S, int* open_lis
                             // (lanes without a second row read row 38 and drop the result)
                             double zp;
                             {
-                                const int r2 = min(lane + 32, NR - 1);
+                                const int r2 = min(lane + 32, nr - 1);
                                 const double* q1 = S.Q + lane * LD;
                                 const double* q2 = S.Q + r2 * LD;
                                 double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
@@ -604,7 +730,7 @@ __device__ __forceinline__ QpResultRegs qp_solve_core(QpShared& S, int* open_lis
                                 const double z1 = S.z[lane] - (a0 + a1);
                                 S.z[lane] = z1;
                                 zp = z1 * z1;
-                                if (lane + 32 < NR) {
+                                if (lane + 32 < nr) {
                                     const double z2 = S.z[lane + 32] - (b0 + b1);
                                     S.z[lane + 32] = z2;
                                     zp += z2 * z2;
@@ -668,15 +794,15 @@ __device__ __forceinline__ QpResultRegs qp_solve_core(QpShared& S, int* open_lis
                     for (int k = lane; k < q; k += 32) S.lam[k] -= t * S.rr[k];
                     lam_p += t;
                     QP_TOCK(3);
-                    if (!primal) { drop_active(S, q, l, lane); QP_TOCK(6); continue; }
+                    if (!primal) { drop_active(S, q, l, lane, nr); QP_TOCK(6); continue; }
                     if (lane == 0) S.travelled += t * (zz * rsq) * (1.0 + 1e-9) + 1e-13;
                     S.vacc[lane] += t * S.z[lane];
-                    if (lane + 32 < NR) S.vacc[lane + 32] += t * S.z[lane + 32];
+                    if (lane + 32 < nr) S.vacc[lane + 32] += t * S.z[lane + 32];
                     slack += t * zz;
                     QP_TOCK(4);
                     if (t2 <= t1) {
                         // the row becomes active: new basis column z / |z|, new column (-rr / |z|, 1 / |z|) of W
-                        for (int r = lane; r < NR; r += 32) S.Q[r * LD + q] = S.z[r] * rsq;
+                        for (int r = lane; r < nr; r += 32) S.Q[r * LD + q] = S.z[r] * rsq;
                         for (int k = lane; k < q; k += 32) { S.W[k * LD + q] = -S.rr[k] * rsq; S.W[q * LD + k] = 0.0; }
                         if (lane == 0) {
                             S.W[q * LD + q] = rsq;
@@ -688,7 +814,7 @@ __device__ __forceinline__ QpResultRegs qp_solve_core(QpShared& S, int* open_lis
                         QP_TOCK(5);
                         break;
                     }
-                    drop_active(S, q, l, lane);
+                    drop_active(S, q, l, lane, nr);
                     QP_TOCK(6);
                 }
             } while (false);
@@ -708,19 +834,23 @@ __device__ __forceinline__ QpResultRegs qp_solve_core(QpShared& S, int* open_lis
             s0 += g[kFree - 1] * va[kFree - 1];
             S.x[e] += s0 + s1;
         }
+        if constexpr (kE > 0) { if (tid < S.n_e) S.e[tid] += S.vacc[NR + tid]; }
         if (stop) break;
     }
     __syncthreads();
     // q, iters and status live in warp 0; hand them to everybody
-    if (tid == 0) { S.act[NR] = q; S.best_id[0] = iters; S.best_id[1] = status; }
+    if (tid == 0) { S.act[NRX] = q; S.best_id[0] = iters; S.best_id[1] = status; }
     __syncthreads();
-    R.q = S.act[NR]; R.iters = S.best_id[0]; R.status = S.best_id[1];
+    R.q = S.act[NRX]; R.iters = S.best_id[0]; R.status = S.best_id[1];
     return R;
 }
 
 // objective as the reference reports it (getObjValue incl. the constant of the terminal cost); call with a full warp
-__device__ __forceinline__ double qp_objective(const QpShared& S, const QpTablesDev& T, int ts, const double* gl3, int lane) {
+// (with slack variables: plus their cost sum c_p eps_p^2 = |e|^2)
+template <class SH>
+__device__ __forceinline__ double qp_objective(const SH& S, const QpTablesDev& T, int ts, const double* gl3, int lane) {
     double jpart = 0.0;
+    if constexpr (SH::kE > 0) { if (lane < S.n_e) jpart = S.e[lane] * S.e[lane]; }
     if (lane < 15) {
         const int k = lane / 5, m = lane % 5;
         const double* c = S.x + k * kAx + m * 6;

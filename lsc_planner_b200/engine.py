@@ -215,6 +215,20 @@ class ReplanEngine:
     def planner_seq(self) -> int:
         return self.lib.lscgpu_get_planner_seq(self.h)
 
+    def set_slack_collision_weight(self, w: float):
+        """opt/slack_collision_weight of the slack variables a state reset brings into the QPs."""
+        A.check(self.lib.lscgpu_set_slack_collision_weight(self.h, float(w)))
+
+    def reset_state(self) -> np.ndarray:
+        """Sticky per-agent "was ever reset" bytes (who is in everybody's obs_slack_indices)."""
+        out = np.zeros(self.n, np.uint8)
+        A.check(self.lib.lscgpu_get_reset_state(self.h, A.p(out)))
+        return out
+
+    def set_reset_state(self, flags):
+        f = np.ascontiguousarray(flags, np.uint8).reshape(self.n)
+        A.check(self.lib.lscgpu_set_reset_state(self.h, A.p(f)))
+
     def get_lsc(self, agent: int):
         """(normals [N-1][5][3] float32, d [N-1][5][6] float64) of the last step, CollisionConstraints layout."""
         nr = np.zeros((max(self.n - 1, 0), 5, 3), np.float32); d = np.zeros((max(self.n - 1, 0), 5, 6), np.float64)
