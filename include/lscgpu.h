@@ -235,6 +235,16 @@ int lscgpu_qp_solve_batch(lscgpu_engine* e, int n_problems, const int32_t* agent
                           const float* lsc_point, const double* lsc_d, double* x, double* cost, int32_t* status,
                           int32_t* iterations);
 
+/* Same with CollisionConstraints::getSlackIndices (src/traj_optimizer.cpp:268,317-326,383-390,455-457): obs_slack[o] != 0
+ * marks the obstacles of obs_slack_indices; their LSC rows are relaxed by eps_{o,m} <= 0 with cost
+ * slack_collision_weight ((M - m) / M) eps^2 (lscgpu_set_slack_collision_weight). eps (optional) receives
+ * eps[o][5] for every obstacle (0 where the obstacle is outside the set). cost includes the slack cost. With no
+ * obstacle marked this is lscgpu_qp_solve_batch. */
+int lscgpu_qp_solve_batch_slack(lscgpu_engine* e, int n_problems, const int32_t* agent_index, const double* state,
+                                const double* goal, const float* sfc, const int32_t* obs_offset, const float* lsc_normal,
+                                const float* lsc_point, const double* lsc_d, const uint8_t* obs_slack, double* x,
+                                double* cost, int32_t* status, int32_t* iterations, double* eps);
+
 /* closestPointsBetweenPointAndConvexHull(origin, hull) (include/geometry.hpp:364-394) -> gjk()
  * (src/openGJK/openGJK.cpp:674-780) for n_hulls hulls of 6 points: hulls double[n][6][3] -> v double[n][3]
  * (closest point of the hull to the origin), iterations int32[n]. */

@@ -66,7 +66,8 @@ def symbols():
             "lscgpu_set_sfc", "lscgpu_get_sfc", "lscgpu_get_planner_seq", "lscgpu_get_lsc", "lscgpu_get_lsc_ex",
             "lscgpu_set_slack_collision_weight", "lscgpu_get_reset_state", "lscgpu_set_reset_state",
             "lscgpu_set_capture_rows",
-            "lscgpu_get_initial_traj", "lscgpu_qp_solve_batch", "lscgpu_gjk_batch", "lscgpu_sfc_expand_batch",
+            "lscgpu_get_initial_traj", "lscgpu_qp_solve_batch", "lscgpu_qp_solve_batch_slack", "lscgpu_gjk_batch",
+            "lscgpu_sfc_expand_batch",
             "lscgpu_get_step_stats", "lscgpu_set_profiling", "lscgpu_sm_clock_khz", "lscgpu_stream",
             "lscgpu_measure_fma_peaks", "lscgpu_measure_latencies"]
 
@@ -111,6 +112,7 @@ def lib():
     L.lscgpu_set_capture_rows.argtypes = [ptr, C.c_int]
     L.lscgpu_get_initial_traj.argtypes = [ptr, ptr]
     L.lscgpu_qp_solve_batch.argtypes = [ptr, C.c_int] + [ptr] * 12
+    L.lscgpu_qp_solve_batch_slack.argtypes = [ptr, C.c_int] + [ptr] * 14
     L.lscgpu_gjk_batch.argtypes = [ptr, C.c_int, ptr, ptr, ptr]
     L.lscgpu_sfc_expand_batch.argtypes = [ptr, C.c_int, ptr, ptr, ptr, ptr, ptr]
     L.lscgpu_get_step_stats.argtypes = [ptr, C.POINTER(StepStats)]

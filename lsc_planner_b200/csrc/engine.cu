@@ -1006,10 +1006,11 @@ extern "C" int lscgpu_get_initial_traj(lscgpu_engine* e, float* out) {
 // ---- operator-level entries ------------------------------------------------------------------------------------------
 // Device scratch comes from the engine's pool (one allocation that only grows): a batch-of-one TrajOptimizer::solve
 // pays four copies in, one kernel chain and one copy out, no cudaMalloc.
-extern "C" int lscgpu_qp_solve_batch(lscgpu_engine* e, int nb, const int32_t* agent_index, const double* state,
-                                     const double* goal, const float* sfc, const int32_t* obs_offset,
-                                     const float* lsc_normal, const float* lsc_point, const double* lsc_d, double* x,
-                                     double* cost, int32_t* status, int32_t* iterations) {
+static int qp_solve_batch_impl(lscgpu_engine* e, int nb, const int32_t* agent_index, const double* state,
+                               const double* goal, const float* sfc, const int32_t* obs_offset,
+                               const float* lsc_normal, const float* lsc_point, const double* lsc_d,
+                               const uint8_t* obs_slack, double slack_w, double* x,
+                               double* cost, int32_t* status, int32_t* iterations, double* eps) {
     if (!e || nb < 0 || !agent_index || !state || !goal || !obs_offset || !x || !cost || !status || !iterations)
         return fail(LSCGPU_ERR_ARG, "null argument");
     if (nb == 0) return LSCGPU_OK;
@@ -1037,6 +1038,8 @@ extern "C" int lscgpu_qp_solve_batch(lscgpu_engine* e, int nb, const int32_t* ag
     const size_t o_sfc = cv.take<float>((size_t)nb * 30);
     const size_t o_n = cv.take<float>(pp * 3), o_p = cv.take<float>(pp * 18), o_d = cv.take<double>(pp * 6);
     const size_t o_rows = cv.take<RowRec>(pp), o_kept = cv.take<int>(pp), o_safe = cv.take<double>(pp);
+    const bool slack = obs_slack != nullptr && total_obs > 0;
+    const size_t o_slack = cv.take<unsigned char>(std::max(total_obs, 1)), o_eps = cv.take<double>(pp);
     CU(e->scratch.reserve(cv.off));
     char* base = (char*)e->scratch.p;
     auto at = [&](size_t o) { return base + o; };
@@ -1051,8 +1054,12 @@ extern "C" int lscgpu_qp_solve_batch(lscgpu_engine* e, int nb, const int32_t* ag
         CU(cudaMemcpyAsync(at(o_p), lsc_point, sizeof(float) * pairs * 18, cudaMemcpyHostToDevice, s));
         CU(cudaMemcpyAsync(at(o_d), lsc_d, sizeof(double) * pairs * 6, cudaMemcpyHostToDevice, s));
     }
+    if (slack) {
+        CU(cudaMemcpyAsync(at(o_slack), obs_slack, (size_t)total_obs, cudaMemcpyHostToDevice, s));
+        CU(cudaMemsetAsync(at(o_eps), 0, sizeof(double) * pairs, s));
+    }
     launch_rows_from_lsc(nb, (int*)at(o_off), total_obs, (float*)at(o_n), (float*)at(o_p), (double*)at(o_d), (RowRec*)at(o_rows),
-                         (int*)at(o_kept), (int*)at(o_kc), (double*)at(o_safe), s);
+                         (int*)at(o_kept), (int*)at(o_kc), (double*)at(o_safe), s, slack ? (unsigned char*)at(o_slack) : nullptr);
     launch_terminal_segments(nb, (double*)at(o_state), (double*)at(o_goal), (int*)at(o_ai), e->d_consts, e->prm.dt, (int*)at(o_ts), s);
     QpBatchLaunch ql{};
     ql.n_problems = nb; ql.T = e->d_tables; ql.consts = e->d_consts; ql.agent_index = (int*)at(o_ai);
@@ -1062,17 +1069,44 @@ extern "C" int lscgpu_qp_solve_batch(lscgpu_engine* e, int nb, const int32_t* ag
     ql.rows = (RowRec*)at(o_rows); ql.obs_offset = (int*)at(o_off);
     ql.kept = (int*)at(o_kept); ql.kept_count = (int*)at(o_kc); ql.safe = (double*)at(o_safe); ql.max_iter = e->max_iter;
     ql.x_out = (double*)at(o_x); ql.cost_out = (double*)at(o_cost); ql.status_out = (int*)at(o_status); ql.iters_out = (int*)at(o_iters);
+    ql.slack = slack ? 1 : 0; ql.slack_w = slack_w; ql.eps_out = slack ? (double*)at(o_eps) : nullptr;
     launch_qp_batch(ql, s);
     CU(cudaGetLastError());
     std::vector<char>& hb = e->host_buf;
     hb.resize(out_bytes);
     CU(cudaMemcpyAsync(hb.data(), base, out_bytes, cudaMemcpyDeviceToHost, s));
+    if (eps) {
+        if (slack) CU(cudaMemcpyAsync(eps, at(o_eps), sizeof(double) * pairs, cudaMemcpyDeviceToHost, s));
+        else std::memset(eps, 0, sizeof(double) * pairs);
+    }
     CU(cudaStreamSynchronize(s));
     std::memcpy(x, hb.data() + o_x, sizeof(double) * kNv * nb);
     std::memcpy(cost, hb.data() + o_cost, sizeof(double) * nb);
     std::memcpy(status, hb.data() + o_status, sizeof(int) * nb);
     std::memcpy(iterations, hb.data() + o_iters, sizeof(int) * nb);
+    for (int b = 0; b < nb; b++) status[b] &= 0xff;       // bit 8: more slack variables needed than the kernel holds (reported as MAXITER)
     return LSCGPU_OK;
+}
+
+extern "C" int lscgpu_qp_solve_batch(lscgpu_engine* e, int nb, const int32_t* agent_index, const double* state,
+                                     const double* goal, const float* sfc, const int32_t* obs_offset,
+                                     const float* lsc_normal, const float* lsc_point, const double* lsc_d, double* x,
+                                     double* cost, int32_t* status, int32_t* iterations) {
+    return qp_solve_batch_impl(e, nb, agent_index, state, goal, sfc, obs_offset, lsc_normal, lsc_point, lsc_d, nullptr, 1.0, x, cost,
+                               status, iterations, nullptr);
+}
+
+extern "C" int lscgpu_qp_solve_batch_slack(lscgpu_engine* e, int nb, const int32_t* agent_index, const double* state,
+                                           const double* goal, const float* sfc, const int32_t* obs_offset,
+                                           const float* lsc_normal, const float* lsc_point, const double* lsc_d,
+                                           const uint8_t* obs_slack, double* x, double* cost, int32_t* status,
+                                           int32_t* iterations, double* eps) {
+    if (!e || !obs_offset || nb < 0) return fail(LSCGPU_ERR_ARG, "null argument");
+    bool any = false;
+    if (obs_slack) for (int o = 0; o < obs_offset[nb]; o++) any |= obs_slack[o] != 0;
+    // the reference adds the variables only when the set is not empty (src/traj_optimizer.cpp:317)
+    return qp_solve_batch_impl(e, nb, agent_index, state, goal, sfc, obs_offset, lsc_normal, lsc_point, lsc_d, any ? obs_slack : nullptr,
+                               e->slack_w, x, cost, status, iterations, eps);
 }
 
 extern "C" int lscgpu_gjk_batch(lscgpu_engine* e, int n, const double* hulls, double* v, int32_t* iterations) {

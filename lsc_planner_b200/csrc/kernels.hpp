@@ -131,7 +131,7 @@ void launch_gjk_batch(int n, const double* hulls, double* v, int* iters, cudaStr
 // LSC arrays of the reference container -> row store (operator-level QP entry)
 void launch_rows_from_lsc(int n_problems, const int* obs_offset, int total_obs, const float* lsc_normal,
                           const float* lsc_point, const double* lsc_d, RowRec* rows, int* kept,
-                          int* kept_count, double* safe, cudaStream_t s);
+                          int* kept_count, double* safe, cudaStream_t s, const unsigned char* obs_slack = nullptr);
 
 void launch_terminal_segments(int n, const double* state9, const double* goal3, const int* agent_index,
                               const AgentConstDev* consts, double dt, int* ts_out, cudaStream_t s);
@@ -154,6 +154,9 @@ struct QpBatchLaunch {
     int max_iter;
     double* x_out;                 // [n_problems][90]
     double* cost_out; int* status_out; int* iters_out;
+    // slack variables (src/traj_optimizer.cpp:317-326,383-390,455-457): the slack instantiation of the kernel
+    int slack; double slack_w;
+    double* eps_out;               // null or [total_obs][5], zero-filled by the caller
 };
 void launch_qp_batch(const QpBatchLaunch& L, cudaStream_t s);
 // order[0..n) = agents a0 .. a0+n-1 (global ids), most expensive solve of the previous step first; deterministic

@@ -290,7 +290,7 @@ void launch_gjk_batch(int n, const double* hulls, double* v, int* iters, cudaStr
 // ------------------------------------------------------------------------------------------------------------
 __global__ void k_rows_from_lsc(int n_problems, const int* obs_offset, int total_obs, const float* lsc_normal,
                                 const float* lsc_point, const double* lsc_d, RowRec* rows, int* kept,
-                                int* kept_count, double* safe) {
+                                int* kept_count, double* safe, const unsigned char* obs_slack) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;     // global (obstacle, segment)
     if (t >= total_obs * kM) return;
     const int o = t / kM, m = t % kM;
@@ -299,7 +299,9 @@ __global__ void k_rows_from_lsc(int n_problems, const int* obs_offset, int total
     while (b + 1 < n_problems && obs_offset[b + 1] <= o) b++;
     const int n_b = obs_offset[b + 1] - obs_offset[b];
     const int p = kM * obs_offset[b] + m * n_b + (o - obs_offset[b]);
-    kept[p] = p - kM * obs_offset[b];                 // every pair is priced (no culling at the operator level)
+    // every pair is priced (no culling at the operator level); obstacles of obs_slack_indices: slack code 31 in the upper
+    // bits (a slack pair without a coordinate yet, qp_core.cuh)
+    kept[p] = (p - kM * obs_offset[b]) | ((obs_slack && obs_slack[o]) ? (31 << 24) : 0);
     safe[p] = -INFINITY;                              // ... starting with the first iteration
     if (o == obs_offset[b] && m == 0) kept_count[b] = kM * n_b;
     const float* nv = lsc_normal + ((size_t)o * kM + m) * 3;
@@ -315,11 +317,11 @@ __global__ void k_rows_from_lsc(int n_problems, const int* obs_offset, int total
 }
 void launch_rows_from_lsc(int n_problems, const int* obs_offset, int total_obs, const float* lsc_normal,
                           const float* lsc_point, const double* lsc_d, RowRec* rows, int* kept,
-                          int* kept_count, double* safe, cudaStream_t s) {
+                          int* kept_count, double* safe, cudaStream_t s, const unsigned char* obs_slack) {
     if (total_obs <= 0) return;
     const int n = total_obs * kM;
     k_rows_from_lsc<<<(n + 127) / 128, 128, 0, s>>>(n_problems, obs_offset, total_obs, lsc_normal, lsc_point, lsc_d, rows,
-                                                    kept, kept_count, safe);
+                                                    kept, kept_count, safe, obs_slack);
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -422,6 +422,7 @@ static cudaError_t configure_one() {
     if (rc == cudaSuccess) rc = cudaFuncSetAttribute(k_agent_plan<kT, kSfc, kSlack>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     return rc;
 }
+cudaError_t configure_qp_batch();
 cudaError_t configure_agent_plan() {
     cudaError_t rc = configure_one<256, true, false>();
     if (rc == cudaSuccess) rc = configure_one<256, false, false>();
@@ -429,6 +430,7 @@ cudaError_t configure_agent_plan() {
     if (rc == cudaSuccess) rc = configure_one<128, false, false>();
     if (rc == cudaSuccess) rc = configure_one<256, true, true>();
     if (rc == cudaSuccess) rc = configure_one<256, false, true>();
+    if (rc == cudaSuccess) rc = configure_qp_batch();
     return rc;
 }
 
@@ -454,9 +456,14 @@ void launch_agent_plan(const PlanLaunch& L, cudaStream_t s) {
 // k_qp_batch — TrajOptimizer::solve (src/traj_optimizer.cpp:31-154) for independent problems whose LSC rows arrive
 // from the host in the reference's container layout (k_rows_from_lsc); rows are priced from global memory.
 // ------------------------------------------------------------------------------------------------------------
+// kSlack: problems whose CollisionConstraints carry obs_slack_indices (slot codes set by k_rows_from_lsc); eps_out
+// receives the slack variable of every (obstacle, segment).
+template <bool kSlack>
 __global__ void __launch_bounds__(kBatchThreads, 2) k_qp_batch(QpBatchLaunch L) {
-    __shared__ __align__(16) QpShared S;
-    __shared__ int open_lists[(kBatchThreads / 32) * kWarpList];
+    using SH = typename std::conditional<kSlack, QpSharedSlack, QpShared>::type;
+    extern __shared__ __align__(16) unsigned char smem[];
+    SH& S = *reinterpret_cast<SH*>(smem);
+    int* open_lists = reinterpret_cast<int*>(smem + align16(sizeof(SH)));
     const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int agent = L.agent_index[b];
     const QpTablesDev& T = *L.T;
@@ -468,17 +475,40 @@ __global__ void __launch_bounds__(kBatchThreads, 2) k_qp_batch(QpBatchLaunch L) 
     rows.n_obs = L.obs_offset[b + 1] - L.obs_offset[b];
     const double* gl = L.goal3 + (size_t)b * 3;
     qp_stage<kBatchThreads>(S, T, ts, L.state9 + (size_t)b * 9, gl, L.boxes ? L.boxes + (size_t)b * 30 : nullptr, L.wmin, L.wmax,
-                           L.consts[agent]);
-    const QpResultRegs R = qp_solve_core<kBatchThreads>(S, open_lists, rows, L.kept_count[b], T.vel_coef, T.acc_coef, L.max_iter, nullptr);
+                           L.consts[agent], L.slack_w);
+    const QpResultRegs R = qp_solve_core<kBatchThreads>(S, open_lists, rows, L.kept_count[b], T.vel_coef, T.acc_coef, L.max_iter, nullptr,
+                                                        /*mirror_rows=*/true);
     if (warp != 0) return;
     const double cost = qp_objective(S, T, ts, gl, lane);
     for (int e = lane; e < kNv; e += 32) L.x_out[(size_t)b * kNv + e] = S.x[e];
-    if (lane == 0) { L.cost_out[b] = cost; L.status_out[b] = R.status; L.iters_out[b] = R.iters; }
+    if (lane == 0) {
+        L.cost_out[b] = cost; L.iters_out[b] = R.iters;
+        int status = R.status;
+        if constexpr (kSlack) { if (S.overflow) status |= 0x100; }      // the host maps this to its own error text
+        L.status_out[b] = status;
+    }
+    if constexpr (kSlack) {
+        if (L.eps_out) {
+            // slot of a pair inside the problem: m * n_b + o  ->  eps_out[(obs_offset[b] + o) * 5 + m]
+            const int n_b = rows.n_obs;
+            for (int c = lane; c < S.n_e; c += 32) {
+                const int slot = S.e_slot[c], m = slot / n_b, o = slot - m * n_b;
+                L.eps_out[((size_t)L.obs_offset[b] + o) * kM + m] = S.e[c] * S.e_isc[c];
+            }
+        }
+    }
 }
 
+static size_t qp_batch_smem(bool slack) {
+    return align16(slack ? sizeof(QpSharedSlack) : sizeof(QpShared)) + sizeof(int) * (kBatchThreads / 32) * kWarpList;
+}
+cudaError_t configure_qp_batch() {
+    return cudaFuncSetAttribute(k_qp_batch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qp_batch_smem(true));
+}
 void launch_qp_batch(const QpBatchLaunch& L, cudaStream_t s) {
     if (L.n_problems <= 0) return;
-    k_qp_batch<<<L.n_problems, kBatchThreads, 0, s>>>(L);
+    if (L.slack) k_qp_batch<true><<<L.n_problems, kBatchThreads, qp_batch_smem(true), s>>>(L);
+    else k_qp_batch<false><<<L.n_problems, kBatchThreads, qp_batch_smem(false), s>>>(L);
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -253,8 +253,9 @@ class ReplanEngine:
         return out
 
     # ---- operator-level entries ----------------------------------------------------------------------------
-    def qp_solve_batch(self, agent_index, state, goal, obs_offset, lsc_normal, lsc_point, lsc_d, sfc=None):
-        """TrajOptimizer::solve for a batch. Returns dict(x [B][90], cost, status, iterations)."""
+    def qp_solve_batch(self, agent_index, state, goal, obs_offset, lsc_normal, lsc_point, lsc_d, sfc=None, obs_slack=None):
+        """TrajOptimizer::solve for a batch. Returns dict(x [B][90], cost, status, iterations[, eps [obstacles][5]]).
+        obs_slack: per obstacle, non-zero = member of obs_slack_indices (its rows get slack variables)."""
         ai = np.ascontiguousarray(agent_index, np.int32); nb = len(ai)
         st = np.ascontiguousarray(state, np.float64).reshape(nb, 9)
         gl = np.ascontiguousarray(goal, np.float64).reshape(nb, 3)
@@ -266,6 +267,13 @@ class ReplanEngine:
         dd = np.ascontiguousarray(lsc_d, np.float64).reshape(tot, 5, 6)
         bx = None if sfc is None else np.ascontiguousarray(sfc, np.float32).reshape(nb, 30)
         x = np.zeros((nb, 90)); cost = np.zeros(nb); status = np.zeros(nb, np.int32); iters = np.zeros(nb, np.int32)
+        if obs_slack is not None:
+            sl = np.ascontiguousarray(obs_slack, np.uint8).reshape(tot)
+            eps = np.zeros((max(tot, 1), 5))
+            A.check(self.lib.lscgpu_qp_solve_batch_slack(self.h, nb, A.p(ai), A.p(st), A.p(gl), None if bx is None else A.p(bx),
+                                                         A.p(off), A.p(nr), A.p(pt), A.p(dd), A.p(sl), A.p(x), A.p(cost),
+                                                         A.p(status), A.p(iters), A.p(eps)))
+            return dict(x=x, cost=cost, status=status, iterations=iters, eps=eps[:tot])
         A.check(self.lib.lscgpu_qp_solve_batch(self.h, nb, A.p(ai), A.p(st), A.p(gl), None if bx is None else A.p(bx),
                                                A.p(off), A.p(nr), A.p(pt), A.p(dd), A.p(x), A.p(cost), A.p(status),
                                                A.p(iters)))

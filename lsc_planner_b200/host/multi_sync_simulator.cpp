@@ -23,6 +23,7 @@ public:
         agents.resize(mission.qn);
         for (int qi = 0; qi < mission.qn; qi++) agents[qi] = std::make_unique<TrajPlanner>(qi, param, mission, batch);
         ideal_states.resize(mission.qn);
+        parseDisturbances();
     }
     void setOctomap(const std::string& file) { batch->setOctomap(file); }
 
@@ -37,7 +38,7 @@ public:
     std::string result_file, summary_file;
     double total_flight_time = SP_INFINITY, total_distance = 0, safety_ratio_agent = SP_INFINITY;
     bool is_collided = false;
-    int qp_failures = 0;
+    int qp_failures = 0, n_resets = 0;
 
 private:
     Param param;
@@ -50,19 +51,52 @@ private:
     bool initial_update = true;
     std::vector<point3d> last_positions;
 
+    int update_count = 0;
+    struct Disturbance { int step, agent; point3d offset; };
+    std::vector<Disturbance> disturbances;
+    void parseDisturbances() {
+        std::stringstream all(param.multisim_disturbance);
+        std::string item;
+        while (std::getline(all, item, ';')) {
+            if (item.empty()) continue;
+            Disturbance d{};
+            float x = 0, y = 0, z = 0;
+            if (std::sscanf(item.c_str(), "%d:%d:%f,%f,%f", &d.step, &d.agent, &x, &y, &z) != 5 || d.agent < 0 || d.agent >= mission.qn)
+                throw std::invalid_argument("[MultiSyncSimulator] multisim/disturbance expects <step>:<agent>:<dx>,<dy>,<dz>;...");
+            d.offset = point3d(x, y, z);
+            disturbances.push_back(d);
+        }
+    }
+    point3d disturbanceOffset(int step, int qi) const {
+        point3d o(0, 0, 0);
+        for (const Disturbance& d : disturbances) if (d.step == step && d.agent == qi) o = o + d.offset;
+        return o;
+    }
     void initializeTimer() { sim_start_time = 0; sim_current_time = 0; }
     void doStep() { sim_current_time += param.multisim_time_step; }
 
-    // src/multi_sync_simulator.cpp:190-318: every agent's next initial state is its trajectory at t = time_step
+    // src/multi_sync_simulator.cpp:190-318: every agent's next initial state is its trajectory at t = time_step —
+    // unless its observed position is farther than reset_threshold from where it should be NOW: then the agent restarts at
+    // rest from the observed position (:229-246) and the engine's checks take it from there (slack variables, corridor).
+    // The reference reads the observed pose from tf; here it is the ideal one plus the offsets of multisim/disturbance.
     void update() {
         for (int qi = 0; qi < mission.qn; qi++) {
             State s;
             if (initial_update) s.position = mission.agents[qi].start_position;        // at rest at the start point
-            else s = agents[qi]->getFutureStateMsg(param.multisim_time_step);
+            else {
+                const State ideal_curr = agents[qi]->getCurrentStateMsg();
+                const point3d real = ideal_curr.position + disturbanceOffset(update_count, qi);
+                if ((ideal_curr.position - real).norm() > param.multisim_reset_threshold) {
+                    s.position = real;                                                 // velocity, acceleration: zero
+                    std::cerr << "[MultiSyncSimulator] agent " << qi << ": diff between ideal and real is too big\n";
+                    n_resets++;
+                } else s = agents[qi]->getFutureStateMsg(param.multisim_time_step);
+            }
             ideal_states[qi] = s;
             agents[qi]->setCurrentState(s);
             agents[qi]->updatePlannerState(PlannerState::GOTO);
         }
+        update_count++;
         if (initial_update) {
             last_positions.resize(mission.qn);
             for (int qi = 0; qi < mission.qn; qi++) last_positions[qi] = mission.agents[qi].start_position;
@@ -146,7 +180,8 @@ private:
                   << "[MultiSyncSimulator] planning time per agent: " << planning_time.total_planning_time.average << "\n"
                   << "[MultiSyncSimulator] goal planning time per agent: " << planning_time.goal_planning_time.average << "\n"
                   << "[MultiSyncSimulator] safety ratio between agent: " << safety_ratio_agent << "\n"
-                  << "[MultiSyncSimulator] is_collided: " << is_collided << " qp_failures: " << qp_failures << "\n";
+                  << "[MultiSyncSimulator] is_collided: " << is_collided << " qp_failures: " << qp_failures
+                  << " state_resets: " << n_resets << "\n";
         if (summary_file.empty()) return;
         std::ifstream in(summary_file);
         const bool header = !in || in.peek() == std::ifstream::traits_type::eof();
@@ -174,7 +209,7 @@ private:
 int main(int argc, char** argv) {
     try {
         Param param = Param::simulationLaunch();
-        param.multisim_max_noise = 0.0;
+        param.multisim_max_noise = 0.0;         // multisim/max_noise=0.02 multisim/noise_seed=<n> for the launch file's value
         param.world_use_octomap = false;
         std::string result, summary, world;
         for (int i = 1; i < argc; i++) {
@@ -189,7 +224,8 @@ int main(int argc, char** argv) {
             }
         }
         Mission mission;
-        mission.initialize(param.mission_file_name, param.multisim_max_noise, param.world_dimension, param.world_z_2d, world);
+        mission.initialize(param.mission_file_name, param.multisim_max_noise, param.world_dimension, param.world_z_2d, world,
+                           param.multisim_noise_seed);
         MultiSyncSimulator sim(param, mission);
         if (param.world_use_octomap) {
             if (world.empty()) throw std::invalid_argument("world/use_octomap needs world/file_name");

@@ -3,6 +3,7 @@
 #pragma once
 #include <cmath>
 #include <fstream>
+#include <random>
 #include <sstream>
 #include <stdexcept>
 #include <string>
@@ -90,6 +91,10 @@ struct Param {
     int multisim_planning_rate = -1, multisim_qn = 2;
     double multisim_time_step = 0.1;
     double multisim_max_noise = 0.0;
+    long long multisim_noise_seed = -1;     // not in the reference: >= 0 seeds Mission::addNoise (the reference uses std::random_device)
+    // not in the reference (it listens to tf): externally observed poses for MultiSyncSimulator::update, as
+    // "<step>:<agent>:<dx>,<dy>,<dz>;..." — at that update the observed position of the agent is its ideal one + the offset
+    std::string multisim_disturbance;
     int multisim_max_planner_iteration = 1000;
     bool multisim_save_result = false, multisim_experiment = false;
     double multisim_record_time_step = 0.1, multisim_reset_threshold = 0.1;
@@ -129,6 +134,8 @@ struct Param {
         else if (key == "world/resolution") world_resolution = d();
         else if (key == "multisim/time_step") multisim_time_step = d();
         else if (key == "multisim/max_noise") multisim_max_noise = d();
+        else if (key == "multisim/noise_seed") multisim_noise_seed = std::stoll(v);
+        else if (key == "multisim/disturbance") multisim_disturbance = v;
         else if (key == "multisim/max_planner_iteration") multisim_max_planner_iteration = i();
         else if (key == "multisim/save_result") multisim_save_result = b();
         else if (key == "multisim/record_time_step") multisim_record_time_step = d();
@@ -167,8 +174,18 @@ struct Mission {
     point3d world_min, world_max;
     std::string mission_file_name, world_file_name;
 
+    // src/mission.cpp:386-395: every desired goal moves by U(0,1) * max_noise per axis (float draws from an mt19937; the
+    // reference seeds it from std::random_device, here a seed >= 0 makes the run repeatable)
+    void addNoise(double max_noise, int dimension, long long seed = -1) {
+        std::random_device rd;
+        std::mt19937 gen(seed >= 0 ? (std::mt19937::result_type)seed : rd());
+        std::uniform_real_distribution<float> dis(0, 1);
+        for (int qi = 0; qi < qn; qi++)
+            for (int k = 0; k < dimension; k++) agents[qi].desired_goal_position(k) += dis(gen) * max_noise;
+    }
+
     bool initialize(const std::string& file, double max_noise = 0.0, int world_dimension = 3, double world_z_2d = 1.0,
-                    const std::string& world_file = "") {
+                    const std::string& world_file = "", long long noise_seed = -1) {
         mission_file_name = file; world_file_name = world_file;
         std::ifstream in(file);
         if (!in) throw std::invalid_argument("[Mission] There is no such file: " + file);
@@ -201,7 +218,8 @@ struct Mission {
         }
         on = doc.has("obstacles") ? (int)doc["obstacles"].size() : 0;
         if (on != 0) throw std::invalid_argument("[Mission] dynamic obstacles are outside the GPU path (all shipped missions have none)");
-        if (max_noise != 0.0) throw std::invalid_argument("[Mission] multisim/max_noise must be 0 (the reference's addNoise is non-deterministic)");
+        addNoise(max_noise, world_dimension, noise_seed);                               // src/mission.cpp:317
+        for (Agent& A : agents) A.current_goal_position = A.desired_goal_position;
         return true;
     }
 };

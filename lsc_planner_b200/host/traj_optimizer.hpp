@@ -52,7 +52,11 @@ inline EnginePtr createEngine(const Param& param, const Mission& mission, int de
     lscgpu_engine* raw = nullptr;
     if (lscgpu_create(&p, mission.qn, ac.data(), device, &raw) != LSCGPU_OK)
         throw std::invalid_argument(std::string("[lscgpu] ") + lscgpu_last_error());
-    return EnginePtr(raw, EngineDeleter());
+    EnginePtr engine(raw, EngineDeleter());
+    // weight of the slack variables a state reset brings into the QPs (src/traj_optimizer.cpp:383-390)
+    if (lscgpu_set_slack_collision_weight(raw, param.slack_collision_weight) != LSCGPU_OK)
+        throw std::invalid_argument(std::string("[lscgpu] ") + lscgpu_last_error());
+    return engine;
 }
 
 class TrajOptimizer {
@@ -97,8 +101,12 @@ public:
         const int32_t obs_offset[2] = {0, n_obs};
         double x[LSCGPU_TRAJ_FLOATS], cost = 0;
         int32_t status = 0, iterations = 0;
-        const int rc = lscgpu_qp_solve_batch(engine.get(), 1, &agent_index, state, goal, sfc.empty() ? nullptr : sfc.data(),
-                                             obs_offset, normal.data(), point.data(), d.data(), x, &cost, &status, &iterations);
+        // obstacles of obs_slack_indices get slack variables (src/traj_optimizer.cpp:268,317-326,455-457)
+        std::vector<uint8_t> obs_slack((size_t)std::max(n_obs, 1), 0);
+        for (int oi : constraints.getSlackIndices()) if (oi >= 0 && oi < n_obs) obs_slack[oi] = 1;
+        const int rc = lscgpu_qp_solve_batch_slack(engine.get(), 1, &agent_index, state, goal, sfc.empty() ? nullptr : sfc.data(),
+                                                   obs_offset, normal.data(), point.data(), d.data(), obs_slack.data(), x, &cost,
+                                                   &status, &iterations, nullptr);
         if (rc != LSCGPU_OK) throw std::invalid_argument(std::string("[lscgpu] ") + lscgpu_last_error());
         if (status != LSCGPU_QP_OK) throw PlanningReport::QPFAILED;          // src/traj_optimizer.cpp:143,152
         for (int k = 0; k < dim; k++)

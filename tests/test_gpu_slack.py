@@ -142,3 +142,42 @@ def test_closed_loop_after_reset_resident():
     assert e.reset_state().nonzero()[0].tolist() == [5]
     e.reset()
     assert not e.reset_state().any()
+
+
+def test_reference_lp_dump_with_slack(golden_dir):
+    """The reference's only recorded QP (log/QPmodel.lp) is infeasible — CPLEX said so, and so do the oracle and the engine.
+    Put its conflicting neighbour (obstacle 3) into obs_slack_indices, as the reference does after a disturbance: the QP
+    is solved, the operator-level entry (TrajOptimizer::solve with CollisionConstraints::getSlackIndices) agrees with the
+    oracle and with the independent NNLS solve of the extended problem on x, eps and the objective."""
+    import lsc_planner_b200 as L
+    import qp_pyref as R
+    from test_gpu_parity import _lp_problem
+    g = np.load(os.path.join(golden_dir, "qpmodel_lp.npz"))
+    agents = [L.AgentType(max_vel=tuple(g["vmax"]), max_acc=tuple(g["amax"]))]
+    lb, ub = g["lb"], g["ub"]
+    wmin = [lb[3], lb[33], lb[63]]; wmax = [ub[3], ub[33], ub[63]]
+    e = L.ReplanEngine(1, L.Param(world_min=wmin, world_max=wmax), agents)
+    T = O.Tables()
+    normal, point, d, rows = _lp_problem(g, None)
+    n_obs = len(normal)
+    st = np.zeros(9); st[:3] = g["state"][0]
+    for w in (1.0, 100000.0):
+        e.set_slack_collision_weight(w)
+        for members in ([3], list(range(n_obs))):
+            obs_slack = np.zeros(n_obs, np.uint8); obs_slack[members] = 1
+            r = e.qp_solve_batch([0], st, g["goal"], [0, n_obs], normal, point, d, obs_slack=obs_slack)
+            row_slack = np.repeat(obs_slack, 5).astype(np.int32)              # rows are (obstacle, segment) entries
+            ro = T.solve_slack(g["state"], g["goal"], int(g["ts"]), lb, ub, g["vmax"], g["amax"], rows, row_slack, w)
+            assert r["status"][0] == 0 and ro["status"] == 0
+            assert np.abs(r["x"][0] - ro["x"]).max() <= 1e-6
+            assert np.abs(r["eps"].reshape(-1) - ro["eps"]).max() <= 1e-6 and r["eps"].min() < 0 and r["eps"].max() <= 0
+            assert abs(r["cost"][0] - ro["cost"]) <= 1e-8 * max(1.0, abs(ro["cost"]))
+            D = T.dense(g["state"], g["goal"], int(g["ts"]), lb, ub, g["vmax"], g["amax"], rows)
+            E, idx = R.with_slack(D, rows, row_slack, w)
+            xe, obj, stt = R.solve_ldp(E)
+            assert stt == "ok"
+            assert np.abs(r["x"][0] - xe[:90]).max() <= 1e-6 and abs(r["cost"][0] - obj) <= 1e-7 * max(1.0, abs(obj))
+            assert np.abs(r["eps"].reshape(-1)[idx] - xe[90:]).max() <= 1e-6
+    # no member: the plain entry, infeasible as recorded
+    r = e.qp_solve_batch([0], st, g["goal"], [0, n_obs], normal, point, d, obs_slack=np.zeros(n_obs, np.uint8))
+    assert r["status"][0] == 1 and not r["eps"].any()

@@ -81,3 +81,43 @@ def test_simulator_matches_oracle_closed_loop(built, tmp_path, mission):
     # which the reference's strict `< 1` test already flags as is_collided; a real collision would be far below
     assert s[4] >= 1.0 - 1e-4
     assert s[3] == (1 if s[4] < 1.0 else 0)
+
+
+@pytest.mark.gpu
+def test_simulator_with_external_disturbances(built, tmp_path):
+    """Observed poses that differ from the ideal ones by more than multisim/reset_threshold (the reference reads them from
+    tf, src/multi_sync_simulator.cpp:207-246; lsc_sim takes them from multisim/disturbance): the agent restarts at rest
+    from the observed position, the planners switch to the slack-variable QPs — same recorded positions as the oracle's
+    closed loop under the same rule, no failed QP."""
+    import lsc_planner_b200 as L
+    import oracle_lib as O
+    mission = "multi_circle20.json"
+    scn = L.scenarios.load_mission(os.path.join(MISSIONS, mission))
+    dist = [(10, 3, (0.3, 0.35, 0.0)), (30, 11, (0.0, -0.2, 0.15)), (31, 3, (0.05, 0.0, 0.0))]     # the last one is below the threshold
+    spec = ";".join(f"{s}:{a}:{o[0]},{o[1]},{o[2]}" for s, a, o in dist)
+    res = str(tmp_path / "result.csv")
+    r = subprocess.run([os.path.join(built, "lsc_sim"), "mission=" + os.path.join(MISSIONS, mission), "mode/goal=static",
+                        "multisim/record_time_step=0.2", "multisim/max_planner_iteration=61", "multisim/disturbance=" + spec,
+                        "result=" + res], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "state_resets: 2" in r.stdout and "qp_failures: 0" in r.stdout, r.stdout
+    rec = _read_result_csv(res, scn.n)
+    sw = O.Swarm(scn.n, scn.world_min, scn.world_max, radius=[a.radius for a in scn.agents],
+                 downwash=[a.downwash for a in scn.agents], vmax=[a.max_vel for a in scn.agents],
+                 amax=[a.max_acc for a in scn.agents], v_nom=[a.nominal_velocity for a in scn.agents])
+    sw.set_state(scn.start); sw.set_goals(scn.goal); sw.set_slack_weight(1e5)      # launch/simulation.launch:69
+    assert len(rec) == 60
+    for k in range(len(rec)):
+        if k > 0:
+            ideal_curr = sw.state()[0].copy()
+            sw.advance()
+            pos, vel, acc = sw.state()
+            for s, a, o in dist:
+                if s == k and np.linalg.norm(np.float32(o)) > 0.15:
+                    pos[a] = ideal_curr[a] + np.float32(o); vel[a] = 0; acc[a] = 0
+            sw.set_state(pos, vel, acc)
+        pos, _, _ = sw.state()
+        assert np.abs(rec[k, :, 2:5] - pos).max() <= 2e-3, k
+        sw.step()
+        assert (sw.qp()["status"] == 0).all()
+    assert sw.reset_ever().nonzero()[0].tolist() == [3, 11]
