@@ -160,9 +160,9 @@ struct lscgpu_engine {
     NcclComm comm = nullptr;
     int rank = 0, n_ranks = 1, block = 0;
     // the step as a CUDA graph (steps with planner_seq >= 2 are identical launches)
-    cudaGraphExec_t graph[2] = {nullptr, nullptr};   // [0] 256-thread, [1] 128-thread configuration
+    cudaGraphExec_t graph[3] = {nullptr, nullptr, nullptr};   // [0] 256-thread, [1] 128-thread, [2] 512-thread configuration
     bool graph_failed = false;
-    int graph_launches[2] = {0, 0};
+    int graph_launches[3] = {0, 0, 0};
     // instrumentation: steps enqueued since the last synchronize
     struct StepEvents { cudaEvent_t ev[7]; };   // begin, predict|, plan|, exchange|, commit|, sfc[ ]sfc
     std::vector<StepEvents> ev_pool;    // per-kernel events of every pending step (profiling mode)
@@ -315,7 +315,7 @@ extern "C" int lscgpu_create(const lscgpu_params* p, int n_agents, const lscgpu_
     CUB(cudaEventCreateWithFlags(&e->ev_sfc, cudaEventDisableTiming));
     if (const char* v = getenv("LSCGPU_LPT_ORDER")) e->lpt_order = atoi(v) != 0;
     if (const char* v = getenv("LSCGPU_GRAPH")) e->use_graph = atoi(v) != 0;
-    if (const char* v = getenv("LSCGPU_PLAN_THREADS")) { const int t = atoi(v); e->plan_threads = t == 128 ? 128 : (t == 256 ? 256 : 0); }
+    if (const char* v = getenv("LSCGPU_PLAN_THREADS")) { const int t = atoi(v); e->plan_threads = (t == 128 || t == 256 || t == 512) ? t : 0; }
     if (const char* v = getenv("LSCGPU_WIDE_KEPT")) e->wide_kept = atoi(v);
     if (const char* v = getenv("LSCGPU_ROW_CAP")) e->row_cap_forced = std::min(std::max(atoi(v), 0), 2560) / 32 * 32;
     if (const char* v = getenv("LSCGPU_SFC_WAIT_CYCLES")) e->sfc_wait_cycles = atoll(v);
@@ -613,7 +613,7 @@ static int enqueue_step_kernels(lscgpu_engine* e, int planner_seq, int threads, 
     if (dealt) L.agent_base = e->rank;
     L.pred = e->d_pred; L.predT = e->d_predT; L.predZs = e->d_predZs; L.consts = e->d_consts; L.rdw = e->d_rdw; L.T = e->d_tables;
     L.state9 = e->d_state9; L.goal3 = e->d_goal3; L.ts = e->d_ts; L.sphere = e->d_sphere; L.tsphere = e->d_tsphere; L.reach = e->d_reach;
-    L.row_cap = e->row_cap_forced >= 0 ? e->row_cap_forced : (threads == 128 ? 256 : 1024);
+    L.row_cap = e->row_cap_forced >= 0 ? e->row_cap_forced : (threads == 128 ? 256 : (threads == 512 ? 2048 : 1024));
     L.P_pad = e->P_pad; L.mirror_rows = e->mirror_rows ? 1 : 0;
     L.kept_step = e->d_kept_step;
     L.rows = e->d_rows; L.kept = e->d_kept; L.kept_count = e->d_kept_count; L.safe = e->d_safe;
@@ -688,8 +688,10 @@ static int step_device(lscgpu_engine* e) {
         // one wave of wide blocks (two per SM) holds every agent: the step is the slowest agent's chain, and eight warps
         // shorten it (multi-GPU shares); otherwise four narrow blocks per SM overlap more QP chains
         threads = (n_plan <= 2 * e->n_sm || kept_last / n_plan >= e->wide_kept) ? 256 : 128;
+        // at most one agent per SM (small shares of a multi-GPU job): sixteen warps per agent
+        if (n_plan <= e->n_sm) threads = 512;
     }
-    const int gi = threads == 128 ? 1 : 0;
+    const int gi = threads == 128 ? 1 : (threads == 512 ? 2 : 0);
     const bool graphable = e->use_graph && !e->graph_failed && !prof && !e->qp_debug && seq >= 2;
     if (graphable && !e->graph[gi]) {
         cudaGraph_t g = nullptr;

@@ -29,7 +29,7 @@
 namespace lscgpu {
 
 constexpr int kBatchThreads = 256;       // k_qp_batch
-constexpr int kMaxPlanWarps = 8;
+constexpr int kMaxPlanWarps = 16;
 
 // LSC-phase scratch (beside QpShared; the survivor queue aliases QpShared::Q, which the QP only touches afterwards)
 struct LscShared {
@@ -48,12 +48,15 @@ struct LscShared {
 
 __host__ __device__ constexpr size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 struct PlanSmemLayout {
-    size_t qp, lists, lsc, nr, rhs, gate, seg, total;
+    size_t qp, lists, lsc, queue, nr, rhs, gate, seg, total;
     __host__ __device__ PlanSmemLayout(int cap, int threads, size_t qp_bytes = sizeof(QpShared)) {
         qp = 0;
         lists = align16(qp + qp_bytes);
         lsc = align16(lists + sizeof(int) * (threads / 32) * kWarpList);
-        nr = align16(lsc + sizeof(LscShared));
+        // survivor queue of the LSC phase: threads * (kM + 1) entries. Up to 256 threads it lives in Q / W (24 KB, untouched
+        // until the QP starts); the 512-thread configuration gets its own region
+        queue = align16(lsc + sizeof(LscShared));
+        nr = align16(queue + (threads > 256 ? sizeof(int2) * (size_t)threads * (kM + 1) : 0));
         rhs = nr + sizeof(float4) * (size_t)cap;
         gate = rhs + sizeof(double2) * 3 * (size_t)cap;
         seg = gate + sizeof(double) * (size_t)cap;
@@ -222,7 +225,7 @@ __device__ __forceinline__ int lsc_phase(const PlanLaunch& L, int a, const RowSr
 // swarm — once any agent was reset, every planner's obs_slack_indices holds it — so both kernels are launched every step
 // and the one the step does not need returns at once (*L.any_reset, set by k_predict).
 template <int kPlanThreads, bool kSfc, bool kSlack>
-__global__ void __launch_bounds__(kPlanThreads, kSlack ? 2 : 512 / kPlanThreads) k_agent_plan(PlanLaunch L) {
+__global__ void __launch_bounds__(kPlanThreads, kSlack ? (kPlanThreads > 256 ? 1 : 2) : 512 / kPlanThreads) k_agent_plan(PlanLaunch L) {
     using SH = typename std::conditional<kSlack, QpSharedSlack, QpShared>::type;
     if (L.any_reset && (*L.any_reset != 0) != kSlack) return;
     const int row_cap = kSlack ? L.row_cap_slack : L.row_cap;
@@ -270,7 +273,8 @@ __global__ void __launch_bounds__(kPlanThreads, kSlack ? 2 : 512 / kPlanThreads)
 
     // ---- phase 1: corridors -------------------------------------------------------------------------------------
     int n_kept = 0, gjk_it = 0;
-    int2* queue = reinterpret_cast<int2*>(S.Q);        // kPlanThreads * (kM + 1) entries <= 12 KB of Q + W's 24 KB
+    int2* queue = kPlanThreads > 256 ? reinterpret_cast<int2*>(smem + lay.queue)
+                                     : reinterpret_cast<int2*>(S.Q);        // kPlanThreads * (kM + 1) entries <= Q + W
     if (n_obs > 0) n_kept = lsc_phase<kPlanThreads, SH>(L, a, rows, X, S, queue, gjk_it);
     if (tid == 0) X.t_lsc = clock64() - t_start;
     if (kSfc && warp == 0) {
@@ -428,6 +432,8 @@ cudaError_t configure_agent_plan() {
     if (rc == cudaSuccess) rc = configure_one<256, false, false>();
     if (rc == cudaSuccess) rc = configure_one<128, true, false>();
     if (rc == cudaSuccess) rc = configure_one<128, false, false>();
+    if (rc == cudaSuccess) rc = configure_one<512, true, false>();
+    if (rc == cudaSuccess) rc = configure_one<512, false, false>();
     if (rc == cudaSuccess) rc = configure_one<256, true, true>();
     if (rc == cudaSuccess) rc = configure_one<256, false, true>();
     if (rc == cudaSuccess) rc = configure_qp_batch();
@@ -440,6 +446,9 @@ void launch_agent_plan(const PlanLaunch& L, cudaStream_t s) {
     if (L.threads == 128) {
         if (L.use_sfc) k_agent_plan<128, true, false><<<L.n_blocks, 128, smem, s>>>(L);
         else k_agent_plan<128, false, false><<<L.n_blocks, 128, smem, s>>>(L);
+    } else if (L.threads == 512) {
+        if (L.use_sfc) k_agent_plan<512, true, false><<<L.n_blocks, 512, smem, s>>>(L);
+        else k_agent_plan<512, false, false><<<L.n_blocks, 512, smem, s>>>(L);
     } else {
         if (L.use_sfc) k_agent_plan<256, true, false><<<L.n_blocks, 256, smem, s>>>(L);
         else k_agent_plan<256, false, false><<<L.n_blocks, 256, smem, s>>>(L);

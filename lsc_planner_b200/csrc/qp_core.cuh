@@ -79,8 +79,8 @@ struct QpSharedT {
     double inv_dyn[kM * 9];     // 1 / whitened length of the velocity (j<5) / acceleration (j>=5) rows
     double lb[15], ub[15], vmax[3], amax[3];
     double travelled;           // path length of the iterate in the whitened space
-    double best_mu[8];          // per-warp pricing result
-    int best_id[8];
+    double best_mu[16];         // per-warp pricing result
+    int best_id[16];
     int act[NRX + 1];
     int stop;                   // 0 run, 1 finished/failed (set by warp 0)
     unsigned long long g_bar;   // mbarrier: completion of the bulk copy of G

@@ -158,3 +158,23 @@ def test_operator_batch_matches_swarm_step():
     x = r["x"].reshape(scn.n, 3, 5, 6).transpose(0, 2, 3, 1)
     assert np.abs(x - out["traj"]).max() <= 2e-6
     assert np.abs(r["cost"] - out["qp_cost"]).max() <= 1e-6 * max(1.0, np.abs(out["qp_cost"]).max())
+
+
+def test_results_do_not_depend_on_the_block_size(monkeypatch):
+    """k_agent_plan runs with 128, 256 or 512 threads per agent depending on the share of the swarm an engine plans; the
+    row order is canonical, so the trajectories must be bit-identical whichever configuration is forced."""
+    import lsc_planner_b200 as L
+    scn = L.scenarios.circle_swap(96)
+    outs = {}
+    for threads in (128, 256, 512):
+        monkeypatch.setenv("LSCGPU_PLAN_THREADS", str(threads))
+        e = L.ReplanEngine(scn.n, L.Param(world_min=scn.world_min, world_max=scn.world_max), scn.agents)
+        e.set_states(scn.start); e.set_goals(scn.goal)
+        e.replan_resident(70)
+        outs[threads] = e.fetch()
+        e.close()
+    for threads in (256, 512):
+        assert np.array_equal(outs[128]["traj"].view(np.uint32), outs[threads]["traj"].view(np.uint32)), threads
+        assert np.array_equal(outs[128]["qp_status"], outs[threads]["qp_status"])
+        assert np.array_equal(outs[128]["qp_iterations"], outs[threads]["qp_iterations"])
+    assert (outs[128]["lsc_pairs_kept"] > 0).any()
