@@ -494,6 +494,9 @@ def run_ours(args):
                    "rows_priced_per_replan": st["qp_rows_priced"] / max(n_local * n_steps_prof, 1),
                    "pricing_passes_per_replan": st["qp_full_passes"] / max(n_local * n_steps_prof, 1),
                    "gjk_iterations_per_hull": st["gjk_iterations"] / max(st["lsc_pairs"], 1),
+                   "warm_start": {"tried_fraction": st["qp_warm_tried"] / max(n_local * n_steps_prof, 1),
+                                  "accepted_of_tried": st["qp_warm_accepted"] / max(st["qp_warm_tried"], 1),
+                                  "rows_per_accepted": st["qp_warm_rows"] / max(st["qp_warm_accepted"], 1)},
                    "failed_last_step": qp_fail, "qp_failed_fraction": qp_fail / n},
             "sharded_check": sharded_check,
         }

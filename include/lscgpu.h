@@ -62,8 +62,13 @@ enum {
     LSCGPU_FLAG_SLACK_MODE = 4,        /* the QP carried slack variables (some agent of the swarm was reset before or in this
                                           step; src/traj_optimizer.cpp:317-326,383-390,455-457) */
     LSCGPU_FLAG_SLACK_USED = 8,        /* ... and at least one of them is < 0 at the solution */
-    LSCGPU_FLAG_SLACK_OVERFLOW = 16    /* the QP needed more slack variables than the kernel holds per agent (25): reported
+    LSCGPU_FLAG_SLACK_OVERFLOW = 16,   /* the QP needed more slack variables than the kernel holds per agent (25): reported
                                           as LSCGPU_QP_MAXITER, the previous trajectory is kept */
+    LSCGPU_FLAG_WARM_START = 32,       /* the QP started from the bound / dynamic-limit rows active at the agent's previous
+                                          solve (accepted only when all their multipliers are >= 0; the minimiser is the same) */
+    LSCGPU_FLAG_IN_BAND = 64           /* at the returned solution some row is violated by more than 1e-9 (and, by construction,
+                                          at most the feasibility tolerance 1e-6, CPLEX's EpRHS): like CPLEX's, the solution is
+                                          then defined only up to such rows and may depend on the pivoting order at that level */
 };
 
 /* The subset of Param (include/param.hpp, defaults src/param.cpp:4-107) that the hot path reads. */
@@ -281,6 +286,9 @@ typedef struct lscgpu_step_stats {
     float ms_steps;                 /* sum over the steps of (last kernel end - first kernel start): like ms_total without
                                        whatever the caller enqueued on the stream between steps */
     float reserved_;
+    /* QP warm starts (all local agents): solves that had candidates from the agent's previous solve, solves whose
+     * candidates were accepted as the starting point, and the rows those put into the working set without an iteration */
+    int64_t qp_warm_tried, qp_warm_accepted, qp_warm_rows;
 } lscgpu_step_stats;
 int lscgpu_get_step_stats(lscgpu_engine* e, lscgpu_step_stats* out);
 /* enable per-kernel event timing (event records between the kernels of every step; off by default) */

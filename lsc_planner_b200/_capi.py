@@ -37,7 +37,8 @@ class StepStats(C.Structure):
                 ("ms_sfc", C.c_float), ("ms_reserved1_", C.c_float), ("ms_exchange", C.c_float), ("ms_commit", C.c_float),
                 ("kernel_launches", C.c_int32), ("lsc_pairs", C.c_int64), ("lsc_pairs_kept", C.c_int64), ("gjk_iterations", C.c_int64),
                 ("qp_rows_priced", C.c_int64), ("qp_iterations", C.c_int64), ("qp_full_passes", C.c_int64),
-                ("ms_steps", C.c_float), ("reserved_", C.c_float)]
+                ("ms_steps", C.c_float), ("reserved_", C.c_float),
+                ("qp_warm_tried", C.c_int64), ("qp_warm_accepted", C.c_int64), ("qp_warm_rows", C.c_int64)]
 
 
 # numpy views of lscgpu_agent_in / lscgpu_agent_out (C layout, natural alignment)

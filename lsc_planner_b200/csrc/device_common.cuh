@@ -43,7 +43,19 @@ struct StepCounters {
     unsigned long long full_passes;
     unsigned long long gjk_iterations;
     unsigned long long kept_pairs;
+    unsigned long long warm_tried, warm_accepted, warm_rows;     // QP warm starts: attempted, accepted, rows they activated
 };
+
+// One slot of the step's gather buffer (what travels between the GPUs of a job): the public result record plus the
+// bounds / dynamic-limit rows active at the solution, the next step's warm-start candidates (replicated like the record:
+// any rank may plan the agent next).
+constexpr int kActSlots = 40;         // [0, 39): row ids, [39]: count
+struct __align__(16) GatherSlot {
+    lscgpu_agent_out rec;
+    unsigned short act[kActSlots];
+    int pad[4];
+};
+static_assert(sizeof(GatherSlot) % 16 == 0, "gather slot must be a multiple of 16 bytes");
 
 // ---- small float3/double3 helpers with explicit IEEE roundings ----------------------------------
 // The reference's geometry is octomap::point3d = float32 with float arithmetic.

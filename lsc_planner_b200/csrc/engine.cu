@@ -135,7 +135,9 @@ struct lscgpu_engine {
     AgentConstDev* d_consts = nullptr;
     float2* d_rdw = nullptr;         // [N] (radius, downwash * radius) in float: all the culling pass needs
     lscgpu_agent_in* d_in = nullptr;
-    lscgpu_agent_out* d_gather = nullptr;  // [n_slots] records in scheduling order, rank-major: the all-gather buffer
+    GatherSlot* d_gather = nullptr;        // [n_slots] records (+ active rows) in scheduling order, rank-major: the all-gather buffer
+    unsigned short* d_act_prev = nullptr;  // [N][kActSlots] rows active at every agent's previous solve (warm-start candidates)
+    bool warm_start = true;
     lscgpu_agent_out* d_res = nullptr;     // [N] the same records in agent order (k_commit)
     int n_slots = 0;
     float *d_traj = nullptr, *d_pred = nullptr, *d_predT = nullptr, *d_predZs = nullptr, *d_boxes = nullptr;
@@ -209,7 +211,7 @@ static int alloc_gather(lscgpu_engine* e, int n_slots) {
     if (n_slots <= e->n_slots) return LSCGPU_OK;
     cudaFree(e->d_gather);
     e->d_gather = nullptr; e->n_slots = 0;
-    CU(cudaMalloc(&e->d_gather, sizeof(lscgpu_agent_out) * (size_t)n_slots));
+    CU(cudaMalloc(&e->d_gather, sizeof(GatherSlot) * (size_t)n_slots));
     e->n_slots = n_slots;
     return LSCGPU_OK;
 }
@@ -232,6 +234,7 @@ extern "C" void lscgpu_destroy(lscgpu_engine* e) {
     if (e->ev_sfc) cudaEventDestroy(e->ev_sfc);
     cudaFree(e->d_rdw); cudaFree(e->d_audit_pos); cudaFree(e->d_audit_ratio); cudaFree(e->d_audit_closest); cudaFree(e->d_dbg);
     cudaFree(e->d_tables); cudaFree(e->d_consts); cudaFree(e->d_in); cudaFree(e->d_gather); cudaFree(e->d_res); cudaFree(e->d_traj);
+    cudaFree(e->d_act_prev);
     cudaFree(e->d_pred); cudaFree(e->d_predT); cudaFree(e->d_predZs); cudaFree(e->d_boxes); cudaFree(e->d_state9); cudaFree(e->d_goal3);
     cudaFree(e->d_last_cost); cudaFree(e->d_ts); cudaFree(e->d_flags); cudaFree(e->d_init_sfc); cudaFree(e->d_goal_kind); cudaFree(e->d_counters);
     cudaFree(e->dm.sqdist); cudaFree(e->dm.sat); cudaFree(e->d_sphere); cudaFree(e->d_tsphere); cudaFree(e->d_reach);
@@ -254,7 +257,8 @@ static int reset_state(lscgpu_engine* e) {
     CU(cudaMemsetAsync(e->d_last_cost, 0, sizeof(double) * N, e->stream));
     CU(cudaMemsetAsync(e->d_in, 0, sizeof(lscgpu_agent_in) * N, e->stream));
     CU(cudaMemsetAsync(e->d_res, 0, sizeof(lscgpu_agent_out) * N, e->stream));
-    CU(cudaMemsetAsync(e->d_gather, 0xff, sizeof(lscgpu_agent_out) * (size_t)e->n_slots, e->stream));   // agent_id = -1: empty slot
+    CU(cudaMemsetAsync(e->d_gather, 0xff, sizeof(GatherSlot) * (size_t)e->n_slots, e->stream));   // agent_id = -1: empty slot
+    CU(cudaMemsetAsync(e->d_act_prev, 0, sizeof(unsigned short) * kActSlots * N, e->stream));     // no candidates: cold starts
     CU(cudaMemsetAsync(e->d_block_of, 0xff, sizeof(int) * N, e->stream));
     CU(cudaMemsetAsync(e->d_reset_ever, 0, N, e->stream));                              // obs_slack_indices start empty
     CU(cudaMemsetAsync(e->d_any_reset, 0, sizeof(int), e->stream));
@@ -320,6 +324,7 @@ extern "C" int lscgpu_create(const lscgpu_params* p, int n_agents, const lscgpu_
     if (const char* v = getenv("LSCGPU_ROW_CAP")) e->row_cap_forced = std::min(std::max(atoi(v), 0), 2560) / 32 * 32;
     if (const char* v = getenv("LSCGPU_SFC_WAIT_CYCLES")) e->sfc_wait_cycles = atoll(v);
     if (const char* v = getenv("LSCGPU_SLACK_KERNEL")) e->slack_kernel = atoi(v) != 0;     // 0: measure the step without its launch
+    if (const char* v = getenv("LSCGPU_WARM_START")) e->warm_start = atoi(v) != 0;         // 0: every QP starts cold
     e->qp_debug = getenv("LSCGPU_QP_DEBUG") != nullptr;
     CUB(cudaEventCreate(&e->ev_begin));
     CUB(cudaEventCreate(&e->ev_end));
@@ -360,6 +365,7 @@ extern "C" int lscgpu_create(const lscgpu_params* p, int n_agents, const lscgpu_
     }
     CUB(cudaMalloc(&e->d_in, sizeof(lscgpu_agent_in) * N));
     CUB(cudaMalloc(&e->d_res, sizeof(lscgpu_agent_out) * N));
+    CUB(cudaMalloc(&e->d_act_prev, sizeof(unsigned short) * kActSlots * N));
     CUB(cudaMalloc(&e->d_order, sizeof(int) * N));
     CUB(cudaMalloc(&e->d_block_of, sizeof(int) * N));
     CUB(cudaMalloc(&e->d_kept_step, sizeof(int)));
@@ -508,7 +514,7 @@ extern "C" int lscgpu_set_shard(lscgpu_engine* e, int a0, int a1) {
     CU(cudaSetDevice(e->device));
     e->a0 = a0; e->a1 = a1;
     // slots of the gather buffer beyond the shard must read "empty"
-    CU(cudaMemsetAsync(e->d_gather, 0xff, sizeof(lscgpu_agent_out) * (size_t)e->n_slots, e->stream));
+    CU(cudaMemsetAsync(e->d_gather, 0xff, sizeof(GatherSlot) * (size_t)e->n_slots, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     return alloc_rows(e);
 }
@@ -541,7 +547,7 @@ extern "C" int lscgpu_nccl_init(lscgpu_engine* e, const uint8_t id_bytes[128], i
     e->a0 = 0; e->a1 = e->N;                             // every rank may plan any agent: the LPT order is dealt out
     const int r1 = alloc_gather(e, e->block * n_ranks);
     if (r1 != LSCGPU_OK) return r1;
-    CU(cudaMemset(e->d_gather, 0xff, sizeof(lscgpu_agent_out) * (size_t)e->n_slots));
+    CU(cudaMemset(e->d_gather, 0xff, sizeof(GatherSlot) * (size_t)e->n_slots));
     return alloc_rows(e);
 }
 
@@ -625,6 +631,7 @@ static int enqueue_step_kernels(lscgpu_engine* e, int planner_seq, int threads, 
     for (int k = 0; k < 3; k++) { L.wmin[k] = e->prm.world_min[k]; L.wmax[k] = e->prm.world_max[k]; }
     L.max_iter = e->max_iter;
     L.out = e->d_gather; L.out_base = dealt ? e->rank * e->block : 0;
+    L.act_prev = e->warm_start ? e->d_act_prev : nullptr;
     L.prev_traj = e->d_traj; L.last_cost = e->d_last_cost; L.goal_kind = e->d_goal_kind;
     L.counters = e->d_counters;
     L.any_reset = e->slack_kernel ? e->d_any_reset : nullptr; L.reset_ever = e->d_reset_ever;
@@ -635,14 +642,14 @@ static int enqueue_step_kernels(lscgpu_engine* e, int planner_seq, int threads, 
 
     if (dealt && e->n_ranks > 1) {
         // in-place all-gather: every rank's block of records lands in every replica
-        const size_t bytes = sizeof(lscgpu_agent_out) * (size_t)e->block;
+        const size_t bytes = sizeof(GatherSlot) * (size_t)e->block;
         const int rc = g_nccl.AllGather((const char*)e->d_gather + bytes * e->rank, e->d_gather, bytes, /*ncclInt8*/ 0, e->comm, s);
         if (rc != 0) return fail(LSCGPU_ERR_NCCL, std::string("ncclAllGather: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
     }
     if (ev) CU(cudaEventRecord(ev[3], s));
     const int n_slots = dealt ? e->block * e->n_ranks : n_plan;
     if (use_sfc && n_plan > 0 && side) CU(cudaStreamWaitEvent(s, e->ev_sfc, 0));     // k_commit rewrites what k_sfc_step reads
-    launch_commit(n_slots, e->d_gather, e->d_res, e->d_traj, e->d_in, e->d_last_cost,
+    launch_commit(n_slots, e->d_gather, e->d_res, e->d_act_prev, e->d_traj, e->d_in, e->d_last_cost,
                   use_sfc ? e->d_boxes : nullptr, e->d_init_sfc, e->d_epoch, e->d_kept_step, e->d_kept_last_map, s); launches++;
     if (ev) CU(cudaEventRecord(ev[4], s));
     *launches_out = launches;
@@ -775,10 +782,10 @@ static int compute_stats(lscgpu_engine* e) {
         int worst = 0; long long wt = -1; long long tot[10] = {0};
         for (int i = 0; i < nl; i++) {
             long long t = 0;
-            for (int k = 0; k < 10; k++) { if (k < 8) t += h[(size_t)i * 10 + k]; tot[k] += h[(size_t)i * 10 + k]; }
+            for (int k = 0; k < 10; k++) { if (k < 8 || k == 9) t += h[(size_t)i * 10 + k]; tot[k] += h[(size_t)i * 10 + k]; }
             if (t > wt) { wt = t; worst = i; }
         }
-        const char* names[10] = {"price", "normal", "gs", "ratio", "step", "add", "drop", "corridor", "sfc-warp", "lsc-warps"};
+        const char* names[10] = {"price", "normal", "gs", "ratio", "step", "add", "drop", "corridor", "sfc-warp", "warm-start"};
         std::string line = "[qp dbg] kcycles, slowest block " + std::to_string(worst) + ":";
         for (int k = 0; k < 10; k++) line += std::string(" ") + names[k] + " " + std::to_string(h[(size_t)worst * 10 + k] >> 10);
         line += " | mean:";
@@ -792,6 +799,7 @@ static int compute_stats(lscgpu_engine* e) {
     st.qp_rows_priced = (int64_t)c.rows_priced;
     st.qp_iterations = (int64_t)c.qp_iterations;
     st.qp_full_passes = (int64_t)c.full_passes;
+    st.qp_warm_tried = (int64_t)c.warm_tried; st.qp_warm_accepted = (int64_t)c.warm_accepted; st.qp_warm_rows = (int64_t)c.warm_rows;
     e->stats_fresh = true;
     return LSCGPU_OK;
 }

@@ -105,7 +105,8 @@ struct PlanLaunch {
     float wmin[3], wmax[3];
     int max_iter;
     // outputs
-    lscgpu_agent_out* out;         // block i writes record out[out_base + i] (gather buffer: rank-major, carries agent_id)
+    GatherSlot* out;               // block i writes slot out[out_base + i] (gather buffer: rank-major, carries agent_id)
+    const unsigned short* act_prev;    // null (cold starts), or [N][kActSlots]: rows active at every agent's previous solve
     int out_base;
     const float* prev_traj;        // [N][90]  (kept when the QP fails)
     double* last_cost;             // [N]
@@ -166,9 +167,9 @@ void launch_qp_order(int n, int a0, const lscgpu_agent_out* res, int* order, cud
 // commit: for every filled slot of the gather buffer (agent_id >= 0) the record goes to res[agent_id], the new
 // trajectory becomes traj_curr, the advanced state becomes the next resident input
 // (and, with an octomap, the agent's SFC window takes the step's new box, src/traj_planner.cpp:1451-1491)
-void launch_commit(int n_slots, const lscgpu_agent_out* gather, lscgpu_agent_out* res, float* prev_traj, lscgpu_agent_in* in,
-                   double* last_cost, float* boxes /* null: no octomap */, int* init_sfc, int* epoch, int* kept_step,
-                   volatile int* kept_host /* mapped host word or null */, cudaStream_t s);
+void launch_commit(int n_slots, const GatherSlot* gather, lscgpu_agent_out* res, unsigned short* act_prev, float* prev_traj,
+                   lscgpu_agent_in* in, double* last_cost, float* boxes /* null: no octomap */, int* init_sfc, int* epoch,
+                   int* kept_step, volatile int* kept_host /* mapped host word or null */, cudaStream_t s);
 
 // safety audit of the planned step (src/multi_sync_simulator.cpp:446-475)
 void launch_safety_audit(int n_agents, const float* traj, const AgentConstDev* consts, double dt, int n_samples,

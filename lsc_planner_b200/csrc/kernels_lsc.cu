@@ -332,9 +332,10 @@ void launch_rows_from_lsc(int n_problems, const int* obs_offset, int total_obs, 
 // box (generateFeasibleSFC, src/traj_planner.cpp:1451-1491) — on every replica, so any rank can plan the agent next.
 // Slots with agent_id < 0 are empty (ranks that own fewer agents).
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_commit(int n_slots, const lscgpu_agent_out* gather, lscgpu_agent_out* res,
-                                                float* prev_traj, lscgpu_agent_in* in, double* last_cost, float* boxes,
-                                                int* init_sfc, int* epoch, int* kept_step, volatile int* kept_host) {
+__global__ void __launch_bounds__(128) k_commit(int n_slots, const GatherSlot* gather, lscgpu_agent_out* res,
+                                                unsigned short* act_prev, float* prev_traj, lscgpu_agent_in* in,
+                                                double* last_cost, float* boxes, int* init_sfc, int* epoch, int* kept_step,
+                                                volatile int* kept_host) {
     const int slot = blockIdx.x;
     const int e = threadIdx.x;
     if (slot == 0 && e == 0) {
@@ -344,9 +345,10 @@ __global__ void __launch_bounds__(128) k_commit(int n_slots, const lscgpu_agent_
             *kept_step = 0;
         }
     }
-    const lscgpu_agent_out& o = gather[slot];
+    const lscgpu_agent_out& o = gather[slot].rec;
     const int a = o.agent_id;
     if (a < 0) return;
+    if (e >= 64 && e < 64 + kActSlots) act_prev[(size_t)a * kActSlots + (e - 64)] = gather[slot].act[e - 64];
     // the record, 16 bytes per thread
     constexpr int kVec = sizeof(lscgpu_agent_out) / 16;
     static_assert(sizeof(lscgpu_agent_out) % 16 == 0, "record must be a multiple of 16 bytes");
@@ -368,10 +370,12 @@ __global__ void __launch_bounds__(128) k_commit(int n_slots, const lscgpu_agent_
         if (e == 127) init_sfc[a] = 0;
     }
 }
-void launch_commit(int n_slots, const lscgpu_agent_out* gather, lscgpu_agent_out* res, float* prev_traj, lscgpu_agent_in* in,
-                   double* last_cost, float* boxes, int* init_sfc, int* epoch, int* kept_step, volatile int* kept_host,
-                   cudaStream_t s) {
-    if (n_slots > 0) k_commit<<<n_slots, 128, 0, s>>>(n_slots, gather, res, prev_traj, in, last_cost, boxes, init_sfc, epoch, kept_step, kept_host);
+void launch_commit(int n_slots, const GatherSlot* gather, lscgpu_agent_out* res, unsigned short* act_prev, float* prev_traj,
+                   lscgpu_agent_in* in, double* last_cost, float* boxes, int* init_sfc, int* epoch, int* kept_step,
+                   volatile int* kept_host, cudaStream_t s) {
+    if (n_slots > 0)
+        k_commit<<<n_slots, 128, 0, s>>>(n_slots, gather, res, act_prev, prev_traj, in, last_cost, boxes, init_sfc, epoch, kept_step,
+                                         kept_host);
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -332,6 +332,14 @@ __global__ void __launch_bounds__(kPlanThreads, kSlack ? (kPlanThreads > 256 ? 1
         }
         S.lb[tid] = lo; S.ub[tid] = hi;
     }
+    // warm-start candidates: the bounds / dynamic-limit rows active at this agent's previous solve (none after a failed
+    // solve, a state reset, or in the slack instantiation)
+    int n_guess = 0;
+    if (!kSlack && L.act_prev && !((L.flags ? L.flags[a] : 0) & LSCGPU_FLAG_SLACK_NEEDED)) {
+        const unsigned short* ap = L.act_prev + (size_t)a * kActSlots;
+        n_guess = min((int)ap[kActSlots - 1], kActSlots - 1);
+        if (tid < n_guess) S.act[tid] = ap[tid];
+    }
     // Q / W start empty (the queue lived in Q)
     __syncthreads();
     const long long t_lsc = clock64();
@@ -344,7 +352,7 @@ __global__ void __launch_bounds__(kPlanThreads, kSlack ? (kPlanThreads > 256 ? 1
     long long* secp = nullptr;
 #endif
     const QpResultRegs R = qp_solve_core<kPlanThreads>(S, open_lists, rows, n_kept, T.vel_coef, T.acc_coef, L.max_iter, secp,
-                                                       L.mirror_rows != 0);
+                                                       L.mirror_rows != 0, n_guess);
 
     // ---- epilogue -----------------------------------------------------------------------------------------------
     if (L.counters) {
@@ -356,10 +364,27 @@ __global__ void __launch_bounds__(kPlanThreads, kSlack ? (kPlanThreads > 256 ? 1
     if (L.counters && lane == 0) {
         atomicAdd(&L.counters->qp_iterations, (unsigned long long)R.iters);
         atomicAdd(&L.counters->full_passes, R.passes);
+        if (n_guess > 0) {
+            atomicAdd(&L.counters->warm_tried, 1ull);
+            if (R.warm > 0) { atomicAdd(&L.counters->warm_accepted, 1ull); atomicAdd(&L.counters->warm_rows, (unsigned long long)R.warm); }
+        }
     }
-    lscgpu_agent_out& o = L.out[L.out_base + bi];
+    GatherSlot& slot_out = L.out[L.out_base + bi];
+    lscgpu_agent_out& o = slot_out.rec;
     float* tr = &o.traj[0][0][0];
     const bool ok = R.status == LSCGPU_QP_OK;
+    {   // next step's warm-start candidates: the fixed rows of the working set, in working-set order
+        int id0 = -1, id1 = -1;
+        if (ok && !kSlack) {
+            if (lane < R.q) id0 = S.act[lane];
+            if (lane + 32 < R.q) id1 = S.act[lane + 32];
+        }
+        const bool k0 = id0 >= 0 && id0 < kFixedRows, k1 = id1 >= 0 && id1 < kFixedRows;
+        const unsigned m0 = __ballot_sync(0xffffffffu, k0), m1 = __ballot_sync(0xffffffffu, k1);
+        if (k0) slot_out.act[__popc(m0 & ((1u << lane) - 1u))] = (unsigned short)id0;
+        if (k1) slot_out.act[__popc(m0) + __popc(m1 & ((1u << lane) - 1u))] = (unsigned short)id1;
+        if (lane == 0) slot_out.act[kActSlots - 1] = (unsigned short)(__popc(m0) + __popc(m1));
+    }
     // failure: the optimizer keeps its last successful trajectory and cost (src/traj_planner.cpp:1553-1584)
     for (int e = lane; e < kTrajFloats; e += 32) {
         const int axis = e % 3, cp = e / 3;
@@ -388,6 +413,8 @@ __global__ void __launch_bounds__(kPlanThreads, kSlack ? (kPlanThreads > 256 ? 1
         o.qp_active = R.q;
         int fl = L.flags ? L.flags[a] : 0;
         if (kSfc && !X.sfc_ok) fl |= LSCGPU_FLAG_SFC_SEED_BLOCKED;
+        if (R.warm > 0) fl |= LSCGPU_FLAG_WARM_START;
+        if (ok && R.worst_slack < -1e-9) fl |= LSCGPU_FLAG_IN_BAND;
         if constexpr (kSlack) {
             fl |= LSCGPU_FLAG_SLACK_MODE;
             bool used = false;
@@ -413,7 +440,7 @@ __global__ void __launch_bounds__(kPlanThreads, kSlack ? (kPlanThreads > 256 ? 1
             L.dbg[(size_t)bi * 10] = R.price_cycles;
             L.dbg[(size_t)bi * 10 + 7] = t_lsc - t_start;
             L.dbg[(size_t)bi * 10 + 8] = X.t_sfc;
-            L.dbg[(size_t)bi * 10 + 9] = X.t_lsc;
+            L.dbg[(size_t)bi * 10 + 9] = sec[7];
         }
 #endif
     }

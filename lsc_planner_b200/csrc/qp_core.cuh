@@ -238,7 +238,8 @@ __device__ __forceinline__ Best warp_argmin(Best b) {
 // `code` (slack kernels): 0 hard rows; otherwise the pair's rows read a . c - eps >= rhs with eps = e_c / sqrt(c_p) of
 // its coordinate (0 while it has none) and are normalised by the length of the extended normal.
 template <class SH>
-__device__ __forceinline__ double price_pair(Best& best, const SH& S, int slot, int m, float4 nr, const double* r6, int code = 0) {
+__device__ __forceinline__ double price_pair(Best& best, const SH& S, int slot, int m, float4 nr, const double* r6, double& raw_min,
+                                             int code = 0) {
     const double ax = (double)nr.x, ay = (double)nr.y, az = (double)nr.z, inv = (double)nr.w;
     double eps = 0.0, isc2 = 0.0;
     bool soft = false;
@@ -276,6 +277,7 @@ __device__ __forceinline__ double price_pair(Best& best, const SH& S, int slot, 
             }
         }
         const bool exists = !(i < kPhi && m == 0);
+        raw_min = fmin(raw_min, exists ? slack : INFINITY);
         const bool finite = scale < INFINITY;
         const double mu = finite ? slack * scale : (slack < 0.0 ? -INFINITY : INFINITY);
         mu_min = fmin(mu_min, exists ? mu : INFINITY);
@@ -367,11 +369,22 @@ __device__ __forceinline__ RowRegs decode_row(int id, const SH& S, const RowSrc&
 }
 
 // Remove active row l (see the header comment): one Householder reflection on the columns of Q and W.
-template <class SH>
-__device__ __forceinline__ void drop_active(SH& S, int& q, int l, int lane, int nr = NR) {
+// kProj: the projection of the entering normal is carried through the drop instead of being recomputed: with
+// Q H = [Q', u] the coefficients become d' = (H^T d)[0 .. q-2] and z' = z + delta u, delta = (H^T d)[q-1] (u is the
+// direction the drop frees); returns delta (|z'|^2 = |z|^2 + delta^2).
+template <class SH, bool kProj = false>
+__device__ __forceinline__ double drop_active(SH& S, int& q, int l, int lane, int nr = NR) {
     constexpr int LD = SH::LDX;
     const int j = q - 1;
+    double delta = 0.0;
     __syncwarp();
+    if (j == 0 && kProj) {
+        // the only active row leaves: u is its basis column
+        delta = S.d[0];
+        const int nrows = SH::kE > 0 ? nr : NR;
+        S.z[lane] += delta * S.Q[lane * LD];
+        if (lane + 32 < nrows) S.z[lane + 32] += delta * S.Q[(lane + 32) * LD];
+    }
     if (j > 0) {
         const double y0 = lane < q ? S.W[l * LD + lane] : 0.0;
         const double y1 = lane + 32 < q ? S.W[l * LD + lane + 32] : 0.0;
@@ -380,8 +393,19 @@ __device__ __forceinline__ void drop_active(SH& S, int& q, int l, int lane, int 
         const double ny = nn * rsqrt(nn);
         const double sg = yj >= 0.0 ? 1.0 : -1.0;
         const double beta = fast_rcp(ny * (ny + fabs(yj)));         // 2 / (v . v),  v = y + sg |y| e_j
-        if (lane < q) S.tmp[lane] = lane == j ? y0 + sg * ny : y0;
-        if (lane + 32 < q) S.tmp[lane + 32] = lane + 32 == j ? y1 + sg * ny : y1;
+        const double v0 = lane == j ? y0 + sg * ny : y0, v1 = lane + 32 == j ? y1 + sg * ny : y1;
+        if (lane < q) S.tmp[lane] = v0;
+        if (lane + 32 < q) S.tmp[lane + 32] = v1;
+        double bvd = 0.0, vj = 0.0;
+        if constexpr (kProj) {
+            // d <- H^T d = d - beta (v . d) v
+            bvd = beta * warp_sum((lane < q ? v0 * S.d[lane] : 0.0) + (lane + 32 < q ? v1 * S.d[lane + 32] : 0.0));
+            vj = yj + sg * ny;
+            delta = S.d[j] - bvd * vj;
+            __syncwarp();
+            if (lane < j) S.d[lane] -= bvd * v0;
+            if (lane + 32 < j) S.d[lane + 32] -= bvd * v1;
+        }
         __syncwarp();
         // Q <- Q - beta (Q v) v^T: lane r owns rows r and r + 32 (lanes without a second row redo row 38 and drop it)
         {
@@ -401,6 +425,11 @@ __device__ __forceinline__ void drop_active(SH& S, int& q, int l, int lane, int 
             for (; k < q; k++) { const double t0 = S.tmp[k]; a0 += q1[k] * t0; b0 += q2[k] * t0; }
             const double sa = beta * (a0 + a1), sb = beta * (b0 + b1);
             const bool second = lane + 32 < nrows;
+            if constexpr (kProj) {
+                // z <- z + delta u, u = column j of Q H
+                S.z[lane] += delta * (q1[j] - sa * vj);
+                if (second) S.z[lane + 32] += delta * (q2[j] - sb * vj);
+            }
             for (k = 0; k < j; k++) {
                 const double t0 = S.tmp[k];
                 q1[k] -= sa * t0;
@@ -428,6 +457,7 @@ __device__ __forceinline__ void drop_active(SH& S, int& q, int l, int lane, int 
     if (lane == 0 && l != j) { S.act[l] = S.act[j]; S.lam[l] = S.lam[j]; }
     q = j;
     __syncwarp();
+    return delta;
 }
 
 // Fixed rows (ids 0..449) are 90 variable-bound pairs and 135 dynamic-limit stencil pairs = 225 items, spread over the
@@ -444,6 +474,9 @@ struct QpResultRegs {
     int q, iters, status;
     unsigned long long pairs_evaluated, passes;
     long long price_cycles;
+    int warm;           // rows the warm start put into the working set (0: cold start)
+    double worst_slack; // smallest unnormalised slack over the rows of the last pricing pass (<= 0; every row it skipped is
+                        // provably satisfied): > -1e-6 by construction, below -1e-9 when a row sits inside the feasibility band
 };
 
 #ifdef LSCGPU_QP_SECTION_TIMERS      // build with -DLSCGPU_QP_SECTION_TIMERS and run with LSCGPU_QP_DEBUG=1: cycles per section
@@ -492,12 +525,340 @@ __device__ __forceinline__ void qp_stage(SH& S, const QpTablesDev& T, int ts, co
     __syncthreads();
 }
 
+// ---- building blocks of the factorisation update (warp 0; every lane calls them) ---------------------------------
+// unit whitened normal nv = (G (+) G (+) G)^T a / |.| of a decoded row: lane c owns coordinates c and c + 32
+template <class SH>
+__device__ __forceinline__ void row_normal_regs(const SH& S, const RowRegs& row, int lane, int c_axis0, int c_col0, double* nv_reg) {
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int c = lane + 32 * h;
+        nv_reg[h] = 0.0;
+        if (c < NR) {
+            const int k = h == 0 ? c_axis0 : 2, cc = h == 0 ? c_col0 : c - 2 * kFree;
+            double sacc = 0.0;
+#pragma unroll
+            for (int t = 0; t < 3; t++) {
+                const int ax_t = row.idx[t] / kAx;
+                if (t < row.nnz && ax_t == k) sacc += row.a[t] * S.G[(row.idx[t] - ax_t * kAx) * kFree + cc];
+            }
+            nv_reg[h] = sacc * row.inv_len;
+        } else if (SH::kE > 0 && c - NR == row.ec) {
+            nv_reg[h] = row.ea * row.inv_len;
+        }
+    }
+}
+
+// z = (I - Q Q^T) nv by Gram-Schmidt (second pass when the first cancelled most of the vector); d = Q^T nv.
+// Writes S.z, S.d (and S.tmp); returns |z|^2. nn = |nv|^2.
+template <class SH>
+__device__ __forceinline__ double gs_project(SH& S, int q, int nr, const double* nv_reg, double nn, int lane) {
+    constexpr int LD = SH::LDX;
+    __syncwarp();
+    S.z[lane] = nv_reg[0]; S.d[lane] = 0.0;
+    if (lane + 32 < nr) { S.z[lane + 32] = nv_reg[1]; S.d[lane + 32] = 0.0; }
+    __syncwarp();
+    double zz = nn;
+    if (q > 0) {
+#pragma unroll 1
+        for (int pass = 0; pass < 2; pass++) {
+            // lane k: column k of Q against z. Three chunks of 13 rows: the 13 column entries are loaded
+            // into registers first (independent shared-memory loads in flight together), then multiplied
+            // against the broadcast z values.
+            if (lane < q) {
+                const double* qc = S.Q + lane;
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+                for (int r0 = 0; r0 < NR; r0 += 13) {
+                    double qv[13];
+#pragma unroll
+                    for (int i = 0; i < 13; i++) qv[i] = qc[(r0 + i) * LD];
+#pragma unroll
+                    for (int i = 0; i < 13; i++) {
+                        const double pz = S.z[r0 + i];
+                        if (i % 3 == 0) s0 += qv[i] * pz;
+                        else if (i % 3 == 1) s1 += qv[i] * pz;
+                        else s2 += qv[i] * pz;
+                    }
+                }
+                if constexpr (SH::kE > 0) {
+#pragma unroll 1
+                    for (int r = NR; r < nr; r++) s0 += qc[r * LD] * S.z[r];
+                }
+                const double sdot = s0 + s1 + s2;
+                S.tmp[lane] = sdot;
+                S.d[lane] += sdot;
+            }
+#pragma unroll 1
+            for (int k = lane + 32; k < q; k += 32) {     // q > 32 only
+                double sdot = 0.0;
+#pragma unroll 1
+                for (int r = 0; r < nr; r++) sdot += S.Q[r * LD + k] * S.z[r];
+                S.tmp[k] = sdot;
+                S.d[k] += sdot;
+            }
+            __syncwarp();
+            // lane r: rows r and r + 32 of Q against the coefficients, both in one pass over k
+            // (lanes without a second row read the last row and drop the result)
+            double zp;
+            {
+                const int r2 = min(lane + 32, nr - 1);
+                const double* q1 = S.Q + lane * LD;
+                const double* q2 = S.Q + r2 * LD;
+                double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+                int k = 0;
+                for (; k + 3 < q; k += 4) {                 // four columns per trip: 12 loads, then 8 FMAs
+                    const double t0 = S.tmp[k], t1 = S.tmp[k + 1], t2 = S.tmp[k + 2], t3 = S.tmp[k + 3];
+                    const double u0 = q1[k], u1 = q1[k + 1], u2 = q1[k + 2], u3 = q1[k + 3];
+                    const double w0 = q2[k], w1 = q2[k + 1], w2 = q2[k + 2], w3 = q2[k + 3];
+                    a0 += u0 * t0; a1 += u1 * t1; b0 += w0 * t0; b1 += w1 * t1;
+                    a0 += u2 * t2; a1 += u3 * t3; b0 += w2 * t2; b1 += w3 * t3;
+                }
+                for (; k < q; k++) { const double t0 = S.tmp[k]; a0 += q1[k] * t0; b0 += q2[k] * t0; }
+                const double z1 = S.z[lane] - (a0 + a1);
+                S.z[lane] = z1;
+                zp = z1 * z1;
+                if (lane + 32 < nr) {
+                    const double z2 = S.z[lane + 32] - (b0 + b1);
+                    S.z[lane + 32] = z2;
+                    zp += z2 * z2;
+                }
+            }
+            const double zz_new = warp_sum(zp);
+            __syncwarp();
+            // "twice is enough": a second pass only when the first one cancelled most of the vector
+            const bool again = zz_new < 0.25 * zz;
+            zz = zz_new;
+            if (!again) break;
+        }
+    }
+    return zz;
+}
+
+// rr = W d (change of the active multipliers per unit step): lane k owns row k; four columns per trip, loads staged
+// before the FMAs. Ends with a warp barrier.
+template <class SH>
+__device__ __forceinline__ void w_times_d(SH& S, int q, int lane) {
+    constexpr int LD = SH::LDX;
+    for (int k = lane; k < q; k += 32) {
+        const double* wk = S.W + k * LD;
+        double a0 = 0.0, a1 = 0.0;
+        int c = 0;
+        for (; c + 3 < q; c += 4) {
+            const double w0 = wk[c], w1 = wk[c + 1], w2 = wk[c + 2], w3 = wk[c + 3];
+            const double d0 = S.d[c], d1 = S.d[c + 1], d2 = S.d[c + 2], d3 = S.d[c + 3];
+            a0 += w0 * d0; a1 += w1 * d1; a0 += w2 * d2; a1 += w3 * d3;
+        }
+        for (; c < q; c++) a0 += wk[c] * S.d[c];
+        S.rr[k] = a0 + a1;
+    }
+    __syncwarp();
+}
+
+// the row becomes active: new basis column z / |z|, new column (-rr / |z|, 1 / |z|) of W; q grows by one
+template <class SH>
+__device__ __forceinline__ void add_column(SH& S, int& q, int nr, double rsq, int id, double lam_new, int lane) {
+    constexpr int LD = SH::LDX;
+    for (int r = lane; r < nr; r += 32) S.Q[r * LD + q] = S.z[r] * rsq;
+    for (int k = lane; k < q; k += 32) { S.W[k * LD + q] = -S.rr[k] * rsq; S.W[q * LD + k] = 0.0; }
+    if (lane == 0) {
+        S.W[q * LD + q] = rsq;
+        S.act[q] = id;
+        S.lam[q] = lam_new;
+    }
+    q++;
+    __syncwarp();
+}
+
+// x += (G (+) G (+) G) vacc by the whole block: element e = axis * 30 + var, 13 products each
+template <int kThreads, class SH>
+__device__ __forceinline__ void apply_vacc(SH& S, int tid) {
+    for (int e = tid; e < kNv; e += kThreads) {
+        const int k = e / kAx;
+        const double* g = S.G + (e - k * kAx) * kFree;
+        const double* va = S.vacc + k * kFree;
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int c = 0; c + 1 < kFree; c += 2) { s0 += g[c] * va[c]; s1 += g[c + 1] * va[c + 1]; }
+        s0 += g[kFree - 1] * va[kFree - 1];
+        S.x[e] += s0 + s1;
+    }
+}
+
+// Warm start. S.act[0 .. n_guess) holds candidate rows: the bounds and dynamic limits active at the agent's previous solve
+// (the plan keeps its shape relative to the horizon, so most of them are active again). They are factorised at once,
+// without pricing, ratio tests or steps, and v = argmin |v|^2 subject to n_k . v = b_k on them is taken as the starting
+// point iff every multiplier is >= 0: then (v, candidates) is an S-pair of Goldfarb-Idnani and the iteration converges
+// from it to the same unique minimiser. Candidates with a negative multiplier are dropped once (Householder drops) and the
+// rest re-checked; otherwise the solve starts cold.
+//
+// Every such row touches one axis only and the three axes share one whitened basis, so the candidate normals are block
+// diagonal: three independent Gram-Schmidt factorisations of at most 13 columns in 13 dimensions, done by warps 0, 1, 2
+// side by side (columns of axis k follow those of the axes before it; everything off the diagonal blocks of Q and W is
+// zero). Call with all threads of the block; returns the number of active rows (0: cold start), the same in every
+// thread. On success S.lam holds the multipliers, S.vacc the whitened step from x0 (the caller applies it to x),
+// S.travelled its length.
+__device__ __forceinline__ int fixed_row_axis(int id) {
+    if (id < 0 || id >= kFixedRows) return -1;
+    return id < 180 ? (id >> 1) / kAx : ((id - 180) >> 1) / 45;
+}
+
+template <int kThreads, class SH>
+__device__ __forceinline__ int qp_warm_start(SH& S, const RowSrc& rows, int n_guess, double vel_coef, double acc_coef) {
+    constexpr int LD = SH::LDX;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cand0 = lane < n_guess ? S.act[lane] : -1, cand1 = lane + 32 < n_guess ? S.act[lane + 32] : -1;
+    if (tid < 4) S.best_id[4 + tid] = 0;                    // [4..6] failure flags of the axes, [7] result
+    __syncthreads();                                        // everybody holds the candidates; S.act is free
+    for (int e = tid; e < NR * LD; e += kThreads) { S.Q[e] = 0.0; S.W[e] = 0.0; }
+    const int ax0 = fixed_row_axis(cand0), ax1 = fixed_row_axis(cand1);
+    unsigned lo[3], hi[3];
+    int cnt[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        lo[a] = __ballot_sync(0xffffffffu, ax0 == a); hi[a] = __ballot_sync(0xffffffffu, ax1 == a);
+        cnt[a] = __popc(lo[a]) + __popc(hi[a]);
+    }
+    const int q_all = cnt[0] + cnt[1] + cnt[2];
+    __syncthreads();                                        // Q, W zeroed
+    if (warp < 3 && q_all > 0 && q_all <= NR) {
+        const int k = warp;
+        const unsigned mlo = k == 0 ? lo[0] : (k == 1 ? lo[1] : lo[2]), mhi = k == 0 ? hi[0] : (k == 1 ? hi[1] : hi[2]);
+        const int nk = k == 0 ? cnt[0] : (k == 1 ? cnt[1] : cnt[2]);
+        const int off = k == 0 ? 0 : (k == 1 ? cnt[0] : cnt[0] + cnt[1]);
+        const int nlo = __popc(mlo);
+        double* zk = S.z + k * kFree;                       // this axis' 13 coordinates of the work vectors
+        bool failed = nk > kFree;
+        for (int j = 0; j < nk && !failed; j++) {
+            // j-th candidate of this axis (candidate order)
+            const int src = j < nlo ? __fns(mlo, 0, j + 1) : __fns(mhi, 0, j - nlo + 1);
+            const int id = __shfl_sync(0xffffffffu, j < nlo ? cand0 : cand1, src);
+            const RowRegs row = decode_row(id, S, rows, vel_coef, acc_coef);
+            if (!(row.inv_len < INFINITY)) { failed = true; break; }
+            double slack = -row.b;
+#pragma unroll
+            for (int t = 0; t < 3; t++) if (t < row.nnz) slack += row.a[t] * S.x[row.idx[t]];
+            slack *= row.inv_len;
+            // unit normal restricted to the axis: lane r < 13 owns coordinate r
+            double zr = 0.0;
+            if (lane < kFree) {
+#pragma unroll
+                for (int t = 0; t < 3; t++)
+                    if (t < row.nnz) zr += row.a[t] * S.G[(row.idx[t] - k * kAx) * kFree + lane];
+                zr *= row.inv_len;
+                zk[lane] = zr;
+            }
+            if (lane < j) S.d[off + lane] = 0.0;
+            __syncwarp();
+            double zz = row.nn;
+            const int c = off + j;
+            if (j > 0) {
+#pragma unroll 1
+                for (int pass = 0; pass < 2; pass++) {
+                    if (lane < j) {                         // lane i: column off + i against z
+                        const double* qc = S.Q + (k * kFree) * LD + off + lane;
+                        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                        for (int r = 0; r + 1 < kFree; r += 2) { s0 += qc[r * LD] * zk[r]; s1 += qc[(r + 1) * LD] * zk[r + 1]; }
+                        s0 += qc[(kFree - 1) * LD] * zk[kFree - 1];
+                        const double sdot = s0 + s1;
+                        S.tmp[off + lane] = sdot;
+                        S.d[off + lane] += sdot;
+                    }
+                    __syncwarp();
+                    double zp = 0.0;
+                    if (lane < kFree) {                     // lane r: row r of the block against the coefficients
+                        const double* qr = S.Q + (k * kFree + lane) * LD + off;
+                        double a0 = 0.0, a1 = 0.0;
+                        int i = 0;
+                        for (; i + 1 < j; i += 2) { a0 += qr[i] * S.tmp[off + i]; a1 += qr[i + 1] * S.tmp[off + i + 1]; }
+                        if (i < j) a0 += qr[i] * S.tmp[off + i];
+                        zr -= a0 + a1;
+                        zk[lane] = zr;
+                        zp = zr * zr;
+                    }
+#pragma unroll
+                    for (int o = 8; o > 0; o >>= 1) zp += __shfl_xor_sync(0xffffffffu, zp, o);      // lanes 0..15
+                    const double zz_new = __shfl_sync(0xffffffffu, zp, 0);
+                    __syncwarp();
+                    const bool again = zz_new < 0.25 * zz;
+                    zz = zz_new;
+                    if (!again) break;
+                }
+            }
+            if (!(zz > 1e-10)) { failed = true; break; }    // (numerically) dependent on the columns taken so far
+            const double rsq = rsqrt(zz);
+            if (lane < j) {                                 // rr = W d inside the block, new column of W
+                const double* wk = S.W + (off + lane) * LD + off;
+                double a0 = 0.0;
+                for (int i = lane; i < j; i++) a0 += wk[i] * S.d[off + i];          // W is upper triangular here
+                S.W[(off + lane) * LD + c] = -a0 * rsq;
+            }
+            if (lane < kFree) S.Q[(k * kFree + lane) * LD + c] = zr * rsq;
+            if (lane == 0) { S.W[c * LD + c] = rsq; S.act[c] = id; S.lam[c] = -slack; }      // S.lam: b_k until the multipliers are known
+            __syncwarp();
+        }
+        if (failed && lane == 0) S.best_id[4 + k] = 1;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        int q = (q_all > 0 && q_all <= NR && !(S.best_id[4] | S.best_id[5] | S.best_id[6])) ? q_all : 0;
+        int result = 0;
+        for (int attempt = 0; attempt < 2 && q > 0; attempt++) {
+            // y = W^T b (S.tmp), lambda = W y (S.rr)
+            for (int j = lane; j < q; j += 32) {
+                double s0 = 0.0;
+                for (int kk = 0; kk < q; kk++) s0 += S.W[kk * LD + j] * S.lam[kk];
+                S.tmp[j] = s0;
+            }
+            __syncwarp();
+            bool neg0 = false, neg1 = false;
+            for (int kk = lane; kk < q; kk += 32) {
+                const double* wk = S.W + kk * LD;
+                double s0 = 0.0;
+                for (int j = 0; j < q; j++) s0 += wk[j] * S.tmp[j];
+                S.rr[kk] = s0;
+                if (s0 < -1e-12) { if (kk < 32) neg0 = true; else neg1 = true; }
+            }
+            __syncwarp();
+            const unsigned m0 = __ballot_sync(0xffffffffu, neg0), m1 = __ballot_sync(0xffffffffu, neg1);
+            if (m0 == 0u && m1 == 0u) {
+                // accepted: multipliers, v = Q y, its length
+                for (int kk = lane; kk < q; kk += 32) S.lam[kk] = fmax(S.rr[kk], 0.0);
+                double vp = 0.0;
+                for (int r = lane; r < NR; r += 32) {
+                    const double* qr = S.Q + r * LD;
+                    double s0 = 0.0;
+                    for (int j = 0; j < q; j++) s0 += qr[j] * S.tmp[j];
+                    S.vacc[r] = s0;
+                    vp += s0 * s0;
+                }
+                const double vv = warp_sum(vp);
+                if (lane == 0) S.travelled = sqrt(vv) * (1.0 + 1e-9) + 1e-13;
+                result = q;
+                break;
+            }
+            // a few stale candidates are worth a Householder drop each; with many the previous working set says little
+            // about this step's and a cold start is cheaper than repairing it
+            if (attempt == 1 || __popc(m0) + __popc(m1) > 3) break;
+            // drop the candidates with a negative multiplier, highest index first (a drop moves the last row into the
+            // hole, and everything behind the hole has been looked at already)
+            for (int l = q - 1; l >= 0; l--) {
+                const bool neg = l < 32 ? ((m0 >> l) & 1u) : ((m1 >> (l - 32)) & 1u);
+                if (neg) drop_active(S, q, l, lane, NR);
+            }
+        }
+        if (lane == 0) S.best_id[7] = result;
+    }
+    __syncthreads();
+    return S.best_id[7];
+}
+
 // The active-set solve. Preconditions: qp_stage done (S.x = x0), the row source holds n_kept pairs with their gates.
 // open_lists: kThreads / 32 lists of kWarpList ints in shared memory. Every thread returns the same result.
 template <int kThreads, class SH>
 __device__ __forceinline__ QpResultRegs qp_solve_core(SH& S, int* open_lists, const RowSrc& rows, int n_kept,
                                                       double vel_coef, double acc_coef, int max_iter, long long* sec,
-                                                      bool mirror_rows = false) {
+                                                      bool mirror_rows = false, int n_guess = 0) {
     constexpr int kE = SH::kE, NRX = SH::NRX, LD = SH::LDX;
     constexpr int kWarps = kThreads / 32;
     constexpr int kItems = (225 + kThreads - 1) / kThreads;
@@ -535,8 +896,17 @@ __device__ __forceinline__ QpResultRegs qp_solve_core(SH& S, int* open_lists, co
     }
     // warp 0: per-lane index constants of the factorisation update (no divisions in the loop)
     const int c_axis0 = lane / kFree, c_col0 = lane - c_axis0 * kFree;      // whitened coordinate c = lane
-    QpResultRegs R{0, 0, LSCGPU_QP_OK, 0ull, 0ull, 0ll};
+    QpResultRegs R{0, 0, LSCGPU_QP_OK, 0ull, 0ull, 0ll, 0, 0.0};
     int q = 0, iters = 0, status = LSCGPU_QP_OK;
+    double raw_min = 0.0;
+
+    if (kE == 0 && n_guess > 0) {       // block-uniform
+        // warm start from the rows in S.act[0 .. n_guess) (qp_warm_start); x is brought up to date by the block
+        QP_TICK();
+        R.warm = qp_warm_start<kThreads>(S, rows, n_guess, vel_coef, acc_coef);
+        if (R.warm > 0) { q = R.warm; apply_vacc<kThreads>(S, tid); }
+        QP_TOCK(7);
+    }
 
     while (true) {
         // ---- pricing by the whole block ---------------------------------------------------------------------------
@@ -544,6 +914,7 @@ __device__ __forceinline__ QpResultRegs qp_solve_core(SH& S, int* open_lists, co
         const long long t_price = clock64();
         __syncthreads();        // x of the previous update is complete (block-wide update below)
         const double travelled = S.travelled;
+        raw_min = 0.0;          // smallest (unnormalised) slack this thread sees in this pass
 #pragma unroll
         for (int t = 0; t < kItems; t++) {
             if (F.base[t] < 0) continue;
@@ -551,10 +922,12 @@ __device__ __forceinline__ QpResultRegs qp_solve_core(SH& S, int* open_lists, co
             if (F.kind[t] == 0) {
                 consider(best, c[0] - F.lo[t], F.inv[t], F.id[t]);
                 consider(best, F.hi[t] - c[0], F.inv[t], F.id[t] + 1);
+                raw_min = fmin(raw_min, fmin(c[0] - F.lo[t], F.hi[t] - c[0]));
             } else {
                 const double expr = F.kind[t] == 1 ? vel_coef * (c[1] - c[0]) : acc_coef * (c[2] - 2.0 * c[1] + c[0]);
                 consider(best, F.lo[t] - expr, F.inv[t], F.id[t]);
                 consider(best, F.lo[t] + expr, F.inv[t], F.id[t] + 1);
+                raw_min = fmin(raw_min, F.lo[t] - fabs(expr));
             }
         }
         for (int base = warp * kWarpList; base < n_kept; base += kWarps * kWarpList) {
@@ -577,7 +950,7 @@ __device__ __forceinline__ QpResultRegs qp_solve_core(SH& S, int* open_lists, co
                 const int slot = my_list[idx];
                 float4 nr; double r6[6]; int m;
                 rows.template load<(kE > 0)>(slot, nr, r6, m);
-                const double mu_min = price_pair(best, S, slot, m, nr, r6, kE > 0 ? rows.code(slot) : 0);
+                const double mu_min = price_pair(best, S, slot, m, nr, r6, raw_min, kE > 0 ? rows.code(slot) : 0);
                 // 1e-6 relative margin: the stored 1/|a| is float32, so mu carries ~6e-8 relative error
                 rows.set_gate(slot, travelled + (mu_min > 0.0 ? mu_min * 0.999999 : mu_min));
                 R.pairs_evaluated++;
@@ -635,25 +1008,8 @@ __device__ __forceinline__ QpResultRegs qp_solve_core(SH& S, int* open_lists, co
                 const int nr = kE > 0 ? NR + S.n_e : NR;        // rows of Q in use
                 const RowRegs row = decode_row(best.id, S, rows, vel_coef, acc_coef);
                 if (!(row.inv_len < INFINITY)) { status = LSCGPU_QP_INFEASIBLE; done = true; break; }
-                // unit whitened normal  nv = (G (+) G (+) G)^T a / |.|: lane c owns coordinates c and c + 32
                 double nv_reg[2];
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int c = lane + 32 * h;
-                    nv_reg[h] = 0.0;
-                    if (c < NR) {
-                        const int k = h == 0 ? c_axis0 : 2, cc = h == 0 ? c_col0 : c - 2 * kFree;
-                        double sacc = 0.0;
-#pragma unroll
-                        for (int t = 0; t < 3; t++) {
-                            const int ax_t = row.idx[t] / kAx;
-                            if (t < row.nnz && ax_t == k) sacc += row.a[t] * S.G[(row.idx[t] - ax_t * kAx) * kFree + cc];
-                        }
-                        nv_reg[h] = sacc * row.inv_len;
-                    } else if (kE > 0 && c - NR == row.ec) {
-                        nv_reg[h] = row.ea * row.inv_len;
-                    }
-                }
+                row_normal_regs(S, row, lane, c_axis0, c_col0, nv_reg);
                 // slack of the selected row (normalised); along the step it grows by t |z|^2 (a . G z = |G^T a| nv . z and
                 // nv . z = z . z for the projection z of nv), so x itself is only brought up to date once per update
                 double slack = -row.b;
@@ -661,105 +1017,14 @@ __device__ __forceinline__ QpResultRegs qp_solve_core(SH& S, int* open_lists, co
                 for (int t = 0; t < 3; t++) if (t < row.nnz) slack += row.a[t] * S.x[row.idx[t]];
                 if constexpr (kE > 0) { if (row.ec >= 0) slack += row.ea * S.e[row.ec]; }
                 slack *= row.inv_len;
-                double lam_p = 0.0;
+                double lam_p = 0.0, zz = 0.0;
+                bool fresh = true;
                 QP_TOCK(1);
                 while (true) {
                     if (++iters > max_iter) { status = LSCGPU_QP_MAXITER; done = true; break; }
-                    // ---- z = (I - Q Q^T) nv by Gram-Schmidt (second pass when needed); d = Q^T nv --------------------
-                    __syncwarp();
-                    S.z[lane] = nv_reg[0]; S.d[lane] = 0.0;
-                    if (lane + 32 < nr) { S.z[lane + 32] = nv_reg[1]; S.d[lane + 32] = 0.0; }
-                    __syncwarp();
-                    double zz = row.nn;              // |nv|^2
-                    if (q > 0) {
-#pragma unroll 1
-                        for (int pass = 0; pass < 2; pass++) {
-                            // lane k: column k of Q against z. Three chunks of 13 rows: the 13 column entries are loaded
-                            // into registers first (independent shared-memory loads in flight together), then multiplied
-                            // against the broadcast z values.
-                            if (lane < q) {
-                                const double* qc = S.Q + lane;
-                                double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-#pragma unroll
-                                for (int r0 = 0; r0 < NR; r0 += 13) {
-                                    double qv[13];
-#pragma unroll
-                                    for (int i = 0; i < 13; i++) qv[i] = qc[(r0 + i) * LD];
-#pragma unroll
-                                    for (int i = 0; i < 13; i++) {
-                                        const double pz = S.z[r0 + i];
-                                        if (i % 3 == 0) s0 += qv[i] * pz;
-                                        else if (i % 3 == 1) s1 += qv[i] * pz;
-                                        else s2 += qv[i] * pz;
-                                    }
-                                }
-                                if constexpr (kE > 0) {
-#pragma unroll 1
-                                    for (int r = NR; r < nr; r++) s0 += qc[r * LD] * S.z[r];
-                                }
-                                const double sdot = s0 + s1 + s2;
-                                S.tmp[lane] = sdot;
-                                S.d[lane] += sdot;
-                            }
-#pragma unroll 1
-                            for (int k = lane + 32; k < q; k += 32) {     // q > 32 only
-                                double sdot = 0.0;
-#pragma unroll 1
-                                for (int r = 0; r < nr; r++) sdot += S.Q[r * LD + k] * S.z[r];
-                                S.tmp[k] = sdot;
-                                S.d[k] += sdot;
-                            }
-                            __syncwarp();
-                            // lane r: rows r and r + 32 of Q against the coefficients, both in one pass over k
-                            // (lanes without a second row read row 38 and drop the result)
-                            double zp;
-                            {
-                                const int r2 = min(lane + 32, nr - 1);
-                                const double* q1 = S.Q + lane * LD;
-                                const double* q2 = S.Q + r2 * LD;
-                                double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
-                                int k = 0;
-                                for (; k + 3 < q; k += 4) {                 // four columns per trip: 12 loads, then 8 FMAs
-                                    const double t0 = S.tmp[k], t1 = S.tmp[k + 1], t2 = S.tmp[k + 2], t3 = S.tmp[k + 3];
-                                    const double u0 = q1[k], u1 = q1[k + 1], u2 = q1[k + 2], u3 = q1[k + 3];
-                                    const double w0 = q2[k], w1 = q2[k + 1], w2 = q2[k + 2], w3 = q2[k + 3];
-                                    a0 += u0 * t0; a1 += u1 * t1; b0 += w0 * t0; b1 += w1 * t1;
-                                    a0 += u2 * t2; a1 += u3 * t3; b0 += w2 * t2; b1 += w3 * t3;
-                                }
-                                for (; k < q; k++) { const double t0 = S.tmp[k]; a0 += q1[k] * t0; b0 += q2[k] * t0; }
-                                const double z1 = S.z[lane] - (a0 + a1);
-                                S.z[lane] = z1;
-                                zp = z1 * z1;
-                                if (lane + 32 < nr) {
-                                    const double z2 = S.z[lane + 32] - (b0 + b1);
-                                    S.z[lane + 32] = z2;
-                                    zp += z2 * z2;
-                                }
-                            }
-                            const double zz_new = warp_sum(zp);
-                            __syncwarp();
-                            // "twice is enough": a second pass only when the first one cancelled most of the vector
-                            const bool again = zz_new < 0.25 * zz;
-                            zz = zz_new;
-                            if (!again) break;
-                        }
-                    }
+                    if (fresh) zz = gs_project(S, q, nr, nv_reg, row.nn, lane);     // after a drop z, d and |z|^2 are carried over
                     QP_TOCK(2);
-                    // rr = W d (change of the active multipliers per unit step): lane k owns row k; four columns per
-                    // trip, loads staged before the FMAs
-                    for (int k = lane; k < q; k += 32) {
-                        const double* wk = S.W + k * LD;
-                        double a0 = 0.0, a1 = 0.0;
-                        int c = 0;
-                        for (; c + 3 < q; c += 4) {
-                            const double w0 = wk[c], w1 = wk[c + 1], w2 = wk[c + 2], w3 = wk[c + 3];
-                            const double d0 = S.d[c], d1 = S.d[c + 1], d2 = S.d[c + 2], d3 = S.d[c + 3];
-                            a0 += w0 * d0; a1 += w1 * d1; a0 += w2 * d2; a1 += w3 * d3;
-                        }
-                        for (; c < q; c++) a0 += wk[c] * S.d[c];
-                        S.rr[k] = a0 + a1;
-                    }
-                    __syncwarp();
+                    w_times_d(S, q, lane);
                     // ratio test over the active multipliers: warp minimum of lam / rr through its order-preserving
                     // 64-bit key (two 32-bit min reductions), ties to the smallest index
                     double t1 = INFINITY;
@@ -794,27 +1059,26 @@ __device__ __forceinline__ QpResultRegs qp_solve_core(SH& S, int* open_lists, co
                     for (int k = lane; k < q; k += 32) S.lam[k] -= t * S.rr[k];
                     lam_p += t;
                     QP_TOCK(3);
-                    if (!primal) { drop_active(S, q, l, lane, nr); QP_TOCK(6); continue; }
+                    if (!primal) {
+                        const double dl = drop_active<SH, true>(S, q, l, lane, nr);
+                        zz += dl * dl; fresh = false;
+                        QP_TOCK(6);
+                        continue;
+                    }
                     if (lane == 0) S.travelled += t * (zz * rsq) * (1.0 + 1e-9) + 1e-13;
                     S.vacc[lane] += t * S.z[lane];
                     if (lane + 32 < nr) S.vacc[lane + 32] += t * S.z[lane + 32];
                     slack += t * zz;
                     QP_TOCK(4);
                     if (t2 <= t1) {
-                        // the row becomes active: new basis column z / |z|, new column (-rr / |z|, 1 / |z|) of W
-                        for (int r = lane; r < nr; r += 32) S.Q[r * LD + q] = S.z[r] * rsq;
-                        for (int k = lane; k < q; k += 32) { S.W[k * LD + q] = -S.rr[k] * rsq; S.W[q * LD + k] = 0.0; }
-                        if (lane == 0) {
-                            S.W[q * LD + q] = rsq;
-                            S.act[q] = best.id;
-                            S.lam[q] = lam_p;
-                        }
-                        q++;
-                        __syncwarp();
+                        add_column(S, q, nr, rsq, best.id, lam_p, lane);
                         QP_TOCK(5);
                         break;
                     }
-                    drop_active(S, q, l, lane, nr);
+                    {
+                        const double dl = drop_active<SH, true>(S, q, l, lane, nr);
+                        zz += dl * dl; fresh = false;
+                    }
                     QP_TOCK(6);
                 }
             } while (false);
@@ -824,24 +1088,21 @@ __device__ __forceinline__ QpResultRegs qp_solve_core(SH& S, int* open_lists, co
         const bool stop = S.stop != 0;
         // x += (G (+) G (+) G) vacc by the whole block: element e = axis * 30 + var, 13 products each (the barrier at the
         // top of the next pass makes it visible)
-        for (int e = tid; e < kNv; e += kThreads) {
-            const int k = e / kAx;
-            const double* g = S.G + (e - k * kAx) * kFree;
-            const double* va = S.vacc + k * kFree;
-            double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-            for (int c = 0; c + 1 < kFree; c += 2) { s0 += g[c] * va[c]; s1 += g[c + 1] * va[c + 1]; }
-            s0 += g[kFree - 1] * va[kFree - 1];
-            S.x[e] += s0 + s1;
-        }
+        apply_vacc<kThreads>(S, tid);
         if constexpr (kE > 0) { if (tid < S.n_e) S.e[tid] += S.vacc[NR + tid]; }
         if (stop) break;
     }
     __syncthreads();
-    // q, iters and status live in warp 0; hand them to everybody
+    // q, iters and status live in warp 0; hand them to everybody; block minimum of the last pass' smallest slack
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) raw_min = fmin(raw_min, __shfl_xor_sync(0xffffffffu, raw_min, o));
+    if (lane == 0) S.best_mu[warp] = raw_min;
     if (tid == 0) { S.act[NRX] = q; S.best_id[0] = iters; S.best_id[1] = status; }
     __syncthreads();
     R.q = S.act[NRX]; R.iters = S.best_id[0]; R.status = S.best_id[1];
+    R.worst_slack = 0.0;
+#pragma unroll
+    for (int w = 0; w < kWarps; w++) R.worst_slack = fmin(R.worst_slack, S.best_mu[w]);
     return R;
 }
 

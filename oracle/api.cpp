@@ -187,6 +187,15 @@ void orc_swarm_free(void* sv) { delete (Swarm*)sv; }
 void orc_swarm_set_map(void* sv, void* map) { ((Swarm*)sv)->dm = map ? &((MapHandle*)map)->dm : nullptr; }
 void orc_swarm_set_capture(void* sv, int on) { ((Swarm*)sv)->capture = on != 0; }
 void orc_swarm_set_slack_weight(void* sv, double w) { ((Swarm*)sv)->prm.slack_w = w; }
+// active rows of agent a's last successful plain solve (canonical ids); returns the count or -1
+int orc_swarm_get_active(void* sv, int a, int* ids) {
+    Swarm* s = (Swarm*)sv;
+    const int n = s->prev_n_act[a];
+    for (int k = 0; k < n; k++) ids[k] = s->prev_act[(size_t)a * QRED + k];
+    return n;
+}
+void orc_swarm_set_warm_start(void* sv, int on) { ((Swarm*)sv)->warm_start = on; }
+void orc_swarm_get_warm_stats(void* sv, long long* tried_accepted) { Swarm* s = (Swarm*)sv; tried_accepted[0] = s->warm_tried; tried_accepted[1] = s->warm_accepted; }
 // sticky disturbance state (who was ever reset) and the slack outputs of the last step
 void orc_swarm_get_reset_ever(void* sv, unsigned char* out) { Swarm* s = (Swarm*)sv; for (int a = 0; a < s->N; a++) out[a] = (unsigned char)s->reset_ever[a]; }
 void orc_swarm_set_reset_ever(void* sv, const unsigned char* in) { Swarm* s = (Swarm*)sv; for (int a = 0; a < s->N; a++) s->reset_ever[a] = (char)in[a]; }

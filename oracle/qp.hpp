@@ -239,6 +239,8 @@ struct QpResult {
     int status, iters, n_active;
     double kkt_stationarity;     // | v - sum lambda_k n_k |_inf in the whitened space
     double max_violation;        // max over all rows of the (unnormalised) violation
+    int act_ids[QRED]; int n_act_ids = 0;   // canonical ids of the rows active at the solution (qp_solve)
+    int warm_accepted = 0;       // qp_solve with a guess: rows of the guess the start point kept (0: cold start)
     std::vector<double> eps;     // qp_solve_slack: slack variable of every (obstacle, segment) row entry, <= 0
     double slack_cost = 0;       // ... their share of `cost`
 };
@@ -311,7 +313,13 @@ inline double g_tier_threshold = INFINITY;
 inline int g_trace_agent = -1;            // debugging: >= 0 prints every pivot of the solve (stderr)
 
 // Goldfarb-Idnani dual active set on  min |v|^2  s.t.  n_j . v >= -slack0_j   (x = x0 + G v)
-inline void qp_solve(const QpTables& T, const QpProblem& p, QpResult& out, int max_iter = 2000) {
+// Optional warm start (guess / n_guess: canonical row ids, e.g. the previous step's active set shifted by one segment):
+// the rows of the guess are factorised at once, v = argmin |v|^2 s.t. n_k . v = b_k on them, and the pair (v, guess) is
+// accepted as the starting point iff every multiplier is >= 0 (then it is an S-pair of Goldfarb-Idnani, from which the
+// iteration below converges to the same unique minimiser); rows with a negative multiplier are removed once and the
+// rest re-tried, otherwise the solve starts cold. Restates the kernel's warm start (csrc/qp_core.cuh) for CPU experiments.
+inline void qp_solve(const QpTables& T, const QpProblem& p, QpResult& out, int max_iter = 2000, const int* guess = nullptr,
+                     int n_guess = 0) {
     const int n = QRED;
     const int ts = p.ts;
     double x[QNV], v[QRED] = {};
@@ -385,6 +393,69 @@ inline void qp_solve(const QpTables& T, const QpProblem& p, QpResult& out, int m
         return true;
     };
     if (tiered) { pbest = -2; for (int id = 450; id < n_ids; id++) price(id); }
+    out.warm_accepted = 0;
+    if (guess && n_guess > 0) {
+        std::vector<int> cand(guess, guess + n_guess);
+        for (int attempt = 0; attempt < 2 && !cand.empty(); attempt++) {
+            // factorise the candidate rows: J, R as after adding them one by one (no steps)
+            std::fill(J.begin(), J.end(), 0.0); std::fill(R.begin(), R.end(), 0.0);
+            for (int i = 0; i < n; i++) J[i * n + i] = 1.0;
+            int qq = 0; int ids[QRED]; double bb[QRED];
+            for (int id : cand) {
+                RowView r;
+                if (qq >= n || id < 0 || id >= n_ids || !row_get(T, p, id, r)) continue;
+                bool dup = false; for (int k = 0; k < qq; k++) dup |= ids[k] == id;
+                if (dup) continue;
+                const double nrm = row_normal(r, nv);
+                if (!(nrm > 0)) continue;
+                for (int c = 0; c < n; c++) nv[c] /= nrm;
+                for (int c = 0; c < n; c++) { double s2 = 0; for (int rr2 = 0; rr2 < n; rr2++) s2 += J[rr2 * n + c] * nv[rr2]; d[c] = s2; }
+                double zz = 0; for (int c = qq; c < n; c++) zz += d[c] * d[c];
+                if (!(zz > 1e-10)) continue;                     // (numerically) dependent on the rows taken so far
+                for (int j = n - 1; j > qq; j--) {
+                    double a = d[j - 1], b = d[j];
+                    if (b == 0.0) continue;
+                    double h = std::hypot(a, b), c = a / h, s2 = b / h;
+                    d[j - 1] = h; d[j] = 0;
+                    for (int rr2 = 0; rr2 < n; rr2++) {
+                        double u1 = J[rr2 * n + j - 1], u2 = J[rr2 * n + j];
+                        J[rr2 * n + j - 1] = c * u1 + s2 * u2; J[rr2 * n + j] = -s2 * u1 + c * u2;
+                    }
+                }
+                for (int k = 0; k <= qq; k++) R[k * n + qq] = d[k];
+                for (int rr2 = 0; rr2 < n; rr2++) Nact[rr2 * n + qq] = nv[rr2];
+                ids[qq] = id; bb[qq] = -row_slack(r) / nrm;      // n . v >= b  with v measured from x0
+                qq++;
+            }
+            // R^T R lambda = b;  v = J1 (R lambda)
+            double y[QRED], lm[QRED];
+            for (int k = 0; k < qq; k++) { double s2 = bb[k]; for (int c = 0; c < k; c++) s2 -= R[c * n + k] * y[c]; y[k] = s2 / R[k * n + k]; }
+            for (int k = qq - 1; k >= 0; k--) { double s2 = y[k]; for (int c = k + 1; c < qq; c++) s2 -= R[k * n + c] * lm[c]; lm[k] = s2 / R[k * n + k]; }
+            bool ok = true;
+            for (int k = 0; k < qq; k++) ok &= lm[k] >= -1e-12;
+            if (ok) {
+                q = qq;
+                for (int k = 0; k < q; k++) { act[k] = ids[k]; lam[k] = std::max(lm[k], 0.0); is_active[ids[k]] = 1; }
+                for (int rr2 = 0; rr2 < n; rr2++) { double s2 = 0; for (int k = 0; k < q; k++) s2 += J[rr2 * n + k] * y[k]; v[rr2] = s2; }
+                for (int k = 0; k < 3; k++)
+                    for (int i = 0; i < QAX; i++) {
+                        double s2 = 0;
+                        for (int c = 0; c < QFREE; c++) s2 += T.G[ts - 1][i][c] * v[k * QFREE + c];
+                        x[k * QAX + i] += s2;
+                    }
+                out.warm_accepted = q;
+                break;
+            }
+            std::vector<int> keep;
+            for (int k = 0; k < qq; k++) if (lm[k] >= -1e-12) keep.push_back(ids[k]);
+            cand.swap(keep);
+            if (attempt == 1 || cand.empty()) {                  // cold start
+                std::fill(J.begin(), J.end(), 0.0); std::fill(R.begin(), R.end(), 0.0);
+                for (int i = 0; i < n; i++) J[i * n + i] = 1.0;
+            }
+        }
+        if (!out.warm_accepted) { std::fill(J.begin(), J.end(), 0.0); std::fill(R.begin(), R.end(), 0.0); for (int i = 0; i < n; i++) J[i * n + i] = 1.0; }
+    }
     while (true) {
         // pricing: most violated row in whitened distance
         pbest = -1; mu_best = -tol;
@@ -459,6 +530,7 @@ inline void qp_solve(const QpTables& T, const QpProblem& p, QpResult& out, int m
     std::memcpy(out.x, x, sizeof x);
     out.cost = objective(T, p, x);
     out.iters = iters; out.n_active = q;
+    out.n_act_ids = q; for (int k = 0; k < q; k++) out.act_ids[k] = act[k];
     double st = 0;
     for (int r = 0; r < n; r++) { double s = v[r]; for (int k = 0; k < q; k++) s -= lam[k] * Nact[r * n + k]; st = std::max(st, std::fabs(s)); }
     out.kkt_stationarity = st;

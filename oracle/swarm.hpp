@@ -41,6 +41,28 @@ namespace orc {
 
 enum StepFlags { FLAG_SLACK_NEEDED = 1, FLAG_SFC_SEED_BLOCKED = 2 };
 
+// Receding horizon: segment m of the previous plan is segment m - 1 of this one. Canonical row ids (qp.hpp) of bounds and
+// dynamic limits shifted accordingly; -1 when the row has no counterpart (segment 0 before, an initial-state row now, or
+// an LSC row, whose slot numbering changes from step to step).
+inline int row_segment(int id) {
+    if (id < 180) return ((id >> 1) / 6) % 5;
+    if (id < 450) return (((id - 180) >> 1) / 9) % 5;
+    return -1;
+}
+inline int shifted_row_id(int id) {
+    if (id < 180) {
+        const int v = id >> 1, i = v % 6, m = (v / 6) % 5;
+        if (m == 0 || (m == 1 && i < 3)) return -1;
+        return id - 12;
+    }
+    if (id < 450) {
+        const int v = (id - 180) >> 1, j = v % 9, m = (v / 9) % 5;
+        if (m == 0 || (m == 1 && (j < 2 || j == 5))) return -1;
+        return id - 18;
+    }
+    return -1;
+}
+
 struct Swarm {
     SwarmParams prm;
     int N = 0;
@@ -61,6 +83,10 @@ struct Swarm {
     // Disturbance handling. Every planner runs the same two checks on the same data (the shifted previous trajectory of
     // agent j against j's observed position), so obs_slack_indices of planner i is: every obstacle once i itself was
     // reset (:1049-1051), else the agents j that were ever reset (:869-870). Sticky: the reference never erases it.
+    // warm start of the QP (experiment mirror of the kernel's, qp.hpp): previous active rows per agent
+    int warm_start = 0;
+    std::vector<int> prev_act; std::vector<int> prev_n_act;     // [N][39], [N]; -1: no usable previous solve
+    long long warm_accepted = 0, warm_tried = 0;
     std::vector<char> reset_ever;
     std::vector<double> qp_slack_cost; std::vector<int> qp_slack_rows;   // step outputs: slack share of the cost, rows with eps < 0
     // step outputs
@@ -80,6 +106,7 @@ struct Swarm {
         box_min.assign((size_t)N * 5, f3(0, 0, 0)); box_max = box_min;
         init_sfc.assign(N, 1);                                      // traj_planner.cpp:49
         reset_ever.assign(N, 0); qp_slack_cost.assign(N, 0); qp_slack_rows.assign(N, 0);
+        prev_act.assign((size_t)N * QRED, 0); prev_n_act.assign(N, -1);
         qp_cost.assign(N, 0); qp_status.assign(N, 0); qp_iters.assign(N, 0); qp_active.assign(N, 0);
         qp_maxviol.assign(N, 0); qp_kkt.assign(N, 0); flags.assign(N, 0);
         pred.assign((size_t)N * 30, f3(0, 0, 0));
@@ -176,7 +203,26 @@ struct Swarm {
         bool any_slack = false;
         for (const LscRows& r : rows_buf) any_slack |= r.slack != 0;
         qp.slack_w = prm.slack_w;
-        if (any_slack) qp_solve_slack(T, qp, res); else qp_solve(T, qp, res);
+        if (any_slack) qp_solve_slack(T, qp, res);
+        else if (warm_start && prev_n_act[a] > 0 && !(flags[a] & FLAG_SLACK_NEEDED)) {
+            int guess[2 * QRED], ng = 0;
+            for (int k = 0; k < prev_n_act[a]; k++) {
+                const int id = prev_act[(size_t)a * QRED + k];
+                if (warm_start & 1) { if (id < 450) guess[ng++] = id; }       // same rows: the plan keeps its shape relative to the horizon
+                if (warm_start & 2) {
+                    const int sh = shifted_row_id(id);
+                    if (sh >= 0) guess[ng++] = sh;
+                    if (!(warm_start & 1) && row_segment(id) == QM - 1) guess[ng++] = id;
+                }
+            }
+            qp_solve(T, qp, res, 2000, guess, ng);
+            __atomic_fetch_add(&warm_tried, 1LL, __ATOMIC_RELAXED);
+            if (res.warm_accepted) __atomic_fetch_add(&warm_accepted, 1LL, __ATOMIC_RELAXED);
+        } else qp_solve(T, qp, res);
+        if (!any_slack && res.status == QP_OK) {
+            prev_n_act[a] = res.n_act_ids;
+            for (int k = 0; k < res.n_act_ids; k++) prev_act[(size_t)a * QRED + k] = res.act_ids[k];
+        } else prev_n_act[a] = -1;
         qp_slack_cost[a] = any_slack ? res.slack_cost : 0.0;
         qp_slack_rows[a] = 0;
         for (double e : res.eps) qp_slack_rows[a] += e < 0.0;

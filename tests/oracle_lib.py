@@ -56,6 +56,9 @@ def lib():
         L.orc_qp_solve_slack.argtypes = qp_args + [i32p, C.c_double, f64p, f64p, f64p]; L.orc_qp_solve_slack.restype = C.c_int
         u8 = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
         L.orc_swarm_set_slack_weight.argtypes = [C.c_void_p, C.c_double]
+        L.orc_swarm_set_warm_start.argtypes = [C.c_void_p, C.c_int]
+        L.orc_swarm_get_active.argtypes = [C.c_void_p, C.c_int, i32p]; L.orc_swarm_get_active.restype = C.c_int
+        L.orc_swarm_get_warm_stats.argtypes = [C.c_void_p, i64p]
         L.orc_swarm_get_reset_ever.argtypes = [C.c_void_p, u8]
         L.orc_swarm_set_reset_ever.argtypes = [C.c_void_p, u8]
         L.orc_swarm_get_slack.argtypes = [C.c_void_p, f64p, i32p]
@@ -253,6 +256,16 @@ class Swarm:
     def set_capture(self, on=True): lib().orc_swarm_set_capture(self.h, int(on))
 
     def set_slack_weight(self, w): lib().orc_swarm_set_slack_weight(self.h, float(w))
+
+    def active_rows(self, a):
+        """Canonical ids of the rows active at agent a's last successful solve (None when it failed / carried slack)."""
+        ids = np.zeros(39, np.int32); n = lib().orc_swarm_get_active(self.h, a, ids)
+        return None if n < 0 else ids[:n].copy()
+
+    def set_warm_start(self, on=True): lib().orc_swarm_set_warm_start(self.h, int(on))
+
+    def warm_stats(self):
+        c = np.zeros(2, np.int64); lib().orc_swarm_get_warm_stats(self.h, c); return int(c[0]), int(c[1])
 
     def reset_ever(self):
         out = np.zeros(self.n, np.uint8); lib().orc_swarm_get_reset_ever(self.h, out); return out

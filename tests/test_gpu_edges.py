@@ -31,7 +31,8 @@ def _lockstep(e, sw, goal, steps, tol=2e-6):
         q = sw.qp()
         assert np.array_equal(out["qp_status"], q["status"]), (step, out["qp_status"], q["status"])
         d = np.abs(out["traj"] - sw.traj()).max()
-        assert d <= (tol if q["maxviol"].max() <= 1e-9 else 2e-5), (step, d)
+        in_band = q["maxviol"].max() > 1e-9 or ((out["flags"] & 64) != 0).any()      # a row inside the feasibility band somewhere
+        assert d <= (2e-5 if in_band else tol), (step, d)
         sw.advance()
     return out
 

@@ -52,7 +52,7 @@ def test_device_goal_planning_matches_oracle(name, steps):
         q = sw.qp()
         assert np.array_equal(out["qp_status"], q["status"]), step
         diffs = np.abs(out["traj"] - sw.traj()).reshape(n, -1).max(1)
-        in_band = q["maxviol"] > 1e-9
+        in_band = (q["maxviol"] > 1e-9) | ((out["flags"] & 64) != 0)     # rows inside the feasibility band, at either solution
         assert diffs[~in_band].max(initial=0) <= 2e-6 and diffs.max() <= 2e-5, (step, diffs.max())
         kinds += np.bincount(k_o, minlength=2)
         clipped += int((np.linalg.norm(g_o - scn.goal, axis=1) > 1e-3).sum())

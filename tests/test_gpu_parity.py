@@ -189,13 +189,13 @@ def _teacher_forced(scn, steps, omap=None, bt=None, check_lsc_agents=(0,), traj_
         t_o = sw.traj()
         diffs = np.abs(out["traj"] - t_o).reshape(n, -1).max(1)
         worst.append(diffs)
-        in_band = q["maxviol"] > 1e-9                      # agents with rows inside the feasibility band
+        in_band = (q["maxviol"] > 1e-9) | ((out["flags"] & 64) != 0)     # rows inside the feasibility band, at either solution
         assert diffs[~in_band].max(initial=0) <= traj_tol, (step, diffs.max())
         assert diffs.max() <= 2e-5, (step, diffs.max())
         ok = q["status"] == 0
         rel = np.abs(out["qp_cost"] - q["cost"]) / np.maximum(1.0, np.abs(q["cost"]))
         assert rel[ok & ~in_band].max(initial=0) <= 1e-6 and rel[ok].max(initial=0) <= 1e-5
-        assert np.array_equal(out["flags"], q["flags"])
+        assert np.array_equal(out["flags"] & 3, q["flags"])          # bits 0-1: the reference's conditions; the rest: engine diagnostics
         sw.advance()
         p2, v2, a2 = sw.state()
         assert np.abs(out["next_position"] - p2).max() <= 2e-5
@@ -416,9 +416,9 @@ def _teacher_forced_all_agents(workload, agents, skip, steps):
         if use_map:
             assert np.array_equal(e.get_sfc()[0].view(np.uint32), sw.boxes().view(np.uint32)), step
         assert np.array_equal(out["qp_status"], q["status"]), (step, np.flatnonzero(out["qp_status"] != q["status"]))
-        assert np.array_equal(out["flags"], q["flags"])
+        assert np.array_equal(out["flags"] & 3, q["flags"])          # bits 0-1: the reference's conditions; the rest: engine diagnostics
         diffs = np.abs(out["traj"] - sw.traj()).reshape(n, -1).max(1)
-        in_band = q["maxviol"] > 1e-9
+        in_band = (q["maxviol"] > 1e-9) | ((out["flags"] & 64) != 0)     # rows inside the feasibility band, at either solution
         ok = q["status"] == 0
         assert diffs[~in_band].max(initial=0) <= tol_exact, (step, diffs[~in_band].max(), tol_exact)
         assert diffs.max() <= 2e-5, (step, diffs.max())
