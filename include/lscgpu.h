@@ -171,6 +171,15 @@ int lscgpu_get_distmap_sqdist(lscgpu_engine* e, uint8_t* out /* size[0]*size[1]*
 int lscgpu_set_shard(lscgpu_engine* e, int a0, int a1);
 int lscgpu_nccl_unique_id(uint8_t id_out[128]);
 int lscgpu_nccl_init(lscgpu_engine* e, const uint8_t id[128], int rank, int n_ranks);
+/* Direct exchange over NVLink peer memory (optional, after lscgpu_nccl_init; one process per GPU on one node): instead of the
+ * all-gather, every planning block stores its finished record straight into every peer's buffer the moment the agent is
+ * planned (the transfer overlaps the planning of the other agents) and bumps an arrival counter there; the commit kernel of
+ * each rank waits for the counters. lscgpu_p2p_export returns the CUDA IPC handle of this rank's exchange buffer; gather the
+ * handles of all ranks in rank order (any out-of-band channel) and pass them to lscgpu_p2p_attach on every rank. Results are
+ * identical to the all-gather path. A peer whose records do not arrive within 2 s makes the next synchronising call fail
+ * with LSCGPU_ERR_NCCL instead of hanging the device. */
+int lscgpu_p2p_export(lscgpu_engine* e, uint8_t handle_out[64]);
+int lscgpu_p2p_attach(lscgpu_engine* e, const uint8_t* handles /* [n_ranks][64] */);
 
 /* ---- the replanning step ------------------------------------------------------------------------
  * Replaces the loop `for qi: agents[qi]->plan(sim_current_time)` of MultiSyncSimulator::plan()

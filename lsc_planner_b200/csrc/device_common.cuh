@@ -57,6 +57,25 @@ struct __align__(16) GatherSlot {
 };
 static_assert(sizeof(GatherSlot) % 16 == 0, "gather slot must be a multiple of 16 bytes");
 
+// Direct exchange over NVLink peer memory (lscgpu_p2p_attach) instead of the all-gather. Every rank owns one exchange
+// buffer: two parities of the gather buffer (a step writes the parity of its epoch, so a rank that is one step ahead never
+// overwrites slots a slower peer is still committing) followed by one arrival counter per source rank. A planning block
+// stores its finished slot into every peer's buffer through the peer mapping, fences, and bumps the peer's counter for this
+// rank; k_commit waits until the counter of a slot's source rank has reached the count this step brings it to.
+struct PeerExchange {
+    GatherSlot* const* peers;      // null: off. Device array [n_ranks]: every rank's exchange buffer as mapped on this device
+    int n_ranks, rank;
+    int slots;                     // slots per parity (= block * n_ranks)
+    int block;                     // slots per rank
+    int n_agents;
+    int base_epoch;                // epoch of the first step that uses the exchange
+    __host__ __device__ static size_t counters_offset(int slots) { return (sizeof(GatherSlot) * 2 * (size_t)slots + 255) & ~(size_t)255; }
+    __device__ int* counters(int r) const {
+        return reinterpret_cast<int*>(reinterpret_cast<char*>(peers[r]) + counters_offset(slots));
+    }
+    __device__ int planned_by(int r) const { return (n_agents - r + n_ranks - 1) / n_ranks; }
+};
+
 // ---- small float3/double3 helpers with explicit IEEE roundings ----------------------------------
 // The reference's geometry is octomap::point3d = float32 with float arithmetic.
 // Where the rounding sequence matters for parity (predictions, normals, margins, terminal-segment count)

@@ -138,6 +138,15 @@ struct lscgpu_engine {
     GatherSlot* d_gather = nullptr;        // [n_slots] records (+ active rows) in scheduling order, rank-major: the all-gather buffer
     unsigned short* d_act_prev = nullptr;  // [N][kActSlots] rows active at every agent's previous solve (warm-start candidates)
     bool warm_start = true;
+    // direct exchange over peer memory (lscgpu_p2p_export / lscgpu_p2p_attach): this rank's exchange buffer, the peers'
+    // buffers as mapped here, the device copy of those pointers
+    GatherSlot* d_xchg = nullptr;
+    std::vector<void*> peer_ptrs;
+    GatherSlot** d_peers = nullptr;
+    bool p2p = false;
+    int p2p_base_epoch = 0;
+    int* d_commit_done = nullptr;          // k_commit's "last block" counter
+    int* h_xchg_err = nullptr; int* d_xchg_err_map = nullptr;      // mapped host word: a peer's records did not arrive in time
     lscgpu_agent_out* d_res = nullptr;     // [N] the same records in agent order (k_commit)
     int n_slots = 0;
     float *d_traj = nullptr, *d_pred = nullptr, *d_predT = nullptr, *d_predZs = nullptr, *d_boxes = nullptr;
@@ -225,6 +234,11 @@ extern "C" void lscgpu_destroy(lscgpu_engine* e) {
     if (e->stream) cudaStreamSynchronize(e->stream);      // the aux stream is joined into this one inside every step
     drop_graph(e);
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+    for (size_t r = 0; r < e->peer_ptrs.size(); r++)
+        if ((int)r != e->rank && e->peer_ptrs[r]) cudaIpcCloseMemHandle(e->peer_ptrs[r]);
+    if (e->p2p) e->d_gather = nullptr;                      // it pointed into d_xchg
+    cudaFree(e->d_xchg); cudaFree(e->d_peers); cudaFree(e->d_commit_done);
+    if (e->h_xchg_err) cudaFreeHost(e->h_xchg_err);
     free_rows(e);
     e->scratch.release();
     cudaFree(e->d_order); cudaFree(e->d_block_of);
@@ -257,7 +271,9 @@ static int reset_state(lscgpu_engine* e) {
     CU(cudaMemsetAsync(e->d_last_cost, 0, sizeof(double) * N, e->stream));
     CU(cudaMemsetAsync(e->d_in, 0, sizeof(lscgpu_agent_in) * N, e->stream));
     CU(cudaMemsetAsync(e->d_res, 0, sizeof(lscgpu_agent_out) * N, e->stream));
-    CU(cudaMemsetAsync(e->d_gather, 0xff, sizeof(GatherSlot) * (size_t)e->n_slots, e->stream));   // agent_id = -1: empty slot
+    // agent_id = -1: empty slot. Not with the direct exchange: a peer that is already in its next step may be writing into
+    // this buffer; its unused slots were marked empty when the buffer was made and are never written
+    if (!e->p2p) CU(cudaMemsetAsync(e->d_gather, 0xff, sizeof(GatherSlot) * (size_t)e->n_slots, e->stream));
     CU(cudaMemsetAsync(e->d_act_prev, 0, sizeof(unsigned short) * kActSlots * N, e->stream));     // no candidates: cold starts
     CU(cudaMemsetAsync(e->d_block_of, 0xff, sizeof(int) * N, e->stream));
     CU(cudaMemsetAsync(e->d_reset_ever, 0, N, e->stream));                              // obs_slack_indices start empty
@@ -375,6 +391,11 @@ extern "C" int lscgpu_create(const lscgpu_params* p, int n_agents, const lscgpu_
     CUB(cudaHostGetDevicePointer(&e->d_kept_last_map, e->h_kept_last, 0));
     CUB(cudaMalloc(&e->d_epoch, sizeof(int)));
     CUB(cudaMemset(e->d_epoch, 0, sizeof(int)));
+    CUB(cudaMalloc(&e->d_commit_done, sizeof(int)));
+    CUB(cudaMemset(e->d_commit_done, 0, sizeof(int)));
+    CUB(cudaHostAlloc(&e->h_xchg_err, sizeof(int), cudaHostAllocMapped));
+    *e->h_xchg_err = 0;
+    CUB(cudaHostGetDevicePointer(&e->d_xchg_err_map, e->h_xchg_err, 0));
     CUB(cudaMalloc(&e->d_reset_ever, N));
     CUB(cudaMalloc(&e->d_any_reset, sizeof(int)));
     CUB(cudaMalloc(&e->d_sfc_ready, sizeof(int) * N));
@@ -551,6 +572,61 @@ extern "C" int lscgpu_nccl_init(lscgpu_engine* e, const uint8_t id_bytes[128], i
     return alloc_rows(e);
 }
 
+// Direct exchange over NVLink peer memory. lscgpu_p2p_export makes this rank's exchange buffer (two parities of the gather
+// buffer + one arrival counter per source rank) and returns its CUDA IPC handle; the caller hands every rank's handle to
+// lscgpu_p2p_attach (any out-of-band channel), which maps the peers' buffers and switches the step from ncclAllGather to
+// stores by the planning blocks (k_agent_plan epilogue, k_commit).
+extern "C" int lscgpu_p2p_export(lscgpu_engine* e, uint8_t handle_out[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    if (!e || !handle_out) return fail(LSCGPU_ERR_ARG, "null argument");
+    if (!e->comm) return fail(LSCGPU_ERR_STATE, "lscgpu_nccl_init first (it fixes rank, n_ranks and the slot layout)");
+    if (e->pending) return fail(LSCGPU_ERR_STATE, "lscgpu_synchronize first");
+    if (e->n_ranks > 32) return fail(LSCGPU_ERR_ARG, "direct exchange supports up to 32 ranks");
+    CU(cudaSetDevice(e->device));
+    if (!e->d_xchg) {
+        const int slots = e->block * e->n_ranks;
+        const size_t bytes = PeerExchange::counters_offset(slots) + sizeof(int) * (size_t)e->n_ranks;
+        CU(cudaMalloc(&e->d_xchg, bytes));
+        CU(cudaMemset(e->d_xchg, 0xff, sizeof(GatherSlot) * 2 * (size_t)slots));
+        CU(cudaMemset((char*)e->d_xchg + PeerExchange::counters_offset(slots), 0, sizeof(int) * (size_t)e->n_ranks));
+        CU(cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, e->d_xchg));
+    std::memcpy(handle_out, &h, 64);
+    return LSCGPU_OK;
+}
+
+extern "C" int lscgpu_p2p_attach(lscgpu_engine* e, const uint8_t* handles) {
+    if (!e || !handles) return fail(LSCGPU_ERR_ARG, "null argument");
+    if (!e->d_xchg) return fail(LSCGPU_ERR_STATE, "lscgpu_p2p_export first");
+    if (e->p2p) return fail(LSCGPU_ERR_STATE, "the direct exchange is already attached");
+    if (e->pending) return fail(LSCGPU_ERR_STATE, "lscgpu_synchronize first");
+    CU(cudaSetDevice(e->device));
+    e->peer_ptrs.assign(e->n_ranks, nullptr);
+    for (int r = 0; r < e->n_ranks; r++) {
+        if (r == e->rank) { e->peer_ptrs[r] = e->d_xchg; continue; }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, handles + 64 * (size_t)r, 64);
+        void* p = nullptr;
+        const cudaError_t rc = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (rc != cudaSuccess) {
+            for (int q = 0; q < r; q++) if (q != e->rank && e->peer_ptrs[q]) cudaIpcCloseMemHandle(e->peer_ptrs[q]);
+            e->peer_ptrs.clear();
+            return fail(LSCGPU_ERR_CUDA, std::string("cudaIpcOpenMemHandle (rank ") + std::to_string(r) + "): " + cudaGetErrorString(rc));
+        }
+        e->peer_ptrs[r] = p;
+    }
+    CU(cudaMalloc(&e->d_peers, sizeof(void*) * (size_t)e->n_ranks));
+    CU(cudaMemcpy(e->d_peers, e->peer_ptrs.data(), sizeof(void*) * (size_t)e->n_ranks, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(&e->p2p_base_epoch, e->d_epoch, sizeof(int), cudaMemcpyDeviceToHost));
+    drop_graph(e);
+    cudaFree(e->d_gather);                                  // the step now writes into the exchange buffer
+    e->d_gather = e->d_xchg;
+    e->p2p = true;
+    return LSCGPU_OK;
+}
+
 // ---- the step ----------------------------------------------------------------------------------------------------
 // Kernels of one step on the engine stream `s` (k_qp_order forks onto the aux stream and is joined before the plan):
 //   k_qp_order || k_predict [-> k_goal_plan] -> k_agent_plan -> [ncclAllGather] -> k_commit
@@ -632,6 +708,12 @@ static int enqueue_step_kernels(lscgpu_engine* e, int planner_seq, int threads, 
     L.max_iter = e->max_iter;
     L.out = e->d_gather; L.out_base = dealt ? e->rank * e->block : 0;
     L.act_prev = e->warm_start ? e->d_act_prev : nullptr;
+    PeerExchange px{};
+    if (e->p2p) {
+        px.peers = e->d_peers; px.n_ranks = e->n_ranks; px.rank = e->rank; px.slots = e->block * e->n_ranks; px.block = e->block;
+        px.n_agents = e->N; px.base_epoch = e->p2p_base_epoch;
+    }
+    L.px = px;
     L.prev_traj = e->d_traj; L.last_cost = e->d_last_cost; L.goal_kind = e->d_goal_kind;
     L.counters = e->d_counters;
     L.any_reset = e->slack_kernel ? e->d_any_reset : nullptr; L.reset_ever = e->d_reset_ever;
@@ -640,8 +722,9 @@ static int enqueue_step_kernels(lscgpu_engine* e, int planner_seq, int threads, 
     if (n_plan > 0) { launch_agent_plan(L, s); launches += L.any_reset ? 2 : 1; }
     if (ev) CU(cudaEventRecord(ev[2], s));
 
-    if (dealt && e->n_ranks > 1) {
-        // in-place all-gather: every rank's block of records lands in every replica
+    if (dealt && e->n_ranks > 1 && !e->p2p) {
+        // in-place all-gather: every rank's block of records lands in every replica (with the direct exchange the planning
+        // blocks have already stored them into every peer's buffer)
         const size_t bytes = sizeof(GatherSlot) * (size_t)e->block;
         const int rc = g_nccl.AllGather((const char*)e->d_gather + bytes * e->rank, e->d_gather, bytes, /*ncclInt8*/ 0, e->comm, s);
         if (rc != 0) return fail(LSCGPU_ERR_NCCL, std::string("ncclAllGather: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
@@ -650,7 +733,8 @@ static int enqueue_step_kernels(lscgpu_engine* e, int planner_seq, int threads, 
     const int n_slots = dealt ? e->block * e->n_ranks : n_plan;
     if (use_sfc && n_plan > 0 && side) CU(cudaStreamWaitEvent(s, e->ev_sfc, 0));     // k_commit rewrites what k_sfc_step reads
     launch_commit(n_slots, e->d_gather, e->d_res, e->d_act_prev, e->d_traj, e->d_in, e->d_last_cost,
-                  use_sfc ? e->d_boxes : nullptr, e->d_init_sfc, e->d_epoch, e->d_kept_step, e->d_kept_last_map, s); launches++;
+                  use_sfc ? e->d_boxes : nullptr, e->d_init_sfc, e->d_epoch, e->d_kept_step, e->d_kept_last_map, px, e->d_commit_done,
+                  e->d_xchg_err_map, s); launches++;
     if (ev) CU(cudaEventRecord(ev[4], s));
     *launches_out = launches;
     return LSCGPU_OK;
@@ -738,6 +822,10 @@ static int step_device(lscgpu_engine* e) {
 // wait for the enqueued steps; the statistics of the batch are computed when somebody asks for them
 static int finish_steps(lscgpu_engine* e) {
     CU(cudaStreamSynchronize(e->stream));
+    if (e->h_xchg_err && *(volatile int*)e->h_xchg_err) {
+        *e->h_xchg_err = 0;
+        return fail(LSCGPU_ERR_NCCL, "direct exchange: a peer's records did not arrive within 2 s (ranks out of step?)");
+    }
     if (e->pending > 0) {
         e->done_steps = e->pending; e->done_launches = e->pending_launches;
         e->stats_fresh = false;

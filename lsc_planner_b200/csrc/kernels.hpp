@@ -106,6 +106,7 @@ struct PlanLaunch {
     int max_iter;
     // outputs
     GatherSlot* out;               // block i writes slot out[out_base + i] (gather buffer: rank-major, carries agent_id)
+    PeerExchange px;               // px.peers != null: the block also stores its slot into every peer's buffer
     const unsigned short* act_prev;    // null (cold starts), or [N][kActSlots]: rows active at every agent's previous solve
     int out_base;
     const float* prev_traj;        // [N][90]  (kept when the QP fails)
@@ -169,7 +170,8 @@ void launch_qp_order(int n, int a0, const lscgpu_agent_out* res, int* order, cud
 // (and, with an octomap, the agent's SFC window takes the step's new box, src/traj_planner.cpp:1451-1491)
 void launch_commit(int n_slots, const GatherSlot* gather, lscgpu_agent_out* res, unsigned short* act_prev, float* prev_traj,
                    lscgpu_agent_in* in, double* last_cost, float* boxes /* null: no octomap */, int* init_sfc, int* epoch,
-                   int* kept_step, volatile int* kept_host /* mapped host word or null */, cudaStream_t s);
+                   int* kept_step, volatile int* kept_host /* mapped host word or null */, PeerExchange px, int* done_count,
+                   volatile int* err_host /* mapped host word: 1 = a peer's records did not arrive in time */, cudaStream_t s);
 
 // safety audit of the planned step (src/multi_sync_simulator.cpp:446-475)
 void launch_safety_audit(int n_agents, const float* traj, const AgentConstDev* consts, double dt, int n_samples,

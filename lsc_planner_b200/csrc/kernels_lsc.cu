@@ -332,22 +332,45 @@ void launch_rows_from_lsc(int n_problems, const int* obs_offset, int total_obs, 
 // box (generateFeasibleSFC, src/traj_planner.cpp:1451-1491) — on every replica, so any rank can plan the agent next.
 // Slots with agent_id < 0 are empty (ranks that own fewer agents).
 // ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
 __global__ void __launch_bounds__(128) k_commit(int n_slots, const GatherSlot* gather, lscgpu_agent_out* res,
                                                 unsigned short* act_prev, float* prev_traj, lscgpu_agent_in* in,
                                                 double* last_cost, float* boxes, int* init_sfc, int* epoch, int* kept_step,
-                                                volatile int* kept_host) {
+                                                volatile int* kept_host, PeerExchange px, int* done_count,
+                                                volatile int* err_host) {
     const int slot = blockIdx.x;
     const int e = threadIdx.x;
     if (slot == 0 && e == 0) {
-        if (epoch) *epoch += 1;
         if (kept_step) {            // kept pairs of the step just planned: the host picks the next steps' block size from it
             if (kept_host) { *kept_host = *kept_step; __threadfence_system(); }
             *kept_step = 0;
         }
     }
+    const int ep = *epoch;          // stable while the kernel runs: the last block to finish bumps it
+    if (px.peers) {
+        // direct exchange: this step's slots are in the parity of its epoch; wait for the slot's source rank
+        gather += (size_t)(ep & 1) * px.slots;
+        if (e == 0) {
+            const int src = slot / px.block;
+            const int expected = (ep - px.base_epoch + 1) * px.planned_by(src);
+            volatile const int* cnt = px.counters(px.rank) + src;
+            const unsigned long long t0 = global_ns();
+            while (*cnt < expected) {
+                if (global_ns() - t0 > 2000000000ull) { *err_host = 1; __threadfence_system(); break; }    // never hang the device
+                __nanosleep(100);
+            }
+            __threadfence_system();
+        }
+        __syncthreads();
+    }
     const lscgpu_agent_out& o = gather[slot].rec;
     const int a = o.agent_id;
-    if (a < 0) return;
+    if (a >= 0) {
     if (e >= 64 && e < 64 + kActSlots) act_prev[(size_t)a * kActSlots + (e - 64)] = gather[slot].act[e - 64];
     // the record, 16 bytes per thread
     constexpr int kVec = sizeof(lscgpu_agent_out) / 16;
@@ -369,13 +392,20 @@ __global__ void __launch_bounds__(128) k_commit(int n_slots, const GatherSlot* g
         if (e >= 96 && e < 126) bx[e - 96] = v;
         if (e == 127) init_sfc[a] = 0;
     }
+    }
+    // the last block to finish closes the step: epoch + 1 (k_sfc_step / k_agent_plan of the next step stamp with it)
+    __syncthreads();
+    if (e == 0) {
+        __threadfence();
+        if (atomicAdd(done_count, 1) == (int)gridDim.x - 1) { *done_count = 0; *epoch = ep + 1; }
+    }
 }
 void launch_commit(int n_slots, const GatherSlot* gather, lscgpu_agent_out* res, unsigned short* act_prev, float* prev_traj,
                    lscgpu_agent_in* in, double* last_cost, float* boxes, int* init_sfc, int* epoch, int* kept_step,
-                   volatile int* kept_host, cudaStream_t s) {
+                   volatile int* kept_host, PeerExchange px, int* done_count, volatile int* err_host, cudaStream_t s) {
     if (n_slots > 0)
         k_commit<<<n_slots, 128, 0, s>>>(n_slots, gather, res, act_prev, prev_traj, in, last_cost, boxes, init_sfc, epoch, kept_step,
-                                         kept_host);
+                                         kept_host, px, done_count, err_host);
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -369,7 +369,9 @@ __global__ void __launch_bounds__(kPlanThreads, kSlack ? (kPlanThreads > 256 ? 1
             if (R.warm > 0) { atomicAdd(&L.counters->warm_accepted, 1ull); atomicAdd(&L.counters->warm_rows, (unsigned long long)R.warm); }
         }
     }
-    GatherSlot& slot_out = L.out[L.out_base + bi];
+    // direct exchange: the step's slots live in the parity of its epoch
+    const int xparity = L.px.peers ? (*L.epoch & 1) : 0;
+    GatherSlot& slot_out = L.out[(size_t)xparity * L.px.slots + L.out_base + bi];
     lscgpu_agent_out& o = slot_out.rec;
     float* tr = &o.traj[0][0][0];
     const bool ok = R.status == LSCGPU_QP_OK;
@@ -443,6 +445,27 @@ __global__ void __launch_bounds__(kPlanThreads, kSlack ? (kPlanThreads > 256 ? 1
             L.dbg[(size_t)bi * 10 + 9] = sec[7];
         }
 #endif
+    }
+    if (L.px.peers) {
+        // The finished slot goes straight into every peer's exchange buffer (stores through the NVLink peer mapping, 16 bytes
+        // per lane), then the peer's arrival counter for this rank is bumped: the transfer of one agent's record overlaps the
+        // planning of the others, and k_commit on the peer starts as soon as the last one has landed.
+        __syncwarp();
+        constexpr int kVec = (int)(sizeof(GatherSlot) / 16);
+        const uint4* src = reinterpret_cast<const uint4*>(&slot_out);
+        uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
+        if (lane < kVec) v0 = src[lane];
+        if (lane + 32 < kVec) v1 = src[lane + 32];
+        static_assert(kVec <= 64, "slot larger than two vectors per lane");
+        for (int r = 0; r < L.px.n_ranks; r++) {
+            if (r == L.px.rank) continue;
+            uint4* dst = reinterpret_cast<uint4*>(L.px.peers[r] + (size_t)xparity * L.px.slots + L.out_base + bi);
+            if (lane < kVec) dst[lane] = v0;
+            if (lane + 32 < kVec) dst[lane + 32] = v1;
+        }
+        __threadfence_system();
+        __syncwarp();
+        if (lane < L.px.n_ranks) atomicAdd_system(L.px.counters(lane) + L.px.rank, 1);
     }
 }
 

@@ -139,6 +139,18 @@ class ReplanEngine:
         self.a0, self.a1 = 0, self.n
         self.rank, self.n_ranks = rank, n_ranks
 
+    def p2p_export(self) -> bytes:
+        """CUDA IPC handle of this rank's exchange buffer (direct exchange over NVLink peer memory)."""
+        h = np.zeros(64, np.uint8)
+        A.check(self.lib.lscgpu_p2p_export(self.h, A.p(h)))
+        return h.tobytes()
+
+    def p2p_attach(self, handles: Sequence[bytes]):
+        """Map every rank's exchange buffer (handles in rank order) and switch the step to the direct exchange."""
+        buf = np.frombuffer(b"".join(handles), np.uint8).copy()
+        assert len(buf) == 64 * len(handles)
+        A.check(self.lib.lscgpu_p2p_attach(self.h, A.p(buf)))
+
     @property
     def n_planned(self) -> int:
         """Agents this engine plans per step."""

@@ -56,10 +56,21 @@ def broadcast_bytes(payload: bytes | None, src: int = 0) -> bytes:
     return box[0]
 
 
-def connect(engine, rank: int, world: int):
-    """Create the engine's NCCL communicator: rank 0 makes the unique id, everybody joins."""
+def connect(engine, rank: int, world: int, p2p: bool | None = None):
+    """Create the engine's NCCL communicator: rank 0 makes the unique id, everybody joins. Then (p2p, default on unless
+    LSCGPU_P2P=0) switch the exchange to direct stores over NVLink peer memory: the ranks swap the CUDA IPC handles of their
+    exchange buffers over torch.distributed and map each other's."""
+    import os
+    import torch.distributed as dist
     uid = broadcast_bytes(engine.nccl_unique_id() if rank == 0 else None)
     engine.nccl_init(uid, rank, world)
+    if p2p is None:
+        p2p = os.environ.get("LSCGPU_P2P", "1") != "0"
+    if p2p and world > 1:
+        handles = [None] * world
+        dist.all_gather_object(handles, engine.p2p_export())
+        engine.p2p_attach(handles)
+        dist.barrier()
     return engine
 
 
