@@ -232,6 +232,13 @@ int lscgpu_get_lsc(lscgpu_engine* e, int agent, float* normals, double* d);
  * ones are recomputed. The agent must have been planned by this engine in the last step. */
 int lscgpu_set_capture_rows(lscgpu_engine* e, int on);
 int lscgpu_get_lsc_ex(lscgpu_engine* e, int agent, float* normals, double* d, uint8_t* kept);
+/* The QP the engine solved for `agent` in the last step as a CPLEX LP file: replaces cplex.exportModel(".../log/QPmodel.lp")
+ * (src/traj_optimizer.cpp:62-69,99-101,146-149). Variables, rows and their order are populatebyrow's; with obs_slack_indices
+ * not empty the epsilon_slack_<oi>_<m> variables are included. lscgpu_set_lp_dump_dir: every lscgpu_replan_batch writes
+ * <dir>/QPmodel_agent<id>_seq<planner_seq>.lp for each agent whose QP failed, as the reference does on an IloException
+ * (NULL or "" switches it off). */
+int lscgpu_dump_qp_lp(lscgpu_engine* e, int agent, const char* path);
+int lscgpu_set_lp_dump_dir(lscgpu_engine* e, const char* dir);
 /* initial_traj of every agent of the last step (= the prediction its neighbours used), float[n_agents][90]. */
 int lscgpu_get_initial_traj(lscgpu_engine* e, float* out);
 

@@ -67,7 +67,7 @@ def symbols():
             "lscgpu_set_states", "lscgpu_replan_resident", "lscgpu_synchronize", "lscgpu_fetch", "lscgpu_reset", "lscgpu_set_prev_traj",
             "lscgpu_set_sfc", "lscgpu_get_sfc", "lscgpu_get_planner_seq", "lscgpu_get_lsc", "lscgpu_get_lsc_ex",
             "lscgpu_set_slack_collision_weight", "lscgpu_get_reset_state", "lscgpu_set_reset_state",
-            "lscgpu_set_capture_rows",
+            "lscgpu_set_capture_rows", "lscgpu_dump_qp_lp", "lscgpu_set_lp_dump_dir",
             "lscgpu_get_initial_traj", "lscgpu_qp_solve_batch", "lscgpu_qp_solve_batch_slack", "lscgpu_gjk_batch",
             "lscgpu_sfc_expand_batch",
             "lscgpu_get_step_stats", "lscgpu_set_profiling", "lscgpu_sm_clock_khz", "lscgpu_stream",
@@ -114,6 +114,8 @@ def lib():
     L.lscgpu_get_lsc.argtypes = [ptr, C.c_int, ptr, ptr]
     L.lscgpu_get_lsc_ex.argtypes = [ptr, C.c_int, ptr, ptr, ptr]
     L.lscgpu_set_capture_rows.argtypes = [ptr, C.c_int]
+    L.lscgpu_dump_qp_lp.argtypes = [ptr, C.c_int, C.c_char_p]
+    L.lscgpu_set_lp_dump_dir.argtypes = [ptr, C.c_char_p]
     L.lscgpu_get_initial_traj.argtypes = [ptr, ptr]
     L.lscgpu_qp_solve_batch.argtypes = [ptr, C.c_int] + [ptr] * 12
     L.lscgpu_qp_solve_batch_slack.argtypes = [ptr, C.c_int] + [ptr] * 14

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "kernels.hpp"
+#include "lp_dump.hpp"
 #include "octomap_bt.hpp"
 
 using namespace lscgpu;
@@ -143,6 +144,7 @@ struct lscgpu_engine {
     GatherSlot* d_xchg = nullptr;
     std::vector<void*> peer_ptrs;
     GatherSlot** d_peers = nullptr;
+    std::string lp_dump_dir;               // not empty: lscgpu_replan_batch writes the LP of every failed QP there
     bool p2p = false;
     int p2p_base_epoch = 0;
     int* d_commit_done = nullptr;          // k_commit's "last block" counter
@@ -892,6 +894,8 @@ static int compute_stats(lscgpu_engine* e) {
     return LSCGPU_OK;
 }
 
+static int dump_qp_lp(lscgpu_engine* e, int agent, const char* path);
+
 extern "C" int lscgpu_replan_batch(lscgpu_engine* e, const lscgpu_agent_in* in, lscgpu_agent_out* out) {
     if (!e || !in || !out) return fail(LSCGPU_ERR_ARG, "null argument");
     CU(cudaSetDevice(e->device));
@@ -899,7 +903,16 @@ extern "C" int lscgpu_replan_batch(lscgpu_engine* e, const lscgpu_agent_in* in, 
     const int rc = step_device(e);
     if (rc != LSCGPU_OK) return rc;
     CU(cudaMemcpyAsync(out, e->d_res, sizeof(lscgpu_agent_out) * (size_t)e->N, cudaMemcpyDeviceToHost, e->stream));
-    return finish_steps(e);
+    const int rf = finish_steps(e);
+    if (rf != LSCGPU_OK || e->lp_dump_dir.empty()) return rf;
+    // as the reference on an IloException (src/traj_optimizer.cpp:99-101): the model of every failed solve goes to a file
+    for (int a = 0; a < e->N; a++)
+        if (out[a].qp_status != LSCGPU_QP_OK) {
+            const std::string path = e->lp_dump_dir + "/QPmodel_agent" + std::to_string(a) + "_seq" + std::to_string(e->planner_seq) + ".lp";
+            const int rd = dump_qp_lp(e, a, path.c_str());
+            if (rd != LSCGPU_OK) return rd;
+        }
+    return LSCGPU_OK;
 }
 
 extern "C" int lscgpu_replan_resident(lscgpu_engine* e) {
@@ -1091,6 +1104,61 @@ extern "C" int lscgpu_get_lsc_ex(lscgpu_engine* e, int agent, float* normals, do
 
 extern "C" int lscgpu_get_lsc(lscgpu_engine* e, int agent, float* normals, double* d) {
     return lscgpu_get_lsc_ex(e, agent, normals, d, nullptr);
+}
+
+// The QP the engine solved for `agent` in the last step, as a CPLEX LP file (what the reference exports to log/QPmodel.lp
+// when a solve fails or param.log is set, src/traj_optimizer.cpp:62-69,99-101): state, goal, terminal segments, SFC window
+// and predictions are the step's own (device copies), the LSC rows are recomputed from the predictions.
+static int dump_qp_lp(lscgpu_engine* e, int agent, const char* path) {
+    const size_t n_obs = (size_t)e->N - 1;
+    CU(cudaStreamSynchronize(e->stream));
+    std::vector<float> normals(std::max<size_t>(n_obs, 1) * 15), pred((size_t)e->N * kTrajFloats), boxes(30);
+    std::vector<double> d(std::max<size_t>(n_obs, 1) * 30);
+    if (n_obs > 0) {
+        const int rc = lscgpu_get_lsc_ex(e, agent, normals.data(), d.data(), nullptr);
+        if (rc != LSCGPU_OK) return rc;
+    }
+    CU(cudaMemcpy(pred.data(), e->d_pred, sizeof(float) * pred.size(), cudaMemcpyDeviceToHost));
+    std::vector<float> points(std::max<size_t>(n_obs, 1) * 90);
+    for (size_t o = 0; o < n_obs; o++) {
+        const size_t j = (int)o < agent ? o : o + 1;
+        std::memcpy(points.data() + o * 90, pred.data() + j * kTrajFloats, sizeof(float) * 90);
+    }
+    std::vector<unsigned char> ever((size_t)e->N), slack(std::max<size_t>(n_obs, 1), 0);
+    CU(cudaMemcpy(ever.data(), e->d_reset_ever, (size_t)e->N, cudaMemcpyDeviceToHost));
+    bool any = false;
+    for (int a = 0; a < e->N; a++) any |= ever[a] != 0;
+    for (size_t o = 0; o < n_obs; o++) slack[o] = ever[agent] || ever[(int)o < agent ? o : o + 1];
+    LpProblem p{};
+    p.dt = e->prm.dt; p.w = e->prm.control_input_weight; p.wT = e->prm.terminal_weight;
+    CU(cudaMemcpy(p.state, e->d_state9 + (size_t)agent * 9, sizeof(double) * 9, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(p.goal, e->d_goal3 + (size_t)agent * 3, sizeof(double) * 3, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&p.ts, e->d_ts + agent, sizeof(int), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 3; k++) { p.wmin[k] = e->prm.world_min[k]; p.wmax[k] = e->prm.world_max[k]; }
+    if (e->prm.world_use_octomap) {
+        CU(cudaMemcpy(boxes.data(), e->d_boxes + (size_t)agent * 30, sizeof(float) * 30, cudaMemcpyDeviceToHost));
+        p.boxes = boxes.data();
+    }
+    p.n_obs = (int)n_obs; p.normals = normals.data(); p.points = points.data(); p.d = d.data();
+    p.slack = any ? slack.data() : nullptr; p.slack_w = e->slack_w;
+    const lscgpu_agent_const& c = e->consts_host[agent];
+    for (int k = 0; k < 3; k++) { p.vmax[k] = c.max_vel[k]; p.amax[k] = c.max_acc[k]; }
+    std::string err;
+    if (!write_qp_lp(path, p, err)) return fail(LSCGPU_ERR_IO, err);
+    return LSCGPU_OK;
+}
+
+extern "C" int lscgpu_dump_qp_lp(lscgpu_engine* e, int agent, const char* path) {
+    if (!e || !path || agent < 0 || agent >= e->N) return fail(LSCGPU_ERR_ARG, "bad argument");
+    if (e->planner_seq < 1) return fail(LSCGPU_ERR_STATE, "no step has been planned yet");
+    CU(cudaSetDevice(e->device));
+    return dump_qp_lp(e, agent, path);
+}
+
+extern "C" int lscgpu_set_lp_dump_dir(lscgpu_engine* e, const char* dir) {
+    if (!e) return fail(LSCGPU_ERR_ARG, "null engine");
+    e->lp_dump_dir = dir ? dir : "";
+    return LSCGPU_OK;
 }
 
 extern "C" int lscgpu_get_initial_traj(lscgpu_engine* e, float* out) {

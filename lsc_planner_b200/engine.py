@@ -259,6 +259,14 @@ class ReplanEngine:
         A.check(self.lib.lscgpu_get_lsc_ex(self.h, agent, A.p(nr), A.p(d), A.p(kept)))
         return nr, d, kept.astype(bool)
 
+    def dump_qp_lp(self, agent: int, path: str):
+        """The QP of `agent` in the last step as a CPLEX LP file (the reference's log/QPmodel.lp)."""
+        A.check(self.lib.lscgpu_dump_qp_lp(self.h, agent, path.encode()))
+
+    def set_lp_dump_dir(self, directory: Optional[str]):
+        """Write the LP of every failed QP of every replan() into `directory` (None: off)."""
+        A.check(self.lib.lscgpu_set_lp_dump_dir(self.h, directory.encode() if directory else None))
+
     def initial_traj(self):
         out = np.zeros((self.n, 5, 6, 3), np.float32)
         A.check(self.lib.lscgpu_get_initial_traj(self.h, A.p(out)))

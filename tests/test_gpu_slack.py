@@ -181,3 +181,71 @@ def test_reference_lp_dump_with_slack(golden_dir):
     # no member: the plain entry, infeasible as recorded
     r = e.qp_solve_batch([0], st, g["goal"], [0, n_obs], normal, point, d, obs_slack=np.zeros(n_obs, np.uint8))
     assert r["status"][0] == 1 and not r["eps"].any()
+
+
+def test_lp_dump_of_a_failed_qp(tmp_path):
+    """The engine's LP dump (the reference's log/QPmodel.lp, written on a failed solve): parsed back, it is the problem the
+    oracle assembles for the same agent — coefficient for coefficient up to the 15 printed digits — and the independent
+    NNLS solve calls it infeasible too; the dump of a solved agent reproduces the engine's trajectory."""
+    import lsc_planner_b200 as L
+    import qp_pyref as R
+    scn = _ring(8, 1.2)
+    n = scn.n
+    sw = O.Swarm(n, scn.world_min, scn.world_max, reset_threshold=1e9); sw.set_state(scn.start); sw.set_goals(scn.goal); sw.set_capture(True)
+    e = L.ReplanEngine(n, L.Param(world_min=scn.world_min, world_max=scn.world_max, reset_threshold=1e9), scn.agents)
+    e.set_lp_dump_dir(str(tmp_path))
+    T = O.Tables()
+    failed_seen = 0
+    for step in range(8):
+        pos, vel, acc = sw.state()
+        if step == 5:            # thrown onto a neighbour, but below the (huge) reset threshold: no slack variables, the QP fails
+            pos[2] = pos[2] + (pos[3] - pos[2]) * 0.8; vel[2] = 0; acc[2] = 0
+            sw.set_state(pos, vel, acc)
+        e.set_prev_traj(sw.traj(), sw.seq)
+        sw.step()
+        out = e.replan(pos, vel, acc, scn.goal)
+        if step != 5:
+            sw.advance()
+            continue
+        files = sorted(os.listdir(tmp_path))
+        bad = np.flatnonzero(out["qp_status"] != 0)
+        assert len(bad) > 0 and files == [f"QPmodel_agent{a}_seq{e.planner_seq}.lp" for a in bad]
+        nr, d, _ = sw.capture(); pred = sw.pred()
+        for a in list(bad[:2]) + [int(np.flatnonzero(out["qp_status"] == 0)[0])]:
+            path = str(tmp_path / f"dump_{a}.lp")
+            e.dump_qp_lp(int(a), path)
+            lp = R.parse_lp(open(path).read())
+            rows = []
+            for j in range(n):
+                if j == a:
+                    continue
+                for m in range(5):
+                    aa = nr[a, j, m].astype(np.float64)
+                    rows.append((m, aa, d[a, j, m] + pred[j, m].astype(np.float64) @ aa))
+            st = np.stack([pos[a], vel[a], acc[a]]).astype(np.float64)
+            ts = O.terminal_segments(pos[a], scn.goal[a])
+            lb = np.full(90, -np.inf); ub = np.full(90, np.inf)
+            for k in range(3):
+                for m in range(5):
+                    for i in range(6):
+                        if not (m == 0 and i < 3):
+                            lb[k * 30 + m * 6 + i] = scn.world_min[k]; ub[k * 30 + m * 6 + i] = scn.world_max[k]
+            D = T.dense(st, scn.goal[a].astype(np.float64), ts, lb, ub, [1, 1, 1], [2, 2, 2], rows)
+            assert lp["Ain"].shape == D["Ain"].shape and lp["Aeq"].shape == D["Aeq"].shape
+            assert np.abs(lp["P"] - D["P"]).max() <= 1e-9 * np.abs(D["P"]).max()
+            assert np.abs(lp["q"] - D["q"]).max() <= 1e-12 and abs(lp["c0"] - D["c0"]) <= 1e-12
+            assert np.abs(lp["Aeq"] - D["Aeq"]).max() <= 1e-9 and np.abs(lp["beq"] - D["beq"]).max() <= 1e-12
+            assert np.abs(lp["Ain"] - D["Ain"]).max() <= 1e-6 * max(1.0, np.abs(D["Ain"]).max())
+            assert np.abs(lp["bin"] - D["bin"]).max() <= 1e-6
+            fin = np.isfinite(D["lb"])
+            assert np.array_equal(np.isfinite(lp["lb"]), fin) and np.abs(lp["lb"][fin] - D["lb"][fin]).max() <= 1e-6
+            x, obj, status = R.solve_ldp(lp)
+            if out["qp_status"][a] != 0:
+                assert status == "infeasible"
+                failed_seen += 1
+            else:
+                assert status == "ok"
+                xe = out["traj"][a].transpose(2, 0, 1).reshape(90)
+                assert np.abs(xe - x).max() <= 2e-5 and abs(out["qp_cost"][a] - obj) <= 1e-5 * max(1.0, abs(obj))
+        break
+    assert failed_seen >= 1
