@@ -84,13 +84,16 @@ typedef struct lscgpu_params {
     int M, n, phi, dim;            /* must be 5, 5, 3, 3 (traj/horizon 1.0, traj/n, traj/phi, world/dimension) */
     /* Goal planning, the step before the path (src/traj_planner.cpp:477-608). 0 = GoalMode::STATIC: lscgpu_agent_in::goal
      * is the current goal. 1 = GoalMode::PRIORBASED (the reference's default) on the GPU: lscgpu_agent_in::goal is the
-     * DESIRED goal and the engine derives the current goal (priority rule, retreat point, clip to goal_radius). Only
-     * without an octomap, where the reference's line-of-sight goal does not depend on its A* path; with an octomap the
-     * host planner (lsc_planner_b200/host/grid_based_planner.hpp) computes the goals and passes them with goal_mode 0. */
+     * DESIRED goal and the engine derives the current goal: priority rule, retreat point, and — with an octomap — the grid
+     * planner (occupancy grid of grid_resolution cells, A* with the reference's tie-breaking, line-of-sight goal by ray
+     * casting in the distance field: src/grid_based_planner.cpp:53-433, src/Astar-3D), clip to goal_radius. Without an
+     * octomap the line-of-sight goal does not depend on the A* path and only the clip remains. */
     int goal_mode;
     double goal_threshold;             /* plan/goal_threshold (0.1) */
     double goal_radius;                /* plan/goal_radius (2.0) */
     double priority_dist_threshold;    /* plan/priority_dist_threshold (0.4) */
+    double grid_resolution;            /* grid/resolution (launch: 0.25; 0 = that): goal_mode 1 with an octomap */
+    double grid_margin;                /* grid/margin (0.1): a grid cell is occupied when getDistance < radius + margin */
 } lscgpu_params;
 
 /* Constant part of Agent (include/sp_const.hpp:153-165). */
@@ -305,6 +308,7 @@ typedef struct lscgpu_step_stats {
     /* QP warm starts (all local agents): solves that had candidates from the agent's previous solve, solves whose
      * candidates were accepted as the starting point, and the rows those put into the working set without an iteration */
     int64_t qp_warm_tried, qp_warm_accepted, qp_warm_rows;
+    int64_t astar_expansions;       /* goal planning with an octomap (goal_mode 1): nodes the A* searches closed */
 } lscgpu_step_stats;
 int lscgpu_get_step_stats(lscgpu_engine* e, lscgpu_step_stats* out);
 /* enable per-kernel event timing (event records between the kernels of every step; off by default) */

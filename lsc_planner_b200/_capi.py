@@ -23,7 +23,7 @@ class Params(C.Structure):
         ("world_min", C.c_float * 3), ("world_max", C.c_float * 3),
         ("M", C.c_int), ("n", C.c_int), ("phi", C.c_int), ("dim", C.c_int),
         ("goal_mode", C.c_int), ("goal_threshold", C.c_double), ("goal_radius", C.c_double),
-        ("priority_dist_threshold", C.c_double),
+        ("priority_dist_threshold", C.c_double), ("grid_resolution", C.c_double), ("grid_margin", C.c_double),
     ]
 
 
@@ -38,7 +38,8 @@ class StepStats(C.Structure):
                 ("kernel_launches", C.c_int32), ("lsc_pairs", C.c_int64), ("lsc_pairs_kept", C.c_int64), ("gjk_iterations", C.c_int64),
                 ("qp_rows_priced", C.c_int64), ("qp_iterations", C.c_int64), ("qp_full_passes", C.c_int64),
                 ("ms_steps", C.c_float), ("reserved_", C.c_float),
-                ("qp_warm_tried", C.c_int64), ("qp_warm_accepted", C.c_int64), ("qp_warm_rows", C.c_int64)]
+                ("qp_warm_tried", C.c_int64), ("qp_warm_accepted", C.c_int64), ("qp_warm_rows", C.c_int64),
+                ("astar_expansions", C.c_int64)]
 
 
 # numpy views of lscgpu_agent_in / lscgpu_agent_out (C layout, natural alignment)

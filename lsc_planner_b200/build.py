@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liblscgpu.so")
-SOURCES = ["engine.cu", "kernels_lsc.cu", "kernels_plan.cu", "kernels_sfc.cu", "peaks.cu"]
+SOURCES = ["engine.cu", "kernels_lsc.cu", "kernels_plan.cu", "kernels_sfc.cu", "kernels_goal.cu", "peaks.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <unordered_map>      // std::__detail::_Prime_rehash_policy (goal_bucket_sequence)
 #include <vector>
 
 #include "kernels.hpp"
@@ -16,7 +17,7 @@
 using namespace lscgpu;
 
 // the ctypes / numpy mirrors in lsc_planner_b200/_capi.py assume these layouts (tests/test_capi_load.py)
-static_assert(sizeof(lscgpu_params) == 112 && sizeof(lscgpu_agent_in) == 48 && sizeof(lscgpu_agent_out) == 496 &&
+static_assert(sizeof(lscgpu_params) == 128 && sizeof(lscgpu_agent_in) == 48 && sizeof(lscgpu_agent_out) == 496 &&
               sizeof(lscgpu_agent_const) == 72, "C-ABI struct layout changed: update _capi.py and the tests");
 
 static thread_local std::string g_error;
@@ -169,6 +170,13 @@ struct lscgpu_engine {
     bool have_map = false;
     DistMapDev dm{};
     int64_t n_occupied = 0;
+    // goal planning with an octomap (k_goal_astar): planning grid, static occupancy per radius, per-warp search scratch
+    GoalGridDev goal_grid{};
+    bool have_goal_grid = false;
+    int goal_blocks = 0;
+    float* d_goal_axis = nullptr; uint8_t* d_goal_static = nullptr;
+    uint8_t* d_goal_cell = nullptr; int* d_goal_g = nullptr; int* d_goal_next = nullptr; int* d_goal_bkt = nullptr; int* d_goal_path = nullptr;
+    unsigned long long* d_goal_expansions = nullptr;
     // exchange
     NcclComm comm = nullptr;
     int rank = 0, n_ranks = 1, block = 0;
@@ -247,6 +255,8 @@ extern "C" void lscgpu_destroy(lscgpu_engine* e) {
     cudaFree(e->d_kept_step); if (e->h_kept_last) cudaFreeHost(e->h_kept_last);
     cudaFree(e->d_epoch); cudaFree(e->d_sfc_ready); cudaFree(e->d_sfc_box); cudaFree(e->d_sfc_ok);
     cudaFree(e->d_reset_ever); cudaFree(e->d_any_reset);
+    cudaFree(e->d_goal_axis); cudaFree(e->d_goal_static); cudaFree(e->d_goal_cell); cudaFree(e->d_goal_g); cudaFree(e->d_goal_next);
+    cudaFree(e->d_goal_bkt); cudaFree(e->d_goal_path); cudaFree(e->d_goal_expansions);
     if (e->ev_sfc) cudaEventDestroy(e->ev_sfc);
     cudaFree(e->d_rdw); cudaFree(e->d_audit_pos); cudaFree(e->d_audit_ratio); cudaFree(e->d_audit_closest); cudaFree(e->d_dbg);
     cudaFree(e->d_tables); cudaFree(e->d_consts); cudaFree(e->d_in); cudaFree(e->d_gather); cudaFree(e->d_res); cudaFree(e->d_traj);
@@ -293,9 +303,8 @@ extern "C" int lscgpu_create(const lscgpu_params* p, int n_agents, const lscgpu_
                              lscgpu_engine** out) {
     if (!p || !agents || !out || n_agents < 1) return fail(LSCGPU_ERR_ARG, "null argument or n_agents < 1");
     if (p->goal_mode != 0 && p->goal_mode != 1) return fail(LSCGPU_ERR_ARG, "goal_mode must be 0 (static) or 1 (prior_based)");
-    if (p->goal_mode == 1 && p->world_use_octomap)
-        return fail(LSCGPU_ERR_ARG, "goal_mode 1 (prior_based on the GPU) needs world_use_octomap = 0: with an octomap the goals "
-                                    "come from the host grid planner (lsc_planner_b200/host/grid_based_planner.hpp)");
+    if (p->goal_mode == 1 && p->world_use_octomap && (p->grid_resolution < 0 || p->grid_margin < 0))
+        return fail(LSCGPU_ERR_ARG, "grid_resolution and grid_margin must not be negative");
     if (p->M != 5 || p->n != 5 || p->phi != 3 || p->dim != 3)
         return fail(LSCGPU_ERR_ARG, "only M=5 (horizon/dt), n=5, phi=3, dim=3 is supported (launch/simulation.launch)");
     if (!(p->dt > 0) || !(p->world_resolution > 0)) return fail(LSCGPU_ERR_ARG, "dt and world_resolution must be positive");
@@ -314,6 +323,7 @@ extern "C" int lscgpu_create(const lscgpu_params* p, int n_agents, const lscgpu_
 
     lscgpu_engine* e = new lscgpu_engine;
     e->prm = *p; e->N = n_agents; e->device = device;
+    if (!(e->prm.grid_resolution > 0)) e->prm.grid_resolution = 0.25;      // launch/simulation.launch:87
     e->n_sm = prop.multiProcessorCount;
     e->n_pad = (n_agents + 31) / 32 * 32;
     e->a0 = 0; e->a1 = n_agents; e->block = n_agents;
@@ -441,6 +451,103 @@ extern "C" int lscgpu_create(const lscgpu_params* p, int n_agents, const lscgpu_
 // ---- octomap ---------------------------------------------------------------------------------------------------
 static int coord_to_key(double c, double res) { return (int)std::floor((1.0 / res) * c); }   // OcTree::coordToKey - 32768
 
+
+// ---- planning grid of goal planning (goal_mode 1 with an octomap) ----------------------------------------------------
+// The bucket counts a std::unordered_map with the default load factor moves through while it grows one element at a
+// time, recorded from libstdc++'s own policy object (astar_core.cuh explains why the search needs them).
+static int goal_bucket_sequence(int row_capacity, int* seq) {
+    std::__detail::_Prime_rehash_policy pol;
+    size_t bkt = 1, cnt = 0;
+    int n = 0;
+    seq[n++] = 1;
+    while ((int)bkt < row_capacity) {
+        if (n == kAstarMaxLevels) return -1;
+        const auto need = pol._M_need_rehash(bkt, cnt, 1);
+        if (need.first) { bkt = need.second; seq[n++] = (int)bkt; }
+        cnt++;
+    }
+    for (int k = n; k < kAstarMaxLevels; k++) seq[k] = seq[n - 1];
+    return n;
+}
+
+// GridBasedPlanner::updateGridInfo (src/grid_based_planner.cpp:70-90) + the static part of updateGridMap (:109-123), once
+// per map; scratch for one search per warp.
+static int setup_goal_grid(lscgpu_engine* e) {
+    cudaFree(e->d_goal_axis); cudaFree(e->d_goal_static); cudaFree(e->d_goal_cell); cudaFree(e->d_goal_g); cudaFree(e->d_goal_next);
+    cudaFree(e->d_goal_bkt); cudaFree(e->d_goal_path);
+    e->d_goal_axis = nullptr; e->d_goal_static = nullptr; e->d_goal_cell = nullptr; e->d_goal_g = nullptr; e->d_goal_next = nullptr;
+    e->d_goal_bkt = nullptr; e->d_goal_path = nullptr;
+    e->have_goal_grid = false;
+    GoalGridDev& g = e->goal_grid;
+    g = GoalGridDev{};
+    const double r = e->prm.grid_resolution;
+    double gmax[3];
+    for (int k = 0; k < 3; k++) {
+        g.gmin[k] = -std::floor((-(double)e->prm.world_min[k] + 1e-9) / r) * r;
+        gmax[k] = std::floor(((double)e->prm.world_max[k] + 1e-9) / r) * r;
+        g.dim[k] = (int)std::round((gmax[k] - g.gmin[k]) / r) + 1;
+        if (g.dim[k] < 1) return fail(LSCGPU_ERR_ARG, "empty planning grid");
+    }
+    g.res = r;
+    if (g.dim[0] > 2048) return fail(LSCGPU_ERR_ARG, "planning grid has more than 2048 rows along x (grid_resolution too fine for this world)");
+    const size_t cells = (size_t)g.dim[0] * g.dim[1] * g.dim[2];
+    if (cells > ((size_t)1 << 26)) return fail(LSCGPU_ERR_ARG, "planning grid too large");
+    g.cells = (int)cells;
+    g.cells_pad = (cells + 15) / 16 * 16;
+    if (goal_bucket_sequence(g.dim[1] * g.dim[2], g.bkt_seq) < 0) return fail(LSCGPU_ERR_ARG, "planning grid rows too long");
+    g.bcap = g.bkt_seq[kAstarMaxLevels - 1];
+    g.magic_a = astar_magic((unsigned)g.dim[2], cells); g.magic_w = astar_magic((unsigned)g.dim[1], cells);
+    for (int k = 0; k < kAstarMaxLevels; k++) g.bkt_magic[k] = astar_magic((unsigned)g.bkt_seq[k], cells);
+    std::vector<float> axis((size_t)g.dim[0] + g.dim[1] + g.dim[2]);
+    {
+        size_t o = 0;
+        for (int k = 0; k < 3; k++)
+            for (int i = 0; i < g.dim[k]; i++) {
+                volatile double prod = i * r;                     // gridVectorToPoint3D (:305-310): product and sum rounded separately
+                axis[o++] = (float)(g.gmin[k] + prod);
+            }
+    }
+    CU(cudaMalloc(&e->d_goal_axis, sizeof(float) * axis.size()));
+    CU(cudaMemcpyAsync(e->d_goal_axis, axis.data(), sizeof(float) * axis.size(), cudaMemcpyHostToDevice, e->stream));
+    g.axis_pts = e->d_goal_axis;
+    const int n_radii = (int)e->radii.size();
+    CU(cudaMalloc(&e->d_goal_static, g.cells_pad * (size_t)n_radii));
+    CU(cudaMemsetAsync(e->d_goal_static, 0, g.cells_pad * (size_t)n_radii, e->stream));
+    g.static_occ = e->d_goal_static;
+    double* d_radii = nullptr;
+    CU(cudaMalloc(&d_radii, sizeof(double) * n_radii));
+    CU(cudaMemcpyAsync(d_radii, e->radii.data(), sizeof(double) * n_radii, cudaMemcpyHostToDevice, e->stream));
+    launch_goal_static_grid(g, e->dm, e->prm.world_resolution, d_radii, n_radii, (float)e->prm.grid_margin, e->d_goal_static, e->stream);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(e->stream));
+    cudaFree(d_radii);
+    // One search per warp. Small grids keep the warp's search state in shared memory (one warp per SM, or more when several
+    // fit); larger ones run on per-warp scratch in global memory, as many warps as the device keeps resident, bounded by
+    // 4 GB of scratch.
+    CU(configure_goal_astar(g));
+    const size_t sh = goal_astar_shared_bytes(g);
+    int blocks;
+    if (sh) {
+        blocks = std::min(e->N, e->n_sm * std::max(1, (int)((227 * 1024) / (sh + 1024))));
+    } else {
+        const size_t per_warp = g.cells_pad * (1 + 3 * sizeof(int)) + (size_t)g.dim[0] * g.bcap * sizeof(int);
+        blocks = std::min(e->N, e->n_sm * 16);
+        blocks = (int)std::max<size_t>(1, std::min<size_t>((size_t)blocks, ((size_t)4 << 30) / per_warp));
+        CU(cudaMalloc(&e->d_goal_cell, g.cells_pad * (size_t)blocks));
+        CU(cudaMalloc(&e->d_goal_g, sizeof(int) * g.cells_pad * (size_t)blocks));
+        CU(cudaMalloc(&e->d_goal_next, sizeof(int) * g.cells_pad * (size_t)blocks));
+        CU(cudaMalloc(&e->d_goal_bkt, sizeof(int) * (size_t)g.dim[0] * g.bcap * (size_t)blocks));
+    }
+    e->goal_blocks = blocks;
+    CU(cudaMalloc(&e->d_goal_path, sizeof(int) * g.cells_pad * (size_t)blocks));
+    if (!e->d_goal_expansions) {
+        CU(cudaMalloc(&e->d_goal_expansions, sizeof(unsigned long long)));
+        CU(cudaMemset(e->d_goal_expansions, 0, sizeof(unsigned long long)));
+    }
+    e->have_goal_grid = true;
+    return LSCGPU_OK;
+}
+
 static int build_map(lscgpu_engine* e, const int32_t* keys, int n) {
     CU(cudaSetDevice(e->device));
     CU(cudaStreamSynchronize(e->stream));
@@ -498,6 +605,7 @@ static int build_map(lscgpu_engine* e, const int32_t* keys, int n) {
     }
     e->n_occupied = occ;
     e->have_map = true;
+    if (e->prm.goal_mode == 1 && e->prm.world_use_octomap) return setup_goal_grid(e);
     return LSCGPU_OK;
 }
 
@@ -644,13 +752,16 @@ static int enqueue_step_kernels(lscgpu_engine* e, int planner_seq, int threads, 
     const bool use_sfc = e->prm.world_use_octomap != 0;
     const bool side = !e->profiling;
     cudaStream_t so = side ? e->stream_aux : s;
-    if (side && (ordered || use_sfc)) { CU(cudaEventRecord(e->ev_fork, s)); CU(cudaStreamWaitEvent(so, e->ev_fork, 0)); }
+    if (side && (ordered || (use_sfc && e->prm.goal_mode != 1))) { CU(cudaEventRecord(e->ev_fork, s)); CU(cudaStreamWaitEvent(so, e->ev_fork, 0)); }
     if (ordered) {
         launch_qp_order(n_order, dealt ? 0 : e->a0, e->d_res, e->d_order, so); launches++;
         if (side) CU(cudaEventRecord(e->ev_order, so));
     }
-    if (use_sfc && n_plan > 0) {
-        // the step's new SFC boxes depend on the step's inputs only: grown beside k_predict and the LSC rows
+    // the step's new SFC boxes depend on the step's inputs only: grown beside k_predict and the LSC rows — unless the goals
+    // are planned in this step (goal_mode 1): the box grows toward the agent's CURRENT goal, so k_sfc_step follows the
+    // goal kernel on the engine stream
+    const bool sfc_after_goal = use_sfc && e->prm.goal_mode == 1;
+    auto launch_sfc = [&](cudaStream_t st, const double* goal3) -> int {
         SfcStepLaunch sl{};
         sl.n = n_plan;
         sl.order = ordered ? e->d_order : nullptr;
@@ -661,9 +772,14 @@ static int enqueue_step_kernels(lscgpu_engine* e, int planner_seq, int threads, 
         sl.in = e->d_in; sl.prev_traj = e->d_traj; sl.consts = e->d_consts; sl.init_sfc = e->d_init_sfc;
         sl.planner_seq = planner_seq; sl.reset_threshold = e->prm.reset_threshold;
         sl.epoch = e->d_epoch; sl.sfc_box_g = e->d_sfc_box; sl.sfc_ok_g = e->d_sfc_ok; sl.sfc_ready = e->d_sfc_ready;
-        if (ev) CU(cudaEventRecord(ev[5], so));
-        launch_sfc_step(sl, so); launches++;
-        if (ev) CU(cudaEventRecord(ev[6], so));
+        sl.goal3 = goal3;
+        if (ev) CU(cudaEventRecord(ev[5], st));
+        launch_sfc_step(sl, st); launches++;
+        if (ev) CU(cudaEventRecord(ev[6], st));
+        return LSCGPU_OK;
+    };
+    if (use_sfc && n_plan > 0 && !sfc_after_goal) {
+        if (const int rc = launch_sfc(so, nullptr)) return rc;
         if (side) CU(cudaEventRecord(e->ev_sfc, so));
     }
     PredictLaunch pl{};
@@ -674,6 +790,7 @@ static int enqueue_step_kernels(lscgpu_engine* e, int planner_seq, int threads, 
     pl.ts = e->d_ts; pl.flags = e->d_flags; pl.sphere = e->d_sphere; pl.tsphere = e->d_tsphere; pl.reach = e->d_reach;
     pl.reset_ever = e->d_reset_ever; pl.any_reset = e->d_any_reset; pl.init_sfc = e->d_init_sfc;
     launch_predict(pl, s); launches++;
+    bool order_waited = false;
     if (e->prm.goal_mode == 1) {
         GoalLaunch gl{};
         gl.reset_ever = e->d_reset_ever;
@@ -681,10 +798,25 @@ static int enqueue_step_kernels(lscgpu_engine* e, int planner_seq, int threads, 
         gl.priority_dist_threshold = e->prm.priority_dist_threshold;
         gl.in = e->d_in; gl.prev_traj = e->d_traj; gl.pred = e->d_pred; gl.consts = e->d_consts;
         gl.goal3 = e->d_goal3; gl.ts = e->d_ts; gl.goal_kind = e->d_goal_kind;
-        launch_goal_plan(gl, s); launches++;
+        if (!use_sfc) {
+            launch_goal_plan(gl, s); launches++;
+        } else if (n_plan > 0) {
+            // with an octomap: grid planner + A* + line-of-sight goal, for the agents this engine plans, in their order
+            if (ordered && !e->profiling) { CU(cudaStreamWaitEvent(s, e->ev_order, 0)); order_waited = true; }
+            GoalAstarLaunch al{};
+            al.g = gl; al.n = n_plan;
+            al.order = ordered ? e->d_order : nullptr;
+            al.order_first = dealt ? e->rank : 0; al.order_stride = dealt ? e->n_ranks : 1;
+            al.agent_base = dealt ? e->rank : e->a0; al.agent_stride = dealt ? e->n_ranks : 1;
+            al.dm = e->dm; al.world_res = e->prm.world_resolution; al.grid = e->goal_grid; al.n_blocks = e->goal_blocks;
+            al.cell = e->d_goal_cell; al.gcost = e->d_goal_g; al.next = e->d_goal_next; al.bkt = e->d_goal_bkt; al.path = e->d_goal_path;
+            al.expansions = e->d_goal_expansions;
+            launch_goal_astar(al, s); launches++;
+            if (const int rc = launch_sfc(s, e->d_goal3)) return rc;
+        }
     }
     if (ev) CU(cudaEventRecord(ev[1], s));
-    if (ordered && !e->profiling) CU(cudaStreamWaitEvent(s, e->ev_order, 0));
+    if (ordered && !e->profiling && !order_waited) CU(cudaStreamWaitEvent(s, e->ev_order, 0));
 
     PlanLaunch L{};
     L.n_agents = e->N; L.n_pad = e->n_pad; L.n_blocks = n_plan;
@@ -733,7 +865,7 @@ static int enqueue_step_kernels(lscgpu_engine* e, int planner_seq, int threads, 
     }
     if (ev) CU(cudaEventRecord(ev[3], s));
     const int n_slots = dealt ? e->block * e->n_ranks : n_plan;
-    if (use_sfc && n_plan > 0 && side) CU(cudaStreamWaitEvent(s, e->ev_sfc, 0));     // k_commit rewrites what k_sfc_step reads
+    if (use_sfc && n_plan > 0 && side && !sfc_after_goal) CU(cudaStreamWaitEvent(s, e->ev_sfc, 0));     // k_commit rewrites what k_sfc_step reads
     launch_commit(n_slots, e->d_gather, e->d_res, e->d_act_prev, e->d_traj, e->d_in, e->d_last_cost,
                   use_sfc ? e->d_boxes : nullptr, e->d_init_sfc, e->d_epoch, e->d_kept_step, e->d_kept_last_map, px, e->d_commit_done,
                   e->d_xchg_err_map, s); launches++;
@@ -745,6 +877,8 @@ static int enqueue_step_kernels(lscgpu_engine* e, int planner_seq, int threads, 
 static int step_device(lscgpu_engine* e) {
     if (e->prm.world_use_octomap && !e->have_map)
         return fail(LSCGPU_ERR_STATE, "world_use_octomap is set but no octomap was uploaded (lscgpu_set_octomap_*)");
+    if (e->prm.world_use_octomap && e->prm.goal_mode == 1 && !e->have_goal_grid)
+        return fail(LSCGPU_ERR_STATE, "goal planning grid missing (octomap upload failed?)");
     cudaStream_t s = e->stream;
     const int seq = e->planner_seq + 1;                     // src/traj_planner.cpp:127; committed once the step is enqueued
     const bool prof = e->profiling;
@@ -843,7 +977,13 @@ static int compute_stats(lscgpu_engine* e) {
     StepCounters c;
     CU(cudaMemcpyAsync(&c, e->d_counters, sizeof c, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaMemsetAsync(e->d_counters, 0, sizeof(StepCounters), e->stream));
+    unsigned long long astar = 0;
+    if (e->d_goal_expansions) {
+        CU(cudaMemcpyAsync(&astar, e->d_goal_expansions, sizeof astar, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaMemsetAsync(e->d_goal_expansions, 0, sizeof astar, e->stream));
+    }
     CU(cudaStreamSynchronize(e->stream));
+    st.astar_expansions = (int64_t)astar;
     st.steps = e->done_steps;
     CU(cudaEventElapsedTime(&st.ms_total, e->ev_begin, e->ev_end));
     for (int i = 0; i < e->done_steps; i++) {

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "astar_core.cuh"
 #include "device_common.cuh"
 
 namespace lscgpu {
@@ -47,6 +48,19 @@ struct GoalLaunch {
     int* goal_kind;                // [N] 0 line-of-sight goal, 1 retreat from the closest higher-priority agent
 };
 void launch_goal_plan(const GoalLaunch& L, cudaStream_t s);
+
+// ---- k_goal_astar: goalPlanningWithPriority WITH an octomap (grid planner, A*, line-of-sight goal) ---------------
+struct GoalGridDev {
+    int dim[3];                    // cells per axis (src/grid_based_planner.cpp:70-90)
+    int cells;                     // dim[0] * dim[1] * dim[2]
+    size_t cells_pad;              // ... rounded up to 16
+    double gmin[3], res;           // grid_min, grid/resolution
+    const float* axis_pts;         // gridVectorToPoint3D per axis: [dim0] x, [dim1] y, [dim2] z
+    const uint8_t* static_occ;     // [distinct radii][cells_pad]: kCellOccupied where getDistance(cell point) < radius + grid/margin
+    int bkt_seq[kAstarMaxLevels];  // bucket counts of libstdc++'s unordered_map growth (astar_core.cuh)
+    int bcap;                      // bucket capacity of one row container
+    unsigned magic_a, magic_w, bkt_magic[kAstarMaxLevels];   // multiply-high reciprocals of dim[2], dim[1] and the bucket counts (astar_magic)
+};
 
 // ---- k_agent_plan: LSC construction + SFC window + trajectory QP of one agent per thread block ------------------
 struct DistMapDev {
@@ -122,6 +136,25 @@ struct PlanLaunch {
     long long* dbg;                // null, or [n_blocks][10] section cycle counts (LSCGPU_QP_DEBUG)
 };
 void launch_agent_plan(const PlanLaunch& L, cudaStream_t s);
+
+struct GoalAstarLaunch {
+    GoalLaunch g;                  // the inputs / outputs k_goal_plan has
+    int n;                         // agents this engine plans in this step, mapped to agents as PlanLaunch does
+    const int* order; int order_stride, order_first, agent_base, agent_stride;
+    DistMapDev dm; double world_res;
+    GoalGridDev grid;
+    int n_blocks;                  // warps = scratch sets
+    // per-warp scratch: path cells [n_blocks][cells_pad]; and, for grids whose search state does not fit shared memory,
+    // cell bytes / g / list links [n_blocks][cells_pad] and row buckets [n_blocks][dim0][bcap]
+    int* path;
+    uint8_t* cell; int* gcost; int* next; int* bkt;
+    unsigned long long* expansions;    // null, or the step's A* expansion counter
+};
+void launch_goal_astar(const GoalAstarLaunch& L, cudaStream_t s);
+size_t goal_astar_shared_bytes(const GoalGridDev& g);      // 0: the grid's search state does not fit one SM's shared memory
+cudaError_t configure_goal_astar(const GoalGridDev& g);    // once per grid, before the first launch
+void launch_goal_static_grid(const GoalGridDev& g, const DistMapDev& dm, double world_res, const double* radii_dev, int n_radii,
+                             float grid_margin, uint8_t* out, cudaStream_t s);
 size_t agent_plan_smem_bytes(int row_cap, int threads);
 size_t agent_plan_slack_smem_bytes(int row_cap, int threads);
 cudaError_t configure_agent_plan();     // once per device, before the first launch
@@ -194,6 +227,7 @@ struct SfcStepLaunch {
     int planner_seq; double reset_threshold;       // a reset in this step re-arms the corridor (k_predict runs beside this kernel)
     const int* epoch;
     float* sfc_box_g; int* sfc_ok_g; int* sfc_ready;
+    const double* goal3;           // null: the goal is lscgpu_agent_in::goal; else [N][3] the goals goal planning chose (goal_mode 1)
 };
 void launch_sfc_step(const SfcStepLaunch& L, cudaStream_t s);
 

@@ -300,7 +300,8 @@ __global__ void __launch_bounds__(kPlanThreads, kSlack ? (kPlanThreads > 256 ? 1
             SfcCtx c;
             sfc_ctx_init(c, L.dm, L.wmin, L.wmax, L.res, lane);
             double face;
-            const bool ok = sfc_agent_box(c, L.dm, L.consts[a].sat_index, L.res, L.in[a], L.prev_traj + (size_t)a * kTrajFloats,
+            const F3 cur_goal{(float)L.goal3[(size_t)a * 3], (float)L.goal3[(size_t)a * 3 + 1], (float)L.goal3[(size_t)a * 3 + 2]};
+            const bool ok = sfc_agent_box(c, L.dm, L.consts[a].sat_index, L.res, L.in[a], cur_goal, L.prev_traj + (size_t)a * kTrajFloats,
                                           L.init_sfc[a] != 0, face);
             if (lane < 6) X.sfc_box[lane] = ok ? (float)face : 0.0f;
             if (lane == 0) { X.sfc_ok = ok ? 1 : 0; X.sfc_self = 1; }

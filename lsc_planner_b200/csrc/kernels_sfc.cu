@@ -142,7 +142,11 @@ __global__ void __launch_bounds__(128) k_sfc_step(SfcStepLaunch L) {
         const F3 dlt = f3_sub(F3{t[0], t[1], t[2]}, F3{in.position[0], in.position[1], in.position[2]});
         first = first || sqrt(f3_dot(dlt, dlt)) > L.reset_threshold;
     }
-    const bool ok = sfc_agent_box(c, L.dm, L.consts[a].sat_index, L.res, L.in[a], L.prev_traj + (size_t)a * kTrajFloats,
+    // the box grows toward the agent's CURRENT goal: the input goal, or what goal planning made of it (goal_mode 1)
+    const lscgpu_agent_in& ia = L.in[a];
+    const F3 goal = L.goal3 ? F3{(float)L.goal3[(size_t)a * 3], (float)L.goal3[(size_t)a * 3 + 1], (float)L.goal3[(size_t)a * 3 + 2]}
+                            : F3{ia.goal[0], ia.goal[1], ia.goal[2]};
+    const bool ok = sfc_agent_box(c, L.dm, L.consts[a].sat_index, L.res, ia, goal, L.prev_traj + (size_t)a * kTrajFloats,
                                   first, face);
     if (c.lane < 6) L.sfc_box_g[(size_t)a * 6 + c.lane] = ok ? (float)face : 0.0f;
     if (c.lane == 0) L.sfc_ok_g[a] = ok ? 1 : 0;

@@ -306,10 +306,9 @@ __device__ __forceinline__ void sfc_ctx_init(SfcCtx& c, const DistMapDev& dm, co
 // goal. Lane f < 6 returns face f in `face`. Returns false when the seed is blocked (the reference throws,
 // include/corridor_constructor.hpp:35-38). The persistent window itself is updated by sfc_window_box below.
 __device__ __forceinline__ bool sfc_agent_box(SfcCtx& c, const DistMapDev& dm, int sat_index, double res, const lscgpu_agent_in& in,
-                                              const float* prev_traj_a, bool first, double& face) {
+                                              F3 g /* Agent::current_goal_position */, const float* prev_traj_a, bool first, double& face) {
     const size_t tab = (size_t)(dm.size[0] + 1) * (dm.size[1] + 1) * (dm.size[2] + 1);
     c.sat = dm.sat + (size_t)sat_index * tab;
-    const F3 g{in.goal[0], in.goal[1], in.goal[2]};
     F3 seed;
     if (first) seed = F3{in.position[0], in.position[1], in.position[2]};
     else {

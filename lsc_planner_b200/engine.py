@@ -29,10 +29,12 @@ class Param:
     n: int = 5
     phi: int = 3
     dim: int = 3
-    goal_mode: int = 0              # 0 static (goal = current goal), 1 prior_based on the GPU (goal = desired goal; no octomap)
+    goal_mode: int = 0              # 0 static (goal = current goal), 1 prior_based on the GPU (goal = desired goal)
     goal_threshold: float = 0.1
     goal_radius: float = 2.0
     priority_dist_threshold: float = 0.4
+    grid_resolution: float = 0.25   # grid/resolution, grid/margin: the planning grid of goal_mode 1 with an octomap
+    grid_margin: float = 0.1
 
     def to_c(self) -> A.Params:
         p = A.Params()
@@ -44,6 +46,7 @@ class Param:
         p.M, p.n, p.phi, p.dim = self.M, self.n, self.phi, self.dim
         p.goal_mode, p.goal_threshold, p.goal_radius = self.goal_mode, self.goal_threshold, self.goal_radius
         p.priority_dist_threshold = self.priority_dist_threshold
+        p.grid_resolution, p.grid_margin = self.grid_resolution, self.grid_margin
         return p
 
 

@@ -3,8 +3,59 @@
 #include <cstring>
 
 #include "grid_based_planner.hpp"
+#include "../csrc/astar_core.cuh"
 
 using namespace DynamicPlanning;
+
+extern "C" int devcore_bucket_sequence(int row_capacity, int* seq, int max_levels);
+
+template <typename I>
+static int devcore_astar_t(const int* dim, const unsigned char* grid, const int* start, const int* goal, int* path_out, int max_len,
+                           long long* expansions, bool accel) {
+    using namespace lscgpu;
+    const int H = dim[0], W = dim[1], A = dim[2];
+    const size_t cells = (size_t)H * W * A;
+    AstarCtx<I> c{};
+    c.H = H; c.W = W; c.A = A;
+    int seq[kAstarMaxLevels] = {0};
+    const int levels = devcore_bucket_sequence(W * A, seq, kAstarMaxLevels);
+    c.bkt_seq = seq;
+    c.bcap = seq[levels - 1];
+    const size_t max_cells = sizeof(I) == 2 ? (size_t)65533 : ((size_t)1 << 30);
+    if ((c.bcap) < W * A || cells > max_cells) return -1;
+    std::vector<uint8_t> cell(cells);
+    for (size_t k = 0; k < cells; k++) cell[k] = grid[k] ? kCellOccupied : 0;
+    std::vector<I> g(cells, (I)77), next(cells, (I)55), bkt((size_t)H * c.bcap, (I)12345);
+    std::vector<int> head(H, -1), count(H, 0), level(H, 0), min_cell(H, -1), min_g(H, 0);
+    std::vector<double> min_f(H, 0.0);
+    c.cell = cell.data(); c.g = g.data(); c.next = next.data(); c.bkt = bkt.data();
+    c.head = head.data(); c.count = count.data(); c.level = level.data(); c.min_cell = min_cell.data(); c.min_g = min_g.data();
+    c.min_f = min_f.data();
+    c.gi = goal[0]; c.gj = goal[1]; c.gz = goal[2];
+    // the accelerators of the shared-memory instantiation: multiply-high divisions and the sqrt table
+    unsigned bkt_magic[kAstarMaxLevels] = {0};
+    std::vector<double> sqrt_tab;
+    if (accel) {
+        c.magic_a = astar_magic(A, cells); c.magic_w = astar_magic(W, cells);
+        for (int k = 0; k < kAstarMaxLevels; k++) bkt_magic[k] = k < levels ? astar_magic(seq[k], cells) : 0;
+        c.bkt_magic = bkt_magic;
+        sqrt_tab.resize((size_t)(H - 1) * (H - 1) + (size_t)(W - 1) * (W - 1) + (size_t)(A - 1) * (A - 1) + 1);
+        for (size_t k = 0; k < sqrt_tab.size(); k++) sqrt_tab[k] = std::sqrt((double)k);
+        c.sqrt_tab = sqrt_tab.data();
+    }
+    astar_begin(c, start[0], start[1], start[2]);
+    int cur = -1, found = 0;
+    while (c.open_size != 0) {
+        cur = astar_find_min(c);
+        if (astar_expand(c, cur)) { found = 1; break; }
+    }
+    if (expansions) *expansions = c.expansions;
+    if (!found) return 0;
+    const int n = (int)g[cur] + 1;
+    for (int k = n - 1, p = cur; k >= 0 && p >= 0; k--, p = astar_parent(c, p))
+        if (k < max_len) { path_out[3 * k] = p / (W * A); path_out[3 * k + 1] = (p / A) % W; path_out[3 * k + 2] = p % A; }
+    return n;
+}
 
 extern "C" {
 
@@ -80,6 +131,28 @@ int host_goal_plan(int a, int n, const float* pos, const float* desired, const f
     goal_out[0] = r.goal.x(); goal_out[1] = r.goal.y(); goal_out[2] = r.goal.z();
     if (expansions) *expansions = r.expansions;
     return r.kind;
+}
+
+// The search core the GPU kernel runs (csrc/astar_core.cuh, compiled here as plain C++) on the same inputs as host_astar:
+// scratch arrays as the engine lays them out, bucket sequence recorded from libstdc++'s policy like the engine does.
+int devcore_bucket_sequence(int row_capacity, int* seq, int max_levels) {
+    std::__detail::_Prime_rehash_policy pol;
+    size_t bkt = 1, cnt = 0;
+    int n = 0;
+    seq[n++] = 1;
+    while ((int)bkt < row_capacity && n < max_levels) {
+        const auto need = pol._M_need_rehash(bkt, cnt, 1);
+        if (need.first) { bkt = need.second; seq[n++] = (int)bkt; }
+        cnt++;
+    }
+    return n;
+}
+
+// index_bits 16: the compact layout the kernel keeps in shared memory (grids below 65 534 cells); 32: the global-memory layout
+int devcore_astar(const int* dim, const unsigned char* grid, const int* start, const int* goal, int* path_out, int max_len,
+                  long long* expansions, int index_bits) {
+    return index_bits == 16 ? devcore_astar_t<uint16_t>(dim, grid, start, goal, path_out, max_len, expansions, true)
+                            : devcore_astar_t<int>(dim, grid, start, goal, path_out, max_len, expansions, false);
 }
 
 }  // extern "C"

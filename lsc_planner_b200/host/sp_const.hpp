@@ -105,6 +105,12 @@ struct Param {
     double control_input_weight = 1, terminal_weight = 1, slack_collision_weight = 1;
     int N_constraint_segments = -1;
     double grid_resolution = 0.3, grid_margin = 0.1;            // src/param.cpp:93-94
+    // not in the reference: where prior_based goal planning with an octomap runs. device: on the GPU inside the step
+    // (k_goal_astar, one warp per agent); host: grid_based_planner.hpp on the host threads before the step (same goals bit
+    // for bit). auto (default): the device from 256 agents on — one A* is a sequential search, a host core runs it ~10x faster
+    // than a GPU lane, the GPU wins by running every agent's search at once
+    int goal_planner = 0;               // 0 auto, 1 device, 2 host
+    bool goalPlannerOnDevice(int n_agents) const { return goal_planner == 1 || (goal_planner == 0 && n_agents >= 256); }
     double goal_threshold = 0.1, goal_radius = 100.0, priority_dist_threshold = 0.4;
     std::string mission_file_name = "default.json", world_file_name = "default.bt", package_path = ".";
 
@@ -159,6 +165,12 @@ struct Param {
         else if (key == "opt/N_constraint_segments") N_constraint_segments = i();
         else if (key == "grid/resolution") grid_resolution = d();
         else if (key == "grid/margin") grid_margin = d();
+        else if (key == "goal/planner") {
+            if (v == "device") goal_planner = 1;
+            else if (v == "host") goal_planner = 2;
+            else if (v == "auto") goal_planner = 0;
+            else throw std::invalid_argument("[Param] goal/planner must be auto, device or host");
+        }
         else if (key == "plan/goal_threshold") goal_threshold = d();
         else if (key == "plan/goal_radius") goal_radius = d();
         else if (key == "plan/priority_dist_threshold") priority_dist_threshold = d();

@@ -24,10 +24,12 @@ inline lscgpu_params toEngineParams(const Param& param, const Mission& mission) 
     p.world_use_octomap = param.world_use_octomap ? 1 : 0;
     for (int k = 0; k < 3; k++) { p.world_min[k] = mission.world_min(k); p.world_max[k] = mission.world_max(k); }
     p.M = param.M; p.n = param.n; p.phi = param.phi; p.dim = param.world_dimension;
-    // prior_based goal planning: on the GPU without an octomap, by the host grid planner (goal_mode 0 for the engine) with one
-    p.goal_mode = (param.goal_mode == GoalMode::PRIORBASED && !param.world_use_octomap) ? 1 : 0;
+    // prior_based goal planning runs on the GPU inside the step; with goal/planner=host and an octomap the host grid planner
+    // computes the goals before the step instead (goal_mode 0 for the engine)
+    p.goal_mode = (param.goal_mode == GoalMode::PRIORBASED && (!param.world_use_octomap || param.goalPlannerOnDevice(mission.qn))) ? 1 : 0;
     p.goal_threshold = param.goal_threshold; p.goal_radius = param.goal_radius;
     p.priority_dist_threshold = param.priority_dist_threshold;
+    p.grid_resolution = param.grid_resolution; p.grid_margin = param.grid_margin;
     return p;
 }
 

@@ -86,7 +86,7 @@ public:
         for (bool f : fresh) if (!f) throw PlanningReport::WAITFORROSMSG;
         const auto t0 = std::chrono::steady_clock::now();
         goal_seconds = 0;
-        if (param.goal_mode == GoalMode::PRIORBASED && param.world_use_octomap) {
+        if (param.goal_mode == GoalMode::PRIORBASED && param.world_use_octomap && !param.goalPlannerOnDevice(mission.qn)) {
             planGoalsOnHost(planner_seq);
             goal_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         }
@@ -94,6 +94,7 @@ public:
             throw std::invalid_argument(std::string("[lscgpu] ") + lscgpu_last_error());
         wall_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         lscgpu_get_step_stats(engine.get(), &stats);
+        astar_expansions += stats.astar_expansions;          // goal planning on the device (k_goal_astar)
         planned_seq = planner_seq;
         std::fill(fresh.begin(), fresh.end(), false);
     }

@@ -32,7 +32,7 @@ def test_header_symbols_exported(lib):
 def test_struct_layouts_match_header():
     assert A.AGENT_IN.itemsize == 48
     assert A.AGENT_OUT.itemsize == 496 and A.AGENT_OUT.fields["qp_cost"][1] == 400
-    assert C.sizeof(A.Params) == 112 and C.sizeof(A.AgentConst) == 72
+    assert C.sizeof(A.Params) == 128 and C.sizeof(A.AgentConst) == 72
 
 
 def test_no_cpu_fallback(lib):

@@ -28,6 +28,7 @@ def host():
     H.host_goal_plan.argtypes = [C.c_int, C.c_int, f32p, f32p, f32p, f32p, f64p, f64p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_double, f32p, f32p] + [C.c_double] * 5 + [f32p, C.POINTER(C.c_longlong)]
     H.host_goal_plan.restype = C.c_int
+    H.devcore_astar.argtypes = H.host_astar.argtypes + [C.c_int]; H.devcore_astar.restype = C.c_int
     return H
 
 
@@ -36,6 +37,16 @@ def host_astar(H, grid, start, goal):
     path = np.zeros((4096, 3), np.int32); ex = C.c_longlong(0)
     n = H.host_astar(np.asarray(grid.shape, np.int32), grid, np.asarray(start, np.int32), np.asarray(goal, np.int32), path,
                      len(path), C.byref(ex))
+    return path[:n].copy(), ex.value
+
+
+def devcore_astar(H, grid, start, goal, bits=32):
+    """The search core of the GPU kernel (csrc/astar_core.cuh) compiled for the host, with 16- or 32-bit indices."""
+    grid = np.ascontiguousarray(grid, np.uint8)
+    path = np.zeros((4096, 3), np.int32); ex = C.c_longlong(0)
+    n = H.devcore_astar(np.asarray(grid.shape, np.int32), grid, np.asarray(start, np.int32), np.asarray(goal, np.int32), path,
+                        len(path), C.byref(ex), bits)
+    assert n >= 0
     return path[:n].copy(), ex.value
 
 
@@ -60,6 +71,28 @@ def test_host_astar_matches_reference_golden(golden_dir, host):
     for grid, s, g, ref_path in golden_cases(golden_dir):
         path, _ = host_astar(host, grid, s, g)
         assert path.shape == ref_path.shape and (path == ref_path).all(), (grid.shape, s, g)
+
+
+def test_device_astar_core_matches_reference_golden_and_host(golden_dir, host):
+    """k_goal_astar's search (flat scratch arrays, packed cell bytes, hash-order model without containers) path for path
+    against the reference's goldens, and against the host planner incl. the expansion count on random grids (walls force
+    long detours, large rows force several rehashes of the row containers)."""
+    for grid, s, g, ref_path in golden_cases(golden_dir):
+        for bits in (16, 32):
+            path, _ = devcore_astar(host, grid, s, g, bits)
+            assert path.shape == ref_path.shape and (path == ref_path).all(), (grid.shape, s, g, bits)
+    rng = np.random.default_rng(7)
+    for t in range(150):
+        dim = (int(rng.integers(3, 60)), int(rng.integers(3, 60)), int(rng.integers(1, 13)))
+        grid = np.ascontiguousarray((rng.random(dim) < rng.choice([0.0, 0.1, 0.25, 0.35])).astype(np.uint8))
+        if t % 4 == 0 and dim[0] > 8:
+            grid[dim[0] // 2, :, :] = 1; grid[dim[0] // 2, int(rng.integers(0, dim[1])), :] = 0     # a wall with one gap
+        s = np.array([rng.integers(0, d) for d in dim], np.int32); g = np.array([rng.integers(0, d) for d in dim], np.int32)
+        grid[tuple(s)] = 0
+        ph, eh = host_astar(host, grid, s, g)
+        for bits in (16, 32):
+            pd, ed = devcore_astar(host, grid, s, g, bits)
+            assert ph.shape == pd.shape and (ph == pd).all() and eh == ed, (dim, s, g, bits)
 
 
 def test_astar_live_against_reference_library(host):

@@ -63,10 +63,72 @@ def test_device_goal_planning_matches_oracle(name, steps):
     e.close()
 
 
-def test_device_goal_mode_needs_no_octomap():
+def _forest_case(case, tmp_path, bt):
     import lsc_planner_b200 as L
-    with pytest.raises(Exception):
-        L.ReplanEngine(4, L.Param(world_use_octomap=True, goal_mode=1))
+    if case == "forest10":
+        mission = str(tmp_path / "forest10.json"); _forest_mission(mission)
+        return L.scenarios.load_mission(mission)
+    tmp = L.ReplanEngine(2, L.Param(world_use_octomap=True)); tmp.set_octomap_file(bt); dm = tmp.distmap(); tmp.close()
+    return L.scenarios.random_forest(int(case[len("random"):]), dm["sqdist"], dm["off"], seed=3)
+
+
+@pytest.mark.parametrize("case,steps", [("forest10", 60), ("random64", 30)])
+def test_device_goal_planning_with_octomap_matches_oracle(case, steps, tmp_path, golden_dir):
+    """goal_mode 1 WITH an octomap: k_goal_astar (priority rule, occupancy grid with the higher-priority agents stamped in,
+    A* with the reference's hash-order tie-breaking, line-of-sight goal by ray casting, clip) against the oracle's
+    goalPlanningWithPriority, teacher-forced. Goals are float32 points compared bit for bit; the A* expansion counts of
+    the whole run are equal too (same searches, not just same goals)."""
+    import lsc_planner_b200 as L
+    bt = os.path.join(golden_dir, "worlds", "simple_forest.bt")
+    scn = _forest_case(case, tmp_path, bt)
+    n = scn.n
+    omap = O.Map.from_bt(bt, scn.world_min, scn.world_max)
+    sw = _oracle_swarm(scn, omap)
+    e = L.ReplanEngine(n, L.Param(world_min=scn.world_min, world_max=scn.world_max, world_use_octomap=True, goal_mode=1), scn.agents)
+    e.set_octomap_file(bt)
+    expanded = 0; kinds = np.zeros(2, int); moved = 0
+    for step in range(steps):
+        pos, vel, acc = sw.state()
+        e.set_sfc(sw.boxes(), np.full(n, 1 if sw.seq == 0 else 0, np.int32))
+        e.set_prev_traj(sw.traj(), sw.seq)
+        sw.step()
+        out = e.replan(pos, vel, acc, scn.goal)
+        expanded += e.step_stats()["astar_expansions"]
+        g_o, k_o = sw.goals()
+        bad = np.flatnonzero((out["current_goal"].view(np.uint32) != g_o.view(np.uint32)).any(axis=1))
+        assert len(bad) == 0, (step, bad[:8], out["current_goal"][bad[:4]], g_o[bad[:4]])
+        assert np.array_equal(out["goal_kind"], k_o), step
+        q = sw.qp()
+        assert np.array_equal(out["qp_status"], q["status"]), step
+        diffs = np.abs(out["traj"] - sw.traj()).reshape(n, -1).max(1)
+        in_band = (q["maxviol"] > 1e-9) | ((out["flags"] & 64) != 0)
+        assert diffs[~in_band].max(initial=0) <= 2e-6 and diffs.max() <= 2e-5, (step, diffs.max())
+        kinds += np.bincount(k_o, minlength=2)
+        moved += int((np.linalg.norm(g_o - scn.goal, axis=1) > 1e-3).sum())
+        sw.advance()
+    assert moved > 0                               # goals that are not simply the desired goal
+    assert expanded == sw.astar_expansions() and expanded > 1000, (expanded, sw.astar_expansions())
+    e.close()
+
+
+def test_device_goal_with_octomap_closed_loop_resident(golden_dir, tmp_path):
+    """Device-resident closed loop (goal planning, corridors and QP without a host round trip) equals the host-driven one."""
+    import lsc_planner_b200 as L
+    bt = os.path.join(golden_dir, "worlds", "simple_forest.bt")
+    scn = _forest_case("forest10", tmp_path, bt)
+    prm = L.Param(world_min=scn.world_min, world_max=scn.world_max, world_use_octomap=True, goal_mode=1)
+    e1 = L.ReplanEngine(scn.n, prm, scn.agents); e2 = L.ReplanEngine(scn.n, prm, scn.agents)
+    e1.set_octomap_file(bt); e2.set_octomap_file(bt)
+    e1.set_states(scn.start); e1.set_goals(scn.goal)
+    pos = scn.start.copy(); vel = np.zeros_like(pos); acc = np.zeros_like(pos)
+    for _ in range(40):
+        e1.replan_resident(1)
+        out = e2.replan(pos, vel, acc, scn.goal)
+        pos, vel, acc = out["next_position"].copy(), out["next_velocity"].copy(), out["next_acceleration"].copy()
+    o1 = e1.fetch()
+    assert np.array_equal(o1["traj"].view(np.uint32), out["traj"].view(np.uint32))
+    assert np.array_equal(o1["current_goal"].view(np.uint32), out["current_goal"].view(np.uint32))
+    e1.close(); e2.close()
 
 
 def test_device_goal_closed_loop_resident():
@@ -101,9 +163,11 @@ def _forest_mission(path, n=10):
         json.dump(ms, f)
 
 
-def test_simulator_prior_based_forest_matches_oracle(tmp_path, golden_dir):
-    """lsc_sim with mode/goal=prior_based and an octomap: goals from the host grid planner (A* + line of sight, threaded),
-    corridors and QP from the kernels — against the oracle's closed loop with goal_mode 1."""
+@pytest.mark.parametrize("planner", ["device", "host"])
+def test_simulator_prior_based_forest_matches_oracle(planner, tmp_path, golden_dir):
+    """lsc_sim with mode/goal=prior_based and an octomap: goals from k_goal_astar inside the step (goal/planner=device, the
+    default) or from the host grid planner (A* + line of sight, threaded; goal/planner=host), corridors and QP from the
+    kernels — against the oracle's closed loop with goal_mode 1."""
     import lsc_planner_b200 as L
     from lsc_planner_b200 import build as B
     B.build()
@@ -113,7 +177,7 @@ def test_simulator_prior_based_forest_matches_oracle(tmp_path, golden_dir):
     res, summ = str(tmp_path / "result.csv"), str(tmp_path / "summary.csv")
     steps = 40
     r = subprocess.run([os.path.join(HOST, "lsc_sim"), "mission=" + mission, "world/file_name=" + bt, "mode/goal=prior_based",
-                        "multisim/record_time_step=0.2", f"multisim/max_planner_iteration={steps + 1}", "result=" + res,
+                        "goal/planner=" + planner, "multisim/record_time_step=0.2", f"multisim/max_planner_iteration={steps + 1}", "result=" + res,
                         "summary=" + summ], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr
     scn = L.scenarios.load_mission(mission)
