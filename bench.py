@@ -356,8 +356,7 @@ def run_ours(args):
 
     def host_step():
         eng.replan_ptr(pin_in.data_ptr(), pin_out.data_ptr())      # H2D + kernels (+ all-gather) + D2H, synchronous
-        h_in["position"] = h_out["next_position"]; h_in["velocity"] = h_out["next_velocity"]
-        h_in["acceleration"] = h_out["next_acceleration"]
+        eng.advance_inputs_ptr(pin_out.data_ptr(), pin_in.data_ptr())   # the host closes the loop: next state = plan at t = dt
 
     for _ in range(args.warmup):
         host_step()

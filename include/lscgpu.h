@@ -191,6 +191,13 @@ int lscgpu_p2p_attach(lscgpu_engine* e, const uint8_t* handles /* [n_ranks][64] 
  * TrajOptimizer::solve. `in` and `out` are host arrays of n_agents elements (all agents, also on a sharded engine:
  * the step ends with the all-gather, so every rank returns every agent). planner_seq is advanced by one. */
 int lscgpu_replan_batch(lscgpu_engine* e, const lscgpu_agent_in* in, lscgpu_agent_out* out);
+/* When `out` is pinned host memory (cudaHostAlloc / cudaHostRegister; 16-byte aligned) and one engine plans every agent, the
+ * planning blocks store their records straight into it as each agent is done (the device-to-host transfer overlaps the
+ * planning of the others); otherwise the records are copied after the step. Same bytes either way.
+ *
+ * The state hand-over of MultiSyncSimulator::update (src/multi_sync_simulator.cpp:203: the next current_state is the planned
+ * trajectory at t = dt): in[a].position / velocity / acceleration = out[a].next_*, goals untouched. Host-side convenience. */
+int lscgpu_advance_inputs(const lscgpu_agent_out* out, lscgpu_agent_in* in, int n_agents);
 
 /* Device-resident variant used for kernel-level timing: the inputs are the engine's own advanced states
  * (previous trajectories evaluated at t = dt) and the goals of the last lscgpu_replan_batch / lscgpu_set_goals.

@@ -64,7 +64,7 @@ def symbols():
     return ["lscgpu_last_error", "lscgpu_version", "lscgpu_create", "lscgpu_destroy", "lscgpu_set_octomap_file",
             "lscgpu_set_octomap_voxels", "lscgpu_get_distmap_info", "lscgpu_get_distmap_sqdist", "lscgpu_set_shard",
             "lscgpu_nccl_unique_id", "lscgpu_nccl_init", "lscgpu_p2p_export", "lscgpu_p2p_attach", "lscgpu_replan_batch",
-            "lscgpu_safety_audit", "lscgpu_set_goals",
+            "lscgpu_advance_inputs",            "lscgpu_safety_audit", "lscgpu_set_goals",
             "lscgpu_set_states", "lscgpu_replan_resident", "lscgpu_synchronize", "lscgpu_fetch", "lscgpu_reset", "lscgpu_set_prev_traj",
             "lscgpu_set_sfc", "lscgpu_get_sfc", "lscgpu_get_planner_seq", "lscgpu_get_lsc", "lscgpu_get_lsc_ex",
             "lscgpu_set_slack_collision_weight", "lscgpu_get_reset_state", "lscgpu_set_reset_state",
@@ -98,6 +98,7 @@ def lib():
     L.lscgpu_p2p_export.argtypes = [ptr, ptr]
     L.lscgpu_p2p_attach.argtypes = [ptr, ptr]
     L.lscgpu_replan_batch.argtypes = [ptr, ptr, ptr]
+    L.lscgpu_advance_inputs.argtypes = [ptr, ptr, C.c_int]
     L.lscgpu_safety_audit.argtypes = [ptr, C.c_double, C.c_double, ptr, ptr]
     L.lscgpu_set_goals.argtypes = [ptr, ptr]
     L.lscgpu_set_states.argtypes = [ptr, ptr, ptr, ptr]

@@ -177,6 +177,14 @@ struct lscgpu_engine {
     float* d_goal_axis = nullptr; uint8_t* d_goal_static = nullptr;
     uint8_t* d_goal_cell = nullptr; int* d_goal_g = nullptr; int* d_goal_next = nullptr; int* d_goal_bkt = nullptr; int* d_goal_path = nullptr;
     unsigned long long* d_goal_expansions = nullptr;
+    // zero-copy results: when lscgpu_replan_batch's `out` is pinned host memory the planning blocks store their records
+    // straight into it (device word d_host_out = its device alias, null otherwise); h_host_out: pinned staging of that word
+    lscgpu_agent_out** d_host_out = nullptr;
+    lscgpu_agent_out** h_host_out = nullptr;
+    lscgpu_agent_out* host_out_on_device = nullptr;      // value the device word holds
+    const void* host_out_queried = nullptr;              // last `out` looked up, and its device alias (null: not mapped)
+    lscgpu_agent_out* host_out_alias = nullptr;
+    bool zero_copy = true;
     // exchange
     NcclComm comm = nullptr;
     int rank = 0, n_ranks = 1, block = 0;
@@ -255,6 +263,7 @@ extern "C" void lscgpu_destroy(lscgpu_engine* e) {
     cudaFree(e->d_kept_step); if (e->h_kept_last) cudaFreeHost(e->h_kept_last);
     cudaFree(e->d_epoch); cudaFree(e->d_sfc_ready); cudaFree(e->d_sfc_box); cudaFree(e->d_sfc_ok);
     cudaFree(e->d_reset_ever); cudaFree(e->d_any_reset);
+    cudaFree(e->d_host_out); if (e->h_host_out) cudaFreeHost(e->h_host_out);
     cudaFree(e->d_goal_axis); cudaFree(e->d_goal_static); cudaFree(e->d_goal_cell); cudaFree(e->d_goal_g); cudaFree(e->d_goal_next);
     cudaFree(e->d_goal_bkt); cudaFree(e->d_goal_path); cudaFree(e->d_goal_expansions);
     if (e->ev_sfc) cudaEventDestroy(e->ev_sfc);
@@ -435,6 +444,11 @@ extern "C" int lscgpu_create(const lscgpu_params* p, int n_agents, const lscgpu_
     CUB(cudaMalloc(&e->d_goal_kind, sizeof(int) * N));
     CUB(cudaMemset(e->d_goal_kind, 0, sizeof(int) * N));
     CUB(cudaMalloc(&e->d_init_sfc, sizeof(int) * N));
+    CUB(cudaMalloc(&e->d_host_out, sizeof(void*)));
+    CUB(cudaMemset(e->d_host_out, 0, sizeof(void*)));
+    CUB(cudaHostAlloc(&e->h_host_out, sizeof(void*), cudaHostAllocDefault));
+    *e->h_host_out = nullptr;
+    if (const char* v = getenv("LSCGPU_ZERO_COPY")) e->zero_copy = atoi(v) != 0;      // 0: always copy the results after the step
     CUB(cudaMalloc(&e->d_counters, sizeof(StepCounters)));
     CUB(cudaMemset(e->d_counters, 0, sizeof(StepCounters)));
     int rc = alloc_gather(e, n_agents);
@@ -848,6 +862,7 @@ static int enqueue_step_kernels(lscgpu_engine* e, int planner_seq, int threads, 
         px.n_agents = e->N; px.base_epoch = e->p2p_base_epoch;
     }
     L.px = px;
+    L.host_out = e->d_host_out;
     L.prev_traj = e->d_traj; L.last_cost = e->d_last_cost; L.goal_kind = e->d_goal_kind;
     L.counters = e->d_counters;
     L.any_reset = e->slack_kernel ? e->d_any_reset : nullptr; L.reset_ever = e->d_reset_ever;
@@ -1036,13 +1051,39 @@ static int compute_stats(lscgpu_engine* e) {
 
 static int dump_qp_lp(lscgpu_engine* e, int agent, const char* path);
 
+// Points the device word the planning blocks read at `alias` (null: they keep their records on the device). Enqueued on the
+// engine stream, only when the value changes.
+static int set_host_out(lscgpu_engine* e, lscgpu_agent_out* alias) {
+    if (alias == e->host_out_on_device) return LSCGPU_OK;
+    CU(cudaStreamSynchronize(e->stream));            // the staging word may still be in flight
+    *e->h_host_out = alias;
+    CU(cudaMemcpyAsync(e->d_host_out, e->h_host_out, sizeof(void*), cudaMemcpyHostToDevice, e->stream));
+    e->host_out_on_device = alias;
+    return LSCGPU_OK;
+}
+
 extern "C" int lscgpu_replan_batch(lscgpu_engine* e, const lscgpu_agent_in* in, lscgpu_agent_out* out) {
     if (!e || !in || !out) return fail(LSCGPU_ERR_ARG, "null argument");
     CU(cudaSetDevice(e->device));
+    // `out` in pinned host memory (cudaHostAlloc / cudaHostRegister, 16-byte aligned), one engine planning every agent: the
+    // planning blocks write their records into it as they finish; otherwise one copy after the step
+    lscgpu_agent_out* alias = nullptr;
+    if (e->zero_copy && !e->comm && e->a0 == 0 && e->a1 == e->N && ((uintptr_t)out & 15) == 0) {
+        if (out != e->host_out_queried) {
+            cudaPointerAttributes at{};
+            e->host_out_alias = nullptr;
+            if (cudaPointerGetAttributes(&at, out) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+                e->host_out_alias = (lscgpu_agent_out*)at.devicePointer;
+            else cudaGetLastError();
+            e->host_out_queried = out;
+        }
+        alias = e->host_out_alias;
+    }
+    if (const int rs = set_host_out(e, alias)) return rs;
     CU(cudaMemcpyAsync(e->d_in, in, sizeof(lscgpu_agent_in) * (size_t)e->N, cudaMemcpyHostToDevice, e->stream));
     const int rc = step_device(e);
     if (rc != LSCGPU_OK) return rc;
-    CU(cudaMemcpyAsync(out, e->d_res, sizeof(lscgpu_agent_out) * (size_t)e->N, cudaMemcpyDeviceToHost, e->stream));
+    if (!alias) CU(cudaMemcpyAsync(out, e->d_res, sizeof(lscgpu_agent_out) * (size_t)e->N, cudaMemcpyDeviceToHost, e->stream));
     const int rf = finish_steps(e);
     if (rf != LSCGPU_OK || e->lp_dump_dir.empty()) return rf;
     // as the reference on an IloException (src/traj_optimizer.cpp:99-101): the model of every failed solve goes to a file
@@ -1055,9 +1096,22 @@ extern "C" int lscgpu_replan_batch(lscgpu_engine* e, const lscgpu_agent_in* in, 
     return LSCGPU_OK;
 }
 
+// MultiSyncSimulator::update's hand-over of the planned state (src/multi_sync_simulator.cpp:203: the next current_state is
+// the trajectory at t = dt): in[a].position / velocity / acceleration = out[a].next_*; goals are left as they are. Host only.
+extern "C" int lscgpu_advance_inputs(const lscgpu_agent_out* out, lscgpu_agent_in* in, int n_agents) {
+    if (!out || !in || n_agents < 0) return fail(LSCGPU_ERR_ARG, "null argument");
+    for (int a = 0; a < n_agents; a++) {
+        std::memcpy(in[a].position, out[a].next_position, sizeof(float) * 3);
+        std::memcpy(in[a].velocity, out[a].next_velocity, sizeof(float) * 3);
+        std::memcpy(in[a].acceleration, out[a].next_acceleration, sizeof(float) * 3);
+    }
+    return LSCGPU_OK;
+}
+
 extern "C" int lscgpu_replan_resident(lscgpu_engine* e) {
     if (!e) return fail(LSCGPU_ERR_ARG, "null engine");
     CU(cudaSetDevice(e->device));
+    if (const int rs = set_host_out(e, nullptr)) return rs;
     return step_device(e);
 }
 

@@ -121,6 +121,9 @@ struct PlanLaunch {
     // outputs
     GatherSlot* out;               // block i writes slot out[out_base + i] (gather buffer: rank-major, carries agent_id)
     PeerExchange px;               // px.peers != null: the block also stores its slot into every peer's buffer
+    lscgpu_agent_out* const* host_out;   // null, or device word holding the caller's result array when that is pinned host memory
+                                   // mapped into the device (else null): the block stores its record straight into
+                                   // host_out[agent] — the device-to-host transfer overlaps the planning of the other agents
     const unsigned short* act_prev;    // null (cold starts), or [N][kActSlots]: rows active at every agent's previous solve
     int out_base;
     const float* prev_traj;        // [N][90]  (kept when the QP fails)

@@ -447,6 +447,17 @@ __global__ void __launch_bounds__(kPlanThreads, kSlack ? (kPlanThreads > 256 ? 1
         }
 #endif
     }
+    if (L.host_out) {
+        lscgpu_agent_out* const h = *L.host_out;
+        if (h) {
+            // the caller's result array is mapped host memory: the record goes there now (posted writes over PCIe), not in a
+            // copy after the step
+            __syncwarp();
+            constexpr int kRecVec = (int)(sizeof(lscgpu_agent_out) / 16);
+            static_assert(kRecVec <= 32, "record larger than one vector per lane");
+            if (lane < kRecVec) reinterpret_cast<uint4*>(h + a)[lane] = reinterpret_cast<const uint4*>(&o)[lane];
+        }
+    }
     if (L.px.peers) {
         // The finished slot goes straight into every peer's exchange buffer (stores through the NVLink peer mapping, 16 bytes
         // per lane), then the peer's arrival counter for this rank is bumped: the transfer of one agent's record overlaps the

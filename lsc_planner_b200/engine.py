@@ -177,6 +177,10 @@ class ReplanEngine:
         """Same, on raw host addresses (e.g. pinned torch tensors)."""
         A.check(self.lib.lscgpu_replan_batch(self.h, A.ptr(in_ptr), A.ptr(out_ptr)))
 
+    def advance_inputs_ptr(self, out_ptr: int, in_ptr: int):
+        """in[a].position / velocity / acceleration = out[a].next_* on raw host addresses (the simulator's state hand-over)."""
+        A.check(self.lib.lscgpu_advance_inputs(A.ptr(out_ptr), A.ptr(in_ptr), self.n))
+
     def set_goals(self, goal):
         g = np.ascontiguousarray(goal, np.float32).reshape(self.n, 3)
         A.check(self.lib.lscgpu_set_goals(self.h, A.p(g)))

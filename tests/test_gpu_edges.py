@@ -179,3 +179,45 @@ def test_results_do_not_depend_on_the_block_size(monkeypatch):
         assert np.array_equal(outs[128]["qp_status"], outs[threads]["qp_status"])
         assert np.array_equal(outs[128]["qp_iterations"], outs[threads]["qp_iterations"])
     assert (outs[128]["lsc_pairs_kept"] > 0).any()
+
+
+def test_pinned_result_buffer_is_written_by_the_planning_blocks(golden_dir):
+    """lscgpu_replan_batch with `out` in pinned host memory: the planning blocks store their records straight into it
+    (no copy after the step). Every field equals what the copy path returns from a twin engine fed the same inputs — the
+    cycle counters aside — over a closed loop that alternates with device-resident steps (which must leave the buffer
+    alone), with and without an octomap."""
+    import torch
+    import lsc_planner_b200 as L
+    from lsc_planner_b200 import _capi as A
+    for use_map in (False, True):
+        scn = L.scenarios.circle_swap(96)
+        prm = L.Param(world_min=scn.world_min, world_max=scn.world_max, world_use_octomap=use_map)
+        e1 = L.ReplanEngine(scn.n, prm, scn.agents); e2 = L.ReplanEngine(scn.n, prm, scn.agents)
+        if use_map:
+            bt = os.path.join(golden_dir, "worlds", "simple_forest.bt")
+            e1.set_octomap_file(bt); e2.set_octomap_file(bt)
+        n = scn.n
+        pin_in = torch.zeros(n * A.AGENT_IN.itemsize, dtype=torch.uint8).pin_memory()
+        pin_out = torch.zeros(n * A.AGENT_OUT.itemsize, dtype=torch.uint8).pin_memory()
+        h_in = pin_in.numpy().view(A.AGENT_IN); h_out = pin_out.numpy().view(A.AGENT_OUT)
+        h_in["position"] = scn.start; h_in["goal"] = scn.goal
+        pos = scn.start.copy(); vel = np.zeros_like(pos); acc = np.zeros_like(pos)
+        timing = ("qp_kcycles", "qp_price_kcycles", "lsc_kcycles", "sfc_in_block")
+        for step in range(12):
+            e1.replan_ptr(pin_in.data_ptr(), pin_out.data_ptr())
+            ref = e2.replan(pos, vel, acc, scn.goal)
+            for name in A.AGENT_OUT.names:
+                if name not in timing:
+                    assert np.array_equal(h_out[name], ref[name]), (use_map, step, name)
+            if step == 5:
+                # a resident step on both engines: the pinned buffer keeps the previous step's records
+                before = h_out.copy()
+                e1.replan_resident(1); e2.replan_resident(1)
+                assert np.array_equal(h_out.view(np.uint8), before.view(np.uint8))
+                ref = e2.fetch(); got = e1.fetch()
+                assert np.array_equal(got["traj"], ref["traj"])
+                h_in["position"] = got["next_position"]; h_in["velocity"] = got["next_velocity"]; h_in["acceleration"] = got["next_acceleration"]
+            else:
+                e1.advance_inputs_ptr(pin_out.data_ptr(), pin_in.data_ptr())
+            pos, vel, acc = h_in["position"].copy(), h_in["velocity"].copy(), h_in["acceleration"].copy()
+        e1.close(); e2.close()
