@@ -53,6 +53,14 @@ struct AstarCtx {
     I* bkt;                 // [H][bcap] bucket array of every row container: kNone, kEnd (= the run starts at the list head)
                             // or the node BEFORE the bucket's first node
     int bcap;
+    // Order stamps (optional; null: off). The runs of the buckets lie in the list in the order in which the buckets became
+    // non-empty, newest first (a node that enters an empty bucket goes to the list head; erasures and insertions into a
+    // non-empty bucket move no run; a rehash re-threads in iteration order, again newest first). bstamp[row][bucket] = value
+    // of the row's event counter when the bucket last became non-empty: of two nodes in different buckets the one with the
+    // SMALLER stamp comes later in the iteration. This lets deleteMin's tie-break (the last of the minimal nodes in
+    // iteration order) be decided without walking the list; only ties inside one bucket walk that bucket's short run.
+    I* bstamp;              // [H][bcap]
+    int* stamp;             // [H] event counter of the row
     // per grid row i: the container (head, element count, index into bkt_seq) and the cached row minimum (isearch.cpp's
     // `min` node per row)
     int *head, *count, *level, *min_cell, *min_g;
@@ -133,6 +141,7 @@ template <typename I> ASTAR_HD void astar_rehash(AstarCtx<I>& c, int r, int lvl)
             if (head >= 0) nb[begin_bkt] = (I)p;
             head = p; nb[b] = kEnd;
             begin_bkt = b;
+            if (c.bstamp) c.bstamp[(size_t)r * c.bcap + b] = (I)(++c.stamp[r]);
         } else if (nb[b] == kEnd) {
             c.next[p] = head < 0 ? kEnd : (I)head; head = p;
         } else {
@@ -166,6 +175,7 @@ template <typename I> ASTAR_HD void astar_insert(AstarCtx<I>& c, int r, int nd) 
         c.next[nd] = old < 0 ? kEnd : (I)old; c.head[r] = nd;
         if (old >= 0) bk[astar_bucket(c, old, cl)] = (I)nd;
         bk[b] = kEnd;
+        if (c.bstamp) c.bstamp[(size_t)r * c.bcap + b] = (I)(++c.stamp[r]);
     }
     c.count[r] = cnt + 1;
 }
@@ -266,6 +276,49 @@ template <typename I> ASTAR_HD void astar_rescan(AstarCtx<I>& c, int ci, int onl
     }
     if (best >= 0) { c.min_cell[ci] = best; c.min_f[ci] = bf; c.min_g[ci] = bg; }
     ASTAR_TICK(2);
+}
+
+// the order stamp of an open cell of row ci (smaller = later in the row container's iteration)
+template <typename I> ASTAR_HD unsigned astar_stamp_of(const AstarCtx<I>& c, int ci, int cell) {
+    return (unsigned)c.bstamp[(size_t)ci * c.bcap + astar_bucket(c, cell, c.level[ci])];
+}
+// the last node of bucket `of_cell`'s run that carries (f, g): the tie-break among minimal nodes sharing one bucket
+template <typename I> ASTAR_HD int astar_last_in_bucket(const AstarCtx<I>& c, int ci, int of_cell, double f, int g) {
+    constexpr I kEnd = AstarCtx<I>::kEnd;
+    const int cl = c.level[ci];
+    const unsigned b = astar_bucket(c, of_cell, cl);
+    const I before = c.bkt[(size_t)ci * c.bcap + b];
+    int last = -1;
+    for (int p = before == kEnd ? c.head[ci] : (int)c.next[before]; p >= 0;) {
+        if (astar_bucket(c, p, cl) != b) break;
+        const int pg = (int)c.g[p];
+        if (pg == g && astar_f(c, p, pg) == f) last = p;
+        const I nx = c.next[p];
+        p = nx == kEnd ? -1 : (int)nx;
+    }
+    return last;
+}
+// deleteMin's re-scan stated over the row's cells and the order stamps instead of the list (serial form of what the kernel
+// does with one slice of the row per lane); returns the new row minimum or -1 for an empty row
+template <typename I> ASTAR_HD int astar_rescan_by_stamp(const AstarCtx<I>& c, int ci) {
+    const int row_cells = c.W * c.A, base = ci * row_cells, di = c.gi - ci;
+    int best = -1, bg = 0; double bf = 0; unsigned bs = 0; bool dup = false;
+    for (int o = 0; o < row_cells; o++) {
+        const int id = base + o;
+        if ((c.cell[id] & kCellStateMask) != kCellOpen) continue;
+        const int pg = (int)c.g[id];
+        const int pj = (int)astar_div((unsigned)o, (unsigned)c.A, c.magic_a), pz = o - pj * c.A;
+        const int dj = c.gj - pj, dz = c.gz - pz;
+        const double pf = (double)pg + astar_h(c, di * di + dj * dj + dz * dz);
+        if (best < 0 || pf < bf || (pf == bf && pg > bg)) { best = id; bf = pf; bg = pg; bs = astar_stamp_of(c, ci, id); dup = false; }
+        else if (pf == bf && pg == bg) {
+            const unsigned st = astar_stamp_of(c, ci, id);
+            if (st < bs) { best = id; bs = st; dup = false; }
+            else if (st == bs) dup = true;
+        }
+    }
+    if (best >= 0 && dup) best = astar_last_in_bucket(c, ci, best, bf, bg);
+    return best;
 }
 
 template <typename I> ASTAR_HD int astar_open_neighbours(AstarCtx<I>& c, int ci, int cj, int cz, int cur_g) {

@@ -78,6 +78,13 @@ struct Scratch {
     }
     void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
 };
+// device buffer that frees itself when the function that made it returns (early error returns included)
+struct TempBuf {
+    void* p = nullptr;
+    ~TempBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
 // carve typed arrays out of one scratch allocation (256-byte aligned)
 struct Carver {
     size_t off = 0;
@@ -175,15 +182,15 @@ struct lscgpu_engine {
     bool have_goal_grid = false;
     int goal_blocks = 0;
     float* d_goal_axis = nullptr; uint8_t* d_goal_static = nullptr;
-    uint8_t* d_goal_cell = nullptr; int* d_goal_g = nullptr; int* d_goal_next = nullptr; int* d_goal_bkt = nullptr; int* d_goal_path = nullptr;
+    uint8_t* d_goal_cell = nullptr; int* d_goal_g = nullptr; int* d_goal_next = nullptr; int* d_goal_bkt = nullptr; int* d_goal_bstamp = nullptr; int* d_goal_path = nullptr;
     unsigned long long* d_goal_expansions = nullptr;
+    int* d_goal_ticket = nullptr;          // next entry of the schedule k_goal_astar hands out
     // zero-copy results: when lscgpu_replan_batch's `out` is pinned host memory the planning blocks store their records
     // straight into it (device word d_host_out = its device alias, null otherwise); h_host_out: pinned staging of that word
     lscgpu_agent_out** d_host_out = nullptr;
     lscgpu_agent_out** h_host_out = nullptr;
     lscgpu_agent_out* host_out_on_device = nullptr;      // value the device word holds
-    const void* host_out_queried = nullptr;              // last `out` looked up, and its device alias (null: not mapped)
-    lscgpu_agent_out* host_out_alias = nullptr;
+    lscgpu_agent_out* host_out_alias = nullptr;          // device alias of the current call's `out` (null: not mapped)
     bool zero_copy = true;
     // exchange
     NcclComm comm = nullptr;
@@ -265,7 +272,7 @@ extern "C" void lscgpu_destroy(lscgpu_engine* e) {
     cudaFree(e->d_reset_ever); cudaFree(e->d_any_reset);
     cudaFree(e->d_host_out); if (e->h_host_out) cudaFreeHost(e->h_host_out);
     cudaFree(e->d_goal_axis); cudaFree(e->d_goal_static); cudaFree(e->d_goal_cell); cudaFree(e->d_goal_g); cudaFree(e->d_goal_next);
-    cudaFree(e->d_goal_bkt); cudaFree(e->d_goal_path); cudaFree(e->d_goal_expansions);
+    cudaFree(e->d_goal_bkt); cudaFree(e->d_goal_bstamp); cudaFree(e->d_goal_path); cudaFree(e->d_goal_expansions); cudaFree(e->d_goal_ticket);
     if (e->ev_sfc) cudaEventDestroy(e->ev_sfc);
     cudaFree(e->d_rdw); cudaFree(e->d_audit_pos); cudaFree(e->d_audit_ratio); cudaFree(e->d_audit_closest); cudaFree(e->d_dbg);
     cudaFree(e->d_tables); cudaFree(e->d_consts); cudaFree(e->d_in); cudaFree(e->d_gather); cudaFree(e->d_res); cudaFree(e->d_traj);
@@ -488,7 +495,8 @@ static int goal_bucket_sequence(int row_capacity, int* seq) {
 // per map; scratch for one search per warp.
 static int setup_goal_grid(lscgpu_engine* e) {
     cudaFree(e->d_goal_axis); cudaFree(e->d_goal_static); cudaFree(e->d_goal_cell); cudaFree(e->d_goal_g); cudaFree(e->d_goal_next);
-    cudaFree(e->d_goal_bkt); cudaFree(e->d_goal_path);
+    cudaFree(e->d_goal_bkt); cudaFree(e->d_goal_bstamp); cudaFree(e->d_goal_path);
+    e->d_goal_bstamp = nullptr;
     e->d_goal_axis = nullptr; e->d_goal_static = nullptr; e->d_goal_cell = nullptr; e->d_goal_g = nullptr; e->d_goal_next = nullptr;
     e->d_goal_bkt = nullptr; e->d_goal_path = nullptr;
     e->have_goal_grid = false;
@@ -528,13 +536,12 @@ static int setup_goal_grid(lscgpu_engine* e) {
     CU(cudaMalloc(&e->d_goal_static, g.cells_pad * (size_t)n_radii));
     CU(cudaMemsetAsync(e->d_goal_static, 0, g.cells_pad * (size_t)n_radii, e->stream));
     g.static_occ = e->d_goal_static;
-    double* d_radii = nullptr;
-    CU(cudaMalloc(&d_radii, sizeof(double) * n_radii));
-    CU(cudaMemcpyAsync(d_radii, e->radii.data(), sizeof(double) * n_radii, cudaMemcpyHostToDevice, e->stream));
-    launch_goal_static_grid(g, e->dm, e->prm.world_resolution, d_radii, n_radii, (float)e->prm.grid_margin, e->d_goal_static, e->stream);
+    TempBuf radii_buf;
+    CU(radii_buf.alloc(sizeof(double) * n_radii));
+    CU(cudaMemcpyAsync(radii_buf.p, e->radii.data(), sizeof(double) * n_radii, cudaMemcpyHostToDevice, e->stream));
+    launch_goal_static_grid(g, e->dm, e->prm.world_resolution, radii_buf.as<double>(), n_radii, (float)e->prm.grid_margin, e->d_goal_static, e->stream);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(e->stream));
-    cudaFree(d_radii);
     // One search per warp. Small grids keep the warp's search state in shared memory (one warp per SM, or more when several
     // fit); larger ones run on per-warp scratch in global memory, as many warps as the device keeps resident, bounded by
     // 4 GB of scratch.
@@ -544,16 +551,18 @@ static int setup_goal_grid(lscgpu_engine* e) {
     if (sh) {
         blocks = std::min(e->N, e->n_sm * std::max(1, (int)((227 * 1024) / (sh + 1024))));
     } else {
-        const size_t per_warp = g.cells_pad * (1 + 3 * sizeof(int)) + (size_t)g.dim[0] * g.bcap * sizeof(int);
+        const size_t per_warp = g.cells_pad * (1 + 3 * sizeof(int)) + 2 * (size_t)g.dim[0] * g.bcap * sizeof(int);
         blocks = std::min(e->N, e->n_sm * 16);
         blocks = (int)std::max<size_t>(1, std::min<size_t>((size_t)blocks, ((size_t)4 << 30) / per_warp));
         CU(cudaMalloc(&e->d_goal_cell, g.cells_pad * (size_t)blocks));
         CU(cudaMalloc(&e->d_goal_g, sizeof(int) * g.cells_pad * (size_t)blocks));
         CU(cudaMalloc(&e->d_goal_next, sizeof(int) * g.cells_pad * (size_t)blocks));
         CU(cudaMalloc(&e->d_goal_bkt, sizeof(int) * (size_t)g.dim[0] * g.bcap * (size_t)blocks));
+        CU(cudaMalloc(&e->d_goal_bstamp, sizeof(int) * (size_t)g.dim[0] * g.bcap * (size_t)blocks));
     }
     e->goal_blocks = blocks;
     CU(cudaMalloc(&e->d_goal_path, sizeof(int) * g.cells_pad * (size_t)blocks));
+    if (!e->d_goal_ticket) CU(cudaMalloc(&e->d_goal_ticket, sizeof(int)));
     if (!e->d_goal_expansions) {
         CU(cudaMalloc(&e->d_goal_expansions, sizeof(unsigned long long)));
         CU(cudaMemset(e->d_goal_expansions, 0, sizeof(unsigned long long)));
@@ -597,20 +606,19 @@ static int build_map(lscgpu_engine* e, const int32_t* keys, int n) {
         thr[t] = last;
     }
     e->dm.n_tables = (int)thr.size();
-    int32_t* d_keys = nullptr; int* d_thr = nullptr; uint8_t *sa = nullptr, *sb = nullptr;
+    TempBuf keys_buf, thr_buf, sa, sb;              // freed on every return path
     CU(cudaMalloc(&e->dm.sqdist, total));
     CU(cudaMalloc(&e->dm.sat, tab * sizeof(int) * thr.size()));
-    CU(cudaMalloc(&sa, total)); CU(cudaMalloc(&sb, total));
-    CU(cudaMalloc(&d_thr, sizeof(int) * thr.size()));
-    CU(cudaMemcpyAsync(d_thr, thr.data(), sizeof(int) * thr.size(), cudaMemcpyHostToDevice, e->stream));
+    CU(sa.alloc(total)); CU(sb.alloc(total));
+    CU(thr_buf.alloc(sizeof(int) * thr.size()));
+    CU(cudaMemcpyAsync(thr_buf.p, thr.data(), sizeof(int) * thr.size(), cudaMemcpyHostToDevice, e->stream));
     if (n > 0) {
-        CU(cudaMalloc(&d_keys, sizeof(int32_t) * 3 * (size_t)n));
-        CU(cudaMemcpyAsync(d_keys, keys, sizeof(int32_t) * 3 * (size_t)n, cudaMemcpyHostToDevice, e->stream));
+        CU(keys_buf.alloc(sizeof(int32_t) * 3 * (size_t)n));
+        CU(cudaMemcpyAsync(keys_buf.p, keys, sizeof(int32_t) * 3 * (size_t)n, cudaMemcpyHostToDevice, e->stream));
     }
-    launch_edt_build(d_keys, n, e->dm, d_thr, e->dm.n_tables, sa, sb, e->stream);
+    launch_edt_build(keys_buf.as<int32_t>(), n, e->dm, thr_buf.as<int>(), e->dm.n_tables, sa.as<uint8_t>(), sb.as<uint8_t>(), e->stream);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(e->stream));
-    cudaFree(d_keys); cudaFree(d_thr); cudaFree(sa); cudaFree(sb);
     int64_t occ = 0;
     for (int i = 0; i < n; i++) {
         bool in = true;
@@ -823,8 +831,10 @@ static int enqueue_step_kernels(lscgpu_engine* e, int planner_seq, int threads, 
             al.order_first = dealt ? e->rank : 0; al.order_stride = dealt ? e->n_ranks : 1;
             al.agent_base = dealt ? e->rank : e->a0; al.agent_stride = dealt ? e->n_ranks : 1;
             al.dm = e->dm; al.world_res = e->prm.world_resolution; al.grid = e->goal_grid; al.n_blocks = e->goal_blocks;
-            al.cell = e->d_goal_cell; al.gcost = e->d_goal_g; al.next = e->d_goal_next; al.bkt = e->d_goal_bkt; al.path = e->d_goal_path;
+            al.cell = e->d_goal_cell; al.gcost = e->d_goal_g; al.next = e->d_goal_next; al.bkt = e->d_goal_bkt; al.bstamp = e->d_goal_bstamp; al.path = e->d_goal_path;
             al.expansions = e->d_goal_expansions;
+            al.next_agent = e->d_goal_ticket;
+            CU(cudaMemsetAsync(e->d_goal_ticket, 0, sizeof(int), s));
             launch_goal_astar(al, s); launches++;
             if (const int rc = launch_sfc(s, e->d_goal3)) return rc;
         }
@@ -1069,14 +1079,12 @@ extern "C" int lscgpu_replan_batch(lscgpu_engine* e, const lscgpu_agent_in* in, 
     // planning blocks write their records into it as they finish; otherwise one copy after the step
     lscgpu_agent_out* alias = nullptr;
     if (e->zero_copy && !e->comm && e->a0 == 0 && e->a1 == e->N && ((uintptr_t)out & 15) == 0) {
-        if (out != e->host_out_queried) {
-            cudaPointerAttributes at{};
-            e->host_out_alias = nullptr;
-            if (cudaPointerGetAttributes(&at, out) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
-                e->host_out_alias = (lscgpu_agent_out*)at.devicePointer;
-            else cudaGetLastError();
-            e->host_out_queried = out;
-        }
+        // looked up on every call (sub-microsecond): the same address may be pinned in one call and pageable in the next
+        cudaPointerAttributes at{};
+        e->host_out_alias = nullptr;
+        if (cudaPointerGetAttributes(&at, out) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+            e->host_out_alias = (lscgpu_agent_out*)at.devicePointer;
+        else cudaGetLastError();
         alias = e->host_out_alias;
     }
     if (const int rs = set_host_out(e, alias)) return rs;

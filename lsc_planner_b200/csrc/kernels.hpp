@@ -150,8 +150,9 @@ struct GoalAstarLaunch {
     // per-warp scratch: path cells [n_blocks][cells_pad]; and, for grids whose search state does not fit shared memory,
     // cell bytes / g / list links [n_blocks][cells_pad] and row buckets [n_blocks][dim0][bcap]
     int* path;
-    uint8_t* cell; int* gcost; int* next; int* bkt;
+    uint8_t* cell; int* gcost; int* next; int* bkt; int* bstamp;
     unsigned long long* expansions;    // null, or the step's A* expansion counter
+    int* next_agent;               // device counter, zero at launch: the next entry of the schedule to plan
 };
 void launch_goal_astar(const GoalAstarLaunch& L, cudaStream_t s);
 size_t goal_astar_shared_bytes(const GoalGridDev& g);      // 0: the grid's search state does not fit one SM's shared memory

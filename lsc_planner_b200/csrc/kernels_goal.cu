@@ -83,12 +83,12 @@ __device__ bool cast_ray(const DistMapDev& dm, double inv_res, double res, F3 a,
     }
 }
 
-// dynamic shared memory: row table [H] (min_f, head, count, level, min_cell, min_g), then — shared variant — the search
+// dynamic shared memory: row table [H] (min_f, head, count, level, min_cell, min_g, stamp), then — shared variant — the search
 // state of the warp
-__host__ __device__ inline size_t goal_rows_bytes(int H) { return ((size_t)H * (sizeof(double) + 5 * sizeof(int)) + 15) / 16 * 16; }
+__host__ __device__ inline size_t goal_rows_bytes(int H) { return ((size_t)H * (sizeof(double) + 6 * sizeof(int)) + 15) / 16 * 16; }
 template <typename I>
 __host__ __device__ inline size_t goal_state_bytes(const GoalGridDev& g) {
-    return g.cells_pad * (1 + 2 * sizeof(I)) + ((size_t)g.dim[0] * g.bcap * sizeof(I) + 15) / 16 * 16;
+    return g.cells_pad * (1 + 2 * sizeof(I)) + 2 * (((size_t)g.dim[0] * g.bcap * sizeof(I) + 15) / 16 * 16);     // buckets + their order stamps
 }
 // entries of the table h = sqrt(d2), d2 = squared cell distance to the goal (shared variant)
 __host__ __device__ inline int goal_sqrt_entries(const GoalGridDev& g) {
@@ -108,7 +108,8 @@ __global__ void __launch_bounds__(32, 1) k_goal_astar(GoalAstarLaunch L) {
     double* r_min_f = reinterpret_cast<double*>(smem);
     int* r_head = reinterpret_cast<int*>(r_min_f + H);
     int* r_count = r_head + H; int* r_level = r_count + H; int* r_min_cell = r_level + H; int* r_min_g = r_min_cell + H;
-    uint8_t* cellb; I* gbuf; I* nextb; I* bkt;
+    int* r_stamp = r_min_g + H;
+    uint8_t* cellb; I* gbuf; I* nextb; I* bkt; I* bstamp;
     double* sqrt_tab = nullptr;
     if (kShared) {
         unsigned char* p = smem + goal_rows_bytes(H);
@@ -117,19 +118,27 @@ __global__ void __launch_bounds__(32, 1) k_goal_astar(GoalAstarLaunch L) {
         cellb = p; p += G.cells_pad;
         gbuf = reinterpret_cast<I*>(p); p += G.cells_pad * sizeof(I);
         nextb = reinterpret_cast<I*>(p); p += G.cells_pad * sizeof(I);
-        bkt = reinterpret_cast<I*>(p);
+        bkt = reinterpret_cast<I*>(p); p += ((size_t)H * G.bcap * sizeof(I) + 15) / 16 * 16;
+        bstamp = reinterpret_cast<I*>(p);
     } else {
         cellb = L.cell + (size_t)blockIdx.x * G.cells_pad;
         gbuf = reinterpret_cast<I*>(L.gcost) + (size_t)blockIdx.x * G.cells_pad;
         nextb = reinterpret_cast<I*>(L.next) + (size_t)blockIdx.x * G.cells_pad;
         bkt = reinterpret_cast<I*>(L.bkt) + (size_t)blockIdx.x * ((size_t)H * G.bcap);
+        bstamp = reinterpret_cast<I*>(L.bstamp) + (size_t)blockIdx.x * ((size_t)H * G.bcap);
     }
     int* path = L.path + (size_t)blockIdx.x * G.cells_pad;
     const GoalLaunch& P = L.g;
     if (lane < kAstarMaxLevels) { s_seq[lane] = G.bkt_seq[lane]; s_magic[lane] = G.bkt_magic[lane]; }
     __syncwarp();
 
-    for (int blk = blockIdx.x; blk < L.n; blk += gridDim.x) {
+    // agents are handed out dynamically (one atomic per agent): searches differ by orders of magnitude in length, a static
+    // split would leave most warps waiting for the unluckiest one
+    for (;;) {
+        int blk = 0;
+        if (lane == 0) blk = atomicAdd(L.next_agent, 1);
+        blk = __shfl_sync(FULL, blk, 0);
+        if (blk >= L.n) break;
         const int a = L.order ? L.order[L.order_first + blk * L.order_stride] : L.agent_base + blk * L.agent_stride;
         const lscgpu_agent_in& me = P.in[a];
         const F3 pos{me.position[0], me.position[1], me.position[2]};
@@ -228,10 +237,11 @@ __global__ void __launch_bounds__(32, 1) k_goal_astar(GoalAstarLaunch L) {
                     uint4* dst = reinterpret_cast<uint4*>(cellb);
                     for (size_t k = lane; k < G.cells_pad / 16; k += 32) dst[k] = src[k];
                 }
-                for (int r = lane; r < H; r += 32) { r_head[r] = -1; r_count[r] = 0; r_level[r] = 0; }
+                for (int r = lane; r < H; r += 32) { r_head[r] = -1; r_count[r] = 0; r_level[r] = 0; r_stamp[r] = 0; }
                 __syncwarp();
                 AstarCtx<I> c;
                 c.cell = cellb; c.g = gbuf; c.next = nextb; c.bkt = bkt; c.bcap = G.bcap;
+                c.bstamp = bstamp; c.stamp = r_stamp;
                 c.head = r_head; c.count = r_count; c.level = r_level; c.min_cell = r_min_cell; c.min_g = r_min_g; c.min_f = r_min_f;
                 c.H = H; c.W = W; c.A = A;
                 c.bkt_seq = s_seq;
@@ -297,10 +307,12 @@ __global__ void __launch_bounds__(32, 1) k_goal_astar(GoalAstarLaunch L) {
                     ci = __shfl_sync(FULL, ci, 0);
                     __syncwarp();
                     // (2) deleteMin's re-scan of the row, by the warp: the open cells of grid row ci ARE the container's
-                    // content; its iteration order only matters when the minimum (F, g) occurs more than once
+                    // content; among the nodes with the minimal (F, g) the reference takes the LAST in the container's iteration
+                    // order = the one whose bucket has the smallest order stamp (astar_core.cuh); only minimal nodes sharing
+                    // a bucket make lane 0 walk that bucket's run
                     {
                         const int row_cells = W * A, row_base = ci * row_cells, di = gc[0] - ci;
-                        double sf = 0.0; int sg = -1, scell = -1, ties = 0;
+                        double sf = 0.0; int sg = -1, scell = -1; unsigned sst = 0; bool have_st = false, dup = false;
                         for (int o = lane; o < row_cells; o += 32) {
                             const int id = row_base + o;
                             if ((cellb[id] & kCellStateMask) != kCellOpen) continue;
@@ -308,8 +320,13 @@ __global__ void __launch_bounds__(32, 1) k_goal_astar(GoalAstarLaunch L) {
                             const int pj = (int)astar_div((unsigned)o, (unsigned)A, c.magic_a), pz = o - pj * A;
                             const int dj = gc[1] - pj, dz = gc[2] - pz;
                             const double pf = (double)pg + astar_h(c, di * di + dj * dj + dz * dz);
-                            if (scell < 0 || pf < sf || (pf == sf && pg > sg)) { sf = pf; sg = pg; scell = id; ties = 1; }
-                            else if (pf == sf && pg == sg) ties++;
+                            if (scell < 0 || pf < sf || (pf == sf && pg > sg)) { sf = pf; sg = pg; scell = id; have_st = false; dup = false; }
+                            else if (pf == sf && pg == sg) {
+                                if (!have_st) { sst = astar_stamp_of(c, ci, scell); have_st = true; }
+                                const unsigned st = astar_stamp_of(c, ci, id);
+                                if (st < sst) { scell = id; sst = st; dup = false; }
+                                else if (st == sst) dup = true;
+                            }
                         }
                         const unsigned hi = scell >= 0 ? (unsigned)__double2hiint(sf) : NOKEY, lo = (unsigned)__double2loint(sf);
                         const unsigned mhi = __reduce_min_sync(FULL, hi);
@@ -319,12 +336,23 @@ __global__ void __launch_bounds__(32, 1) k_goal_astar(GoalAstarLaunch L) {
                             cand = cand && lo == mlo;
                             const int mg = __reduce_max_sync(FULL, cand ? sg : -1);
                             cand = cand && sg == mg;
-                            const int n_ties = __reduce_add_sync(FULL, cand ? ties : 0);
-                            const int mcell = __reduce_max_sync(FULL, cand ? scell : -1);
+                            int mcell;
+                            const unsigned cmask = __ballot_sync(FULL, cand);
+                            bool walk = false;
+                            if (__popc(cmask) == 1 && !__shfl_sync(FULL, (int)dup, __ffs(cmask) - 1)) {
+                                mcell = __shfl_sync(FULL, scell, __ffs(cmask) - 1);
+                            } else {
+                                if (cand && !have_st) sst = astar_stamp_of(c, ci, scell);
+                                const unsigned ms = __reduce_min_sync(FULL, cand ? sst : NOKEY);
+                                cand = cand && sst == ms;
+                                const unsigned m2 = __ballot_sync(FULL, cand);
+                                walk = __popc(m2) > 1 || __shfl_sync(FULL, (int)dup, __ffs(m2) - 1) != 0;
+                                mcell = __shfl_sync(FULL, scell, __ffs(m2) - 1);
+                            }
                             if (lane == 0) {
                                 const double mf = __hiloint2double((int)mhi, (int)mlo);
-                                if (n_ties == 1) { r_min_cell[ci] = mcell; r_min_f[ci] = mf; r_min_g[ci] = mg; }
-                                else astar_rescan(c, ci, mg, mf);
+                                if (walk) mcell = astar_last_in_bucket(c, ci, mcell, mf, mg);
+                                r_min_cell[ci] = mcell; r_min_f[ci] = mf; r_min_g[ci] = mg;
                             }
                         }
 #ifdef LSCGPU_GOAL_TIMERS

@@ -29,6 +29,9 @@ static int devcore_astar_t(const int* dim, const unsigned char* grid, const int*
     std::vector<int> head(H, -1), count(H, 0), level(H, 0), min_cell(H, -1), min_g(H, 0);
     std::vector<double> min_f(H, 0.0);
     c.cell = cell.data(); c.g = g.data(); c.next = next.data(); c.bkt = bkt.data();
+    std::vector<I> bstamp((size_t)H * c.bcap, (I)999);
+    std::vector<int> stamp(H, 0);
+    c.bstamp = bstamp.data(); c.stamp = stamp.data();
     c.head = head.data(); c.count = count.data(); c.level = level.data(); c.min_cell = min_cell.data(); c.min_g = min_g.data();
     c.min_f = min_f.data();
     c.gi = goal[0]; c.gj = goal[1]; c.gz = goal[2];
@@ -45,10 +48,18 @@ static int devcore_astar_t(const int* dim, const unsigned char* grid, const int*
     }
     astar_begin(c, start[0], start[1], start[2]);
     int cur = -1, found = 0;
+    long long stamp_mismatch = 0;
     while (c.open_size != 0) {
         cur = astar_find_min(c);
-        if (astar_expand(c, cur)) { found = 1; break; }
+        // the expansion in its three pieces; the list-walk re-scan is the statement of the reference, the stamp-based one
+        // (what the kernel's warp does) must name the same node every time
+        int ci, cj, cz;
+        const int cur_g = astar_close(c, cur, ci, cj, cz);
+        astar_rescan(c, ci);
+        if (count[ci] > 0 && astar_rescan_by_stamp(c, ci) != min_cell[ci]) stamp_mismatch++;
+        if (astar_open_neighbours(c, ci, cj, cz, cur_g)) { found = 1; break; }
     }
+    if (stamp_mismatch) return -2;
     if (expansions) *expansions = c.expansions;
     if (!found) return 0;
     const int n = (int)g[cur] + 1;
