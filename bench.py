@@ -369,6 +369,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = n * args.steps / float(e2e_s.item())
+    e2e_device_ms = float(eng.step_stats()["ms_steps"])      # device time of the last end-to-end step (no L2 flush before it)
     clk = clocks.stop()
     e2e_matches_resident = bool(np.array_equal(h_out["traj"], out_mid["traj"]))
 
@@ -479,7 +480,10 @@ def run_ours(args):
                                   else "k_goal_plan = priority rule + clip (no octomap)")) if GOAL_MODES[args.goal_mode]
                               else "fixed to the mission goals (goal planning is outside the path, SURVEY.md §8f)")},
             "e2e": {"value": e2e_value, "unit": "agent-replans/s", "h2d_bytes_per_step": n * A.AGENT_IN.itemsize,
-                    "d2h_bytes_per_step": n * A.AGENT_OUT.itemsize, "same_trajectories_as_resident_pass": e2e_matches_resident},
+                    "d2h_bytes_per_step": n * A.AGENT_OUT.itemsize, "same_trajectories_as_resident_pass": e2e_matches_resident,
+                    "ms_per_step": 1e3 * float(e2e_s.item()) / args.steps, "device_ms_last_step": e2e_device_ms,
+                    "results": "written by the planning blocks straight into the pinned result array (no copy after the step)"
+                               if world == 1 else "one device-to-host copy after the step"},
             "gpu_launches": int(launches.item()),
             "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]},
             "roofline": roofline, "path_roofline": path_roofline,
