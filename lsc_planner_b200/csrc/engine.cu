@@ -172,7 +172,7 @@ struct lscgpu_engine {
     float* d_reach = nullptr;        // [N][5]
     StepCounters* d_counters = nullptr;
     Scratch scratch;                 // operator-level entries and setters
-    std::vector<char> host_buf;      // results of an operator-level call, one D2H copy
+    char* h_stage = nullptr; size_t stage_bytes = 0;     // pinned host staging of lscgpu_qp_solve_batch (inputs | results)
     // map
     bool have_map = false;
     DistMapDev dm{};
@@ -271,6 +271,7 @@ extern "C" void lscgpu_destroy(lscgpu_engine* e) {
     cudaFree(e->d_epoch); cudaFree(e->d_sfc_ready); cudaFree(e->d_sfc_box); cudaFree(e->d_sfc_ok);
     cudaFree(e->d_reset_ever); cudaFree(e->d_any_reset);
     cudaFree(e->d_host_out); if (e->h_host_out) cudaFreeHost(e->h_host_out);
+    if (e->h_stage) cudaFreeHost(e->h_stage);
     cudaFree(e->d_goal_axis); cudaFree(e->d_goal_static); cudaFree(e->d_goal_cell); cudaFree(e->d_goal_g); cudaFree(e->d_goal_next);
     cudaFree(e->d_goal_bkt); cudaFree(e->d_goal_bstamp); cudaFree(e->d_goal_path); cudaFree(e->d_goal_expansions); cudaFree(e->d_goal_ticket);
     if (e->ev_sfc) cudaEventDestroy(e->ev_sfc);
@@ -1401,31 +1402,46 @@ static int qp_solve_batch_impl(lscgpu_engine* e, int nb, const int32_t* agent_in
     const size_t o_iters = cv.off; cv.off += sizeof(int) * nb;
     const size_t out_bytes = cv.off;
     cv.off = (cv.off + 255) & ~(size_t)255;
-    const size_t o_ai = cv.take<int>(nb), o_off = cv.take<int>(nb + 1), o_ts = cv.take<int>(nb), o_kc = cv.take<int>(nb);
+    // inputs next, contiguous as well: packed into one pinned staging buffer on the host and uploaded by ONE copy (a
+    // batch-of-one TrajOptimizer::solve would otherwise pay seven pageable copies of a few bytes each); the kept counters
+    // travel with them as zeros
+    const bool slack = obs_slack != nullptr && total_obs > 0;
+    const size_t in_begin = cv.off;
+    const size_t o_ai = cv.take<int>(nb), o_off = cv.take<int>(nb + 1), o_kc = cv.take<int>(nb);
     const size_t o_state = cv.take<double>((size_t)nb * 9), o_goal = cv.take<double>((size_t)nb * 3);
     const size_t o_sfc = cv.take<float>((size_t)nb * 30);
     const size_t o_n = cv.take<float>(pp * 3), o_p = cv.take<float>(pp * 18), o_d = cv.take<double>(pp * 6);
+    const size_t o_slack = cv.take<unsigned char>(std::max(total_obs, 1));
+    const size_t in_bytes = cv.off - in_begin;
+    const size_t o_ts = cv.take<int>(nb);
     const size_t o_rows = cv.take<RowRec>(pp), o_kept = cv.take<int>(pp), o_safe = cv.take<double>(pp);
-    const bool slack = obs_slack != nullptr && total_obs > 0;
-    const size_t o_slack = cv.take<unsigned char>(std::max(total_obs, 1)), o_eps = cv.take<double>(pp);
+    const size_t o_eps = cv.take<double>(pp);
     CU(e->scratch.reserve(cv.off));
+    if (e->stage_bytes < in_bytes + out_bytes) {
+        if (e->h_stage) cudaFreeHost(e->h_stage);
+        e->h_stage = nullptr; e->stage_bytes = 0;
+        const size_t want = std::max<size_t>(2 * (in_bytes + out_bytes), 1 << 16);
+        CU(cudaHostAlloc((void**)&e->h_stage, want, cudaHostAllocDefault));
+        e->stage_bytes = want;
+    }
     char* base = (char*)e->scratch.p;
     auto at = [&](size_t o) { return base + o; };
-    CU(cudaMemcpyAsync(at(o_ai), agent_index, sizeof(int) * nb, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(at(o_off), obs_offset, sizeof(int) * (nb + 1), cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(at(o_state), state, sizeof(double) * 9 * nb, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(at(o_goal), goal, sizeof(double) * 3 * nb, cudaMemcpyHostToDevice, s));
-    if (sfc) CU(cudaMemcpyAsync(at(o_sfc), sfc, sizeof(float) * 30 * nb, cudaMemcpyHostToDevice, s));
-    CU(cudaMemsetAsync(at(o_kc), 0, sizeof(int) * nb, s));
+    char* hin = e->h_stage;                           // mirrors [in_begin, in_begin + in_bytes) of the device scratch
+    auto hat = [&](size_t o) { return hin + (o - in_begin); };
+    std::memcpy(hat(o_ai), agent_index, sizeof(int) * nb);
+    std::memcpy(hat(o_off), obs_offset, sizeof(int) * (nb + 1));
+    std::memset(hat(o_kc), 0, sizeof(int) * nb);
+    std::memcpy(hat(o_state), state, sizeof(double) * 9 * nb);
+    std::memcpy(hat(o_goal), goal, sizeof(double) * 3 * nb);
+    if (sfc) std::memcpy(hat(o_sfc), sfc, sizeof(float) * 30 * nb);
     if (pairs) {
-        CU(cudaMemcpyAsync(at(o_n), lsc_normal, sizeof(float) * pairs * 3, cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(at(o_p), lsc_point, sizeof(float) * pairs * 18, cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(at(o_d), lsc_d, sizeof(double) * pairs * 6, cudaMemcpyHostToDevice, s));
+        std::memcpy(hat(o_n), lsc_normal, sizeof(float) * pairs * 3);
+        std::memcpy(hat(o_p), lsc_point, sizeof(float) * pairs * 18);
+        std::memcpy(hat(o_d), lsc_d, sizeof(double) * pairs * 6);
     }
-    if (slack) {
-        CU(cudaMemcpyAsync(at(o_slack), obs_slack, (size_t)total_obs, cudaMemcpyHostToDevice, s));
-        CU(cudaMemsetAsync(at(o_eps), 0, sizeof(double) * pairs, s));
-    }
+    if (slack) std::memcpy(hat(o_slack), obs_slack, (size_t)total_obs);
+    CU(cudaMemcpyAsync(at(in_begin), hin, in_bytes, cudaMemcpyHostToDevice, s));
+    if (slack) CU(cudaMemsetAsync(at(o_eps), 0, sizeof(double) * pairs, s));
     launch_rows_from_lsc(nb, (int*)at(o_off), total_obs, (float*)at(o_n), (float*)at(o_p), (double*)at(o_d), (RowRec*)at(o_rows),
                          (int*)at(o_kept), (int*)at(o_kc), (double*)at(o_safe), s, slack ? (unsigned char*)at(o_slack) : nullptr);
     launch_terminal_segments(nb, (double*)at(o_state), (double*)at(o_goal), (int*)at(o_ai), e->d_consts, e->prm.dt, (int*)at(o_ts), s);
@@ -1440,18 +1456,17 @@ static int qp_solve_batch_impl(lscgpu_engine* e, int nb, const int32_t* agent_in
     ql.slack = slack ? 1 : 0; ql.slack_w = slack_w; ql.eps_out = slack ? (double*)at(o_eps) : nullptr;
     launch_qp_batch(ql, s);
     CU(cudaGetLastError());
-    std::vector<char>& hb = e->host_buf;
-    hb.resize(out_bytes);
-    CU(cudaMemcpyAsync(hb.data(), base, out_bytes, cudaMemcpyDeviceToHost, s));
+    char* hb = e->h_stage + in_bytes;                 // results land in the pinned staging buffer, behind the inputs
+    CU(cudaMemcpyAsync(hb, base, out_bytes, cudaMemcpyDeviceToHost, s));
     if (eps) {
         if (slack) CU(cudaMemcpyAsync(eps, at(o_eps), sizeof(double) * pairs, cudaMemcpyDeviceToHost, s));
         else std::memset(eps, 0, sizeof(double) * pairs);
     }
     CU(cudaStreamSynchronize(s));
-    std::memcpy(x, hb.data() + o_x, sizeof(double) * kNv * nb);
-    std::memcpy(cost, hb.data() + o_cost, sizeof(double) * nb);
-    std::memcpy(status, hb.data() + o_status, sizeof(int) * nb);
-    std::memcpy(iterations, hb.data() + o_iters, sizeof(int) * nb);
+    std::memcpy(x, hb + o_x, sizeof(double) * kNv * nb);
+    std::memcpy(cost, hb + o_cost, sizeof(double) * nb);
+    std::memcpy(status, hb + o_status, sizeof(int) * nb);
+    std::memcpy(iterations, hb + o_iters, sizeof(int) * nb);
     for (int b = 0; b < nb; b++) status[b] &= 0xff;       // bit 8: more slack variables needed than the kernel holds (reported as MAXITER)
     return LSCGPU_OK;
 }
