@@ -359,7 +359,8 @@ __global__ void __launch_bounds__(32, 1) k_goal_astar(GoalAstarLaunch L) {
                         if (lane == 0) { const long long t = clock64(); c.tsec[2] += t - c.tlast; c.tlast = t; }
 #endif
                     }
-                    // (3) goal test, neighbours
+                    // (3) goal test, neighbours (lane 0 rewrites what the other lanes have just read: order the two)
+                    __syncwarp();
                     if (lane == 0) found = astar_open_neighbours(c, ci, cj, cz, cur_g);
 #ifdef LSCGPU_GOAL_TIMERS
                     c.tlast = clock64();
