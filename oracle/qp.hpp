@@ -16,6 +16,7 @@
 // (iii) KKT residuals. The QP is strictly convex on the equality manifold, so the minimiser is
 // unique and the comparison is on coefficients as well as objective/residuals.
 #pragma once
+#include <cstdlib>
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -311,6 +312,9 @@ inline bool row_get(const QpTables& T, const QpProblem& p, int id, RowView& r) {
 // threshold, extended by a full sweep whenever nothing in it is violated. Default: every row priced every iteration.
 inline double g_tier_threshold = INFINITY;
 inline int g_trace_agent = -1;            // debugging: >= 0 prints every pivot of the solve (stderr)
+// warm-start experiment knob: how often candidates with a negative multiplier are removed and the rest re-tried before the
+// solve starts cold (environment ORC_WARM_ATTEMPTS; the kernel's rule is 2)
+inline int g_warm_attempts = std::getenv("ORC_WARM_ATTEMPTS") ? std::atoi(std::getenv("ORC_WARM_ATTEMPTS")) : 2;
 
 // Goldfarb-Idnani dual active set on  min |v|^2  s.t.  n_j . v >= -slack0_j   (x = x0 + G v)
 // Optional warm start (guess / n_guess: canonical row ids, e.g. the previous step's active set shifted by one segment):
@@ -396,7 +400,7 @@ inline void qp_solve(const QpTables& T, const QpProblem& p, QpResult& out, int m
     out.warm_accepted = 0;
     if (guess && n_guess > 0) {
         std::vector<int> cand(guess, guess + n_guess);
-        for (int attempt = 0; attempt < 2 && !cand.empty(); attempt++) {
+        for (int attempt = 0; attempt < g_warm_attempts && !cand.empty(); attempt++) {
             // factorise the candidate rows: J, R as after adding them one by one (no steps)
             std::fill(J.begin(), J.end(), 0.0); std::fill(R.begin(), R.end(), 0.0);
             for (int i = 0; i < n; i++) J[i * n + i] = 1.0;
@@ -449,7 +453,7 @@ inline void qp_solve(const QpTables& T, const QpProblem& p, QpResult& out, int m
             std::vector<int> keep;
             for (int k = 0; k < qq; k++) if (lm[k] >= -1e-12) keep.push_back(ids[k]);
             cand.swap(keep);
-            if (attempt == 1 || cand.empty()) {                  // cold start
+            if (attempt == g_warm_attempts - 1 || cand.empty()) {                  // cold start
                 std::fill(J.begin(), J.end(), 0.0); std::fill(R.begin(), R.end(), 0.0);
                 for (int i = 0; i < n; i++) J[i * n + i] = 1.0;
             }

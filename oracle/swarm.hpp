@@ -209,6 +209,7 @@ struct Swarm {
             for (int k = 0; k < prev_n_act[a]; k++) {
                 const int id = prev_act[(size_t)a * QRED + k];
                 if (warm_start & 1) { if (id < 450) guess[ng++] = id; }       // same rows: the plan keeps its shape relative to the horizon
+                if ((warm_start & 4) && id >= 450) guess[ng++] = id;           // ... and the same LSC rows (neighbour, segment, point)
                 if (warm_start & 2) {
                     const int sh = shifted_row_id(id);
                     if (sh >= 0) guess[ng++] = sh;
