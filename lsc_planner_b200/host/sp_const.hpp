@@ -7,6 +7,7 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "mini_json.hpp"
@@ -107,10 +108,16 @@ struct Param {
     double grid_resolution = 0.3, grid_margin = 0.1;            // src/param.cpp:93-94
     // not in the reference: where prior_based goal planning with an octomap runs. device: on the GPU inside the step
     // (k_goal_astar, one warp per agent); host: grid_based_planner.hpp on the host threads before the step (same goals bit
-    // for bit). auto (default): the device from 256 agents on — one A* is a sequential search, a host core runs it ~10x faster
-    // than a GPU lane, the GPU wins by running every agent's search at once
+    // for bit). One A* is a sequential search: a host core runs it ~10x faster than a GPU lane, and the GPU step lasts as
+    // long as its longest search (~40 ms in the shipped 10 m world, whatever the swarm size), while the host needs
+    // ~0.5 ms of one core per agent (measured, profiles/r02e_goal_crossover.txt: 16 threads beat the device up to 512
+    // agents). auto (default): the device only when the swarm is large for the host cores at hand (>= 80 agents per thread,
+    // e.g. several ranks sharing one node's cores).
     int goal_planner = 0;               // 0 auto, 1 device, 2 host
-    bool goalPlannerOnDevice(int n_agents) const { return goal_planner == 1 || (goal_planner == 0 && n_agents >= 256); }
+    bool goalPlannerOnDevice(int n_agents) const {
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        return goal_planner == 1 || (goal_planner == 0 && (unsigned)n_agents >= 80u * hw);
+    }
     double goal_threshold = 0.1, goal_radius = 100.0, priority_dist_threshold = 0.4;
     std::string mission_file_name = "default.json", world_file_name = "default.bt", package_path = ".";
 
