@@ -18,11 +18,9 @@ ms = {"quadrotors": {"crazyflie": {"max_vel": [1.0, 1.0, 1.0], "max_acc": [2.0, 
 json.dump(ms, open(f"/tmp/rf{n}.json", "w"))
 PY
   for PL in host device; do
-    T0=$(date +%s.%N)
     lsc_planner_b200/host/lsc_sim mission=/tmp/rf$N.json world/file_name=$BT mode/goal=prior_based goal/planner=$PL \
         multisim/max_planner_iteration=31 multisim/save_result=false > /tmp/sim_${N}_${PL}.log 2>&1
-    T1=$(date +%s.%N)
-    echo "N=$N goal/planner=$PL: $(grep -E 'planning time per agent|goal planning time' /tmp/sim_${N}_${PL}.log | tr '\n' ' ') wall $(echo "$T1 - $T0" | bc) s" >> $OUT
+    echo "N=$N goal/planner=$PL: $(grep -E 'planning time per agent|goal planning time' /tmp/sim_${N}_${PL}.log | tr '\n' ' ')" >> $OUT
   done
 done
 cat $OUT
