@@ -65,6 +65,8 @@ struct AstarCtx {
     // `min` node per row)
     int *head, *count, *level, *min_cell, *min_g;
     double* min_f;
+    int *jlo, *jhi;         // optional (null: off): range of j in which the row has ever had an open node — deleteMin's re-scan
+                            // of the row's cells stops there
     int H, W, A;
     const int* bkt_seq;     // bucket counts the row containers move through: 1, 13, 29, 59, ... (kAstarMaxLevels entries)
     // Optional accelerators (0 / null: plain division, sqrt). Divisions by A, W and the bucket counts as one multiply-high
@@ -109,9 +111,12 @@ template <typename I> ASTAR_HD unsigned astar_key(const AstarCtx<I>& c, int cell
     return (unsigned)(c.H * c.W * z + c.W * i + j);
 }
 // key % (bucket count of level lvl)
-template <typename I> ASTAR_HD unsigned astar_bucket(const AstarCtx<I>& c, int cell, int lvl) {
-    const unsigned key = astar_key(c, cell), n = (unsigned)c.bkt_seq[lvl];
+template <typename I> ASTAR_HD unsigned astar_bucket_of_key(const AstarCtx<I>& c, unsigned key, int lvl) {
+    const unsigned n = (unsigned)c.bkt_seq[lvl];
     return key - astar_div(key, n, c.bkt_magic ? c.bkt_magic[lvl] : 0u) * n;
+}
+template <typename I> ASTAR_HD unsigned astar_bucket(const AstarCtx<I>& c, int cell, int lvl) {
+    return astar_bucket_of_key(c, astar_key(c, cell), lvl);
 }
 template <typename I> ASTAR_HD double astar_h(const AstarCtx<I>& c, int d2) { return c.sqrt_tab ? c.sqrt_tab[d2] : sqrt((double)d2); }
 template <typename I> ASTAR_HD double astar_heuristic(const AstarCtx<I>& c, int i, int j, int z) {
@@ -152,7 +157,8 @@ template <typename I> ASTAR_HD void astar_rehash(AstarCtx<I>& c, int r, int lvl)
     c.head[r] = head;
 }
 
-template <typename I> ASTAR_HD void astar_insert(AstarCtx<I>& c, int r, int nd) {
+// (j, z): the node's coordinates inside row r — the caller knows them, so the key needs no division
+template <typename I> ASTAR_HD void astar_insert(AstarCtx<I>& c, int r, int nd, int j, int z) {
     constexpr I kEnd = AstarCtx<I>::kEnd, kNone = AstarCtx<I>::kNone;
     // _Prime_rehash_policy::_M_need_rehash with max_load_factor 1: grow when the new element count exceeds the bucket
     // count (the empty container has one bucket and always grows)
@@ -164,9 +170,10 @@ template <typename I> ASTAR_HD void astar_insert(AstarCtx<I>& c, int r, int nd) 
     }
     const int cl = c.level[r];
     I* bk = c.bkt + (size_t)r * c.bcap;
-    const unsigned b = astar_bucket(c, nd, cl);
+    const unsigned b = astar_bucket_of_key(c, (unsigned)(c.H * c.W * z + c.W * r + j), cl);
     const I at = bk[b];
     const int old = c.head[r];
+    if (c.jlo) { if (j < c.jlo[r]) c.jlo[r] = j; if (j > c.jhi[r]) c.jhi[r] = j; }
     if (at == kEnd) {
         c.next[nd] = old < 0 ? kEnd : (I)old; c.head[r] = nd;
     } else if (at != kNone) {
@@ -180,11 +187,11 @@ template <typename I> ASTAR_HD void astar_insert(AstarCtx<I>& c, int r, int nd) 
     c.count[r] = cnt + 1;
 }
 
-template <typename I> ASTAR_HD void astar_erase(AstarCtx<I>& c, int r, int nd) {
+template <typename I> ASTAR_HD void astar_erase(AstarCtx<I>& c, int r, int nd, int j, int z) {
     constexpr I kEnd = AstarCtx<I>::kEnd, kNone = AstarCtx<I>::kNone;
     const int cl = c.level[r];
     I* bk = c.bkt + (size_t)r * c.bcap;
-    const unsigned b = astar_bucket(c, nd, cl);
+    const unsigned b = astar_bucket_of_key(c, (unsigned)(c.H * c.W * z + c.W * r + j), cl);
     const I first_prev = bk[b];
     I prev = first_prev;                                    // kEnd: "before the list head"
     for (int p = prev == kEnd ? c.head[r] : (int)c.next[prev]; p != nd; p = (int)c.next[p]) prev = (I)p;
@@ -203,12 +210,14 @@ template <typename I> ASTAR_HD void astar_erase(AstarCtx<I>& c, int r, int nd) {
     c.count[r]--;
 }
 
-// isearch.cpp:244-284 (addOpen)
-template <typename I> ASTAR_HD void astar_add_open(AstarCtx<I>& c, int i, int cell, double f, int g, int dir) {
+// isearch.cpp:244-284 (addOpen); (j, z): the cell's coordinates inside row i
+template <typename I> ASTAR_HD void astar_add_open(AstarCtx<I>& c, int i, int j, int z, int cell, double f, int g, int dir) {
     bool inserted = false;
     const uint8_t st = c.cell[cell];
     if ((st & kCellStateMask) == kCellOpen) {
-        if (f < astar_f(c, cell, (int)c.g[cell])) {
+        // the reference compares F = g + h with the stored F of the same cell: the same h on both sides and integer g's
+        // at least one apart (far above an ulp of the sums), so the comparison of the doubles is the comparison of the g's
+        if (g < (int)c.g[cell]) {
             c.g[cell] = (I)g;
             c.cell[cell] = (uint8_t)((st & ~(7 << kCellDirShift)) | (dir << kCellDirShift));
             inserted = true;
@@ -216,13 +225,13 @@ template <typename I> ASTAR_HD void astar_add_open(AstarCtx<I>& c, int i, int ce
     } else {
         c.g[cell] = (I)g;
         c.cell[cell] = (uint8_t)((st & kCellOccupied) | kCellOpen | (dir << kCellDirShift));
-        astar_insert(c, i, cell);
+        astar_insert(c, i, cell, j, z);
         inserted = true;
         c.open_size++;
     }
     if (c.count[i] == 1) {
-        const int gg = (int)c.g[cell];
-        c.min_cell[i] = cell; c.min_f[i] = inserted ? f : astar_f(c, cell, gg); c.min_g[i] = gg;
+        // the row's only node: when it was not touched just now it is the cached minimum already
+        if (inserted) { c.min_cell[i] = cell; c.min_f[i] = f; c.min_g[i] = g; }
     } else if (inserted && f <= c.min_f[i]) {
         if (f == c.min_f[i]) { if (g >= c.min_g[i]) { c.min_cell[i] = cell; c.min_g[i] = g; } }
         else { c.min_cell[i] = cell; c.min_f[i] = f; c.min_g[i] = g; }
@@ -249,7 +258,7 @@ template <typename I> ASTAR_HD int astar_close(AstarCtx<I>& c, int cur, int& ci,
     c.expansions++;
     const int cur_g = (int)c.g[cur];
     ASTAR_TICK(0);
-    astar_erase(c, ci, cur);
+    astar_erase(c, ci, cur, cj, cz);
     ASTAR_TICK(1);
     return cur_g;
 }
@@ -303,7 +312,8 @@ template <typename I> ASTAR_HD int astar_last_in_bucket(const AstarCtx<I>& c, in
 template <typename I> ASTAR_HD int astar_rescan_by_stamp(const AstarCtx<I>& c, int ci) {
     const int row_cells = c.W * c.A, base = ci * row_cells, di = c.gi - ci;
     int best = -1, bg = 0; double bf = 0; unsigned bs = 0; bool dup = false;
-    for (int o = 0; o < row_cells; o++) {
+    const int o_lo = c.jlo ? c.jlo[ci] * c.A : 0, o_hi = c.jlo ? (c.jhi[ci] + 1) * c.A : row_cells;
+    for (int o = o_lo; o < o_hi; o++) {
         const int id = base + o;
         if ((c.cell[id] & kCellStateMask) != kCellOpen) continue;
         const int pg = (int)c.g[id];
@@ -333,7 +343,7 @@ template <typename I> ASTAR_HD int astar_open_neighbours(AstarCtx<I>& c, int ci,
         const int nc = astar_cell(c, ni, nj, nz);
         const uint8_t st = c.cell[nc];
         if ((st & kCellOccupied) || (st & kCellStateMask) == kCellClosed) continue;
-        astar_add_open(c, ni, nc, (double)g + astar_heuristic(c, ni, nj, nz), g, s);
+        astar_add_open(c, ni, nj, nz, nc, (double)g + astar_heuristic(c, ni, nj, nz), g, s);
     }
     ASTAR_TICK(3);
     return 0;
@@ -358,7 +368,7 @@ template <typename I> ASTAR_HD int astar_parent(const AstarCtx<I>& c, int cell) 
 template <typename I> ASTAR_HD void astar_begin(AstarCtx<I>& c, int si, int sj, int sz) {
     c.expansions = 0; c.open_size = 0;
     const int s = astar_cell(c, si, sj, sz);
-    astar_add_open(c, si, s, astar_heuristic(c, si, sj, sz), 0, kCellNoParent);
+    astar_add_open(c, si, sj, sz, s, astar_heuristic(c, si, sj, sz), 0, kCellNoParent);
     c.open_size = 1;
 }
 

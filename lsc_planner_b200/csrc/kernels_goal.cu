@@ -83,9 +83,9 @@ __device__ bool cast_ray(const DistMapDev& dm, double inv_res, double res, F3 a,
     }
 }
 
-// dynamic shared memory: row table [H] (min_f, head, count, level, min_cell, min_g, stamp), then — shared variant — the search
+// dynamic shared memory: row table [H] (min_f, head, count, level, min_cell, min_g, stamp, jlo, jhi), then — shared variant — the search
 // state of the warp
-__host__ __device__ inline size_t goal_rows_bytes(int H) { return ((size_t)H * (sizeof(double) + 6 * sizeof(int)) + 15) / 16 * 16; }
+__host__ __device__ inline size_t goal_rows_bytes(int H) { return ((size_t)H * (sizeof(double) + 8 * sizeof(int)) + 15) / 16 * 16; }
 template <typename I>
 __host__ __device__ inline size_t goal_state_bytes(const GoalGridDev& g) {
     return g.cells_pad * (1 + 2 * sizeof(I)) + 2 * (((size_t)g.dim[0] * g.bcap * sizeof(I) + 15) / 16 * 16);     // buckets + their order stamps
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(32, 1) k_goal_astar(GoalAstarLaunch L) {
     double* r_min_f = reinterpret_cast<double*>(smem);
     int* r_head = reinterpret_cast<int*>(r_min_f + H);
     int* r_count = r_head + H; int* r_level = r_count + H; int* r_min_cell = r_level + H; int* r_min_g = r_min_cell + H;
-    int* r_stamp = r_min_g + H;
+    int* r_stamp = r_min_g + H; int* r_jlo = r_stamp + H; int* r_jhi = r_jlo + H;
     uint8_t* cellb; I* gbuf; I* nextb; I* bkt; I* bstamp;
     double* sqrt_tab = nullptr;
     if (kShared) {
@@ -237,11 +237,11 @@ __global__ void __launch_bounds__(32, 1) k_goal_astar(GoalAstarLaunch L) {
                     uint4* dst = reinterpret_cast<uint4*>(cellb);
                     for (size_t k = lane; k < G.cells_pad / 16; k += 32) dst[k] = src[k];
                 }
-                for (int r = lane; r < H; r += 32) { r_head[r] = -1; r_count[r] = 0; r_level[r] = 0; r_stamp[r] = 0; }
+                for (int r = lane; r < H; r += 32) { r_head[r] = -1; r_count[r] = 0; r_level[r] = 0; r_stamp[r] = 0; r_jlo[r] = W; r_jhi[r] = -1; }
                 __syncwarp();
                 AstarCtx<I> c;
                 c.cell = cellb; c.g = gbuf; c.next = nextb; c.bkt = bkt; c.bcap = G.bcap;
-                c.bstamp = bstamp; c.stamp = r_stamp;
+                c.bstamp = bstamp; c.stamp = r_stamp; c.jlo = r_jlo; c.jhi = r_jhi;
                 c.head = r_head; c.count = r_count; c.level = r_level; c.min_cell = r_min_cell; c.min_g = r_min_g; c.min_f = r_min_f;
                 c.H = H; c.W = W; c.A = A;
                 c.bkt_seq = s_seq;
@@ -311,9 +311,11 @@ __global__ void __launch_bounds__(32, 1) k_goal_astar(GoalAstarLaunch L) {
                     // order = the one whose bucket has the smallest order stamp (astar_core.cuh); only minimal nodes sharing
                     // a bucket make lane 0 walk that bucket's run
                     {
-                        const int row_cells = W * A, row_base = ci * row_cells, di = gc[0] - ci;
+                        const int row_base = ci * W * A, di = gc[0] - ci;
+                        // only the span of j in which this row has ever had an open node
+                        const int o_lo = r_jlo[ci] * A, o_hi = (r_jhi[ci] + 1) * A;
                         double sf = 0.0; int sg = -1, scell = -1; unsigned sst = 0; bool have_st = false, dup = false;
-                        for (int o = lane; o < row_cells; o += 32) {
+                        for (int o = o_lo + lane; o < o_hi; o += 32) {
                             const int id = row_base + o;
                             if ((cellb[id] & kCellStateMask) != kCellOpen) continue;
                             const int pg = (int)gbuf[id];

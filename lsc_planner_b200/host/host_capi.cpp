@@ -32,6 +32,8 @@ static int devcore_astar_t(const int* dim, const unsigned char* grid, const int*
     std::vector<I> bstamp((size_t)H * c.bcap, (I)999);
     std::vector<int> stamp(H, 0);
     c.bstamp = bstamp.data(); c.stamp = stamp.data();
+    std::vector<int> jlo(H, W), jhi(H, -1);
+    c.jlo = jlo.data(); c.jhi = jhi.data();
     c.head = head.data(); c.count = count.data(); c.level = level.data(); c.min_cell = min_cell.data(); c.min_g = min_g.data();
     c.min_f = min_f.data();
     c.gi = goal[0]; c.gj = goal[1]; c.gz = goal[2];
