@@ -72,12 +72,13 @@ def _forest_case(case, tmp_path, bt):
     return L.scenarios.random_forest(int(case[len("random"):]), dm["sqdist"], dm["off"], seed=3)
 
 
-@pytest.mark.parametrize("case,steps", [("forest10", 60), ("random64", 30)])
+@pytest.mark.parametrize("case,steps", [("forest10", 60), ("random64", 30), ("random512", 6)])
 def test_device_goal_planning_with_octomap_matches_oracle(case, steps, tmp_path, golden_dir):
     """goal_mode 1 WITH an octomap: k_goal_astar (priority rule, occupancy grid with the higher-priority agents stamped in,
     A* with the reference's hash-order tie-breaking, line-of-sight goal by ray casting, clip) against the oracle's
     goalPlanningWithPriority, teacher-forced. Goals are float32 points compared bit for bit; the A* expansion counts of
-    the whole run are equal too (same searches, not just same goals)."""
+    the whole run are equal too (same searches, not just same goals). random512 is BASELINE config 4's swarm (the dense
+    one: agents walled in by higher-priority neighbours re-plan without them)."""
     import lsc_planner_b200 as L
     bt = os.path.join(golden_dir, "worlds", "simple_forest.bt")
     scn = _forest_case(case, tmp_path, bt)
@@ -91,7 +92,7 @@ def test_device_goal_planning_with_octomap_matches_oracle(case, steps, tmp_path,
         pos, vel, acc = sw.state()
         e.set_sfc(sw.boxes(), np.full(n, 1 if sw.seq == 0 else 0, np.int32))
         e.set_prev_traj(sw.traj(), sw.seq)
-        sw.step()
+        sw.step(0, n, os.cpu_count() or 1)
         out = e.replan(pos, vel, acc, scn.goal)
         expanded += e.step_stats()["astar_expansions"]
         g_o, k_o = sw.goals()
