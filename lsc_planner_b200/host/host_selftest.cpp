@@ -25,6 +25,18 @@ int main(int argc, char** argv) {
     bool threw = false;
     try { p.set("mode/planner", "orca"); } catch (const std::invalid_argument&) { threw = true; }
     CHECK(threw);
+    {   // where prior_based goal planning with an octomap runs (not in the reference): goal/planner=auto|device|host
+        Param g = Param::simulationLaunch();
+        CHECK(!g.goalPlannerOnDevice(10));                        // auto: a small swarm goes to the host threads
+        CHECK(g.goalPlannerOnDevice(80 * 4096));                  // ... a swarm that is large for the host cores does not
+        g.set("goal/planner", "device"); CHECK(g.goalPlannerOnDevice(1));
+        CHECK(toEngineParams(g, ms).goal_mode == 1 && toEngineParams(g, ms).grid_resolution == 0.25);
+        g.set("goal/planner", "host"); CHECK(!g.goalPlannerOnDevice(1000000));
+        CHECK(toEngineParams(g, ms).goal_mode == 0);              // the host computes the goals; the engine takes them as given
+        bool bad = false;
+        try { g.set("goal/planner", "gpu"); } catch (const std::invalid_argument&) { bad = true; }
+        CHECK(bad);
+    }
     const lscgpu_params ep = toEngineParams(Param::simulationLaunch(), ms);
     CHECK(ep.M == 5 && ep.world_min[0] == -10.f && ep.control_input_weight == 0.01);
 
