@@ -251,7 +251,7 @@ static int alloc_gather(lscgpu_engine* e, int n_slots) {
 }
 
 extern "C" const char* lscgpu_last_error(void) { return g_error.c_str(); }
-extern "C" int lscgpu_version(void) { return 200; }
+extern "C" int lscgpu_version(void) { return 210; }     // 2.1: lscgpu_params grew (grid_resolution, grid_margin), lscgpu_step_stats grew (astar_expansions)
 
 extern "C" void lscgpu_destroy(lscgpu_engine* e) {
     if (!e) return;
