@@ -66,3 +66,20 @@ def test_scenarios_are_deterministic():
     assert d.min() > 0.6
     m = lsc_planner_b200.scenarios.load_mission(os.path.join(ROOT, "tests", "golden", "missions", "multi_simple3.json"))
     assert m.n == 3 and m.agents[0].radius == 0.15
+
+
+def test_advance_inputs_is_the_state_hand_over(lib):
+    """lscgpu_advance_inputs (host only, no device needed): in[a].position / velocity / acceleration = out[a].next_*, goals
+    untouched (MultiSyncSimulator::update, src/multi_sync_simulator.cpp:203)."""
+    rng = np.random.default_rng(0)
+    n = 7
+    out = np.zeros(n, A.AGENT_OUT); inp = np.zeros(n, A.AGENT_IN)
+    for f in ("next_position", "next_velocity", "next_acceleration"):
+        out[f] = rng.standard_normal((n, 3)).astype(np.float32)
+    inp["goal"] = rng.standard_normal((n, 3)).astype(np.float32)
+    inp["position"] = 9.0
+    goal = inp["goal"].copy()
+    assert lib.lscgpu_advance_inputs(A.p(out), A.p(inp), n) == 0
+    assert np.array_equal(inp["position"], out["next_position"]) and np.array_equal(inp["velocity"], out["next_velocity"])
+    assert np.array_equal(inp["acceleration"], out["next_acceleration"]) and np.array_equal(inp["goal"], goal)
+    assert lib.lscgpu_advance_inputs(None, A.p(inp), n) == -1          # LSCGPU_ERR_ARG
