@@ -161,6 +161,19 @@ int devcore_bucket_sequence(int row_capacity, int* seq, int max_levels) {
     return n;
 }
 
+// bucket counts a real std::unordered_map<uint32_t, int> of this toolchain moves through while n keys are inserted one by one
+int host_unordered_map_bucket_counts(int n, int* out, int max_out) {
+    std::unordered_map<uint32_t, int> m;
+    int k = 0;
+    size_t last = m.bucket_count();
+    if (k < max_out) out[k++] = (int)last;
+    for (int i = 0; i < n; i++) {
+        m.emplace((uint32_t)i * 2654435761u, i);
+        if (m.bucket_count() != last) { last = m.bucket_count(); if (k < max_out) out[k++] = (int)last; }
+    }
+    return k;
+}
+
 // index_bits 16: the compact layout the kernel keeps in shared memory (grids below 65 534 cells); 32: the global-memory layout
 int devcore_astar(const int* dim, const unsigned char* grid, const int* start, const int* goal, int* path_out, int max_len,
                   long long* expansions, int index_bits) {

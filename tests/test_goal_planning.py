@@ -123,6 +123,19 @@ def test_hash_order_model_matches_unordered_map(host):
         assert host.host_hash_order_check(seed, key_range, ops) == 0, (seed, key_range)
 
 
+def test_bucket_sequence_is_the_containers(host):
+    """The bucket counts the engine records from libstdc++'s rehash policy (goal_bucket_sequence in csrc/engine.cu, same
+    code as devcore_bucket_sequence) are the ones a real std::unordered_map goes through while it grows one element at a
+    time — the device A* sizes and re-threads its row containers by them."""
+    host.devcore_bucket_sequence.argtypes = [C.c_int, i32p, C.c_int]; host.devcore_bucket_sequence.restype = C.c_int
+    host.host_unordered_map_bucket_counts.argtypes = [C.c_int, i32p, C.c_int]; host.host_unordered_map_bucket_counts.restype = C.c_int
+    seq = np.zeros(16, np.int32); real = np.zeros(32, np.int32)
+    n_seq = host.devcore_bucket_sequence(1771, seq, 16)              # the longest row of the 40 m world: 161 x 11 cells
+    n_real = host.host_unordered_map_bucket_counts(int(seq[n_seq - 1]), real, 32)
+    assert seq[0] == 1 and seq[n_seq - 1] >= 1771
+    assert n_real >= n_seq and (real[:n_seq] == seq[:n_seq]).all(), (seq[:n_seq], real[:n_real])
+
+
 def test_astar_properties(host):
     """6-connected unit steps, free cells only, shortest length in an empty grid, goal test ignores the altitude
     (src/Astar-3D/isearch.cpp:74), no path when the goal column is walled in."""
